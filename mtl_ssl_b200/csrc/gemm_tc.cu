@@ -1,0 +1,728 @@
+// tcgen05 / TMEM / TMA implicit-GEMM convolution engine for sm_100a.
+//
+// One persistent, warp-specialised kernel serves the three GEMMs of a
+// convolution layer on NHWC bf16 activations (fp32 accumulate in TMEM):
+//   FPROP  y[NPQ,K]   = im2col(x)[NPQ,RSC] * w[K,RSC]^T       (A K-major, B K-major)
+//   DGRAD  dx[NHW,C]  = im2col^T(dy)[NHW,RSK] * w[K,(RS)C]    (A K-major, B MN-major)
+//   WGRAD  dw[K,RSC] += dy[NPQ,K]^T * im2col(x)[NPQ,RSC]      (A MN-major, B MN-major, split-K)
+// The reference delegates these to cuDNN through slim.conv2d
+// (/root/reference/slim/nets/resnet_v1.py:107-126, resnet_utils.py:77-122); there is no
+// reference kernel to mirror, so the design below is new.
+//
+// Data path: weight / plain-matrix operands arrive by TMA (cp.async.bulk.tensor,
+// 128-byte swizzle) issued by one producer thread; im2col operands (3x3, strided,
+// padded, or transposed gathers) are staged into the same swizzled shared-memory
+// layout by four gather warps with 16-byte cp.async + zero fill.  One thread issues
+// tcgen05.mma (M=128, N=BN, K=16) into a double-buffered TMEM accumulator; four
+// epilogue warps drain it with tcgen05.ld and apply bias / residual / ReLU / mask
+// (FPROP, DGRAD) or a scaled fp32 red.global.add (WGRAD).
+#include "common.cuh"
+#include <cuda.h>
+#include <string.h>
+
+namespace tc {
+
+constexpr int BM = 128;            // rows per tile (UMMA M)
+constexpr int BK = 64;             // bf16 per K chunk (= one 128 B swizzle row)
+constexpr int A_STAGE_BYTES = BM * 128;
+constexpr int NUM_GATHER_THREADS = 128;
+
+enum { FPROP = 0, DGRAD = 1, WGRAD = 2 };
+
+struct Params {
+  int M, N;                  // GEMM output rows / cols
+  int k_iters;               // total K iterations (taps*cpt, or pixel blocks for WGRAD)
+  int taps, cpt;             // filter taps and 64-wide channel chunks per tap
+  int tiles_m, tiles_n, splits;
+  // gather geometry (operand staged by the gather warps)
+  const bf16* gsrc;          // NHWC tensor being gathered
+  int gH, gW, gC;            // its spatial dims and channel count (row pitch)
+  int oH, oW;                // row-space spatial dims: row -> (n, oh, ow)
+  int rows;                  // number of valid rows in row space
+  int S, stride, pad_h, pad_w, dil, transposed;
+  int ntot;                  // DGRAD: Cin (columns per tap of w); WGRAD: Cin
+  // epilogue
+  void* out; long long ldo; int out_fp32;
+  const float* bias;         // per output column (FPROP/DGRAD) or nullptr
+  const float* rowscale;     // WGRAD: per output row scale or nullptr
+  const void* res; long long ldr; int res_fp32;
+  const bf16* mask; long long ldm;
+  int relu;
+  float alpha;
+};
+
+// ----------------------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done;
+}
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// Bounded wait: a protocol bug must kill the kernel (trap) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  uint64_t t0 = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 0x3fffu) == 0) {
+      uint64_t now = globaltimer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ull) {
+        printf("gemm_tc: mbarrier wait timeout (block %d thread %d bar %u parity %u)\n",
+               blockIdx.x, threadIdx.x, bar, parity);
+        __trap();
+      }
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
+                                            int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src),
+               "r"(src_bytes)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tcgen05_mma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                                 uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+        "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// UMMA shared-memory descriptor, 128-byte swizzle (cute/arch/mma_sm100_desc.hpp bit layout):
+// [0,14) start>>4, [16,30) LBO>>4, [32,46) SBO>>4, [46,48) version=1, [61,64) layout=2 (SW128).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr >> 4) & 0x3fffu);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3fffu) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3fffu) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
+template <int BN> struct Cfg {
+  static constexpr int B_STAGE_BYTES = BN * 128;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int TMEM_COLS = 2 * BN;   // double-buffered accumulator (power of two >= 32)
+  static constexpr int BAR_BYTES = 8 * (2 * STAGES + 4) + 16;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // + alignment slack
+};
+
+template <int MODE, int BN, bool GATHER>
+__global__ void __launch_bounds__(GATHER ? 384 : 256, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const Params p) {
+  using C = Cfg<BN>;
+  constexpr int STAGES = C::STAGES;
+  constexpr bool A_MN = (MODE == WGRAD);
+  constexpr bool B_MN = (MODE != FPROP);
+  // which operand the gather warps stage (the other always comes by TMA)
+  constexpr bool GATHER_A = GATHER && (MODE != WGRAD);
+  constexpr bool GATHER_B = GATHER && (MODE == WGRAD);
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + STAGES * C::STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+  auto stage_a = [&](int s) { return smem_base + s * C::STAGE_BYTES; };
+  auto stage_b = [&](int s) { return smem_base + s * C::STAGE_BYTES + A_STAGE_BYTES; };
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1 + (GATHER ? NUM_GATHER_THREADS : 0));
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                 "r"((uint32_t)C::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+
+  const int tiles_mn = p.tiles_m * p.tiles_n;
+  const int total_tiles = tiles_mn * p.splits;
+  const int ips = (p.k_iters + p.splits - 1) / p.splits;   // K iterations per split
+
+  if (warp == 0) {
+    // ============================ TMA producer (one thread) ============================
+    if (lane == 0) {
+      uint32_t it = 0;
+      constexpr uint32_t tx_bytes =
+          (GATHER_A ? 0u : (uint32_t)A_STAGE_BYTES) + (GATHER_B ? 0u : (uint32_t)C::B_STAGE_BYTES);
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int split = tile / tiles_mn;
+        const int rem = tile - split * tiles_mn;
+        const int m_tile = rem / p.tiles_n, n_tile = rem - m_tile * p.tiles_n;
+        const int m0 = m_tile * BM;
+        const int kb = split * ips, ke = min(kb + ips, p.k_iters);
+        for (int k = kb; k < ke; ++k, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1u;
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          mbar_arrive_expect_tx(full_bar(s), tx_bytes);
+          if (MODE == FPROP) {
+            const int tap = k / p.cpt, chunk = k - tap * p.cpt;
+            if (!GATHER_A) tma_load_2d(stage_a(s), &tmA, full_bar(s), chunk * BK, m0);
+            tma_load_2d(stage_b(s), &tmB, full_bar(s), tap * p.gC + chunk * BK, n_tile * BN);
+          } else if (MODE == DGRAD) {
+            const int tap = k / p.cpt, chunk = k - tap * p.cpt;
+            if (!GATHER_A) tma_load_2d(stage_a(s), &tmA, full_bar(s), chunk * BK, m0);
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+              tma_load_2d(stage_b(s) + j * 8192, &tmB, full_bar(s),
+                          tap * p.ntot + n_tile * BN + j * 64, chunk * BK);
+          } else {
+            const int p0 = k * BK;
+            tma_load_2d(stage_a(s), &tmA, full_bar(s), m0, p0);
+            tma_load_2d(stage_a(s) + 8192, &tmA, full_bar(s), m0 + 64, p0);
+            if (!GATHER_B) {
+              const int nper = p.ntot / BN;           // n-tiles per tap
+              const int ci0 = (n_tile % nper) * BN;   // non-gather WGRAD has a single tap
+#pragma unroll
+              for (int j = 0; j < BN / 64; ++j)
+                tma_load_2d(stage_b(s) + j * 8192, &tmB, full_bar(s), ci0 + j * 64, p0);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================ MMA issuer (one thread) ==============================
+    if (lane == 0) {
+      // instruction descriptor: fp32 accum, bf16 A/B, majors, N>>3 at [17,23), M>>4 at [24,29)
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) |
+                             ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) |
+                             ((uint32_t)(BM >> 4) << 24);
+      uint32_t it = 0, tcount = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+        const int split = tile / tiles_mn;
+        const int kb = split * ips, ke = min(kb + ips, p.k_iters);
+        const uint32_t acc = tcount & 1u, aph = (tcount >> 1) & 1u;
+        mbar_wait(tempty_bar(acc), aph ^ 1u);
+        tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int k = kb; k < ke; ++k, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1u;
+          mbar_wait(full_bar(s), ph);
+          tcgen05_fence_after();
+#pragma unroll
+          for (int ks = 0; ks < BK / 16; ++ks) {
+            const uint64_t da = A_MN ? umma_desc(stage_a(s) + ks * 2048, 8192, 1024)
+                                     : umma_desc(stage_a(s) + ks * 32, 16, 1024);
+            const uint64_t db = B_MN ? umma_desc(stage_b(s) + ks * 2048, 8192, 1024)
+                                     : umma_desc(stage_b(s) + ks * 32, 16, 1024);
+            tcgen05_mma_bf16(tmem_d, da, db, idesc, (k > kb || ks > 0) ? 1u : 0u);
+          }
+          tcgen05_commit(empty_bar(s));     // frees the smem stage when these MMAs retire
+        }
+        tcgen05_commit(tfull_bar(acc));     // accumulator ready for the epilogue
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ============================ epilogue warps =======================================
+    const int quad = warp & 3;              // TMEM lane quadrant this warp may access
+    const int row = quad * 32 + lane;
+    uint32_t tcount = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+      const int split = tile / tiles_mn;
+      const int rem = tile - split * tiles_mn;
+      const int m_tile = rem / p.tiles_n, n_tile = rem - m_tile * p.tiles_n;
+      const int m = m_tile * BM + row;
+      const uint32_t acc = tcount & 1u, aph = (tcount >> 1) & 1u;
+      mbar_wait(tfull_bar(acc), aph);
+      tcgen05_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN;
+      long long ncol0;     // first output column of this tile
+      if (MODE == WGRAD) {
+        const int nper = p.ntot / BN;
+        ncol0 = (long long)(n_tile / nper) * p.ntot + (long long)(n_tile % nper) * BN;
+      } else {
+        ncol0 = (long long)n_tile * BN;
+      }
+      const bool row_ok = m < p.M;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld32(taddr + c * 32, v);
+        tmem_ld_wait();
+        const long long n0 = ncol0 + c * 32;
+        if (!row_ok) continue;
+        if (MODE == WGRAD) {
+          const float sc = p.alpha * (p.rowscale ? __ldg(p.rowscale + m) : 1.0f);
+          float* o = reinterpret_cast<float*>(p.out) + (long long)m * p.ldo + n0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) atomicAdd(o + j, __uint_as_float(v[j]) * sc);
+        } else {
+          const int nvalid = (int)min((long long)32, (long long)p.N - n0);
+          if (nvalid <= 0) continue;
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          if (p.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < nvalid) f[j] += __ldg(p.bias + n0 + j);
+          }
+          const bool vec = (nvalid == 32);
+          if (p.res) {
+            if (p.res_fp32) {
+              const float* r = reinterpret_cast<const float*>(p.res) + (long long)m * p.ldr + n0;
+              if (vec && (p.ldr & 3) == 0) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const float4 t = __ldg(reinterpret_cast<const float4*>(r) + j);
+                  f[4 * j] += t.x; f[4 * j + 1] += t.y; f[4 * j + 2] += t.z; f[4 * j + 3] += t.w;
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (j < nvalid) f[j] += __ldg(r + j);
+              }
+            } else {
+              const bf16* r = reinterpret_cast<const bf16*>(p.res) + (long long)m * p.ldr + n0;
+              if (vec && (p.ldr & 7) == 0) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const uint4 t = __ldg(reinterpret_cast<const uint4*>(r) + j);
+                  const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+                  for (int q = 0; q < 4; ++q) {
+                    f[8 * j + 2 * q] += __uint_as_float(w[q] << 16);
+                    f[8 * j + 2 * q + 1] += __uint_as_float(w[q] & 0xffff0000u);
+                  }
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (j < nvalid) f[j] += __bfloat162float(r[j]);
+              }
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
+          }
+          if (p.mask) {
+            const bf16* r = p.mask + (long long)m * p.ldm + n0;
+            if (vec && (p.ldm & 7) == 0) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint4 t = __ldg(reinterpret_cast<const uint4*>(r) + j);
+                const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  if (!(__uint_as_float(w[q] << 16) > 0.0f)) f[8 * j + 2 * q] = 0.0f;
+                  if (!(__uint_as_float(w[q] & 0xffff0000u) > 0.0f)) f[8 * j + 2 * q + 1] = 0.0f;
+                }
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < nvalid && !(__bfloat162float(r[j]) > 0.0f)) f[j] = 0.0f;
+            }
+          }
+          if (p.out_fp32) {
+            float* o = reinterpret_cast<float*>(p.out) + (long long)m * p.ldo + n0;
+            if (vec && (p.ldo & 3) == 0) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                reinterpret_cast<float4*>(o)[j] =
+                    make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < nvalid) o[j] = f[j];
+            }
+          } else {
+            bf16* o = reinterpret_cast<bf16*>(p.out) + (long long)m * p.ldo + n0;
+            if (vec && (p.ldo & 7) == 0) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                uint4 t;
+                uint32_t w[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const __nv_bfloat162 h = __floats2bfloat162_rn(f[8 * j + 2 * q], f[8 * j + 2 * q + 1]);
+                  w[q] = *reinterpret_cast<const uint32_t*>(&h);
+                }
+                t.x = w[0]; t.y = w[1]; t.z = w[2]; t.w = w[3];
+                reinterpret_cast<uint4*>(o)[j] = t;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < nvalid) o[j] = __float2bfloat16_rn(f[j]);
+            }
+          }
+        }
+      }
+      tcgen05_fence_before();
+      mbar_arrive(tempty_bar(acc));
+    }
+  } else if (GATHER && warp >= 8) {
+    // ============================ im2col gather warps ==================================
+    // Each of the 128 threads owns one 128-byte row (FPROP/DGRAD: one output pixel of the A
+    // tile; WGRAD: one pixel of the B tile for half of the 64-channel column blocks).
+    constexpr int DEPTH = 2;   // cp.async groups kept in flight besides the current one
+    const int g = threadIdx.x - 256;
+    uint32_t it = 0;
+    uint32_t pending_first = 0;    // oldest iteration whose full-barrier arrive is outstanding
+    const int ohw = p.oH * p.oW;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int split = tile / tiles_mn;
+      const int rem = tile - split * tiles_mn;
+      const int m_tile = rem / p.tiles_n, n_tile = rem - m_tile * p.tiles_n;
+      const int kb = split * ips, ke = min(kb + ips, p.k_iters);
+      int rn = 0, roh = 0, row_ = 0;
+      bool rvalid = false;
+      if (GATHER_A) {
+        const int m = m_tile * BM + g;
+        rvalid = m < p.rows;
+        if (rvalid) {
+          rn = m / ohw;
+          const int r2 = m - rn * ohw;
+          roh = r2 / p.oW;
+          row_ = r2 - roh * p.oW;
+        }
+      }
+      for (int k = kb; k < ke; ++k, ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1u;
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        if (GATHER_A) {
+          const int tap = k / p.cpt, chunk = k - tap * p.cpt;
+          const int fr = tap / p.S, fs = tap - fr * p.S;
+          int hi, wi;
+          bool ok = rvalid;
+          if (!p.transposed) {
+            hi = roh * p.stride - p.pad_h + fr * p.dil;
+            wi = row_ * p.stride - p.pad_w + fs * p.dil;
+          } else {
+            const int hy = roh + p.pad_h - fr * p.dil, wy = row_ + p.pad_w - fs * p.dil;
+            ok = ok && hy >= 0 && wy >= 0 && (hy % p.stride == 0) && (wy % p.stride == 0);
+            hi = hy / p.stride;
+            wi = wy / p.stride;
+          }
+          ok = ok && hi >= 0 && hi < p.gH && wi >= 0 && wi < p.gW;
+          const int c0 = chunk * BK;
+          const bf16* src = ok ? p.gsrc + ((long long)(rn * p.gH + hi) * p.gW + wi) * p.gC + c0 : p.gsrc;
+          const uint32_t dst = stage_a(s) + g * 128;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const bool pv = ok && (c0 + q * 8 < p.gC);
+            cp_async16(dst + ((q ^ (g & 7)) << 4), pv ? (const void*)(src + q * 8) : (const void*)p.gsrc,
+                       pv ? 16u : 0u);
+          }
+        } else {
+          // WGRAD: rows are pixels of this K block, columns are ci of tap (n_tile / nper)
+          const int nper = p.ntot / BN;
+          const int tap = n_tile / nper, ci0 = (n_tile - tap * nper) * BN;
+          const int fr = tap / p.S, fs = tap - fr * p.S;
+          const int pr = g & 63;
+          const int pix = k * BK + pr;
+          bool ok = pix < p.rows;
+          int n = 0, oh = 0, ow = 0;
+          if (ok) {
+            n = pix / ohw;
+            const int r2 = pix - n * ohw;
+            oh = r2 / p.oW;
+            ow = r2 - oh * p.oW;
+          }
+          const int hi = oh * p.stride - p.pad_h + fr * p.dil;
+          const int wi = ow * p.stride - p.pad_w + fs * p.dil;
+          ok = ok && hi >= 0 && hi < p.gH && wi >= 0 && wi < p.gW;
+          const bf16* src = ok ? p.gsrc + ((long long)(n * p.gH + hi) * p.gW + wi) * p.gC + ci0 : p.gsrc;
+#pragma unroll
+          for (int jj = 0; jj < BN / 128; ++jj) {
+            const int j = (g >> 6) + 2 * jj;
+            const uint32_t dst = stage_b(s) + j * 8192 + pr * 128;
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              cp_async16(dst + ((q ^ (pr & 7)) << 4),
+                         ok ? (const void*)(src + j * 64 + q * 8) : (const void*)p.gsrc, ok ? 16u : 0u);
+          }
+          if (BN == 64) {   // single column block: threads 0..63 stage it, 64..127 only arrive
+            if ((g >> 6) == 0) {
+              const uint32_t dst = stage_b(s) + pr * 128;
+#pragma unroll
+              for (int q = 0; q < 8; ++q)
+                cp_async16(dst + ((q ^ (pr & 7)) << 4),
+                           ok ? (const void*)(src + q * 8) : (const void*)p.gsrc, ok ? 16u : 0u);
+            }
+          }
+        }
+        cp_async_commit();
+        if (it - pending_first >= (uint32_t)DEPTH) {
+          cp_async_wait<DEPTH>();
+          fence_proxy_async();
+          mbar_arrive(full_bar(pending_first % STAGES));
+          ++pending_first;
+        }
+      }
+    }
+    cp_async_wait<0>();
+    fence_proxy_async();
+    for (; pending_first < it; ++pending_first) mbar_arrive(full_bar(pending_first % STAGES));
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"((uint32_t)C::TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// ----------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// 2-D bf16 row-major matrix [rows, cols] with row pitch ld (elements); box = 64 cols x box_rows.
+static int make_map(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld,
+                    int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { mtl_set_error("gemm_tc: cuTensorMapEncodeTiled unavailable"); return MTL_ERR_CUDA; }
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld & 7)) {
+    mtl_set_error("gemm_tc: TMA operand must be 16B aligned with row pitch %% 8 == 0 (ld=%lld)", ld);
+    return MTL_ERR_ARG;
+  }
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { mtl_set_error("gemm_tc: cuTensorMapEncodeTiled failed (%d)", (int)r); return MTL_ERR_CUDA; }
+  return MTL_OK;
+}
+
+template <int MODE, int BN, bool GATHER>
+static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const Params& p, cudaStream_t stream) {
+  using C = Cfg<BN>;
+  auto kern = tc_gemm_kernel<MODE, BN, GATHER>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    if (e != cudaSuccess) { mtl_set_error("gemm_tc: smem attribute: %s", cudaGetErrorString(e)); return MTL_ERR_CUDA; }
+    attr_set = true;
+  }
+  const int total = p.tiles_m * p.tiles_n * p.splits;
+  const int grid = total < mtl_num_sms() ? total : mtl_num_sms();
+  kern<<<grid, GATHER ? 384 : 256, C::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  MTL_CUDA_LAUNCH_CHECK("tc_gemm_kernel");
+  return MTL_OK;
+}
+
+template <int MODE, bool GATHER>
+static int dispatch_bn(int bn, const CUtensorMap& a, const CUtensorMap& b, const Params& p, cudaStream_t st) {
+  switch (bn) {
+    case 256: return launch<MODE, 256, GATHER>(a, b, p, st);
+    case 128: return launch<MODE, 128, GATHER>(a, b, p, st);
+    case 64: return launch<MODE, 64, GATHER>(a, b, p, st);
+  }
+  mtl_set_error("gemm_tc: unsupported BN %d", bn);
+  return MTL_ERR_UNSUPPORTED;
+}
+
+}  // namespace tc
+
+// Public C ABI --------------------------------------------------------------------------
+struct mtl_conv_args {
+  int mode;                 // 0 fprop, 1 dgrad, 2 wgrad
+  int N, H, W, C;           // input-side activation geometry x[N,H,W,C]
+  int K;                    // output channels
+  int R, S, stride, pad_h, pad_w, dil;
+  int P, Q;                 // output-side spatial dims y[N,P,Q,K]
+  const void* x;            // fprop/wgrad: x (bf16). dgrad: unused
+  const void* w;            // fprop/dgrad: w[K,R,S,C] bf16. wgrad: unused
+  const void* dy;           // dgrad/wgrad: dy[N,P,Q,K] bf16
+  void* out;                // fprop: y; dgrad: dx; wgrad: dw fp32 [K,R,S,C] (accumulated)
+  int out_fp32;             // fprop/dgrad: output element type
+  const float* bias;        // fprop: per-K bias (or null)
+  const float* rowscale;    // wgrad: per-K scale (or null)
+  const void* res; int res_fp32;   // tensor added before relu/mask, same shape as out
+  const void* mask;         // bf16 tensor, same shape as out: out = mask > 0 ? out : 0
+  int relu;
+  float alpha;              // wgrad scale
+  int force_bn;             // 0 = auto
+  int force_splits;         // 0 = auto
+};
+
+extern "C" int mtl_conv_tc(const mtl_conv_args* a, cudaStream_t stream) {
+  using namespace tc;
+  MTL_CHECK_ARG(a != nullptr, "mtl_conv_tc: null args");
+  MTL_CHECK_ARG(a->C % 8 == 0 && a->K % 8 == 0, "mtl_conv_tc: C and K must be multiples of 8 (C=%d K=%d)", a->C, a->K);
+  MTL_CHECK_ARG(a->N > 0 && a->H > 0 && a->W > 0 && a->P > 0 && a->Q > 0, "mtl_conv_tc: empty geometry");
+  const bool plain = (a->R == 1 && a->S == 1 && a->stride == 1 && a->pad_h == 0 && a->pad_w == 0);
+  if (plain) MTL_CHECK_ARG(a->P == a->H && a->Q == a->W, "mtl_conv_tc: 1x1 geometry mismatch");
+  const long long npq = (long long)a->N * a->P * a->Q, nhw = (long long)a->N * a->H * a->W;
+  MTL_CHECK_ARG(npq < (1ll << 31) && nhw < (1ll << 31), "mtl_conv_tc: too many pixels");
+
+  Params p;
+  memset(&p, 0, sizeof(p));
+  p.S = a->S; p.stride = a->stride; p.pad_h = a->pad_h; p.pad_w = a->pad_w; p.dil = a->dil > 0 ? a->dil : 1;
+  p.out = a->out; p.out_fp32 = a->out_fp32; p.bias = a->bias; p.rowscale = a->rowscale;
+  p.res = a->res; p.res_fp32 = a->res_fp32; p.mask = reinterpret_cast<const bf16*>(a->mask);
+  p.relu = a->relu; p.alpha = a->alpha; p.splits = 1; p.taps = a->R * a->S;
+  CUtensorMap tmA, tmB;
+  memset(&tmA, 0, sizeof(tmA)); memset(&tmB, 0, sizeof(tmB));
+  int bn, rc;
+  const bool gather = !plain;
+  if (a->mode == FPROP) {
+    MTL_CHECK_ARG(a->x && a->w && a->out, "mtl_conv_tc fprop: null tensor");
+    p.M = (int)npq; p.N = a->K; p.cpt = ceil_div(a->C, BK); p.k_iters = p.taps * p.cpt;
+    p.gsrc = reinterpret_cast<const bf16*>(a->x); p.gH = a->H; p.gW = a->W; p.gC = a->C;
+    p.oH = a->P; p.oW = a->Q; p.rows = p.M; p.transposed = 0;
+    p.ldo = a->K; p.ldr = a->K; p.ldm = a->K;
+    bn = a->force_bn ? a->force_bn : (a->K > 128 ? 256 : (a->K > 64 ? 128 : 64));
+    // keep the machine busy when M is small: prefer narrower tiles if they add CTAs
+    if (!a->force_bn && bn == 256 && ceil_div(p.M, BM) * ceil_div(a->K, 256) < mtl_num_sms() / 2) bn = 128;
+    if (!gather && (rc = make_map(&tmA, a->x, npq, a->C, a->C, BM))) return rc;
+    if ((rc = make_map(&tmB, a->w, a->K, (long long)p.taps * a->C, (long long)p.taps * a->C, bn))) return rc;
+    if (gather) tmA = tmB;
+  } else if (a->mode == DGRAD) {
+    MTL_CHECK_ARG(a->dy && a->w && a->out, "mtl_conv_tc dgrad: null tensor");
+    p.M = (int)nhw; p.N = a->C; p.cpt = ceil_div(a->K, BK); p.k_iters = p.taps * p.cpt;
+    p.gsrc = reinterpret_cast<const bf16*>(a->dy); p.gH = a->P; p.gW = a->Q; p.gC = a->K;
+    p.oH = a->H; p.oW = a->W; p.rows = p.M; p.transposed = 1; p.ntot = a->C;
+    p.ldo = a->C; p.ldr = a->C; p.ldm = a->C;
+    bn = a->force_bn ? a->force_bn : (a->C > 128 ? 256 : (a->C > 64 ? 128 : 64));
+    if (!a->force_bn && bn == 256 && ceil_div(p.M, BM) * ceil_div(a->C, 256) < mtl_num_sms() / 2) bn = 128;
+    if (!gather && (rc = make_map(&tmA, a->dy, npq, a->K, a->K, BM))) return rc;
+    if ((rc = make_map(&tmB, a->w, a->K, (long long)p.taps * a->C, (long long)p.taps * a->C, 64))) return rc;
+    if (gather) tmA = tmB;
+  } else if (a->mode == WGRAD) {
+    MTL_CHECK_ARG(a->dy && a->x && a->out, "mtl_conv_tc wgrad: null tensor");
+    MTL_CHECK_ARG(a->C % 64 == 0, "mtl_conv_tc wgrad: C must be a multiple of 64 (C=%d)", a->C);
+    p.M = a->K; p.N = p.taps * a->C; p.cpt = 1; p.k_iters = (int)ceil_div_ll(npq, BK);
+    p.gsrc = reinterpret_cast<const bf16*>(a->x); p.gH = a->H; p.gW = a->W; p.gC = a->C;
+    p.oH = a->P; p.oW = a->Q; p.rows = (int)npq; p.transposed = 0; p.ntot = a->C;
+    p.ldo = (long long)p.taps * a->C;
+    bn = a->force_bn ? a->force_bn : (a->C % 256 == 0 ? 256 : (a->C % 128 == 0 ? 128 : 64));
+    MTL_CHECK_ARG(a->C % bn == 0, "mtl_conv_tc wgrad: BN %d must divide C %d", bn, a->C);
+    if ((rc = make_map(&tmA, a->dy, npq, a->K, a->K, 64))) return rc;
+    if (!gather && (rc = make_map(&tmB, a->x, nhw, a->C, a->C, 64))) return rc;
+    if (gather) tmB = tmA;
+    // split K (pixels) so that about one wave of CTAs is launched
+    const int tiles = ceil_div(p.M, BM) * (p.N / bn);
+    int splits = a->force_splits ? a->force_splits : (mtl_num_sms() + tiles - 1) / tiles;
+    if (splits > p.k_iters) splits = p.k_iters;
+    if (splits < 1) splits = 1;
+    const int ips = ceil_div(p.k_iters, splits);
+    p.splits = ceil_div(p.k_iters, ips);   // every split owns at least one K iteration
+  } else {
+    mtl_set_error("mtl_conv_tc: bad mode %d", a->mode);
+    return MTL_ERR_ARG;
+  }
+  p.tiles_m = ceil_div(p.M, BM);
+  p.tiles_n = (a->mode == WGRAD) ? p.N / bn : ceil_div(p.N, bn);
+  if (a->mode == FPROP) return gather ? dispatch_bn<FPROP, true>(bn, tmA, tmB, p, stream)
+                                      : dispatch_bn<FPROP, false>(bn, tmA, tmB, p, stream);
+  if (a->mode == DGRAD) return gather ? dispatch_bn<DGRAD, true>(bn, tmA, tmB, p, stream)
+                                      : dispatch_bn<DGRAD, false>(bn, tmA, tmB, p, stream);
+  return gather ? dispatch_bn<WGRAD, true>(bn, tmA, tmB, p, stream)
+                : dispatch_bn<WGRAD, false>(bn, tmA, tmB, p, stream);
+}

@@ -1,0 +1,121 @@
+"""Python binding of the tcgen05 convolution engine (csrc/gemm_tc.cu, mtl_conv_tc).
+
+Layouts: activations NHWC bf16, weights [K, R, S, C] bf16 (the reference's HWIO weights
+of slim.conv2d, /root/reference/slim/nets/resnet_utils.py:111-122, are transposed once at
+load time).  All functions enqueue on the current torch stream and never synchronise.
+"""
+import ctypes
+
+import torch
+
+from ._lib import lib, check, ptr, cur_stream
+
+FPROP, DGRAD, WGRAD = 0, 1, 2
+
+
+class ConvArgs(ctypes.Structure):
+    _fields_ = [
+        ("mode", ctypes.c_int),
+        ("N", ctypes.c_int), ("H", ctypes.c_int), ("W", ctypes.c_int), ("C", ctypes.c_int),
+        ("K", ctypes.c_int),
+        ("R", ctypes.c_int), ("S", ctypes.c_int), ("stride", ctypes.c_int),
+        ("pad_h", ctypes.c_int), ("pad_w", ctypes.c_int), ("dil", ctypes.c_int),
+        ("P", ctypes.c_int), ("Q", ctypes.c_int),
+        ("x", ctypes.c_void_p), ("w", ctypes.c_void_p), ("dy", ctypes.c_void_p),
+        ("out", ctypes.c_void_p), ("out_fp32", ctypes.c_int),
+        ("bias", ctypes.c_void_p), ("rowscale", ctypes.c_void_p),
+        ("res", ctypes.c_void_p), ("res_fp32", ctypes.c_int),
+        ("mask", ctypes.c_void_p),
+        ("relu", ctypes.c_int), ("alpha", ctypes.c_float),
+        ("force_bn", ctypes.c_int), ("force_splits", ctypes.c_int),
+    ]
+
+
+def out_size(h, k, stride, pad_beg, pad_end, dil=1):
+    return (h + pad_beg + pad_end - dil * (k - 1) - 1) // stride + 1
+
+
+def _dp(t):
+    return t.data_ptr() if t is not None else None
+
+
+def _geom(a, xshape, wshape, stride, pad, dil, P, Q):
+    a.N, a.H, a.W, a.C = xshape
+    a.K, a.R, a.S, _ = wshape
+    a.stride, a.pad_h, a.pad_w, a.dil = stride, pad[0], pad[1], dil
+    a.P, a.Q = P, Q
+
+
+def conv_fprop(x, w, stride=1, pad=(0, 0), dil=1, out_hw=None, bias=None, res=None, relu=False,
+               out=None, out_dtype=torch.bfloat16, force_bn=0):
+    """y = relu?(conv(x, w) + bias + res).  x [N,H,W,C] bf16, w [K,R,S,C] bf16."""
+    N, H, W, C = x.shape
+    K, R, S, C2 = w.shape
+    assert C == C2 and x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
+    assert x.is_contiguous() and w.is_contiguous()
+    if out_hw is None:
+        out_hw = (out_size(H, R, stride, pad[0], pad[0], dil), out_size(W, S, stride, pad[1], pad[1], dil))
+    P, Q = out_hw
+    if out is None:
+        out = torch.empty((N, P, Q, K), device=x.device, dtype=out_dtype)
+    a = ConvArgs()
+    a.mode = FPROP
+    _geom(a, (N, H, W, C), (K, R, S, C), stride, pad, dil, P, Q)
+    a.x, a.w, a.out = _dp(x), _dp(w), _dp(out)
+    a.out_fp32 = int(out.dtype == torch.float32)
+    a.bias = _dp(bias)
+    if res is not None:
+        assert res.shape == out.shape and res.is_contiguous()
+        a.res, a.res_fp32 = _dp(res), int(res.dtype == torch.float32)
+    a.relu = int(relu)
+    a.alpha = 1.0
+    a.force_bn = force_bn
+    check(lib().mtl_conv_tc(ctypes.byref(a), cur_stream()), "mtl_conv_tc(fprop)")
+    return out
+
+
+def conv_dgrad(dy, w, x_shape, stride=1, pad=(0, 0), dil=1, res=None, mask=None, out=None,
+               out_dtype=torch.bfloat16, force_bn=0):
+    """dx = mask>0 ? (conv_transpose(dy, w) + res) : 0.  dy [N,P,Q,K], w [K,R,S,C]."""
+    N, P, Q, K = dy.shape
+    K2, R, S, C = w.shape
+    assert K == K2 and dy.is_contiguous() and w.is_contiguous()
+    _, H, W, C2 = x_shape
+    assert C2 == C
+    if out is None:
+        out = torch.empty((N, H, W, C), device=dy.device, dtype=out_dtype)
+    a = ConvArgs()
+    a.mode = DGRAD
+    _geom(a, (N, H, W, C), (K, R, S, C), stride, pad, dil, P, Q)
+    a.dy, a.w, a.out = _dp(dy), _dp(w), _dp(out)
+    a.out_fp32 = int(out.dtype == torch.float32)
+    if res is not None:
+        assert res.shape == out.shape and res.is_contiguous()
+        a.res, a.res_fp32 = _dp(res), int(res.dtype == torch.float32)
+    if mask is not None:
+        assert mask.shape == out.shape and mask.dtype == torch.bfloat16 and mask.is_contiguous()
+        a.mask = _dp(mask)
+    a.alpha = 1.0
+    a.force_bn = force_bn
+    check(lib().mtl_conv_tc(ctypes.byref(a), cur_stream()), "mtl_conv_tc(dgrad)")
+    return out
+
+
+def conv_wgrad(dy, x, dw, stride=1, pad=(0, 0), dil=1, rowscale=None, alpha=1.0, force_bn=0,
+               force_splits=0):
+    """dw[K,R,S,C] (fp32) += alpha * rowscale[k] * sum_pixels dy[p,k] * im2col(x)[p,(r,s,c)]."""
+    N, P, Q, K = dy.shape
+    N2, H, W, C = x.shape
+    K2, R, S, C2 = dw.shape
+    assert N == N2 and K == K2 and C == C2 and dw.dtype == torch.float32
+    assert dy.is_contiguous() and x.is_contiguous() and dw.is_contiguous()
+    a = ConvArgs()
+    a.mode = WGRAD
+    _geom(a, (N, H, W, C), (K, R, S, C), stride, pad, dil, P, Q)
+    a.dy, a.x, a.out = _dp(dy), _dp(x), _dp(dw)
+    a.rowscale = _dp(rowscale)
+    a.alpha = float(alpha)
+    a.force_bn = force_bn
+    a.force_splits = force_splits
+    check(lib().mtl_conv_tc(ctypes.byref(a), cur_stream()), "mtl_conv_tc(wgrad)")
+    return dw
