@@ -1,0 +1,528 @@
+// HBM-bound feature-map kernels (sm_100a): ROI bilinear gather/scatter (tf.image.crop_and_resize),
+// position-sensitive ROI pooling, max / average pooling, stem im2col + preprocessing.
+//
+// Reference call sites (under /root/reference/):
+//   crop_and_resize   object_detection/meta_architectures/faster_rcnn_meta_arch.py:1340-1348
+//   PS-ROI            object_detection/utils/ops.py:462-609
+//   max pool          slim/nets/resnet_v1.py:222, slim/nets/resnet_utils.py:59-74, fmA:1345-1348
+//   spatial average   object_detection/core/box_predictor.py:470-472
+//   preprocessing     object_detection/models/faster_rcnn_resnet_v1_feature_extractor.py:74-90
+// The arithmetic of CropAndResize / MaxPool / ResizeBilinear is TensorFlow 1.7's (not vendored);
+// it is restated in oracle/nn.py and these kernels follow the same formulas.
+// All activations are NHWC; channel vectors are moved as 16-byte (8 x bf16) accesses, one
+// warp per output pixel, so every global transaction is a full coalesced line.
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ void unpack8(const uint4 v, float (&f)[8]) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    f[2 * q] = __uint_as_float(w[q] << 16);
+    f[2 * q + 1] = __uint_as_float(w[q] & 0xffff0000u);
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint32_t w[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * q], f[2 * q + 1]);
+    w[q] = *reinterpret_cast<const uint32_t*>(&h);
+  }
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// ------------------------------------------------------------------ crop_and_resize
+struct CropGeom {
+  bool valid;
+  int top, bot, left, right;
+  float yl, xl;
+};
+
+// TF 1.7 crop_and_resize_op.cc coordinate arithmetic for output pixel (i, j) of box (y1,x1,y2,x2).
+__device__ __forceinline__ CropGeom crop_geom(const float4 bx, int i, int j, int ch, int cw, int H, int W) {
+  CropGeom g;
+  const float hs = ch > 1 ? (bx.z - bx.x) * (float)(H - 1) / (float)(ch - 1) : 0.0f;
+  const float ws = cw > 1 ? (bx.w - bx.y) * (float)(W - 1) / (float)(cw - 1) : 0.0f;
+  const float in_y = ch > 1 ? bx.x * (float)(H - 1) + (float)i * hs : 0.5f * (bx.x + bx.z) * (float)(H - 1);
+  const float in_x = cw > 1 ? bx.y * (float)(W - 1) + (float)j * ws : 0.5f * (bx.y + bx.w) * (float)(W - 1);
+  g.valid = !(in_y < 0.0f || in_y > (float)(H - 1) || in_x < 0.0f || in_x > (float)(W - 1));
+  const float fy = floorf(in_y), fx = floorf(in_x);
+  g.top = (int)fy; g.bot = (int)ceilf(in_y);
+  g.left = (int)fx; g.right = (int)ceilf(in_x);
+  g.yl = in_y - fy; g.xl = in_x - fx;
+  return g;
+}
+
+// one warp per output pixel (r, i, j); lanes stride over 8-channel vectors
+__global__ void __launch_bounds__(256)
+crop_resize_fwd_kernel(const bf16* __restrict__ feat, int H, int W, int C, const float4* __restrict__ boxes,
+                       const int* __restrict__ box_ind, int R, int ch, int cw, bf16* __restrict__ out) {
+  const long long gw = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const long long total = (long long)R * ch * cw;
+  if (gw >= total) return;
+  const int j = (int)(gw % cw);
+  const int i = (int)((gw / cw) % ch);
+  const int r = (int)(gw / ((long long)cw * ch));
+  const float4 bx = boxes[r];
+  const int bi = box_ind ? box_ind[r] : 0;
+  const CropGeom g = crop_geom(bx, i, j, ch, cw, H, W);
+  uint4* o = reinterpret_cast<uint4*>(out + gw * C);
+  const int nvec = C >> 3;
+  if (!g.valid) {
+    for (int v = lane; v < nvec; v += 32) o[v] = make_uint4(0, 0, 0, 0);   // extrapolation_value = 0
+    return;
+  }
+  const bf16* base = feat + (long long)bi * H * W * C;
+  const uint4* tl = reinterpret_cast<const uint4*>(base + ((long long)g.top * W + g.left) * C);
+  const uint4* tr = reinterpret_cast<const uint4*>(base + ((long long)g.top * W + g.right) * C);
+  const uint4* bl = reinterpret_cast<const uint4*>(base + ((long long)g.bot * W + g.left) * C);
+  const uint4* br = reinterpret_cast<const uint4*>(base + ((long long)g.bot * W + g.right) * C);
+  for (int v = lane; v < nvec; v += 32) {
+    float a[8], b[8], c[8], d[8], y[8];
+    unpack8(__ldg(tl + v), a); unpack8(__ldg(tr + v), b);
+    unpack8(__ldg(bl + v), c); unpack8(__ldg(br + v), d);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float top = a[q] + (b[q] - a[q]) * g.xl;
+      const float bot = c[q] + (d[q] - c[q]) * g.xl;
+      y[q] = top + (bot - top) * g.yl;
+    }
+    o[v] = pack8(y);
+  }
+}
+
+// CropAndResizeGradImage: scatter-add of dcrops into an fp32 feature gradient (vector atomics)
+__global__ void __launch_bounds__(256)
+crop_resize_bwd_kernel(const bf16* __restrict__ dcrop, int H, int W, int C, const float4* __restrict__ boxes,
+                       const int* __restrict__ box_ind, int R, int ch, int cw, float* __restrict__ dfeat) {
+  const long long gw = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const long long total = (long long)R * ch * cw;
+  if (gw >= total) return;
+  const int j = (int)(gw % cw);
+  const int i = (int)((gw / cw) % ch);
+  const int r = (int)(gw / ((long long)cw * ch));
+  const float4 bx = boxes[r];
+  const int bi = box_ind ? box_ind[r] : 0;
+  const CropGeom g = crop_geom(bx, i, j, ch, cw, H, W);
+  if (!g.valid) return;
+  const uint4* src = reinterpret_cast<const uint4*>(dcrop + gw * C);
+  float* base = dfeat + (long long)bi * H * W * C;
+  float* tl = base + ((long long)g.top * W + g.left) * C;
+  float* tr = base + ((long long)g.top * W + g.right) * C;
+  float* bl = base + ((long long)g.bot * W + g.left) * C;
+  float* br = base + ((long long)g.bot * W + g.right) * C;
+  const float wtl = (1.0f - g.yl) * (1.0f - g.xl), wtr = (1.0f - g.yl) * g.xl;
+  const float wbl = g.yl * (1.0f - g.xl), wbr = g.yl * g.xl;
+  const int nvec = C >> 3;
+  for (int v = lane; v < nvec; v += 32) {
+    float d[8];
+    unpack8(__ldg(src + v), d);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const float4 x = make_float4(d[4 * h], d[4 * h + 1], d[4 * h + 2], d[4 * h + 3]);
+      const int off = v * 8 + h * 4;
+      atomicAdd(reinterpret_cast<float4*>(tl + off), make_float4(x.x * wtl, x.y * wtl, x.z * wtl, x.w * wtl));
+      if (wtr != 0.0f)
+        atomicAdd(reinterpret_cast<float4*>(tr + off), make_float4(x.x * wtr, x.y * wtr, x.z * wtr, x.w * wtr));
+      if (wbl != 0.0f)
+        atomicAdd(reinterpret_cast<float4*>(bl + off), make_float4(x.x * wbl, x.y * wbl, x.z * wbl, x.w * wbl));
+      if (wbr != 0.0f)
+        atomicAdd(reinterpret_cast<float4*>(br + off), make_float4(x.x * wbr, x.y * wbr, x.z * wbr, x.w * wbr));
+    }
+  }
+}
+
+// ------------------------------------------------------------------ max pool (NHWC bf16)
+__global__ void __launch_bounds__(256)
+maxpool_fwd_kernel(const bf16* __restrict__ x, int N, int H, int W, int C, int k, int stride, int pad_h,
+                   int pad_w, int P, int Q, bf16* __restrict__ y) {
+  const int nvec = C >> 3;
+  const long long total = (long long)N * P * Q * nvec;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(t % nvec);
+    const long long pix = t / nvec;
+    const int q = (int)(pix % Q);
+    const int p = (int)((pix / Q) % P);
+    const int n = (int)(pix / ((long long)P * Q));
+    float m[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) m[e] = -INFINITY;
+    for (int r = 0; r < k; ++r) {
+      const int h = p * stride - pad_h + r;
+      if (h < 0 || h >= H) continue;
+      for (int s = 0; s < k; ++s) {
+        const int w = q * stride - pad_w + s;
+        if (w < 0 || w >= W) continue;
+        float f[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(x + (((long long)n * H + h) * W + w) * C) + v), f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) m[e] = fmaxf(m[e], f[e]);
+      }
+    }
+    reinterpret_cast<uint4*>(y + pix * C)[v] = pack8(m);
+  }
+}
+
+// gather-form MaxPoolGrad: dx[h,w] = sum over windows containing (h,w) whose FIRST maximum
+// (scan order r, s) is (h,w) of dy[window].  Deterministic, no atomics.
+__global__ void __launch_bounds__(256)
+maxpool_bwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy, int N, int H, int W, int C, int k,
+                   int stride, int pad_h, int pad_w, int P, int Q, bf16* __restrict__ dx) {
+  const int nvec = C >> 3;
+  const long long total = (long long)N * H * W * nvec;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(t % nvec);
+    const long long pix = t / nvec;
+    const int w = (int)(pix % W);
+    const int h = (int)((pix / W) % H);
+    const int n = (int)(pix / ((long long)H * W));
+    float mine[8], acc[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(x + pix * C) + v), mine);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.0f;
+    // windows p with p*stride - pad_h <= h < p*stride - pad_h + k
+    const int p_lo = max(0, (h + pad_h - k + stride) / stride);   // ceil((h+pad-k+1)/stride)
+    const int p_hi = min(P - 1, (h + pad_h) / stride);
+    const int q_lo = max(0, (w + pad_w - k + stride) / stride);
+    const int q_hi = min(Q - 1, (w + pad_w) / stride);
+    for (int p = p_lo; p <= p_hi; ++p) {
+      for (int q = q_lo; q <= q_hi; ++q) {
+        // is (h,w) the first maximum of window (p,q)?
+        bool first[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) first[e] = true;
+        for (int r = 0; r < k; ++r) {
+          const int hh = p * stride - pad_h + r;
+          if (hh < 0 || hh >= H) continue;
+          for (int s = 0; s < k; ++s) {
+            const int ww = q * stride - pad_w + s;
+            if (ww < 0 || ww >= W) continue;
+            if (hh == h && ww == w) continue;
+            float f[8];
+            unpack8(__ldg(reinterpret_cast<const uint4*>(x + (((long long)n * H + hh) * W + ww) * C) + v), f);
+            const bool before = (hh < h) || (hh == h && ww < w);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              if (before ? (f[e] >= mine[e]) : (f[e] > mine[e])) first[e] = false;
+            }
+          }
+        }
+        float g[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(dy + (((long long)n * P + p) * Q + q) * C) + v), g);
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          if (first[e]) acc[e] += g[e];
+      }
+    }
+    reinterpret_cast<uint4*>(dx + pix * C)[v] = pack8(acc);
+  }
+}
+
+// ------------------------------------------------------------------ spatial average (ROI heads)
+__global__ void __launch_bounds__(256)
+avgpool_fwd_kernel(const bf16* __restrict__ x, int R, int HW, int C, bf16* __restrict__ y) {
+  const int nvec = C >> 3;
+  const long long total = (long long)R * nvec;
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int v = (int)(t % nvec);
+  const long long r = t / nvec;
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.0f;
+  const uint4* src = reinterpret_cast<const uint4*>(x + r * HW * C) + v;
+  for (int p = 0; p < HW; ++p) {
+    float f[8];
+    unpack8(__ldg(src + (long long)p * nvec), f);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] += f[e];
+  }
+  const float inv = 1.0f / (float)HW;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] *= inv;
+  reinterpret_cast<uint4*>(y + r * C)[v] = pack8(acc);
+}
+
+// dx[r,p,c] = (mask[r,p,c] > 0 ? 1 : 0) * dy[r,c] / HW   (mask = the ReLU output being pooled)
+template <typename TDY>
+__global__ void __launch_bounds__(256)
+avgpool_bwd_kernel(const TDY* __restrict__ dy, long long ldy, const bf16* __restrict__ mask, int R, int HW, int C,
+                   bf16* __restrict__ dx) {
+  const int nvec = C >> 3;
+  const long long total = (long long)R * HW * nvec;
+  const float inv = 1.0f / (float)HW;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(t % nvec);
+    const long long rp = t / nvec;
+    const long long r = rp / HW;
+    float g[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) g[e] = to_f32<TDY>(dy[r * ldy + v * 8 + e]) * inv;
+    if (mask) {
+      float m[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(mask + rp * C) + v), m);
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        if (!(m[e] > 0.0f)) g[e] = 0.0f;
+    }
+    reinterpret_cast<uint4*>(dx + rp * C)[v] = pack8(g);
+  }
+}
+
+// ------------------------------------------------------------------ stem im2col (+ preprocessing)
+// rows[b,p,q, (r*S+s)*C + c] = (img[b, p*stride-pad+r, q*stride-pad+s, c] - mean[c]) * scale, zero
+// outside the image and in the pad columns [R*S*C, ld).  One warp per output pixel.
+__global__ void __launch_bounds__(256)
+im2col_f32_kernel(const float* __restrict__ img, int B, int H, int W, int C, int R, int S, int stride, int pad_h,
+                  int pad_w, int P, int Q, float m0, float m1, float m2, float m3, float scale,
+                  bf16* __restrict__ out, int ld) {
+  const long long gw = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const long long total = (long long)B * P * Q;
+  if (gw >= total) return;
+  const int q = (int)(gw % Q);
+  const int p = (int)((gw / Q) % P);
+  const int b = (int)(gw / ((long long)P * Q));
+  const int kk = R * S * C;
+  const float mean[4] = {m0, m1, m2, m3};
+  bf16* o = out + gw * ld;
+  for (int e = lane; e < ld; e += 32) {
+    float val = 0.0f;
+    if (e < kk) {
+      const int c = e % C;
+      const int rs = e / C;
+      const int s = rs % S, r = rs / S;
+      const int h = p * stride - pad_h + r, w = q * stride - pad_w + s;
+      if (h >= 0 && h < H && w >= 0 && w < W)
+        val = (__ldg(img + (((long long)b * H + h) * W + w) * C + c) - mean[c & 3]) * scale;
+    }
+    o[e] = __float2bfloat16_rn(val);
+  }
+}
+
+// (x - mean[c]) * scale -> bf16 NHWC, for inspection / the oracle's view of the preprocessed image
+__global__ void preprocess_kernel(const float* __restrict__ img, long long total, int C, float m0, float m1,
+                                  float m2, float m3, float scale, float* __restrict__ out) {
+  const float mean[4] = {m0, m1, m2, m3};
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x)
+    out[t] = (img[t] - mean[(int)(t % C) & 3]) * scale;
+}
+
+// ------------------------------------------------------------------ position-sensitive ROI pooling
+// utils/ops.py:462-609 with global_pool=True: bin (by,bx) of the box crops channel group
+// (by*nbx + bx) to a (ch/nby x cw/nbx) grid with crop_and_resize arithmetic; the output is the
+// mean over bins of the mean over the grid.  feat [B,H,W,nb*D] -> out [R, D] fp32.
+__global__ void __launch_bounds__(128)
+psroi_fwd_kernel(const bf16* __restrict__ feat, int H, int W, int D, int nby, int nbx, int gh, int gw_,
+                 const float4* __restrict__ boxes, const int* __restrict__ box_ind, int R, float* __restrict__ out) {
+  const int r = blockIdx.x;
+  const float4 bx = boxes[r];
+  const int bi = box_ind ? box_ind[r] : 0;
+  const int Ct = nby * nbx * D;
+  const bf16* base = feat + (long long)bi * H * W * Ct;
+  const float sy = (bx.z - bx.x) / (float)nby, sx = (bx.w - bx.y) / (float)nbx;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    float total = 0.0f;
+    for (int by = 0; by < nby; ++by)
+      for (int bxi = 0; bxi < nbx; ++bxi) {
+        const float4 bb = make_float4(bx.x + (float)by * sy, bx.y + (float)bxi * sx,
+                                      bx.x + (float)(by + 1) * sy, bx.y + (float)(bxi + 1) * sx);
+        const int c = (by * nbx + bxi) * D + d;
+        float acc = 0.0f;
+        for (int i = 0; i < gh; ++i)
+          for (int j = 0; j < gw_; ++j) {
+            const CropGeom g = crop_geom(bb, i, j, gh, gw_, H, W);
+            if (!g.valid) continue;
+            const float a = __bfloat162float(base[((long long)g.top * W + g.left) * Ct + c]);
+            const float b = __bfloat162float(base[((long long)g.top * W + g.right) * Ct + c]);
+            const float cc = __bfloat162float(base[((long long)g.bot * W + g.left) * Ct + c]);
+            const float dd = __bfloat162float(base[((long long)g.bot * W + g.right) * Ct + c]);
+            const float top = a + (b - a) * g.xl, bot = cc + (dd - cc) * g.xl;
+            acc += top + (bot - top) * g.yl;
+          }
+        total += acc / (float)(gh * gw_);
+      }
+    out[(long long)r * D + d] = total / (float)(nby * nbx);
+  }
+}
+
+__global__ void __launch_bounds__(128)
+psroi_bwd_kernel(const float* __restrict__ dout, int H, int W, int D, int nby, int nbx, int gh, int gw_,
+                 const float4* __restrict__ boxes, const int* __restrict__ box_ind, int R, float* __restrict__ dfeat) {
+  const int r = blockIdx.x;
+  const float4 bx = boxes[r];
+  const int bi = box_ind ? box_ind[r] : 0;
+  const int Ct = nby * nbx * D;
+  float* base = dfeat + (long long)bi * H * W * Ct;
+  const float sy = (bx.z - bx.x) / (float)nby, sx = (bx.w - bx.y) / (float)nbx;
+  const float sc = 1.0f / (float)(nby * nbx) / (float)(gh * gw_);
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    const float g0 = dout[(long long)r * D + d] * sc;
+    if (g0 == 0.0f) continue;
+    for (int by = 0; by < nby; ++by)
+      for (int bxi = 0; bxi < nbx; ++bxi) {
+        const float4 bb = make_float4(bx.x + (float)by * sy, bx.y + (float)bxi * sx,
+                                      bx.x + (float)(by + 1) * sy, bx.y + (float)(bxi + 1) * sx);
+        const int c = (by * nbx + bxi) * D + d;
+        for (int i = 0; i < gh; ++i)
+          for (int j = 0; j < gw_; ++j) {
+            const CropGeom g = crop_geom(bb, i, j, gh, gw_, H, W);
+            if (!g.valid) continue;
+            atomicAdd(base + ((long long)g.top * W + g.left) * Ct + c, g0 * (1.0f - g.yl) * (1.0f - g.xl));
+            atomicAdd(base + ((long long)g.top * W + g.right) * Ct + c, g0 * (1.0f - g.yl) * g.xl);
+            atomicAdd(base + ((long long)g.bot * W + g.left) * Ct + c, g0 * g.yl * (1.0f - g.xl));
+            atomicAdd(base + ((long long)g.bot * W + g.right) * Ct + c, g0 * g.yl * g.xl);
+          }
+      }
+  }
+}
+
+}  // namespace
+
+// ===================================================================================== C ABI
+#define CHECK_VEC8(C, name) MTL_CHECK_ARG((C) > 0 && (C) % 8 == 0, name ": channels must be a multiple of 8 (C=%d)", (C))
+
+extern "C" int mtl_crop_and_resize_fwd(const void* feat, int B, int H, int W, int C, const float* boxes,
+                                       const int* box_ind, int R, int crop_h, int crop_w, void* out,
+                                       cudaStream_t stream) {
+  MTL_CHECK_ARG(feat && boxes && out, "mtl_crop_and_resize_fwd: null tensor");
+  CHECK_VEC8(C, "mtl_crop_and_resize_fwd");
+  if (R == 0) return MTL_OK;
+  const long long warps = (long long)R * crop_h * crop_w;
+  crop_resize_fwd_kernel<<<(unsigned)ceil_div_ll(warps, 8), 256, 0, stream>>>(
+      reinterpret_cast<const bf16*>(feat), H, W, C, reinterpret_cast<const float4*>(boxes), box_ind, R, crop_h,
+      crop_w, reinterpret_cast<bf16*>(out));
+  MTL_CUDA_LAUNCH_CHECK("crop_resize_fwd_kernel");
+  (void)B;
+  return MTL_OK;
+}
+
+extern "C" int mtl_crop_and_resize_bwd(const void* dcrop, int B, int H, int W, int C, const float* boxes,
+                                       const int* box_ind, int R, int crop_h, int crop_w, float* dfeat,
+                                       cudaStream_t stream) {
+  MTL_CHECK_ARG(dcrop && boxes && dfeat, "mtl_crop_and_resize_bwd: null tensor");
+  CHECK_VEC8(C, "mtl_crop_and_resize_bwd");
+  if (R == 0) return MTL_OK;
+  const long long warps = (long long)R * crop_h * crop_w;
+  crop_resize_bwd_kernel<<<(unsigned)ceil_div_ll(warps, 8), 256, 0, stream>>>(
+      reinterpret_cast<const bf16*>(dcrop), H, W, C, reinterpret_cast<const float4*>(boxes), box_ind, R, crop_h,
+      crop_w, dfeat);
+  MTL_CUDA_LAUNCH_CHECK("crop_resize_bwd_kernel");
+  (void)B;
+  return MTL_OK;
+}
+
+extern "C" int mtl_maxpool_fwd(const void* x, int N, int H, int W, int C, int k, int stride, int pad_h, int pad_w,
+                               int P, int Q, void* y, cudaStream_t stream) {
+  MTL_CHECK_ARG(x && y, "mtl_maxpool_fwd: null tensor");
+  CHECK_VEC8(C, "mtl_maxpool_fwd");
+  const long long total = (long long)N * P * Q * (C / 8);
+  const int grid = (int)min(ceil_div_ll(total, 256), (long long)mtl_num_sms() * 16);
+  maxpool_fwd_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const bf16*>(x), N, H, W, C, k, stride, pad_h,
+                                               pad_w, P, Q, reinterpret_cast<bf16*>(y));
+  MTL_CUDA_LAUNCH_CHECK("maxpool_fwd_kernel");
+  return MTL_OK;
+}
+
+extern "C" int mtl_maxpool_bwd(const void* x, const void* dy, int N, int H, int W, int C, int k, int stride,
+                               int pad_h, int pad_w, int P, int Q, void* dx, cudaStream_t stream) {
+  MTL_CHECK_ARG(x && dy && dx, "mtl_maxpool_bwd: null tensor");
+  CHECK_VEC8(C, "mtl_maxpool_bwd");
+  const long long total = (long long)N * H * W * (C / 8);
+  const int grid = (int)min(ceil_div_ll(total, 256), (long long)mtl_num_sms() * 16);
+  maxpool_bwd_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const bf16*>(x), reinterpret_cast<const bf16*>(dy),
+                                               N, H, W, C, k, stride, pad_h, pad_w, P, Q,
+                                               reinterpret_cast<bf16*>(dx));
+  MTL_CUDA_LAUNCH_CHECK("maxpool_bwd_kernel");
+  return MTL_OK;
+}
+
+extern "C" int mtl_avgpool_fwd(const void* x, int R, int HW, int C, void* y, cudaStream_t stream) {
+  MTL_CHECK_ARG(x && y, "mtl_avgpool_fwd: null tensor");
+  CHECK_VEC8(C, "mtl_avgpool_fwd");
+  if (R == 0) return MTL_OK;
+  const long long total = (long long)R * (C / 8);
+  avgpool_fwd_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, stream>>>(reinterpret_cast<const bf16*>(x), R, HW,
+                                                                           C, reinterpret_cast<bf16*>(y));
+  MTL_CUDA_LAUNCH_CHECK("avgpool_fwd_kernel");
+  return MTL_OK;
+}
+
+extern "C" int mtl_avgpool_bwd(const void* dy, int dy_fp32, long long ldy, const void* relu_mask, int R, int HW,
+                               int C, void* dx, cudaStream_t stream) {
+  MTL_CHECK_ARG(dy && dx, "mtl_avgpool_bwd: null tensor");
+  CHECK_VEC8(C, "mtl_avgpool_bwd");
+  if (R == 0) return MTL_OK;
+  const long long total = (long long)R * HW * (C / 8);
+  const int grid = (int)min(ceil_div_ll(total, 256), (long long)mtl_num_sms() * 16);
+  if (dy_fp32)
+    avgpool_bwd_kernel<float><<<grid, 256, 0, stream>>>(reinterpret_cast<const float*>(dy), ldy,
+                                                        reinterpret_cast<const bf16*>(relu_mask), R, HW, C,
+                                                        reinterpret_cast<bf16*>(dx));
+  else
+    avgpool_bwd_kernel<bf16><<<grid, 256, 0, stream>>>(reinterpret_cast<const bf16*>(dy), ldy,
+                                                       reinterpret_cast<const bf16*>(relu_mask), R, HW, C,
+                                                       reinterpret_cast<bf16*>(dx));
+  MTL_CUDA_LAUNCH_CHECK("avgpool_bwd_kernel");
+  return MTL_OK;
+}
+
+extern "C" int mtl_im2col_f32(const float* img, int B, int H, int W, int C, int R, int S, int stride, int pad_h,
+                              int pad_w, int P, int Q, const float* mean, float scale, void* out, int ld,
+                              cudaStream_t stream) {
+  MTL_CHECK_ARG(img && out, "mtl_im2col_f32: null tensor");
+  MTL_CHECK_ARG(C >= 1 && C <= 4, "mtl_im2col_f32: 1..4 input channels (C=%d)", C);
+  MTL_CHECK_ARG(ld >= R * S * C && ld % 8 == 0, "mtl_im2col_f32: ld must be >= R*S*C and a multiple of 8");
+  float m[4] = {0, 0, 0, 0};
+  if (mean) for (int c = 0; c < C; ++c) m[c] = mean[c];
+  const long long warps = (long long)B * P * Q;
+  im2col_f32_kernel<<<(unsigned)ceil_div_ll(warps, 8), 256, 0, stream>>>(img, B, H, W, C, R, S, stride, pad_h, pad_w,
+                                                                        P, Q, m[0], m[1], m[2], m[3], scale,
+                                                                        reinterpret_cast<bf16*>(out), ld);
+  MTL_CUDA_LAUNCH_CHECK("im2col_f32_kernel");
+  return MTL_OK;
+}
+
+extern "C" int mtl_preprocess(const float* img, long long total, int C, const float* mean, float scale, float* out,
+                              cudaStream_t stream) {
+  MTL_CHECK_ARG(img && out && C >= 1 && C <= 4, "mtl_preprocess: bad args");
+  float m[4] = {0, 0, 0, 0};
+  if (mean) for (int c = 0; c < C; ++c) m[c] = mean[c];
+  const int grid = (int)min(ceil_div_ll(total, 256), (long long)mtl_num_sms() * 16);
+  preprocess_kernel<<<grid, 256, 0, stream>>>(img, total, C, m[0], m[1], m[2], m[3], scale, out);
+  MTL_CUDA_LAUNCH_CHECK("preprocess_kernel");
+  return MTL_OK;
+}
+
+extern "C" int mtl_psroi_fwd(const void* feat, int B, int H, int W, int D, int nby, int nbx, int crop_h, int crop_w,
+                             const float* boxes, const int* box_ind, int R, float* out, cudaStream_t stream) {
+  MTL_CHECK_ARG(feat && boxes && out, "mtl_psroi_fwd: null tensor");
+  MTL_CHECK_ARG(crop_h % nby == 0 && crop_w % nbx == 0, "mtl_psroi_fwd: crop size must be divisible by bins");
+  if (R == 0) return MTL_OK;
+  psroi_fwd_kernel<<<R, 128, 0, stream>>>(reinterpret_cast<const bf16*>(feat), H, W, D, nby, nbx, crop_h / nby,
+                                          crop_w / nbx, reinterpret_cast<const float4*>(boxes), box_ind, R, out);
+  MTL_CUDA_LAUNCH_CHECK("psroi_fwd_kernel");
+  (void)B;
+  return MTL_OK;
+}
+
+extern "C" int mtl_psroi_bwd(const float* dout, int B, int H, int W, int D, int nby, int nbx, int crop_h,
+                             int crop_w, const float* boxes, const int* box_ind, int R, float* dfeat,
+                             cudaStream_t stream) {
+  MTL_CHECK_ARG(dout && boxes && dfeat, "mtl_psroi_bwd: null tensor");
+  MTL_CHECK_ARG(crop_h % nby == 0 && crop_w % nbx == 0, "mtl_psroi_bwd: crop size must be divisible by bins");
+  if (R == 0) return MTL_OK;
+  psroi_bwd_kernel<<<R, 128, 0, stream>>>(dout, H, W, D, nby, nbx, crop_h / nby, crop_w / nbx,
+                                          reinterpret_cast<const float4*>(boxes), box_ind, R, dfeat);
+  MTL_CUDA_LAUNCH_CHECK("psroi_bwd_kernel");
+  (void)B;
+  return MTL_OK;
+}

@@ -1,0 +1,109 @@
+"""Layer objects with explicit forward / backward over the tcgen05 conv engine.
+
+A layer owns its parameters (in the ParamStore arena) and exposes
+  fwd(x, tag)        -> y            (activations live in the Workspace, keyed by scope+tag)
+  wgrad(x, dy)                        (accumulates into the fp32 gradient arena)
+  dgrad(dy, ...)     -> dx
+There is no autograd tape: the callers (nets/resnet_v1.py, the meta-architecture) sequence the
+backward pass explicitly, which is what lets one training step be a fixed list of kernel
+launches (CUDA-graph capturable).  Mirrors slim.conv2d + slim.batch_norm(is_training=False) +
+activation as configured by resnet_arg_scope (/root/reference/slim/nets/resnet_utils.py:203-256).
+"""
+import torch
+
+from .. import ops_conv as oc
+from .. import ops
+
+
+def same_pad(in_size, k, stride, rate=1):
+    """TensorFlow SAME padding: (out, pad_begin)."""
+    out = -(-in_size // stride)
+    ke = k + (k - 1) * (rate - 1)
+    total = max((out - 1) * stride + ke - in_size, 0)
+    return out, total // 2
+
+
+class Conv2d(object):
+    def __init__(self, store, scope, cin, cout, k=1, stride=1, rate=1, padding="SAME", bn=True, bias=False,
+                 relu=True, l2=1e-4, trainable=True, init=("variance_scaling",), bn_eps=1e-5, weight_name="weights"):
+        self.scope = scope
+        self.cin, self.cout, self.k, self.stride, self.rate = cin, cout, k, stride, rate
+        self.padding = padding          # "SAME" | "VALID" | "EXPLICIT" (resnet_utils.conv2d_same)
+        self.relu = relu
+        self.trainable = trainable
+        self.bn = store.add_bn(scope + "/BatchNorm", cout, bn_eps) if bn else None
+        self.weight = store.add(scope + "/" + weight_name, (cout, k, k, cin), l2=l2, trainable=trainable,
+                                init=init, fold=self.bn)
+        self.bias = store.add(scope + "/biases", (cout,), l2=0.0, trainable=trainable) if bias else None
+
+    # geometry -------------------------------------------------------------------------------
+    def geom(self, H, W):
+        k, s, r = self.k, self.stride, self.rate
+        if self.padding == "SAME":
+            P, ph = same_pad(H, k, s, r)
+            Q, pw = same_pad(W, k, s, r)
+        elif self.padding == "VALID":
+            ke = k + (k - 1) * (r - 1)
+            P, Q, ph, pw = (H - ke) // s + 1, (W - ke) // s + 1, 0, 0
+        else:   # conv2d_same with stride > 1: pad (ke-1)//2 before, rest after, then VALID
+            ke = k + (k - 1) * (r - 1)
+            ph = pw = (ke - 1) // 2
+            P, Q = (H + ke - 1 - ke) // s + 1, (W + ke - 1 - ke) // s + 1
+        return P, Q, ph, pw
+
+    def epilogue_bias(self):
+        if self.bn is not None:
+            return self.bn.bias
+        return self.bias.w if self.bias is not None else None
+
+    # kernels --------------------------------------------------------------------------------
+    def fwd(self, x, out, res=None, relu=None):
+        N, H, W, C = x.shape
+        P, Q, ph, pw = self.geom(H, W)
+        assert out.shape == (N, P, Q, self.cout), (out.shape, (N, P, Q, self.cout))
+        return oc.conv_fprop(x, self.weight.wb, self.stride, (ph, pw), self.rate, (P, Q),
+                             bias=self.epilogue_bias(), res=res, relu=self.relu if relu is None else relu,
+                             out=out)
+
+    def wgrad(self, x, dy):
+        if not self.trainable:
+            return
+        N, H, W, C = x.shape
+        P, Q, ph, pw = self.geom(H, W)
+        oc.conv_wgrad(dy, x, self.weight.g, self.stride, (ph, pw), self.rate,
+                      rowscale=self.bn.scale if self.bn is not None else None)
+        if self.bias is not None:
+            ops.call("mtl_colsum", dy, 0, self.cout, dy.numel() // self.cout, self.cout, 1.0, self.bias.g)
+
+    def dgrad(self, dy, x_shape, out, res=None, mask=None):
+        N, H, W, C = x_shape
+        P, Q, ph, pw = self.geom(H, W)
+        return oc.conv_dgrad(dy, self.weight.wb, x_shape, self.stride, (ph, pw), self.rate, res=res, mask=mask,
+                             out=out)
+
+
+def max_pool(x, out, k, stride, padding="SAME"):
+    N, H, W, C = x.shape
+    if padding == "SAME":
+        P, ph = same_pad(H, k, stride)
+        Q, pw = same_pad(W, k, stride)
+    else:
+        P, Q, ph, pw = (H - k) // stride + 1, (W - k) // stride + 1, 0, 0
+    assert out.shape == (N, P, Q, C)
+    ops.call("mtl_maxpool_fwd", x, N, H, W, C, k, stride, ph, pw, P, Q, out)
+    return out
+
+
+def max_pool_out_hw(H, W, k, stride, padding="SAME"):
+    if padding == "SAME":
+        return same_pad(H, k, stride)[0], same_pad(W, k, stride)[0]
+    return (H - k) // stride + 1, (W - k) // stride + 1
+
+
+def max_pool_bwd(x, dy, dx, k, stride, padding="SAME"):
+    N, H, W, C = x.shape
+    _, P, Q, _ = dy.shape
+    ph = same_pad(H, k, stride)[1] if padding == "SAME" else 0
+    pw = same_pad(W, k, stride)[1] if padding == "SAME" else 0
+    ops.call("mtl_maxpool_bwd", x, dy, N, H, W, C, k, stride, ph, pw, P, Q, dx)
+    return dx

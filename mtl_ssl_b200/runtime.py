@@ -1,0 +1,284 @@
+"""Device-memory runtime: one flat parameter arena, persistent activation workspaces, and the
+fused multi-tensor optimizer step.
+
+PyTorch is used here purely as an allocator / stream / NCCL front end.  Layout decisions
+(B200, 180 GB HBM3e): all fp32 master weights, gradients and momenta live in three arenas of
+identical layout, so that (a) the data-parallel gradient exchange is ONE NCCL all-reduce over
+one contiguous buffer (replacing the CPU `tf.add_n` of slim/deployment/model_deploy.py:414-444)
+and (b) the optimizer is two HBM-bound passes over contiguous memory.  A fourth arena holds the
+bf16 compute copy of every weight with the frozen batch-norm scale folded in.
+Variable names are the reference's TF variable names (scope strings of
+faster_rcnn_meta_arch.py:431-461) so checkpoint name maps stay valid.
+"""
+import ctypes
+import math
+
+import numpy as np
+import torch
+
+from . import ops
+
+ALIGN = 64
+
+
+class Param(object):
+    """One named tensor inside the arenas; `.w`/.g/.m are fp32 views, `.wb` the bf16 compute view."""
+
+    def __init__(self, name, shape, l2, trainable, init, fold=None, grad_mult=1.0):
+        self.name = name
+        self.shape = tuple(int(s) for s in shape)
+        self.numel = int(np.prod(self.shape))
+        self.l2 = float(l2)
+        self.trainable = bool(trainable)
+        self.init = init
+        self.fold = fold            # BatchNorm object whose scale is folded into the bf16 copy
+        self.grad_mult = grad_mult
+        self.offset = None
+        self.w = self.g = self.m = self.wb = None
+
+
+class BatchNorm(object):
+    """Frozen (inference-mode) slim.batch_norm: y = gamma * (x - mean) / sqrt(var + eps) + beta
+    (slim/nets/resnet_utils.py:229-256; is_training=False at fe:139).  Folded into the conv."""
+
+    def __init__(self, scope, channels, eps, scale=True):
+        self.scope = scope
+        self.channels = channels
+        self.eps = eps
+        self.has_gamma = scale
+        self.gamma = torch.ones(channels)
+        self.beta = torch.zeros(channels)
+        self.mean = torch.zeros(channels)
+        self.var = torch.ones(channels)
+        self.scale_off = None
+        self.scale = None           # device fp32 [K] view into fold_scales
+        self.bias = None            # device fp32 [K]
+
+    def fold_host(self):
+        s = self.gamma / torch.sqrt(self.var + self.eps)
+        return s.float(), (self.beta - self.mean * s).float()
+
+
+class ParamStore(object):
+    def __init__(self):
+        self.params = []
+        self.by_name = {}
+        self.groups = []            # lists of params laid out contiguously (fused GEMM operands)
+        self.bns = []
+        self.finalized = False
+
+    def add(self, name, shape, l2=0.0, trainable=True, init=("zeros",), fold=None, grad_mult=1.0):
+        assert not self.finalized
+        if name in self.by_name:
+            raise ValueError("duplicate variable %s" % name)
+        p = Param(name, shape, l2, trainable, init, fold, grad_mult)
+        self.params.append(p)
+        self.by_name[name] = p
+        self.groups.append([p])
+        return p
+
+    def add_group(self, specs):
+        """specs: list of dicts for add(); the tensors are packed back to back (no padding) so a
+        single GEMM can view them as one operand while the optimizer still clips each separately."""
+        ps = []
+        for s in specs:
+            p = self.add(**s)
+            self.groups.pop()
+            ps.append(p)
+        for p in ps[:-1]:
+            assert p.numel % 4 == 0, "grouped tensors must keep 16-byte alignment (%s)" % p.name
+        self.groups.append(ps)
+        return ps
+
+    def add_bn(self, scope, channels, eps, scale=True):
+        bn = BatchNorm(scope, channels, eps, scale)
+        self.bns.append(bn)
+        return bn
+
+    # ------------------------------------------------------------------ layout + allocation
+    def finalize(self, device, seed=0):
+        off = 0
+        for grp in self.groups:
+            off = (off + ALIGN - 1) // ALIGN * ALIGN
+            for p in grp:
+                p.offset = off
+                off += p.numel
+        self.total = (off + ALIGN - 1) // ALIGN * ALIGN
+        self.device = device
+        host = torch.zeros(self.total, dtype=torch.float32)
+        gen = torch.Generator().manual_seed(seed)
+        for p in self.params:
+            host[p.offset:p.offset + p.numel] = _init_tensor(p, gen).reshape(-1)
+        self.w = host.to(device)
+        self.g = torch.zeros(self.total, dtype=torch.float32, device=device)
+        self.m = torch.zeros(self.total, dtype=torch.float32, device=device)
+        self.wb = torch.zeros(self.total, dtype=torch.bfloat16, device=device)
+        for p in self.params:
+            sl = slice(p.offset, p.offset + p.numel)
+            p.w = self.w[sl].view(p.shape)
+            p.g = self.g[sl].view(p.shape)
+            p.m = self.m[sl].view(p.shape)
+            p.wb = self.wb[sl].view(p.shape)
+        self._upload_bn()
+        self._build_tables()
+        self.finalized = True
+        self.fold()
+        return self
+
+    def group_view(self, ps, rows, cols, arena="wb"):
+        """View a contiguous group as one [rows, cols] matrix (rows may include zero padding)."""
+        base = getattr(self, arena)
+        return base[ps[0].offset:ps[0].offset + rows * cols].view(rows, cols)
+
+    def _upload_bn(self):
+        n = sum(b.channels for b in self.bns)
+        scales = torch.ones(max(n, 1), dtype=torch.float32)
+        biases = torch.zeros(max(n, 1), dtype=torch.float32)
+        o = 0
+        for b in self.bns:
+            s, bi = b.fold_host()
+            scales[o:o + b.channels] = s
+            biases[o:o + b.channels] = bi
+            b.scale_off = o
+            o += b.channels
+        self.fold_scales = scales.to(self.device)
+        self.fold_biases = biases.to(self.device)
+        for b in self.bns:
+            b.scale = self.fold_scales[b.scale_off:b.scale_off + b.channels]
+            b.bias = self.fold_biases[b.scale_off:b.scale_off + b.channels]
+
+    def _build_tables(self):
+        chunk = ops.opt_chunk_size()
+        T = len(self.params)
+        td = (ops.TensorDesc * T)()
+        chunks = []
+        for i, p in enumerate(self.params):
+            td[i].offset = p.offset
+            td[i].numel = p.numel
+            if p.fold is not None:
+                td[i].row_len = p.numel // p.shape[0]
+                td[i].scale_off = p.fold.scale_off
+            else:
+                td[i].row_len = 0
+                td[i].scale_off = -1
+            td[i].l2_weight = p.l2
+            td[i].grad_mult = p.grad_mult
+            td[i].trainable = int(p.trainable)
+            for s in range(0, p.numel, chunk):
+                chunks.append((i, min(chunk, p.numel - s), s))
+        cd = (ops.ChunkDesc * len(chunks))()
+        for j, (t, ln, st) in enumerate(chunks):
+            cd[j].tensor, cd[j].len, cd[j].start = t, ln, st
+        self.num_tensors = T
+        self.num_chunks = len(chunks)
+        self.td = torch.frombuffer(bytearray(bytes(td)), dtype=torch.uint8).to(self.device)
+        self.cd = torch.frombuffer(bytearray(bytes(cd)), dtype=torch.uint8).to(self.device)
+        self.stats = torch.zeros(T * 2, dtype=torch.float32, device=self.device)
+        self.reg_loss = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self.hyper = torch.zeros(4, dtype=torch.float32, device=self.device)
+
+    # ------------------------------------------------------------------ kernels
+    def fold(self):
+        """(Re)build the bf16 compute copy from the fp32 masters (after init / load)."""
+        ops.call("mtl_opt_fold", self.td, self.cd, self.num_chunks, self.w, self.wb, self.fold_scales)
+
+    def stats_and_reg_loss(self, grad_scale=1.0):
+        ops.call("mtl_opt_stats", self.td, self.num_tensors, self.cd, self.num_chunks, self.w, self.g,
+                 grad_scale, self.stats, self.reg_loss)
+        return self.reg_loss
+
+    def apply(self, grad_scale=1.0):
+        ops.call("mtl_opt_apply", self.td, self.cd, self.num_chunks, self.w, self.g, self.m, self.wb,
+                 self.fold_scales, self.stats, self.hyper, grad_scale)
+
+    def set_hyper(self, lr, momentum, clip_norm):
+        self.hyper.copy_(torch.tensor([lr, momentum, clip_norm, 0.0], dtype=torch.float32))
+
+    # ------------------------------------------------------------------ host import / export
+    def state_dict(self):
+        """name -> fp32 CPU tensor (weights in this framework's [K,R,S,C] layout) + BN statistics."""
+        out = {}
+        for p in self.params:
+            out[p.name] = p.w.detach().cpu().clone()
+        for b in self.bns:
+            out[b.scope + "/gamma"] = b.gamma.clone()
+            out[b.scope + "/beta"] = b.beta.clone()
+            out[b.scope + "/moving_mean"] = b.mean.clone()
+            out[b.scope + "/moving_variance"] = b.var.clone()
+        return out
+
+    def load_state_dict(self, sd, strict=True):
+        missing = []
+        for p in self.params:
+            if p.name in sd:
+                p.w.copy_(sd[p.name].reshape(p.shape).to(self.device))
+            else:
+                missing.append(p.name)
+        for b in self.bns:
+            for attr, key in (("gamma", "gamma"), ("beta", "beta"), ("mean", "moving_mean"),
+                              ("var", "moving_variance")):
+                k = b.scope + "/" + key
+                if k in sd:
+                    setattr(b, attr, sd[k].clone().float())
+                else:
+                    missing.append(k)
+        if strict and missing:
+            raise KeyError("missing variables: %s" % missing[:8])
+        self._upload_bn_inplace()
+        self.fold()
+        return missing
+
+    def _upload_bn_inplace(self):
+        for b in self.bns:
+            s, bi = b.fold_host()
+            b.scale.copy_(s.to(self.device))
+            b.bias.copy_(bi.to(self.device))
+
+
+def _init_tensor(p, gen):
+    kind = p.init[0]
+    if kind == "zeros":
+        return torch.zeros(p.shape)
+    if kind == "const":
+        return torch.full(p.shape, float(p.init[1]))
+    if kind == "truncated_normal":          # tf.truncated_normal_initializer(stddev): resample |z| > 2
+        return _trunc_normal(p.shape, float(p.init[1]), gen)
+    if kind == "variance_scaling":
+        # slim.variance_scaling_initializer() defaults: factor 2.0, FAN_IN, truncated normal with
+        # stddev sqrt(1.3 * factor / fan_in) (tf.contrib.layers initializers.py)
+        fan_in = p.numel // p.shape[0]
+        return _trunc_normal(p.shape, math.sqrt(1.3 * 2.0 / fan_in), gen)
+    if kind == "normal":
+        return torch.randn(p.shape, generator=gen) * float(p.init[1])
+    raise ValueError(kind)
+
+
+def _trunc_normal(shape, std, gen):
+    t = torch.randn(shape, generator=gen)
+    bad = t.abs() > 2
+    while bad.any():
+        t[bad] = torch.randn(int(bad.sum()), generator=gen)
+        bad = t.abs() > 2
+    return t * std
+
+
+class Workspace(object):
+    """Persistent, shape-keyed device buffers: allocated on first use, reused every step, so a
+    whole training step issues no allocator calls and can be captured into one CUDA graph."""
+
+    def __init__(self, device):
+        self.device = device
+        self.bufs = {}
+
+    def get(self, key, shape, dtype=torch.bfloat16, zero=False):
+        shape = tuple(int(s) for s in shape)
+        t = self.bufs.get(key)
+        if t is None or t.shape != shape or t.dtype != dtype:
+            t = torch.zeros(shape, dtype=dtype, device=self.device)
+            self.bufs[key] = t
+        elif zero:
+            t.zero_()
+        return t
+
+    def nbytes(self):
+        return sum(t.numel() * t.element_size() for t in self.bufs.values())
