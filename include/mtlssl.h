@@ -130,6 +130,9 @@ int mtl_avgpool_bwd(const void* dy, int dy_fp32, long long ldy, const void* relu
 int mtl_im2col_f32(const float* img /* [B,H,W,C<=4] */, int B, int H, int W, int C, int R, int S, int stride,
                    int pad_h, int pad_w, int P, int Q, const float* mean /* host [C] or NULL */, float scale,
                    void* out /* bf16 [B*P*Q, ld] */, int ld, mtl_stream_t stream);
+/* core/preprocessor.py:1362-1419 resize_to_range -> tf.image.resize_images (bilinear). */
+int mtl_resize_bilinear_f32(const float* x, int B, int H, int W, int C, int out_h, int out_w, float* y,
+                            mtl_stream_t stream);
 int mtl_preprocess(const float* img, long long total, int C, const float* mean /* host */, float scale, float* out,
                    mtl_stream_t stream);
 int mtl_psroi_fwd(const void* feat /* bf16 [B,H,W,nby*nbx*D] */, int B, int H, int W, int D, int nby, int nbx,

@@ -61,7 +61,7 @@ opt_stats_kernel(const mtl_tensor_desc* __restrict__ td, const mtl_chunk_desc* _
   float sw = 0.0f, sg = 0.0f;
   const float gm = t.grad_mult * gscale;
   for (int i = threadIdx.x * 4; i < c.len; i += 256 * 4) {
-    if (i + 4 <= c.len) {
+    if (i + 4 <= c.len && (base & 3) == 0) {
       const float4 w = *reinterpret_cast<const float4*>(params + base + i);
       sw += w.x * w.x + w.y * w.y + w.z * w.z + w.w * w.w;
       if (t.trainable) {
@@ -71,7 +71,7 @@ opt_stats_kernel(const mtl_tensor_desc* __restrict__ td, const mtl_chunk_desc* _
         sg += a * a + b * b + cc * cc + d * d;
       }
     } else {
-      for (int e = i; e < c.len; ++e) {
+      for (int e = i; e < min(i + 4, c.len); ++e) {
         const float w = params[base + e];
         sw += w * w;
         if (t.trainable) {

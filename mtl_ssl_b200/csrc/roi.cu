@@ -385,6 +385,32 @@ psroi_bwd_kernel(const float* __restrict__ dout, int H, int W, int D, int nby, i
   }
 }
 
+// ------------------------------------------------------------------ image resize (preprocessing)
+// tf.image.resize_images(BILINEAR, align_corners=False) of TF 1.7: src = dst * in/out,
+// lower = floor(src), upper = min(lower + 1, in - 1)  (core/kernels/resize_bilinear_op.cc).
+__global__ void resize_bilinear_f32_kernel(const float* __restrict__ x, int B, int H, int W, int C, int oh, int ow,
+                                           float* __restrict__ y) {
+  const long long total = (long long)B * oh * ow * C;
+  const float sy = (float)H / (float)oh, sx = (float)W / (float)ow;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(t % C);
+    const long long pix = t / C;
+    const int ox = (int)(pix % ow);
+    const int oy = (int)((pix / ow) % oh);
+    const int b = (int)(pix / ((long long)oh * ow));
+    const float in_y = (float)oy * sy, in_x = (float)ox * sx;
+    const int y0 = (int)floorf(in_y), x0 = (int)floorf(in_x);
+    const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
+    const float yl = in_y - (float)y0, xl = in_x - (float)x0;
+    const float* base = x + (long long)b * H * W * C + c;
+    const float tl = base[((long long)y0 * W + x0) * C], tr = base[((long long)y0 * W + x1) * C];
+    const float bl = base[((long long)y1 * W + x0) * C], br = base[((long long)y1 * W + x1) * C];
+    const float top = tl + (tr - tl) * xl, bot = bl + (br - bl) * xl;
+    y[t] = top + (bot - top) * yl;
+  }
+}
+
 }  // namespace
 
 // ===================================================================================== C ABI
@@ -524,5 +550,15 @@ extern "C" int mtl_psroi_bwd(const float* dout, int B, int H, int W, int D, int 
                                           reinterpret_cast<const float4*>(boxes), box_ind, R, dfeat);
   MTL_CUDA_LAUNCH_CHECK("psroi_bwd_kernel");
   (void)B;
+  return MTL_OK;
+}
+
+extern "C" int mtl_resize_bilinear_f32(const float* x, int B, int H, int W, int C, int out_h, int out_w, float* y,
+                                       cudaStream_t stream) {
+  MTL_CHECK_ARG(x && y && out_h > 0 && out_w > 0, "mtl_resize_bilinear_f32: bad args");
+  const long long total = (long long)B * out_h * out_w * C;
+  const int grid = (int)min(ceil_div_ll(total, 256), (long long)mtl_num_sms() * 16);
+  resize_bilinear_f32_kernel<<<grid, 256, 0, stream>>>(x, B, H, W, C, out_h, out_w, y);
+  MTL_CUDA_LAUNCH_CHECK("resize_bilinear_f32_kernel");
   return MTL_OK;
 }

@@ -42,7 +42,7 @@ class Bottleneck(object):
         P, Q, _, _ = self.conv2.geom(H, W)
         return P, Q
 
-    def fwd(self, x, ws, tag, keep=True):
+    def fwd(self, x, ws, tag, keep=True, parity=0):
         """keep=False: forward-only pass, intermediates share scratch buffers across units."""
         N, H, W, C = x.shape
         P, Q = self.out_hw(H, W)
@@ -56,7 +56,7 @@ class Bottleneck(object):
             sc = max_pool(x, ws.get(key + "/sc", (N, P, Q, self.depth)), 1, self.stride)
         r1 = self.conv1.fwd(x, ws.get(key + "/r1", (N, H, W, db)))
         r2 = self.conv2.fwd(r1, ws.get(key + "/r2", (N, P, Q, db)))
-        okey = (self.scope + "/" + tag + "/out") if keep else ("scratch/" + tag + "/out%d" % (id(self) % 2))
+        okey = (self.scope + "/" + tag + "/out") if keep else ("scratch/" + tag + "/out%d" % parity)
         out = self.conv3.fwd(r2, ws.get(okey, (N, P, Q, self.depth)), res=sc, relu=True)
         if keep:
             self.saved = getattr(self, "saved", {})
@@ -102,6 +102,10 @@ class Stem(object):
         # [64, 160] is packed in the bf16 arena by pack()
         self.weight = store.add(scope + "/conv1/weights", (64, 7, 7, 3), l2=l2, trainable=False,
                                 init=("variance_scaling",), fold=self.bn)
+        self.packed = None
+        store.post_load_hooks.append(self.invalidate)
+
+    def invalidate(self):
         self.packed = None
 
     def pack(self, device):
@@ -183,8 +187,8 @@ class Block4(object):
         self.out_channels = 2048
 
     def fwd(self, x, ws, tag, keep=True):
-        for u in self.units:
-            x = u.fwd(x, ws, tag, keep)
+        for i, u in enumerate(self.units):
+            x = u.fwd(x, ws, tag, keep, i % 2)
         return x
 
     def bwd(self, g, ws, tag, need_dx=True, dx_extra=None):

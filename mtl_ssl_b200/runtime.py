@@ -66,6 +66,7 @@ class ParamStore(object):
         self.groups = []            # lists of params laid out contiguously (fused GEMM operands)
         self.bns = []
         self.finalized = False
+        self.post_load_hooks = []   # callables run after weights change outside the optimizer
 
     def add(self, name, shape, l2=0.0, trainable=True, init=("zeros",), fold=None, grad_mult=1.0):
         assert not self.finalized
@@ -85,8 +86,6 @@ class ParamStore(object):
             p = self.add(**s)
             self.groups.pop()
             ps.append(p)
-        for p in ps[:-1]:
-            assert p.numel % 4 == 0, "grouped tensors must keep 16-byte alignment (%s)" % p.name
         self.groups.append(ps)
         return ps
 
@@ -226,6 +225,8 @@ class ParamStore(object):
             raise KeyError("missing variables: %s" % missing[:8])
         self._upload_bn_inplace()
         self.fold()
+        for h in self.post_load_hooks:
+            h()
         return missing
 
     def _upload_bn_inplace(self):

@@ -1,0 +1,200 @@
+"""One synchronous data-parallel training step on B200s.
+
+Replaces the per-clone loss graph + optimizer of /root/reference/object_detection/trainer.py:157-214
+(`_create_losses`), :379-429 (gradient post-processing + apply) and the clone deployment of
+slim/deployment/model_deploy.py:143-307: one process per GPU; every rank runs forward, loss and the
+explicit backward on its shard of the batch, ONE NCCL all-reduce sums the flat gradient arena
+(replacing the CPU `tf.add_n`, model_deploy.py:414-444), then every rank applies the identical
+per-tensor-clip + momentum update.  Loss scaling follows the reference: task losses / num_replicas,
+L2 regularisation once (model_deploy.py:221-225, :296).
+
+The step is a fixed list of kernel launches over persistent buffers; after a warm-up it is
+captured into CUDA graphs (forward+backward, optimizer) and replayed, so the ~2000 launches cost
+no Python time.  Inputs arrive through pinned host staging buffers (one H2D per step); the only
+D2H is the 9-float loss vector.
+"""
+import numpy as np
+import torch
+
+from .meta_architectures.faster_rcnn_meta_arch import LOSS_KEYS
+from .utils import learning_schedules
+
+
+def pack_groundtruth(examples, num_classes, height, width, gmax):
+    """Host-side packing of a list of examples (data/synthetic.py format) into fixed-shape arrays:
+    boxes normalised -> absolute float32 (fmA:1218-1266), class index with background 0."""
+    B, K1 = len(examples), num_classes + 1
+    out = dict(gt=np.zeros((B, gmax, 4), np.float32), num_gt=np.zeros((B,), np.int32),
+               gt_cls=np.zeros((B, gmax), np.int32), gt_close=np.zeros((B, gmax, K1), np.float32))
+    scale = np.array([height, width, height, width], np.float32)
+    for b, ex in enumerate(examples):
+        bx = np.asarray(ex["groundtruth_boxes"], np.float32).reshape(-1, 4)
+        g = bx.shape[0]
+        if g > gmax:
+            raise ValueError("image has %d groundtruth boxes, static limit is %d" % (g, gmax))
+        if g and bx.max() > 1.01:
+            raise ValueError("maximum box coordinate value is larger than 1.01")
+        out["num_gt"][b] = g
+        out["gt"][b, :g] = bx * scale
+        oh = np.asarray(ex["groundtruth_classes"], np.float32).reshape(g, -1)
+        if g:
+            if not np.all((oh.sum(1) == 1) & (oh.max(1) == 1)):
+                raise ValueError("groundtruth classes must be one-hot on the B200 path")
+            out["gt_cls"][b, :g] = oh.argmax(1) + 1
+        cl = ex.get("groundtruth_closeness")
+        if cl is not None and g:
+            out["gt_close"][b, :g] = np.asarray(cl, np.float32).reshape(g, K1)
+    if examples and examples[0].get("window_boxes") is not None:
+        out["win_boxes"] = np.stack([np.asarray(e["window_boxes"], np.float32).reshape(-1, 4) for e in examples])
+        out["win_cls"] = np.stack([np.asarray(e["window_classes"], np.float32).reshape(-1, K1) for e in examples])
+    if examples and examples[0].get("groundtruth_edgemask") is not None:
+        out["edgemask"] = np.stack([np.asarray(e["groundtruth_edgemask"], np.float32) for e in examples])
+    return out
+
+
+class StaticInputs(object):
+    """Pinned host staging + device buffers of fixed shape; `load()` is the step's only H2D."""
+
+    def __init__(self, device, arrays):
+        self.host, self.dev = {}, {}
+        for k, a in arrays.items():
+            t = torch.from_numpy(np.ascontiguousarray(a))
+            self.host[k] = t.pin_memory() if torch.cuda.is_available() else t
+            self.dev[k] = torch.empty_like(t, device=device)
+        self.nbytes = sum(t.numel() * t.element_size() for t in self.host.values())
+
+    def load(self, arrays):
+        for k, a in arrays.items():
+            self.host[k].copy_(torch.from_numpy(np.ascontiguousarray(a)))
+            self.dev[k].copy_(self.host[k], non_blocking=True)
+
+
+class Trainer(object):
+    def __init__(self, model, train_config=None, height=600, width=1000, batch_size=1, gmax=64,
+                 use_cuda_graph=True, world_size=1, process_group=None, learning_rate=None, momentum=0.9,
+                 clip_norm=10.0):
+        self.model = model
+        self.H, self.W, self.B = height, width, batch_size
+        self.gmax = gmax
+        self.world_size = world_size
+        self.pg = process_group
+        self.use_graph = use_cuda_graph
+        self.global_step = 0
+        self.device = model.device
+        if train_config is not None:
+            self.lr_fn, momentum = learning_schedules.from_optimizer_config(train_config.optimizer)
+            clip_norm = train_config.gradient_clipping_by_norm
+        else:
+            lr = 0.001 if learning_rate is None else learning_rate
+            self.lr_fn = lambda step: lr
+        self.momentum, self.clip_norm = momentum, clip_norm
+        self._hyper_host = torch.zeros(4).pin_memory() if torch.cuda.is_available() else torch.zeros(4)
+        self.inputs = None
+        self.graph_fb = None
+        self.graph_opt = None
+        self._loss_host = (torch.zeros(9).pin_memory() if torch.cuda.is_available() else torch.zeros(9))
+        self._loss_dev = torch.zeros(9, device=self.device)
+        self.launches_per_step = None
+
+    # ------------------------------------------------------------------ one step
+    def _bind(self, arrays):
+        if self.inputs is None:
+            self.inputs = StaticInputs(self.device, arrays)
+        self.inputs.load(arrays)
+        d = self.inputs.dev
+        m = self.model
+        gt = dict(gt=d["gt"], num_gt=d["num_gt"], gt_cls=d["gt_cls"], gt_close=d["gt_close"], gmax=self.gmax,
+                  B=self.B)
+        for k in ("win_boxes", "win_cls", "edgemask"):
+            if k in d:
+                gt[k] = d[k]
+        m._gt, m._gt_shape, m._groundtruth_dirty = gt, (self.B, self.H, self.W, 3), False
+        m.provide_sampler_keys(d["keys1"], d["keys2"])
+        return d["image"]
+
+    def _forward_backward(self, image):
+        m = self.model
+        mtl = m._mtl
+        pd = m.predict(m.preprocess(image))
+        if mtl is not None and mtl.window:
+            pd = m.predict_with_window(pd)
+        if mtl is not None and mtl.edgemask:
+            pd = m.predict_edgemask(pd)
+        if mtl is not None and mtl.refine:
+            pd = m.predict_with_mtl_results(pd)
+        m.loss(pd)
+        m.backward(pd)
+        return pd
+
+    def _optimize(self):
+        st = self.model.param_store
+        gs = 1.0 / self.world_size
+        st.stats_and_reg_loss(gs)
+        st.apply(gs)
+        self._loss_dev[:8].copy_(self.model.workspace.bufs["loss/values"])
+        self._loss_dev[8:9].copy_(st.reg_loss)
+
+    def _allreduce(self):
+        if self.world_size > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.model.param_store.g, op=dist.ReduceOp.SUM, group=self.pg)
+
+    def host_arrays(self, examples, keys):
+        arrays = pack_groundtruth(examples, self.model.num_classes, self.H, self.W, self.gmax)
+        arrays["image"] = np.stack([e["image"] for e in examples]).astype(np.float32)
+        arrays["keys1"], arrays["keys2"] = keys
+        return arrays
+
+    def step(self, arrays, read_losses=True):
+        """arrays: output of host_arrays().  Returns {loss name: float} (+ 'regularization_loss',
+        'total_loss') when read_losses."""
+        st = self.model.param_store
+        self._hyper_host[0] = float(self.lr_fn(self.global_step))
+        self._hyper_host[1] = self.momentum
+        self._hyper_host[2] = self.clip_norm if self.clip_norm else 0.0
+        st.hyper.copy_(self._hyper_host, non_blocking=True)
+        image = self._bind(arrays)
+        if not self.use_graph:
+            self._forward_backward(image)
+            self._allreduce()
+            self._optimize()
+        elif self.graph_fb is None:
+            self._capture(image)
+            self.graph_fb.replay()
+            self._allreduce()
+            self.graph_opt.replay()
+        else:
+            self.graph_fb.replay()
+            self._allreduce()
+            self.graph_opt.replay()
+        self.global_step += 1
+        if not read_losses:
+            return None
+        self._loss_host.copy_(self._loss_dev, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return self.losses_from_host()
+
+    def losses_from_host(self):
+        v = self._loss_host.tolist()
+        out = {k: v[i] for i, k in enumerate(LOSS_KEYS)}
+        out["regularization_loss"] = v[8]
+        # model_deploy.py:198-236: sum of task losses / num_clones + regularisation
+        out["total_loss"] = sum(v[:8]) + v[8]
+        return out
+
+    def _capture(self, image):
+        """Warm up eagerly (allocates every workspace buffer, fills the anchor cache), then capture."""
+        st = self.model.param_store
+        snap = (st.w.clone(), st.m.clone(), st.wb.clone())
+        for _ in range(2):
+            self._forward_backward(image)
+            st.g.zero_()
+        st.w.copy_(snap[0]); st.m.copy_(snap[1]); st.wb.copy_(snap[2])
+        torch.cuda.synchronize()
+        self.graph_fb = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph_fb):
+            self._forward_backward(image)
+        self.graph_opt = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph_opt):
+            self._optimize()
+        torch.cuda.synchronize()

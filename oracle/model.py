@@ -1,0 +1,321 @@
+"""Oracle (TEST INFRASTRUCTURE): CPU fp32 restatement of one Faster R-CNN + aux-heads training
+step of the reference, with torch autograd supplying the reference gradients.
+
+Follows, line by line where cited:
+  object_detection/meta_architectures/faster_rcnn_meta_arch.py  predict :507-719,
+      predict_with_window :721-755, predict_edgemask :757-762, predict_with_mtl_results :764-846,
+      _postprocess_rpn :1055-1132, _unpad_proposals_and_sample_box_classifier_batch :1134-1216,
+      _sample_box_classifier_minibatch :1268-1302, _compute_second_stage_input_feature_maps
+      :1304-1348, loss :1514-1590, _loss_rpn :1591-1668, _loss_box_classifier :1670-1793,
+      _loss_refined_classifier :1795-1837, _loss_window_class :1839-1858, _loss_edgemask :1860-1881
+  slim/nets/resnet_v1.py :69-130, :133-237; slim/nets/resnet_utils.py :59-200
+  object_detection/models/faster_rcnn_resnet_v1_feature_extractor.py :74-185
+  object_detection/core/box_predictor.py :430-611, :682-755; core/mask_predictor.py :90-119
+  slim/deployment/model_deploy.py :198-307 (total loss = task losses + L2 terms)
+The reference cannot run here (Python 2 + TF 1.7); TF kernels are restated in oracle/nn.py.
+The aux heads / refine / closeness have no reference tests: parity unpinned.
+
+Weights come as a dict {TF variable name: tensor}, conv / FC weights in [K, R, S, C] layout
+(TF's HWIO transposed).  `bf16=True` mirrors the device path's rounding points (weights with the
+folded BN scale, and every activation tensor the device stores in bf16) with straight-through
+gradients, so that losses can be compared tightly; `bf16=False` is the plain fp32 reference.
+"""
+import numpy as np
+import torch
+import torch.nn.functional as TF
+
+from . import assign as OA
+from . import boxes as OB
+from . import nn as ON
+from . import postprocess as OP
+
+BLOCKS = {
+    "resnet_v1_50": [("block1", 256, 64, 3, 2), ("block2", 512, 128, 4, 2), ("block3", 1024, 256, 6, 2)],
+    "resnet_v1_101": [("block1", 256, 64, 3, 2), ("block2", 512, 128, 4, 2), ("block3", 1024, 256, 23, 2)],
+    "resnet_v1_152": [("block1", 256, 64, 3, 2), ("block2", 512, 128, 8, 2), ("block3", 1024, 256, 36, 2)],
+}
+
+
+class _RoundBF16(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return x.to(torch.bfloat16).to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+class Oracle(object):
+    def __init__(self, params, cfg, bf16=True):
+        """params: {name: fp32 tensor} (leaf tensors get requires_grad for trainable names);
+        cfg: dict with the model hyper-parameters (see tests/helpers.py: oracle_config)."""
+        self.cfg = cfg
+        self.bf16 = bf16
+        self.p = {}
+        for k, v in params.items():
+            t = v.detach().clone().float()
+            self.p[k] = t
+        self.arch = cfg["architecture"]
+
+    def rb(self, x):
+        return _RoundBF16.apply(x) if self.bf16 else x
+
+    def require_grad(self, names):
+        for n in names:
+            self.p[n].requires_grad_(True)
+
+    # ------------------------------------------------------------------ layers
+    def conv(self, x, scope, stride=1, rate=1, padding="SAME", bn=True, relu=True, res=None, out_round=True):
+        w = self.p[scope + "/weights"]                       # [K,R,S,C]
+        if bn:
+            eps = 1e-5
+            s = self.p[scope + "/BatchNorm/gamma"] / torch.sqrt(self.p[scope + "/BatchNorm/moving_variance"] + eps)
+            bias = self.p[scope + "/BatchNorm/beta"] - self.p[scope + "/BatchNorm/moving_mean"] * s
+            w = w * s[:, None, None, None]
+        else:
+            bias = self.p.get(scope + "/biases")
+        w = self.rb(w)
+        whwio = w.permute(1, 2, 3, 0)
+        if padding == "EXPLICIT":
+            y = ON.conv2d_same(x, whwio, stride, rate)
+        else:
+            y = ON.conv2d_tf(x, whwio, stride, padding, rate)
+        if bias is not None:
+            y = y + bias
+        if res is not None:
+            y = y + res
+        if relu:
+            y = torch.relu(y)
+        return self.rb(y) if out_round else y
+
+    def bottleneck(self, x, scope, depth, stride, rate=1):
+        s = scope + "/bottleneck_v1"
+        cin = x.shape[-1]
+        if depth == cin:
+            sc = x if stride == 1 else ON.max_pool_tf(x, 1, stride)          # resnet_utils.subsample
+        else:
+            sc = self.conv(x, s + "/shortcut", stride, relu=False)
+        r = self.conv(x, s + "/conv1")
+        r = self.conv(r, s + "/conv2", stride, rate, padding="SAME" if stride == 1 else "EXPLICIT")
+        return self._unit_out(r, s, sc)
+
+    def _unit_out(self, r, s, sc):
+        # conv3 (no activation) + shortcut -> relu; the device fuses add+relu in the conv3 epilogue
+        w_scope = s + "/conv3"
+        y = self.conv(r, w_scope, relu=False, res=sc, out_round=False)
+        return self.rb(torch.relu(y))
+
+    def trunk(self, img, scope):
+        """fe:92-146 with output_stride 16."""
+        means = torch.tensor(self.cfg.get("means", [123.68, 116.779, 103.939]))
+        x = self.rb(img - means)
+        x = self.conv(x, scope + "/conv1", 2, padding="EXPLICIT")
+        x = ON.max_pool_tf(x, 3, 2, "SAME")
+        current_stride, rate = 4, 1
+        for bname, depth, db, n, bstride in BLOCKS[self.arch]:
+            for u in range(n):
+                stride = bstride if u == n - 1 else 1
+                us = "%s/%s/unit_%d" % (scope, bname, u + 1)
+                if current_stride == 16:
+                    x = self.bottleneck(x, us, depth, 1, rate)
+                    rate *= stride
+                else:
+                    x = self.bottleneck(x, us, depth, stride, 1)
+                    current_stride *= stride
+        return x
+
+    def block4(self, x, scope):
+        for u in range(3):
+            x = self.bottleneck(x, "%s/block4/unit_%d" % (scope, u + 1), 2048, 1)
+        return x
+
+    def head(self, feats, scope, names):
+        """MaskRCNNBoxPredictor: spatial average -> FC(s) (bp:470-500, :568-602)."""
+        pooled = self.rb(feats.mean(dim=(1, 2)))
+        outs = []
+        for n in names:
+            w = self.rb(self.p["%s/%s/weights" % (scope, n)].reshape(-1, pooled.shape[1]))
+            outs.append(pooled @ w.t() + self.p["%s/%s/biases" % (scope, n)])
+        return outs
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, images, examples, keys, H, W):
+        cfg, p = self.cfg, self.p
+        B = images.shape[0]
+        K = cfg["num_classes"]
+        K1 = K + 1
+        A = len(cfg["scales"]) * len(cfg["aspect_ratios"])
+        fs = "FirstStageFeatureExtractor/" + self.arch
+        feat = self.trunk(images, fs)
+        _, Hf, Wf, _ = feat.shape
+        rpn_feat = self.conv(feat, "FirstStageBoxPredictor/Conv", bn=False, relu=True)
+        box = self.conv(rpn_feat, "FirstStageBoxPredictor/BoxEncodingPredictor", bn=False, relu=False, out_round=False)
+        cls = self.conv(rpn_feat, "FirstStageBoxPredictor/ClassPredictor", bn=False, relu=False, out_round=False)
+        box = box.reshape(B, Hf * Wf * A, 4)
+        cls = cls.reshape(B, Hf * Wf * A, 2)
+        anchors_all = OB.grid_anchors(Hf, Wf, cfg["scales"], cfg["aspect_ratios"], (256, 256), (16, 16), (0, 0))
+        anchors, keep = OB.prune_outside_window(anchors_all, (0, 0, H, W))        # fmA:930-976
+        keep_t = torch.from_numpy(keep).long()
+        rpn_box, rpn_cls = box[:, keep_t], cls[:, keep_t]
+        P, M = cfg["second_stage_batch_size"], cfg["first_stage_max_proposals"]
+        # ---- _postprocess_rpn + minibatch sampling (no gradient: fmA:1109-1110)
+        gts = []
+        prop_norm = np.zeros((B, P, 4), np.float32)
+        prop_abs = np.zeros((B, P, 4), np.float32)
+        nprop = np.zeros((B,), np.int64)
+        nms_out = []
+        for b in range(B):
+            ex = examples[b]
+            gt_abs = OB.to_absolute_coordinates(np.asarray(ex["groundtruth_boxes"], np.float32).reshape(-1, 4), H, W)
+            oh = np.asarray(ex["groundtruth_classes"], np.float32)
+            gt_cls_bg = np.concatenate([np.zeros((len(oh), 1), np.float32), oh], 1)
+            gts.append((gt_abs, gt_cls_bg, np.asarray(ex["groundtruth_closeness"], np.float32)))
+            pb, ps, n = OP.rpn_postprocess_single(rpn_box[b].detach().numpy(), rpn_cls[b].detach().numpy(), anchors,
+                                                  (H, W), cfg["nms_score_threshold"], cfg["nms_iou_threshold"], M)
+            nms_out.append((pb, ps, n))
+            t = OA.assign_detection(pb[:n], gt_abs, gt_cls_bg)
+            pos = t["cls_targets"].argmax(1) > 0
+            sel = OA.balanced_subsample(t["cls_weights"] > 0, P, pos, cfg["second_stage_balance_fraction"],
+                                        keys[1][b][:n])
+            idx = np.nonzero(sel)[0][:P]
+            nprop[b] = len(idx)
+            nb = OB.to_normalized_coordinates(pb[idx], H, W)
+            prop_norm[b, :len(idx)] = nb
+            prop_abs[b, :len(idx)] = OB.to_absolute_coordinates(nb, H, W)          # fmA:682-683
+        c = cfg["initial_crop_size"]
+        mk = cfg["maxpool_kernel_size"]
+
+        def crops_of(boxes_flat, box_ind):
+            cr = self.rb(ON.crop_and_resize(feat, torch.from_numpy(boxes_flat), torch.from_numpy(box_ind), (c, c)))
+            return ON.max_pool_tf(cr, mk, mk, "VALID") if mk > 1 else cr
+
+        bi = np.repeat(np.arange(B), P).astype(np.int64)
+        maps = crops_of(prop_norm.reshape(-1, 4), bi)
+        out = dict(feat=feat, rpn_box=rpn_box, rpn_cls=rpn_cls, anchors=anchors, keep=keep, prop_norm=prop_norm,
+                   prop_abs=prop_abs, nprop=nprop, gts=gts, nms=nms_out)
+        bx, cl = self.head(self.block4(maps, "SecondStageFeatureExtractor/" + self.arch), "SecondStageBoxPredictor",
+                           ["BoxEncodingPredictor", "ClassPredictor"])
+        out["refined_box_encodings"] = bx.reshape(B * P, K, 4)
+        out["class_predictions_with_background"] = cl
+        mtl = cfg["mtl"]
+        stop = mtl.get("stop_gradient_for_aux_tasks", False)
+        if mtl.get("closeness"):
+            m2 = maps.detach() if stop else maps
+            out["closeness_predictions"] = self.head(self.block4(m2, "ClosenessBoxPredictor/" + self.arch),
+                                                     "ClosenessBoxPredictor", ["ClassPredictor"])[0]
+        if mtl.get("window"):
+            wb = np.stack([np.asarray(e["window_boxes"], np.float32) for e in examples])
+            nw = wb.shape[1]
+            wm = crops_of(wb.reshape(-1, 4), np.repeat(np.arange(B), nw).astype(np.int64))
+            if stop:
+                wm = wm.detach()
+            out["window_class_predictions"] = self.head(self.block4(wm, "WindowBoxPredictor/" + self.arch),
+                                                        "WindowBoxPredictor", ["ClassPredictor"])[0]
+        if mtl.get("edgemask"):
+            w = p["EdgeMaskPredictor/BoxEncodingPredictor/weights"].reshape(2, -1)
+            out["edgemask_predictions"] = torch.tanh(feat @ w.t() + p["EdgeMaskPredictor/BoxEncodingPredictor/biases"])
+        if mtl.get("refine"):
+            src = [cl]
+            if mtl.get("window"):
+                pn = prop_norm                                              # fmA:783-803
+                ymin, xmin, ymax, xmax = [pn[..., i] for i in range(4)]
+                F32 = np.float32
+                exp = []
+                for e in range(5):
+                    exp.append(np.stack([ymin - (ymin / F32(4)) * F32(e), xmin - (xmin / F32(4)) * F32(e),
+                                         ymax + ((F32(1) - ymax) / F32(4)) * F32(e),
+                                         xmax + ((F32(1) - xmax) / F32(4)) * F32(e)], -1).astype(F32))
+                exp = np.stack(exp)                                         # [5,B,P,4]
+                ebi = np.broadcast_to(np.arange(B)[None, :, None], (5, B, P)).reshape(-1).astype(np.int64)
+                with torch.no_grad():
+                    em = crops_of(exp.reshape(-1, 4), ebi)
+                    ew = self.head(self.block4(em, "WindowBoxPredictor/" + self.arch), "WindowBoxPredictor",
+                                   ["ClassPredictor"])[0]
+                src.append(ew.reshape(5, B * P, K1).permute(1, 0, 2).reshape(B * P, 5 * K1))
+            if mtl.get("closeness"):
+                cm = out["closeness_predictions"].detach().mean(0, keepdim=True)
+                src.append(cm.expand(B * P, K1))
+            net = torch.cat([s.detach() for s in src], 1)
+            ref = net @ p["MTLClassRefiner/fc1/weights"].t() + p["MTLClassRefiner/fc1/biases"]
+            if mtl.get("refine_residue"):
+                ref = ref + cl
+            out["mtl_refined_class_predictions_with_background"] = ref
+            out["refine_in"] = net
+        return out
+
+    # ------------------------------------------------------------------ losses
+    def loss(self, out, examples, keys, H, W):
+        cfg, mtl = self.cfg, self.cfg["mtl"]
+        B = len(examples)
+        K = cfg["num_classes"]
+        K1 = K + 1
+        P = cfg["second_stage_batch_size"]
+        anchors = out["anchors"]
+        losses = {}
+        loc_l = obj_l = 0.0
+        for b in range(B):                                                   # _loss_rpn
+            t = OA.assign_proposal(anchors, out["gts"][b][0])
+            s = OA.balanced_subsample(t["cls_weights"] > 0, cfg["first_stage_minibatch_size"],
+                                      t["cls_targets"][:, 0] > 0, cfg["first_stage_positive_balance_fraction"],
+                                      keys[0][b])
+            sf = torch.from_numpy(s.astype(np.float32))
+            norm = sf.sum()
+            loc = ON.smooth_l1(out["rpn_box"][b], torch.from_numpy(t["reg_targets"]),
+                               sf * torch.from_numpy(t["reg_weights"]), 3.0)
+            onehot = TF.one_hot(torch.from_numpy(t["cls_targets"][:, 0]).long(), 2).float()
+            obj = ON.softmax_ce(out["rpn_cls"][b], onehot, sf)
+            loc_l = loc_l + loc.sum() / norm
+            obj_l = obj_l + obj.sum() / norm
+        losses["first_stage_localization_loss"] = cfg["first_stage_localization_loss_weight"] * loc_l / B
+        losses["first_stage_objectness_loss"] = cfg["first_stage_objectness_loss_weight"] * obj_l / B
+        # _loss_box_classifier
+        cls_t, reg_t, reg_w, cls_w, close_t = [], [], [], [], []
+        for b in range(B):
+            gt_abs, gt_cls_bg, gt_close = out["gts"][b]
+            t = OA.assign_detection(out["prop_abs"][b], gt_abs, gt_cls_bg, gt_close)
+            cls_t.append(t["cls_targets"]); reg_t.append(t["reg_targets"]); reg_w.append(t["reg_weights"])
+            cls_w.append(t["cls_weights"]); close_t.append(t["closeness_targets"])
+        cls_t = torch.from_numpy(np.stack(cls_t)); reg_t = torch.from_numpy(np.stack(reg_t))
+        reg_w = torch.from_numpy(np.stack(reg_w)); cls_w = torch.from_numpy(np.stack(cls_w))
+        close_t = torch.from_numpy(np.stack(close_t))
+        nprop = torch.from_numpy(out["nprop"])
+        pad = (torch.arange(P)[None, :] < nprop[:, None]).float()
+        norm = (nprop.clamp(min=1).float() * B)[:, None].expand(B, P)
+        enc_bg = torch.cat([torch.zeros(B * P, 1, 4), out["refined_box_encodings"]], 1)
+        flat_t = cls_t.reshape(B * P, K1)
+        sel = enc_bg[flat_t > 0].reshape(B, P, 4)                           # boolean_mask (one-hot, T12)
+        loc = ON.smooth_l1(sel, reg_t, reg_w, 1.0) / norm
+        cl = ON.softmax_ce(out["class_predictions_with_background"].reshape(B, P, K1), cls_t, cls_w) / norm
+        losses["second_stage_localization_loss"] = cfg["second_stage_localization_loss_weight"] * (loc * pad).sum()
+        losses["second_stage_classification_loss"] = cfg["second_stage_classification_loss_weight"] * (cl * pad).sum()
+        if mtl.get("closeness"):
+            norm_reg = reg_w.sum(1, keepdim=True).clamp(min=1.0)
+            cp = out["closeness_predictions"].reshape(B, P, K1)[:, :, 1:]
+            ct = close_t[:, :, 1:]
+            closs = ON.softmax_ce(cp, ct, reg_w) / norm_reg * ct.sum(2)
+            losses["closeness_classification_loss"] = mtl["closeness_loss_weight"] * closs.sum()
+        if mtl.get("window"):
+            wc = torch.from_numpy(np.stack([np.asarray(e["window_classes"], np.float32) for e in examples]))
+            wl = ON.softmax_ce(out["window_class_predictions"], wc.reshape(-1, K1))
+            losses["window_class_loss"] = mtl["window_class_loss_weight"] * wl.mean()
+        if mtl.get("edgemask"):
+            em = torch.from_numpy(np.stack([np.asarray(e["groundtruth_edgemask"], np.float32) for e in examples]))
+            fg, wt = em[:, 0], em[:, 1]
+            tg = torch.stack([1.0 - fg, fg], -1)
+            pr = ON.resize_bilinear(out["edgemask_predictions"], (em.shape[2], em.shape[3]))
+            losses["edgemask_loss"] = mtl["edgemask_loss_weight"] * (ON.softmax_ce(pr, tg) * wt).mean()
+        if mtl.get("refine"):
+            rl = ON.softmax_ce(out["mtl_refined_class_predictions_with_background"].reshape(B, P, K1), cls_t,
+                               cls_w) / norm
+            losses["refined_classification_loss"] = mtl["refined_classification_loss_weight"] * (rl * pad).sum()
+        out["targets"] = dict(cls_t=cls_t, reg_t=reg_t, reg_w=reg_w, cls_w=cls_w, close_t=close_t)
+        return losses
+
+    def regularization_loss(self, l2_table):
+        """sum over variables of weight * 0.5 * sum(w^2) (slim.l2_regularizer; model_deploy.py:296)."""
+        tot = 0.0
+        for name, l2 in l2_table.items():
+            if l2:
+                tot = tot + l2 * 0.5 * (self.p[name] ** 2).sum()
+        return tot

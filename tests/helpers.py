@@ -1,0 +1,58 @@
+"""Shared test helpers: config fixtures, oracle configuration derived from a parsed config."""
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CONFIG_DIR = os.path.join(HERE, "golden", "configs")
+
+
+def load_config(name="model12.config", replace=()):
+    from mtl_ssl_b200.protos import text_format
+    text = open(os.path.join(CONFIG_DIR, name)).read()
+    for a, b in replace:
+        assert a in text, a
+        text = text.replace(a, b)
+    return text_format.Merge(text, text_format.Message("TrainEvalPipelineConfig"))
+
+
+def oracle_config(cfg):
+    """The hyper-parameters oracle/model.py needs, read from the parsed pipeline config."""
+    fr, mtl = cfg.model.faster_rcnn, cfg.model.mtl
+    g = fr.first_stage_anchor_generator.grid_anchor_generator
+    arch = {"faster_rcnn_resnet50": "resnet_v1_50", "faster_rcnn_resnet101": "resnet_v1_101",
+            "faster_rcnn_resnet152": "resnet_v1_152"}[fr.feature_extractor.type]
+    return dict(
+        architecture=arch, num_classes=fr.num_classes, scales=list(g.scales), aspect_ratios=list(g.aspect_ratios),
+        first_stage_max_proposals=fr.first_stage_max_proposals, second_stage_batch_size=fr.second_stage_batch_size,
+        second_stage_balance_fraction=fr.second_stage_balance_fraction,
+        first_stage_minibatch_size=fr.first_stage_minibatch_size,
+        first_stage_positive_balance_fraction=fr.first_stage_positive_balance_fraction,
+        nms_score_threshold=fr.first_stage_nms_score_threshold, nms_iou_threshold=fr.first_stage_nms_iou_threshold,
+        initial_crop_size=fr.initial_crop_size, maxpool_kernel_size=fr.maxpool_kernel_size,
+        first_stage_localization_loss_weight=fr.first_stage_localization_loss_weight,
+        first_stage_objectness_loss_weight=fr.first_stage_objectness_loss_weight,
+        second_stage_localization_loss_weight=fr.second_stage_localization_loss_weight,
+        second_stage_classification_loss_weight=fr.second_stage_classification_loss_weight,
+        mtl=dict(window=mtl.window, closeness=mtl.closeness, edgemask=mtl.edgemask, refine=mtl.refine,
+                 refine_residue=mtl.refine_residue, stop_gradient_for_aux_tasks=mtl.stop_gradient_for_aux_tasks,
+                 window_class_loss_weight=mtl.window_class_loss_weight,
+                 closeness_loss_weight=mtl.closeness_loss_weight, edgemask_loss_weight=mtl.edgemask_loss_weight,
+                 refined_classification_loss_weight=mtl.refined_classification_loss_weight))
+
+
+def randomize_bn(sd, seed=0):
+    """Non-trivial frozen batch-norm statistics so that the fold (scale, bias) is exercised."""
+    rng = np.random.default_rng(seed)
+    import torch
+    for k in list(sd):
+        n = sd[k].numel()
+        if k.endswith("/BatchNorm/gamma"):
+            sd[k] = torch.from_numpy(rng.uniform(0.6, 1.2, n).astype(np.float32))
+        elif k.endswith("/BatchNorm/beta"):
+            sd[k] = torch.from_numpy(rng.uniform(-0.2, 0.2, n).astype(np.float32))
+        elif k.endswith("/BatchNorm/moving_mean"):
+            sd[k] = torch.from_numpy(rng.uniform(-0.2, 0.2, n).astype(np.float32))
+        elif k.endswith("/BatchNorm/moving_variance"):
+            sd[k] = torch.from_numpy(rng.uniform(0.7, 1.3, n).astype(np.float32))
+    return sd
