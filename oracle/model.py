@@ -140,7 +140,10 @@ class Oracle(object):
         return outs
 
     # ------------------------------------------------------------------ forward
-    def forward(self, images, examples, keys, H, W):
+    def forward(self, images, examples, keys, H, W, proposal_inputs=None):
+        """proposal_inputs: optional (rpn_box [B,N,4], rpn_cls [B,N,2]) numpy arrays used INSTEAD of the
+        oracle's own RPN outputs for the (non-differentiable) proposal selection, so that index-level
+        parity can be checked on identical inputs."""
         cfg, p = self.cfg, self.p
         B = images.shape[0]
         K = cfg["num_classes"]
@@ -171,7 +174,9 @@ class Oracle(object):
             oh = np.asarray(ex["groundtruth_classes"], np.float32)
             gt_cls_bg = np.concatenate([np.zeros((len(oh), 1), np.float32), oh], 1)
             gts.append((gt_abs, gt_cls_bg, np.asarray(ex["groundtruth_closeness"], np.float32)))
-            pb, ps, n = OP.rpn_postprocess_single(rpn_box[b].detach().numpy(), rpn_cls[b].detach().numpy(), anchors,
+            src_box = proposal_inputs[0][b] if proposal_inputs is not None else rpn_box[b].detach().numpy()
+            src_cls = proposal_inputs[1][b] if proposal_inputs is not None else rpn_cls[b].detach().numpy()
+            pb, ps, n = OP.rpn_postprocess_single(src_box, src_cls, anchors,
                                                   (H, W), cfg["nms_score_threshold"], cfg["nms_iou_threshold"], M)
             nms_out.append((pb, ps, n))
             t = OA.assign_detection(pb[:n], gt_abs, gt_cls_bg)

@@ -42,17 +42,26 @@ def oracle_config(cfg):
 
 
 def randomize_bn(sd, seed=0):
-    """Non-trivial frozen batch-norm statistics so that the fold (scale, bias) is exercised."""
+    """Non-trivial frozen batch-norm statistics so that the fold (scale, bias) is exercised, chosen
+    so that activations stay O(1) through the residual stack (stem variance ~ pixel variance x
+    fan-in x He variance; small conv3 gammas keep the residual sum from growing)."""
     rng = np.random.default_rng(seed)
     import torch
+    u = lambda lo, hi, n: torch.from_numpy(rng.uniform(lo, hi, n).astype(np.float32))
     for k in list(sd):
         n = sd[k].numel()
+        stem = "/block" not in k and "/conv1/BatchNorm/" in k
         if k.endswith("/BatchNorm/gamma"):
-            sd[k] = torch.from_numpy(rng.uniform(0.6, 1.2, n).astype(np.float32))
+            if "/conv3/" in k:
+                sd[k] = u(0.15, 0.3, n)
+            elif "/shortcut/" in k:
+                sd[k] = u(0.5, 0.8, n)
+            else:
+                sd[k] = u(0.7, 1.2, n)
         elif k.endswith("/BatchNorm/beta"):
-            sd[k] = torch.from_numpy(rng.uniform(-0.2, 0.2, n).astype(np.float32))
+            sd[k] = u(-0.2, 0.2, n)
         elif k.endswith("/BatchNorm/moving_mean"):
-            sd[k] = torch.from_numpy(rng.uniform(-0.2, 0.2, n).astype(np.float32))
+            sd[k] = u(-0.2, 0.2, n)
         elif k.endswith("/BatchNorm/moving_variance"):
-            sd[k] = torch.from_numpy(rng.uniform(0.7, 1.3, n).astype(np.float32))
+            sd[k] = u(0.7, 1.3, n) * (14000.0 if stem else 1.0)
     return sd
