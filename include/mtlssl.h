@@ -30,6 +30,7 @@ typedef void* mtl_stream_t;
 const char* mtl_last_error_string(void);
 int mtl_abi_version(void);
 int mtl_device_sm_count(void);
+long long mtl_launch_count(void);   /* kernels launched (or graph-captured) by this library so far */
 
 /* ---- tcgen05 implicit-GEMM convolution engine (csrc/gemm_tc.cu) -------------------------
  * Replaces slim.conv2d / slim.fully_connected and their gradients

@@ -16,6 +16,11 @@ extern "C" const char* mtl_last_error_string(void) { return g_err; }
 
 extern "C" int mtl_abi_version(void) { return 1; }
 
+static long long g_launches = 0;
+extern "C" void mtl_count_launch(void) { ++g_launches; }
+// number of kernels this library has launched (or captured into a CUDA graph) so far
+extern "C" long long mtl_launch_count(void) { return g_launches; }
+
 int mtl_num_sms() {
   static int sms = 0;
   if (sms == 0) {

@@ -13,6 +13,8 @@ typedef __nv_bfloat16 bf16;
 #define MTL_ERR_UNSUPPORTED (-3)
 
 extern "C" void mtl_set_error(const char* fmt, ...);
+// every kernel launch of the library passes through MTL_CUDA_LAUNCH_CHECK, which counts it
+extern "C" void mtl_count_launch(void);
 
 #define MTL_CHECK_ARG(cond, ...)                 \
   do {                                           \
@@ -24,6 +26,7 @@ extern "C" void mtl_set_error(const char* fmt, ...);
 
 #define MTL_CUDA_LAUNCH_CHECK(name)                                          \
   do {                                                                       \
+    mtl_count_launch();                                                      \
     cudaError_t e__ = cudaGetLastError();                                    \
     if (e__ != cudaSuccess) {                                                \
       mtl_set_error("%s: launch failed: %s", name, cudaGetErrorString(e__)); \

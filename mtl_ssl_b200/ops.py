@@ -128,7 +128,13 @@ def opt_chunk_size():
     return int(lib().mtl_opt_chunk_size())
 
 
+def launch_count():
+    f = lib().mtl_launch_count
+    f.restype = ctypes.c_longlong
+    return int(f())
+
+
 def exported_symbols():
     """Names this module binds (used by the CPU test that checks the .so exports them all)."""
     return sorted(_SIGS) + ["mtl_conv_tc", "mtl_last_error_string", "mtl_abi_version",
-                            "mtl_device_sm_count", "mtl_opt_chunk_size"]
+                            "mtl_device_sm_count", "mtl_opt_chunk_size", "mtl_launch_count"]

@@ -12,6 +12,22 @@ from ._lib import lib, check, ptr, cur_stream
 
 FPROP, DGRAD, WGRAD = 0, 1, 2
 
+# bench.py sets this to a list to time every tcgen05 launch with CUDA events on the launching
+# stream: entries are (mode, algorithmic flops, start event, end event).
+PROFILE = None
+
+
+def _launch(a, what):
+    if PROFILE is None:
+        check(lib().mtl_conv_tc(ctypes.byref(a), cur_stream()), what)
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    check(lib().mtl_conv_tc(ctypes.byref(a), cur_stream()), what)
+    e1.record()
+    flops = 2.0 * a.N * a.P * a.Q * a.K * a.R * a.S * a.C
+    PROFILE.append((a.mode, flops, e0, e1))
+
 
 class ConvArgs(ctypes.Structure):
     _fields_ = [
@@ -70,7 +86,7 @@ def conv_fprop(x, w, stride=1, pad=(0, 0), dil=1, out_hw=None, bias=None, res=No
     a.relu = int(relu)
     a.alpha = 1.0
     a.force_bn = force_bn
-    check(lib().mtl_conv_tc(ctypes.byref(a), cur_stream()), "mtl_conv_tc(fprop)")
+    _launch(a, "mtl_conv_tc(fprop)")
     return out
 
 
@@ -97,7 +113,7 @@ def conv_dgrad(dy, w, x_shape, stride=1, pad=(0, 0), dil=1, res=None, mask=None,
         a.mask = _dp(mask)
     a.alpha = 1.0
     a.force_bn = force_bn
-    check(lib().mtl_conv_tc(ctypes.byref(a), cur_stream()), "mtl_conv_tc(dgrad)")
+    _launch(a, "mtl_conv_tc(dgrad)")
     return out
 
 
@@ -117,5 +133,5 @@ def conv_wgrad(dy, x, dw, stride=1, pad=(0, 0), dil=1, rowscale=None, alpha=1.0,
     a.alpha = float(alpha)
     a.force_bn = force_bn
     a.force_splits = force_splits
-    check(lib().mtl_conv_tc(ctypes.byref(a), cur_stream()), "mtl_conv_tc(wgrad)")
+    _launch(a, "mtl_conv_tc(wgrad)")
     return dw
