@@ -246,10 +246,10 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.synchronize()
     prof, ops_conv.PROFILE = ops_conv.PROFILE, None
     model.param_store.g.zero_()
-    conv_ms = sum(a.elapsed_time(b) for _, _, a, b in prof)
-    conv_flops = sum(f for _, f, _, _ in prof)
+    conv_ms = sum(p_[2].elapsed_time(p_[3]) for p_ in prof)
+    conv_flops = sum(p_[1] for p_ in prof)
     by_mode = {}
-    for m, f, a, b in prof:
+    for m, f, a, b, _g in prof:
         d = by_mode.setdefault(("fprop", "dgrad", "wgrad")[m], [0.0, 0.0, 0])
         d[0] += f; d[1] += a.elapsed_time(b); d[2] += 1
     peaks = {}

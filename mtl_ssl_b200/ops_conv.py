@@ -26,7 +26,7 @@ def _launch(a, what):
     check(lib().mtl_conv_tc(ctypes.byref(a), cur_stream()), what)
     e1.record()
     flops = 2.0 * a.N * a.P * a.Q * a.K * a.R * a.S * a.C
-    PROFILE.append((a.mode, flops, e0, e1))
+    PROFILE.append((a.mode, flops, e0, e1, (a.N, a.H, a.W, a.C, a.K, a.R, a.stride, a.P, a.Q)))
 
 
 class ConvArgs(ctypes.Structure):
