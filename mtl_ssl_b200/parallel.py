@@ -1,0 +1,19 @@
+"""Data-parallel gradient exchange: one all-reduce over the flat gradient arena.
+
+Replaces the in-graph clone sum of /root/reference/slim/deployment/model_deploy.py:414-444
+(`_sum_clones_gradients`: tf.add_n on the CPU) and its loss scaling (:221-225 clone loss / num_clones,
+:296 regularisation losses added once).  With torch.distributed the backend is NCCL over
+NVLink-5 / NVSwitch on the GPUs and gloo in the CPU tests."""
+import torch
+import torch.distributed as dist
+
+
+def data_parallel_scale(world_size):
+    """Factor applied to the summed task-loss gradients (the L2 gradient is added after scaling)."""
+    return 1.0 / float(world_size)
+
+
+def allreduce_gradients(flat_grads, world_size, group=None):
+    if world_size > 1:
+        dist.all_reduce(flat_grads, op=dist.ReduceOp.SUM, group=group)
+    return flat_grads

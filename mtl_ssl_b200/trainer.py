@@ -17,6 +17,7 @@ import numpy as np
 import torch
 
 from .meta_architectures.faster_rcnn_meta_arch import LOSS_KEYS
+from .parallel import allreduce_gradients, data_parallel_scale
 from .utils import learning_schedules
 
 
@@ -128,16 +129,14 @@ class Trainer(object):
 
     def _optimize(self):
         st = self.model.param_store
-        gs = 1.0 / self.world_size
+        gs = data_parallel_scale(self.world_size)
         st.stats_and_reg_loss(gs)
         st.apply(gs)
         self._loss_dev[:8].copy_(self.model.workspace.bufs["loss/values"])
         self._loss_dev[8:9].copy_(st.reg_loss)
 
     def _allreduce(self):
-        if self.world_size > 1:
-            import torch.distributed as dist
-            dist.all_reduce(self.model.param_store.g, op=dist.ReduceOp.SUM, group=self.pg)
+        allreduce_gradients(self.model.param_store.g, self.world_size, self.pg)
 
     def host_arrays(self, examples, keys):
         arrays = pack_groundtruth(examples, self.model.num_classes, self.H, self.W, self.gmax)

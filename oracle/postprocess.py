@@ -106,3 +106,36 @@ def rpn_postprocess_single(box_encodings, objectness_logits, anchors, image_hw, 
     out_b[:len(sel)] = boxes_c[sel]
     out_s[:len(sel)] = scores_c[sel]
     return out_b, out_s, len(sel)
+
+
+def multiclass_non_max_suppression(boxes, scores, score_thresh, iou_thresh, max_size_per_class,
+                                   max_total_size=0, clip_window=None, change_coordinate_frame=False):
+    """core/post_processing.py:25-164.  boxes [N,q,4] (q = 1 or num_classes), scores [N,C].
+    Returns (boxes [k,4], scores [k], classes [k]) sorted by descending score."""
+    boxes = np.asarray(boxes, F)
+    scores = np.asarray(scores, F)
+    n, q = boxes.shape[0], boxes.shape[1]
+    num_classes = scores.shape[1]
+    out_b, out_s, out_c = [], [], []
+    for c in range(num_classes):
+        b = boxes[:, c if q > 1 else 0]
+        s = scores[:, c]
+        keep = np.nonzero(s > F(score_thresh))[0]                    # filter_greater_than (blo:652-687)
+        b, s = b[keep], s[keep]
+        if clip_window is not None:
+            b, kidx = B.clip_to_window(b, clip_window)
+            s = s[kidx]
+            if change_coordinate_frame:
+                wy0, wx0, wy1, wx1 = [F(v) for v in clip_window]
+                hh, ww = wy1 - wy0, wx1 - wx0
+                b = np.stack([(b[:, 0] - wy0) / hh, (b[:, 1] - wx0) / ww, (b[:, 2] - wy0) / hh,
+                              (b[:, 3] - wx0) / ww], 1).astype(F)
+        sel = nms_vectorized(b, s, min(max_size_per_class, len(b)), iou_thresh)
+        out_b.append(b[sel]); out_s.append(s[sel]); out_c.append(np.full(len(sel), c, F))
+    ob = np.concatenate(out_b) if out_b else np.zeros((0, 4), F)
+    os_ = np.concatenate(out_s) if out_s else np.zeros((0,), F)
+    oc = np.concatenate(out_c) if out_c else np.zeros((0,), F)
+    order = np.argsort(-os_, kind="stable")                          # sort_by_field (blo:554-594)
+    if max_total_size:
+        order = order[:max_total_size]
+    return ob[order], os_[order], oc[order]

@@ -1,0 +1,172 @@
+"""CPU tests of the host-side mirror: config drop-in, variable table, C-ABI exports, schedules,
+aux-label synthesis, and the data-parallel gradient exchange (gloo, world size 2)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import CONFIG_DIR, load_config
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_all_fixture_configs_parse_unchanged():
+    for name in sorted(os.listdir(CONFIG_DIR)):
+        if not name.endswith(".config"):
+            continue
+        cfg = load_config(name)
+        fr = cfg.model.faster_rcnn
+        assert cfg.model.WhichOneof("model") == "faster_rcnn"
+        assert fr.num_classes in (20, 90)
+        assert fr.first_stage_max_proposals == 300 and fr.first_stage_minibatch_size == 256   # default
+        assert abs(fr.first_stage_nms_iou_threshold - 0.7) < 1e-6
+        assert cfg.train_config.gradient_clipping_by_norm == 10.0
+        assert cfg.train_config.optimizer.WhichOneof("optimizer") == "momentum_optimizer"
+
+
+def test_config_proto2_semantics():
+    from mtl_ssl_b200.protos import text_format
+    cfg = load_config("model12.config")
+    m = cfg.model.mtl
+    assert m.window and m.closeness and m.edgemask and m.refine and m.refine_residue
+    assert m.shared_feature == "proposal_feature_maps" and m.global_closeness is True      # defaults
+    assert abs(m.closeness_loss_weight - 0.3) < 1e-7
+    assert cfg.model.faster_rcnn.feature_extractor.freeze_layer == "block1"                # default
+    assert cfg.model.faster_rcnn.HasField("initial_crop_size")
+    assert not cfg.model.faster_rcnn.HasField("hard_example_miner")
+    g = cfg.model.faster_rcnn.first_stage_anchor_generator.grid_anchor_generator
+    assert list(g.scales) == [0.25, 0.5, 1.0, 2.0] and g.height == 256 and g.height_stride == 16
+    with pytest.raises(text_format.ParseError):
+        text_format.Merge("model { no_such_field: 1 }", text_format.Message("TrainEvalPipelineConfig"))
+    c22 = load_config("model22.config")
+    assert c22.model.mtl.stop_gradient_for_aux_tasks and c22.train_config.batch_size == 3
+
+
+def test_learning_rate_schedule_from_config():
+    from mtl_ssl_b200.utils import learning_schedules as ls
+    cfg = load_config("model12.config")
+    fn, mom = ls.from_optimizer_config(cfg.train_config.optimizer)
+    assert abs(mom - 0.9) < 1e-7
+    assert [fn(s) for s in (0, 89999, 90000, 119999, 120000, 10 ** 6)] == \
+        pytest.approx([1e-3, 1e-3, 1e-4, 1e-4, 1e-5, 1e-5])
+    # utils/learning_schedules_test.py: boundaries [2,3,7], rates [1,2,3,4]
+    got = [ls.manual_stepping(s, [2, 3, 7], [1.0, 2.0, 3.0, 4.0]) for s in range(10)]
+    assert got == [1.0, 1.0, 2.0, 3.0, 3.0, 3.0, 3.0, 4.0, 4.0, 4.0]
+    with pytest.raises(ValueError):
+        ls.manual_stepping(0, [3, 2], [1.0, 2.0, 3.0])
+
+
+def test_variable_table_matches_reference_scopes():
+    """Variable names / shapes of the model built from model12.config (no device needed)."""
+    from mtl_ssl_b200.builders import model_builder
+    cfg = load_config("model12.config")
+    model = model_builder.build(cfg.model, True, device=None)
+    st = model.param_store
+    names = {p.name: p for p in st.params}
+    arch = "resnet_v1_101"
+    assert names["FirstStageFeatureExtractor/%s/conv1/weights" % arch].shape == (64, 7, 7, 3)
+    assert not names["FirstStageFeatureExtractor/%s/conv1/weights" % arch].trainable            # rv1:216-221
+    assert not names["FirstStageFeatureExtractor/%s/block1/unit_1/bottleneck_v1/conv1/weights" % arch].trainable
+    assert names["FirstStageFeatureExtractor/%s/block2/unit_1/bottleneck_v1/conv1/weights" % arch].trainable
+    assert names["FirstStageFeatureExtractor/%s/block3/unit_23/bottleneck_v1/conv3/weights" % arch].shape == (1024, 1, 1, 256)
+    for sc in ("SecondStageFeatureExtractor", "ClosenessBoxPredictor", "WindowBoxPredictor"):
+        assert names["%s/%s/block4/unit_1/bottleneck_v1/shortcut/weights" % (sc, arch)].shape == (2048, 1, 1, 1024)
+    assert names["FirstStageBoxPredictor/Conv/weights"].shape == (512, 3, 3, 1024)
+    assert names["FirstStageBoxPredictor/BoxEncodingPredictor/weights"].shape == (48, 1, 1, 512)
+    assert names["FirstStageBoxPredictor/ClassPredictor/weights"].shape == (24, 1, 1, 512)
+    assert names["SecondStageBoxPredictor/BoxEncodingPredictor/weights"].shape == (80, 1, 1, 2048)
+    assert names["SecondStageBoxPredictor/ClassPredictor/weights"].shape == (21, 1, 1, 2048)
+    assert names["WindowBoxPredictor/ClassPredictor/weights"].shape == (21, 1, 1, 2048)          # K+1 (T11)
+    assert names["ClosenessBoxPredictor/ClassPredictor/biases"].shape == (21,)
+    assert names["EdgeMaskPredictor/BoxEncodingPredictor/weights"].shape == (2, 1, 1, 1024)
+    assert names["MTLClassRefiner/fc1/weights"].shape == (21, 147)
+    assert abs(names["WindowBoxPredictor/ClassPredictor/weights"].l2 - 1e-3) < 1e-9
+    assert abs(names["SecondStageBoxPredictor/ClassPredictor/weights"].l2 - 1e-4) < 1e-9
+    n_train = sum(p.numel for p in st.params if p.trainable and "/_dead/" not in p.name)
+    assert 76e6 < n_train < 78.5e6, n_train                                                     # SURVEY: ~77.1 M
+    rm = model.restore_map(from_detection_checkpoint=False)
+    key = "%s/block4/unit_1/bottleneck_v1/conv1/weights" % arch
+    assert len(rm[key]) == 4          # dead stage-1 copy + second stage + closeness + window (T5, T14)
+    base = model_builder.build(load_config("model11.config").model, True, device=None)
+    assert not any(n.startswith(("WindowBoxPredictor", "ClosenessBoxPredictor", "EdgeMaskPredictor", "MTLClassRefiner"))
+                   for n in base.param_store.by_name)
+
+
+def test_product_path_fails_loudly_without_cuda():
+    from mtl_ssl_b200.builders import model_builder
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    with pytest.raises(Exception):
+        model_builder.build(load_config("model12.config").model, True, device="cuda")
+
+
+def test_cabi_library_exports_every_declared_symbol():
+    from mtl_ssl_b200 import _lib, ops
+    hdr = open(os.path.join(ROOT, "include", "mtlssl.h")).read()
+    declared = set(re.findall(r"\b(mtl_[a-z0-9_]+)\s*\(", hdr)) - {"mtl_conv_args"}
+    assert len(declared) >= 40
+    assert os.path.exists(_lib.LIB_PATH), "run `python -m mtl_ssl_b200.build` first"
+    h = ctypes.CDLL(_lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(h, name), name
+    assert set(ops._SIGS) <= declared
+    assert h.mtl_abi_version() == 1
+    # no torch / C++ types cross the boundary: undefined symbols must not reference at:: / c10::
+    out = subprocess.run(["nm", "-D", "--undefined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "c10" not in out and "at6" not in out and "torch" not in out.lower()
+
+
+def test_aux_label_synthesis():
+    from mtl_ssl_b200.data import aux_labels as AL
+    # two unit-overlap boxes: union by inclusion-exclusion = 2*4 - 1
+    assert AL.union_area([[0, 0, 2, 2], [1, 1, 3, 3]]) == pytest.approx(7.0)
+    boxes = np.array([[100., 100, 300, 300], [200, 200, 500, 600]])
+    classes = np.array([3, 7])
+    lab, bg = AL.window_label(boxes, classes, [0, 0, 600, 1000], 20)
+    assert lab.shape == (21,) and abs(lab.sum() - 1.0) < 5e-3 and lab[3] > 0 and lab[7] > lab[3] and lab[1] == 0
+    a3 = 200 * 200 / 6e5; a7 = 300 * 400 / 6e5; abg = 1 - (a3 + a7 - 100 * 100 / 6e5)
+    raw = np.array([np.sqrt(abg), np.sqrt(a3), np.sqrt(a7)])
+    np.testing.assert_allclose([lab[0], lab[3], lab[7]], np.round(raw / raw.sum(), 3), atol=1e-6)
+    cl = AL.closeness_labels(boxes, classes, 600, 1000, 20)
+    assert cl.shape == (2, 21) and cl[0, 7] == 1.0 and cl[1, 3] == 1.0
+    assert AL.closeness_labels(boxes[:1], classes[:1], 600, 1000, 20)[0, 0] == 1.0
+    em = AL.edgemask(boxes, 600., 1000.)
+    assert em.shape == (2, 64, 64) and em[0].max() == 1 and abs(em[1].mean() - 1) < 1e-5
+    rng = np.random.default_rng(0)
+    wb, wl = AL.random_windows(boxes, classes, 600., 1000., 20, rng, 64)
+    assert wb.shape == (64, 4) and wl.shape == (64, 21) and (wl[:, 0] < 1).all() and (wb <= 1).all()
+
+
+_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, %r)
+from mtl_ssl_b200.parallel import allreduce_gradients, data_parallel_scale
+dist.init_process_group("gloo", rank=int(os.environ["RANK"]), world_size=2)
+r = dist.get_rank()
+g = torch.arange(10, dtype=torch.float32) * (r + 1)
+allreduce_gradients(g, 2)
+exp = torch.arange(10, dtype=torch.float32) * 3
+assert torch.equal(g, exp), g
+# reference semantics (model_deploy.py:221-225, :296): task-loss gradients averaged, L2 counted once
+assert data_parallel_scale(2) == 0.5
+w = torch.ones(10); l2 = 0.1
+total = g * data_parallel_scale(2) + l2 * w
+assert torch.allclose(total, exp * 0.5 + 0.1)
+dist.destroy_process_group()
+print("rank", r, "ok")
+"""
+
+
+def test_data_parallel_gradient_exchange_gloo_world2(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER % ROOT)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29533", WORLD_SIZE="2")
+    procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r)), stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=120)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs

@@ -1,0 +1,272 @@
+"""Pins the CPU oracle (oracle/) to the reference's own known-answer tests and to outputs of the
+reference's importable NumPy code (tests/golden/np_reference.npz, made by tests/golden/make_golden.py).
+
+Every test names the reference test it restates (paths under /root/reference/object_detection/).
+CPU only; runs in seconds."""
+import math
+import os
+
+import numpy as np
+import torch
+
+from oracle import assign as OA
+from oracle import boxes as OB
+from oracle import nn as ON
+from oracle import postprocess as OP
+
+F = np.float32
+GOLD = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "np_reference.npz"))
+
+
+# ---- anchor_generators/grid_anchor_generator_test.py:25-73
+def test_construct_single_anchor():
+    exp = [[-121, -35, 135, 29], [-249, -67, 263, 61], [-505, -131, 519, 125], [-57, -67, 71, 61],
+           [-121, -131, 135, 125], [-249, -259, 263, 253], [-25, -131, 39, 125], [-57, -259, 71, 253],
+           [-121, -515, 135, 509]]
+    got = OB.grid_anchors(1, 1, [0.5, 1.0, 2.0], [0.25, 1.0, 4.0], anchor_offset=(7, -3))
+    np.testing.assert_allclose(got, exp, rtol=1e-6, atol=1e-4)
+
+
+def test_construct_anchor_grid():
+    exp = [[-2.5, -2.5, 2.5, 2.5], [-5., -5., 5., 5.], [-10., -10., 10., 10.], [-2.5, 16.5, 2.5, 21.5],
+           [-5., 14., 5, 24], [-10., 9., 10, 29], [16.5, -2.5, 21.5, 2.5], [14., -5., 24, 5], [9., -10., 29, 10],
+           [16.5, 16.5, 21.5, 21.5], [14., 14., 24, 24], [9., 9., 29, 29]]
+    got = OB.grid_anchors(2, 2, [0.5, 1.0, 2.0], [1.0], (10, 10), (19, 19), (0, 0))
+    np.testing.assert_allclose(got, exp, rtol=1e-6, atol=1e-5)
+
+
+# ---- box_coders/faster_rcnn_box_coder_test.py:26-92 (scale factors passed explicitly there)
+BOXES = [[10.0, 10.0, 20.0, 15.0], [0.2, 0.1, 0.5, 0.4]]
+ANCHORS = [[15.0, 12.0, 30.0, 18.0], [0.1, 0.0, 0.7, 0.9]]
+
+
+def test_box_coder_encode():
+    exp = [[-0.5, -0.416666, -0.405465, -0.182321], [-0.083333, -0.222222, -0.693147, -1.098612]]
+    np.testing.assert_allclose(OB.box_encode(BOXES, ANCHORS, None), exp, rtol=1e-5, atol=1e-6)
+
+
+def test_box_coder_encode_with_scaling():
+    exp = [[-1., -1.25, -1.62186, -0.911608], [-0.166667, -0.666667, -2.772588, -5.493062]]
+    np.testing.assert_allclose(OB.box_encode(BOXES, ANCHORS, [2, 3, 4, 5]), exp, rtol=1e-5, atol=1e-6)
+
+
+def test_box_coder_decode():
+    codes = [[-0.5, -0.416666, -0.405465, -0.182321], [-0.083333, -0.222222, -0.693147, -1.098612]]
+    np.testing.assert_allclose(OB.box_decode(codes, ANCHORS, None), BOXES, rtol=1e-5, atol=1e-5)
+
+
+def test_box_coder_decode_with_scaling():
+    codes = [[-1., -1.25, -1.62186, -0.911608], [-0.166667, -0.666667, -2.772588, -5.493062]]
+    np.testing.assert_allclose(OB.box_decode(codes, ANCHORS, [2, 3, 4, 5]), BOXES, rtol=1e-5, atol=1e-5)
+
+
+def test_box_coder_very_small_width():
+    exp = [[-0.833333, 0., -21.128731, 0.510826]]
+    got = OB.box_encode([[10.0, 10.0, 10.0000001, 20.0]], [[15.0, 12.0, 30.0, 18.0]], None)
+    np.testing.assert_allclose(got, exp, rtol=1e-5, atol=1e-5)
+
+
+# ---- core/region_similarity_calculator_test.py:25-36
+def test_iou_similarity():
+    c1 = [[4.0, 3.0, 7.0, 5.0], [5.0, 6.0, 10.0, 7.0]]
+    c2 = [[3.0, 4.0, 6.0, 8.0], [14.0, 14.0, 15.0, 15.0], [0.0, 0.0, 20.0, 20.0]]
+    exp = [[2.0 / 16.0, 0, 6.0 / 400.0], [1.0 / 16.0, 0.0, 5.0 / 400.0]]
+    np.testing.assert_allclose(OB.iou(c1, c2), exp, rtol=1e-6)
+
+
+# ---- reference NumPy code run in the build container (utils/np_box_ops.py:25-97)
+def test_geometry_matches_reference_numpy():
+    a, b = GOLD["iou_a"], GOLD["iou_b"]
+    np.testing.assert_allclose(OB.area(b), GOLD["area"], rtol=1e-6)
+    np.testing.assert_allclose(OB.intersection(a, b), GOLD["intersection"], rtol=1e-6, atol=1e-3)
+    np.testing.assert_allclose(OB.iou(a, b), GOLD["iou"], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(OB.ioa(a, b), GOLD["ioa"], rtol=1e-5, atol=1e-7)
+
+
+def test_clip_and_prune_match_reference_numpy():
+    """utils/np_box_list_ops.py:467-522 clip_to_window, :524-552 prune_outside_window."""
+    b, w = GOLD["iou_b"], GOLD["window"]
+    got, _ = OB.clip_to_window(b, w)
+    np.testing.assert_array_equal(got, GOLD["clip_to_window"])
+    pb, idx = OB.prune_outside_window(b, w)
+    np.testing.assert_array_equal(idx, GOLD["prune_outside_window_idx"])
+    np.testing.assert_array_equal(pb, GOLD["prune_outside_window_boxes"])
+
+
+def test_nms_matches_reference_numpy():
+    """utils/np_box_list_ops.py:185-257 non_max_suppression (suppress iff IoU > threshold)."""
+    b, s = GOLD["nms_boxes_in"], GOLD["nms_scores_in"]
+    for thr, mx in ((0.5, 50), (0.7, 300)):
+        for fn in (OP.tf_non_max_suppression, OP.nms_vectorized):
+            sel = fn(b, s, mx, thr)
+            np.testing.assert_array_equal(b[sel], GOLD["nms_%g_%d_boxes" % (thr, mx)])
+            np.testing.assert_array_equal(s[sel], GOLD["nms_%g_%d_scores" % (thr, mx)])
+
+
+# ---- matchers/argmax_matcher_test.py:26-192
+SIM = np.array([[1., 1, 1, 3, 1], [2, -1, 2, 0, 4], [3, 0, -1, 0, 0]])
+SIM2 = np.array([[1, 1, 1, 3, 1], [-1, 0, -2, -2, -1], [3, 0, -1, 2, 0]], F)
+
+
+def _cols(m):
+    return np.nonzero(m >= 0)[0], m[m >= 0], np.nonzero(m == -1)[0]
+
+
+def test_matcher_default_thresholds():
+    m = OA.argmax_match(SIM, None)
+    np.testing.assert_array_equal(m, [2, 0, 1, 0, 1])
+
+
+def test_matcher_empty_rows():
+    m = OA.argmax_match(np.zeros((0, 5), F), None)
+    np.testing.assert_array_equal(m, [-1] * 5)
+
+
+def test_matcher_matched_threshold():
+    mc, mr, un = _cols(OA.argmax_match(SIM, 3.0))
+    np.testing.assert_array_equal(mc, [0, 3, 4]); np.testing.assert_array_equal(mr, [2, 0, 1])
+    np.testing.assert_array_equal(un, [1, 2])
+
+
+def test_matcher_matched_and_unmatched_threshold():
+    mc, mr, un = _cols(OA.argmax_match(SIM, 3.0, 2.0))
+    np.testing.assert_array_equal(mc, [0, 3, 4]); np.testing.assert_array_equal(mr, [2, 0, 1])
+    np.testing.assert_array_equal(un, [1])
+
+
+def test_matcher_negatives_lower_than_unmatched_false():
+    mc, mr, un = _cols(OA.argmax_match(SIM, 3.0, 2.0, negatives_lower_than_unmatched=False))
+    np.testing.assert_array_equal(mc, [0, 3, 4]); np.testing.assert_array_equal(mr, [2, 0, 1])
+    np.testing.assert_array_equal(un, [2])
+
+
+def test_matcher_unmatched_row_without_and_with_force_match():
+    mc, mr, un = _cols(OA.argmax_match(SIM2, 3.0, 2.0))
+    np.testing.assert_array_equal(mc, [0, 3]); np.testing.assert_array_equal(mr, [2, 0])
+    np.testing.assert_array_equal(un, [1, 2, 4])
+    mc, mr, un = _cols(OA.argmax_match(SIM2, 3.0, 2.0, force_match_for_each_row=True))
+    np.testing.assert_array_equal(mc, [0, 1, 3]); np.testing.assert_array_equal(mr, [2, 1, 0])
+    np.testing.assert_array_equal(un, [2, 4])
+
+
+# ---- core/target_assigner_test.py:412-466 (empty groundtruth) + fmA detector semantics
+def test_assign_empty_groundtruth():
+    anchors = [[0.0, 0.0, 0.5, 0.5], [0.5, 0.5, 1.0, 0.8], [0, 0.5, .5, 1.0], [.75, 0, 1.0, .25]]
+    t = OA.assign_targets(anchors, np.zeros((0, 4), F), np.zeros((0, 4), F), [0, 0, 0, 0], 0.5)
+    np.testing.assert_array_equal(t["cls_targets"], np.zeros((4, 4)))
+    np.testing.assert_array_equal(t["cls_weights"], [1, 1, 1, 1])
+    np.testing.assert_array_equal(t["reg_targets"], np.zeros((4, 4)))
+    np.testing.assert_array_equal(t["reg_weights"], [0, 0, 0, 0])
+
+
+def test_assign_detection_targets_and_weights():
+    props = [[0, 0, 10, 10], [0, 0, 10, 9], [50, 50, 60, 60], [0, 0, 3, 3]]
+    gt = [[0, 0, 10, 10], [50, 50, 61, 61]]
+    cls = [[0, 0, 1], [0, 1, 0]]
+    t = OA.assign_detection(props, gt, cls)
+    np.testing.assert_array_equal(t["match"], [0, 0, 1, -1])
+    np.testing.assert_array_equal(t["cls_targets"], [[0, 0, 1], [0, 0, 1], [0, 1, 0], [1, 0, 0]])
+    np.testing.assert_array_equal(t["cls_weights"], [1, 1, 1, 1])
+    np.testing.assert_array_equal(t["reg_weights"], [1, 1, 1, 0])
+    np.testing.assert_allclose(t["reg_targets"][0], [0, 0, 0, 0], atol=1e-6)
+
+
+def test_rpn_assign_ignore_band_and_force_match():
+    anchors = [[0, 0, 10, 10], [0, 0, 10, 5], [0, 0, 10, 4.5], [20, 20, 30, 30]]
+    gt = [[0, 0, 10, 10], [20, 20, 26, 26]]            # second GT has best IoU 0.36 with anchor 3
+    t = OA.assign_proposal(anchors, gt)
+    np.testing.assert_array_equal(t["match"], [0, -2, -2, 1])       # 0.5 / 0.45 ignored, forced match
+    np.testing.assert_array_equal(t["cls_weights"], [1, 0, 0, 1])
+    np.testing.assert_array_equal(t["cls_targets"][:, 0], [1, 0, 0, 1])
+
+
+# ---- core/balanced_positive_negative_sampler_test.py:26-63 (counts; indices are key-defined here)
+def test_balanced_sampler_counts():
+    rng = np.random.default_rng(0)
+    labels = np.array([True] * 100 + [False] * 200)
+    keys = rng.random(300).astype(F)
+    s = OA.balanced_subsample(np.ones(300, bool), 64, labels, 0.5, keys)
+    assert s.sum() == 64 and s[labels].sum() == 32
+    ind = np.array([True] * 90 + [False] * 210)                    # only 10 negatives available
+    ind[290:] = True
+    s = OA.balanced_subsample(ind, 64, labels, 0.5, keys)
+    assert s[labels].sum() == 32 and s[~labels].sum() == 10 and not s[~ind].any()
+    few = np.zeros(300, bool); few[:5] = True                      # 5 positives -> 59 negatives
+    s = OA.balanced_subsample(np.ones(300, bool), 64, few, 0.5, keys)
+    assert s[few].sum() == 5 and s[~few].sum() == 59
+
+
+# ---- core/losses_test.py:98-118, :228-283
+def test_smooth_l1_loss():
+    pred = torch.tensor([[[2.5, 0, .4, 0], [0, 0, 0, 0], [0, 2.5, 0, .4]],
+                         [[3.5, 0, 0, 0], [0, .4, 0, .9], [0, 0, 1.5, 0]]])
+    w = torch.tensor([[2., 1, 1], [0, 3, 0]])
+    np.testing.assert_allclose(ON.smooth_l1(pred, torch.zeros_like(pred), w).sum().item(), 7.695, rtol=1e-6)
+
+
+def test_softmax_loss_and_anchorwise():
+    pred = torch.tensor([[[-100., 100, -100], [100, -100, -100], [0, 0, -100], [-100, -100, 100]],
+                         [[-100, 0, 0], [-100, 100, -100], [-100, 100, -100], [100, -100, -100]]])
+    tgt = torch.tensor([[[0., 1, 0], [1, 0, 0], [1, 0, 0], [0, 0, 1]], [[0, 0, 1], [0, 1, 0], [0, 1, 0], [1, 0, 0]]])
+    w = torch.tensor([[1, 1, .5, 1], [1., 1, 1, 0]])
+    aw = ON.softmax_ce(pred, tgt, w)
+    np.testing.assert_allclose(aw.sum().item(), -1.5 * math.log(.5), rtol=1e-6)
+    exp = [[0, 0, -0.5 * math.log(.5), 0], [-math.log(.5), 0, 0, 0]]
+    np.testing.assert_allclose(aw.numpy(), exp, atol=1e-6)
+
+
+# ---- core/post_processing_test.py:43-76, :301-347
+def test_multiclass_nms_select_with_shared_boxes():
+    boxes = np.array([[[0, 0, 1, 1]], [[0, 0.1, 1, 1.1]], [[0, -0.1, 1, 0.9]], [[0, 10, 1, 11]], [[0, 10.1, 1, 11.1]],
+                      [[0, 100, 1, 101]], [[0, 1000, 1, 1002]], [[0, 1000, 1, 1002.1]]], F)
+    scores = np.array([[.9, 0.01], [.75, 0.05], [.6, 0.01], [.95, 0], [.5, 0.01], [.3, 0.01], [.01, .85], [.01, .5]], F)
+    b, s, c = OP.multiclass_non_max_suppression(boxes, scores, 0.1, .5, 4)
+    np.testing.assert_allclose(b, [[0, 10, 1, 11], [0, 0, 1, 1], [0, 1000, 1, 1002], [0, 100, 1, 101]])
+    np.testing.assert_allclose(s, [.95, .9, .85, .3])
+    np.testing.assert_array_equal(c, [0, 0, 1, 0])
+
+
+def test_multiclass_nms_with_clip_window():
+    boxes = np.array([[[0, 0, 10, 10]], [[1, 1, 11, 11]]], F)
+    scores = np.array([[.9], [.75]], F)
+    b, s, c = OP.multiclass_non_max_suppression(boxes, scores, 0.0, 0.5, 100, clip_window=[5, 4, 8, 7])
+    np.testing.assert_allclose(b, [[5, 4, 8, 7]]); np.testing.assert_allclose(s, [.9])
+    b, s, c = OP.multiclass_non_max_suppression(boxes, scores, 0.0, 0.5, 100, clip_window=[5, 4, 8, 7],
+                                                change_coordinate_frame=True)
+    np.testing.assert_allclose(b, [[0, 0, 1, 1]])
+
+
+# ---- meta_architectures/faster_rcnn_meta_arch_test_lib.py:603-987 closed-form loss values
+def test_second_stage_loc_loss_closed_form():
+    """One positive proposal whose code is off by 5*ln(0.8)-ish in the reference test yields
+    (-5 ln 0.8 - 0.5)/3; restated on the loss primitive: |d| = -5 ln 0.8 > 1 -> |d| - 0.5."""
+    d = -5 * math.log(0.8)
+    got = ON.smooth_l1(torch.tensor([[d, 0, 0, 0.]]), torch.zeros(1, 4), torch.ones(1), 1.0).item() / 3
+    np.testing.assert_allclose(got, (-5 * math.log(.8) - 0.5) / 3, rtol=1e-6)
+    # the fork's first stage uses sigma = 3 (fmA:391-392): |d| - 0.5/9
+    got = ON.smooth_l1(torch.tensor([[d, 0, 0, 0.]]), torch.zeros(1, 4), torch.ones(1), 3.0).item() / 3
+    np.testing.assert_allclose(got, (-5 * math.log(.8) - 0.5 / 9) / 3, rtol=1e-6)
+
+
+# ---- TF kernel restatements: self-consistency against torch primitives
+def test_crop_and_resize_identity_and_extrapolation():
+    img = torch.arange(2 * 5 * 7 * 3, dtype=torch.float32).reshape(2, 5, 7, 3)
+    full = ON.crop_and_resize(img, torch.tensor([[0., 0, 1, 1]]), torch.tensor([1]), (5, 7))
+    torch.testing.assert_close(full[0], img[1])
+    out = ON.crop_and_resize(img, torch.tensor([[-1., -1, -0.5, -0.5]]), torch.tensor([0]), (2, 2))
+    assert not out.any()
+
+
+def test_resize_bilinear_matches_formula():
+    x = torch.rand(1, 3, 4, 2)
+    y = ON.resize_bilinear(x, (6, 8))
+    # src = dst * in/out (no half-pixel offset): output (0,0) equals input (0,0); row 2 reads source row 1
+    torch.testing.assert_close(y[0, 0, 0], x[0, 0, 0])
+    torch.testing.assert_close(y[0, 2, 0], x[0, 1, 0])
+    torch.testing.assert_close(y[0, 1, 0], 0.5 * (x[0, 0, 0] + x[0, 1, 0]))
+
+
+def test_same_padding_arithmetic():
+    assert ON.same_pad(300, 3, 2) == (150, 0, 1)
+    assert ON.same_pad(75, 3, 1) == (75, 1, 1)
+    assert ON.same_pad(7, 1, 2) == (4, 0, 0)
