@@ -9,6 +9,7 @@ import torch
 
 from .. import ops
 from .. import ops_conv as oc
+from ..nets.layers import Concurrency
 from .standard_fields import (BOX_ENCODINGS, CLASS_PREDICTIONS, CLASS_PREDICTIONS_WITH_BACKGROUND)
 
 
@@ -56,9 +57,10 @@ class _FusedHead(object):
 
     def bwd(self, x, dy_bf16, dx=None, dx_mask=None):
         if self.trainable:
-            oc.conv_wgrad(dy_bf16, x, self.w_grad())
-            rows = dy_bf16.numel() // self.n_pad
-            ops.call("mtl_colsum", dy_bf16, 0, self.n_pad, rows, self.n_pad, 1.0, self.bias_grad())
+            with torch.cuda.stream(Concurrency.fork()):
+                oc.conv_wgrad(dy_bf16, x, self.w_grad())
+                rows = dy_bf16.numel() // self.n_pad
+                ops.call("mtl_colsum", dy_bf16, 0, self.n_pad, rows, self.n_pad, 1.0, self.bias_grad())
         if dx is not None:
             oc.conv_dgrad(dy_bf16, self.w_bf16(), x.shape, mask=dx_mask, out=dx)
         return dx

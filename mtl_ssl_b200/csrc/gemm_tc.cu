@@ -18,6 +18,7 @@
 // (FPROP, DGRAD) or a scaled fp32 red.global.add (WGRAD).
 #include "common.cuh"
 #include <cuda.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace tc {
@@ -41,6 +42,10 @@ struct Params {
   int rows;                  // number of valid rows in row space
   int S, stride, pad_h, pad_w, dil, transposed;
   int ntot;                  // DGRAD: Cin (columns per tap of w); WGRAD: Cin
+  unsigned long long div_ohw, div_ow;   // multiply-shift division constants for oH*oW and oW
+  int im2col;                // gathered operand comes by TMA im2col (stride-1 filters), no gather warps
+  int im_low_h, im_low_w;    // base-pixel offset of filter offset (0,0)
+  int R;                     // filter rows (mirrored offsets in DGRAD)
   // epilogue
   void* out; long long ldo; int out_fp32;
   const float* bias;         // per output column (FPROP/DGRAD) or nullptr
@@ -76,6 +81,11 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
       : "memory");
   return done;
 }
+// x / d for 0 <= x < 2^31 with a host-made constant: low 32 bits = multiplier ceil(2^s / d), high = s
+__device__ __forceinline__ int fast_div(int x, unsigned long long c) {
+  const uint32_t mul = (uint32_t)c, sh = (uint32_t)(c >> 32);
+  return (int)(((unsigned long long)(uint32_t)x * mul) >> sh);
+}
 __device__ __forceinline__ uint64_t globaltimer_ns() {
   uint64_t t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -103,6 +113,18 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
       " [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+// TMA im2col load (rank-4 NHWC tensor map made by cuTensorMapEncodeIm2col): `pixels` consecutive
+// output positions starting at base pixel (w, h, n) -- wrapping over rows / images inside the
+// bounding box in hardware -- for filter offset (offw, offh), 64 channels from c; zero fill outside.
+__device__ __forceinline__ void tma_load_im2col(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c,
+                                                int w, int h, int n, int offw, int offh) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n),
+        "h"((unsigned short)offw), "h"((unsigned short)offh)
       : "memory");
 }
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
@@ -239,32 +261,62 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int m_tile = rem / p.tiles_n, n_tile = rem - m_tile * p.tiles_n;
         const int m0 = m_tile * BM;
         const int kb = split * ips, ke = min(kb + ips, p.k_iters);
+        int tn0 = 0, tp0 = 0, tq0 = 0;      // (n, p, q) of the tile's first row (im2col TMA base pixel)
+        if (MODE != WGRAD && p.im2col) {
+          tn0 = fast_div(m0, p.div_ohw);
+          const int r2 = m0 - tn0 * (p.oH * p.oW);
+          tp0 = fast_div(r2, p.div_ow);
+          tq0 = r2 - tp0 * p.oW;
+        }
         for (int k = kb; k < ke; ++k, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1u;
           mbar_wait(empty_bar(s), ph ^ 1u);
           mbar_arrive_expect_tx(full_bar(s), tx_bytes);
-          if (MODE == FPROP) {
+          if (MODE == FPROP || MODE == DGRAD) {
             const int tap = k / p.cpt, chunk = k - tap * p.cpt;
-            if (!GATHER_A) tma_load_2d(stage_a(s), &tmA, full_bar(s), chunk * BK, m0);
-            tma_load_2d(stage_b(s), &tmB, full_bar(s), tap * p.gC + chunk * BK, n_tile * BN);
-          } else if (MODE == DGRAD) {
-            const int tap = k / p.cpt, chunk = k - tap * p.cpt;
-            if (!GATHER_A) tma_load_2d(stage_a(s), &tmA, full_bar(s), chunk * BK, m0);
+            if (!GATHER_A) {
+              if (p.im2col) {
+                const int fr = tap / p.S, fs = tap - fr * p.S;
+                const int offh = (MODE == FPROP ? fr : p.R - 1 - fr) * p.dil;
+                const int offw = (MODE == FPROP ? fs : p.S - 1 - fs) * p.dil;
+                tma_load_im2col(stage_a(s), &tmA, full_bar(s), chunk * BK, tq0 + p.im_low_w, tp0 + p.im_low_h, tn0,
+                                offw, offh);
+              } else {
+                tma_load_2d(stage_a(s), &tmA, full_bar(s), chunk * BK, m0);
+              }
+            }
+            if (MODE == FPROP) {
+              tma_load_2d(stage_b(s), &tmB, full_bar(s), tap * p.gC + chunk * BK, n_tile * BN);
+            } else {
 #pragma unroll
-            for (int j = 0; j < BN / 64; ++j)
-              tma_load_2d(stage_b(s) + j * 8192, &tmB, full_bar(s),
-                          tap * p.ntot + n_tile * BN + j * 64, chunk * BK);
+              for (int j = 0; j < BN / 64; ++j)
+                tma_load_2d(stage_b(s) + j * 8192, &tmB, full_bar(s),
+                            tap * p.ntot + n_tile * BN + j * 64, chunk * BK);
+            }
           } else {
             const int p0 = k * BK;
             tma_load_2d(stage_a(s), &tmA, full_bar(s), m0, p0);
             tma_load_2d(stage_a(s) + 8192, &tmA, full_bar(s), m0 + 64, p0);
             if (!GATHER_B) {
               const int nper = p.ntot / BN;           // n-tiles per tap
-              const int ci0 = (n_tile % nper) * BN;   // non-gather WGRAD has a single tap
+              const int tap = n_tile / nper;
+              const int ci0 = (n_tile - tap * nper) * BN;
+              if (p.im2col) {
+                const int fr = tap / p.S, fs = tap - fr * p.S;
+                const int pn = fast_div(p0, p.div_ohw);
+                const int r2 = p0 - pn * (p.oH * p.oW);
+                const int pp = fast_div(r2, p.div_ow);
+                const int pq = r2 - pp * p.oW;
 #pragma unroll
-              for (int j = 0; j < BN / 64; ++j)
-                tma_load_2d(stage_b(s) + j * 8192, &tmB, full_bar(s), ci0 + j * 64, p0);
+                for (int j = 0; j < BN / 64; ++j)
+                  tma_load_im2col(stage_b(s) + j * 8192, &tmB, full_bar(s), ci0 + j * 64, pq + p.im_low_w,
+                                  pp + p.im_low_h, pn, fs * p.dil, fr * p.dil);
+              } else {
+#pragma unroll
+                for (int j = 0; j < BN / 64; ++j)
+                  tma_load_2d(stage_b(s) + j * 8192, &tmB, full_bar(s), ci0 + j * 64, p0);
+              }
             }
           }
         }
@@ -325,30 +377,78 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         ncol0 = (long long)n_tile * BN;
       }
       const bool row_ok = m < p.M;
+      // Software-pipelined drain: the TMEM load of chunk c+1 and the residual / mask loads of
+      // chunk c+1 are in flight while chunk c is combined and stored, so the ~1 us
+      // tcgen05.ld -> global load -> store dependency chain is paid once per tile, not per chunk.
+      constexpr int NCH = BN / 32;
+      uint32_t v[32];
+      tmem_ld32(taddr, v);
+      if (MODE == WGRAD) {
+        const float sc = p.alpha * ((p.rowscale && row_ok) ? __ldg(p.rowscale + m) : 1.0f);
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld32(taddr + c * 32, v);
-        tmem_ld_wait();
-        const long long n0 = ncol0 + c * 32;
-        if (!row_ok) continue;
-        if (MODE == WGRAD) {
-          const float sc = p.alpha * (p.rowscale ? __ldg(p.rowscale + m) : 1.0f);
-          float* o = reinterpret_cast<float*>(p.out) + (long long)m * p.ldo + n0;
+        for (int c = 0; c < NCH; ++c) {
+          tmem_ld_wait();
+          float f[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) atomicAdd(o + j, __uint_as_float(v[j]) * sc);
-        } else {
-          const int nvalid = (int)min((long long)32, (long long)p.N - n0);
-          if (nvalid <= 0) continue;
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * sc;
+          if (c + 1 < NCH) tmem_ld32(taddr + (c + 1) * 32, v);
+          if (row_ok) {
+            float* o = reinterpret_cast<float*>(p.out) + (long long)m * p.ldo + ncol0 + c * 32;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              atomicAdd(reinterpret_cast<float4*>(o) + j, make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]));
+          }
+        }
+      } else {
+        const bool res_bf16 = p.res && !p.res_fp32 && (p.ldr & 7) == 0;
+        const bool mask_vec = p.mask && (p.ldm & 7) == 0;
+        uint4 rnext[4], mnext[4];
+        auto prefetch = [&](int c) {
+          const long long n0 = ncol0 + c * 32;
+          const bool full = row_ok && (p.N - n0 >= 32);
+          if (res_bf16 && full) {
+            const uint4* r = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.res) + (long long)m * p.ldr + n0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) rnext[j] = __ldg(r + j);
+          }
+          if (mask_vec && full) {
+            const uint4* r = reinterpret_cast<const uint4*>(p.mask + (long long)m * p.ldm + n0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) mnext[j] = __ldg(r + j);
+          }
+        };
+        prefetch(0);
+#pragma unroll 1
+        for (int c = 0; c < NCH; ++c) {
+          tmem_ld_wait();
           float f[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-          if (p.bias) {
+          uint4 rcur[4], mcur[4];
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < nvalid) f[j] += __ldg(p.bias + n0 + j);
+          for (int j = 0; j < 4; ++j) { rcur[j] = rnext[j]; mcur[j] = mnext[j]; }
+          if (c + 1 < NCH) {
+            tmem_ld32(taddr + (c + 1) * 32, v);
+            prefetch(c + 1);
           }
+          const long long n0 = ncol0 + c * 32;
+          if (!row_ok) continue;
+          const int nvalid = (int)min((long long)32, (long long)p.N - n0);
+          if (nvalid <= 0) continue;
           const bool vec = (nvalid == 32);
+          if (p.bias) {
+            if (vec) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + j);
+                f[4 * j] += t.x; f[4 * j + 1] += t.y; f[4 * j + 2] += t.z; f[4 * j + 3] += t.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < nvalid) f[j] += __ldg(p.bias + n0 + j);
+            }
+          }
           if (p.res) {
             if (p.res_fp32) {
               const float* r = reinterpret_cast<const float*>(p.res) + (long long)m * p.ldr + n0;
@@ -363,24 +463,21 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (int j = 0; j < 32; ++j)
                   if (j < nvalid) f[j] += __ldg(r + j);
               }
+            } else if (vec && res_bf16) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint32_t w[4] = {rcur[j].x, rcur[j].y, rcur[j].z, rcur[j].w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  f[8 * j + 2 * q] += __uint_as_float(w[q] << 16);
+                  f[8 * j + 2 * q + 1] += __uint_as_float(w[q] & 0xffff0000u);
+                }
+              }
             } else {
               const bf16* r = reinterpret_cast<const bf16*>(p.res) + (long long)m * p.ldr + n0;
-              if (vec && (p.ldr & 7) == 0) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const uint4 t = __ldg(reinterpret_cast<const uint4*>(r) + j);
-                  const uint32_t w[4] = {t.x, t.y, t.z, t.w};
-#pragma unroll
-                  for (int q = 0; q < 4; ++q) {
-                    f[8 * j + 2 * q] += __uint_as_float(w[q] << 16);
-                    f[8 * j + 2 * q + 1] += __uint_as_float(w[q] & 0xffff0000u);
-                  }
-                }
-              } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                  if (j < nvalid) f[j] += __bfloat162float(r[j]);
-              }
+              for (int j = 0; j < 32; ++j)
+                if (j < nvalid) f[j] += __bfloat162float(r[j]);
             }
           }
           if (p.relu) {
@@ -388,12 +485,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
           }
           if (p.mask) {
-            const bf16* r = p.mask + (long long)m * p.ldm + n0;
-            if (vec && (p.ldm & 7) == 0) {
+            if (vec && mask_vec) {
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                const uint4 t = __ldg(reinterpret_cast<const uint4*>(r) + j);
-                const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+                const uint32_t w[4] = {mcur[j].x, mcur[j].y, mcur[j].z, mcur[j].w};
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                   if (!(__uint_as_float(w[q] << 16) > 0.0f)) f[8 * j + 2 * q] = 0.0f;
@@ -401,6 +496,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
               }
             } else {
+              const bf16* r = p.mask + (long long)m * p.ldm + n0;
 #pragma unroll
               for (int j = 0; j < 32; ++j)
                 if (j < nvalid && !(__bfloat162float(r[j]) > 0.0f)) f[j] = 0.0f;
@@ -448,100 +544,128 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ============================ im2col gather warps ==================================
     // Each of the 128 threads owns one 128-byte row (FPROP/DGRAD: one output pixel of the A
     // tile; WGRAD: one pixel of the B tile for half of the 64-channel column blocks).
-    constexpr int DEPTH = 2;   // cp.async groups kept in flight besides the current one
+    constexpr int DEPTH = (STAGES >= 6) ? 3 : 2;   // cp.async groups kept in flight besides the current one
     const int g = threadIdx.x - 256;
     uint32_t it = 0;
     uint32_t pending_first = 0;    // oldest iteration whose full-barrier arrive is outstanding
     const int ohw = p.oH * p.oW;
+    // The gather is on the critical path of every 3x3 / strided layer: all per-iteration index math
+    // is strength-reduced (no divisions inside the K loop; row decode uses multiply-shift division).
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int split = tile / tiles_mn;
       const int rem = tile - split * tiles_mn;
       const int m_tile = rem / p.tiles_n, n_tile = rem - m_tile * p.tiles_n;
       const int kb = split * ips, ke = min(kb + ips, p.k_iters);
-      int rn = 0, roh = 0, row_ = 0;
-      bool rvalid = false;
       if (GATHER_A) {
         const int m = m_tile * BM + g;
-        rvalid = m < p.rows;
+        const bool rvalid = m < p.rows;
+        int rn = 0, roh = 0, row_ = 0;
         if (rvalid) {
-          rn = m / ohw;
+          rn = fast_div(m, p.div_ohw);
           const int r2 = m - rn * ohw;
-          roh = r2 / p.oW;
+          roh = fast_div(r2, p.div_ow);
           row_ = r2 - roh * p.oW;
         }
-      }
-      for (int k = kb; k < ke; ++k, ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1u;
-        mbar_wait(empty_bar(s), ph ^ 1u);
-        if (GATHER_A) {
-          const int tap = k / p.cpt, chunk = k - tap * p.cpt;
-          const int fr = tap / p.S, fs = tap - fr * p.S;
+        const bf16* img = p.gsrc + (long long)rn * p.gH * p.gW * p.gC;
+        // fprop: input coordinate of tap (0,0); dgrad: output-gradient coordinate before the stride division
+        const int h0 = p.transposed ? roh + p.pad_h : roh * p.stride - p.pad_h;
+        const int w0 = p.transposed ? row_ + p.pad_w : row_ * p.stride - p.pad_w;
+        int tap = kb / p.cpt;
+        int chunk = kb - tap * p.cpt;
+        int fr = tap / p.S, fs = tap - fr * p.S;
+        const uint32_t dst_row = g * 128;
+        const int sw = g & 7;
+        for (int k = kb; k < ke; ++k, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1u;
+          mbar_wait(empty_bar(s), ph ^ 1u);
           int hi, wi;
           bool ok = rvalid;
           if (!p.transposed) {
-            hi = roh * p.stride - p.pad_h + fr * p.dil;
-            wi = row_ * p.stride - p.pad_w + fs * p.dil;
+            hi = h0 + fr * p.dil;
+            wi = w0 + fs * p.dil;
           } else {
-            const int hy = roh + p.pad_h - fr * p.dil, wy = row_ + p.pad_w - fs * p.dil;
-            ok = ok && hy >= 0 && wy >= 0 && (hy % p.stride == 0) && (wy % p.stride == 0);
-            hi = hy / p.stride;
-            wi = wy / p.stride;
+            hi = h0 - fr * p.dil;
+            wi = w0 - fs * p.dil;
+            ok = ok && hi >= 0 && wi >= 0;
+            if (p.stride != 1) {
+              ok = ok && (hi % p.stride == 0) && (wi % p.stride == 0);
+              hi /= p.stride;
+              wi /= p.stride;
+            }
           }
           ok = ok && hi >= 0 && hi < p.gH && wi >= 0 && wi < p.gW;
           const int c0 = chunk * BK;
-          const bf16* src = ok ? p.gsrc + ((long long)(rn * p.gH + hi) * p.gW + wi) * p.gC + c0 : p.gsrc;
-          const uint32_t dst = stage_a(s) + g * 128;
+          const bf16* src = ok ? img + ((hi * p.gW + wi) * p.gC + c0) : p.gsrc;
+          const uint32_t dst = stage_a(s) + dst_row;
+          if (c0 + BK <= p.gC) {
+            const uint32_t nb = ok ? 16u : 0u;
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const bool pv = ok && (c0 + q * 8 < p.gC);
-            cp_async16(dst + ((q ^ (g & 7)) << 4), pv ? (const void*)(src + q * 8) : (const void*)p.gsrc,
-                       pv ? 16u : 0u);
+            for (int q = 0; q < 8; ++q) cp_async16(dst + ((q ^ sw) << 4), src + (ok ? q * 8 : 0), nb);
+          } else {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const bool pv = ok && (c0 + q * 8 < p.gC);
+              cp_async16(dst + ((q ^ sw) << 4), pv ? (const void*)(src + q * 8) : (const void*)p.gsrc, pv ? 16u : 0u);
+            }
           }
-        } else {
-          // WGRAD: rows are pixels of this K block, columns are ci of tap (n_tile / nper)
-          const int nper = p.ntot / BN;
-          const int tap = n_tile / nper, ci0 = (n_tile - tap * nper) * BN;
-          const int fr = tap / p.S, fs = tap - fr * p.S;
-          const int pr = g & 63;
+          if (++chunk == p.cpt) {
+            chunk = 0;
+            if (++fs == p.S) { fs = 0; ++fr; }
+          }
+          cp_async_commit();
+          if (it - pending_first >= (uint32_t)DEPTH) {
+            cp_async_wait<DEPTH>();
+            fence_proxy_async();
+            mbar_arrive(full_bar(pending_first % STAGES));
+            ++pending_first;
+          }
+        }
+      } else {
+        // WGRAD: rows are pixels of this K block, columns are ci of tap (n_tile / nper)
+        const int nper = p.ntot / BN;
+        const int tap = n_tile / nper, ci0 = (n_tile - tap * nper) * BN;
+        const int fr = tap / p.S, fs = tap - fr * p.S;
+        const int dh = fr * p.dil - p.pad_h, dw = fs * p.dil - p.pad_w;
+        const int pr = g & 63;
+        const int sw = pr & 7;
+        for (int k = kb; k < ke; ++k, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1u;
+          mbar_wait(empty_bar(s), ph ^ 1u);
           const int pix = k * BK + pr;
           bool ok = pix < p.rows;
-          int n = 0, oh = 0, ow = 0;
-          if (ok) {
-            n = pix / ohw;
-            const int r2 = pix - n * ohw;
-            oh = r2 / p.oW;
-            ow = r2 - oh * p.oW;
-          }
-          const int hi = oh * p.stride - p.pad_h + fr * p.dil;
-          const int wi = ow * p.stride - p.pad_w + fs * p.dil;
+          const int n = fast_div(pix, p.div_ohw);
+          const int r2 = pix - n * ohw;
+          const int oh = fast_div(r2, p.div_ow);
+          const int ow = r2 - oh * p.oW;
+          const int hi = oh * p.stride + dh;
+          const int wi = ow * p.stride + dw;
           ok = ok && hi >= 0 && hi < p.gH && wi >= 0 && wi < p.gW;
           const bf16* src = ok ? p.gsrc + ((long long)(n * p.gH + hi) * p.gW + wi) * p.gC + ci0 : p.gsrc;
+          const uint32_t nb = ok ? 16u : 0u;
 #pragma unroll
           for (int jj = 0; jj < BN / 128; ++jj) {
             const int j = (g >> 6) + 2 * jj;
             const uint32_t dst = stage_b(s) + j * 8192 + pr * 128;
 #pragma unroll
             for (int q = 0; q < 8; ++q)
-              cp_async16(dst + ((q ^ (pr & 7)) << 4),
-                         ok ? (const void*)(src + j * 64 + q * 8) : (const void*)p.gsrc, ok ? 16u : 0u);
+              cp_async16(dst + ((q ^ sw) << 4), src + (ok ? j * 64 + q * 8 : 0), nb);
           }
           if (BN == 64) {   // single column block: threads 0..63 stage it, 64..127 only arrive
             if ((g >> 6) == 0) {
               const uint32_t dst = stage_b(s) + pr * 128;
 #pragma unroll
-              for (int q = 0; q < 8; ++q)
-                cp_async16(dst + ((q ^ (pr & 7)) << 4),
-                           ok ? (const void*)(src + q * 8) : (const void*)p.gsrc, ok ? 16u : 0u);
+              for (int q = 0; q < 8; ++q) cp_async16(dst + ((q ^ sw) << 4), src + (ok ? q * 8 : 0), nb);
             }
           }
-        }
-        cp_async_commit();
-        if (it - pending_first >= (uint32_t)DEPTH) {
-          cp_async_wait<DEPTH>();
-          fence_proxy_async();
-          mbar_arrive(full_bar(pending_first % STAGES));
-          ++pending_first;
+          cp_async_commit();
+          if (it - pending_first >= (uint32_t)DEPTH) {
+            cp_async_wait<DEPTH>();
+            fence_proxy_async();
+            mbar_arrive(full_bar(pending_first % STAGES));
+            ++pending_first;
+          }
         }
       }
     }
@@ -596,6 +720,52 @@ static int make_map(CUtensorMap* map, const void* base, long long rows, long lon
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { mtl_set_error("gemm_tc: cuTensorMapEncodeTiled failed (%d)", (int)r); return MTL_ERR_CUDA; }
+  return MTL_OK;
+}
+
+static unsigned long long make_fast_div(int d) {
+  // Granlund-Montgomery round-up method, exact for 0 <= x < 2^31 (d >= 1)
+  if (d <= 1) return 1ull;                      // mul = 1, shift = 0
+  int l = 0;
+  while ((1ll << l) < d) ++l;
+  const int s = 31 + l;
+  const unsigned long long mul = ((1ull << s) + (unsigned long long)d - 1) / (unsigned long long)d;
+  return (mul & 0xffffffffull) | ((unsigned long long)s << 32);
+}
+
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const int*, const int*, cuuint32_t, cuuint32_t,
+                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// NHWC bf16 activation [N,H,W,C] as an im2col tensor map: 64 channels x `pixels` positions per load;
+// the base pixel ranges over [low, dim + up) in each spatial dimension (stride-1 traversal).
+static int make_im2col_map(CUtensorMap* map, const void* base, int N, int H, int W, int C, int low_h, int low_w,
+                           int up_h, int up_w, int pixels) {
+  static EncodeIm2colFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess) {
+      mtl_set_error("gemm_tc: cuTensorMapEncodeIm2col unavailable");
+      return MTL_ERR_CUDA;
+    }
+    fn = reinterpret_cast<EncodeIm2colFn>(ptr);
+  }
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (C & 7)) {
+    mtl_set_error("gemm_tc: im2col operand must be 16B aligned with C %% 8 == 0");
+    return MTL_ERR_ARG;
+  }
+  cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t gstr[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  int lower[2] = {low_w, low_h};
+  int upper[2] = {up_w, up_h};
+  cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstr, lower, upper, 64u,
+                  (cuuint32_t)pixels, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { mtl_set_error("gemm_tc: cuTensorMapEncodeIm2col failed (%d)", (int)r); return MTL_ERR_CUDA; }
   return MTL_OK;
 }
 
@@ -670,7 +840,13 @@ extern "C" int mtl_conv_tc(const mtl_conv_args* a, cudaStream_t stream) {
   CUtensorMap tmA, tmB;
   memset(&tmA, 0, sizeof(tmA)); memset(&tmB, 0, sizeof(tmB));
   int bn, rc;
-  const bool gather = !plain;
+  // stride-1 filters: the gathered operand is fetched by TMA im2col loads (no gather warps)
+  static const bool no_im2col = getenv("MTL_NO_TMA_IM2COL") != nullptr;
+  const bool im2col = !plain && !no_im2col && a->stride == 1 && a->R * p.dil < 120 && a->S * p.dil < 120 &&
+                      a->pad_h < 120 && a->pad_w < 120;
+  const bool gather = !plain && !im2col;
+  p.im2col = im2col ? 1 : 0;
+  p.R = a->R;
   if (a->mode == FPROP) {
     MTL_CHECK_ARG(a->x && a->w && a->out, "mtl_conv_tc fprop: null tensor");
     p.M = (int)npq; p.N = a->K; p.cpt = ceil_div(a->C, BK); p.k_iters = p.taps * p.cpt;
@@ -680,7 +856,11 @@ extern "C" int mtl_conv_tc(const mtl_conv_args* a, cudaStream_t stream) {
     bn = a->force_bn ? a->force_bn : (a->K > 128 ? 256 : (a->K > 64 ? 128 : 64));
     // keep the machine busy when M is small: prefer narrower tiles if they add CTAs
     if (!a->force_bn && bn == 256 && ceil_div(p.M, BM) * ceil_div(a->K, 256) < mtl_num_sms() / 2) bn = 128;
-    if (!gather && (rc = make_map(&tmA, a->x, npq, a->C, a->C, BM))) return rc;
+    if (im2col) {
+      p.im_low_h = -a->pad_h; p.im_low_w = -a->pad_w;
+      if ((rc = make_im2col_map(&tmA, a->x, a->N, a->H, a->W, a->C, p.im_low_h, p.im_low_w,
+                                a->P + p.im_low_h - a->H, a->Q + p.im_low_w - a->W, BM))) return rc;
+    } else if (!gather && (rc = make_map(&tmA, a->x, npq, a->C, a->C, BM))) return rc;
     if ((rc = make_map(&tmB, a->w, a->K, (long long)p.taps * a->C, (long long)p.taps * a->C, bn))) return rc;
     if (gather) tmA = tmB;
   } else if (a->mode == DGRAD) {
@@ -691,7 +871,12 @@ extern "C" int mtl_conv_tc(const mtl_conv_args* a, cudaStream_t stream) {
     p.ldo = a->C; p.ldr = a->C; p.ldm = a->C;
     bn = a->force_bn ? a->force_bn : (a->C > 128 ? 256 : (a->C > 64 ? 128 : 64));
     if (!a->force_bn && bn == 256 && ceil_div(p.M, BM) * ceil_div(a->C, 256) < mtl_num_sms() / 2) bn = 128;
-    if (!gather && (rc = make_map(&tmA, a->dy, npq, a->K, a->K, BM))) return rc;
+    if (im2col) {
+      // dx[h] = sum_r dy[h + pad - r*dil]: a stride-1 correlation over dy with mirrored filter offsets
+      p.im_low_h = a->pad_h - (a->R - 1) * p.dil; p.im_low_w = a->pad_w - (a->S - 1) * p.dil;
+      if ((rc = make_im2col_map(&tmA, a->dy, a->N, a->P, a->Q, a->K, p.im_low_h, p.im_low_w,
+                                a->H + p.im_low_h - a->P, a->W + p.im_low_w - a->Q, BM))) return rc;
+    } else if (!gather && (rc = make_map(&tmA, a->dy, npq, a->K, a->K, BM))) return rc;
     if ((rc = make_map(&tmB, a->w, a->K, (long long)p.taps * a->C, (long long)p.taps * a->C, 64))) return rc;
     if (gather) tmA = tmB;
   } else if (a->mode == WGRAD) {
@@ -704,7 +889,11 @@ extern "C" int mtl_conv_tc(const mtl_conv_args* a, cudaStream_t stream) {
     bn = a->force_bn ? a->force_bn : (a->C % 256 == 0 ? 256 : (a->C % 128 == 0 ? 128 : 64));
     MTL_CHECK_ARG(a->C % bn == 0, "mtl_conv_tc wgrad: BN %d must divide C %d", bn, a->C);
     if ((rc = make_map(&tmA, a->dy, npq, a->K, a->K, 64))) return rc;
-    if (!gather && (rc = make_map(&tmB, a->x, nhw, a->C, a->C, 64))) return rc;
+    if (im2col) {
+      p.im_low_h = -a->pad_h; p.im_low_w = -a->pad_w;
+      if ((rc = make_im2col_map(&tmB, a->x, a->N, a->H, a->W, a->C, p.im_low_h, p.im_low_w,
+                                a->P + p.im_low_h - a->H, a->Q + p.im_low_w - a->W, 64))) return rc;
+    } else if (!gather && (rc = make_map(&tmB, a->x, nhw, a->C, a->C, 64))) return rc;
     if (gather) tmB = tmA;
     // split K (pixels) so that about one wave of CTAs is launched
     const int tiles = ceil_div(p.M, BM) * (p.N / bn);
@@ -717,6 +906,8 @@ extern "C" int mtl_conv_tc(const mtl_conv_args* a, cudaStream_t stream) {
     mtl_set_error("mtl_conv_tc: bad mode %d", a->mode);
     return MTL_ERR_ARG;
   }
+  p.div_ohw = make_fast_div(p.oH * p.oW);
+  p.div_ow = make_fast_div(p.oW);
   p.tiles_m = ceil_div(p.M, BM);
   p.tiles_n = (a->mode == WGRAD) ? p.N / bn : ceil_div(p.N, bn);
   if (a->mode == FPROP) return gather ? dispatch_bn<FPROP, true>(bn, tmA, tmB, p, stream)

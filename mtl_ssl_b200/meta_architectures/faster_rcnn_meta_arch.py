@@ -27,7 +27,7 @@ from .. import ops
 from ..core import model
 from ..core.standard_fields import (BoxListFields as fields, BOX_ENCODINGS, CLASS_PREDICTIONS,
                                     CLASS_PREDICTIONS_WITH_BACKGROUND, MASK_PREDICTIONS)
-from ..nets.layers import Conv2d, max_pool, max_pool_bwd, max_pool_out_hw
+from ..nets.layers import Concurrency, Conv2d, max_pool, max_pool_bwd, max_pool_out_hw
 from ..runtime import ParamStore, Workspace
 
 LOSS_KEYS = ["first_stage_localization_loss", "first_stage_objectness_loss", "second_stage_localization_loss",
@@ -595,6 +595,7 @@ class FasterRCNNMetaArch(model.DetectionModel):
         self._rpn_conv.wgrad(feat, d_rpn_feat)
         gfeat = self._rpn_conv.dgrad(d_rpn_feat, feat.shape, ws.get("bwd/g_feat", feat.shape), res=dfeat, mask=feat)
         fe.backward_proposal_features(self.first_stage_feature_extractor_scope, gfeat, ws)
+        Concurrency.join()      # side-stream weight-gradient GEMMs must land before the optimizer
 
     def _crop_backward(self, pd, dmaps, maps, pre_pool, boxes, box_ind, dfeat, tag):
         ws = self._ws

@@ -15,6 +15,36 @@ from .. import ops_conv as oc
 from .. import ops
 
 
+class Concurrency(object):
+    """Fork/join helper: weight-gradient GEMMs are off the backward critical path (they only feed the
+    optimizer), so they are launched on side streams and overlap the dgrad chain.  Under CUDA-graph
+    capture the stream waits become graph edges, i.e. the captured step keeps the concurrency."""
+    enabled = True
+    num_streams = 2
+    _streams = None
+    _idx = 0
+
+    @classmethod
+    def fork(cls):
+        cur = torch.cuda.current_stream()
+        if not cls.enabled:
+            return cur
+        if cls._streams is None:
+            cls._streams = [torch.cuda.Stream() for _ in range(cls.num_streams)]
+        s = cls._streams[cls._idx % len(cls._streams)]
+        cls._idx += 1
+        s.wait_stream(cur)
+        return s
+
+    @classmethod
+    def join(cls):
+        if cls._streams is None:
+            return
+        cur = torch.cuda.current_stream()
+        for s in cls._streams:
+            cur.wait_stream(s)
+
+
 def same_pad(in_size, k, stride, rate=1):
     """TensorFlow SAME padding: (out, pad_begin)."""
     out = -(-in_size // stride)
@@ -70,10 +100,11 @@ class Conv2d(object):
             return
         N, H, W, C = x.shape
         P, Q, ph, pw = self.geom(H, W)
-        oc.conv_wgrad(dy, x, self.weight.g, self.stride, (ph, pw), self.rate,
-                      rowscale=self.bn.scale if self.bn is not None else None)
-        if self.bias is not None:
-            ops.call("mtl_colsum", dy, 0, self.cout, dy.numel() // self.cout, self.cout, 1.0, self.bias.g)
+        with torch.cuda.stream(Concurrency.fork()):
+            oc.conv_wgrad(dy, x, self.weight.g, self.stride, (ph, pw), self.rate,
+                          rowscale=self.bn.scale if self.bn is not None else None)
+            if self.bias is not None:
+                ops.call("mtl_colsum", dy, 0, self.cout, dy.numel() // self.cout, self.cout, 1.0, self.bias.g)
 
     def dgrad(self, dy, x_shape, out, res=None, mask=None):
         N, H, W, C = x_shape
