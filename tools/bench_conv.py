@@ -9,6 +9,7 @@ mode, N, H, W, C, K, R = sys.argv[1], *[int(v) for v in sys.argv[2:8]]
 stride = int(sys.argv[8]) if len(sys.argv) > 8 else 1
 iters = int(sys.argv[9]) if len(sys.argv) > 9 else 20
 res_on = os.environ.get("RES", "1") == "1"
+BNF = int(os.environ.get("BN", "0"))
 pad = (R - 1) // 2
 P, Q = oc.out_size(H, R, stride, pad, pad), oc.out_size(W, R, stride, pad, pad)
 x = torch.randn(N, H, W, C, device="cuda").bfloat16()
@@ -25,11 +26,11 @@ dx = torch.empty(N, H, W, C, device="cuda", dtype=torch.bfloat16)
 
 def run():
     if mode == "fprop":
-        oc.conv_fprop(x, w, stride, (pad, pad), 1, (P, Q), bias=bias, res=res if res_on else None, relu=True, out=y)
+        oc.conv_fprop(x, w, stride, (pad, pad), 1, (P, Q), bias=bias, res=res if res_on else None, relu=True, out=y, force_bn=BNF)
     elif mode == "dgrad":
-        oc.conv_dgrad(dy, w, (N, H, W, C), stride, (pad, pad), 1, mask=mask if res_on else None, out=dx)
+        oc.conv_dgrad(dy, w, (N, H, W, C), stride, (pad, pad), 1, mask=mask if res_on else None, out=dx, force_bn=BNF)
     else:
-        oc.conv_wgrad(dy, x, dw, stride, (pad, pad), 1, rowscale=scale)
+        oc.conv_wgrad(dy, x, dw, stride, (pad, pad), 1, rowscale=scale, force_bn=BNF, force_splits=int(os.environ.get('SPLITS','0')))
 
 
 for _ in range(3):
