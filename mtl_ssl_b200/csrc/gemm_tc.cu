@@ -54,6 +54,7 @@ struct Params {
   const bf16* mask; long long ldm;
   int relu;
   float alpha;
+  int epi_tma;               // FPROP/DGRAD bf16 output (and bf16 residual) move through smem + TMA
 };
 
 // ----------------------------------------------------------------------------- PTX helpers
@@ -127,6 +128,24 @@ __device__ __forceinline__ void tma_load_im2col(uint32_t dst, const CUtensorMap*
         "h"((unsigned short)offw), "h"((unsigned short)offh)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src),
                "r"(src_bytes)
@@ -192,14 +211,15 @@ template <int BN> struct Cfg {
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int TMEM_COLS = 2 * BN;   // double-buffered accumulator (power of two >= 32)
-  static constexpr int BAR_BYTES = 8 * (2 * STAGES + 4) + 16;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // + alignment slack
+  static constexpr int EPI_BYTES = 4 * 8192;   // per epilogue warp: 2 output + 2 residual 32x32 bf16 tiles
+  static constexpr int BAR_BYTES = 8 * (2 * STAGES + 4) + 16 + 8 * 8;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;  // + alignment slack
 };
 
 template <int MODE, int BN, bool GATHER>
 __global__ void __launch_bounds__(GATHER ? 384 : 256, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const Params p) {
+               const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR, const Params p) {
   using C = Cfg<BN>;
   constexpr int STAGES = C::STAGES;
   constexpr bool A_MN = (MODE == WGRAD);
@@ -210,12 +230,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + STAGES * C::STAGE_BYTES;
+  const uint32_t epi_base = smem_base + STAGES * C::STAGE_BYTES;
+  const uint32_t bar_base = epi_base + C::EPI_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+  auto res_bar = [&](int q, int b) { return bar_base + 8u * (2 * STAGES + 4) + 16u + 8u * (q * 2 + b); };
   auto stage_a = [&](int s) { return smem_base + s * C::STAGE_BYTES; };
   auto stage_b = [&](int s) { return smem_base + s * C::STAGE_BYTES + A_STAGE_BYTES; };
 
@@ -231,6 +253,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), 128);
     }
+    for (int q = 0; q < 4; ++q)
+      for (int b = 0; b < 2; ++b) mbar_init(res_bar(q, b), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -365,6 +389,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int quad = warp & 3;              // TMEM lane quadrant this warp may access
     const int row = quad * 32 + lane;
     uint32_t tcount = 0;
+    uint32_t gchunk = 0;                    // running 32-column chunk counter (staging buffer parity)
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
       const int split = tile / tiles_mn;
       const int rem = tile - split * tiles_mn;
@@ -404,6 +429,121 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               atomicAdd(reinterpret_cast<float4*>(o) + j, make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]));
           }
         }
+      } else if (p.epi_tma) {
+        // Output (and residual) tiles travel through swizzled shared memory and TMA: no per-thread
+        // 64-byte strided global accesses, rows/columns outside the tensor are clipped by hardware.
+        const bool has_res = p.res != nullptr;
+        const bool mask_vec = p.mask && (p.ldm & 7) == 0;
+        const int m0w = m_tile * BM + quad * 32;
+        const uint32_t ebase = epi_base + quad * 8192;
+        const uint32_t swz = ((uint32_t)(lane >> 1) & 3u);
+        uint4 mnext[4];
+        auto prefetch = [&](int c, uint32_t gcn) {
+          const long long n0 = ncol0 + c * 32;
+          if (has_res && lane == 0 && n0 < p.N) {
+            const uint32_t rb = res_bar(quad, gcn & 1u);
+            mbar_arrive_expect_tx(rb, 2048u);
+            tma_load_2d(ebase + 4096u + (gcn & 1u) * 2048u, &tmR, rb, (int)n0, m0w);
+          }
+          if (mask_vec && row_ok && (p.N - n0 >= 32)) {
+            const uint4* r = reinterpret_cast<const uint4*>(p.mask + (long long)m * p.ldm + n0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) mnext[j] = __ldg(r + j);
+          }
+        };
+        prefetch(0, gchunk);
+#pragma unroll 1
+        for (int c = 0; c < NCH; ++c, ++gchunk) {
+          tmem_ld_wait();
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          uint4 mcur[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) mcur[j] = mnext[j];
+          if (c + 1 < NCH) {
+            tmem_ld32(taddr + (c + 1) * 32, v);
+            prefetch(c + 1, gchunk + 1);
+          } else {
+            tcgen05_fence_before();
+            mbar_arrive(tempty_bar(acc));       // accumulator fully drained: the MMA warp may reuse it
+          }
+          const long long n0 = ncol0 + c * 32;
+          if (n0 >= p.N) continue;
+          const int nvalid = (int)min((long long)32, (long long)p.N - n0);
+          const bool vec = (nvalid == 32);
+          const uint32_t buf = gchunk & 1u;
+          if (p.bias) {
+            if (vec) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + j);
+                f[4 * j] += t.x; f[4 * j + 1] += t.y; f[4 * j + 2] += t.z; f[4 * j + 3] += t.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < nvalid) f[j] += __ldg(p.bias + n0 + j);
+            }
+          }
+          if (has_res) {
+            mbar_wait(res_bar(quad, buf), (gchunk >> 1) & 1u);
+            const uint32_t rrow = ebase + 4096u + buf * 2048u + lane * 64u;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 t = lds128(rrow + ((j ^ swz) << 4));
+              const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                f[8 * j + 2 * q] += __uint_as_float(w[q] << 16);
+                f[8 * j + 2 * q + 1] += __uint_as_float(w[q] & 0xffff0000u);
+              }
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
+          }
+          if (p.mask && row_ok) {
+            if (vec && mask_vec) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint32_t w[4] = {mcur[j].x, mcur[j].y, mcur[j].z, mcur[j].w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  if (!(__uint_as_float(w[q] << 16) > 0.0f)) f[8 * j + 2 * q] = 0.0f;
+                  if (!(__uint_as_float(w[q] & 0xffff0000u) > 0.0f)) f[8 * j + 2 * q + 1] = 0.0f;
+                }
+              }
+            } else {
+              const bf16* r = p.mask + (long long)m * p.ldm + n0;
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < nvalid && !(__bfloat162float(r[j]) > 0.0f)) f[j] = 0.0f;
+            }
+          }
+          // the TMA store issued two chunks ago must have finished reading this staging buffer
+          if (lane == 0) bulk_wait_read<1>();
+          __syncwarp();
+          const uint32_t orow = ebase + buf * 2048u + lane * 64u;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint32_t w[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const __nv_bfloat162 h = __floats2bfloat162_rn(f[8 * j + 2 * q], f[8 * j + 2 * q + 1]);
+              w[q] = *reinterpret_cast<const uint32_t*>(&h);
+            }
+            sts128(orow + ((j ^ swz) << 4), make_uint4(w[0], w[1], w[2], w[3]));
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmO, ebase + buf * 2048u, (int)n0, m0w);
+            bulk_commit();
+          }
+        }
+        continue;     // tempty already signalled
       } else {
         const bool res_bf16 = p.res && !p.res_fp32 && (p.ldr & 7) == 0;
         const bool mask_vec = p.mask && (p.ldm & 7) == 0;
@@ -545,6 +685,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tcgen05_fence_before();
       mbar_arrive(tempty_bar(acc));
     }
+    if (MODE != WGRAD && p.epi_tma && lane == 0) bulk_wait_all();
   } else if (GATHER && warp >= 8) {
     // ============================ im2col gather warps ==================================
     // Each of the 128 threads owns one 128-byte row (FPROP/DGRAD: one output pixel of the A
@@ -710,7 +851,7 @@ static EncodeTiledFn get_encode_fn() {
 
 // 2-D bf16 row-major matrix [rows, cols] with row pitch ld (elements); box = 64 cols x box_rows.
 static int make_map(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld,
-                    int box_rows) {
+                    int box_rows, int box_cols = 64, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) { mtl_set_error("gemm_tc: cuTensorMapEncodeTiled unavailable"); return MTL_ERR_CUDA; }
   if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld & 7)) {
@@ -719,10 +860,10 @@ static int make_map(CUtensorMap* map, const void* base, long long rows, long lon
   }
   cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1u, 1u};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { mtl_set_error("gemm_tc: cuTensorMapEncodeTiled failed (%d)", (int)r); return MTL_ERR_CUDA; }
   return MTL_OK;
@@ -775,7 +916,8 @@ static int make_im2col_map(CUtensorMap* map, const void* base, int N, int H, int
 }
 
 template <int MODE, int BN, bool GATHER>
-static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const Params& p, cudaStream_t stream) {
+static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const CUtensorMap& tmR,
+                  const Params& p, cudaStream_t stream) {
   using C = Cfg<BN>;
   auto kern = tc_gemm_kernel<MODE, BN, GATHER>;
   static bool attr_set = false;
@@ -798,7 +940,7 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const Params& 
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = no_pdl ? 0 : 1;
-  cudaError_t le = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p);
+  cudaError_t le = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmO, tmR, p);
   if (le != cudaSuccess) {
     mtl_set_error("tc_gemm_kernel: launch failed: %s", cudaGetErrorString(le));
     (void)cudaGetLastError();
@@ -809,11 +951,12 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const Params& 
 }
 
 template <int MODE, bool GATHER>
-static int dispatch_bn(int bn, const CUtensorMap& a, const CUtensorMap& b, const Params& p, cudaStream_t st) {
+static int dispatch_bn(int bn, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& o,
+                       const CUtensorMap& r, const Params& p, cudaStream_t st) {
   switch (bn) {
-    case 256: return launch<MODE, 256, GATHER>(a, b, p, st);
-    case 128: return launch<MODE, 128, GATHER>(a, b, p, st);
-    case 64: return launch<MODE, 64, GATHER>(a, b, p, st);
+    case 256: return launch<MODE, 256, GATHER>(a, b, o, r, p, st);
+    case 128: return launch<MODE, 128, GATHER>(a, b, o, r, p, st);
+    case 64: return launch<MODE, 64, GATHER>(a, b, o, r, p, st);
   }
   mtl_set_error("gemm_tc: unsupported BN %d", bn);
   return MTL_ERR_UNSUPPORTED;
@@ -940,10 +1083,25 @@ extern "C" int mtl_conv_tc(const mtl_conv_args* a, cudaStream_t stream) {
   p.div_ow = make_fast_div(p.oW);
   p.tiles_m = ceil_div(p.M, BM);
   p.tiles_n = (a->mode == WGRAD) ? p.N / bn : ceil_div(p.N, bn);
-  if (a->mode == FPROP) return gather ? dispatch_bn<FPROP, true>(bn, tmA, tmB, p, stream)
-                                      : dispatch_bn<FPROP, false>(bn, tmA, tmB, p, stream);
-  if (a->mode == DGRAD) return gather ? dispatch_bn<DGRAD, true>(bn, tmA, tmB, p, stream)
-                                      : dispatch_bn<DGRAD, false>(bn, tmA, tmB, p, stream);
-  return gather ? dispatch_bn<WGRAD, true>(bn, tmA, tmB, p, stream)
-                : dispatch_bn<WGRAD, false>(bn, tmA, tmB, p, stream);
+  // epilogue through shared memory + TMA whenever the output (and residual) are plain bf16 matrices
+  CUtensorMap tmO, tmR;
+  memset(&tmO, 0, sizeof(tmO)); memset(&tmR, 0, sizeof(tmR));
+  static const bool no_epi_tma = getenv("MTL_NO_TMA_EPILOGUE") != nullptr;
+  p.epi_tma = 0;
+  if (a->mode != WGRAD && !no_epi_tma && !a->out_fp32 && (p.ldo & 7) == 0 &&
+      (reinterpret_cast<uintptr_t>(a->out) & 15) == 0 &&
+      (!a->res || (!a->res_fp32 && (p.ldr & 7) == 0 && (reinterpret_cast<uintptr_t>(a->res) & 15) == 0))) {
+    if ((rc = make_map(&tmO, a->out, p.M, p.N, p.ldo, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+    if (a->res && (rc = make_map(&tmR, a->res, p.M, p.N, p.ldr, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+    if (!a->res) tmR = tmO;
+    p.epi_tma = 1;
+  } else {
+    tmO = tmB; tmR = tmB;
+  }
+  if (a->mode == FPROP) return gather ? dispatch_bn<FPROP, true>(bn, tmA, tmB, tmO, tmR, p, stream)
+                                      : dispatch_bn<FPROP, false>(bn, tmA, tmB, tmO, tmR, p, stream);
+  if (a->mode == DGRAD) return gather ? dispatch_bn<DGRAD, true>(bn, tmA, tmB, tmO, tmR, p, stream)
+                                      : dispatch_bn<DGRAD, false>(bn, tmA, tmB, tmO, tmR, p, stream);
+  return gather ? dispatch_bn<WGRAD, true>(bn, tmA, tmB, tmO, tmR, p, stream)
+                : dispatch_bn<WGRAD, false>(bn, tmA, tmB, tmO, tmR, p, stream);
 }
