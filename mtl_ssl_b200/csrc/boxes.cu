@@ -247,7 +247,6 @@ nms_kernel(const float4* __restrict__ boxes, const float* __restrict__ scores, c
         if (m) { nxt = (w << 5) + __ffs(m) - 1; break; }
       }
       if (nxt < 0) break;
-      __syncthreads();                       // everyone has read `alive` before it changes
       if (threadIdx.x == nxt) {
         kb[nkept] = me; ka[nkept] = area;
         const long long o = (long long)b * max_out + nkept;
@@ -255,16 +254,10 @@ nms_kernel(const float4* __restrict__ boxes, const float* __restrict__ scores, c
         if (out_scores) out_scores[o] = scores[(long long)b * N + idx];
         if (out_idx) out_idx[o] = idx;
       }
-      __syncthreads();
-      bool dead = false;
-      if (live && (int)threadIdx.x > nxt) dead = nms_iou_gt(me, area, kb[nkept], ka[nkept], thr);
-      if (dead) live = false;
+      __syncthreads();                       // kept box visible; every thread has read `alive`
+      if (live && (int)threadIdx.x > nxt && nms_iou_gt(me, area, kb[nkept], ka[nkept], thr)) live = false;
       const unsigned bal2 = __ballot_sync(0xffffffffu, live && (int)threadIdx.x > nxt);
-      __syncthreads();
-      if (lane == 0) {
-        // bits <= nxt are irrelevant from now on (cur moves past them)
-        alive[warp] = bal2;
-      }
+      if (lane == 0) alive[warp] = bal2;     // bits <= nxt are irrelevant from now on (cur moves past them)
       __syncthreads();
       ++nkept;
       cur = nxt + 1;
@@ -356,54 +349,131 @@ __global__ void force_match_kernel(const int* __restrict__ num_gt, int Gmax, int
 // code: 1 positive candidate (match >= 0), 0 negative candidate (match == -1), else excluded.
 __device__ __forceinline__ int sample_code(int m) { return m >= 0 ? 1 : (m == -1 ? 0 : -1); }
 
-__global__ void sampler_count_kernel(const int* __restrict__ match, int N, int* __restrict__ counts /*[B,4]*/) {
-  const int b = blockIdx.y;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int code = i < N ? sample_code(match[(long long)b * N + i]) : -1;
-  const unsigned bp = __ballot_sync(0xffffffffu, code == 1);
-  const unsigned bn = __ballot_sync(0xffffffffu, code == 0);
-  if ((threadIdx.x & 31) == 0) {
-    if (bp) atomicAdd(counts + b * 4 + 0, __popc(bp));
-    if (bn) atomicAdd(counts + b * 4 + 1, __popc(bn));
-  }
+// order-preserving float -> uint map (handles negative keys too)
+__device__ __forceinline__ unsigned key_bits(float k) {
+  const unsigned u = __float_as_uint(k);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 
-// selected iff rank among same-class candidates (ascending key, ties lower index) < quota
-__global__ void __launch_bounds__(RS_THREADS)
-sampler_select_kernel(const int* __restrict__ match, const float* __restrict__ keys, int N, int batch_size,
-                      int max_pos, int* __restrict__ counts, unsigned char* __restrict__ sampled) {
-  __shared__ float tk[RS_TILE];
-  __shared__ signed char tc[RS_TILE];
-  const int b = blockIdx.y;
+// One block per image: exact selection of the `quota` smallest (key, index) pairs per class by a
+// 2048-bin radix histogram on the key bits, a block scan to find the threshold bin, and an exact
+// rank among the few candidates that fall INTO the threshold bin.  O(N) work instead of O(N^2).
+constexpr int SB_BINS = 2048;
+constexpr int SB_LIST = 2048;
+__global__ void __launch_bounds__(1024)
+sampler_kernel(const int* __restrict__ match, const float* __restrict__ keys, int N, int batch_size, int max_pos,
+               int* __restrict__ counts, unsigned char* __restrict__ sampled) {
+  __shared__ int hist[2][SB_BINS];
+  __shared__ int list[2][SB_LIST];
+  __shared__ int wsum[33];
+  __shared__ int s_tot[2], s_thr[2], s_before[2], s_nlist[2];
+  const int b = blockIdx.x;
   const int* mt = match + (long long)b * N;
   const float* ky = keys + (long long)b * N;
-  const int i = blockIdx.x * RS_THREADS + threadIdx.x;
-  const int code = i < N ? sample_code(mt[i]) : -1;
-  const float mykey = i < N ? ky[i] : 0.0f;
-  const int npos = counts[b * 4 + 0], nneg = counts[b * 4 + 1];
+  unsigned char* out = sampled + (long long)b * N;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 2 * SB_BINS; i += blockDim.x) (&hist[0][0])[i] = 0;
+  if (tid < 2) { s_tot[tid] = 0; s_thr[tid] = -1; s_before[tid] = 0; s_nlist[tid] = 0; }
+  __syncthreads();
+  for (int i = tid; i < N; i += blockDim.x) {
+    const int c = sample_code(mt[i]);
+    if (c >= 0) atomicAdd(&hist[c][key_bits(ky[i]) >> 21], 1);
+  }
+  __syncthreads();
+  // class totals
+  for (int c = 0; c < 2; ++c) {
+    int v = 0;
+    for (int i = tid; i < SB_BINS; i += blockDim.x) v += hist[c][i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((tid & 31) == 0 && v) atomicAdd(&s_tot[c], v);
+  }
+  __syncthreads();
+  const int npos = s_tot[1], nneg = s_tot[0];
   const int take_pos = min(npos, max_pos);
   const int take_neg = min(nneg, batch_size - take_pos);
-  const int quota = code == 1 ? take_pos : take_neg;
-  int rank = 0;
-  for (int t0 = 0; t0 < N; t0 += RS_TILE) {
-    const int n = min(RS_TILE, N - t0);
-    __syncthreads();
-    for (int t = threadIdx.x; t < n; t += RS_THREADS) {
-      tk[t] = ky[t0 + t];
-      tc[t] = (signed char)sample_code(mt[t0 + t]);
+  // threshold bin per class: exclusive prefix < quota <= inclusive prefix (2 bins per thread)
+  for (int c = 0; c < 2; ++c) {
+    const int quota = c == 1 ? take_pos : take_neg;
+    const int h0 = hist[c][2 * tid], h1 = hist[c][2 * tid + 1];
+    const int mine = h0 + h1;
+    int incl = mine;
+    const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
     }
     __syncthreads();
-    if (code >= 0) {
-      for (int t = 0; t < n; ++t) {
-        const bool same = tc[t] == code;
-        const float kt = tk[t];
-        const bool less = (kt < mykey) || (kt == mykey && (t0 + t) < i);
-        rank += (same && less);
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      const int v = wsum[lane];
+      int wi = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, wi, o);
+        if (lane >= o) wi += t;
+      }
+      wsum[lane] = wi - v;
+    }
+    __syncthreads();
+    const int excl = wsum[warp] + incl - mine;
+    if (quota > 0) {
+      if (excl < quota && quota <= excl + h0) { s_thr[c] = 2 * tid; s_before[c] = excl; }
+      else if (excl + h0 < quota && quota <= excl + mine) { s_thr[c] = 2 * tid + 1; s_before[c] = excl + h0; }
+    }
+  }
+  __syncthreads();
+  // decide everything outside the threshold bins, collect the candidates inside them
+  for (int i = tid; i < N; i += blockDim.x) {
+    const int c = sample_code(mt[i]);
+    unsigned char sel = 0;
+    if (c >= 0) {
+      const int bin = (int)(key_bits(ky[i]) >> 21);
+      if (bin < s_thr[c]) sel = 1;
+      else if (bin == s_thr[c]) {
+        const int pos = atomicAdd(&s_nlist[c], 1);
+        if (pos < SB_LIST) list[c][pos] = i;
+      }
+    }
+    out[i] = sel;
+  }
+  __syncthreads();
+  for (int c = 0; c < 2; ++c) {
+    const int quota = (c == 1 ? take_pos : take_neg) - s_before[c];
+    const int m = s_nlist[c];
+    if (m <= SB_LIST) {
+      for (int e = tid; e < m; e += blockDim.x) {
+        const int i = list[c][e];
+        const float ki = ky[i];
+        int rank = 0;
+        for (int f = 0; f < m; ++f) {
+          const int j = list[c][f];
+          const float kj = ky[j];
+          rank += (kj < ki) || (kj == ki && j < i);
+        }
+        out[i] = rank < quota ? 1 : 0;
+      }
+    } else {
+      // pathological tie mass (more than SB_LIST equal-bin keys): exact but O(m N)
+      const int thr = s_thr[c];
+      for (int i = tid; i < N; i += blockDim.x) {
+        if (sample_code(mt[i]) != c || (int)(key_bits(ky[i]) >> 21) != thr) continue;
+        const float ki = ky[i];
+        int rank = 0;
+        for (int j = 0; j < N; ++j) {
+          if (sample_code(mt[j]) != c || (int)(key_bits(ky[j]) >> 21) != thr) continue;
+          const float kj = ky[j];
+          rank += (kj < ki) || (kj == ki && j < i);
+        }
+        out[i] = rank < quota ? 1 : 0;
       }
     }
   }
-  if (i < N) sampled[(long long)b * N + i] = (code >= 0 && rank < quota) ? 1 : 0;
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
+  if (tid == 0) {
+    counts[b * 4 + 0] = npos;
+    counts[b * 4 + 1] = nneg;
     counts[b * 4 + 2] = take_pos;
     counts[b * 4 + 3] = take_pos + take_neg;     // number of sampled entries (the RPN normaliser)
   }
@@ -648,15 +718,9 @@ extern "C" int mtl_balanced_sample(const int* match, const float* keys, int B, i
                                    float positive_fraction, unsigned char* sampled, int* counts,
                                    cudaStream_t stream) {
   MTL_CHECK_ARG(match && keys && sampled && counts && B > 0 && N > 0, "mtl_balanced_sample: bad args");
-  cudaError_t e = cudaMemsetAsync(counts, 0, sizeof(int) * 4 * B, stream);
-  if (e != cudaSuccess) { mtl_set_error("mtl_balanced_sample: memset: %s", cudaGetErrorString(e)); return MTL_ERR_CUDA; }
   const int max_pos = (int)(positive_fraction * (float)batch_size);   // int(frac * batch) (bpns:72)
-  dim3 g1(ceil_div(N, 256), B);
-  sampler_count_kernel<<<g1, 256, 0, stream>>>(match, N, counts);
-  MTL_CUDA_LAUNCH_CHECK("sampler_count_kernel");
-  dim3 g2(ceil_div(N, RS_THREADS), B);
-  sampler_select_kernel<<<g2, RS_THREADS, 0, stream>>>(match, keys, N, batch_size, max_pos, counts, sampled);
-  MTL_CUDA_LAUNCH_CHECK("sampler_select_kernel");
+  sampler_kernel<<<B, 1024, 0, stream>>>(match, keys, N, batch_size, max_pos, counts, sampled);
+  MTL_CUDA_LAUNCH_CHECK("sampler_kernel");
   return MTL_OK;
 }
 

@@ -116,6 +116,35 @@ opt_apply_kernel(const mtl_tensor_desc* __restrict__ td, const mtl_chunk_desc* _
     factor = clip / fmaxf(norm, clip);                  // tf.clip_by_norm
   }
   const float gm = t.grad_mult * gscale;
+  if ((base & 3) == 0 && (c.len & 3) == 0 && (t.scale_off < 0 || (t.row_len & 3) == 0)) {
+    // vector path: 4 parameters per thread, 16-byte loads / stores (8-byte for the bf16 copy)
+    for (int i = threadIdx.x * 4; i < c.len; i += 256 * 4) {
+      const long long o = base + i;
+      const float4 w = *reinterpret_cast<const float4*>(params + o);
+      const float4 g4 = *reinterpret_cast<const float4*>(grads + o);
+      const float4 m4 = *reinterpret_cast<const float4*>(mom + o);
+      const float sc = t.scale_off >= 0 ? fold_scales[t.scale_off + (c.start + i) / t.row_len] : 1.0f;
+      float wv[4] = {w.x, w.y, w.z, w.w};
+      const float gv[4] = {g4.x, g4.y, g4.z, g4.w};
+      float mv[4] = {m4.x, m4.y, m4.z, m4.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float g = (gv[e] * gm + t.l2_weight * wv[e]) * factor;
+        mv[e] = momentum * mv[e] + g;
+        wv[e] = wv[e] - lr * mv[e];
+      }
+      *reinterpret_cast<float4*>(mom + o) = make_float4(mv[0], mv[1], mv[2], mv[3]);
+      *reinterpret_cast<float4*>(params + o) = make_float4(wv[0], wv[1], wv[2], wv[3]);
+      *reinterpret_cast<float4*>(grads + o) = make_float4(0.f, 0.f, 0.f, 0.f);
+      __nv_bfloat162 lo = __floats2bfloat162_rn(wv[0] * sc, wv[1] * sc);
+      __nv_bfloat162 hi = __floats2bfloat162_rn(wv[2] * sc, wv[3] * sc);
+      uint2 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&lo);
+      pk.y = *reinterpret_cast<uint32_t*>(&hi);
+      *reinterpret_cast<uint2*>(params_bf16 + o) = pk;
+    }
+    return;
+  }
   for (int i = threadIdx.x; i < c.len; i += 256) {
     const long long o = base + i;
     const float w = params[o];

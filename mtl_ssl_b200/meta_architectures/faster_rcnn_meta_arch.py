@@ -35,6 +35,42 @@ LOSS_KEYS = ["first_stage_localization_loss", "first_stage_objectness_loss", "se
              "edgemask_loss", "refined_classification_loss"]
 
 
+class _Lanes(object):
+    """Named side streams + events: the independent second-stage chains (closeness tail, window tail,
+    forward-only refine windows, edge mask) run concurrently with the main chain; cross-chain
+    dependencies are events, which CUDA-graph capture turns into graph edges."""
+
+    def __init__(self):
+        self.streams, self.events = {}, {}
+
+    def mark(self, name):
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        self.events[name] = ev
+
+    def run(self, lane, after=()):
+        import contextlib
+        if not Concurrency.enabled:
+            return contextlib.nullcontext()
+        if lane not in self.streams:
+            self.streams[lane] = torch.cuda.Stream()
+        s = self.streams[lane]
+        for n in after:
+            s.wait_event(self.events[n])
+        return torch.cuda.stream(s)
+
+    def wait(self, *names):
+        if not Concurrency.enabled:
+            return
+        cur = torch.cuda.current_stream()
+        for n in names:
+            if n in self.events:
+                cur.wait_event(self.events[n])
+
+    def reset(self):
+        self.events = {}
+
+
 class PredictionDict(dict):
     """dict whose values may be thunks: API tensors (reshaped views of the fused kernel outputs)
     are materialised only when somebody reads them, keeping the training hot path copy-free."""
@@ -117,6 +153,7 @@ class FasterRCNNMetaArch(model.DetectionModel):
         self._store = ParamStore()
         self._anchor_cache = {}
         self._sampler_keys = None
+        self._lanes = _Lanes()
         self._create_variables(first_stage_box_predictor_arg_scope, first_stage_box_predictor_trainable)
         if device is not None:          # device=None: variable table only (host-side inspection)
             self._store.finalize(device, seed)
@@ -275,7 +312,9 @@ class FasterRCNNMetaArch(model.DetectionModel):
         ws, fe = self._ws, self._feature_extractor
         B, H, W, _ = preprocessed_inputs.shape
         image_shape = (B, H, W, 3)
+        self._lanes.reset()
         feat = fe.extract_proposal_features(preprocessed_inputs, self.first_stage_feature_extractor_scope, ws)
+        self._lanes.mark("feat")
         _, Hf, Wf, Cf = feat.shape
         anchors, keep_idx, Nk = self._anchors(Hf, Wf, H, W)
         rpn_feat = self._rpn_conv.fwd(feat, ws.get("rpn/conv", (B, Hf, Wf, self._rpn_conv.cout)))
@@ -366,6 +405,7 @@ class FasterRCNNMetaArch(model.DetectionModel):
         feat = pd["rpn_features_to_crop"]
         maps, pre_pool = self._compute_second_stage_input_feature_maps(
             feat, prop_norm.view(B * P, 4), self._box_ind(B, P, "props"), "props")
+        self._lanes.mark("crops")
         cls_feat = fe.extract_box_classifier_features(maps, self.second_stage_feature_extractor_scope, ws, "main")
         bp = self._mask_rcnn_box_predictor.predict(cls_feat, 1, self.second_stage_box_predictor_scope, ws=ws,
                                                    tag="main", boxes_normalized=prop_norm.view(B * P, 4))
@@ -376,15 +416,17 @@ class FasterRCNNMetaArch(model.DetectionModel):
             "_head_out": bp["_raw"], "_proposal_maps": maps, "_proposal_prepool": pre_pool,
         }
         if mtl is not None and mtl.closeness:
-            cfeat = fe.extract_box_classifier_features(maps, self.closeness_box_predictor_scope, ws, "close")
-            cp = self._closeness_box_predictor.predict_class(cfeat, self.closeness_box_predictor_scope, ws=ws,
-                                                             tag="close")
+            with self._lanes.run("close", after=["crops"]):
+                cfeat = fe.extract_box_classifier_features(maps, self.closeness_box_predictor_scope, ws, "close")
+                cp = self._closeness_box_predictor.predict_class(cfeat, self.closeness_box_predictor_scope, ws=ws,
+                                                                 tag="close")
+                self._lanes.mark("close_fwd")
             out["closeness_predictions"] = lambda: cp[CLASS_PREDICTIONS]().squeeze(1)
             out["_close_out"] = cp["_raw"]
         return out
 
     def predict_with_window(self, prediction_dict, window_boxes_normalized=None, _tag="win", _keep=True,
-                            _box_ind=None):
+                            _box_ind=None, _pre=None):
         """fmA:721-755."""
         ws, fe = self._ws, self._feature_extractor
         feat = prediction_dict["rpn_features_to_crop"]
@@ -398,10 +440,15 @@ class FasterRCNNMetaArch(model.DetectionModel):
             wb = wb.reshape(-1, 4)
         else:
             box_ind = _box_ind          # rank-2 boxes: all box_ind = 0 in the reference (fmA:1330-1332)
-        maps, pre_pool = self._compute_second_stage_input_feature_maps(feat, wb, box_ind, _tag)
-        wfeat = fe.extract_box_classifier_features(maps, self.window_box_predictor_scope, ws, _tag, keep=_keep)
-        wp = self._window_box_predictor.predict_class(wfeat, self.window_box_predictor_scope, ws=ws, tag=_tag,
-                                                      activation_fn=None)
+        lane, after = ("win", ["feat"]) if _tag == "win" else ("ref", ["crops"])
+        with self._lanes.run(lane, after=after):
+            if _pre is not None:
+                _pre()
+            maps, pre_pool = self._compute_second_stage_input_feature_maps(feat, wb, box_ind, _tag)
+            wfeat = fe.extract_box_classifier_features(maps, self.window_box_predictor_scope, ws, _tag, keep=_keep)
+            wp = self._window_box_predictor.predict_class(wfeat, self.window_box_predictor_scope, ws=ws, tag=_tag,
+                                                          activation_fn=None)
+            self._lanes.mark(lane + "_fwd")
         prediction_dict["window_class_predictions"] = lambda: wp[CLASS_PREDICTIONS]().squeeze(1)
         prediction_dict["_%s_out" % _tag] = wp["_raw"]
         prediction_dict["_%s_boxes" % _tag] = (wb, box_ind, pre_pool)
@@ -412,7 +459,9 @@ class FasterRCNNMetaArch(model.DetectionModel):
         feat = prediction_dict["rpn_features_to_crop"]
         B, Hf, Wf, _ = feat.shape
         act = self._ws.get("edgemask/act", (B, Hf, Wf, 2), torch.float32)
-        r = self._edgemask_predictor.predict(feat, self.edgemask_predictor_scope, out=act)
+        with self._lanes.run("win", after=["feat"]):
+            r = self._edgemask_predictor.predict(feat, self.edgemask_predictor_scope, out=act)
+            self._lanes.mark("em_fwd")
         prediction_dict["edgemask_predictions"] = r[MASK_PREDICTIONS]
         return prediction_dict
 
@@ -433,18 +482,20 @@ class FasterRCNNMetaArch(model.DetectionModel):
             E = 5
             exp = ws.get("refine/expand", (E, B, P, 4), torch.float32)
             bi = ws.get("refine/box_ind", (E, B, P), torch.int32)
-            ops.call("mtl_expand_windows", prediction_dict["proposal_boxes_normalized"], B, P, E - 1, exp, bi)
+            pbn = prediction_dict["proposal_boxes_normalized"]
             wpd = PredictionDict()
             wpd["rpn_features_to_crop"] = prediction_dict["rpn_features_to_crop"]
             wpd["image_shape"] = prediction_dict["image_shape"]
             self.predict_with_window(wpd, window_boxes_normalized=exp.view(E * B * P, 4), _tag="refine",
-                                     _keep=False, _box_ind=bi.view(-1))
+                                     _keep=False, _box_ind=bi.view(-1),
+                                     _pre=lambda: ops.call("mtl_expand_windows", pbn, B, P, E - 1, exp, bi))
             win_out = wpd["_refine_out"]
             prediction_dict["expand_window_class_predictions"] = \
                 lambda: win_out[:, :K1].reshape(E, B * P, K1).transpose(0, 1)
         close_out = prediction_dict.get("_close_out") if mtl.closeness else None
         if close_out is not None and not mtl.global_closeness:
             raise ValueError("global_closeness: false is not supported on the B200 path")
+        self._lanes.wait("ref_fwd", "close_fwd")
         nf = self._refine_nf
         cat = ws.get("refine/in", (B * P, nf), torch.float32)
         wl = self._window_box_predictor.layout(self.window_box_predictor_scope)["ld"] if mtl.window else 0
@@ -468,6 +519,7 @@ class FasterRCNNMetaArch(model.DetectionModel):
         P, K = self.max_num_proposals, self.num_classes
         K1 = K + 1
         gt = self._format_groundtruth_data(pd["image_shape"])
+        self._lanes.wait("win_fwd", "em_fwd", "close_fwd", "ref_fwd")
         losses = ws.get("loss/values", (8,), torch.float32, zero=True)
         Hf, Wf = pd["_feat_hw"]
         lay, Nk, HW = pd["_rpn_layout"], pd["_Nk"], Hf * Wf
@@ -555,36 +607,45 @@ class FasterRCNNMetaArch(model.DetectionModel):
         P = self.max_num_proposals
         stop_aux = mtl is not None and mtl.stop_gradient_for_aux_tasks
         dfeat = ws.get("bwd/dfeat_f32", feat.shape, torch.float32, zero=True)
+        L = self._lanes
         # refiner FC (inputs are behind stop_gradient: weights / bias only)
         if mtl is not None and mtl.refine:
             K1 = self.num_classes + 1
             ops.call("mtl_fc_bwd", pd["_refine_in"], self._refine_nf, self._refine_w.w, ws.bufs["refine/d_out"], K1,
                      B * P, K1, self._refine_nf, self._refine_w.g, self._refine_b.g, None, 0)
-        # closeness tail first so that its crop gradient can ride on the main tail's last dgrad
+        if mtl is not None and mtl.edgemask:     # plain read-modify-write of dfeat: before the atomic scatters start
+            self._edgemask_predictor.backward(self.edgemask_predictor_scope, feat, pd["edgemask_predictions"],
+                                              ws.bufs["edgemask/d_act"], dfeat)
+        L.mark("bwd_start")
+        # closeness and window tails run on their own lanes, concurrently with the main tail
         d_extra = None
         if mtl is not None and mtl.closeness:
-            g = self._closeness_box_predictor.backward(self.closeness_box_predictor_scope, "close",
-                                                       ws.bufs["det/d_close"], ws)
-            d_extra = fe.backward_box_classifier_features(self.closeness_box_predictor_scope, g, ws, "close",
-                                                          need_dx=not stop_aux)
+            with L.run("close", after=["bwd_start"]):
+                g = self._closeness_box_predictor.backward(self.closeness_box_predictor_scope, "close",
+                                                           ws.bufs["det/d_close"], ws)
+                d_extra = fe.backward_box_classifier_features(self.closeness_box_predictor_scope, g, ws, "close",
+                                                              need_dx=not stop_aux)
+                L.mark("close_bwd")
+        if mtl is not None and mtl.window:
+            with L.run("win", after=["bwd_start"]):
+                g = self._window_box_predictor.backward(self.window_box_predictor_scope, "win", ws.bufs["det/d_win"],
+                                                        ws)
+                dwin = fe.backward_box_classifier_features(self.window_box_predictor_scope, g, ws, "win",
+                                                           need_dx=not stop_aux)
+                if not stop_aux:
+                    wb, bi, pre = pd["_win_boxes"]
+                    self._crop_backward(pd, dwin, None, pre, wb, bi, dfeat, "win")
+                L.mark("win_bwd")
         g = self._mask_rcnn_box_predictor.backward(self.second_stage_box_predictor_scope, "main",
                                                    ws.bufs["det/d_head"], ws)
+        # the closeness crop gradient rides on the main tail's last dgrad (residual input of the epilogue)
         dmaps = fe.backward_box_classifier_features(self.second_stage_feature_extractor_scope, g, ws, "main",
-                                                    need_dx=True, dx_extra=d_extra)
+                                                    need_dx=True, dx_extra=d_extra,
+                                                    pre_unit0=lambda: L.wait("close_bwd"))
         self._crop_backward(pd, dmaps, pd["_proposal_maps"], pd["_proposal_prepool"],
                             pd["proposal_boxes_normalized"].view(B * P, 4), self._box_ind(B, P, "props"), dfeat,
                             "props")
-        if mtl is not None and mtl.window:
-            g = self._window_box_predictor.backward(self.window_box_predictor_scope, "win", ws.bufs["det/d_win"], ws)
-            dwin = fe.backward_box_classifier_features(self.window_box_predictor_scope, g, ws, "win",
-                                                       need_dx=not stop_aux)
-            if not stop_aux:
-                wb, bi, pre = pd["_win_boxes"]
-                self._crop_backward(pd, dwin, ws.bufs["crops/win/pool"] if pre is not None else ws.bufs["crops/win"],
-                                    pre, wb, bi, dfeat, "win")
-        if mtl is not None and mtl.edgemask:
-            self._edgemask_predictor.backward(self.edgemask_predictor_scope, feat, pd["edgemask_predictions"],
-                                              ws.bufs["edgemask/d_act"], dfeat)
+        L.wait("win_bwd", "close_bwd")
         # RPN head and conv; the conv's dgrad epilogue merges the fp32 ROI/edgemask gradient and
         # applies the ReLU mask of the trunk output
         rpn_feat = pd["rpn_box_predictor_features"]

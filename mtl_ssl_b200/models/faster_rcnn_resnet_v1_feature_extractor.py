@@ -80,8 +80,9 @@ class FasterRCNNResnetV1FeatureExtractor(FasterRCNNFeatureExtractor):
     def extract_box_classifier_features(self, proposal_feature_maps, scope, ws, tag="main", keep=True):
         return self._tails[scope].fwd(proposal_feature_maps, ws, tag, keep)
 
-    def backward_box_classifier_features(self, scope, grad, ws, tag="main", need_dx=True, dx_extra=None):
-        return self._tails[scope].bwd(grad, ws, tag, need_dx, dx_extra)
+    def backward_box_classifier_features(self, scope, grad, ws, tag="main", need_dx=True, dx_extra=None,
+                                         pre_unit0=None):
+        return self._tails[scope].bwd(grad, ws, tag, need_dx, dx_extra, pre_unit0)
 
 
 class FasterRCNNResnet50FeatureExtractor(FasterRCNNResnetV1FeatureExtractor):

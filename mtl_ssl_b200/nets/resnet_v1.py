@@ -191,7 +191,9 @@ class Block4(object):
             x = u.fwd(x, ws, tag, keep, i % 2)
         return x
 
-    def bwd(self, g, ws, tag, need_dx=True, dx_extra=None):
+    def bwd(self, g, ws, tag, need_dx=True, dx_extra=None, pre_unit0=None):
         for i in (2, 1):
             g = self.units[i].bwd(g, ws, tag)
+        if pre_unit0 is not None:
+            pre_unit0()
         return self.units[0].bwd(g, ws, tag, need_dx=need_dx, mask_x=False, dx_extra=dx_extra)
