@@ -196,6 +196,8 @@ def run_ours(args, rank, world, local_rank):
     # kernels per step, counted by the library itself during one eager replay of the step body
     c0 = ops.launch_count()
     tr._forward_backward(tr.inputs.dev["image"])
+    if world > 1:
+        tr._backward_trunk()
     model.param_store.g.zero_()
     c1 = ops.launch_count()
     launches_per_step = (c1 - c0) + 3          # + optimizer stats, reg-loss, apply
@@ -211,14 +213,7 @@ def run_ours(args, rank, world, local_rank):
     sync()
     e0.record()
     for i in range(args.steps):
-        if tr.use_graph:
-            tr.graph_fb.replay()
-            tr._allreduce()
-            tr.graph_opt.replay()
-        else:
-            tr._forward_backward(tr.inputs.dev["image"])
-            tr._allreduce()
-            tr._optimize()
+        tr._run_step_body()
     e1.record()
     sync()
     ms_dev = e0.elapsed_time(e1)
@@ -243,6 +238,8 @@ def run_ours(args, rank, world, local_rank):
     # ---- roofline of the dominant kernel family, measured live: one eager step with per-launch events
     ops_conv.PROFILE = []
     tr._forward_backward(tr.inputs.dev["image"])
+    if world > 1:
+        tr._backward_trunk()
     torch.cuda.synchronize()
     prof, ops_conv.PROFILE = ops_conv.PROFILE, None
     model.param_store.g.zero_()

@@ -174,6 +174,14 @@ class FasterRCNNMetaArch(model.DetectionModel):
             return self._second_stage_batch_size
         return self._first_stage_max_proposals
 
+    def gradient_buckets(self):
+        """(second-stage bucket, trunk+RPN bucket) as views of the flat gradient arena; the dead
+        stage-1 block4 copy (no task gradient) is excluded from the exchange."""
+        st = self._store
+        first = next(p.offset for p in st.params if p.name.startswith(self.second_stage_feature_extractor_scope))
+        dead = next((p.offset for p in st.params if "/_dead/" in p.name), st.total)
+        return st.g[first:dead], st.g[:first]
+
     @property
     def param_store(self):
         return self._store
@@ -597,10 +605,15 @@ class FasterRCNNMetaArch(model.DetectionModel):
         return loss_dict
 
     # ------------------------------------------------------------------ backward
-    def backward(self, prediction_dict=None):
+    def backward(self, prediction_dict=None, part=None):
         """Explicit reverse pass: accumulates d(sum of task losses)/d(weights) into the gradient
-        arena (`param_store.g`).  Regularisation gradients are added by the optimizer kernel."""
+        arena (`param_store.g`).  Regularisation gradients are added by the optimizer kernel.
+        part="heads" runs the second-stage / aux-head half (everything whose gradients live after the
+        trunk + RPN variables in the arena), part="trunk" the RPN + trunk half; the trainer all-reduces
+        the first half's gradient bucket while the second half computes."""
         pd = prediction_dict or self._last_pd
+        if part == "trunk":
+            return self._backward_trunk(pd)
         ws, fe, mtl = self._ws, self._feature_extractor, self._mtl
         feat = pd["rpn_features_to_crop"]
         B, Hf, Wf, C = feat.shape
@@ -646,6 +659,15 @@ class FasterRCNNMetaArch(model.DetectionModel):
                             pd["proposal_boxes_normalized"].view(B * P, 4), self._box_ind(B, P, "props"), dfeat,
                             "props")
         L.wait("win_bwd", "close_bwd")
+        if part == "heads":
+            Concurrency.join()
+            return
+        self._backward_trunk(pd)
+
+    def _backward_trunk(self, pd):
+        ws, fe = self._ws, self._feature_extractor
+        feat = pd["rpn_features_to_crop"]
+        dfeat = ws.bufs["bwd/dfeat_f32"]
         # RPN head and conv; the conv's dgrad epilogue merges the fp32 ROI/edgemask gradient and
         # applies the ReLU mask of the trunk output
         rpn_feat = pd["rpn_box_predictor_features"]

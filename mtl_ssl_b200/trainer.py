@@ -124,8 +124,11 @@ class Trainer(object):
         if mtl is not None and mtl.refine:
             pd = m.predict_with_mtl_results(pd)
         m.loss(pd)
-        m.backward(pd)
+        m.backward(pd, part="heads" if self.world_size > 1 else None)
         return pd
+
+    def _backward_trunk(self):
+        self.model.backward(None, part="trunk")
 
     def _optimize(self):
         st = self.model.param_store
@@ -137,6 +140,24 @@ class Trainer(object):
 
     def _allreduce(self):
         allreduce_gradients(self.model.param_store.g, self.world_size, self.pg)
+
+    def _run_step_body(self):
+        """forward + backward + gradient exchange + optimizer.  With several replicas the backward is cut
+        in two: the second-stage bucket is all-reduced (NCCL stream) while the trunk half still computes."""
+        graph = self.use_graph
+        if self.world_size == 1:
+            self.graph_fb.replay() if graph else self._forward_backward(self.inputs.dev["image"])
+            self.graph_opt.replay() if graph else self._optimize()
+            return
+        import torch.distributed as dist
+        b_heads, b_trunk = self.model.gradient_buckets()
+        self.graph_fb.replay() if graph else self._forward_backward(self.inputs.dev["image"])
+        w1 = dist.all_reduce(b_heads, op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
+        self.graph_fb2.replay() if graph else self._backward_trunk()
+        w2 = dist.all_reduce(b_trunk, op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
+        w1.wait()
+        w2.wait()
+        self.graph_opt.replay() if graph else self._optimize()
 
     def host_arrays(self, examples, keys):
         arrays = pack_groundtruth(examples, self.model.num_classes, self.H, self.W, self.gmax)
@@ -153,19 +174,9 @@ class Trainer(object):
         self._hyper_host[2] = self.clip_norm if self.clip_norm else 0.0
         st.hyper.copy_(self._hyper_host, non_blocking=True)
         image = self._bind(arrays)
-        if not self.use_graph:
-            self._forward_backward(image)
-            self._allreduce()
-            self._optimize()
-        elif self.graph_fb is None:
+        if self.use_graph and self.graph_fb is None:
             self._capture(image)
-            self.graph_fb.replay()
-            self._allreduce()
-            self.graph_opt.replay()
-        else:
-            self.graph_fb.replay()
-            self._allreduce()
-            self.graph_opt.replay()
+        self._run_step_body()
         self.global_step += 1
         if not read_losses:
             return None
@@ -187,12 +198,18 @@ class Trainer(object):
         snap = (st.w.clone(), st.m.clone(), st.wb.clone())
         for _ in range(2):
             self._forward_backward(image)
+            if self.world_size > 1:
+                self._backward_trunk()
             st.g.zero_()
         st.w.copy_(snap[0]); st.m.copy_(snap[1]); st.wb.copy_(snap[2])
         torch.cuda.synchronize()
         self.graph_fb = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph_fb):
             self._forward_backward(image)
+        if self.world_size > 1:
+            self.graph_fb2 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_fb2):
+                self._backward_trunk()
         self.graph_opt = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph_opt):
             self._optimize()
