@@ -51,10 +51,11 @@ typedef struct mtl_conv_args {
   const float* rowscale;    /* wgrad: per-K scale (frozen BN fold) or NULL */
   const void* res; int res_fp32;   /* added before relu/mask; same shape as out */
   const void* mask;         /* bf16, same shape as out: out = mask > 0 ? out : 0 */
-  int relu;
+  int relu;                 /* 0 none, 1 ReLU, 2 ReLU6 */
   float alpha;              /* wgrad scale */
   int force_bn;             /* 0 = auto tile width */
   int force_splits;         /* 0 = auto split-K */
+  float mask_hi;            /* dgrad: > 0 -> ReLU6 mask: gradient only where 0 < mask < mask_hi */
 } mtl_conv_args;
 int mtl_conv_tc(const mtl_conv_args* args /* host */, mtl_stream_t stream);
 
@@ -127,7 +128,8 @@ int mtl_maxpool_bwd(const void* x, const void* dy, int N, int H, int W, int C, i
 int mtl_avgpool_fwd(const void* x /* bf16 [R,HW,C] */, int R, int HW, int C, void* y /* bf16 [R,C] */,
                     mtl_stream_t stream);
 int mtl_avgpool_bwd(const void* dy, int dy_fp32, long long ldy, const void* relu_mask /* bf16 [R,HW,C] or NULL */,
-                    int R, int HW, int C, void* dx /* bf16 [R,HW,C] */, mtl_stream_t stream);
+                    float mask_hi /* > 0: ReLU6-style upper bound */, int R, int HW, int C,
+                    void* dx /* bf16 [R,HW,C] */, mtl_stream_t stream);
 int mtl_im2col_f32(const float* img /* [B,H,W,C<=4] */, int B, int H, int W, int C, int R, int S, int stride,
                    int pad_h, int pad_w, int P, int Q, const float* mean /* host [C] or NULL */, float scale,
                    void* out /* bf16 [B*P*Q, ld] */, int ld, mtl_stream_t stream);
@@ -136,6 +138,14 @@ int mtl_resize_bilinear_f32(const float* x, int B, int H, int W, int C, int out_
                             mtl_stream_t stream);
 int mtl_preprocess(const float* img, long long total, int C, const float* mean /* host */, float scale, float* out,
                    mtl_stream_t stream);
+/* slim.separable_conv2d depthwise stage (slim/nets/mobilenet_v1.py:230-238); w bf16 [C,3,3];
+ * activation 0 none / 1 ReLU / 2 ReLU6; dgrad masks by (0 < mask [< mask_hi]). */
+int mtl_dwconv3x3_fwd(const void* x, const void* w, const float* bias, int N, int H, int W, int C, int stride,
+                      int pad_h, int pad_w, int P, int Q, int activation, void* y, mtl_stream_t stream);
+int mtl_dwconv3x3_dgrad(const void* dy, const void* w, int N, int H, int W, int C, int stride, int pad_h, int pad_w,
+                        int P, int Q, const void* mask, float mask_hi, void* dx, mtl_stream_t stream);
+int mtl_dwconv3x3_wgrad(const void* dy, const void* x, int N, int H, int W, int C, int stride, int pad_h, int pad_w,
+                        int P, int Q, const float* scale, float* dw /* fp32 [C,3,3], += */, mtl_stream_t stream);
 int mtl_psroi_fwd(const void* feat /* bf16 [B,H,W,nby*nbx*D] */, int B, int H, int W, int D, int nby, int nbx,
                   int crop_h, int crop_w, const float* boxes, const int* box_ind, int R, float* out /* [R,D] */,
                   mtl_stream_t stream);

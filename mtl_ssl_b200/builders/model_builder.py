@@ -11,6 +11,7 @@ from ..core.hyperparams import Hyperparams
 from ..core.mask_predictor import MaskPredictor
 from ..core import preprocessor
 from ..meta_architectures import faster_rcnn_meta_arch
+from ..models import faster_rcnn_mobilenet_v1_feature_extractor as frcnn_mobilenet_v1
 from ..models import faster_rcnn_resnet_v1_feature_extractor as frcnn_resnet_v1
 
 # model_builder.py:50-66
@@ -18,6 +19,7 @@ FASTER_RCNN_FEATURE_EXTRACTOR_CLASS_MAP = {
     "faster_rcnn_resnet50": frcnn_resnet_v1.FasterRCNNResnet50FeatureExtractor,
     "faster_rcnn_resnet101": frcnn_resnet_v1.FasterRCNNResnet101FeatureExtractor,
     "faster_rcnn_resnet152": frcnn_resnet_v1.FasterRCNNResnet152FeatureExtractor,
+    "frcnn_mobilenet_v1": frcnn_mobilenet_v1.FasterRCNNMobilenetV1FeatureExtractor,
 }
 
 

@@ -139,6 +139,7 @@ class MaskRCNNBoxPredictor(BoxPredictor):
         self._box_code_size = box_code_size
         self._heads = {}
         self._saved = {}
+        self._feature_mask_hi = 0.0     # 6.0 when the ROI features come out of a ReLU6 (MobileNet tail)
 
     def create_variables(self, store, scope, in_channels, class_only=False):
         if class_only:
@@ -197,5 +198,5 @@ class MaskRCNNBoxPredictor(BoxPredictor):
         if not need_dx:
             return None
         g = ws.get("%s/%s/d_feat" % (scope, tag), feats.shape)
-        ops.call("mtl_avgpool_bwd", dpool, 0, C, feats, R, H * W, C, g)
+        ops.call("mtl_avgpool_bwd", dpool, 0, C, feats, self._feature_mask_hi, R, H * W, C, g)
         return g

@@ -54,6 +54,7 @@ struct Params {
   const bf16* mask; long long ldm;
   int relu;
   float alpha;
+  float mask_hi;             // > 0: the mask is a ReLU6 output, gradient also dies at mask >= mask_hi
   int epi_tma;               // FPROP/DGRAD bf16 output (and bf16 residual) move through smem + TMA
 };
 
@@ -87,6 +88,7 @@ __device__ __forceinline__ int fast_div(int x, unsigned long long c) {
   const uint32_t mul = (uint32_t)c, sh = (uint32_t)(c >> 32);
   return (int)(((unsigned long long)(uint32_t)x * mul) >> sh);
 }
+__device__ __forceinline__ bool mask_dead(float m, float hi) { return !(m > 0.0f) || (hi > 0.0f && !(m < hi)); }
 __device__ __forceinline__ uint64_t globaltimer_ns() {
   uint64_t t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -328,7 +330,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tma_load_2d(stage_a(s), &tmA, full_bar(s), m0, p0);
             tma_load_2d(stage_a(s) + 8192, &tmA, full_bar(s), m0 + 64, p0);
             if (!GATHER_B) {
-              const int nper = p.ntot / BN;           // n-tiles per tap
+              const int nper = p.taps == 1 ? p.tiles_n : p.ntot / BN;   // n-tiles per tap
               const int tap = n_tile / nper;
               const int ci0 = (n_tile - tap * nper) * BN;
               if (p.im2col) {
@@ -401,7 +403,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN;
       long long ncol0;     // first output column of this tile
       if (MODE == WGRAD) {
-        const int nper = p.ntot / BN;
+        const int nper = p.taps == 1 ? p.tiles_n : p.ntot / BN;
         ncol0 = (long long)(n_tile / nper) * p.ntot + (long long)(n_tile % nper) * BN;
       } else {
         ncol0 = (long long)n_tile * BN;
@@ -422,7 +424,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * sc;
           if (c + 1 < NCH) tmem_ld32(taddr + (c + 1) * 32, v);
-          if (row_ok) {
+          if (row_ok && ncol0 + c * 32 < p.N) {      // (1x1 layers may have C < BN: columns past C are padding)
             float* o = reinterpret_cast<float*>(p.out) + (long long)m * p.ldo + ncol0 + c * 32;
 #pragma unroll
             for (int j = 0; j < 8; ++j)
@@ -503,6 +505,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (p.relu) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
+            if (p.relu == 2) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = fminf(f[j], 6.0f);
+            }
           }
           if (p.mask && row_ok) {
             if (vec && mask_vec) {
@@ -511,15 +517,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const uint32_t w[4] = {mcur[j].x, mcur[j].y, mcur[j].z, mcur[j].w};
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                  if (!(__uint_as_float(w[q] << 16) > 0.0f)) f[8 * j + 2 * q] = 0.0f;
-                  if (!(__uint_as_float(w[q] & 0xffff0000u) > 0.0f)) f[8 * j + 2 * q + 1] = 0.0f;
+                  if (mask_dead(__uint_as_float(w[q] << 16), p.mask_hi)) f[8 * j + 2 * q] = 0.0f;
+                  if (mask_dead(__uint_as_float(w[q] & 0xffff0000u), p.mask_hi)) f[8 * j + 2 * q + 1] = 0.0f;
                 }
               }
             } else {
               const bf16* r = p.mask + (long long)m * p.ldm + n0;
 #pragma unroll
               for (int j = 0; j < 32; ++j)
-                if (j < nvalid && !(__bfloat162float(r[j]) > 0.0f)) f[j] = 0.0f;
+                if (j < nvalid && mask_dead(__bfloat162float(r[j]), p.mask_hi)) f[j] = 0.0f;
             }
           }
           // the TMA store issued two chunks ago must have finished reading this staging buffer
@@ -628,6 +634,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (p.relu) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
+            if (p.relu == 2) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = fminf(f[j], 6.0f);
+            }
           }
           if (p.mask) {
             if (vec && mask_vec) {
@@ -636,15 +646,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const uint32_t w[4] = {mcur[j].x, mcur[j].y, mcur[j].z, mcur[j].w};
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                  if (!(__uint_as_float(w[q] << 16) > 0.0f)) f[8 * j + 2 * q] = 0.0f;
-                  if (!(__uint_as_float(w[q] & 0xffff0000u) > 0.0f)) f[8 * j + 2 * q + 1] = 0.0f;
+                  if (mask_dead(__uint_as_float(w[q] << 16), p.mask_hi)) f[8 * j + 2 * q] = 0.0f;
+                  if (mask_dead(__uint_as_float(w[q] & 0xffff0000u), p.mask_hi)) f[8 * j + 2 * q + 1] = 0.0f;
                 }
               }
             } else {
               const bf16* r = p.mask + (long long)m * p.ldm + n0;
 #pragma unroll
               for (int j = 0; j < 32; ++j)
-                if (j < nvalid && !(__bfloat162float(r[j]) > 0.0f)) f[j] = 0.0f;
+                if (j < nvalid && mask_dead(__bfloat162float(r[j]), p.mask_hi)) f[j] = 0.0f;
             }
           }
           if (p.out_fp32) {
@@ -995,6 +1005,7 @@ struct mtl_conv_args {
   float alpha;              // wgrad scale
   int force_bn;             // 0 = auto
   int force_splits;         // 0 = auto
+  float mask_hi;            // dgrad: > 0 -> mask is a ReLU6 output (gradient only where 0 < mask < mask_hi)
 };
 
 extern "C" int mtl_conv_tc(const mtl_conv_args* a, cudaStream_t stream) {
@@ -1012,7 +1023,7 @@ extern "C" int mtl_conv_tc(const mtl_conv_args* a, cudaStream_t stream) {
   p.S = a->S; p.stride = a->stride; p.pad_h = a->pad_h; p.pad_w = a->pad_w; p.dil = a->dil > 0 ? a->dil : 1;
   p.out = a->out; p.out_fp32 = a->out_fp32; p.bias = a->bias; p.rowscale = a->rowscale;
   p.res = a->res; p.res_fp32 = a->res_fp32; p.mask = reinterpret_cast<const bf16*>(a->mask);
-  p.relu = a->relu; p.alpha = a->alpha; p.splits = 1; p.taps = a->R * a->S;
+  p.relu = a->relu; p.mask_hi = a->mask_hi; p.alpha = a->alpha; p.splits = 1; p.taps = a->R * a->S;
   CUtensorMap tmA, tmB;
   memset(&tmA, 0, sizeof(tmA)); memset(&tmB, 0, sizeof(tmB));
   int bn, rc;
@@ -1054,13 +1065,14 @@ extern "C" int mtl_conv_tc(const mtl_conv_args* a, cudaStream_t stream) {
     if (gather) tmA = tmB;
   } else if (a->mode == WGRAD) {
     MTL_CHECK_ARG(a->dy && a->x && a->out, "mtl_conv_tc wgrad: null tensor");
-    MTL_CHECK_ARG(a->C % 64 == 0, "mtl_conv_tc wgrad: C must be a multiple of 64 (C=%d)", a->C);
+    MTL_CHECK_ARG(a->C % 64 == 0 || (plain && a->C % 32 == 0),
+                  "mtl_conv_tc wgrad: C must be a multiple of 64 (32 for 1x1 layers) (C=%d)", a->C);
     p.M = a->K; p.N = p.taps * a->C; p.cpt = 1; p.k_iters = (int)ceil_div_ll(npq, BK);
     p.gsrc = reinterpret_cast<const bf16*>(a->x); p.gH = a->H; p.gW = a->W; p.gC = a->C;
     p.oH = a->P; p.oW = a->Q; p.rows = (int)npq; p.transposed = 0; p.ntot = a->C;
     p.ldo = (long long)p.taps * a->C;
     bn = a->force_bn ? a->force_bn : (a->C % 256 == 0 ? 256 : (a->C % 128 == 0 ? 128 : 64));
-    MTL_CHECK_ARG(a->C % bn == 0, "mtl_conv_tc wgrad: BN %d must divide C %d", bn, a->C);
+    MTL_CHECK_ARG(a->C % bn == 0 || (plain && bn == 64), "mtl_conv_tc wgrad: BN %d must divide C %d", bn, a->C);
     if ((rc = make_map(&tmA, a->dy, npq, a->K, a->K, 64))) return rc;
     if (im2col) {
       p.im_low_h = -a->pad_h; p.im_low_w = -a->pad_w;
@@ -1069,7 +1081,7 @@ extern "C" int mtl_conv_tc(const mtl_conv_args* a, cudaStream_t stream) {
     } else if (!gather && (rc = make_map(&tmB, a->x, nhw, a->C, a->C, 64))) return rc;
     if (gather) tmB = tmA;
     // split K (pixels) so that about one wave of CTAs is launched
-    const int tiles = ceil_div(p.M, BM) * (p.N / bn);
+    const int tiles = ceil_div(p.M, BM) * ceil_div(p.N, bn);
     int splits = a->force_splits ? a->force_splits : (mtl_num_sms() + tiles - 1) / tiles;
     if (splits > p.k_iters) splits = p.k_iters;
     if (splits < 1) splits = 1;
@@ -1082,7 +1094,7 @@ extern "C" int mtl_conv_tc(const mtl_conv_args* a, cudaStream_t stream) {
   p.div_ohw = make_fast_div(p.oH * p.oW);
   p.div_ow = make_fast_div(p.oW);
   p.tiles_m = ceil_div(p.M, BM);
-  p.tiles_n = (a->mode == WGRAD) ? p.N / bn : ceil_div(p.N, bn);
+  p.tiles_n = ceil_div(p.N, bn);
   // epilogue through shared memory + TMA whenever the output (and residual) are plain bf16 matrices
   CUtensorMap tmO, tmR;
   memset(&tmO, 0, sizeof(tmO)); memset(&tmR, 0, sizeof(tmR));

@@ -252,8 +252,8 @@ avgpool_fwd_kernel(const bf16* __restrict__ x, int R, int HW, int C, bf16* __res
 // dx[r,p,c] = (mask[r,p,c] > 0 ? 1 : 0) * dy[r,c] / HW   (mask = the ReLU output being pooled)
 template <typename TDY>
 __global__ void __launch_bounds__(256)
-avgpool_bwd_kernel(const TDY* __restrict__ dy, long long ldy, const bf16* __restrict__ mask, int R, int HW, int C,
-                   bf16* __restrict__ dx) {
+avgpool_bwd_kernel(const TDY* __restrict__ dy, long long ldy, const bf16* __restrict__ mask, float mask_hi, int R,
+                   int HW, int C, bf16* __restrict__ dx) {
   const int nvec = C >> 3;
   const long long total = (long long)R * HW * nvec;
   const float inv = 1.0f / (float)HW;
@@ -270,7 +270,7 @@ avgpool_bwd_kernel(const TDY* __restrict__ dy, long long ldy, const bf16* __rest
       unpack8(__ldg(reinterpret_cast<const uint4*>(mask + rp * C) + v), m);
 #pragma unroll
       for (int e = 0; e < 8; ++e)
-        if (!(m[e] > 0.0f)) g[e] = 0.0f;
+        if (!(m[e] > 0.0f) || (mask_hi > 0.0f && !(m[e] < mask_hi))) g[e] = 0.0f;
     }
     reinterpret_cast<uint4*>(dx + rp * C)[v] = pack8(g);
   }
@@ -482,8 +482,8 @@ extern "C" int mtl_avgpool_fwd(const void* x, int R, int HW, int C, void* y, cud
   return MTL_OK;
 }
 
-extern "C" int mtl_avgpool_bwd(const void* dy, int dy_fp32, long long ldy, const void* relu_mask, int R, int HW,
-                               int C, void* dx, cudaStream_t stream) {
+extern "C" int mtl_avgpool_bwd(const void* dy, int dy_fp32, long long ldy, const void* relu_mask, float mask_hi,
+                               int R, int HW, int C, void* dx, cudaStream_t stream) {
   MTL_CHECK_ARG(dy && dx, "mtl_avgpool_bwd: null tensor");
   CHECK_VEC8(C, "mtl_avgpool_bwd");
   if (R == 0) return MTL_OK;
@@ -491,11 +491,11 @@ extern "C" int mtl_avgpool_bwd(const void* dy, int dy_fp32, long long ldy, const
   const int grid = (int)min(ceil_div_ll(total, 256), (long long)mtl_num_sms() * 16);
   if (dy_fp32)
     avgpool_bwd_kernel<float><<<grid, 256, 0, stream>>>(reinterpret_cast<const float*>(dy), ldy,
-                                                        reinterpret_cast<const bf16*>(relu_mask), R, HW, C,
+                                                        reinterpret_cast<const bf16*>(relu_mask), mask_hi, R, HW, C,
                                                         reinterpret_cast<bf16*>(dx));
   else
     avgpool_bwd_kernel<bf16><<<grid, 256, 0, stream>>>(reinterpret_cast<const bf16*>(dy), ldy,
-                                                       reinterpret_cast<const bf16*>(relu_mask), R, HW, C,
+                                                       reinterpret_cast<const bf16*>(relu_mask), mask_hi, R, HW, C,
                                                        reinterpret_cast<bf16*>(dx));
   MTL_CUDA_LAUNCH_CHECK("avgpool_bwd_kernel");
   return MTL_OK;
@@ -560,5 +560,206 @@ extern "C" int mtl_resize_bilinear_f32(const float* x, int B, int H, int W, int 
   const int grid = (int)min(ceil_div_ll(total, 256), (long long)mtl_num_sms() * 16);
   resize_bilinear_f32_kernel<<<grid, 256, 0, stream>>>(x, B, H, W, C, out_h, out_w, y);
   MTL_CUDA_LAUNCH_CHECK("resize_bilinear_f32_kernel");
+  return MTL_OK;
+}
+
+// ===================================================================================== depthwise 3x3
+// slim.separable_conv2d(depth_multiplier=1) depthwise stage (slim/nets/mobilenet_v1.py:230-238,
+// object_detection/models/faster_rcnn_mobilenet_v1_feature_extractor.py:169-182): NHWC bf16, weights
+// [C, 3, 3] bf16 (frozen batch-norm scale folded in), per-channel bias, optional ReLU6.  HBM-bound:
+// one thread per (pixel, 8-channel vector), 16-byte accesses, taps served from L1/L2.
+namespace {
+
+__device__ __forceinline__ void unpack8b(const uint4 v, float (&f)[8]) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    f[2 * q] = __uint_as_float(w[q] << 16);
+    f[2 * q + 1] = __uint_as_float(w[q] & 0xffff0000u);
+  }
+}
+__device__ __forceinline__ uint4 pack8b(const float (&f)[8]) {
+  uint32_t w[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * q], f[2 * q + 1]);
+    w[q] = *reinterpret_cast<const uint32_t*>(&h);
+  }
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+__global__ void __launch_bounds__(256)
+dwconv3x3_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, const float* __restrict__ bias, int N,
+                     int H, int W, int C, int stride, int pad_h, int pad_w, int P, int Q, int act,
+                     bf16* __restrict__ y) {
+  const int nvec = C >> 3;
+  const long long total = (long long)N * P * Q * nvec;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(t % nvec);
+    const long long pix = t / nvec;
+    const int q = (int)(pix % Q);
+    const int p = (int)((pix / Q) % P);
+    const int n = (int)(pix / ((long long)P * Q));
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = bias ? bias[v * 8 + e] : 0.0f;
+    for (int r = 0; r < 3; ++r) {
+      const int h = p * stride - pad_h + r;
+      if (h < 0 || h >= H) continue;
+      for (int s = 0; s < 3; ++s) {
+        const int ww = q * stride - pad_w + s;
+        if (ww < 0 || ww >= W) continue;
+        float f[8];
+        unpack8b(__ldg(reinterpret_cast<const uint4*>(x + (((long long)n * H + h) * W + ww) * C) + v), f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] += f[e] * __bfloat162float(w[(v * 8 + e) * 9 + r * 3 + s]);
+      }
+    }
+    if (act) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] = fmaxf(acc[e], 0.0f);
+      if (act == 2) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = fminf(acc[e], 6.0f);
+      }
+    }
+    reinterpret_cast<uint4*>(y + pix * C)[v] = pack8b(acc);
+  }
+}
+
+// dx[n,h,w,c] = sum_{r,s} dy[n,(h+pad-r)/stride,(w+pad-s)/stride,c] * w[c,r,s], masked by the activation
+// that produced x (mask > 0, and mask < mask_hi when mask_hi > 0)
+__global__ void __launch_bounds__(256)
+dwconv3x3_dgrad_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ w, int N, int H, int W, int C,
+                       int stride, int pad_h, int pad_w, int P, int Q, const bf16* __restrict__ mask,
+                       float mask_hi, bf16* __restrict__ dx) {
+  const int nvec = C >> 3;
+  const long long total = (long long)N * H * W * nvec;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(t % nvec);
+    const long long pix = t / nvec;
+    const int ww = (int)(pix % W);
+    const int h = (int)((pix / W) % H);
+    const int n = (int)(pix / ((long long)H * W));
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.0f;
+    for (int r = 0; r < 3; ++r) {
+      const int hy = h + pad_h - r;
+      if (hy < 0 || hy % stride) continue;
+      const int p = hy / stride;
+      if (p >= P) continue;
+      for (int s = 0; s < 3; ++s) {
+        const int wy = ww + pad_w - s;
+        if (wy < 0 || wy % stride) continue;
+        const int q = wy / stride;
+        if (q >= Q) continue;
+        float g[8];
+        unpack8b(__ldg(reinterpret_cast<const uint4*>(dy + (((long long)n * P + p) * Q + q) * C) + v), g);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] += g[e] * __bfloat162float(w[(v * 8 + e) * 9 + r * 3 + s]);
+      }
+    }
+    if (mask) {
+      float m[8];
+      unpack8b(__ldg(reinterpret_cast<const uint4*>(mask + pix * C) + v), m);
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        if (!(m[e] > 0.0f) || (mask_hi > 0.0f && !(m[e] < mask_hi))) acc[e] = 0.0f;
+    }
+    reinterpret_cast<uint4*>(dx + pix * C)[v] = pack8b(acc);
+  }
+}
+
+// dw[c,r,s] += scale[c] * sum_pixels dy[p,c] * x[p*stride - pad + (r,s), c]; block = 32 channels x 8 pixel lanes
+__global__ void __launch_bounds__(256)
+dwconv3x3_wgrad_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, int N, int H, int W, int C,
+                       int stride, int pad_h, int pad_w, int P, int Q, const float* __restrict__ scale,
+                       float* __restrict__ dw) {
+  __shared__ float part[8][32][9];
+  const int cl = threadIdx.x & 31, pl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
+  const long long npix = (long long)N * P * Q;
+  const long long per = (npix + gridDim.y - 1) / gridDim.y;
+  const long long p0 = blockIdx.y * per, p1 = min(p0 + per, npix);
+  float acc[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) acc[k] = 0.0f;
+  if (c < C) {
+    for (long long pix = p0 + pl; pix < p1; pix += 8) {
+      const int q = (int)(pix % Q);
+      const int p = (int)((pix / Q) % P);
+      const int n = (int)(pix / ((long long)P * Q));
+      const float g = __bfloat162float(dy[pix * C + c]);
+      if (g == 0.0f) continue;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const int h = p * stride - pad_h + r;
+        if (h < 0 || h >= H) continue;
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+          const int ww = q * stride - pad_w + s;
+          if (ww < 0 || ww >= W) continue;
+          acc[r * 3 + s] += g * __bfloat162float(x[(((long long)n * H + h) * W + ww) * C + c]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 9; ++k) part[pl][cl][k] = acc[k];
+  __syncthreads();
+  if (pl == 0 && c < C) {
+    const float sc = scale ? scale[c] : 1.0f;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      float s = 0.0f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s += part[i][cl][k];
+      atomicAdd(dw + (long long)c * 9 + k, s * sc);
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int mtl_dwconv3x3_fwd(const void* x, const void* w, const float* bias, int N, int H, int W, int C,
+                                 int stride, int pad_h, int pad_w, int P, int Q, int activation, void* y,
+                                 cudaStream_t stream) {
+  MTL_CHECK_ARG(x && w && y, "mtl_dwconv3x3_fwd: null tensor");
+  CHECK_VEC8(C, "mtl_dwconv3x3_fwd");
+  const long long total = (long long)N * P * Q * (C / 8);
+  const int grid = (int)min(ceil_div_ll(total, 256), (long long)mtl_num_sms() * 16);
+  dwconv3x3_fwd_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const bf16*>(x), reinterpret_cast<const bf16*>(w),
+                                                 bias, N, H, W, C, stride, pad_h, pad_w, P, Q, activation,
+                                                 reinterpret_cast<bf16*>(y));
+  MTL_CUDA_LAUNCH_CHECK("dwconv3x3_fwd_kernel");
+  return MTL_OK;
+}
+
+extern "C" int mtl_dwconv3x3_dgrad(const void* dy, const void* w, int N, int H, int W, int C, int stride, int pad_h,
+                                   int pad_w, int P, int Q, const void* mask, float mask_hi, void* dx,
+                                   cudaStream_t stream) {
+  MTL_CHECK_ARG(dy && w && dx, "mtl_dwconv3x3_dgrad: null tensor");
+  CHECK_VEC8(C, "mtl_dwconv3x3_dgrad");
+  const long long total = (long long)N * H * W * (C / 8);
+  const int grid = (int)min(ceil_div_ll(total, 256), (long long)mtl_num_sms() * 16);
+  dwconv3x3_dgrad_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const bf16*>(dy),
+                                                   reinterpret_cast<const bf16*>(w), N, H, W, C, stride, pad_h, pad_w,
+                                                   P, Q, reinterpret_cast<const bf16*>(mask), mask_hi,
+                                                   reinterpret_cast<bf16*>(dx));
+  MTL_CUDA_LAUNCH_CHECK("dwconv3x3_dgrad_kernel");
+  return MTL_OK;
+}
+
+extern "C" int mtl_dwconv3x3_wgrad(const void* dy, const void* x, int N, int H, int W, int C, int stride, int pad_h,
+                                   int pad_w, int P, int Q, const float* scale, float* dw, cudaStream_t stream) {
+  MTL_CHECK_ARG(dy && x && dw, "mtl_dwconv3x3_wgrad: null tensor");
+  const long long npix = (long long)N * P * Q;
+  dim3 grid(ceil_div(C, 32), (unsigned)min((long long)256, ceil_div_ll(npix, 64)));
+  dwconv3x3_wgrad_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const bf16*>(dy), reinterpret_cast<const bf16*>(x),
+                                                   N, H, W, C, stride, pad_h, pad_w, P, Q, scale, dw);
+  MTL_CUDA_LAUNCH_CHECK("dwconv3x3_wgrad_kernel");
   return MTL_OK;
 }

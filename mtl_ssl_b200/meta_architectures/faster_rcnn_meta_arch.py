@@ -154,6 +154,9 @@ class FasterRCNNMetaArch(model.DetectionModel):
         self._anchor_cache = {}
         self._sampler_keys = None
         self._lanes = _Lanes()
+        for pred in (second_stage_mask_rcnn_box_predictor, window_box_predictor, closeness_box_predictor):
+            if pred is not None and hasattr(pred, "_feature_mask_hi"):
+                pred._feature_mask_hi = feature_extractor.feature_mask_hi
         self._create_variables(first_stage_box_predictor_arg_scope, first_stage_box_predictor_trainable)
         if device is not None:          # device=None: variable table only (host-side inspection)
             self._store.finalize(device, seed)
@@ -228,9 +231,7 @@ class FasterRCNNMetaArch(model.DetectionModel):
                                     trainable=self._is_training, init=hp.init)
             self._refine_b = st.add(self.mtl_refiner_scope + "/fc1/biases", (K1,), trainable=self._is_training)
             self._refine_nf = nf
-        # the reference also instantiates block4 inside the stage-1 network (its output is unused,
-        # fe:145-146); the variables exist, are regularised and decay (trap T4)
-        fe.create_box_classifier_variables(st, self.first_stage_feature_extractor_scope + "/_dead")
+        fe.create_dead_variables(st, self.first_stage_feature_extractor_scope)
 
     # ------------------------------------------------------------------ inputs
     def preprocess(self, inputs):
@@ -638,6 +639,11 @@ class FasterRCNNMetaArch(model.DetectionModel):
                                                            ws.bufs["det/d_close"], ws)
                 d_extra = fe.backward_box_classifier_features(self.closeness_box_predictor_scope, g, ws, "close",
                                                               need_dx=not stop_aux)
+                if d_extra is not None and not fe.supports_dx_extra:
+                    self._crop_backward(pd, d_extra, pd["_proposal_maps"], pd["_proposal_prepool"],
+                                        pd["proposal_boxes_normalized"].view(B * P, 4), self._box_ind(B, P, "props"),
+                                        dfeat, "close")
+                    d_extra = None
                 L.mark("close_bwd")
         if mtl is not None and mtl.window:
             with L.run("win", after=["bwd_start"]):
@@ -676,7 +682,8 @@ class FasterRCNNMetaArch(model.DetectionModel):
                                                  ws.bufs["rpn/d_out"], d_rpn_feat,
                                                  rpn_feat if self._rpn_conv.relu else None)
         self._rpn_conv.wgrad(feat, d_rpn_feat)
-        gfeat = self._rpn_conv.dgrad(d_rpn_feat, feat.shape, ws.get("bwd/g_feat", feat.shape), res=dfeat, mask=feat)
+        gfeat = self._rpn_conv.dgrad(d_rpn_feat, feat.shape, ws.get("bwd/g_feat", feat.shape), res=dfeat, mask=feat,
+                                     mask_hi=fe.feature_mask_hi)
         fe.backward_proposal_features(self.first_stage_feature_extractor_scope, gfeat, ws)
         Concurrency.join()      # side-stream weight-gradient GEMMs must land before the optimizer
 

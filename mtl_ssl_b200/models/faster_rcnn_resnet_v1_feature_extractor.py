@@ -35,6 +35,8 @@ class FasterRCNNResnetV1FeatureExtractor(FasterRCNNFeatureExtractor):
         self.means = (123.68, 116.779, 103.939)
         self.feature_depth = 1024
         self.classifier_depth = 2048
+        self.feature_mask_hi = 0.0           # activations are plain ReLU
+        self.supports_dx_extra = True
 
     def preprocess(self, resized_inputs):
         """fe:74-90 subtracts the ImageNet channel means.  On the B200 path the subtraction is
@@ -52,6 +54,11 @@ class FasterRCNNResnetV1FeatureExtractor(FasterRCNNFeatureExtractor):
         t = self._is_training if trainable is None else trainable
         self._tails[scope] = resnet_v1.Block4(store, scope + "/" + self._architecture, self._weight_decay,
                                               self.feature_depth, t)
+
+    def create_dead_variables(self, store, scope):
+        """The reference also instantiates block4 inside the stage-1 network (output unused, fe:145-146):
+        the variables exist, are regularised and decay (trap T4)."""
+        self.create_box_classifier_variables(store, scope + "/_dead")
 
     def feature_map_shape(self, H, W):
         h, w = self._trunk_any().stem.out_hw(H, W)

@@ -59,7 +59,7 @@ class Conv2d(object):
         self.scope = scope
         self.cin, self.cout, self.k, self.stride, self.rate = cin, cout, k, stride, rate
         self.padding = padding          # "SAME" | "VALID" | "EXPLICIT" (resnet_utils.conv2d_same)
-        self.relu = relu
+        self.relu = relu                # False | True (ReLU) | 2 (ReLU6)
         self.trainable = trainable
         self.bn = store.add_bn(scope + "/BatchNorm", cout, bn_eps) if bn else None
         self.weight = store.add(scope + "/" + weight_name, (cout, k, k, cin), l2=l2, trainable=trainable,
@@ -92,7 +92,7 @@ class Conv2d(object):
         P, Q, ph, pw = self.geom(H, W)
         assert out.shape == (N, P, Q, self.cout), (out.shape, (N, P, Q, self.cout))
         return oc.conv_fprop(x, self.weight.wb, self.stride, (ph, pw), self.rate, (P, Q),
-                             bias=self.epilogue_bias(), res=res, relu=self.relu if relu is None else relu,
+                             bias=self.epilogue_bias(), res=res, relu=int(self.relu if relu is None else relu),
                              out=out)
 
     def wgrad(self, x, dy):
@@ -106,11 +106,50 @@ class Conv2d(object):
             if self.bias is not None:
                 ops.call("mtl_colsum", dy, 0, self.cout, dy.numel() // self.cout, self.cout, 1.0, self.bias.g)
 
-    def dgrad(self, dy, x_shape, out, res=None, mask=None):
+    def dgrad(self, dy, x_shape, out, res=None, mask=None, mask_hi=0.0):
         N, H, W, C = x_shape
         P, Q, ph, pw = self.geom(H, W)
         return oc.conv_dgrad(dy, self.weight.wb, x_shape, self.stride, (ph, pw), self.rate, res=res, mask=mask,
-                             out=out)
+                             out=out, mask_hi=mask_hi)
+
+
+class DepthwiseConv3x3(object):
+    """Depthwise stage of slim.separable_conv2d (depth_multiplier 1), SAME padding; weights [C,3,3]
+    (TF depthwise_weights [3,3,C,1] transposed), optional folded batch norm + ReLU6."""
+
+    def __init__(self, store, scope, channels, stride=1, bn=True, act=2, l2=0.0, trainable=True,
+                 init=("truncated_normal", 0.09), bn_eps=1e-3):
+        self.scope, self.C, self.stride, self.act, self.trainable = scope, channels, stride, act, trainable
+        self.bn = store.add_bn(scope + "/BatchNorm", channels, bn_eps) if bn else None
+        self.weight = store.add(scope + "/depthwise_weights", (channels, 3, 3), l2=l2, trainable=trainable,
+                                init=init, fold=self.bn)
+
+    def geom(self, H, W):
+        P, ph = same_pad(H, 3, self.stride)
+        Q, pw = same_pad(W, 3, self.stride)
+        return P, Q, ph, pw
+
+    def fwd(self, x, out):
+        N, H, W, C = x.shape
+        P, Q, ph, pw = self.geom(H, W)
+        ops.call("mtl_dwconv3x3_fwd", x, self.weight.wb, self.bn.bias if self.bn is not None else None, N, H, W, C,
+                 self.stride, ph, pw, P, Q, self.act, out)
+        return out
+
+    def wgrad(self, x, dy):
+        if not self.trainable:
+            return
+        N, H, W, C = x.shape
+        P, Q, ph, pw = self.geom(H, W)
+        with torch.cuda.stream(Concurrency.fork()):
+            ops.call("mtl_dwconv3x3_wgrad", dy, x, N, H, W, C, self.stride, ph, pw, P, Q,
+                     self.bn.scale if self.bn is not None else None, self.weight.g)
+
+    def dgrad(self, dy, x_shape, out, mask=None, mask_hi=0.0):
+        N, H, W, C = x_shape
+        P, Q, ph, pw = self.geom(H, W)
+        ops.call("mtl_dwconv3x3_dgrad", dy, self.weight.wb, N, H, W, C, self.stride, ph, pw, P, Q, mask, mask_hi, out)
+        return out
 
 
 def max_pool(x, out, k, stride, padding="SAME"):

@@ -43,7 +43,7 @@ class ConvArgs(ctypes.Structure):
         ("res", ctypes.c_void_p), ("res_fp32", ctypes.c_int),
         ("mask", ctypes.c_void_p),
         ("relu", ctypes.c_int), ("alpha", ctypes.c_float),
-        ("force_bn", ctypes.c_int), ("force_splits", ctypes.c_int),
+        ("force_bn", ctypes.c_int), ("force_splits", ctypes.c_int), ("mask_hi", ctypes.c_float),
     ]
 
 
@@ -91,7 +91,7 @@ def conv_fprop(x, w, stride=1, pad=(0, 0), dil=1, out_hw=None, bias=None, res=No
 
 
 def conv_dgrad(dy, w, x_shape, stride=1, pad=(0, 0), dil=1, res=None, mask=None, out=None,
-               out_dtype=torch.bfloat16, force_bn=0):
+               out_dtype=torch.bfloat16, force_bn=0, mask_hi=0.0):
     """dx = mask>0 ? (conv_transpose(dy, w) + res) : 0.  dy [N,P,Q,K], w [K,R,S,C]."""
     N, P, Q, K = dy.shape
     K2, R, S, C = w.shape
@@ -111,6 +111,7 @@ def conv_dgrad(dy, w, x_shape, stride=1, pad=(0, 0), dil=1, res=None, mask=None,
     if mask is not None:
         assert mask.shape == out.shape and mask.dtype == torch.bfloat16 and mask.is_contiguous()
         a.mask = _dp(mask)
+        a.mask_hi = float(mask_hi)
     a.alpha = 1.0
     a.force_bn = force_bn
     _launch(a, "mtl_conv_tc(dgrad)")

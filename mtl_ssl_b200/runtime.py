@@ -249,6 +249,11 @@ def _init_tensor(p, gen):
         # stddev sqrt(1.3 * factor / fan_in) (tf.contrib.layers initializers.py)
         fan_in = p.numel // p.shape[0]
         return _trunc_normal(p.shape, math.sqrt(1.3 * 2.0 / fan_in), gen)
+    if kind == "packed_conv":           # [K, ld] rows holding `real` truncated-normal columns, zero padding
+        real, std = int(p.init[1]), float(p.init[2])
+        t = torch.zeros(p.shape)
+        t.view(p.shape[0], -1)[:, :real] = _trunc_normal((p.shape[0], real), std, gen)
+        return t
     if kind == "normal":
         return torch.randn(p.shape, generator=gen) * float(p.init[1])
     raise ValueError(kind)

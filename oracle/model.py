@@ -66,10 +66,10 @@ class Oracle(object):
             self.p[n].requires_grad_(True)
 
     # ------------------------------------------------------------------ layers
-    def conv(self, x, scope, stride=1, rate=1, padding="SAME", bn=True, relu=True, res=None, out_round=True):
-        w = self.p[scope + "/weights"]                       # [K,R,S,C]
+    def conv(self, x, scope, stride=1, rate=1, padding="SAME", bn=True, relu=True, res=None, out_round=True,
+             eps=1e-5, weight_name="weights"):
+        w = self.p[scope + "/" + weight_name]                # [K,R,S,C]
         if bn:
-            eps = 1e-5
             s = self.p[scope + "/BatchNorm/gamma"] / torch.sqrt(self.p[scope + "/BatchNorm/moving_variance"] + eps)
             bias = self.p[scope + "/BatchNorm/beta"] - self.p[scope + "/BatchNorm/moving_mean"] * s
             w = w * s[:, None, None, None]
@@ -87,7 +87,56 @@ class Oracle(object):
             y = y + res
         if relu:
             y = torch.relu(y)
+            if relu == 2:                       # ReLU6 (mobilenet_v1_arg_scope)
+                y = torch.clamp(y, max=6.0)
         return self.rb(y) if out_round else y
+
+    def dwconv(self, x, scope, stride, bn=True, act=2, eps=1e-3):
+        """Depthwise stage of slim.separable_conv2d (depth_multiplier 1, SAME): weights [C,3,3]."""
+        w = self.p[scope + "/depthwise_weights"]
+        bias = None
+        if bn:
+            s = self.p[scope + "/BatchNorm/gamma"] / torch.sqrt(self.p[scope + "/BatchNorm/moving_variance"] + eps)
+            bias = self.p[scope + "/BatchNorm/beta"] - self.p[scope + "/BatchNorm/moving_mean"] * s
+            w = w * s[:, None, None]
+        w = self.rb(w)
+        C = x.shape[-1]
+        xn = x.permute(0, 3, 1, 2)
+        _, pt, pb = ON.same_pad(x.shape[1], 3, stride)
+        _, pl, pr = ON.same_pad(x.shape[2], 3, stride)
+        xn = TF.pad(xn, (pl, pr, pt, pb))
+        y = TF.conv2d(xn, w[:, None], stride=stride, groups=C).permute(0, 2, 3, 1)
+        if bias is not None:
+            y = y + bias
+        if act:
+            y = torch.clamp(torch.relu(y), max=6.0)
+        return self.rb(y)
+
+    def trunk_mobilenet(self, img, scope):
+        """mobilenet_v1_base up to Conv2d_11_pointwise (slim/nets/mobilenet_v1.py:142-266); the device
+        stores Conv2d_0 as packed [32, 64] im2col-GEMM weights (27 real columns)."""
+        defs = [(64, 1), (128, 2), (128, 1), (256, 2), (256, 1), (512, 2), (512, 1), (512, 1), (512, 1), (512, 1),
+                (512, 1)]
+        x = self.rb((img - 127.5) * (2.0 / 255.0))
+        s0 = scope + "/Conv2d_0"
+        w0 = self.p[s0 + "/weights"].reshape(32, -1)[:, :27].reshape(32, 3, 3, 3)
+        sc = self.p[s0 + "/BatchNorm/gamma"] / torch.sqrt(self.p[s0 + "/BatchNorm/moving_variance"] + 1e-3)
+        b0 = self.p[s0 + "/BatchNorm/beta"] - self.p[s0 + "/BatchNorm/moving_mean"] * sc
+        w0 = self.rb(w0 * sc[:, None, None, None])
+        x = ON.conv2d_tf(x, w0.permute(1, 2, 3, 0), 2, "SAME") + b0
+        x = self.rb(torch.clamp(torch.relu(x), max=6.0))
+        for i, (depth, stride) in enumerate(defs):
+            x = self.dwconv(x, "%s/Conv2d_%d_depthwise" % (scope, i + 1), stride)
+            x = self.conv(x, "%s/Conv2d_%d_pointwise" % (scope, i + 1), relu=2, eps=1e-3)
+        return x
+
+    def tail_mobilenet(self, x, scope):
+        """Conv2d_12_pointwise (stride 2) + Conv2d_13_pointwise fused separable convs (mob fe:148-184)."""
+        for name, stride in (("Conv2d_12_pointwise", 2), ("Conv2d_13_pointwise", 1)):
+            s = scope + "/" + name
+            x = self.dwconv(x, s, stride, bn=False, act=0)
+            x = self.conv(x, s, relu=2, eps=1e-3, weight_name="pointwise_weights")
+        return x
 
     def bottleneck(self, x, scope, depth, stride, rate=1):
         s = scope + "/bottleneck_v1"
@@ -149,8 +198,10 @@ class Oracle(object):
         K = cfg["num_classes"]
         K1 = K + 1
         A = len(cfg["scales"]) * len(cfg["aspect_ratios"])
+        mobile = self.arch == "MobilenetV1"
         fs = "FirstStageFeatureExtractor/" + self.arch
-        feat = self.trunk(images, fs)
+        feat = self.trunk_mobilenet(images, fs) if mobile else self.trunk(images, fs)
+        tail = self.tail_mobilenet if mobile else self.block4
         _, Hf, Wf, _ = feat.shape
         rpn_feat = self.conv(feat, "FirstStageBoxPredictor/Conv", bn=False, relu=True)
         box = self.conv(rpn_feat, "FirstStageBoxPredictor/BoxEncodingPredictor", bn=False, relu=False, out_round=False)
@@ -199,7 +250,7 @@ class Oracle(object):
         maps = crops_of(prop_norm.reshape(-1, 4), bi)
         out = dict(feat=feat, rpn_box=rpn_box, rpn_cls=rpn_cls, anchors=anchors, keep=keep, prop_norm=prop_norm,
                    prop_abs=prop_abs, nprop=nprop, gts=gts, nms=nms_out)
-        bx, cl = self.head(self.block4(maps, "SecondStageFeatureExtractor/" + self.arch), "SecondStageBoxPredictor",
+        bx, cl = self.head(tail(maps, "SecondStageFeatureExtractor/" + self.arch), "SecondStageBoxPredictor",
                            ["BoxEncodingPredictor", "ClassPredictor"])
         out["refined_box_encodings"] = bx.reshape(B * P, K, 4)
         out["class_predictions_with_background"] = cl
@@ -207,7 +258,7 @@ class Oracle(object):
         stop = mtl.get("stop_gradient_for_aux_tasks", False)
         if mtl.get("closeness"):
             m2 = maps.detach() if stop else maps
-            out["closeness_predictions"] = self.head(self.block4(m2, "ClosenessBoxPredictor/" + self.arch),
+            out["closeness_predictions"] = self.head(tail(m2, "ClosenessBoxPredictor/" + self.arch),
                                                      "ClosenessBoxPredictor", ["ClassPredictor"])[0]
         if mtl.get("window"):
             wb = np.stack([np.asarray(e["window_boxes"], np.float32) for e in examples])
@@ -215,7 +266,7 @@ class Oracle(object):
             wm = crops_of(wb.reshape(-1, 4), np.repeat(np.arange(B), nw).astype(np.int64))
             if stop:
                 wm = wm.detach()
-            out["window_class_predictions"] = self.head(self.block4(wm, "WindowBoxPredictor/" + self.arch),
+            out["window_class_predictions"] = self.head(tail(wm, "WindowBoxPredictor/" + self.arch),
                                                         "WindowBoxPredictor", ["ClassPredictor"])[0]
         if mtl.get("edgemask"):
             w = p["EdgeMaskPredictor/BoxEncodingPredictor/weights"].reshape(2, -1)
@@ -235,7 +286,7 @@ class Oracle(object):
                 ebi = np.broadcast_to(np.arange(B)[None, :, None], (5, B, P)).reshape(-1).astype(np.int64)
                 with torch.no_grad():
                     em = crops_of(exp.reshape(-1, 4), ebi)
-                    ew = self.head(self.block4(em, "WindowBoxPredictor/" + self.arch), "WindowBoxPredictor",
+                    ew = self.head(tail(em, "WindowBoxPredictor/" + self.arch), "WindowBoxPredictor",
                                    ["ClassPredictor"])[0]
                 src.append(ew.reshape(5, B * P, K1).permute(1, 0, 2).reshape(B * P, 5 * K1))
             if mtl.get("closeness"):

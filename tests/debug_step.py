@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
-from test_gpu_train_step import _setup, SMALL
+from test_gpu_train_step import _setup, SMALL, MOBILE
 from helpers import oracle_config
 from oracle.model import Oracle
 from oracle import nn as ON
@@ -12,14 +12,15 @@ from oracle import nn as ON
 name = sys.argv[1] if len(sys.argv) > 1 else "model12.config"
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 H, W = 224, 320
-cfg, model, sd, examples, keys, tr = _setup(name, SMALL, H, W, B)
+cfg, model, sd, examples, keys, tr = _setup(name, MOBILE if name.startswith("model5") else SMALL, H, W, B)
 arrays = tr.host_arrays(examples, keys)
 image = tr._bind(arrays)
 pd = tr._forward_backward(image)
 torch.cuda.synchronize()
 orc = Oracle({k: v for k, v in sd.items() if "/_pad/" not in k}, oracle_config(cfg), bf16=True)
 orc.require_grad([p.name for p in model.param_store.params if p.trainable and "/_pad/" not in p.name and "/_dead/" not in p.name])
-out = orc.forward(torch.from_numpy(arrays["image"]), examples, keys, H, W)
+prop_in = (pd["rpn_box_encodings"].cpu().numpy(), pd["rpn_objectness_predictions_with_background"].cpu().numpy())
+out = orc.forward(torch.from_numpy(arrays["image"]), examples, keys, H, W, proposal_inputs=prop_in)
 want = orc.loss(out, examples, keys, H, W)
 
 

@@ -21,7 +21,7 @@ def oracle_config(cfg):
     fr, mtl = cfg.model.faster_rcnn, cfg.model.mtl
     g = fr.first_stage_anchor_generator.grid_anchor_generator
     arch = {"faster_rcnn_resnet50": "resnet_v1_50", "faster_rcnn_resnet101": "resnet_v1_101",
-            "faster_rcnn_resnet152": "resnet_v1_152"}[fr.feature_extractor.type]
+            "faster_rcnn_resnet152": "resnet_v1_152", "frcnn_mobilenet_v1": "MobilenetV1"}[fr.feature_extractor.type]
     return dict(
         architecture=arch, num_classes=fr.num_classes, scales=list(g.scales), aspect_ratios=list(g.aspect_ratios),
         first_stage_max_proposals=fr.first_stage_max_proposals, second_stage_batch_size=fr.second_stage_batch_size,
@@ -50,7 +50,23 @@ def randomize_bn(sd, seed=0):
     u = lambda lo, hi, n: torch.from_numpy(rng.uniform(lo, hi, n).astype(np.float32))
     for k in list(sd):
         n = sd[k].numel()
-        stem = "/block" not in k and "/conv1/BatchNorm/" in k
+        stem = ("/block" not in k and "/conv1/BatchNorm/" in k)
+        if "/MobilenetV1/" in k:                # keep ReLU6 activations in range through 13 layers
+            if k.endswith("/BatchNorm/gamma"):
+                sd[k] = u(0.8, 1.1, n)
+            elif k.endswith("/BatchNorm/beta"):
+                sd[k] = u(0.0, 0.3, n)
+            elif k.endswith("/BatchNorm/moving_mean"):
+                sd[k] = u(-0.1, 0.1, n)
+            elif k.endswith("/BatchNorm/moving_variance"):
+                # normalise each layer to ~unit output variance: var = fan_in * stddev_init^2 * E[x^2]
+                base = k[:-len("/BatchNorm/moving_variance")]
+                wkey = [c for c in (base + "/weights", base + "/depthwise_weights", base + "/pointwise_weights")
+                        if c in sd and "depthwise" not in c or (c in sd and base.endswith("_depthwise"))][0]
+                w = sd[wkey]
+                fan_in = 27 if base.endswith("Conv2d_0") else w[0].numel()
+                sd[k] = u(0.8, 1.2, n) * fan_in * 0.0081 * 0.6
+            continue
         if k.endswith("/BatchNorm/gamma"):
             if "/conv3/" in k:
                 sd[k] = u(0.15, 0.3, n)

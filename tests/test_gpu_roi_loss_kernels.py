@@ -77,7 +77,7 @@ def test_avgpool_fwd_bwd():
     torch.testing.assert_close(y.float().cpu(), x.float().mean(1), rtol=4e-3, atol=4e-3)
     dy = torch.randn(R, 72, generator=g)
     dx = torch.empty(R, HW, C, dtype=torch.bfloat16, device="cuda")
-    ops.call("mtl_avgpool_bwd", dy.cuda(), 1, 72, x.cuda(), R, HW, C, dx)
+    ops.call("mtl_avgpool_bwd", dy.cuda(), 1, 72, x.cuda(), 0.0, R, HW, C, dx)
     want = (dy[:, None, :C] / HW) * (x.float() > 0)
     torch.testing.assert_close(dx.float().cpu(), want, rtol=4e-3, atol=1e-4)
 
@@ -304,3 +304,35 @@ def test_optimizer_matches_reference_update():
     torch.testing.assert_close(fz.wb.float().cpu(), w0[3].to(torch.bfloat16).float())
     hv = store.group_view(grp, 21, 64)
     torch.testing.assert_close(hv.float().cpu(), torch.cat([w_ref[1], w_ref[2]]).to(torch.bfloat16).float())
+
+
+@pytest.mark.parametrize("stride", [1, 2])
+def test_depthwise_conv3x3_fwd_dgrad_wgrad(stride):
+    """slim.separable_conv2d depthwise stage (mobilenet_v1.py:230-238) against torch grouped conv."""
+    from mtl_ssl_b200 import ops
+    g = torch.Generator().manual_seed(stride)
+    N, H, W, C = 2, 9, 11, 32
+    x = bf(torch.randn(N, H, W, C, generator=g) * 2)
+    w = bf(torch.randn(C, 3, 3, generator=g) * 0.3)
+    bias = torch.randn(C, generator=g) * 0.1
+    P, pt, pb = ON.same_pad(H, 3, stride)
+    Q, pl, pr = ON.same_pad(W, 3, stride)
+    y = torch.empty(N, P, Q, C, dtype=torch.bfloat16, device="cuda")
+    ops.call("mtl_dwconv3x3_fwd", x.cuda(), w.cuda(), bias.cuda(), N, H, W, C, stride, pt, pl, P, Q, 2, y)
+    xr = x.float().requires_grad_(True)
+    wr = w.float().requires_grad_(True)
+    xp = torch.nn.functional.pad(xr.permute(0, 3, 1, 2), (pl, pr, pt, pb))
+    pre = torch.nn.functional.conv2d(xp, wr[:, None], stride=stride, groups=C).permute(0, 2, 3, 1) + bias
+    want = torch.clamp(torch.relu(pre), max=6.0)
+    torch.testing.assert_close(y.float().cpu(), want.detach(), rtol=8e-3, atol=8e-3)
+    dy = bf(torch.randn(N, P, Q, C, generator=g))
+    pre.backward(dy.float())                      # gradient w.r.t. the pre-activation (callers mask dy themselves)
+    mask = bf(torch.rand(N, H, W, C, generator=g) * 8 - 1)       # ReLU6-style mask: alive iff 0 < m < 6
+    dx = torch.empty(N, H, W, C, dtype=torch.bfloat16, device="cuda")
+    ops.call("mtl_dwconv3x3_dgrad", dy.cuda(), w.cuda(), N, H, W, C, stride, pt, pl, P, Q, mask.cuda(), 6.0, dx)
+    alive = (mask.float() > 0) & (mask.float() < 6)
+    torch.testing.assert_close(dx.float().cpu(), xr.grad * alive, rtol=8e-3, atol=8e-3)
+    scale = torch.rand(C, generator=g) + 0.5
+    dw = torch.zeros(C, 3, 3, device="cuda")
+    ops.call("mtl_dwconv3x3_wgrad", dy.cuda(), x.cuda(), N, H, W, C, stride, pt, pl, P, Q, scale.cuda(), dw)
+    torch.testing.assert_close(dw.cpu(), wr.grad * scale[:, None, None], rtol=1e-3, atol=1e-3)
