@@ -146,11 +146,14 @@ int mtl_dwconv3x3_dgrad(const void* dy, const void* w, int N, int H, int W, int 
                         int P, int Q, const void* mask, float mask_hi, void* dx, mtl_stream_t stream);
 int mtl_dwconv3x3_wgrad(const void* dy, const void* x, int N, int H, int W, int C, int stride, int pad_h, int pad_w,
                         int P, int Q, const float* scale, float* dw /* fp32 [C,3,3], += */, mtl_stream_t stream);
-int mtl_psroi_fwd(const void* feat /* bf16 [B,H,W,nby*nbx*D] */, int B, int H, int W, int D, int nby, int nbx,
-                  int crop_h, int crop_w, const float* boxes, const int* box_ind, int R, float* out /* [R,D] */,
+int mtl_psroi_fwd(const void* feat /* bf16 [B,H,W,Ct] */, int B, int H, int W, int Ct, int c0 /* first PS channel */,
+                  int D /* outputs per bin */, int nby, int nbx, int crop_h, int crop_w, const float* boxes,
+                  const int* box_ind, int R, float* out /* [R,ldo] at column ocol0 */, long long ldo, int ocol0,
                   mtl_stream_t stream);
-int mtl_psroi_bwd(const float* dout, int B, int H, int W, int D, int nby, int nbx, int crop_h, int crop_w,
-                  const float* boxes, const int* box_ind, int R, float* dfeat /* fp32, += */, mtl_stream_t stream);
+int mtl_psroi_bwd(const float* dout, long long ldo, int ocol0, int B, int H, int W, int Ct, int c0, int D, int nby,
+                  int nbx, int crop_h, int crop_w, const float* boxes, const int* box_ind, int R,
+                  float* dfeat /* fp32 [B,H,W,Ct], += */, mtl_stream_t stream);
+int mtl_add_bf16_to_f32(const void* src /* bf16 */, long long n, float* dst /* += */, mtl_stream_t stream);
 
 /* ---- fused loss epilogues (core/losses.py:169-196, 285-352; fmA:1591-1881) ---------------- */
 int mtl_rpn_loss(const float* rpn_out, long long ld, int box_col0, int cls_col0, int A, int HW, const int* keep_idx,

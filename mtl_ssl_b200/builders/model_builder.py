@@ -10,7 +10,7 @@ from ..core import box_predictor
 from ..core.hyperparams import Hyperparams
 from ..core.mask_predictor import MaskPredictor
 from ..core import preprocessor
-from ..meta_architectures import faster_rcnn_meta_arch
+from ..meta_architectures import faster_rcnn_meta_arch, rfcn_meta_arch
 from ..models import faster_rcnn_mobilenet_v1_feature_extractor as frcnn_mobilenet_v1
 from ..models import faster_rcnn_resnet_v1_feature_extractor as frcnn_resnet_v1
 
@@ -79,7 +79,13 @@ def build_box_predictor(cfg, is_training, num_classes):
             use_dropout=m.use_dropout, dropout_keep_prob=m.dropout_keep_probability, box_code_size=m.box_code_size,
             predict_instance_masks=m.predict_instance_masks, spatial_average=m.spatial_average)
     if which == "rfcn_box_predictor":
-        raise ValueError("R-FCN box predictor: not built yet on the B200 path")
+        r = cfg.rfcn_box_predictor
+        return box_predictor.RfcnBoxPredictor(
+            is_training=is_training, num_classes=num_classes,
+            conv_hyperparams=Hyperparams.from_proto(r.conv_hyperparams),
+            crop_size=[r.crop_height, r.crop_width],
+            num_spatial_bins=[r.num_spatial_bins_height, r.num_spatial_bins_width], depth=r.depth,
+            box_code_size=r.box_code_size)
     raise ValueError("Unknown box predictor: {}".format(which))
 
 
@@ -142,6 +148,9 @@ def _build_faster_rcnn_model(frcnn_config, is_training, mtl=None, device="cuda",
         hard_example_miner=None, mtl=mtl, mtl_refiner_arg_scope=mtl_refiner_arg_scope,
         window_box_predictor=window_box_predictor, closeness_box_predictor=closeness_box_predictor,
         edgemask_predictor=edgemask_predictor, device=device, seed=seed)
+    if isinstance(second_stage_box_predictor, box_predictor.RfcnBoxPredictor):
+        return rfcn_meta_arch.RFCNMetaArch(second_stage_rfcn_box_predictor=second_stage_box_predictor,
+                                           **common_kwargs)
     return faster_rcnn_meta_arch.FasterRCNNMetaArch(
         initial_crop_size=frcnn_config.initial_crop_size, maxpool_kernel_size=frcnn_config.maxpool_kernel_size,
         maxpool_stride=frcnn_config.maxpool_stride,

@@ -200,3 +200,121 @@ class MaskRCNNBoxPredictor(BoxPredictor):
         g = ws.get("%s/%s/d_feat" % (scope, tag), feats.shape)
         ops.call("mtl_avgpool_bwd", dpool, 0, C, feats, self._feature_mask_hi, R, H * W, C, g)
         return g
+
+
+class RfcnBoxPredictor(BoxPredictor):
+    """R-FCN predictor (/root/reference/object_detection/core/box_predictor.py:131-337): 1x1
+    `reduce_depth` conv (+bias, activation of the conv hyperparams), 1x1 `refined_locations`
+    (bins*K*4) and `class_predictions` (bins*(K+1)) maps without activation, then position-sensitive
+    ROI pooling with global average (utils/ops.py:462-609).  The two map convs are one fused GEMM;
+    pooling reads the bf16 maps with one block per ROI (mtl_psroi_fwd / mtl_psroi_bwd)."""
+
+    def __init__(self, is_training, num_classes, conv_hyperparams, num_spatial_bins, depth, crop_size,
+                 box_code_size=4):
+        super(RfcnBoxPredictor, self).__init__(is_training, num_classes)
+        self._hp = conv_hyperparams
+        self._num_spatial_bins = list(num_spatial_bins)
+        self._depth = depth
+        self._crop_size = list(crop_size)
+        self._box_code_size = box_code_size
+        self._vars = {}
+        self._saved = {}
+        self._feature_mask_hi = 0.0
+
+    def create_variables(self, store, scope, in_channels, class_only=False):
+        from ..nets.layers import Conv2d
+        hp = self._hp
+        if hp.activation == "RELU_6":
+            raise ValueError("RELU_6 in the R-FCN predictor is not supported on the B200 path")
+        reduce = Conv2d(store, scope + "/reduce_depth", in_channels, self._depth, 1, 1, bn=False, bias=True,
+                        relu=(hp.activation != "NONE"), l2=hp.l2_weight, trainable=self._is_training, init=hp.init)
+        bins = self._num_spatial_bins[0] * self._num_spatial_bins[1]
+        if class_only:
+            groups = [("class_predictions", self._num_classes)]
+        else:
+            groups = [("refined_locations", self._num_classes * self._box_code_size),
+                      ("class_predictions", self._num_classes + 1)]
+        head = _FusedHead(store, scope, [(n, bins * d) for n, d in groups], self._depth, hp, self._is_training)
+        self._vars[scope] = (reduce, head, groups)
+
+    def layout(self, scope):
+        _, _, groups = self._vars[scope]
+        ld = _round8(sum(d for _, d in groups))
+        if len(groups) == 1:
+            return dict(ld=ld, cls_col0=0, num=groups[0][1])
+        return dict(ld=ld, box_col0=0, cls_col0=groups[0][1], num=groups[1][1])
+
+    def _pool(self, scope, tag, src_tag, boxes, box_ind, ws):
+        reduce, head, groups = self._vars[scope]
+        feats, red, pmap = self._saved[(scope, src_tag)][:3]
+        B, H, W, _ = feats.shape
+        R = boxes.shape[0]
+        ld = self.layout(scope)["ld"]
+        out = ws.get("%s/%s/head_out" % (scope, tag), (R, ld), torch.float32)
+        bins = self._num_spatial_bins[0] * self._num_spatial_bins[1]
+        c0 = ocol = 0
+        for _, d in groups:
+            ops.call("mtl_psroi_fwd", pmap, B, H, W, head.n_pad, c0, d, self._num_spatial_bins[0],
+                     self._num_spatial_bins[1], self._crop_size[0], self._crop_size[1], boxes, box_ind, R, out, ld, ocol)
+            c0 += bins * d
+            ocol += d
+        self._saved[(scope, tag)] = (feats, red, pmap, boxes, box_ind)
+        return out
+
+    def _run(self, image_features, boxes, box_ind, scope, ws, tag):
+        reduce, head, groups = self._vars[scope]
+        B, H, W, C = image_features.shape
+        red = reduce.fwd(image_features, ws.get("%s/%s/reduce" % (scope, tag), (B, H, W, self._depth)))
+        pmap = ws.get("%s/%s/ps_maps" % (scope, tag), (B, H, W, head.n_pad))
+        head.fwd(red, pmap)
+        self._saved[(scope, tag)] = (image_features, red, pmap, boxes, box_ind)
+        return self._pool(scope, tag, tag, boxes, box_ind, ws)
+
+    def predict(self, image_features, num_predictions_per_location, scope, proposal_boxes=None, box_ind=None,
+                ws=None, tag="main", **params):
+        if num_predictions_per_location != 1:
+            raise ValueError("Currently RfcnBoxPredictor only supports predicting a single box per class per "
+                             "location.")
+        out = self._run(image_features, proposal_boxes, box_ind, scope, ws, tag)
+        R = out.shape[0]
+        nb, k1 = self._num_classes * self._box_code_size, self._num_classes + 1
+        return {"_raw": out,
+                BOX_ENCODINGS: lambda: out[:, :nb].reshape(R, 1, self._num_classes, self._box_code_size),
+                CLASS_PREDICTIONS_WITH_BACKGROUND: lambda: out[:, nb:nb + k1].reshape(R, 1, k1)}
+
+    def predict_class(self, image_features, scope, proposal_boxes=None, box_ind=None, ws=None, tag="main",
+                      activation_fn=None, with_background=False, reuse_maps_of=None):
+        """reuse_maps_of: tag of an earlier call on the SAME features and scope whose position-sensitive
+        maps are pooled again with new boxes (the reference recomputes block4 + maps for the refine
+        windows, rfcn_meta_arch.py:312-381; the values are identical)."""
+        if reuse_maps_of is not None:
+            out = self._pool(scope, tag, reuse_maps_of, proposal_boxes, box_ind, ws)
+        else:
+            out = self._run(image_features, proposal_boxes, box_ind, scope, ws, tag)
+        R, n = out.shape[0], self._num_classes
+        key = CLASS_PREDICTIONS_WITH_BACKGROUND if with_background else CLASS_PREDICTIONS
+        return {"_raw": out, key: lambda: out[:, :n].reshape(R, 1, n)}
+
+    def backward(self, scope, tag, d_out, ws, need_dx=True):
+        """d_out fp32 [R, ld] -> gradient w.r.t. image_features (bf16, masked by features > 0)."""
+        reduce, head, groups = self._vars[scope]
+        feats, red, pmap, boxes, box_ind = self._saved[(scope, tag)]
+        B, H, W, C = feats.shape
+        R = boxes.shape[0]
+        ld = self.layout(scope)["ld"]
+        dmap = ws.get("%s/%s/d_ps_maps_f32" % (scope, tag), pmap.shape, torch.float32, zero=True)
+        bins = self._num_spatial_bins[0] * self._num_spatial_bins[1]
+        c0 = ocol = 0
+        for _, d in groups:
+            ops.call("mtl_psroi_bwd", d_out, ld, ocol, B, H, W, head.n_pad, c0, d, self._num_spatial_bins[0],
+                     self._num_spatial_bins[1], self._crop_size[0], self._crop_size[1], boxes, box_ind, R, dmap)
+            c0 += bins * d
+            ocol += d
+        dmb = ws.get("%s/%s/d_ps_maps" % (scope, tag), pmap.shape)
+        ops.call("mtl_cast_f32_bf16", dmap, dmap.numel(), 1.0, dmb)
+        dred = ws.get("%s/%s/d_reduce" % (scope, tag), red.shape)
+        head.bwd(red, dmb, dred, red if reduce.relu else None)
+        reduce.wgrad(feats, dred)
+        if not need_dx:
+            return None
+        return reduce.dgrad(dred, feats.shape, ws.get("%s/%s/d_feat" % (scope, tag), feats.shape), mask=feats)

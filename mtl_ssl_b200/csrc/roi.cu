@@ -321,13 +321,13 @@ __global__ void preprocess_kernel(const float* __restrict__ img, long long total
 // (by*nbx + bx) to a (ch/nby x cw/nbx) grid with crop_and_resize arithmetic; the output is the
 // mean over bins of the mean over the grid.  feat [B,H,W,nb*D] -> out [R, D] fp32.
 __global__ void __launch_bounds__(128)
-psroi_fwd_kernel(const bf16* __restrict__ feat, int H, int W, int D, int nby, int nbx, int gh, int gw_,
-                 const float4* __restrict__ boxes, const int* __restrict__ box_ind, int R, float* __restrict__ out) {
+psroi_fwd_kernel(const bf16* __restrict__ feat, int H, int W, int Ct, int c0, int D, int nby, int nbx, int gh, int gw_,
+                 const float4* __restrict__ boxes, const int* __restrict__ box_ind, int R, float* __restrict__ out,
+                 long long ldo, int ocol0) {
   const int r = blockIdx.x;
   const float4 bx = boxes[r];
   const int bi = box_ind ? box_ind[r] : 0;
-  const int Ct = nby * nbx * D;
-  const bf16* base = feat + (long long)bi * H * W * Ct;
+  const bf16* base = feat + (long long)bi * H * W * Ct + c0;
   const float sy = (bx.z - bx.x) / (float)nby, sx = (bx.w - bx.y) / (float)nbx;
   for (int d = threadIdx.x; d < D; d += blockDim.x) {
     float total = 0.0f;
@@ -350,22 +350,22 @@ psroi_fwd_kernel(const bf16* __restrict__ feat, int H, int W, int D, int nby, in
           }
         total += acc / (float)(gh * gw_);
       }
-    out[(long long)r * D + d] = total / (float)(nby * nbx);
+    out[(long long)r * ldo + ocol0 + d] = total / (float)(nby * nbx);
   }
 }
 
 __global__ void __launch_bounds__(128)
-psroi_bwd_kernel(const float* __restrict__ dout, int H, int W, int D, int nby, int nbx, int gh, int gw_,
-                 const float4* __restrict__ boxes, const int* __restrict__ box_ind, int R, float* __restrict__ dfeat) {
+psroi_bwd_kernel(const float* __restrict__ dout, long long ldo, int ocol0, int H, int W, int Ct, int c0, int D, int nby,
+                 int nbx, int gh, int gw_, const float4* __restrict__ boxes, const int* __restrict__ box_ind, int R,
+                 float* __restrict__ dfeat) {
   const int r = blockIdx.x;
   const float4 bx = boxes[r];
   const int bi = box_ind ? box_ind[r] : 0;
-  const int Ct = nby * nbx * D;
-  float* base = dfeat + (long long)bi * H * W * Ct;
+  float* base = dfeat + (long long)bi * H * W * Ct + c0;
   const float sy = (bx.z - bx.x) / (float)nby, sx = (bx.w - bx.y) / (float)nbx;
   const float sc = 1.0f / (float)(nby * nbx) / (float)(gh * gw_);
   for (int d = threadIdx.x; d < D; d += blockDim.x) {
-    const float g0 = dout[(long long)r * D + d] * sc;
+    const float g0 = dout[(long long)r * ldo + ocol0 + d] * sc;
     if (g0 == 0.0f) continue;
     for (int by = 0; by < nby; ++by)
       for (int bxi = 0; bxi < nbx; ++bxi) {
@@ -528,28 +528,45 @@ extern "C" int mtl_preprocess(const float* img, long long total, int C, const fl
   return MTL_OK;
 }
 
-extern "C" int mtl_psroi_fwd(const void* feat, int B, int H, int W, int D, int nby, int nbx, int crop_h, int crop_w,
-                             const float* boxes, const int* box_ind, int R, float* out, cudaStream_t stream) {
+extern "C" int mtl_psroi_fwd(const void* feat, int B, int H, int W, int Ct, int c0, int D, int nby, int nbx,
+                             int crop_h, int crop_w, const float* boxes, const int* box_ind, int R, float* out,
+                             long long ldo, int ocol0, cudaStream_t stream) {
   MTL_CHECK_ARG(feat && boxes && out, "mtl_psroi_fwd: null tensor");
   MTL_CHECK_ARG(crop_h % nby == 0 && crop_w % nbx == 0, "mtl_psroi_fwd: crop size must be divisible by bins");
+  MTL_CHECK_ARG(c0 + nby * nbx * D <= Ct, "mtl_psroi_fwd: position-sensitive channels exceed the map depth");
   if (R == 0) return MTL_OK;
-  psroi_fwd_kernel<<<R, 128, 0, stream>>>(reinterpret_cast<const bf16*>(feat), H, W, D, nby, nbx, crop_h / nby,
-                                          crop_w / nbx, reinterpret_cast<const float4*>(boxes), box_ind, R, out);
+  psroi_fwd_kernel<<<R, 128, 0, stream>>>(reinterpret_cast<const bf16*>(feat), H, W, Ct, c0, D, nby, nbx,
+                                          crop_h / nby, crop_w / nbx, reinterpret_cast<const float4*>(boxes), box_ind,
+                                          R, out, ldo, ocol0);
   MTL_CUDA_LAUNCH_CHECK("psroi_fwd_kernel");
   (void)B;
   return MTL_OK;
 }
 
-extern "C" int mtl_psroi_bwd(const float* dout, int B, int H, int W, int D, int nby, int nbx, int crop_h,
-                             int crop_w, const float* boxes, const int* box_ind, int R, float* dfeat,
-                             cudaStream_t stream) {
+extern "C" int mtl_psroi_bwd(const float* dout, long long ldo, int ocol0, int B, int H, int W, int Ct, int c0, int D,
+                             int nby, int nbx, int crop_h, int crop_w, const float* boxes, const int* box_ind, int R,
+                             float* dfeat, cudaStream_t stream) {
   MTL_CHECK_ARG(dout && boxes && dfeat, "mtl_psroi_bwd: null tensor");
   MTL_CHECK_ARG(crop_h % nby == 0 && crop_w % nbx == 0, "mtl_psroi_bwd: crop size must be divisible by bins");
   if (R == 0) return MTL_OK;
-  psroi_bwd_kernel<<<R, 128, 0, stream>>>(dout, H, W, D, nby, nbx, crop_h / nby, crop_w / nbx,
+  psroi_bwd_kernel<<<R, 128, 0, stream>>>(dout, ldo, ocol0, H, W, Ct, c0, D, nby, nbx, crop_h / nby, crop_w / nbx,
                                           reinterpret_cast<const float4*>(boxes), box_ind, R, dfeat);
   MTL_CUDA_LAUNCH_CHECK("psroi_bwd_kernel");
   (void)B;
+  return MTL_OK;
+}
+
+// dst (fp32) += src (bf16): merges dense bf16 feature gradients into the fp32 accumulator
+__global__ void add_bf16_to_f32_kernel(const bf16* __restrict__ src, long long n, float* __restrict__ dst) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    dst[i] += __bfloat162float(src[i]);
+}
+extern "C" int mtl_add_bf16_to_f32(const void* src, long long n, float* dst, cudaStream_t stream) {
+  MTL_CHECK_ARG(src && dst, "mtl_add_bf16_to_f32: null tensor");
+  if (n == 0) return MTL_OK;
+  const int grid = (int)min(ceil_div_ll(n, 256), (long long)mtl_num_sms() * 16);
+  add_bf16_to_f32_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const bf16*>(src), n, dst);
+  MTL_CUDA_LAUNCH_CHECK("add_bf16_to_f32_kernel");
   return MTL_OK;
 }
 

@@ -138,6 +138,36 @@ class Oracle(object):
             x = self.conv(x, s, relu=2, eps=1e-3, weight_name="pointwise_weights")
         return x
 
+    def psroi(self, fmap, boxes, box_ind, D, bins, crop):
+        """utils/ops.py:462-609 position_sensitive_crop_regions(global_pool=True): fmap [B,H,W,bins*D],
+        boxes float32 numpy [R,4] -> [R, D]."""
+        F32 = np.float32
+        nby, nbx = bins
+        gh, gw = crop[0] // nby, crop[1] // nbx
+        boxes = np.asarray(boxes, F32)
+        ymin, xmin, ymax, xmax = [boxes[:, i] for i in range(4)]
+        step_y = ((ymax - ymin) / F32(nby)).astype(F32)
+        step_x = ((xmax - xmin) / F32(nbx)).astype(F32)
+        crops = []
+        for by in range(nby):
+            for bx in range(nbx):
+                b = np.stack([ymin + F32(by) * step_y, xmin + F32(bx) * step_x, ymin + F32(by + 1) * step_y,
+                              xmin + F32(bx + 1) * step_x], 1).astype(F32)
+                split = fmap[..., (by * nbx + bx) * D:(by * nbx + bx + 1) * D]
+                crops.append(ON.crop_and_resize(split, torch.from_numpy(b), torch.from_numpy(box_ind), (gh, gw)))
+        ps = sum(crops) / len(crops)
+        return ps.mean(dim=(1, 2))
+
+    def rfcn_head(self, feats, scope, boxes, box_ind, groups):
+        """RfcnBoxPredictor (bp:180-337): reduce_depth (+bias, ReLU) -> per-group 1x1 maps -> PS-ROI."""
+        r = self.cfg["rfcn"]
+        red = self.conv(feats, scope + "/reduce_depth", bn=False, relu=True)
+        outs = []
+        for name, D in groups:
+            m = self.rb(self.conv(red, scope + "/" + name, bn=False, relu=False, out_round=False))
+            outs.append(self.psroi(m, boxes, box_ind, D, r["bins"], r["crop"]))
+        return outs
+
     def bottleneck(self, x, scope, depth, stride, rate=1):
         s = scope + "/bottleneck_v1"
         cin = x.shape[-1]
@@ -247,27 +277,48 @@ class Oracle(object):
             return ON.max_pool_tf(cr, mk, mk, "VALID") if mk > 1 else cr
 
         bi = np.repeat(np.arange(B), P).astype(np.int64)
-        maps = crops_of(prop_norm.reshape(-1, 4), bi)
+        maps = None if cfg.get("rfcn") else crops_of(prop_norm.reshape(-1, 4), bi)
         out = dict(feat=feat, rpn_box=rpn_box, rpn_cls=rpn_cls, anchors=anchors, keep=keep, prop_norm=prop_norm,
                    prop_abs=prop_abs, nprop=nprop, gts=gts, nms=nms_out)
-        bx, cl = self.head(tail(maps, "SecondStageFeatureExtractor/" + self.arch), "SecondStageBoxPredictor",
-                           ["BoxEncodingPredictor", "ClassPredictor"])
-        out["refined_box_encodings"] = bx.reshape(B * P, K, 4)
-        out["class_predictions_with_background"] = cl
+        rfcn = cfg.get("rfcn")
         mtl = cfg["mtl"]
         stop = mtl.get("stop_gradient_for_aux_tasks", False)
+        flat_props = prop_norm.reshape(-1, 4)
+        if rfcn:
+            bx, cl = self.rfcn_head(self.block4(feat, "SecondStageFeatureExtractor/" + self.arch),
+                                    "SecondStageBoxPredictor", flat_props, bi,
+                                    [("refined_locations", 4 * K), ("class_predictions", K1)])
+        else:
+            bx, cl = self.head(tail(maps, "SecondStageFeatureExtractor/" + self.arch), "SecondStageBoxPredictor",
+                               ["BoxEncodingPredictor", "ClassPredictor"])
+        out["refined_box_encodings"] = bx.reshape(B * P, K, 4)
+        out["class_predictions_with_background"] = cl
         if mtl.get("closeness"):
-            m2 = maps.detach() if stop else maps
-            out["closeness_predictions"] = self.head(tail(m2, "ClosenessBoxPredictor/" + self.arch),
-                                                     "ClosenessBoxPredictor", ["ClassPredictor"])[0]
+            if rfcn:
+                f2 = feat.detach() if stop else feat
+                out["closeness_predictions"] = self.rfcn_head(self.block4(f2, "ClosenessBoxPredictor/" + self.arch),
+                                                              "ClosenessBoxPredictor", flat_props, bi,
+                                                              [("class_predictions", K1)])[0]
+            else:
+                m2 = maps.detach() if stop else maps
+                out["closeness_predictions"] = self.head(tail(m2, "ClosenessBoxPredictor/" + self.arch),
+                                                         "ClosenessBoxPredictor", ["ClassPredictor"])[0]
+        win_feat = None
         if mtl.get("window"):
             wb = np.stack([np.asarray(e["window_boxes"], np.float32) for e in examples])
             nw = wb.shape[1]
-            wm = crops_of(wb.reshape(-1, 4), np.repeat(np.arange(B), nw).astype(np.int64))
-            if stop:
-                wm = wm.detach()
-            out["window_class_predictions"] = self.head(tail(wm, "WindowBoxPredictor/" + self.arch),
-                                                        "WindowBoxPredictor", ["ClassPredictor"])[0]
+            wbi = np.repeat(np.arange(B), nw).astype(np.int64)
+            if rfcn:
+                f3 = feat.detach() if stop else feat
+                win_feat = self.block4(f3, "WindowBoxPredictor/" + self.arch)
+                out["window_class_predictions"] = self.rfcn_head(win_feat, "WindowBoxPredictor", wb.reshape(-1, 4), wbi,
+                                                                 [("class_predictions", K1)])[0]
+            else:
+                wm = crops_of(wb.reshape(-1, 4), wbi)
+                if stop:
+                    wm = wm.detach()
+                out["window_class_predictions"] = self.head(tail(wm, "WindowBoxPredictor/" + self.arch),
+                                                            "WindowBoxPredictor", ["ClassPredictor"])[0]
         if mtl.get("edgemask"):
             w = p["EdgeMaskPredictor/BoxEncodingPredictor/weights"].reshape(2, -1)
             out["edgemask_predictions"] = torch.tanh(feat @ w.t() + p["EdgeMaskPredictor/BoxEncodingPredictor/biases"])
@@ -285,9 +336,13 @@ class Oracle(object):
                 exp = np.stack(exp)                                         # [5,B,P,4]
                 ebi = np.broadcast_to(np.arange(B)[None, :, None], (5, B, P)).reshape(-1).astype(np.int64)
                 with torch.no_grad():
-                    em = crops_of(exp.reshape(-1, 4), ebi)
-                    ew = self.head(tail(em, "WindowBoxPredictor/" + self.arch), "WindowBoxPredictor",
-                                   ["ClassPredictor"])[0]
+                    if rfcn:
+                        ew = self.rfcn_head(win_feat, "WindowBoxPredictor", exp.reshape(-1, 4), ebi,
+                                            [("class_predictions", K1)])[0]
+                    else:
+                        em = crops_of(exp.reshape(-1, 4), ebi)
+                        ew = self.head(tail(em, "WindowBoxPredictor/" + self.arch), "WindowBoxPredictor",
+                                       ["ClassPredictor"])[0]
                 src.append(ew.reshape(5, B * P, K1).permute(1, 0, 2).reshape(B * P, 5 * K1))
             if mtl.get("closeness"):
                 cm = out["closeness_predictions"].detach().mean(0, keepdim=True)

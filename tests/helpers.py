@@ -22,8 +22,13 @@ def oracle_config(cfg):
     g = fr.first_stage_anchor_generator.grid_anchor_generator
     arch = {"faster_rcnn_resnet50": "resnet_v1_50", "faster_rcnn_resnet101": "resnet_v1_101",
             "faster_rcnn_resnet152": "resnet_v1_152", "frcnn_mobilenet_v1": "MobilenetV1"}[fr.feature_extractor.type]
+    rfcn = None
+    if fr.second_stage_box_predictor.WhichOneof("box_predictor_oneof") == "rfcn_box_predictor":
+        r = fr.second_stage_box_predictor.rfcn_box_predictor
+        rfcn = dict(bins=(r.num_spatial_bins_height, r.num_spatial_bins_width), crop=(r.crop_height, r.crop_width),
+                    depth=r.depth)
     return dict(
-        architecture=arch, num_classes=fr.num_classes, scales=list(g.scales), aspect_ratios=list(g.aspect_ratios),
+        rfcn=rfcn, architecture=arch, num_classes=fr.num_classes, scales=list(g.scales), aspect_ratios=list(g.aspect_ratios),
         first_stage_max_proposals=fr.first_stage_max_proposals, second_stage_batch_size=fr.second_stage_batch_size,
         second_stage_balance_fraction=fr.second_stage_balance_fraction,
         first_stage_minibatch_size=fr.first_stage_minibatch_size,

@@ -39,7 +39,7 @@ MOBILE = SMALL[1:]       # MobileNet configs (BASELINE configs[0]: model51 = bas
 
 
 @pytest.mark.parametrize("name,B", [("model12.config", 1), ("model12.config", 2), ("model11.config", 1),
-                                    ("model51.config", 2), ("model52.config", 1)])
+                                    ("model51.config", 2), ("model52.config", 1), ("model42.config", 1)])
 def test_losses_and_gradients_match_oracle(name, B):
     from oracle.model import Oracle
     H, W = 224, 320
