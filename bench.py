@@ -235,13 +235,25 @@ def run_ours(args, rank, world, local_rank):
         ms_dev, ms_e2e = t.tolist()
     if rank != 0:
         return
-    # ---- roofline of the dominant kernel family, measured live: one eager step with per-launch events
+    # ---- roofline of the dominant kernel family, measured live: one eager step with per-launch events.
+    # Two precautions make the event pairs bracket ONLY kernel time: (a) the multi-stream overlap is switched
+    # off for this pass (overlapping kernels share SMs and would inflate each other's duration), (b) a spin
+    # kernel keeps the GPU busy while Python enqueues the step, so no event pair contains host launch latency.
+    from mtl_ssl_b200.nets.layers import Concurrency
+    Concurrency.enabled = False
+    tr._forward_backward(tr.inputs.dev["image"])            # re-warm the single-stream path
+    if world > 1:
+        tr._backward_trunk()
+    model.param_store.g.zero_()
+    torch.cuda.synchronize()
     ops_conv.PROFILE = []
+    torch.cuda._sleep(int(60e-3 * 1.9e9))                   # ~60 ms head start for the host
     tr._forward_backward(tr.inputs.dev["image"])
     if world > 1:
         tr._backward_trunk()
     torch.cuda.synchronize()
     prof, ops_conv.PROFILE = ops_conv.PROFILE, None
+    Concurrency.enabled = True
     model.param_store.g.zero_()
     conv_ms = sum(p_[2].elapsed_time(p_[3]) for p_ in prof)
     conv_flops = sum(p_[1] for p_ in prof)

@@ -336,3 +336,28 @@ def test_depthwise_conv3x3_fwd_dgrad_wgrad(stride):
     dw = torch.zeros(C, 3, 3, device="cuda")
     ops.call("mtl_dwconv3x3_wgrad", dy.cuda(), x.cuda(), N, H, W, C, stride, pt, pl, P, Q, scale.cuda(), dw)
     torch.testing.assert_close(dw.cpu(), wr.grad * scale[:, None, None], rtol=1e-3, atol=1e-3)
+
+
+def test_psroi_fwd_bwd_matches_oracle():
+    """utils/ops.py:462-609 (global_pool=True) through mtl_psroi_fwd / mtl_psroi_bwd, with channel offset."""
+    from mtl_ssl_b200 import ops
+    from oracle.model import Oracle
+    g = torch.Generator().manual_seed(4)
+    B, H, W, D, nb = 2, 11, 13, 5, 9
+    Ct, c0 = 64, 8                                   # PS channels live at [c0, c0 + 9*D) of a wider map
+    fmap = bf(torch.randn(B, H, W, Ct, generator=g))
+    R = 12
+    boxes = rand_norm_boxes(g, R)
+    bi = torch.randint(0, B, (R,), generator=g).int()
+    out = torch.zeros(R, 16, device="cuda")
+    ops.call("mtl_psroi_fwd", fmap.cuda(), B, H, W, Ct, c0, D, 3, 3, 18, 18, boxes.cuda(), bi.cuda(), R, out, 16, 3)
+    fr = fmap.float().requires_grad_(True)
+    o = Oracle({}, {"architecture": "resnet_v1_50"}, bf16=False)
+    want = o.psroi(fr[..., c0:c0 + nb * D], boxes.numpy(), bi.numpy().astype(np.int64), D, (3, 3), (18, 18))
+    torch.testing.assert_close(out[:, 3:3 + D].cpu(), want.detach(), rtol=1e-4, atol=1e-5)
+    assert not out[:, :3].any() and not out[:, 3 + D:].any()
+    dout = torch.randn(R, 16, generator=g)
+    want.backward(dout[:, 3:3 + D])
+    dmap = torch.zeros(B, H, W, Ct, device="cuda")
+    ops.call("mtl_psroi_bwd", dout.cuda(), 16, 3, B, H, W, Ct, c0, D, 3, 3, 18, 18, boxes.cuda(), bi.cuda(), R, dmap)
+    torch.testing.assert_close(dmap.cpu(), fr.grad, rtol=1e-4, atol=1e-5)

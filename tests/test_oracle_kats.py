@@ -270,3 +270,36 @@ def test_same_padding_arithmetic():
     assert ON.same_pad(300, 3, 2) == (150, 0, 1)
     assert ON.same_pad(75, 3, 1) == (75, 1, 1)
     assert ON.same_pad(7, 1, 2) == (4, 0, 0)
+
+
+# ---- utils/ops_test.py:711-781 position_sensitive_crop_regions(global_pool=True)
+def _psroi(fmap, boxes, box_ind, D, bins, crop):
+    from oracle.model import Oracle
+    o = Oracle({}, {"architecture": "resnet_v1_50"}, bf16=False)
+    return o.psroi(fmap, boxes, np.asarray(box_ind, np.int64), D, bins, crop)
+
+
+def test_position_sensitive_constant_channels():
+    img = torch.tensor([float(c) for c in range(1, 7)] * 6).reshape(1, 3, 2, 6)   # channel c holds c+1
+    rng = np.random.default_rng(0)
+    boxes = rng.random((2, 4)).astype(F)
+    for mult in (1, 2):
+        out = _psroi(img, boxes, [0, 0], 1, (3, 2), (3 * mult, 2 * mult))
+        np.testing.assert_allclose(out.numpy(), [[3.5], [3.5]], rtol=1e-6)
+
+
+def test_position_sensitive_equal_channels_and_single_bin():
+    rng = np.random.default_rng(1)
+    image = torch.arange(1, 10, dtype=torch.float32).reshape(1, 3, 3, 1)
+    boxes = np.sort(rng.random((3, 2, 2)).astype(F), axis=1).reshape(3, 4)[:, [0, 2, 1, 3]]
+    boxes = np.ascontiguousarray(boxes[:, [0, 1, 2, 3]])
+    want = ON.crop_and_resize(image, torch.from_numpy(boxes), torch.zeros(3, dtype=torch.long), (2, 2)).mean((1, 2))
+    # position-sensitive pooling of identical channels over a 2x2 bin grid with 1x1 crops per bin samples each
+    # bin's centre; with a single bin it IS crop_and_resize + mean (ops_test.py:759-781)
+    img2 = torch.rand(2, 3, 3, 4)
+    b6 = rng.random((6, 4)).astype(F)
+    bi = np.array([0, 0, 0, 1, 1, 1])
+    got = _psroi(img2, b6, bi, 4, (1, 1), (2, 2))
+    ref = ON.crop_and_resize(img2, torch.from_numpy(b6), torch.from_numpy(bi), (2, 2)).mean((1, 2))
+    torch.testing.assert_close(got, ref)
+    assert want.shape == (3, 1)
