@@ -56,6 +56,8 @@ typedef struct mtl_conv_args {
   int force_bn;             /* 0 = auto tile width */
   int force_splits;         /* 0 = auto split-K */
   float mask_hi;            /* dgrad: > 0 -> ReLU6 mask: gradient only where 0 < mask < mask_hi */
+  long long dy_ld, out_ld, res_ld, mask_ld;   /* pixel pitches in elements for channel slices; 0 = dense */
+  float bias_scale;         /* bias added as bias[n] * bias_scale; 0 = 1.0 */
 } mtl_conv_args;
 int mtl_conv_tc(const mtl_conv_args* args /* host */, mtl_stream_t stream);
 
@@ -122,9 +124,11 @@ int mtl_crop_and_resize_bwd(const void* dcrop /* bf16 */, int B, int H, int W, i
                             const int* box_ind, int R, int crop_h, int crop_w, float* dfeat /* fp32, += */,
                             mtl_stream_t stream);
 int mtl_maxpool_fwd(const void* x, int N, int H, int W, int C, int k, int stride, int pad_h, int pad_w, int P,
-                    int Q, void* y, mtl_stream_t stream);
-int mtl_maxpool_bwd(const void* x, const void* dy, int N, int H, int W, int C, int k, int stride, int pad_h,
-                    int pad_w, int P, int Q, void* dx, mtl_stream_t stream);
+                    int Q, void* y, long long ldy /* pixel pitch of y, 0 = C */, mtl_stream_t stream);
+int mtl_maxpool_bwd(const void* x, const void* dy, long long ldy, int N, int H, int W, int C, int k, int stride,
+                    int pad_h, int pad_w, int P, int Q, void* dx, mtl_stream_t stream);
+/* slim.avg_pool2d(3, stride 1, SAME) of Mixed_5b (slim/nets/inception_resnet_v2.py:176-181); backward=1: gradient */
+int mtl_avgpool3x3_same(const void* x, int N, int H, int W, int C, int backward, void* y, mtl_stream_t stream);
 int mtl_avgpool_fwd(const void* x /* bf16 [R,HW,C] */, int R, int HW, int C, void* y /* bf16 [R,C] */,
                     mtl_stream_t stream);
 int mtl_avgpool_bwd(const void* dy, int dy_fp32, long long ldy, const void* relu_mask /* bf16 [R,HW,C] or NULL */,

@@ -37,7 +37,8 @@ struct Params {
   int tiles_m, tiles_n, splits;
   // gather geometry (operand staged by the gather warps)
   const bf16* gsrc;          // NHWC tensor being gathered
-  int gH, gW, gC;            // its spatial dims and channel count (row pitch)
+  int gH, gW, gC;            // its spatial dims and channel count
+  int gld;                   // its pixel pitch in elements (>= gC: the tensor may be a channel slice)
   int oH, oW;                // row-space spatial dims: row -> (n, oh, ow)
   int rows;                  // number of valid rows in row space
   int S, stride, pad_h, pad_w, dil, transposed;
@@ -49,6 +50,7 @@ struct Params {
   // epilogue
   void* out; long long ldo; int out_fp32;
   const float* bias;         // per output column (FPROP/DGRAD) or nullptr
+  float bias_scale;          // bias is added as bias[n] * bias_scale (scaled residual branches)
   const float* rowscale;     // WGRAD: per output row scale or nullptr
   const void* res; long long ldr; int res_fp32;
   const bf16* mask; long long ldm;
@@ -330,7 +332,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tma_load_2d(stage_a(s), &tmA, full_bar(s), m0, p0);
             tma_load_2d(stage_a(s) + 8192, &tmA, full_bar(s), m0 + 64, p0);
             if (!GATHER_B) {
-              const int nper = p.taps == 1 ? p.tiles_n : p.ntot / BN;   // n-tiles per tap
+              const int nper = (p.ntot + BN - 1) / BN;   // n-tiles per tap
               const int tap = n_tile / nper;
               const int ci0 = (n_tile - tap * nper) * BN;
               if (p.im2col) {
@@ -402,9 +404,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN;
       long long ncol0;     // first output column of this tile
+      int wg_col_in_tap = 0;   // WGRAD: channel offset of this tile inside its filter tap
       if (MODE == WGRAD) {
-        const int nper = p.taps == 1 ? p.tiles_n : p.ntot / BN;
+        const int nper = (p.ntot + BN - 1) / BN;
         ncol0 = (long long)(n_tile / nper) * p.ntot + (long long)(n_tile % nper) * BN;
+        wg_col_in_tap = (n_tile % nper) * BN;
       } else {
         ncol0 = (long long)n_tile * BN;
       }
@@ -424,11 +428,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * sc;
           if (c + 1 < NCH) tmem_ld32(taddr + (c + 1) * 32, v);
-          if (row_ok && ncol0 + c * 32 < p.N) {      // (1x1 layers may have C < BN: columns past C are padding)
+          if (row_ok) {      // columns past C inside a tap are padding (C need not be a multiple of BN)
             float* o = reinterpret_cast<float*>(p.out) + (long long)m * p.ldo + ncol0 + c * 32;
 #pragma unroll
             for (int j = 0; j < 8; ++j)
-              atomicAdd(reinterpret_cast<float4*>(o) + j, make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]));
+              if (wg_col_in_tap + c * 32 + 4 * j < p.ntot)
+                atomicAdd(reinterpret_cast<float4*>(o) + j, make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]));
           }
         }
       } else if (p.epi_tma) {
@@ -480,12 +485,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
                 const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + j);
-                f[4 * j] += t.x; f[4 * j + 1] += t.y; f[4 * j + 2] += t.z; f[4 * j + 3] += t.w;
+                f[4 * j] += t.x * p.bias_scale; f[4 * j + 1] += t.y * p.bias_scale;
+                f[4 * j + 2] += t.z * p.bias_scale; f[4 * j + 3] += t.w * p.bias_scale;
               }
             } else {
 #pragma unroll
               for (int j = 0; j < 32; ++j)
-                if (j < nvalid) f[j] += __ldg(p.bias + n0 + j);
+                if (j < nvalid) f[j] += __ldg(p.bias + n0 + j) * p.bias_scale;
             }
           }
           if (has_res) {
@@ -592,12 +598,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
                 const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + j);
-                f[4 * j] += t.x; f[4 * j + 1] += t.y; f[4 * j + 2] += t.z; f[4 * j + 3] += t.w;
+                f[4 * j] += t.x * p.bias_scale; f[4 * j + 1] += t.y * p.bias_scale;
+                f[4 * j + 2] += t.z * p.bias_scale; f[4 * j + 3] += t.w * p.bias_scale;
               }
             } else {
 #pragma unroll
               for (int j = 0; j < 32; ++j)
-                if (j < nvalid) f[j] += __ldg(p.bias + n0 + j);
+                if (j < nvalid) f[j] += __ldg(p.bias + n0 + j) * p.bias_scale;
             }
           }
           if (p.res) {
@@ -722,7 +729,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           roh = fast_div(r2, p.div_ow);
           row_ = r2 - roh * p.oW;
         }
-        const bf16* img = p.gsrc + (long long)rn * p.gH * p.gW * p.gC;
+        const bf16* img = p.gsrc + (long long)rn * p.gH * p.gW * p.gld;
         // fprop: input coordinate of tap (0,0); dgrad: output-gradient coordinate before the stride division
         const int h0 = p.transposed ? roh + p.pad_h : roh * p.stride - p.pad_h;
         const int w0 = p.transposed ? row_ + p.pad_w : row_ * p.stride - p.pad_w;
@@ -752,7 +759,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           ok = ok && hi >= 0 && hi < p.gH && wi >= 0 && wi < p.gW;
           const int c0 = chunk * BK;
-          const bf16* src = ok ? img + ((hi * p.gW + wi) * p.gC + c0) : p.gsrc;
+          const bf16* src = ok ? img + ((hi * p.gW + wi) * p.gld + c0) : p.gsrc;
           const uint32_t dst = stage_a(s) + dst_row;
           if (c0 + BK <= p.gC) {
             const uint32_t nb = ok ? 16u : 0u;
@@ -779,7 +786,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       } else {
         // WGRAD: rows are pixels of this K block, columns are ci of tap (n_tile / nper)
-        const int nper = p.ntot / BN;
+        const int nper = (p.ntot + BN - 1) / BN;
         const int tap = n_tile / nper, ci0 = (n_tile - tap * nper) * BN;
         const int fr = tap / p.S, fs = tap - fr * p.S;
         const int dh = fr * p.dil - p.pad_h, dw = fs * p.dil - p.pad_w;
@@ -798,21 +805,25 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int hi = oh * p.stride + dh;
           const int wi = ow * p.stride + dw;
           ok = ok && hi >= 0 && hi < p.gH && wi >= 0 && wi < p.gW;
-          const bf16* src = ok ? p.gsrc + ((long long)(n * p.gH + hi) * p.gW + wi) * p.gC + ci0 : p.gsrc;
-          const uint32_t nb = ok ? 16u : 0u;
+          const bf16* src = ok ? p.gsrc + ((long long)(n * p.gH + hi) * p.gW + wi) * p.gld + ci0 : p.gsrc;
 #pragma unroll
           for (int jj = 0; jj < BN / 128; ++jj) {
             const int j = (g >> 6) + 2 * jj;
             const uint32_t dst = stage_b(s) + j * 8192 + pr * 128;
 #pragma unroll
-            for (int q = 0; q < 8; ++q)
-              cp_async16(dst + ((q ^ sw) << 4), src + (ok ? j * 64 + q * 8 : 0), nb);
+            for (int q = 0; q < 8; ++q) {
+              const bool pv = ok && (ci0 + j * 64 + q * 8 < p.gC);      // channels past C are padding
+              cp_async16(dst + ((q ^ sw) << 4), src + (pv ? j * 64 + q * 8 : 0), pv ? 16u : 0u);
+            }
           }
           if (BN == 64) {   // single column block: threads 0..63 stage it, 64..127 only arrive
             if ((g >> 6) == 0) {
               const uint32_t dst = stage_b(s) + pr * 128;
 #pragma unroll
-              for (int q = 0; q < 8; ++q) cp_async16(dst + ((q ^ sw) << 4), src + (ok ? q * 8 : 0), nb);
+              for (int q = 0; q < 8; ++q) {
+                const bool pv = ok && (ci0 + q * 8 < p.gC);
+                cp_async16(dst + ((q ^ sw) << 4), src + (pv ? q * 8 : 0), pv ? 16u : 0u);
+              }
             }
           }
           cp_async_commit();
@@ -897,7 +908,8 @@ typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t
 // NHWC bf16 activation [N,H,W,C] as an im2col tensor map: 64 channels x `pixels` positions per load;
 // the base pixel ranges over [low, dim + up) in each spatial dimension (stride-1 traversal).
 static int make_im2col_map(CUtensorMap* map, const void* base, int N, int H, int W, int C, int low_h, int low_w,
-                           int up_h, int up_w, int pixels) {
+                           int up_h, int up_w, int pixels, long long ld = 0) {
+  if (ld == 0) ld = C;
   static EncodeIm2colFn fn = nullptr;
   if (!fn) {
     void* ptr = nullptr;
@@ -909,12 +921,12 @@ static int make_im2col_map(CUtensorMap* map, const void* base, int N, int H, int
     }
     fn = reinterpret_cast<EncodeIm2colFn>(ptr);
   }
-  if ((reinterpret_cast<uintptr_t>(base) & 15) || (C & 7)) {
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (C & 7) || (ld & 7)) {
     mtl_set_error("gemm_tc: im2col operand must be 16B aligned with C %% 8 == 0");
     return MTL_ERR_ARG;
   }
   cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
-  cuuint64_t gstr[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint64_t gstr[3] = {(cuuint64_t)ld * 2, (cuuint64_t)W * ld * 2, (cuuint64_t)H * W * ld * 2};
   int lower[2] = {low_w, low_h};
   int upper[2] = {up_w, up_h};
   cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
@@ -1006,6 +1018,9 @@ struct mtl_conv_args {
   int force_bn;             // 0 = auto
   int force_splits;         // 0 = auto
   float mask_hi;            // dgrad: > 0 -> mask is a ReLU6 output (gradient only where 0 < mask < mask_hi)
+  // channel-slice support (concatenated branches): pixel pitches in elements, 0 = dense
+  long long dy_ld, out_ld, res_ld, mask_ld;
+  float bias_scale;         // 0 = 1.0
 };
 
 extern "C" int mtl_conv_tc(const mtl_conv_args* a, cudaStream_t stream) {
@@ -1023,7 +1038,8 @@ extern "C" int mtl_conv_tc(const mtl_conv_args* a, cudaStream_t stream) {
   p.S = a->S; p.stride = a->stride; p.pad_h = a->pad_h; p.pad_w = a->pad_w; p.dil = a->dil > 0 ? a->dil : 1;
   p.out = a->out; p.out_fp32 = a->out_fp32; p.bias = a->bias; p.rowscale = a->rowscale;
   p.res = a->res; p.res_fp32 = a->res_fp32; p.mask = reinterpret_cast<const bf16*>(a->mask);
-  p.relu = a->relu; p.mask_hi = a->mask_hi; p.alpha = a->alpha; p.splits = 1; p.taps = a->R * a->S;
+  p.relu = a->relu; p.mask_hi = a->mask_hi; p.alpha = a->alpha;
+  p.bias_scale = a->bias_scale != 0.0f ? a->bias_scale : 1.0f; p.splits = 1; p.taps = a->R * a->S;
   CUtensorMap tmA, tmB;
   memset(&tmA, 0, sizeof(tmA)); memset(&tmB, 0, sizeof(tmB));
   int bn, rc;
@@ -1037,9 +1053,10 @@ extern "C" int mtl_conv_tc(const mtl_conv_args* a, cudaStream_t stream) {
   if (a->mode == FPROP) {
     MTL_CHECK_ARG(a->x && a->w && a->out, "mtl_conv_tc fprop: null tensor");
     p.M = (int)npq; p.N = a->K; p.cpt = ceil_div(a->C, BK); p.k_iters = p.taps * p.cpt;
-    p.gsrc = reinterpret_cast<const bf16*>(a->x); p.gH = a->H; p.gW = a->W; p.gC = a->C;
+    p.gsrc = reinterpret_cast<const bf16*>(a->x); p.gH = a->H; p.gW = a->W; p.gC = a->C; p.gld = a->C;
     p.oH = a->P; p.oW = a->Q; p.rows = p.M; p.transposed = 0;
-    p.ldo = a->K; p.ldr = a->K; p.ldm = a->K;
+    p.ldo = a->out_ld ? a->out_ld : a->K; p.ldr = a->res_ld ? a->res_ld : a->K;
+    p.ldm = a->mask_ld ? a->mask_ld : a->K;
     bn = a->force_bn ? a->force_bn : pick_bn(p.M, a->K);
     if (im2col) {
       p.im_low_h = -a->pad_h; p.im_low_w = -a->pad_w;
@@ -1051,29 +1068,31 @@ extern "C" int mtl_conv_tc(const mtl_conv_args* a, cudaStream_t stream) {
   } else if (a->mode == DGRAD) {
     MTL_CHECK_ARG(a->dy && a->w && a->out, "mtl_conv_tc dgrad: null tensor");
     p.M = (int)nhw; p.N = a->C; p.cpt = ceil_div(a->K, BK); p.k_iters = p.taps * p.cpt;
-    p.gsrc = reinterpret_cast<const bf16*>(a->dy); p.gH = a->P; p.gW = a->Q; p.gC = a->K;
+    const long long dyld = a->dy_ld ? a->dy_ld : a->K;
+    p.gsrc = reinterpret_cast<const bf16*>(a->dy); p.gH = a->P; p.gW = a->Q; p.gC = a->K; p.gld = (int)dyld;
     p.oH = a->H; p.oW = a->W; p.rows = p.M; p.transposed = 1; p.ntot = a->C;
-    p.ldo = a->C; p.ldr = a->C; p.ldm = a->C;
+    p.ldo = a->out_ld ? a->out_ld : a->C; p.ldr = a->res_ld ? a->res_ld : a->C;
+    p.ldm = a->mask_ld ? a->mask_ld : a->C;
     bn = a->force_bn ? a->force_bn : pick_bn(p.M, a->C);
     if (im2col) {
       // dx[h] = sum_r dy[h + pad - r*dil]: a stride-1 correlation over dy with mirrored filter offsets
       p.im_low_h = a->pad_h - (a->R - 1) * p.dil; p.im_low_w = a->pad_w - (a->S - 1) * p.dil;
       if ((rc = make_im2col_map(&tmA, a->dy, a->N, a->P, a->Q, a->K, p.im_low_h, p.im_low_w,
-                                a->H + p.im_low_h - a->P, a->W + p.im_low_w - a->Q, BM))) return rc;
-    } else if (!gather && (rc = make_map(&tmA, a->dy, npq, a->K, a->K, BM))) return rc;
+                                a->H + p.im_low_h - a->P, a->W + p.im_low_w - a->Q, BM, dyld))) return rc;
+    } else if (!gather && (rc = make_map(&tmA, a->dy, npq, a->K, dyld, BM))) return rc;
     if ((rc = make_map(&tmB, a->w, a->K, (long long)p.taps * a->C, (long long)p.taps * a->C, 64))) return rc;
     if (gather) tmA = tmB;
   } else if (a->mode == WGRAD) {
     MTL_CHECK_ARG(a->dy && a->x && a->out, "mtl_conv_tc wgrad: null tensor");
-    MTL_CHECK_ARG(a->C % 64 == 0 || (plain && a->C % 32 == 0),
-                  "mtl_conv_tc wgrad: C must be a multiple of 64 (32 for 1x1 layers) (C=%d)", a->C);
+    const long long dyld = a->dy_ld ? a->dy_ld : a->K;
     p.M = a->K; p.N = p.taps * a->C; p.cpt = 1; p.k_iters = (int)ceil_div_ll(npq, BK);
-    p.gsrc = reinterpret_cast<const bf16*>(a->x); p.gH = a->H; p.gW = a->W; p.gC = a->C;
+    p.gsrc = reinterpret_cast<const bf16*>(a->x); p.gH = a->H; p.gW = a->W; p.gC = a->C; p.gld = a->C;
     p.oH = a->P; p.oW = a->Q; p.rows = (int)npq; p.transposed = 0; p.ntot = a->C;
     p.ldo = (long long)p.taps * a->C;
-    bn = a->force_bn ? a->force_bn : (a->C % 256 == 0 ? 256 : (a->C % 128 == 0 ? 128 : 64));
-    MTL_CHECK_ARG(a->C % bn == 0 || (plain && bn == 64), "mtl_conv_tc wgrad: BN %d must divide C %d", bn, a->C);
-    if ((rc = make_map(&tmA, a->dy, npq, a->K, a->K, 64))) return rc;
+    // channels per tap need not fill the tile: columns past C are zero-filled operands and masked stores
+    bn = a->force_bn ? a->force_bn : (a->C >= 256 ? 256 : (a->C > 64 ? 128 : 64));
+    if (!a->force_bn && bn == 256 && a->C % 256 != 0 && a->C % 256 <= 128) bn = 128;
+    if ((rc = make_map(&tmA, a->dy, npq, a->K, dyld, 64))) return rc;
     if (im2col) {
       p.im_low_h = -a->pad_h; p.im_low_w = -a->pad_w;
       if ((rc = make_im2col_map(&tmB, a->x, a->N, a->H, a->W, a->C, p.im_low_h, p.im_low_w,
@@ -1081,7 +1100,7 @@ extern "C" int mtl_conv_tc(const mtl_conv_args* a, cudaStream_t stream) {
     } else if (!gather && (rc = make_map(&tmB, a->x, nhw, a->C, a->C, 64))) return rc;
     if (gather) tmB = tmA;
     // split K (pixels) so that about one wave of CTAs is launched
-    const int tiles = ceil_div(p.M, BM) * ceil_div(p.N, bn);
+    const int tiles = ceil_div(p.M, BM) * p.taps * ceil_div(a->C, bn);
     int splits = a->force_splits ? a->force_splits : (mtl_num_sms() + tiles - 1) / tiles;
     if (splits > p.k_iters) splits = p.k_iters;
     if (splits < 1) splits = 1;
@@ -1094,7 +1113,7 @@ extern "C" int mtl_conv_tc(const mtl_conv_args* a, cudaStream_t stream) {
   p.div_ohw = make_fast_div(p.oH * p.oW);
   p.div_ow = make_fast_div(p.oW);
   p.tiles_m = ceil_div(p.M, BM);
-  p.tiles_n = ceil_div(p.N, bn);
+  p.tiles_n = (a->mode == WGRAD) ? p.taps * ceil_div(a->C, bn) : ceil_div(p.N, bn);
   // epilogue through shared memory + TMA whenever the output (and residual) are plain bf16 matrices
   CUtensorMap tmO, tmR;
   memset(&tmO, 0, sizeof(tmO)); memset(&tmR, 0, sizeof(tmR));

@@ -139,7 +139,7 @@ crop_resize_bwd_kernel(const bf16* __restrict__ dcrop, int H, int W, int C, cons
 // ------------------------------------------------------------------ max pool (NHWC bf16)
 __global__ void __launch_bounds__(256)
 maxpool_fwd_kernel(const bf16* __restrict__ x, int N, int H, int W, int C, int k, int stride, int pad_h,
-                   int pad_w, int P, int Q, bf16* __restrict__ y) {
+                   int pad_w, int P, int Q, bf16* __restrict__ y, long long ldy) {
   const int nvec = C >> 3;
   const long long total = (long long)N * P * Q * nvec;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
@@ -164,15 +164,15 @@ maxpool_fwd_kernel(const bf16* __restrict__ x, int N, int H, int W, int C, int k
         for (int e = 0; e < 8; ++e) m[e] = fmaxf(m[e], f[e]);
       }
     }
-    reinterpret_cast<uint4*>(y + pix * C)[v] = pack8(m);
+    reinterpret_cast<uint4*>(y + pix * ldy)[v] = pack8(m);
   }
 }
 
 // gather-form MaxPoolGrad: dx[h,w] = sum over windows containing (h,w) whose FIRST maximum
 // (scan order r, s) is (h,w) of dy[window].  Deterministic, no atomics.
 __global__ void __launch_bounds__(256)
-maxpool_bwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy, int N, int H, int W, int C, int k,
-                   int stride, int pad_h, int pad_w, int P, int Q, bf16* __restrict__ dx) {
+maxpool_bwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy, long long ldy, int N, int H, int W, int C,
+                   int k, int stride, int pad_h, int pad_w, int P, int Q, bf16* __restrict__ dx) {
   const int nvec = C >> 3;
   const long long total = (long long)N * H * W * nvec;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
@@ -214,7 +214,7 @@ maxpool_bwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy, int 
           }
         }
         float g[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(dy + (((long long)n * P + p) * Q + q) * C) + v), g);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(dy + (((long long)n * P + p) * Q + q) * ldy) + v), g);
 #pragma unroll
         for (int e = 0; e < 8; ++e)
           if (first[e]) acc[e] += g[e];
@@ -447,25 +447,27 @@ extern "C" int mtl_crop_and_resize_bwd(const void* dcrop, int B, int H, int W, i
 }
 
 extern "C" int mtl_maxpool_fwd(const void* x, int N, int H, int W, int C, int k, int stride, int pad_h, int pad_w,
-                               int P, int Q, void* y, cudaStream_t stream) {
+                               int P, int Q, void* y, long long ldy, cudaStream_t stream) {
+  if (ldy == 0) ldy = C;
   MTL_CHECK_ARG(x && y, "mtl_maxpool_fwd: null tensor");
   CHECK_VEC8(C, "mtl_maxpool_fwd");
   const long long total = (long long)N * P * Q * (C / 8);
   const int grid = (int)min(ceil_div_ll(total, 256), (long long)mtl_num_sms() * 16);
   maxpool_fwd_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const bf16*>(x), N, H, W, C, k, stride, pad_h,
-                                               pad_w, P, Q, reinterpret_cast<bf16*>(y));
+                                               pad_w, P, Q, reinterpret_cast<bf16*>(y), ldy);
   MTL_CUDA_LAUNCH_CHECK("maxpool_fwd_kernel");
   return MTL_OK;
 }
 
-extern "C" int mtl_maxpool_bwd(const void* x, const void* dy, int N, int H, int W, int C, int k, int stride,
-                               int pad_h, int pad_w, int P, int Q, void* dx, cudaStream_t stream) {
+extern "C" int mtl_maxpool_bwd(const void* x, const void* dy, long long ldy, int N, int H, int W, int C, int k,
+                               int stride, int pad_h, int pad_w, int P, int Q, void* dx, cudaStream_t stream) {
+  if (ldy == 0) ldy = C;
   MTL_CHECK_ARG(x && dy && dx, "mtl_maxpool_bwd: null tensor");
   CHECK_VEC8(C, "mtl_maxpool_bwd");
   const long long total = (long long)N * H * W * (C / 8);
   const int grid = (int)min(ceil_div_ll(total, 256), (long long)mtl_num_sms() * 16);
   maxpool_bwd_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const bf16*>(x), reinterpret_cast<const bf16*>(dy),
-                                               N, H, W, C, k, stride, pad_h, pad_w, P, Q,
+                                               ldy, N, H, W, C, k, stride, pad_h, pad_w, P, Q,
                                                reinterpret_cast<bf16*>(dx));
   MTL_CUDA_LAUNCH_CHECK("maxpool_bwd_kernel");
   return MTL_OK;
@@ -778,5 +780,64 @@ extern "C" int mtl_dwconv3x3_wgrad(const void* dy, const void* x, int N, int H, 
   dwconv3x3_wgrad_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const bf16*>(dy), reinterpret_cast<const bf16*>(x),
                                                    N, H, W, C, stride, pad_h, pad_w, P, Q, scale, dw);
   MTL_CUDA_LAUNCH_CHECK("dwconv3x3_wgrad_kernel");
+  return MTL_OK;
+}
+
+// ===================================================================================== avg pool 3x3/1 SAME
+// slim.avg_pool2d(net, 3, stride=1, padding='SAME') of Mixed_5b (slim/nets/inception_resnet_v2.py:176-181):
+// TF divides by the number of in-bounds taps.  bwd: dx[h,w] = sum over windows containing (h,w) of dy/count.
+namespace {
+__global__ void __launch_bounds__(256)
+avgpool3x3_kernel(const bf16* __restrict__ x, int N, int H, int W, int C, int backward, bf16* __restrict__ y) {
+  const int nvec = C >> 3;
+  const long long total = (long long)N * H * W * nvec;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(t % nvec);
+    const long long pix = t / nvec;
+    const int w = (int)(pix % W);
+    const int h = (int)((pix / W) % H);
+    const int n = (int)(pix / ((long long)H * W));
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.0f;
+    int cnt = 0;
+    for (int r = -1; r <= 1; ++r) {
+      const int hh = h + r;
+      if (hh < 0 || hh >= H) continue;
+      for (int s = -1; s <= 1; ++s) {
+        const int ww = w + s;
+        if (ww < 0 || ww >= W) continue;
+        float f[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(x + (((long long)n * H + hh) * W + ww) * C) + v), f);
+        float sc = 1.0f;
+        if (backward) {   // the neighbour's own window size normalises its gradient
+          const int ch = min(hh + 1, H - 1) - max(hh - 1, 0) + 1, cw = min(ww + 1, W - 1) - max(ww - 1, 0) + 1;
+          sc = 1.0f / (float)(ch * cw);
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] += f[e] * sc;
+        ++cnt;
+      }
+    }
+    if (!backward) {
+      const float inv = 1.0f / (float)cnt;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] *= inv;
+    }
+    reinterpret_cast<uint4*>(y + pix * C)[v] = pack8(acc);
+  }
+}
+}  // namespace
+
+extern "C" int mtl_avgpool3x3_same(const void* x, int N, int H, int W, int C, int backward, void* y,
+                                   cudaStream_t stream) {
+  MTL_CHECK_ARG(x && y, "mtl_avgpool3x3_same: null tensor");
+  CHECK_VEC8(C, "mtl_avgpool3x3_same");
+  const long long total = (long long)N * H * W * (C / 8);
+  const int grid = (int)min(ceil_div_ll(total, 256), (long long)mtl_num_sms() * 16);
+  avgpool3x3_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const bf16*>(x), N, H, W, C, backward,
+                                              reinterpret_cast<bf16*>(y));
+  MTL_CUDA_LAUNCH_CHECK("avgpool3x3_kernel");
   return MTL_OK;
 }

@@ -159,8 +159,8 @@ def max_pool(x, out, k, stride, padding="SAME"):
         Q, pw = same_pad(W, k, stride)
     else:
         P, Q, ph, pw = (H - k) // stride + 1, (W - k) // stride + 1, 0, 0
-    assert out.shape == (N, P, Q, C)
-    ops.call("mtl_maxpool_fwd", x, N, H, W, C, k, stride, ph, pw, P, Q, out)
+    assert tuple(out.shape) == (N, P, Q, C)
+    ops.call("mtl_maxpool_fwd", x, N, H, W, C, k, stride, ph, pw, P, Q, out, out.stride(2) if Q > 1 else 0)
     return out
 
 
@@ -175,5 +175,5 @@ def max_pool_bwd(x, dy, dx, k, stride, padding="SAME"):
     _, P, Q, _ = dy.shape
     ph = same_pad(H, k, stride)[1] if padding == "SAME" else 0
     pw = same_pad(W, k, stride)[1] if padding == "SAME" else 0
-    ops.call("mtl_maxpool_bwd", x, dy, N, H, W, C, k, stride, ph, pw, P, Q, dx)
+    ops.call("mtl_maxpool_bwd", x, dy, dy.stride(2) if Q > 1 else 0, N, H, W, C, k, stride, ph, pw, P, Q, dx)
     return dx

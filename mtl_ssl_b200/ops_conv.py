@@ -44,6 +44,8 @@ class ConvArgs(ctypes.Structure):
         ("mask", ctypes.c_void_p),
         ("relu", ctypes.c_int), ("alpha", ctypes.c_float),
         ("force_bn", ctypes.c_int), ("force_splits", ctypes.c_int), ("mask_hi", ctypes.c_float),
+        ("dy_ld", ctypes.c_longlong), ("out_ld", ctypes.c_longlong), ("res_ld", ctypes.c_longlong),
+        ("mask_ld", ctypes.c_longlong), ("bias_scale", ctypes.c_float),
     ]
 
 
@@ -55,6 +57,18 @@ def _dp(t):
     return t.data_ptr() if t is not None else None
 
 
+def _pitch(t):
+    """Pixel pitch (elements) of an NHWC tensor that may be a channel slice of a wider buffer."""
+    N, H, W, C = t.shape
+    ld = t.stride(2) if W > 1 else (t.stride(1) if H > 1 else (t.stride(0) if N > 1 else C))
+    ok = t.stride(3) == 1 and (W == 1 or t.stride(2) == ld) and (H == 1 or t.stride(1) == W * ld) and \
+        (N == 1 or t.stride(0) == H * W * ld) and ld >= C
+    if not ok:
+        raise ValueError("tensor must be NHWC-dense or a channel slice of an NHWC-dense buffer (strides %s)"
+                         % (t.stride(),))
+    return ld
+
+
 def _geom(a, xshape, wshape, stride, pad, dil, P, Q):
     a.N, a.H, a.W, a.C = xshape
     a.K, a.R, a.S, _ = wshape
@@ -63,7 +77,7 @@ def _geom(a, xshape, wshape, stride, pad, dil, P, Q):
 
 
 def conv_fprop(x, w, stride=1, pad=(0, 0), dil=1, out_hw=None, bias=None, res=None, relu=False,
-               out=None, out_dtype=torch.bfloat16, force_bn=0):
+               out=None, out_dtype=torch.bfloat16, force_bn=0, bias_scale=1.0):
     """y = relu?(conv(x, w) + bias + res).  x [N,H,W,C] bf16, w [K,R,S,C] bf16."""
     N, H, W, C = x.shape
     K, R, S, C2 = w.shape
@@ -80,11 +94,13 @@ def conv_fprop(x, w, stride=1, pad=(0, 0), dil=1, out_hw=None, bias=None, res=No
     a.x, a.w, a.out = _dp(x), _dp(w), _dp(out)
     a.out_fp32 = int(out.dtype == torch.float32)
     a.bias = _dp(bias)
+    a.out_ld = _pitch(out)
     if res is not None:
-        assert res.shape == out.shape and res.is_contiguous()
-        a.res, a.res_fp32 = _dp(res), int(res.dtype == torch.float32)
+        assert res.shape == out.shape
+        a.res, a.res_fp32, a.res_ld = _dp(res), int(res.dtype == torch.float32), _pitch(res)
     a.relu = int(relu)
     a.alpha = 1.0
+    a.bias_scale = float(bias_scale)
     a.force_bn = force_bn
     _launch(a, "mtl_conv_tc(fprop)")
     return out
@@ -95,7 +111,7 @@ def conv_dgrad(dy, w, x_shape, stride=1, pad=(0, 0), dil=1, res=None, mask=None,
     """dx = mask>0 ? (conv_transpose(dy, w) + res) : 0.  dy [N,P,Q,K], w [K,R,S,C]."""
     N, P, Q, K = dy.shape
     K2, R, S, C = w.shape
-    assert K == K2 and dy.is_contiguous() and w.is_contiguous()
+    assert K == K2 and w.is_contiguous()
     _, H, W, C2 = x_shape
     assert C2 == C
     if out is None:
@@ -104,13 +120,14 @@ def conv_dgrad(dy, w, x_shape, stride=1, pad=(0, 0), dil=1, res=None, mask=None,
     a.mode = DGRAD
     _geom(a, (N, H, W, C), (K, R, S, C), stride, pad, dil, P, Q)
     a.dy, a.w, a.out = _dp(dy), _dp(w), _dp(out)
+    a.dy_ld, a.out_ld = _pitch(dy), _pitch(out)
     a.out_fp32 = int(out.dtype == torch.float32)
     if res is not None:
-        assert res.shape == out.shape and res.is_contiguous()
-        a.res, a.res_fp32 = _dp(res), int(res.dtype == torch.float32)
+        assert res.shape == out.shape
+        a.res, a.res_fp32, a.res_ld = _dp(res), int(res.dtype == torch.float32), _pitch(res)
     if mask is not None:
-        assert mask.shape == out.shape and mask.dtype == torch.bfloat16 and mask.is_contiguous()
-        a.mask = _dp(mask)
+        assert mask.shape == out.shape and mask.dtype == torch.bfloat16
+        a.mask, a.mask_ld = _dp(mask), _pitch(mask)
         a.mask_hi = float(mask_hi)
     a.alpha = 1.0
     a.force_bn = force_bn
@@ -125,11 +142,12 @@ def conv_wgrad(dy, x, dw, stride=1, pad=(0, 0), dil=1, rowscale=None, alpha=1.0,
     N2, H, W, C = x.shape
     K2, R, S, C2 = dw.shape
     assert N == N2 and K == K2 and C == C2 and dw.dtype == torch.float32
-    assert dy.is_contiguous() and x.is_contiguous() and dw.is_contiguous()
+    assert x.is_contiguous() and dw.is_contiguous()
     a = ConvArgs()
     a.mode = WGRAD
     _geom(a, (N, H, W, C), (K, R, S, C), stride, pad, dil, P, Q)
     a.dy, a.x, a.out = _dp(dy), _dp(x), _dp(dw)
+    a.dy_ld = _pitch(dy)
     a.rowscale = _dp(rowscale)
     a.alpha = float(alpha)
     a.force_bn = force_bn
