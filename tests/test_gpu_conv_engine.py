@@ -1,0 +1,140 @@
+"""GPU numerics of the tcgen05 conv engine (mtl_conv_tc) against a plain PyTorch fp32 reference of the same
+op on the same bf16-rounded operands: fprop / dgrad / wgrad, 1x1, square and rectangular filters, strides,
+odd channel counts, channel-slice inputs/outputs (concatenated branches), fused epilogues.
+Tolerances: bf16 outputs 1e-2 relative to the tensor scale (half a bf16 ulp is 2^-9); fp32 outputs 2e-3."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def ref_conv(x, w, stride, pad, P, Q):
+    xf = x.float().permute(0, 3, 1, 2)
+    wf = w.float().permute(0, 3, 1, 2)
+    xp = F.pad(xf, (pad[1], pad[1] + stride * 8, pad[0], pad[0] + stride * 8))
+    return F.conv2d(xp, wf, stride=stride)[:, :, :P, :Q].permute(0, 2, 3, 1).contiguous()
+
+
+def close(got, want, tol):
+    err = (got.float() - want).abs().max().item()
+    scale = want.abs().max().item() + 1e-6
+    assert err <= tol * scale, (err, scale)
+
+
+CASES = [
+    # N, H, W, C, K, R, S, stride, pad_h, pad_w
+    (64, 7, 7, 1024, 512, 1, 1, 1, 0, 0),
+    (8, 7, 7, 512, 512, 3, 3, 1, 1, 1),
+    (3, 9, 11, 192, 72, 3, 3, 1, 1, 1),
+    (2, 17, 17, 320, 384, 3, 3, 2, 0, 0),
+    (2, 19, 23, 64, 256, 1, 1, 2, 0, 0),          # strided 1x1 (shortcut)
+    (2, 19, 23, 128, 128, 3, 3, 2, 1, 1),         # conv2d_same stride 2
+    (2, 17, 17, 128, 160, 1, 7, 1, 0, 3),         # block17 1x7
+    (2, 17, 17, 160, 192, 7, 1, 1, 3, 0),         # block17 7x1 (C = 2.5 x 64)
+    (4, 8, 8, 192, 224, 1, 3, 1, 0, 1),           # block8 1x3
+    (4, 8, 8, 224, 256, 3, 1, 1, 1, 0),           # block8 3x1 (C = 3.5 x 64)
+    (1, 35, 35, 48, 64, 5, 5, 1, 2, 2),           # Mixed_5b 5x5 on 48 channels
+    (1, 35, 35, 32, 48, 3, 3, 1, 1, 1),           # block35 3x3 on 32 channels
+    (1, 35, 35, 80, 192, 3, 3, 1, 1, 1),          # Conv2d_4a (C = 80)
+    (2, 8, 8, 2080, 192, 1, 1, 1, 0, 0),          # block8 1x1 on 2080 channels
+    (2, 17, 17, 288, 320, 3, 3, 2, 0, 0),         # Mixed_7a strided 3x3, C = 4.5 x 64 (gather path)
+]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_fprop_dgrad_wgrad(case):
+    from mtl_ssl_b200 import ops_conv as oc
+    N, H, W, C, K, R, S, stride, ph, pw = case
+    torch.manual_seed(hash(case) % 1000)
+    P = (H + 2 * ph - R) // stride + 1
+    Q = (W + 2 * pw - S) // stride + 1
+    dev = "cuda"
+    x = torch.randn(N, H, W, C, device=dev).bfloat16()
+    w = (torch.randn(K, R, S, C, device=dev) / (R * S * C) ** 0.5).bfloat16()
+    bias = torch.randn(K, device=dev)
+    res = torch.randn(N, P, Q, K, device=dev).bfloat16()
+    y = oc.conv_fprop(x, w, stride, (ph, pw), 1, (P, Q), bias=bias, res=res, relu=True, bias_scale=0.5)
+    want = torch.relu(ref_conv(x, w, stride, (ph, pw), P, Q) + 0.5 * bias + res.float())
+    close(y, want, 1e-2)
+    y32 = oc.conv_fprop(x, w, stride, (ph, pw), 1, (P, Q), out_dtype=torch.float32)
+    close(y32, ref_conv(x, w, stride, (ph, pw), P, Q), 2e-3)
+    xf = x.float().requires_grad_(True)
+    wf = w.float().requires_grad_(True)
+    yr = ref_conv(xf, wf, stride, (ph, pw), P, Q)
+    dy = torch.randn(N, P, Q, K, device=dev).bfloat16()
+    yr.backward(dy.float())
+    mask = torch.randn(N, H, W, C, device=dev).bfloat16()
+    res2 = torch.randn(N, H, W, C, device=dev).bfloat16()
+    dx = oc.conv_dgrad(dy, w, (N, H, W, C), stride, (ph, pw), 1, res=res2, mask=mask)
+    close(dx, torch.where(mask.float() > 0, xf.grad + res2.float(), torch.zeros_like(xf.grad)), 1e-2)
+    dw = torch.zeros(K, R, S, C, device=dev)
+    rs = torch.rand(K, device=dev) + 0.5
+    oc.conv_wgrad(dy, x, dw, stride, (ph, pw), 1, rowscale=rs, alpha=0.5)
+    oc.conv_wgrad(dy, x, dw, stride, (ph, pw), 1, rowscale=rs, alpha=0.5)       # accumulates
+    close(dw, wf.grad * rs[:, None, None, None], 3e-3)
+
+
+@pytest.mark.parametrize("R,S", [(1, 1), (3, 3), (1, 7)])
+def test_channel_slices(R, S):
+    """Branch outputs written straight into a concat buffer; gradients read from / masked by slices of it."""
+    from mtl_ssl_b200 import ops_conv as oc
+    torch.manual_seed(R * 10 + S)
+    N, H, W, C, K, Ct, c0 = 2, 17, 17, 128, 192, 448, 64
+    ph, pw = (R - 1) // 2, (S - 1) // 2
+    dev = "cuda"
+    x = torch.randn(N, H, W, C, device=dev).bfloat16()
+    w = (torch.randn(K, R, S, C, device=dev) / (R * S * C) ** 0.5).bfloat16()
+    cat = torch.full((N, H, W, Ct), 7.0, device=dev).bfloat16()
+    sl = cat[..., c0:c0 + K]
+    oc.conv_fprop(x, w, 1, (ph, pw), 1, (H, W), relu=True, out=sl)
+    want = torch.relu(ref_conv(x, w, 1, (ph, pw), H, W))
+    close(sl, want, 1e-2)
+    assert (cat[..., :c0] == 7).all() and (cat[..., c0 + K:] == 7).all()
+    dcat = torch.randn(N, H, W, Ct, device=dev).bfloat16()
+    dsl = dcat[..., c0:c0 + K]
+    xf = x.float().requires_grad_(True)
+    wf = w.float().requires_grad_(True)
+    ref_conv(xf, wf, 1, (ph, pw), H, W).backward(dsl.float())
+    xcat = torch.randn(N, H, W, Ct, device=dev).bfloat16()                 # mask living in another concat buffer
+    msl = xcat[..., 32:32 + C]
+    dx = oc.conv_dgrad(dsl, w, (N, H, W, C), 1, (ph, pw), 1, mask=msl)
+    close(dx, torch.where(msl.float() > 0, xf.grad, torch.zeros_like(xf.grad)), 1e-2)
+    dw = torch.zeros(K, R, S, C, device=dev)
+    oc.conv_wgrad(dsl, x, dw, 1, (ph, pw), 1)
+    close(dw, wf.grad, 3e-3)
+
+
+def test_relu6_and_mask_hi():
+    from mtl_ssl_b200 import ops_conv as oc
+    torch.manual_seed(5)
+    N, H, W, C, K = 2, 9, 9, 64, 128
+    x = (torch.randn(N, H, W, C, device="cuda") * 3).bfloat16()
+    w = (torch.randn(K, 1, 1, C, device="cuda") * 0.3).bfloat16()
+    y = oc.conv_fprop(x, w, relu=2)
+    close(y, torch.clamp(ref_conv(x, w, 1, (0, 0), H, W), 0, 6), 1e-2)
+    dy = torch.randn(N, H, W, K, device="cuda").bfloat16()
+    mask = (torch.rand(N, H, W, C, device="cuda") * 8 - 1).bfloat16()
+    dx = oc.conv_dgrad(dy, w, (N, H, W, C), mask=mask, mask_hi=6.0)
+    full = oc.conv_dgrad(dy, w, (N, H, W, C))
+    alive = (mask.float() > 0) & (mask.float() < 6)
+    assert torch.equal(dx, torch.where(alive, full, torch.zeros_like(full)))
+
+
+def test_avgpool3x3_same_fwd_bwd():
+    from mtl_ssl_b200 import ops
+    torch.manual_seed(6)
+    N, H, W, C = 2, 7, 9, 32
+    x = torch.randn(N, H, W, C, device="cuda").bfloat16()
+    y = torch.empty_like(x)
+    ops.call("mtl_avgpool3x3_same", x, N, H, W, C, 0, y)
+    # reference on the CPU in NCHW-contiguous layout (torch's CUDA channels-last backward of
+    # count_include_pad=False pooling returned wrong indices on this build)
+    xr = x.float().cpu().permute(0, 3, 1, 2).contiguous().requires_grad_(True)
+    want = F.avg_pool2d(xr, 3, 1, 1, count_include_pad=False)
+    close(y.cpu(), want.detach().permute(0, 2, 3, 1), 1e-2)
+    dy = torch.randn(N, H, W, C, device="cuda").bfloat16()
+    want.backward(dy.float().cpu().permute(0, 3, 1, 2).contiguous())
+    dx = torch.empty_like(x)
+    ops.call("mtl_avgpool3x3_same", dy, N, H, W, C, 1, dx)
+    close(dx.cpu(), xr.grad.permute(0, 2, 3, 1), 1e-2)
