@@ -11,6 +11,7 @@ from ..core.hyperparams import Hyperparams
 from ..core.mask_predictor import MaskPredictor
 from ..core import preprocessor
 from ..meta_architectures import faster_rcnn_meta_arch, rfcn_meta_arch
+from ..models import faster_rcnn_inception_resnet_v2_feature_extractor as frcnn_inc_res
 from ..models import faster_rcnn_mobilenet_v1_feature_extractor as frcnn_mobilenet_v1
 from ..models import faster_rcnn_resnet_v1_feature_extractor as frcnn_resnet_v1
 
@@ -20,6 +21,9 @@ FASTER_RCNN_FEATURE_EXTRACTOR_CLASS_MAP = {
     "faster_rcnn_resnet101": frcnn_resnet_v1.FasterRCNNResnet101FeatureExtractor,
     "faster_rcnn_resnet152": frcnn_resnet_v1.FasterRCNNResnet152FeatureExtractor,
     "frcnn_mobilenet_v1": frcnn_mobilenet_v1.FasterRCNNMobilenetV1FeatureExtractor,
+    # model_builder.py:64-65: the fork registers Inception-ResNet-v2 under both names
+    "faster_rcnn_inception_v2": frcnn_inc_res.FasterRCNNInceptionResnetV2FeatureExtractor,
+    "faster_rcnn_inception_resnet_v2": frcnn_inc_res.FasterRCNNInceptionResnetV2FeatureExtractor,
 }
 
 

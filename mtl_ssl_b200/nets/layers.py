@@ -54,29 +54,42 @@ def same_pad(in_size, k, stride, rate=1):
 
 
 class Conv2d(object):
+    """slim.conv2d (+ frozen batch norm folded, or bias) + activation.  `k` is an int or (rows, cols);
+    `out_scale` multiplies the whole pre-activation output (Inception-ResNet `net += scale * up`): it is
+    folded into the bf16 weights like a batch-norm scale and applied to the bias in the epilogue."""
+
     def __init__(self, store, scope, cin, cout, k=1, stride=1, rate=1, padding="SAME", bn=True, bias=False,
-                 relu=True, l2=1e-4, trainable=True, init=("variance_scaling",), bn_eps=1e-5, weight_name="weights"):
+                 relu=True, l2=1e-4, trainable=True, init=("variance_scaling",), bn_eps=1e-5, weight_name="weights",
+                 bn_scale=True, bias_l2=0.0, out_scale=None):
         self.scope = scope
-        self.cin, self.cout, self.k, self.stride, self.rate = cin, cout, k, stride, rate
+        self.kh, self.kw = (k, k) if isinstance(k, int) else k
+        self.k = self.kh
+        self.cin, self.cout, self.stride, self.rate = cin, cout, stride, rate
         self.padding = padding          # "SAME" | "VALID" | "EXPLICIT" (resnet_utils.conv2d_same)
         self.relu = relu                # False | True (ReLU) | 2 (ReLU6)
         self.trainable = trainable
-        self.bn = store.add_bn(scope + "/BatchNorm", cout, bn_eps) if bn else None
-        self.weight = store.add(scope + "/" + weight_name, (cout, k, k, cin), l2=l2, trainable=trainable,
-                                init=init, fold=self.bn)
-        self.bias = store.add(scope + "/biases", (cout,), l2=0.0, trainable=trainable) if bias else None
+        self.out_scale = out_scale
+        self.bn = store.add_bn(scope + "/BatchNorm", cout, bn_eps, bn_scale) if bn else None
+        self.fold = self.bn
+        if out_scale is not None:
+            assert not bn
+            self.fold = store.add_bn(None, cout, 0.0)           # virtual: constant per-channel scale
+            self.fold.gamma = self.fold.gamma * float(out_scale)
+        self.weight = store.add(scope + "/" + weight_name, (cout, self.kh, self.kw, cin), l2=l2, trainable=trainable,
+                                init=init, fold=self.fold)
+        self.bias = store.add(scope + "/biases", (cout,), l2=bias_l2, trainable=trainable) if bias else None
 
     # geometry -------------------------------------------------------------------------------
     def geom(self, H, W):
-        k, s, r = self.k, self.stride, self.rate
+        s, r = self.stride, self.rate
         if self.padding == "SAME":
-            P, ph = same_pad(H, k, s, r)
-            Q, pw = same_pad(W, k, s, r)
+            P, ph = same_pad(H, self.kh, s, r)
+            Q, pw = same_pad(W, self.kw, s, r)
         elif self.padding == "VALID":
-            ke = k + (k - 1) * (r - 1)
-            P, Q, ph, pw = (H - ke) // s + 1, (W - ke) // s + 1, 0, 0
+            keh, kew = self.kh + (self.kh - 1) * (r - 1), self.kw + (self.kw - 1) * (r - 1)
+            P, Q, ph, pw = (H - keh) // s + 1, (W - kew) // s + 1, 0, 0
         else:   # conv2d_same with stride > 1: pad (ke-1)//2 before, rest after, then VALID
-            ke = k + (k - 1) * (r - 1)
+            ke = self.kh + (self.kh - 1) * (r - 1)
             ph = pw = (ke - 1) // 2
             P, Q = (H + ke - 1 - ke) // s + 1, (W + ke - 1 - ke) // s + 1
         return P, Q, ph, pw
@@ -90,10 +103,10 @@ class Conv2d(object):
     def fwd(self, x, out, res=None, relu=None):
         N, H, W, C = x.shape
         P, Q, ph, pw = self.geom(H, W)
-        assert out.shape == (N, P, Q, self.cout), (out.shape, (N, P, Q, self.cout))
+        assert tuple(out.shape) == (N, P, Q, self.cout), (out.shape, (N, P, Q, self.cout))
         return oc.conv_fprop(x, self.weight.wb, self.stride, (ph, pw), self.rate, (P, Q),
                              bias=self.epilogue_bias(), res=res, relu=int(self.relu if relu is None else relu),
-                             out=out)
+                             out=out, bias_scale=self.out_scale if self.out_scale is not None else 1.0)
 
     def wgrad(self, x, dy):
         if not self.trainable:
@@ -102,9 +115,11 @@ class Conv2d(object):
         P, Q, ph, pw = self.geom(H, W)
         with torch.cuda.stream(Concurrency.fork()):
             oc.conv_wgrad(dy, x, self.weight.g, self.stride, (ph, pw), self.rate,
-                          rowscale=self.bn.scale if self.bn is not None else None)
+                          rowscale=self.fold.scale if self.fold is not None else None)
             if self.bias is not None:
-                ops.call("mtl_colsum", dy, 0, self.cout, dy.numel() // self.cout, self.cout, 1.0, self.bias.g)
+                rows = dy.shape[0] * dy.shape[1] * dy.shape[2]
+                ops.call("mtl_colsum", dy, 0, oc._pitch(dy), rows, self.cout,
+                         self.out_scale if self.out_scale is not None else 1.0, self.bias.g)
 
     def dgrad(self, dy, x_shape, out, res=None, mask=None, mask_hi=0.0):
         N, H, W, C = x_shape

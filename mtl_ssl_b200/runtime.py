@@ -200,7 +200,10 @@ class ParamStore(object):
         for p in self.params:
             out[p.name] = p.w.detach().cpu().clone()
         for b in self.bns:
-            out[b.scope + "/gamma"] = b.gamma.clone()
+            if b.scope is None:
+                continue
+            if b.has_gamma:
+                out[b.scope + "/gamma"] = b.gamma.clone()
             out[b.scope + "/beta"] = b.beta.clone()
             out[b.scope + "/moving_mean"] = b.mean.clone()
             out[b.scope + "/moving_variance"] = b.var.clone()
@@ -214,8 +217,10 @@ class ParamStore(object):
             else:
                 missing.append(p.name)
         for b in self.bns:
-            for attr, key in (("gamma", "gamma"), ("beta", "beta"), ("mean", "moving_mean"),
-                              ("var", "moving_variance")):
+            if b.scope is None:
+                continue
+            for attr, key in ((("gamma", "gamma"),) if b.has_gamma else ()) + (("beta", "beta"), ("mean", "moving_mean"),
+                                                                                   ("var", "moving_variance")):
                 k = b.scope + "/" + key
                 if k in sd:
                     setattr(b, attr, sd[k].clone().float())
@@ -254,6 +259,11 @@ def _init_tensor(p, gen):
         t = torch.zeros(p.shape)
         t.view(p.shape[0], -1)[:, :real] = _trunc_normal((p.shape[0], real), std, gen)
         return t
+    if kind == "xavier":                # slim default: xavier_initializer (uniform)
+        fan_in = p.numel // p.shape[0]
+        fan_out = p.shape[0] * (p.numel // (p.shape[0] * p.shape[-1])) if len(p.shape) == 4 else p.shape[0]
+        lim = math.sqrt(6.0 / (fan_in + fan_out))
+        return (torch.rand(p.shape, generator=gen) * 2 - 1) * lim
     if kind == "normal":
         return torch.randn(p.shape, generator=gen) * float(p.init[1])
     raise ValueError(kind)

@@ -67,14 +67,18 @@ class Oracle(object):
 
     # ------------------------------------------------------------------ layers
     def conv(self, x, scope, stride=1, rate=1, padding="SAME", bn=True, relu=True, res=None, out_round=True,
-             eps=1e-5, weight_name="weights"):
+             eps=1e-5, weight_name="weights", out_scale=None):
         w = self.p[scope + "/" + weight_name]                # [K,R,S,C]
         if bn:
-            s = self.p[scope + "/BatchNorm/gamma"] / torch.sqrt(self.p[scope + "/BatchNorm/moving_variance"] + eps)
+            gamma = self.p.get(scope + "/BatchNorm/gamma")   # absent when slim.batch_norm(scale=False)
+            s = (1.0 if gamma is None else gamma) / torch.sqrt(self.p[scope + "/BatchNorm/moving_variance"] + eps)
             bias = self.p[scope + "/BatchNorm/beta"] - self.p[scope + "/BatchNorm/moving_mean"] * s
             w = w * s[:, None, None, None]
         else:
             bias = self.p.get(scope + "/biases")
+            if out_scale is not None:                        # net += scale * (conv + bias)
+                w = w * out_scale
+                bias = bias * out_scale
         w = self.rb(w)
         whwio = w.permute(1, 2, 3, 0)
         if padding == "EXPLICIT":
@@ -168,6 +172,75 @@ class Oracle(object):
             outs.append(self.psroi(m, boxes, box_ind, D, r["bins"], r["crop"]))
         return outs
 
+    # ---- Inception-ResNet-v2 (slim/nets/inception_resnet_v2.py:33-268; incres fe:112-170)
+    def _ic(self, x, scope, stride=1, padding="SAME"):
+        return self.conv(x, scope, stride, 1, padding, bn=True, relu=True, eps=1e-3)
+
+    def _ir_block(self, x, scope, kind, scale, act=True):
+        c = self._ic
+        if kind == 35:
+            b = [c(x, scope + "/Branch_0/Conv2d_1x1"),
+                 c(c(x, scope + "/Branch_1/Conv2d_0a_1x1"), scope + "/Branch_1/Conv2d_0b_3x3"),
+                 c(c(c(x, scope + "/Branch_2/Conv2d_0a_1x1"), scope + "/Branch_2/Conv2d_0b_3x3"),
+                   scope + "/Branch_2/Conv2d_0c_3x3")]
+        elif kind == 17:
+            b = [c(x, scope + "/Branch_0/Conv2d_1x1"),
+                 c(c(c(x, scope + "/Branch_1/Conv2d_0a_1x1"), scope + "/Branch_1/Conv2d_0b_1x7"),
+                   scope + "/Branch_1/Conv2d_0c_7x1")]
+        else:
+            b = [c(x, scope + "/Branch_0/Conv2d_1x1"),
+                 c(c(c(x, scope + "/Branch_1/Conv2d_0a_1x1"), scope + "/Branch_1/Conv2d_0b_1x3"),
+                   scope + "/Branch_1/Conv2d_0c_3x1")]
+        mixed = torch.cat(b, 3)
+        y = self.conv(mixed, scope + "/Conv2d_1x1", bn=False, relu=False, res=x, out_round=False, out_scale=scale)
+        return self.rb(torch.relu(y) if act else y)
+
+    def _avgpool3_same(self, x):
+        xn = x.permute(0, 3, 1, 2).contiguous()
+        return TF.avg_pool2d(xn, 3, 1, 1, count_include_pad=False).permute(0, 2, 3, 1)
+
+    def trunk_incres(self, img, scope):
+        c = self._ic
+        x = self.rb((img - 127.5) * (2.0 / 255.0))
+        s0 = scope + "/Conv2d_1a_3x3"
+        w0 = self.p[s0 + "/weights"].reshape(32, -1)[:, :27].reshape(32, 3, 3, 3)
+        sc = 1.0 / torch.sqrt(self.p[s0 + "/BatchNorm/moving_variance"] + 1e-3)
+        b0 = self.p[s0 + "/BatchNorm/beta"] - self.p[s0 + "/BatchNorm/moving_mean"] * sc
+        x = self.rb(torch.relu(ON.conv2d_tf(x, self.rb(w0 * sc[:, None, None, None]).permute(1, 2, 3, 0), 2, "SAME") + b0))
+        x = c(c(x, scope + "/Conv2d_2a_3x3"), scope + "/Conv2d_2b_3x3")
+        x = ON.max_pool_tf(x, 3, 2, "SAME")
+        x = c(c(x, scope + "/Conv2d_3b_1x1"), scope + "/Conv2d_4a_3x3")
+        x = ON.max_pool_tf(x, 3, 2, "SAME")
+        m = scope + "/Mixed_5b"
+        x = torch.cat([c(x, m + "/Branch_0/Conv2d_1x1"),
+                       c(c(x, m + "/Branch_1/Conv2d_0a_1x1"), m + "/Branch_1/Conv2d_0b_5x5"),
+                       c(c(c(x, m + "/Branch_2/Conv2d_0a_1x1"), m + "/Branch_2/Conv2d_0b_3x3"),
+                         m + "/Branch_2/Conv2d_0c_3x3"),
+                       c(self.rb(self._avgpool3_same(x)), m + "/Branch_3/Conv2d_0b_1x1")], 3)
+        for i in range(10):
+            x = self._ir_block(x, "%s/Repeat/block35_%d" % (scope, i + 1), 35, 0.17)
+        m = scope + "/Mixed_6a"
+        x = torch.cat([c(x, m + "/Branch_0/Conv2d_1a_3x3", 2),
+                       c(c(c(x, m + "/Branch_1/Conv2d_0a_1x1"), m + "/Branch_1/Conv2d_0b_3x3"),
+                         m + "/Branch_1/Conv2d_1a_3x3", 2),
+                       ON.max_pool_tf(x, 3, 2, "SAME")], 3)
+        for i in range(20):
+            x = self._ir_block(x, "%s/Repeat_1/block17_%d" % (scope, i + 1), 17, 0.10)
+        return x
+
+    def tail_incres(self, x, scope):
+        c = self._ic
+        m = scope + "/Mixed_7a"
+        x = torch.cat([c(c(x, m + "/Branch_0/Conv2d_0a_1x1"), m + "/Branch_0/Conv2d_1a_3x3", 2, "VALID"),
+                       c(c(x, m + "/Branch_1/Conv2d_0a_1x1"), m + "/Branch_1/Conv2d_1a_3x3", 2, "VALID"),
+                       c(c(c(x, m + "/Branch_2/Conv2d_0a_1x1"), m + "/Branch_2/Conv2d_0b_3x3"),
+                         m + "/Branch_2/Conv2d_1a_3x3", 2, "VALID"),
+                       ON.max_pool_tf(x, 3, 2, "VALID")], 3)
+        for i in range(9):
+            x = self._ir_block(x, "%s/Repeat_2/block8_%d" % (scope, i + 1), 8, 0.20)
+        x = self._ir_block(x, scope + "/Block8", 8, 1.0, act=False)
+        return c(x, scope + "/Conv2d_7b_1x1")
+
     def bottleneck(self, x, scope, depth, stride, rate=1):
         s = scope + "/bottleneck_v1"
         cin = x.shape[-1]
@@ -230,8 +303,10 @@ class Oracle(object):
         A = len(cfg["scales"]) * len(cfg["aspect_ratios"])
         mobile = self.arch == "MobilenetV1"
         fs = "FirstStageFeatureExtractor/" + self.arch
-        feat = self.trunk_mobilenet(images, fs) if mobile else self.trunk(images, fs)
-        tail = self.tail_mobilenet if mobile else self.block4
+        incres = self.arch == "InceptionResnetV2"
+        feat = self.trunk_mobilenet(images, fs) if mobile else (self.trunk_incres(images, fs) if incres
+                                                                  else self.trunk(images, fs))
+        tail = self.tail_mobilenet if mobile else (self.tail_incres if incres else self.block4)
         _, Hf, Wf, _ = feat.shape
         rpn_feat = self.conv(feat, "FirstStageBoxPredictor/Conv", bn=False, relu=True)
         box = self.conv(rpn_feat, "FirstStageBoxPredictor/BoxEncodingPredictor", bn=False, relu=False, out_round=False)

@@ -12,7 +12,7 @@ from oracle import nn as ON
 name = sys.argv[1] if len(sys.argv) > 1 else "model12.config"
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 H, W = 224, 320
-cfg, model, sd, examples, keys, tr = _setup(name, MOBILE if name.startswith("model5") else SMALL, H, W, B)
+cfg, model, sd, examples, keys, tr = _setup(name, MOBILE if name[5] in "56" else SMALL, H, W, B)
 arrays = tr.host_arrays(examples, keys)
 image = tr._bind(arrays)
 pd = tr._forward_backward(image)

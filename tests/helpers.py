@@ -21,7 +21,8 @@ def oracle_config(cfg):
     fr, mtl = cfg.model.faster_rcnn, cfg.model.mtl
     g = fr.first_stage_anchor_generator.grid_anchor_generator
     arch = {"faster_rcnn_resnet50": "resnet_v1_50", "faster_rcnn_resnet101": "resnet_v1_101",
-            "faster_rcnn_resnet152": "resnet_v1_152", "frcnn_mobilenet_v1": "MobilenetV1"}[fr.feature_extractor.type]
+            "faster_rcnn_resnet152": "resnet_v1_152", "frcnn_mobilenet_v1": "MobilenetV1",
+            "faster_rcnn_inception_v2": "InceptionResnetV2"}[fr.feature_extractor.type]
     rfcn = None
     if fr.second_stage_box_predictor.WhichOneof("box_predictor_oneof") == "rfcn_box_predictor":
         r = fr.second_stage_box_predictor.rfcn_box_predictor

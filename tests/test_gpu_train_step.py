@@ -39,11 +39,12 @@ MOBILE = SMALL[1:]       # MobileNet configs (BASELINE configs[0]: model51 = bas
 
 
 @pytest.mark.parametrize("name,B", [("model12.config", 1), ("model12.config", 2), ("model11.config", 1),
-                                    ("model51.config", 2), ("model52.config", 1), ("model42.config", 1)])
+                                    ("model51.config", 2), ("model52.config", 1), ("model42.config", 1),
+                                    ("model62.config", 1)])
 def test_losses_and_gradients_match_oracle(name, B):
     from oracle.model import Oracle
     H, W = 224, 320
-    cfg, model, sd, examples, keys, tr = _setup(name, MOBILE if name.startswith("model5") else SMALL, H, W, B)
+    cfg, model, sd, examples, keys, tr = _setup(name, MOBILE if name[5] in "56" else SMALL, H, W, B)
     arrays = tr.host_arrays(examples, keys)
     image = tr._bind(arrays)
     pd = tr._forward_backward(image)
