@@ -125,18 +125,13 @@ _CPU_WARM = [False]
 
 
 def cpu_reference_throughput(threads, budget_s=25.0):
-    """images/sec of the CPU restatement, extrapolated from two bounded samples (16 and 48 ROIs per head, after
-    one discarded warm-up pass) to the full 256-ROI step by a linear fit time = a + b * rois."""
+    """images/sec of the CPU restatement: one discarded warm-up pass (8 ROIs per head), then ONE complete
+    step of the real workload (256 ROIs per head, 64 windows, 1280 refine windows) timed end to end."""
     if not _CPU_WARM[0]:
         oracle_sample(threads, 8)
         _CPU_WARM[0] = True
-    lo, hi = 16, 48
-    t_lo, _, _ = oracle_sample(threads, lo)
-    t_hi, loss, _ = oracle_sample(threads, hi)
-    b = max((t_hi - t_lo) / float(hi - lo), 0.0)
-    a = max(t_lo - lo * b, 0.0)
-    full = a + 256 * b
-    return 1.0 / full, dict(t_16rois=t_lo, t_48rois=t_hi, fixed_s=a, per_roi_s=b, full_step_s=full, loss=loss)
+    t_full, loss, _ = oracle_sample(threads, 256)
+    return 1.0 / t_full, dict(full_step_s=t_full, loss=loss)
 
 
 def run_reference(args, rank, world):
@@ -151,8 +146,8 @@ def run_reference(args, rank, world):
             vals.append(v)
     value = sum(vals) / len(vals)
     sample = ("oracle/model.py fp32 torch-CPU restatement of the reference step (TF1/py2 reference cannot run "
-              "here); full stage-1 + RPN + proposal path at 600x1000, second stage timed at 16 and 48 ROIs per "
-              "head and extrapolated linearly to 256: %s" % json.dumps(detail))
+              "here); sample = one complete 600x1000 training step (forward, 8 losses + L2, autograd backward) after one "
+              "discarded warm-up pass: %s" % json.dumps(detail))
     line = {"impl": "reference", "metric": "images/sec", "value": value, "unit": "images/sec", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / value, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -312,8 +307,8 @@ def run_ours(args, rank, world, local_rank):
         v, detail = cpu_reference_throughput(threads)
         line["cpu_baseline"] = {"value": v, "unit": "images/sec", "cores": threads, "kind": "port",
                                 "sample": "oracle/model.py (fp32 torch-CPU restatement; the TF1/py2 reference cannot "
-                                          "run here): full stage-1+RPN+proposals at 600x1000, second stage at 16 and "
-                                          "48 ROIs/head extrapolated linearly to 256: %s" % json.dumps(detail)}
+                                          "run here): one complete 600x1000 training step (forward, losses, "
+                                          "autograd backward) after a discarded warm-up pass: %s" % json.dumps(detail)}
     print(json.dumps(line), flush=True)
 
 
