@@ -40,7 +40,7 @@ MOBILE = SMALL[1:]       # MobileNet configs (BASELINE configs[0]: model51 = bas
 
 @pytest.mark.parametrize("name,B", [("model12.config", 1), ("model12.config", 2), ("model11.config", 1),
                                     ("model51.config", 2), ("model52.config", 1), ("model42.config", 1),
-                                    ("model62.config", 1)])
+                                    ("model62.config", 1), ("model22.config", 1)])
 def test_losses_and_gradients_match_oracle(name, B):
     from oracle.model import Oracle
     H, W = 224, 320
@@ -89,3 +89,64 @@ def test_losses_and_gradients_match_oracle(name, B):
         if cos < 0.98 or not (0.9 < ng / max(nw, 1e-30) < 1.1):
             bad.append((p.name, cos, ng, nw))
     assert not bad, bad[:10]
+
+
+def test_full_size_step_properties():
+    """BASELINE configs[1] at full size (model12.config unchanged, 600x1000): size-independent properties of
+    the proposal path, the samplers and the optimizer that must hold whatever the weights are."""
+    from mtl_ssl_b200.builders import model_builder
+    from mtl_ssl_b200.data import synthetic
+    from mtl_ssl_b200.trainer import Trainer
+    from mtl_ssl_b200.utils import synthetic_init
+    from oracle import boxes as OB
+    H, W, B = 600, 1000, 1
+    cfg = load_config("model12.config")
+    model = model_builder.build(cfg.model, True, device="cuda", seed=3)
+    synthetic_init.apply(model.param_store)
+    nk = model.num_kept_anchors((B, H, W, 3))
+    assert nk == 13965                                           # SURVEY 8(a) a5
+    tr = Trainer(model, cfg.train_config, H, W, B, gmax=16, use_cuda_graph=False)
+    ex = synthetic.make_batch(11, B, H, W, 20)
+    arrays = tr.host_arrays(ex, synthetic.make_sampler_keys(12, B, nk, 300))
+    w_before = model.param_store.w.clone()
+    losses = tr.step(arrays)
+    assert all(np.isfinite(v) for v in losses.values()), losses
+    ws = model.workspace.bufs
+    # NMS: scores sorted descending, boxes inside the window with positive area, pairwise IoU <= 0.7, zero padding
+    n = int(ws["rpn/nms_num"][0].item())
+    b = ws["rpn/nms_boxes"][0].cpu().numpy()
+    sc = ws["rpn/nms_scores"][0].cpu().numpy()
+    assert 0 < n <= 300
+    assert np.all(np.diff(sc[:n]) <= 0) and np.all(sc[:n] > 0)
+    assert b[:n].min() >= 0 and b[:n, [0, 2]].max() <= H and b[:n, [1, 3]].max() <= W and np.all(OB.area(b[:n]) > 0)
+    iou = OB.iou(b[:n], b[:n]) - np.eye(n, dtype=np.float32)
+    assert iou.max() <= 0.7 + 1e-6
+    assert not b[n:].any() and not sc[n:].any()
+    # every kept proposal is one of the decoded candidates (gather, not arithmetic)
+    dec = ws["rpn/dec_boxes"][0].cpu().numpy()
+    assert set(map(tuple, b[:n].round(3))) <= set(map(tuple, dec.round(3)))
+    # RPN sampler: exactly 256 anchors, at most 128 positives, only from non-ignored anchors
+    m = ws["rpn/match"][0].cpu().numpy()
+    s = ws["rpn/sampled"][0].cpu().numpy().astype(bool)
+    assert s.sum() == 256 and (m[s] >= 0).sum() <= 128 and np.all(m[s] >= -1)
+    assert int(ws["rpn/sample_counts"][0, 3].item()) == 256
+    # second-stage sampler: <= 256 proposals, <= 64 positives, padding rows are zero
+    npz = int(ws["det/num_proposals"][0].item())
+    pa = ws["det/prop_abs"][0].cpu().numpy()
+    assert 0 < npz <= 256 and not pa[npz:].any()
+    dm = ws["det/match"][0].cpu().numpy()
+    assert (dm[:npz] >= 0).sum() <= 64
+    # optimizer: frozen tensors untouched, trainable tensors moved, gradient arena zeroed, bf16 copy in sync
+    st = model.param_store
+    for p in st.params:
+        sl = slice(p.offset, p.offset + p.numel)
+        moved = not torch.equal(st.w[sl], w_before[sl])
+        if "/_pad/" in p.name:
+            continue
+        if not p.trainable:
+            assert not moved, p.name
+        elif p.l2 > 0:                       # regularised trainable weights always receive a gradient
+            assert moved, p.name
+    assert not st.g.any()
+    p = st.by_name["SecondStageBoxPredictor/ClassPredictor/weights"]
+    assert torch.equal(p.wb.float(), p.w.to(torch.bfloat16).float())
