@@ -80,7 +80,7 @@ int mtl_rpn_decode(const float* rpn_out /* [B,HW,ld] */, long long ld, int box_c
 int mtl_nms_make_keys(const float* boxes, const float* scores, int B, int N, float score_thresh, int require_area,
                       unsigned long long* keys, mtl_stream_t stream);
 int mtl_rank_sort_desc(const unsigned long long* keys, int B, int N, int* order /* [B,N] */,
-                       int* num_valid /* [B] */, mtl_stream_t stream);
+                       int* num_valid /* [B] */, int* rank_ws /* [B,N] workspace */, mtl_stream_t stream);
 /* tf.image.non_max_suppression semantics (TF 1.7), one block per image, zero padded output. */
 int mtl_nms(const float* boxes /* [B,N,4] */, const float* scores /* [B,N] or NULL */, const int* order,
             const int* num_valid, int B, int N, float iou_thresh, int max_out, float* out_boxes /* [B,max,4] */,

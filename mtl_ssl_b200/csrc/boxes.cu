@@ -162,29 +162,40 @@ __global__ void make_keys_kernel(const float4* __restrict__ boxes, const float* 
 // spread over the whole GPU: 14 k keys -> 0.2 G compares, far cheaper than a multi-pass sort's launches.
 constexpr int RS_THREADS = 256;
 constexpr int RS_TILE = 2048;
+constexpr int RS_SPLIT = 4;       // the comparison range is cut in RS_SPLIT slices (grid z) to fill all SMs
 __global__ void __launch_bounds__(RS_THREADS)
-rank_sort_kernel(const u64* __restrict__ keys, int N, int* __restrict__ order, int* __restrict__ num_valid) {
+rank_count_kernel(const u64* __restrict__ keys, int N, int* __restrict__ rank) {
   __shared__ u64 tile[RS_TILE];
   const int b = blockIdx.y;
   const u64* k = keys + (long long)b * N;
   const int i = blockIdx.x * RS_THREADS + threadIdx.x;
   const u64 mine = i < N ? k[i] : 0ull;
-  int rank = 0;
-  for (int t0 = 0; t0 < N; t0 += RS_TILE) {
-    const int n = min(RS_TILE, N - t0);
+  const int per = (N + RS_SPLIT - 1) / RS_SPLIT;
+  const int j0 = blockIdx.z * per, j1 = min(j0 + per, N);
+  int r = 0;
+  for (int t0 = j0; t0 < j1; t0 += RS_TILE) {
+    const int n = min(RS_TILE, j1 - t0);
     __syncthreads();
     for (int t = threadIdx.x; t < n; t += RS_THREADS) tile[t] = k[t0 + t];
     __syncthreads();
     if (mine != 0ull) {
       int t = 0;
       for (; t + 4 <= n; t += 4) {
-        rank += (tile[t] > mine) + (tile[t + 1] > mine) + (tile[t + 2] > mine) + (tile[t + 3] > mine);
+        r += (tile[t] > mine) + (tile[t + 1] > mine) + (tile[t + 2] > mine) + (tile[t + 3] > mine);
       }
-      for (; t < n; ++t) rank += (tile[t] > mine);
+      for (; t < n; ++t) r += (tile[t] > mine);
     }
   }
-  if (mine != 0ull) order[(long long)b * N + rank] = i;
-  const unsigned bal = __ballot_sync(0xffffffffu, mine != 0ull);
+  if (mine != 0ull && r) atomicAdd(rank + (long long)b * N + i, r);
+}
+
+__global__ void rank_scatter_kernel(const u64* __restrict__ keys, const int* __restrict__ rank, int N,
+                                    int* __restrict__ order, int* __restrict__ num_valid) {
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = i < N && keys[(long long)b * N + i] != 0ull;
+  if (valid) order[(long long)b * N + rank[(long long)b * N + i]] = i;
+  const unsigned bal = __ballot_sync(0xffffffffu, valid);
   if ((threadIdx.x & 31) == 0 && bal) atomicAdd(num_valid + b, __popc(bal));
 }
 
@@ -199,81 +210,118 @@ __device__ __forceinline__ bool nms_iou_gt(const float4 a, float area_a, const f
   return iou > thr;
 }
 
-constexpr int NMS_THREADS = 1024;
+constexpr int NMS_CHUNK = 256;        // candidates per chunk
+constexpr int NMS_THREADS = 1024;     // 4 threads per candidate
 constexpr int NMS_MAX_OUT = 1024;
-// One block per image.  Candidates are visited in score order in chunks of 1024: every thread
-// first tests its candidate against the kept list (shared memory), then the chunk's survivors
-// are resolved in order — the next live survivor is found with a bitmask scan, appended to the
-// kept list, and all later survivors test against it in parallel.  Stops at max_out kept.
+// One block per image.  Candidates are visited in score order in chunks of 256, four threads each:
+//   1. the four threads of a candidate test it against interleaved quarters of the kept list of
+//      earlier chunks (shared memory);
+//   2. they compute the candidate's row of the chunk's upper-triangular suppression bit matrix
+//      (8 x 32-bit words in shared memory, two words per thread);
+//   3. ONE warp resolves the chunk in order with the live mask in registers (lane l owns word l):
+//      the lowest live bit is kept and its matrix row is and-not'ed into the mask -- no block barriers
+//      in the serial part and only kept boxes cost an iteration;
+//   4. the newly kept boxes are appended to the kept list / outputs in parallel.
+// Stops at max_out kept.  Same decisions, in the same order, as TF 1.7 NonMaxSuppression.
 __global__ void __launch_bounds__(NMS_THREADS)
 nms_kernel(const float4* __restrict__ boxes, const float* __restrict__ scores, const int* __restrict__ order,
            const int* __restrict__ num_valid, int N, float thr, int max_out, float4* __restrict__ out_boxes,
            float* __restrict__ out_scores, int* __restrict__ out_idx, int* __restrict__ num_out) {
   __shared__ float4 kb[NMS_MAX_OUT];
   __shared__ float ka[NMS_MAX_OUT];
-  __shared__ unsigned alive[NMS_THREADS / 32];
-  __shared__ int s_nkept;
+  __shared__ float4 cb[NMS_CHUNK];
+  __shared__ float ca[NMS_CHUNK];
+  __shared__ int cidx[NMS_CHUNK];
+  __shared__ int dead[NMS_CHUNK];
+  __shared__ unsigned mask[NMS_CHUNK][NMS_CHUNK / 32];
+  __shared__ int newlist[NMS_CHUNK];
+  __shared__ int s_new;
   const int b = blockIdx.x;
   const float4* bx = boxes + (long long)b * N;
   const int* ord = order + (long long)b * N;
   const int nv = min(num_valid[b], N);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int ci = t & (NMS_CHUNK - 1), part = t >> 8;       // candidate in chunk, quarter 0..3
+  constexpr int W = NMS_CHUNK / 32;
   int nkept = 0;
-  for (int pos = 0; pos < nv && nkept < max_out; pos += NMS_THREADS) {
-    const int c = pos + threadIdx.x;
-    bool live = c < nv;
+  for (int pos = 0; pos < nv && nkept < max_out; pos += NMS_CHUNK) {
+    const int c = pos + ci;
+    const int nc = min(NMS_CHUNK, nv - pos);
+    const bool valid = c < nv;
     float4 me = make_float4(0, 0, 0, 0);
     float area = 0.0f;
     int idx = -1;
-    if (live) {
+    if (valid) {
       idx = ord[c];
       const float4 r = bx[idx];
       me = make_float4(fminf(r.x, r.z), fminf(r.y, r.w), fmaxf(r.x, r.z), fmaxf(r.y, r.w));
       area = (me.z - me.x) * (me.w - me.y);
-      for (int k = nkept - 1; k >= 0; --k) {
-        if (nms_iou_gt(me, area, kb[k], ka[k], thr)) { live = false; break; }
-      }
     }
-    const unsigned bal = __ballot_sync(0xffffffffu, live);
-    if (lane == 0) alive[warp] = bal;
+    if (part == 0) { cb[ci] = me; ca[ci] = area; cidx[ci] = idx; dead[ci] = valid ? 0 : 1; }
     __syncthreads();
-    int cur = 0;       // scan position inside the chunk (uniform across the block)
-    while (nkept < max_out) {
-      // next live candidate at position >= cur
-      int nxt = -1;
-      for (int w = cur >> 5; w < NMS_THREADS / 32; ++w) {
-        unsigned m = alive[w];
-        if (w == (cur >> 5)) m &= ~((1u << (cur & 31)) - 1u);
-        if (m) { nxt = (w << 5) + __ffs(m) - 1; break; }
+    if (valid) {
+      for (int k = nkept - 1 - part; k >= 0; k -= 4) {
+        if (nms_iou_gt(me, area, kb[k], ka[k], thr)) { dead[ci] = 1; break; }
       }
-      if (nxt < 0) break;
-      if (threadIdx.x == nxt) {
-        kb[nkept] = me; ka[nkept] = area;
-        const long long o = (long long)b * max_out + nkept;
-        out_boxes[o] = bx[idx];
-        if (out_scores) out_scores[o] = scores[(long long)b * N + idx];
-        if (out_idx) out_idx[o] = idx;
-      }
-      __syncthreads();                       // kept box visible; every thread has read `alive`
-      if (live && (int)threadIdx.x > nxt && nms_iou_gt(me, area, kb[nkept], ka[nkept], thr)) live = false;
-      const unsigned bal2 = __ballot_sync(0xffffffffu, live && (int)threadIdx.x > nxt);
-      if (lane == 0) alive[warp] = bal2;     // bits <= nxt are irrelevant from now on (cur moves past them)
-      __syncthreads();
-      ++nkept;
-      cur = nxt + 1;
-      if (cur >= NMS_THREADS) break;
     }
+    __syncthreads();
+    if (!dead[ci]) {
+#pragma unroll 1
+      for (int w = 2 * part; w < 2 * part + 2; ++w) {    // upper triangle only: columns j > ci
+        unsigned word = 0;
+        const int j0 = w * 32;
+        if (j0 + 31 > ci) {
+          for (int bit = 0; bit < 32; ++bit) {
+            const int j = j0 + bit;
+            if (j > ci && j < nc && nms_iou_gt(cb[j], ca[j], me, area, thr)) word |= 1u << bit;
+          }
+        }
+        mask[ci][w] = word;
+      }
+    }
+    __syncthreads();
+    if (warp == 0) {
+      unsigned aw = 0;
+      if (lane < W) {
+        for (int bit = 0; bit < 32; ++bit)
+          if (!dead[lane * 32 + bit]) aw |= 1u << bit;
+      }
+      int nnew = 0;
+      while (true) {
+        const unsigned nz = __ballot_sync(0xffffffffu, aw != 0u);
+        if (!nz) break;
+        const int L = __ffs(nz) - 1;
+        const unsigned word = __shfl_sync(0xffffffffu, aw, L);
+        const int i = L * 32 + __ffs(word) - 1;
+        if (lane == 0) newlist[nnew] = i;
+        ++nnew;
+        if (nkept + nnew >= max_out) break;
+        if (lane == L) aw &= ~(1u << (i & 31));
+        if (lane >= L && lane < W) aw &= ~mask[i][lane];
+      }
+      if (lane == 0) s_new = nnew;
+    }
+    __syncthreads();
+    const int nnew = s_new;
+    for (int k = t; k < nnew; k += NMS_THREADS) {
+      const int i = newlist[k];
+      kb[nkept + k] = cb[i]; ka[nkept + k] = ca[i];
+      const long long o = (long long)b * max_out + nkept + k;
+      out_boxes[o] = bx[cidx[i]];
+      if (out_scores) out_scores[o] = scores[(long long)b * N + cidx[i]];
+      if (out_idx) out_idx[o] = cidx[i];
+    }
+    nkept += nnew;
     __syncthreads();
   }
   // zero padding (post_processing.py:281-296)
-  for (int k = nkept + threadIdx.x; k < max_out; k += NMS_THREADS) {
+  for (int k = nkept + t; k < max_out; k += NMS_THREADS) {
     const long long o = (long long)b * max_out + k;
     out_boxes[o] = make_float4(0, 0, 0, 0);
     if (out_scores) out_scores[o] = 0.0f;
     if (out_idx) out_idx[o] = -1;
   }
-  if (threadIdx.x == 0) num_out[b] = nkept;
-  (void)s_nkept;
+  if (t == 0) num_out[b] = nkept;
 }
 
 // ------------------------------------------------------------------ IoU + ArgMaxMatcher
@@ -668,13 +716,17 @@ extern "C" int mtl_nms_make_keys(const float* boxes, const float* scores, int B,
 }
 
 extern "C" int mtl_rank_sort_desc(const unsigned long long* keys, int B, int N, int* order, int* num_valid,
-                                  cudaStream_t stream) {
-  MTL_CHECK_ARG(keys && order && num_valid && B > 0 && N > 0, "mtl_rank_sort_desc: bad args");
+                                  int* rank_ws, cudaStream_t stream) {
+  MTL_CHECK_ARG(keys && order && num_valid && rank_ws && B > 0 && N > 0, "mtl_rank_sort_desc: bad args");
   cudaError_t e = cudaMemsetAsync(num_valid, 0, sizeof(int) * B, stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(rank_ws, 0, sizeof(int) * (size_t)B * N, stream);
   if (e != cudaSuccess) { mtl_set_error("mtl_rank_sort_desc: memset: %s", cudaGetErrorString(e)); return MTL_ERR_CUDA; }
-  dim3 grid(ceil_div(N, RS_THREADS), B);
-  rank_sort_kernel<<<grid, RS_THREADS, 0, stream>>>(keys, N, order, num_valid);
-  MTL_CUDA_LAUNCH_CHECK("rank_sort_kernel");
+  dim3 grid(ceil_div(N, RS_THREADS), B, RS_SPLIT);
+  rank_count_kernel<<<grid, RS_THREADS, 0, stream>>>(keys, N, rank_ws);
+  MTL_CUDA_LAUNCH_CHECK("rank_count_kernel");
+  dim3 g2(ceil_div(N, 256), B);
+  rank_scatter_kernel<<<g2, 256, 0, stream>>>(keys, rank_ws, N, order, num_valid);
+  MTL_CUDA_LAUNCH_CHECK("rank_scatter_kernel");
   return MTL_OK;
 }
 

@@ -283,27 +283,34 @@ __global__ void __launch_bounds__(256)
 im2col_f32_kernel(const float* __restrict__ img, int B, int H, int W, int C, int R, int S, int stride, int pad_h,
                   int pad_w, int P, int Q, float m0, float m1, float m2, float m3, float scale,
                   bf16* __restrict__ out, int ld) {
-  const long long gw = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  const long long total = (long long)B * P * Q;
-  if (gw >= total) return;
-  const int q = (int)(gw % Q);
-  const int p = (int)((gw / Q) % P);
-  const int b = (int)(gw / ((long long)P * Q));
+  // one thread per (output pixel, 8-element vector): eight gathered taps -> one 16-byte store
+  const int nvec = ld >> 3;
+  const long long total = (long long)B * P * Q * nvec;
   const int kk = R * S * C;
   const float mean[4] = {m0, m1, m2, m3};
-  bf16* o = out + gw * ld;
-  for (int e = lane; e < ld; e += 32) {
-    float val = 0.0f;
-    if (e < kk) {
-      const int c = e % C;
-      const int rs = e / C;
-      const int s = rs % S, r = rs / S;
-      const int h = p * stride - pad_h + r, w = q * stride - pad_w + s;
-      if (h >= 0 && h < H && w >= 0 && w < W)
-        val = (__ldg(img + (((long long)b * H + h) * W + w) * C + c) - mean[c & 3]) * scale;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(t % nvec);
+    const long long pix = t / nvec;
+    const int q = (int)(pix % Q);
+    const int p = (int)((pix / Q) % P);
+    const int b = (int)(pix / ((long long)P * Q));
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int e = v * 8 + j;
+      float val = 0.0f;
+      if (e < kk) {
+        const int c = e % C;
+        const int rs = e / C;
+        const int s = rs % S, r = rs / S;
+        const int h = p * stride - pad_h + r, w = q * stride - pad_w + s;
+        if (h >= 0 && h < H && w >= 0 && w < W)
+          val = (__ldg(img + (((long long)b * H + h) * W + w) * C + c) - mean[c & 3]) * scale;
+      }
+      f[j] = val;
     }
-    o[e] = __float2bfloat16_rn(val);
+    reinterpret_cast<uint4*>(out + pix * ld)[v] = pack8(f);
   }
 }
 
@@ -511,10 +518,10 @@ extern "C" int mtl_im2col_f32(const float* img, int B, int H, int W, int C, int 
   MTL_CHECK_ARG(ld >= R * S * C && ld % 8 == 0, "mtl_im2col_f32: ld must be >= R*S*C and a multiple of 8");
   float m[4] = {0, 0, 0, 0};
   if (mean) for (int c = 0; c < C; ++c) m[c] = mean[c];
-  const long long warps = (long long)B * P * Q;
-  im2col_f32_kernel<<<(unsigned)ceil_div_ll(warps, 8), 256, 0, stream>>>(img, B, H, W, C, R, S, stride, pad_h, pad_w,
-                                                                        P, Q, m[0], m[1], m[2], m[3], scale,
-                                                                        reinterpret_cast<bf16*>(out), ld);
+  const long long total = (long long)B * P * Q * (ld / 8);
+  const int grid = (int)min(ceil_div_ll(total, 256), (long long)mtl_num_sms() * 32);
+  im2col_f32_kernel<<<grid, 256, 0, stream>>>(img, B, H, W, C, R, S, stride, pad_h, pad_w, P, Q, m[0], m[1], m[2],
+                                              m[3], scale, reinterpret_cast<bf16*>(out), ld);
   MTL_CUDA_LAUNCH_CHECK("im2col_f32_kernel");
   return MTL_OK;
 }

@@ -359,7 +359,7 @@ class FasterRCNNMetaArch(model.DetectionModel):
                  boxes, scores, keys)
         order = ws.get("rpn/order", (B, Nk), torch.int32)
         nvalid = ws.get("rpn/nvalid", (B,), torch.int32)
-        ops.call("mtl_rank_sort_desc", keys, B, Nk, order, nvalid)
+        ops.call("mtl_rank_sort_desc", keys, B, Nk, order, nvalid, ws.get("rpn/rank_ws", (B, Nk), torch.int32))
         nms_b = ws.get("rpn/nms_boxes", (B, M, 4), torch.float32)
         nms_s = ws.get("rpn/nms_scores", (B, M), torch.float32)
         nms_n = ws.get("rpn/nms_num", (B,), torch.int32)

@@ -103,7 +103,7 @@ def test_sort_and_nms_bit_exact(n, max_out):
     ops.call("mtl_nms_make_keys", db, ds, B, n, 0.0, 1, keys)
     order = torch.full((B, n), -1, dtype=torch.int32, device="cuda")
     nvalid = torch.zeros(B, dtype=torch.int32, device="cuda")
-    ops.call("mtl_rank_sort_desc", keys, B, n, order, nvalid)
+    ops.call("mtl_rank_sort_desc", keys, B, n, order, nvalid, torch.empty(B, n, dtype=torch.int32, device="cuda"))
     ob = torch.empty(B, max_out, 4, device="cuda"); osc = torch.empty(B, max_out, device="cuda")
     oi = torch.empty(B, max_out, dtype=torch.int32, device="cuda"); no = torch.zeros(B, dtype=torch.int32, device="cuda")
     ops.call("mtl_nms", db, ds, order, nvalid, B, n, 0.7, max_out, ob, osc, oi, no)
