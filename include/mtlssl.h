@@ -58,8 +58,13 @@ typedef struct mtl_conv_args {
   float mask_hi;            /* dgrad: > 0 -> ReLU6 mask: gradient only where 0 < mask < mask_hi */
   long long dy_ld, out_ld, res_ld, mask_ld;   /* pixel pitches in elements for channel slices; 0 = dense */
   float bias_scale;         /* bias added as bias[n] * bias_scale; 0 = 1.0 */
+  int force_stages;         /* 0 = auto operand pipeline depth */
+  void* ws;                 /* fprop/dgrad split-K workspace (zero filled; left zeroed) or NULL = never split */
+  long long ws_bytes;
 } mtl_conv_args;
 int mtl_conv_tc(const mtl_conv_args* args /* host */, mtl_stream_t stream);
+/* bytes of zeroed workspace mtl_conv_tc would use to split the K loop of this fprop/dgrad (0 = no split) */
+long long mtl_conv_tc_ws_bytes(const mtl_conv_args* args /* host */);
 
 /* ---- anchors (object_detection/anchor_generators/grid_anchor_generator.py:96-214) ------ */
 int mtl_grid_anchors(int Hf, int Wf, const float* scales /* host */, int num_scales,

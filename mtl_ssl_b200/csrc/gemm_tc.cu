@@ -57,7 +57,12 @@ struct Params {
   int relu;
   float alpha;
   float mask_hi;             // > 0: the mask is a ReLU6 output, gradient also dies at mask >= mask_hi
-  int epi_tma;               // FPROP/DGRAD bf16 output (and bf16 residual) move through smem + TMA
+  int epi_tma;               // FPROP/DGRAD bf16 output (and bf16 residual / mask) move through smem + TMA
+  int stages;                // operand pipeline depth (shared memory is carved at launch time)
+  int res_slots;             // per epilogue warp: 32x32 residual(+mask) tiles kept in flight by TMA
+  int epi_warp_bytes;        // per epilogue warp: 2 output staging tiles + res_slots * slot bytes
+  float* ws;                 // FPROP/DGRAD split-K: fp32 partial-sum tiles [tiles_m*tiles_n][BN/4][BM][4], all zero between launches
+  int* ws_cnt;               // FPROP/DGRAD split-K: arrival counter per output tile, zero between launches
 };
 
 // ----------------------------------------------------------------------------- PTX helpers
@@ -213,41 +218,64 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
 template <int BN> struct Cfg {
   static constexpr int B_STAGE_BYTES = BN * 128;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int DEF_STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int TMEM_COLS = 2 * BN;   // double-buffered accumulator (power of two >= 32)
-  static constexpr int EPI_BYTES = 4 * 8192;   // per epilogue warp: 2 output + 2 residual 32x32 bf16 tiles
-  static constexpr int BAR_BYTES = 8 * (2 * STAGES + 4) + 16 + 8 * 8;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;  // + alignment slack
 };
+constexpr int MAX_STAGES = 8;
+constexpr int MAX_RES_SLOTS = 8;
+// barrier block: full[8] empty[8] tfull[2] tempty[2] | tmem slot, split flag | res_bar[8 warps][8 slots]
+constexpr int MAX_EPI_WARPS = 8;
+constexpr int BAR_BYTES = 8 * (2 * MAX_STAGES + 4) + 8 + 8 * MAX_EPI_WARPS * MAX_RES_SLOTS;
+constexpr int SMEM_LIMIT = 232448;           // 227 KB: most dynamic shared memory a CTA may opt in to
+// shared memory of one launch: alignment slack + operand stages + epilogue staging + barriers
+static inline int smem_bytes(int stage_bytes, int stages, int epi_warps, int epi_warp_bytes) {
+  return 1024 + stages * stage_bytes + epi_warps * epi_warp_bytes + BAR_BYTES;
+}
 
 template <int MODE, int BN, bool GATHER>
-__global__ void __launch_bounds__(GATHER ? 384 : 256, 1)
+__global__ void __launch_bounds__(384, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR, const Params p) {
+               const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR,
+               const __grid_constant__ CUtensorMap tmM, const Params p) {
   using C = Cfg<BN>;
-  constexpr int STAGES = C::STAGES;
+  const int STAGES = p.stages;
   constexpr bool A_MN = (MODE == WGRAD);
   constexpr bool B_MN = (MODE != FPROP);
   // which operand the gather warps stage (the other always comes by TMA)
   constexpr bool GATHER_A = GATHER && (MODE != WGRAD);
   constexpr bool GATHER_B = GATHER && (MODE == WGRAD);
+  // warps: 0 TMA producer, 1 MMA issuer, 2 TMEM allocator, 4-7 epilogue; warps 8-11 stage the im2col operand
+  // in the GATHER variants and are a second epilogue group otherwise (the drain of a 128 x BN tile is
+  // issue-latency bound with one warp per scheduler: two groups take alternate 32-column chunks)
+  constexpr int EPI_GROUPS = GATHER ? 1 : 2;
+  constexpr int EPI_THREADS = 128 * EPI_GROUPS;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t epi_base = smem_base + STAGES * C::STAGE_BYTES;
-  const uint32_t bar_base = epi_base + C::EPI_BYTES;
+  const uint32_t bar_base = epi_base + (uint32_t)(4 * EPI_GROUPS) * (uint32_t)p.epi_warp_bytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
-  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
-  auto res_bar = [&](int q, int b) { return bar_base + 8u * (2 * STAGES + 4) + 16u + 8u * (q * 2 + b); };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (MAX_STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * MAX_STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * MAX_STAGES + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * MAX_STAGES + 4);
+  const uint32_t split_flag = tmem_slot + 4u;
+  auto res_bar = [&](int q, int b) { return bar_base + 8u * (2 * MAX_STAGES + 4) + 8u + 8u * (q * MAX_RES_SLOTS + b); };
   auto stage_a = [&](int s) { return smem_base + s * C::STAGE_BYTES; };
   auto stage_b = [&](int s) { return smem_base + s * C::STAGE_BYTES + A_STAGE_BYTES; };
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
+  if (threadIdx.x == 32) {      // descriptors are kernel parameters: fetch them while the previous kernel drains
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+    if (MODE != WGRAD && p.epi_tma) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmO)) : "memory");
+      if (p.res) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmR)) : "memory");
+      if (p.mask) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmM)) : "memory");
+    }
+  }
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1 + (GATHER ? NUM_GATHER_THREADS : 0));
@@ -255,10 +283,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 128);
+      mbar_init(tempty_bar(a), EPI_THREADS);
     }
-    for (int q = 0; q < 4; ++q)
-      for (int b = 0; b < 2; ++b) mbar_init(res_bar(q, b), 1);
+    for (int q = 0; q < 4 * EPI_GROUPS; ++q)
+      for (int b = 0; b < MAX_RES_SLOTS; ++b) mbar_init(res_bar(q, b), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -281,16 +309,24 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int tiles_mn = p.tiles_m * p.tiles_n;
   const int total_tiles = tiles_mn * p.splits;
   const int ips = (p.k_iters + p.splits - 1) / p.splits;   // K iterations per split
+  // tile id -> (split, output tile): WGRAD walks all output tiles of one split first; FPROP/DGRAD keep
+  // the splits of one output tile adjacent so that their partial sums meet in L2 at about the same time
+  auto decode_tile = [&](int tile, int& split, int& rem) {
+    if (MODE == WGRAD) { split = tile / tiles_mn; rem = tile - split * tiles_mn; }
+    else if (p.splits == 1) { split = 0; rem = tile; }
+    else { rem = tile / p.splits; split = tile - rem * p.splits; }
+  };
 
   if (warp == 0) {
     // ============================ TMA producer (one thread) ============================
     if (lane == 0) {
-      uint32_t it = 0;
+      int s = 0;
+      uint32_t ph = 0;
       constexpr uint32_t tx_bytes =
           (GATHER_A ? 0u : (uint32_t)A_STAGE_BYTES) + (GATHER_B ? 0u : (uint32_t)C::B_STAGE_BYTES);
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int split = tile / tiles_mn;
-        const int rem = tile - split * tiles_mn;
+        int split, rem;
+        decode_tile(tile, split, rem);
         const int m_tile = rem / p.tiles_n, n_tile = rem - m_tile * p.tiles_n;
         const int m0 = m_tile * BM;
         const int kb = split * ips, ke = min(kb + ips, p.k_iters);
@@ -301,56 +337,72 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tp0 = fast_div(r2, p.div_ow);
           tq0 = r2 - tp0 * p.oW;
         }
-        for (int k = kb; k < ke; ++k, ++it) {
-          const int s = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1u;
-          mbar_wait(empty_bar(s), ph ^ 1u);
-          mbar_arrive_expect_tx(full_bar(s), tx_bytes);
-          if (MODE == FPROP || MODE == DGRAD) {
-            const int tap = k / p.cpt, chunk = k - tap * p.cpt;
+        // The issue loop is the critical path of the short trunk GEMMs (one thread, dependent integer
+        // chains): every coordinate is carried incrementally, no division inside the K loop.
+        if (MODE == FPROP || MODE == DGRAD) {
+          int tap = 0, chunk = kb;
+          if (kb >= p.cpt) { tap = kb / p.cpt; chunk = kb - tap * p.cpt; }
+          int fr = 0, fs = tap;
+          if (tap >= p.S) { fr = tap / p.S; fs = tap - fr * p.S; }
+          const int ntap = (MODE == FPROP) ? p.gC : p.ntot;    // B-matrix columns per filter tap
+          int acol = chunk * BK;
+          int bbase = tap * ntap + (MODE == FPROP ? 0 : n_tile * BN);
+          int offh = (MODE == FPROP ? fr : p.R - 1 - fr) * p.dil;
+          int offw = (MODE == FPROP ? fs : p.S - 1 - fs) * p.dil;
+          const int bw = tq0 + p.im_low_w, bh = tp0 + p.im_low_h, n0 = n_tile * BN;
+          for (int k = kb; k < ke; ++k) {
+            mbar_wait(empty_bar(s), ph ^ 1u);
+            const uint32_t fb = full_bar(s), sa = stage_a(s);
+            mbar_arrive_expect_tx(fb, tx_bytes);
             if (!GATHER_A) {
-              if (p.im2col) {
-                const int fr = tap / p.S, fs = tap - fr * p.S;
-                const int offh = (MODE == FPROP ? fr : p.R - 1 - fr) * p.dil;
-                const int offw = (MODE == FPROP ? fs : p.S - 1 - fs) * p.dil;
-                tma_load_im2col(stage_a(s), &tmA, full_bar(s), chunk * BK, tq0 + p.im_low_w, tp0 + p.im_low_h, tn0,
-                                offw, offh);
-              } else {
-                tma_load_2d(stage_a(s), &tmA, full_bar(s), chunk * BK, m0);
-              }
+              if (p.im2col) tma_load_im2col(sa, &tmA, fb, acol, bw, bh, tn0, offw, offh);
+              else tma_load_2d(sa, &tmA, fb, acol, m0);
             }
             if (MODE == FPROP) {
-              tma_load_2d(stage_b(s), &tmB, full_bar(s), tap * p.gC + chunk * BK, n_tile * BN);
+              tma_load_2d(sa + A_STAGE_BYTES, &tmB, fb, bbase + acol, n0);
             } else {
 #pragma unroll
               for (int j = 0; j < BN / 64; ++j)
-                tma_load_2d(stage_b(s) + j * 8192, &tmB, full_bar(s),
-                            tap * p.ntot + n_tile * BN + j * 64, chunk * BK);
+                tma_load_2d(sa + A_STAGE_BYTES + j * 8192, &tmB, fb, bbase + j * 64, acol);
             }
-          } else {
+            acol += BK;
+            if (++chunk == p.cpt) {
+              chunk = 0; acol = 0; bbase += ntap;
+              if (++fs == p.S) { fs = 0; ++fr; }
+              offh = (MODE == FPROP ? fr : p.R - 1 - fr) * p.dil;
+              offw = (MODE == FPROP ? fs : p.S - 1 - fs) * p.dil;
+            }
+            if (++s == STAGES) { s = 0; ph ^= 1u; }
+          }
+        } else {
+          const int nper = (p.ntot + BN - 1) / BN;   // n-tiles per tap
+          const int tap = n_tile / nper;
+          const int ci0 = (n_tile - tap * nper) * BN;
+          const int fr = tap / p.S, fs = tap - fr * p.S;
+          for (int k = kb; k < ke; ++k) {
+            mbar_wait(empty_bar(s), ph ^ 1u);
+            const uint32_t fb = full_bar(s), sa = stage_a(s);
+            mbar_arrive_expect_tx(fb, tx_bytes);
             const int p0 = k * BK;
-            tma_load_2d(stage_a(s), &tmA, full_bar(s), m0, p0);
-            tma_load_2d(stage_a(s) + 8192, &tmA, full_bar(s), m0 + 64, p0);
+            tma_load_2d(sa, &tmA, fb, m0, p0);
+            tma_load_2d(sa + 8192, &tmA, fb, m0 + 64, p0);
             if (!GATHER_B) {
-              const int nper = (p.ntot + BN - 1) / BN;   // n-tiles per tap
-              const int tap = n_tile / nper;
-              const int ci0 = (n_tile - tap * nper) * BN;
               if (p.im2col) {
-                const int fr = tap / p.S, fs = tap - fr * p.S;
                 const int pn = fast_div(p0, p.div_ohw);
                 const int r2 = p0 - pn * (p.oH * p.oW);
                 const int pp = fast_div(r2, p.div_ow);
                 const int pq = r2 - pp * p.oW;
 #pragma unroll
                 for (int j = 0; j < BN / 64; ++j)
-                  tma_load_im2col(stage_b(s) + j * 8192, &tmB, full_bar(s), ci0 + j * 64, pq + p.im_low_w,
+                  tma_load_im2col(sa + A_STAGE_BYTES + j * 8192, &tmB, fb, ci0 + j * 64, pq + p.im_low_w,
                                   pp + p.im_low_h, pn, fs * p.dil, fr * p.dil);
               } else {
 #pragma unroll
                 for (int j = 0; j < BN / 64; ++j)
-                  tma_load_2d(stage_b(s) + j * 8192, &tmB, full_bar(s), ci0 + j * 64, p0);
+                  tma_load_2d(sa + A_STAGE_BYTES + j * 8192, &tmB, fb, ci0 + j * 64, p0);
               }
             }
+            if (++s == STAGES) { s = 0; ph ^= 1u; }
           }
         }
       }
@@ -362,17 +414,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) |
                              ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) |
                              ((uint32_t)(BM >> 4) << 24);
-      uint32_t it = 0, tcount = 0;
+      uint32_t tcount = 0;
+      int s = 0;
+      uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
-        const int split = tile / tiles_mn;
+        int split, rem;
+        decode_tile(tile, split, rem);
         const int kb = split * ips, ke = min(kb + ips, p.k_iters);
         const uint32_t acc = tcount & 1u, aph = (tcount >> 1) & 1u;
         mbar_wait(tempty_bar(acc), aph ^ 1u);
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
-        for (int k = kb; k < ke; ++k, ++it) {
-          const int s = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1u;
+        for (int k = kb; k < ke; ++k) {
           mbar_wait(full_bar(s), ph);
           tcgen05_fence_after();
 #pragma unroll
@@ -384,19 +437,62 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tcgen05_mma_bf16(tmem_d, da, db, idesc, (k > kb || ks > 0) ? 1u : 0u);
           }
           tcgen05_commit(empty_bar(s));     // frees the smem stage when these MMAs retire
+          if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
         tcgen05_commit(tfull_bar(acc));     // accumulator ready for the epilogue
       }
     }
-  } else if (warp >= 4 && warp < 8) {
+  } else if (warp >= 4 && (warp < 8 || !GATHER)) {
     // ============================ epilogue warps =======================================
     const int quad = warp & 3;              // TMEM lane quadrant this warp may access
+    const int egrp = (EPI_GROUPS == 2 && warp >= 8) ? 1 : 0;   // group g takes chunks g, g + EPI_GROUPS, ...
+    const int ew = quad + 4 * egrp;         // epilogue warp index (staging memory, barriers)
     const int row = quad * 32 + lane;
+    constexpr int NCH = BN / 32;            // 32-column chunks per tile
+    constexpr int CPW = NCH / EPI_GROUPS;   // chunks per warp per tile
     uint32_t tcount = 0;
-    uint32_t gchunk = 0;                    // running 32-column chunk counter (staging buffer parity)
+    uint32_t gchunk = 0;                    // running chunk counter (output staging buffer parity)
+    // Residual / mask tiles (32 rows x 32 columns bf16) are fetched by TMA into a ring of `res_slots`
+    // slots per warp, `res_slots` chunks ahead of their use and across tile boundaries, so the ~1 us
+    // HBM round trip of a 500 MB residual stream never sits on the drain path.  Chunks are numbered
+    // in processing order; chunk g lives in slot g % res_slots.  iq_* is the issue cursor, cq_slot /
+    // slot_ph the consume cursor and the expected phase bit of every slot's barrier.
+    const int R = (MODE != WGRAD && p.epi_tma) ? p.res_slots : 0;
+    const bool has_res = p.res != nullptr;
+    const bool has_mask = p.mask != nullptr;
+    const uint32_t slot_bytes = 2048u * ((has_res ? 1u : 0u) + (has_mask ? 1u : 0u));
+    const uint32_t ebase = epi_base + (uint32_t)ew * (uint32_t)p.epi_warp_bytes;
+    int iq_tile = blockIdx.x, iq_c = 0, iq_slot = 0, iq_m0 = 0, iq_n0 = 0;
+    int cq_slot = 0;
+    uint32_t slot_ph = 0;
+    auto issue_next = [&](int cur_tile) {
+      if (R == 0) return;
+      if (p.splits > 1 && iq_tile != cur_tile) return;   // split-K: only the finishing CTA reads them
+      if (iq_tile < total_tiles) {
+        if (iq_c == 0) {
+          int sp, rm;
+          decode_tile(iq_tile, sp, rm);
+          const int mt = rm / p.tiles_n;
+          iq_m0 = mt * BM + quad * 32;
+          iq_n0 = (rm - mt * p.tiles_n) * BN;
+        }
+        const int n0 = iq_n0 + (egrp + iq_c * EPI_GROUPS) * 32;
+        if (n0 < p.N && lane == 0) {
+          const uint32_t rb = res_bar(ew, iq_slot);
+          const uint32_t dst = ebase + 4096u + (uint32_t)iq_slot * slot_bytes;
+          mbar_arrive_expect_tx(rb, slot_bytes);
+          if (has_res) tma_load_2d(dst, &tmR, rb, n0, iq_m0);
+          if (has_mask) tma_load_2d(dst + (has_res ? 2048u : 0u), &tmM, rb, n0, iq_m0);
+        }
+      }
+      if (++iq_c == CPW) { iq_c = 0; iq_tile += gridDim.x; }
+      if (++iq_slot == R) iq_slot = 0;
+    };
+    if (p.splits == 1)
+      for (int i = 0; i < R; ++i) issue_next(-1);
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
-      const int split = tile / tiles_mn;
-      const int rem = tile - split * tiles_mn;
+      int split, rem;
+      decode_tile(tile, split, rem);
       const int m_tile = rem / p.tiles_n, n_tile = rem - m_tile * p.tiles_n;
       const int m = m_tile * BM + row;
       const uint32_t acc = tcount & 1u, aph = (tcount >> 1) & 1u;
@@ -413,21 +509,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         ncol0 = (long long)n_tile * BN;
       }
       const bool row_ok = m < p.M;
-      // Software-pipelined drain: the TMEM load of chunk c+1 and the residual / mask loads of
-      // chunk c+1 are in flight while chunk c is combined and stored, so the ~1 us
-      // tcgen05.ld -> global load -> store dependency chain is paid once per tile, not per chunk.
-      constexpr int NCH = BN / 32;
+      // Software-pipelined drain: the TMEM load of chunk c+1 is in flight while chunk c is combined
+      // and stored, so the tcgen05.ld -> store dependency chain is paid once per tile, not per chunk.
       uint32_t v[32];
-      tmem_ld32(taddr, v);
+      tmem_ld32(taddr + egrp * 32, v);
       if (MODE == WGRAD) {
         const float sc = p.alpha * ((p.rowscale && row_ok) ? __ldg(p.rowscale + m) : 1.0f);
 #pragma unroll 1
-        for (int c = 0; c < NCH; ++c) {
+        for (int c = egrp; c < NCH; c += EPI_GROUPS) {
           tmem_ld_wait();
           float f[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * sc;
-          if (c + 1 < NCH) tmem_ld32(taddr + (c + 1) * 32, v);
+          if (c + EPI_GROUPS < NCH) tmem_ld32(taddr + (c + EPI_GROUPS) * 32, v);
           if (row_ok) {      // columns past C inside a tap are padding (C need not be a multiple of BN)
             float* o = reinterpret_cast<float*>(p.out) + (long long)m * p.ldo + ncol0 + c * 32;
 #pragma unroll
@@ -437,46 +531,83 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
       } else if (p.epi_tma) {
-        // Output (and residual) tiles travel through swizzled shared memory and TMA: no per-thread
+        // Output, residual and mask tiles travel through swizzled shared memory and TMA: no per-thread
         // 64-byte strided global accesses, rows/columns outside the tensor are clipped by hardware.
-        const bool has_res = p.res != nullptr;
-        const bool mask_vec = p.mask && (p.ldm & 7) == 0;
         const int m0w = m_tile * BM + quad * 32;
-        const uint32_t ebase = epi_base + quad * 8192;
         const uint32_t swz = ((uint32_t)(lane >> 1) & 3u);
-        uint4 mnext[4];
-        auto prefetch = [&](int c, uint32_t gcn) {
-          const long long n0 = ncol0 + c * 32;
-          if (has_res && lane == 0 && n0 < p.N) {
-            const uint32_t rb = res_bar(quad, gcn & 1u);
-            mbar_arrive_expect_tx(rb, 2048u);
-            tma_load_2d(ebase + 4096u + (gcn & 1u) * 2048u, &tmR, rb, (int)n0, m0w);
-          }
-          if (mask_vec && row_ok && (p.N - n0 >= 32)) {
-            const uint4* r = reinterpret_cast<const uint4*>(p.mask + (long long)m * p.ldm + n0);
+        bool from_ws = false;
+        float4* wst = nullptr;          // this thread's column of the workspace tile [BN/4 float4 columns][128 rows]
+        if (p.splits > 1) {
+          // Split-K: add this CTA's partial tile into the fp32 workspace (L2 reduces); the CTA that
+          // arrives last reads the sum back, runs the fused epilogue on it and re-zeroes the workspace.
+          wst = reinterpret_cast<float4*>(p.ws) + (long long)rem * (BM * BN / 4) + row;
+#pragma unroll 1
+          for (int c = egrp; c < NCH; c += EPI_GROUPS) {
+            tmem_ld_wait();
+            float f[32];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) mnext[j] = __ldg(r + j);
+            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+            if (c + EPI_GROUPS < NCH) tmem_ld32(taddr + (c + EPI_GROUPS) * 32, v);
+            if (row_ok && ncol0 + c * 32 < p.N) {
+              float4* q = wst + c * (8 * BM);      // a warp's 32 lanes hit 512 contiguous bytes
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                atomicAdd(q + j * BM, make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]));
+            }
+          }
+          tcgen05_fence_before();
+          mbar_arrive(tempty_bar(acc));
+          __threadfence();
+          asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+          if (threadIdx.x == 128) {
+            const int old = atomicAdd(p.ws_cnt + rem, 1);
+            const uint32_t fin = (old == p.splits - 1) ? 1u : 0u;
+            if (fin) p.ws_cnt[rem] = 0;
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(split_flag), "r"(fin) : "memory");
+          }
+          asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+          uint32_t fin;
+          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(fin) : "r"(split_flag) : "memory");
+          if (!fin) continue;
+          __threadfence();
+          from_ws = true;
+          iq_tile = tile; iq_c = 0; iq_slot = cq_slot;
+          for (int i = 0; i < R && i < CPW; ++i) issue_next(tile);
+        }
+        auto load_acc = [&](int c) {
+          if (from_ws) {
+            if (row_ok && ncol0 + c * 32 < p.N) {
+              float4* q = wst + c * (8 * BM);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 t = __ldcg(q + j * BM);
+                v[4 * j] = __float_as_uint(t.x); v[4 * j + 1] = __float_as_uint(t.y);
+                v[4 * j + 2] = __float_as_uint(t.z); v[4 * j + 3] = __float_as_uint(t.w);
+              }
+#pragma unroll
+              for (int j = 0; j < 8; ++j) __stcg(q + j * BM, make_float4(0.0f, 0.0f, 0.0f, 0.0f));
+            }
+          } else {
+            tmem_ld32(taddr + c * 32, v);
           }
         };
-        prefetch(0, gchunk);
+        if (from_ws) load_acc(egrp);
 #pragma unroll 1
-        for (int c = 0; c < NCH; ++c, ++gchunk) {
+        for (int c = egrp; c < NCH; c += EPI_GROUPS, ++gchunk) {
           tmem_ld_wait();
           float f[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-          uint4 mcur[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) mcur[j] = mnext[j];
-          if (c + 1 < NCH) {
-            tmem_ld32(taddr + (c + 1) * 32, v);
-            prefetch(c + 1, gchunk + 1);
-          } else {
+          if (c + EPI_GROUPS < NCH) {
+            load_acc(c + EPI_GROUPS);
+          } else if (!from_ws) {
             tcgen05_fence_before();
             mbar_arrive(tempty_bar(acc));       // accumulator fully drained: the MMA warp may reuse it
           }
           const long long n0 = ncol0 + c * 32;
-          if (n0 >= p.N) continue;
+          const int slot = cq_slot;
+          if (R && ++cq_slot == R) cq_slot = 0;
+          if (n0 >= p.N) { issue_next(tile); continue; }
           const int nvalid = (int)min((long long)32, (long long)p.N - n0);
           const bool vec = (nvalid == 32);
           const uint32_t buf = gchunk & 1u;
@@ -494,9 +625,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (j < nvalid) f[j] += __ldg(p.bias + n0 + j) * p.bias_scale;
             }
           }
+          const uint32_t rrow = ebase + 4096u + (uint32_t)slot * slot_bytes + lane * 64u;
+          if (R) {
+            mbar_wait(res_bar(ew, slot), (slot_ph >> slot) & 1u);
+            slot_ph ^= 1u << slot;
+          }
           if (has_res) {
-            mbar_wait(res_bar(quad, buf), (gchunk >> 1) & 1u);
-            const uint32_t rrow = ebase + 4096u + buf * 2048u + lane * 64u;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const uint4 t = lds128(rrow + ((j ^ swz) << 4));
@@ -516,23 +650,22 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               for (int j = 0; j < 32; ++j) f[j] = fminf(f[j], 6.0f);
             }
           }
-          if (p.mask && row_ok) {
-            if (vec && mask_vec) {
+          if (has_mask) {      // rows outside the tensor arrive as zeros: dead
+            const uint32_t mrow = rrow + (has_res ? 2048u : 0u);
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const uint32_t w[4] = {mcur[j].x, mcur[j].y, mcur[j].z, mcur[j].w};
+            for (int j = 0; j < 4; ++j) {
+              const uint4 t = lds128(mrow + ((j ^ swz) << 4));
+              const uint32_t w[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                  if (mask_dead(__uint_as_float(w[q] << 16), p.mask_hi)) f[8 * j + 2 * q] = 0.0f;
-                  if (mask_dead(__uint_as_float(w[q] & 0xffff0000u), p.mask_hi)) f[8 * j + 2 * q + 1] = 0.0f;
-                }
+              for (int q = 0; q < 4; ++q) {
+                if (mask_dead(__uint_as_float(w[q] << 16), p.mask_hi)) f[8 * j + 2 * q] = 0.0f;
+                if (mask_dead(__uint_as_float(w[q] & 0xffff0000u), p.mask_hi)) f[8 * j + 2 * q + 1] = 0.0f;
               }
-            } else {
-              const bf16* r = p.mask + (long long)m * p.ldm + n0;
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (j < nvalid && mask_dead(__bfloat162float(r[j]), p.mask_hi)) f[j] = 0.0f;
             }
+          }
+          if (R) {
+            __syncwarp();        // every lane has read the slot: refill it with the chunk `R` ahead
+            issue_next(tile);
           }
           // the TMA store issued two chunks ago must have finished reading this staging buffer
           if (lane == 0) bulk_wait_read<1>();
@@ -557,37 +690,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         continue;     // tempty already signalled
       } else {
+        // Direct epilogue (fp32 outputs / residuals, unaligned pitches: the small FC heads): per-thread
+        // row accesses straight to global memory.
         const bool res_bf16 = p.res && !p.res_fp32 && (p.ldr & 7) == 0;
         const bool mask_vec = p.mask && (p.ldm & 7) == 0;
-        uint4 rnext[4], mnext[4];
-        auto prefetch = [&](int c) {
-          const long long n0 = ncol0 + c * 32;
-          const bool full = row_ok && (p.N - n0 >= 32);
-          if (res_bf16 && full) {
-            const uint4* r = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.res) + (long long)m * p.ldr + n0);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) rnext[j] = __ldg(r + j);
-          }
-          if (mask_vec && full) {
-            const uint4* r = reinterpret_cast<const uint4*>(p.mask + (long long)m * p.ldm + n0);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) mnext[j] = __ldg(r + j);
-          }
-        };
-        prefetch(0);
 #pragma unroll 1
-        for (int c = 0; c < NCH; ++c) {
+        for (int c = egrp; c < NCH; c += EPI_GROUPS) {
           tmem_ld_wait();
           float f[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-          uint4 rcur[4], mcur[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) { rcur[j] = rnext[j]; mcur[j] = mnext[j]; }
-          if (c + 1 < NCH) {
-            tmem_ld32(taddr + (c + 1) * 32, v);
-            prefetch(c + 1);
-          }
+          if (c + EPI_GROUPS < NCH) tmem_ld32(taddr + (c + EPI_GROUPS) * 32, v);
           const long long n0 = ncol0 + c * 32;
           if (!row_ok) continue;
           const int nvalid = (int)min((long long)32, (long long)p.N - n0);
@@ -622,9 +735,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                   if (j < nvalid) f[j] += __ldg(r + j);
               }
             } else if (vec && res_bf16) {
+              const uint4* r = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.res) + (long long)m * p.ldr + n0);
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                const uint32_t w[4] = {rcur[j].x, rcur[j].y, rcur[j].z, rcur[j].w};
+                const uint4 t = __ldg(r + j);
+                const uint32_t w[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                   f[8 * j + 2 * q] += __uint_as_float(w[q] << 16);
@@ -648,9 +763,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           if (p.mask) {
             if (vec && mask_vec) {
+              const uint4* r = reinterpret_cast<const uint4*>(p.mask + (long long)m * p.ldm + n0);
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                const uint32_t w[4] = {mcur[j].x, mcur[j].y, mcur[j].z, mcur[j].w};
+                const uint4 t = __ldg(r + j);
+                const uint32_t w[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                   if (mask_dead(__uint_as_float(w[q] << 16), p.mask_hi)) f[8 * j + 2 * q] = 0.0f;
@@ -707,16 +824,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ============================ im2col gather warps ==================================
     // Each of the 128 threads owns one 128-byte row (FPROP/DGRAD: one output pixel of the A
     // tile; WGRAD: one pixel of the B tile for half of the 64-channel column blocks).
-    constexpr int DEPTH = (STAGES >= 6) ? 3 : 2;   // cp.async groups kept in flight besides the current one
+    constexpr int DEPTH = (BN <= 128) ? 3 : 2;   // cp.async groups kept in flight besides the current one (< stages)
     const int g = threadIdx.x - 256;
     uint32_t it = 0;
     uint32_t pending_first = 0;    // oldest iteration whose full-barrier arrive is outstanding
+    int s = 0, pf_s = 0;           // stage of iteration `it` / of iteration `pending_first`
+    uint32_t ph = 0;
     const int ohw = p.oH * p.oW;
     // The gather is on the critical path of every 3x3 / strided layer: all per-iteration index math
     // is strength-reduced (no divisions inside the K loop; row decode uses multiply-shift division).
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int split = tile / tiles_mn;
-      const int rem = tile - split * tiles_mn;
+      int split, rem;
+      decode_tile(tile, split, rem);
       const int m_tile = rem / p.tiles_n, n_tile = rem - m_tile * p.tiles_n;
       const int kb = split * ips, ke = min(kb + ips, p.k_iters);
       if (GATHER_A) {
@@ -739,8 +858,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t dst_row = g * 128;
         const int sw = g & 7;
         for (int k = kb; k < ke; ++k, ++it) {
-          const int s = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1u;
           mbar_wait(empty_bar(s), ph ^ 1u);
           int hi, wi;
           bool ok = rvalid;
@@ -777,10 +894,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (++fs == p.S) { fs = 0; ++fr; }
           }
           cp_async_commit();
+          if (++s == STAGES) { s = 0; ph ^= 1u; }
           if (it - pending_first >= (uint32_t)DEPTH) {
             cp_async_wait<DEPTH>();
             fence_proxy_async();
-            mbar_arrive(full_bar(pending_first % STAGES));
+            mbar_arrive(full_bar(pf_s));
+            if (++pf_s == STAGES) pf_s = 0;
             ++pending_first;
           }
         }
@@ -793,8 +912,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int pr = g & 63;
         const int sw = pr & 7;
         for (int k = kb; k < ke; ++k, ++it) {
-          const int s = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1u;
           mbar_wait(empty_bar(s), ph ^ 1u);
           const int pix = k * BK + pr;
           bool ok = pix < p.rows;
@@ -827,10 +944,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
           cp_async_commit();
+          if (++s == STAGES) { s = 0; ph ^= 1u; }
           if (it - pending_first >= (uint32_t)DEPTH) {
             cp_async_wait<DEPTH>();
             fence_proxy_async();
-            mbar_arrive(full_bar(pending_first % STAGES));
+            mbar_arrive(full_bar(pf_s));
+            if (++pf_s == STAGES) pf_s = 0;
             ++pending_first;
           }
         }
@@ -838,7 +957,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     cp_async_wait<0>();
     fence_proxy_async();
-    for (; pending_first < it; ++pending_first) mbar_arrive(full_bar(pending_first % STAGES));
+    for (; pending_first < it; ++pending_first) {
+      mbar_arrive(full_bar(pf_s));
+      if (++pf_s == STAGES) pf_s = 0;
+    }
   }
 
   tcgen05_fence_before();
@@ -939,14 +1061,20 @@ static int make_im2col_map(CUtensorMap* map, const void* base, int N, int H, int
 
 template <int MODE, int BN, bool GATHER>
 static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const CUtensorMap& tmR,
-                  const Params& p, cudaStream_t stream) {
+                  const CUtensorMap& tmM, const Params& p, cudaStream_t stream) {
   using C = Cfg<BN>;
   auto kern = tc_gemm_kernel<MODE, BN, GATHER>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
     if (e != cudaSuccess) { mtl_set_error("gemm_tc: smem attribute: %s", cudaGetErrorString(e)); return MTL_ERR_CUDA; }
     attr_set = true;
+  }
+  const int smem = smem_bytes(C::STAGE_BYTES, p.stages, GATHER ? 4 : 8, p.epi_warp_bytes);
+  if (smem > SMEM_LIMIT || p.stages < 3 || p.stages > MAX_STAGES || (GATHER && BN <= 128 && p.stages < 4)) {
+    mtl_set_error("gemm_tc: bad shared-memory carve (stages %d, epilogue %d B/warp, %d B)", p.stages,
+                  p.epi_warp_bytes, smem);
+    return MTL_ERR_ARG;
   }
   const int total = p.tiles_m * p.tiles_n * p.splits;
   const int grid = total < mtl_num_sms() ? total : mtl_num_sms();
@@ -954,15 +1082,15 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensor
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(GATHER ? 384 : 256);
-  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.blockDim = dim3(384);
+  cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = no_pdl ? 0 : 1;
-  cudaError_t le = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmO, tmR, p);
+  cudaError_t le = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmO, tmR, tmM, p);
   if (le != cudaSuccess) {
     mtl_set_error("tc_gemm_kernel: launch failed: %s", cudaGetErrorString(le));
     (void)cudaGetLastError();
@@ -972,13 +1100,14 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensor
   return MTL_OK;
 }
 
+struct Maps { CUtensorMap a, b, o, r, m; };
+
 template <int MODE, bool GATHER>
-static int dispatch_bn(int bn, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& o,
-                       const CUtensorMap& r, const Params& p, cudaStream_t st) {
+static int dispatch_bn(int bn, const Maps& t, const Params& p, cudaStream_t st) {
   switch (bn) {
-    case 256: return launch<MODE, 256, GATHER>(a, b, o, r, p, st);
-    case 128: return launch<MODE, 128, GATHER>(a, b, o, r, p, st);
-    case 64: return launch<MODE, 64, GATHER>(a, b, o, r, p, st);
+    case 256: return launch<MODE, 256, GATHER>(t.a, t.b, t.o, t.r, t.m, p, st);
+    case 128: return launch<MODE, 128, GATHER>(t.a, t.b, t.o, t.r, t.m, p, st);
+    case 64: return launch<MODE, 64, GATHER>(t.a, t.b, t.o, t.r, t.m, p, st);
   }
   mtl_set_error("gemm_tc: unsupported BN %d", bn);
   return MTL_ERR_UNSUPPORTED;
@@ -993,6 +1122,13 @@ static int pick_bn(int M, int N) {
   if (bn == 256 && tm * ceil_div(N, 256) < sms / 2) bn = 128;
   if (bn == 128 && tm * ceil_div(N, 128) < (sms * 2) / 5) bn = 64;
   return bn;
+}
+
+// FPROP / DGRAD split-K factor (1 = none) for `tiles` output tiles of width bn with k_iters K steps.
+// Tuned on B200 (tools/sweep_conv.py).
+static int pick_splits(int tiles, int k_iters, int bn) {
+  (void)tiles; (void)k_iters; (void)bn;
+  return 1;
 }
 
 }  // namespace tc
@@ -1021,6 +1157,9 @@ struct mtl_conv_args {
   // channel-slice support (concatenated branches): pixel pitches in elements, 0 = dense
   long long dy_ld, out_ld, res_ld, mask_ld;
   float bias_scale;         // 0 = 1.0
+  int force_stages;         // 0 = auto operand pipeline depth
+  void* ws;                 // fprop/dgrad split-K workspace (all zero between launches) or null
+  long long ws_bytes;
 };
 
 extern "C" int mtl_conv_tc(const mtl_conv_args* a, cudaStream_t stream) {
@@ -1114,25 +1253,95 @@ extern "C" int mtl_conv_tc(const mtl_conv_args* a, cudaStream_t stream) {
   p.div_ow = make_fast_div(p.oW);
   p.tiles_m = ceil_div(p.M, BM);
   p.tiles_n = (a->mode == WGRAD) ? p.taps * ceil_div(a->C, bn) : ceil_div(p.N, bn);
-  // epilogue through shared memory + TMA whenever the output (and residual) are plain bf16 matrices
-  CUtensorMap tmO, tmR;
-  memset(&tmO, 0, sizeof(tmO)); memset(&tmR, 0, sizeof(tmR));
+  // epilogue through shared memory + TMA whenever the output (and residual / mask) are plain bf16 matrices
+  Maps t;
+  memset(&t, 0, sizeof(t));
+  t.a = tmA; t.b = tmB;
   static const bool no_epi_tma = getenv("MTL_NO_TMA_EPILOGUE") != nullptr;
   p.epi_tma = 0;
+  int nmaps = 0;
   if (a->mode != WGRAD && !no_epi_tma && !a->out_fp32 && (p.ldo & 7) == 0 &&
       (reinterpret_cast<uintptr_t>(a->out) & 15) == 0 &&
-      (!a->res || (!a->res_fp32 && (p.ldr & 7) == 0 && (reinterpret_cast<uintptr_t>(a->res) & 15) == 0))) {
-    if ((rc = make_map(&tmO, a->out, p.M, p.N, p.ldo, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
-    if (a->res && (rc = make_map(&tmR, a->res, p.M, p.N, p.ldr, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
-    if (!a->res) tmR = tmO;
+      (!a->res || (!a->res_fp32 && (p.ldr & 7) == 0 && (reinterpret_cast<uintptr_t>(a->res) & 15) == 0)) &&
+      (!a->mask || ((p.ldm & 7) == 0 && (reinterpret_cast<uintptr_t>(a->mask) & 15) == 0))) {
+    if ((rc = make_map(&t.o, a->out, p.M, p.N, p.ldo, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+    if (a->res && (rc = make_map(&t.r, a->res, p.M, p.N, p.ldr, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+    if (a->mask && (rc = make_map(&t.m, a->mask, p.M, p.N, p.ldm, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+    if (!a->res) t.r = t.o;
+    if (!a->mask) t.m = t.o;
     p.epi_tma = 1;
+    nmaps = (a->res ? 1 : 0) + (a->mask ? 1 : 0);
   } else {
-    tmO = tmB; tmR = tmB;
+    t.o = tmB; t.r = tmB; t.m = tmB;
   }
-  if (a->mode == FPROP) return gather ? dispatch_bn<FPROP, true>(bn, tmA, tmB, tmO, tmR, p, stream)
-                                      : dispatch_bn<FPROP, false>(bn, tmA, tmB, tmO, tmR, p, stream);
-  if (a->mode == DGRAD) return gather ? dispatch_bn<DGRAD, true>(bn, tmA, tmB, tmO, tmR, p, stream)
-                                      : dispatch_bn<DGRAD, false>(bn, tmA, tmB, tmO, tmR, p, stream);
-  return gather ? dispatch_bn<WGRAD, true>(bn, tmA, tmB, tmO, tmR, p, stream)
-                : dispatch_bn<WGRAD, false>(bn, tmA, tmB, tmO, tmR, p, stream);
+  // Shared-memory carve.  Layers with a residual / mask stream give up one or two operand stages for a
+  // deep ring of residual tiles in the epilogue (their K loops are short, the 2nd-stage residual
+  // stream is not L2 resident).
+  const int stage_bytes = A_STAGE_BYTES + bn * 128;
+  const int def_stages = bn == 256 ? 4 : (bn == 128 ? 6 : 8);
+  p.stages = def_stages;
+  if (nmaps) p.stages = bn == 256 ? 3 : (bn == 128 ? 5 : 6);
+  if (a->force_stages) p.stages = a->force_stages;
+  p.res_slots = 0;
+  p.epi_warp_bytes = 4096;
+  if (p.epi_tma) {
+    const int epi_warps = gather ? 4 : 8;
+    int blocks = (SMEM_LIMIT - 1024 - BAR_BYTES - p.stages * stage_bytes) / (epi_warps * 2048);   // 2 KB tiles per warp
+    if (blocks < 2 + nmaps) {
+      mtl_set_error("gemm_tc: %d stages leave no room for the epilogue", p.stages);
+      return MTL_ERR_ARG;
+    }
+    if (nmaps) {
+      p.res_slots = (blocks - 2) / nmaps;
+      if (p.res_slots > MAX_RES_SLOTS) p.res_slots = MAX_RES_SLOTS;
+    }
+    p.epi_warp_bytes = 2048 * (2 + p.res_slots * nmaps);
+  }
+  // FPROP / DGRAD split-K (needs the TMA epilogue and a zeroed workspace from the caller): fills the
+  // machine when M x N alone yields too few tiles or a ragged last wave.
+  if (a->mode != WGRAD) {
+    int splits = 1;
+    const int tiles = p.tiles_m * p.tiles_n;
+    if (p.epi_tma && a->ws) {
+      splits = a->force_splits > 0 ? a->force_splits : pick_splits(tiles, p.k_iters, bn);
+      if (splits > p.k_iters) splits = p.k_iters;
+      if (splits < 1) splits = 1;
+      const int ips = ceil_div(p.k_iters, splits);
+      splits = ceil_div(p.k_iters, ips);
+      const long long need = (long long)tiles * BM * bn * 4 + (long long)tiles * 4;
+      if (splits > 1 && need > a->ws_bytes) {
+        mtl_set_error("gemm_tc: split-K workspace too small (%lld < %lld bytes)", a->ws_bytes, need);
+        return MTL_ERR_ARG;
+      }
+    }
+    p.splits = splits;
+    if (splits > 1) {
+      p.ws = reinterpret_cast<float*>(a->ws);
+      p.ws_cnt = reinterpret_cast<int*>(p.ws + (long long)tiles * BM * bn);
+    }
+  }
+  if (a->mode == FPROP) return gather ? dispatch_bn<FPROP, true>(bn, t, p, stream)
+                                      : dispatch_bn<FPROP, false>(bn, t, p, stream);
+  if (a->mode == DGRAD) return gather ? dispatch_bn<DGRAD, true>(bn, t, p, stream)
+                                      : dispatch_bn<DGRAD, false>(bn, t, p, stream);
+  return gather ? dispatch_bn<WGRAD, true>(bn, t, p, stream)
+                : dispatch_bn<WGRAD, false>(bn, t, p, stream);
+}
+
+// Bytes of zeroed split-K workspace mtl_conv_tc would use for this FPROP / DGRAD problem (0: it would not
+// split).  The caller allocates it once (zero filled; the kernel leaves it zeroed) and passes it as args->ws.
+extern "C" long long mtl_conv_tc_ws_bytes(const mtl_conv_args* a) {
+  using namespace tc;
+  if (!a || a->mode == WGRAD || a->out_fp32) return 0;
+  const long long M = a->mode == FPROP ? (long long)a->N * a->P * a->Q : (long long)a->N * a->H * a->W;
+  const int N = a->mode == FPROP ? a->K : a->C;
+  const int red = a->mode == FPROP ? a->C : a->K;
+  if (M <= 0 || M >= (1ll << 31) || N <= 0) return 0;
+  const int k_iters = a->R * a->S * ceil_div(red, BK);
+  const int bn = a->force_bn ? a->force_bn : pick_bn((int)M, N);
+  const int tiles = ceil_div((int)M, BM) * ceil_div(N, bn);
+  int splits = a->force_splits > 0 ? a->force_splits : pick_splits(tiles, k_iters, bn);
+  if (splits > k_iters) splits = k_iters;
+  if (splits <= 1) return 0;
+  return (long long)tiles * BM * bn * 4 + (long long)tiles * 4;
 }

@@ -46,7 +46,34 @@ class ConvArgs(ctypes.Structure):
         ("force_bn", ctypes.c_int), ("force_splits", ctypes.c_int), ("mask_hi", ctypes.c_float),
         ("dy_ld", ctypes.c_longlong), ("out_ld", ctypes.c_longlong), ("res_ld", ctypes.c_longlong),
         ("mask_ld", ctypes.c_longlong), ("bias_scale", ctypes.c_float),
+        ("force_stages", ctypes.c_int), ("ws", ctypes.c_void_p), ("ws_bytes", ctypes.c_longlong),
     ]
+
+
+# Split-K workspaces (fprop / dgrad): one zero-filled fp32 buffer per CUDA stream -- launches on one stream
+# are ordered, and the kernel leaves the buffer zeroed.  Outgrown buffers are kept alive because CUDA graphs
+# captured earlier still point at them.
+SPLIT_K = True
+_ws_by_stream = {}
+_ws_retired = []
+
+
+def _attach_ws(a):
+    if not SPLIT_K:
+        return
+    f = lib().mtl_conv_tc_ws_bytes
+    f.restype = ctypes.c_longlong
+    need = int(f(ctypes.byref(a)))
+    if need <= 0:
+        return
+    key = torch.cuda.current_stream().cuda_stream
+    buf = _ws_by_stream.get(key)
+    if buf is None or buf.numel() * 4 < need:
+        if buf is not None:
+            _ws_retired.append(buf)
+        buf = torch.zeros((max(need, 8 << 20) + 3) // 4, device="cuda", dtype=torch.float32)
+        _ws_by_stream[key] = buf
+    a.ws, a.ws_bytes = buf.data_ptr(), buf.numel() * 4
 
 
 def out_size(h, k, stride, pad_beg, pad_end, dil=1):
@@ -77,7 +104,7 @@ def _geom(a, xshape, wshape, stride, pad, dil, P, Q):
 
 
 def conv_fprop(x, w, stride=1, pad=(0, 0), dil=1, out_hw=None, bias=None, res=None, relu=False,
-               out=None, out_dtype=torch.bfloat16, force_bn=0, bias_scale=1.0):
+               out=None, out_dtype=torch.bfloat16, force_bn=0, bias_scale=1.0, force_splits=0, force_stages=0):
     """y = relu?(conv(x, w) + bias + res).  x [N,H,W,C] bf16, w [K,R,S,C] bf16."""
     N, H, W, C = x.shape
     K, R, S, C2 = w.shape
@@ -101,13 +128,14 @@ def conv_fprop(x, w, stride=1, pad=(0, 0), dil=1, out_hw=None, bias=None, res=No
     a.relu = int(relu)
     a.alpha = 1.0
     a.bias_scale = float(bias_scale)
-    a.force_bn = force_bn
+    a.force_bn, a.force_splits, a.force_stages = force_bn, force_splits, force_stages
+    _attach_ws(a)
     _launch(a, "mtl_conv_tc(fprop)")
     return out
 
 
 def conv_dgrad(dy, w, x_shape, stride=1, pad=(0, 0), dil=1, res=None, mask=None, out=None,
-               out_dtype=torch.bfloat16, force_bn=0, mask_hi=0.0):
+               out_dtype=torch.bfloat16, force_bn=0, mask_hi=0.0, force_splits=0, force_stages=0):
     """dx = mask>0 ? (conv_transpose(dy, w) + res) : 0.  dy [N,P,Q,K], w [K,R,S,C]."""
     N, P, Q, K = dy.shape
     K2, R, S, C = w.shape
@@ -130,7 +158,8 @@ def conv_dgrad(dy, w, x_shape, stride=1, pad=(0, 0), dil=1, res=None, mask=None,
         a.mask, a.mask_ld = _dp(mask), _pitch(mask)
         a.mask_hi = float(mask_hi)
     a.alpha = 1.0
-    a.force_bn = force_bn
+    a.force_bn, a.force_splits, a.force_stages = force_bn, force_splits, force_stages
+    _attach_ws(a)
     _launch(a, "mtl_conv_tc(dgrad)")
     return out
 

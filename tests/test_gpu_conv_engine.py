@@ -75,6 +75,59 @@ def test_fprop_dgrad_wgrad(case):
     close(dw, wf.grad * rs[:, None, None, None], 3e-3)
 
 
+SPLIT_CASES = [
+    # N, H, W, C, K, R, stride, bn, splits, stages
+    (1, 38, 63, 256, 256, 3, 1, 256, 7, 0),       # block3 conv2: 19 tiles x 7 splits
+    (1, 38, 63, 256, 256, 3, 1, 128, 3, 0),
+    (1, 38, 63, 1024, 256, 1, 1, 64, 2, 0),       # block3 conv1
+    (1, 38, 63, 256, 1024, 1, 1, 256, 2, 0),      # block3 conv3 (residual), 4 K iterations
+    (256, 7, 7, 256, 512, 3, 1, 256, 3, 0),       # 196 tiles x 3 splits > 148 CTAs: several tiles per CTA
+    (256, 7, 7, 256, 1024, 1, 1, 256, 1, 0),      # no split, residual ring crossing tile boundaries
+    (256, 7, 7, 256, 1024, 1, 1, 128, 1, 4),      # explicit pipeline depth
+    (256, 7, 7, 128, 200, 1, 1, 64, 2, 0),        # N not a multiple of 32, ragged last column chunk
+    (2, 19, 23, 128, 128, 3, 2, 64, 3, 0),        # gather-warp path (stride 2) with split K
+]
+
+
+@pytest.mark.parametrize("case", SPLIT_CASES)
+def test_split_k_and_residual_ring(case):
+    """FPROP / DGRAD with forced split-K (fp32 workspace + last-arriver epilogue) and the deep residual /
+    mask TMA ring; every call runs twice to prove the workspace is left zeroed."""
+    from mtl_ssl_b200 import ops_conv as oc
+    N, H, W, C, K, R, stride, bn, splits, stages = case
+    torch.manual_seed(hash(case) % 1000)
+    pad = (R - 1) // 2
+    P = (H + 2 * pad - R) // stride + 1
+    Q = (W + 2 * pad - R) // stride + 1
+    dev = "cuda"
+    x = torch.randn(N, H, W, C, device=dev).bfloat16()
+    w = (torch.randn(K, R, R, C, device=dev) / (R * R * C) ** 0.5).bfloat16()
+    bias = torch.randn(K, device=dev)
+    res = torch.randn(N, P, Q, K, device=dev).bfloat16()
+    want = torch.relu(ref_conv(x, w, stride, (pad, pad), P, Q) + bias + res.float())
+    for _ in range(2):
+        y = oc.conv_fprop(x, w, stride, (pad, pad), 1, (P, Q), bias=bias, res=res, relu=True,
+                          force_bn=bn, force_splits=splits, force_stages=stages)
+        close(y, want, 1e-2)
+    y0 = oc.conv_fprop(x, w, stride, (pad, pad), 1, (P, Q), force_bn=bn, force_splits=splits, force_stages=stages)
+    close(y0, ref_conv(x, w, stride, (pad, pad), P, Q), 1e-2)
+    xf = x.float().requires_grad_(True)
+    yr = ref_conv(xf, w.float(), stride, (pad, pad), P, Q)
+    dy = torch.randn(N, P, Q, K, device=dev).bfloat16()
+    yr.backward(dy.float())
+    mask = torch.randn(N, H, W, C, device=dev).bfloat16()
+    res2 = torch.randn(N, H, W, C, device=dev).bfloat16()
+    want_dx = torch.where(mask.float() > 0, xf.grad + res2.float(), torch.zeros_like(xf.grad))
+    for _ in range(2):
+        dx = oc.conv_dgrad(dy, w, (N, H, W, C), stride, (pad, pad), 1, res=res2, mask=mask,
+                           force_bn=bn, force_splits=splits, force_stages=stages)
+        close(dx, want_dx, 1e-2)
+    dx1 = oc.conv_dgrad(dy, w, (N, H, W, C), stride, (pad, pad), 1, mask=mask, force_bn=bn, force_splits=splits)
+    close(dx1, torch.where(mask.float() > 0, xf.grad, torch.zeros_like(xf.grad)), 1e-2)
+    for buf in oc._ws_by_stream.values():
+        assert not buf.any(), "split-K workspace not left zeroed"
+
+
 @pytest.mark.parametrize("R,S", [(1, 1), (3, 3), (1, 7)])
 def test_channel_slices(R, S):
     """Branch outputs written straight into a concat buffer; gradients read from / masked by slices of it."""
