@@ -142,6 +142,12 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t sr
                ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1)
                : "memory");
 }
+// fp32 tile += shared-memory tile, element-wise in L2 (the tensor map carries the element type)
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void bulk_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
@@ -270,7 +276,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (threadIdx.x == 32) {      // descriptors are kernel parameters: fetch them while the previous kernel drains
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
-    if (MODE != WGRAD && p.epi_tma) {
+    if (p.epi_tma) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmO)) : "memory");
       if (p.res) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmR)) : "memory");
       if (p.mask) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmM)) : "memory");
@@ -515,6 +521,34 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tmem_ld32(taddr + egrp * 32, v);
       if (MODE == WGRAD) {
         const float sc = p.alpha * ((p.rowscale && row_ok) ? __ldg(p.rowscale + m) : 1.0f);
+        if (p.epi_tma) {
+          // 32 x 32 fp32 chunks are staged in swizzled shared memory and added to dw by TMA reduce-add:
+          // full 128-byte rows reach L2 instead of 32 scattered 16-byte atomics per warp instruction.
+          // Padding columns (channels past C) hold exact zeros and rows past K are clipped by hardware.
+          const uint32_t sw = (uint32_t)lane & 7u;
+#pragma unroll 1
+          for (int c = egrp; c < NCH; c += EPI_GROUPS) {
+            tmem_ld_wait();
+            float f[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * sc;
+            if (c + EPI_GROUPS < NCH) tmem_ld32(taddr + (c + EPI_GROUPS) * 32, v);
+            if (wg_col_in_tap + c * 32 >= p.ntot) continue;
+            if (lane == 0) bulk_wait_read<0>();       // the previous reduce has read the staging tile
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              sts128(ebase + lane * 128u + ((j ^ sw) << 4),
+                     make_uint4(__float_as_uint(f[4 * j]), __float_as_uint(f[4 * j + 1]),
+                                __float_as_uint(f[4 * j + 2]), __float_as_uint(f[4 * j + 3])));
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              tma_reduce_add_2d(&tmO, ebase, (int)(ncol0 + c * 32), m_tile * BM + quad * 32);
+              bulk_commit();
+            }
+          }
+        } else {
 #pragma unroll 1
         for (int c = egrp; c < NCH; c += EPI_GROUPS) {
           tmem_ld_wait();
@@ -529,6 +563,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               if (wg_col_in_tap + c * 32 + 4 * j < p.ntot)
                 atomicAdd(reinterpret_cast<float4*>(o) + j, make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]));
           }
+        }
         }
       } else if (p.epi_tma) {
         // Output, residual and mask tiles travel through swizzled shared memory and TMA: no per-thread
@@ -819,7 +854,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tcgen05_fence_before();
       mbar_arrive(tempty_bar(acc));
     }
-    if (MODE != WGRAD && p.epi_tma && lane == 0) bulk_wait_all();
+    if (p.epi_tma && lane == 0) bulk_wait_all();
   } else if (GATHER && warp >= 8) {
     // ============================ im2col gather warps ==================================
     // Each of the 128 threads owns one 128-byte row (FPROP/DGRAD: one output pixel of the A
@@ -994,19 +1029,20 @@ static EncodeTiledFn get_encode_fn() {
 
 // 2-D bf16 row-major matrix [rows, cols] with row pitch ld (elements); box = 64 cols x box_rows.
 static int make_map(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld,
-                    int box_rows, int box_cols = 64, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
+                    int box_rows, int box_cols = 64, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B,
+                    bool fp32 = false) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) { mtl_set_error("gemm_tc: cuTensorMapEncodeTiled unavailable"); return MTL_ERR_CUDA; }
-  if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld & 7)) {
-    mtl_set_error("gemm_tc: TMA operand must be 16B aligned with row pitch %% 8 == 0 (ld=%lld)", ld);
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld & (fp32 ? 3 : 7))) {
+    mtl_set_error("gemm_tc: TMA operand must be 16B aligned with a 16B-multiple row pitch (ld=%lld)", ld);
     return MTL_ERR_ARG;
   }
   cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * (fp32 ? 4 : 2)};
   cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1u, 1u};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+  CUresult r = fn(map, fp32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                  const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { mtl_set_error("gemm_tc: cuTensorMapEncodeTiled failed (%d)", (int)r); return MTL_ERR_CUDA; }
   return MTL_OK;
@@ -1124,11 +1160,35 @@ static int pick_bn(int M, int N) {
   return bn;
 }
 
-// FPROP / DGRAD split-K factor (1 = none) for `tiles` output tiles of width bn with k_iters K steps.
-// Tuned on B200 (tools/sweep_conv.py).
-static int pick_splits(int tiles, int k_iters, int bn) {
-  (void)tiles; (void)k_iters; (void)bn;
-  return 1;
+// FPROP / DGRAD tile width and split-K factor.  Split-K (fp32 workspace, see the epilogue) pays off only
+// when a long K loop meets too few output tiles to fill the machine: the 3x3 trunk layers at batch 1
+// (2394 pixels: 13.2 vs 14.3 us) and the RPN 3x3 conv (31 vs 47 us), measured with tools/sweep_conv.py.
+static void plan_tile(int M, int N, int k_iters, bool can_split, int force_bn, int force_splits, int* bn_out,
+                      int* splits_out) {
+  int bn = force_bn ? force_bn : pick_bn(M, N);
+  int splits = 1;
+  if (can_split) {
+    if (force_splits > 0) {
+      splits = force_splits;
+    } else if (!force_bn) {
+      const int sms = mtl_num_sms(), tm = ceil_div(M, BM);
+      if (k_iters >= 96 && N >= 256 && tm * ceil_div(N, 256) * 3 <= sms) { bn = 256; splits = 3; }
+      else if (k_iters >= 32 && N >= 128 && tm * ceil_div(N, 128) * 3 <= sms) { bn = 128; splits = 3; }
+    }
+    if (splits > k_iters) splits = k_iters;
+    if (splits < 1) splits = 1;
+    splits = ceil_div(k_iters, ceil_div(k_iters, splits));     // every split owns at least one K iteration
+  }
+  *bn_out = bn; *splits_out = splits;
+}
+
+// the output (and residual / mask) of an FPROP / DGRAD call can travel through the TMA epilogue
+static bool epi_tma_ok(const void* out, int out_fp32, long long ldo, const void* res, int res_fp32, long long ldr,
+                       const void* mask, long long ldm) {
+  static const bool no_epi_tma = getenv("MTL_NO_TMA_EPILOGUE") != nullptr;
+  return !no_epi_tma && !out_fp32 && (ldo & 7) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
+         (!res || (!res_fp32 && (ldr & 7) == 0 && (reinterpret_cast<uintptr_t>(res) & 15) == 0)) &&
+         (!mask || ((ldm & 7) == 0 && (reinterpret_cast<uintptr_t>(mask) & 15) == 0));
 }
 
 }  // namespace tc
@@ -1182,6 +1242,7 @@ extern "C" int mtl_conv_tc(const mtl_conv_args* a, cudaStream_t stream) {
   CUtensorMap tmA, tmB;
   memset(&tmA, 0, sizeof(tmA)); memset(&tmB, 0, sizeof(tmB));
   int bn, rc;
+  bool epi_ok = false;
   // stride-1 filters: the gathered operand is fetched by TMA im2col loads (no gather warps)
   static const bool no_im2col = getenv("MTL_NO_TMA_IM2COL") != nullptr;
   const bool im2col = !plain && !no_im2col && a->stride == 1 && a->R * p.dil < 120 && a->S * p.dil < 120 &&
@@ -1196,7 +1257,8 @@ extern "C" int mtl_conv_tc(const mtl_conv_args* a, cudaStream_t stream) {
     p.oH = a->P; p.oW = a->Q; p.rows = p.M; p.transposed = 0;
     p.ldo = a->out_ld ? a->out_ld : a->K; p.ldr = a->res_ld ? a->res_ld : a->K;
     p.ldm = a->mask_ld ? a->mask_ld : a->K;
-    bn = a->force_bn ? a->force_bn : pick_bn(p.M, a->K);
+    epi_ok = epi_tma_ok(a->out, a->out_fp32, p.ldo, a->res, a->res_fp32, p.ldr, a->mask, p.ldm);
+    plan_tile(p.M, p.N, p.k_iters, epi_ok && a->ws, a->force_bn, a->force_splits, &bn, &p.splits);
     if (im2col) {
       p.im_low_h = -a->pad_h; p.im_low_w = -a->pad_w;
       if ((rc = make_im2col_map(&tmA, a->x, a->N, a->H, a->W, a->C, p.im_low_h, p.im_low_w,
@@ -1212,7 +1274,8 @@ extern "C" int mtl_conv_tc(const mtl_conv_args* a, cudaStream_t stream) {
     p.oH = a->H; p.oW = a->W; p.rows = p.M; p.transposed = 1; p.ntot = a->C;
     p.ldo = a->out_ld ? a->out_ld : a->C; p.ldr = a->res_ld ? a->res_ld : a->C;
     p.ldm = a->mask_ld ? a->mask_ld : a->C;
-    bn = a->force_bn ? a->force_bn : pick_bn(p.M, a->C);
+    epi_ok = epi_tma_ok(a->out, a->out_fp32, p.ldo, a->res, a->res_fp32, p.ldr, a->mask, p.ldm);
+    plan_tile(p.M, p.N, p.k_iters, epi_ok && a->ws, a->force_bn, a->force_splits, &bn, &p.splits);
     if (im2col) {
       // dx[h] = sum_r dy[h + pad - r*dil]: a stride-1 correlation over dy with mirrored filter offsets
       p.im_low_h = a->pad_h - (a->R - 1) * p.dil; p.im_low_w = a->pad_w - (a->S - 1) * p.dil;
@@ -1260,10 +1323,7 @@ extern "C" int mtl_conv_tc(const mtl_conv_args* a, cudaStream_t stream) {
   static const bool no_epi_tma = getenv("MTL_NO_TMA_EPILOGUE") != nullptr;
   p.epi_tma = 0;
   int nmaps = 0;
-  if (a->mode != WGRAD && !no_epi_tma && !a->out_fp32 && (p.ldo & 7) == 0 &&
-      (reinterpret_cast<uintptr_t>(a->out) & 15) == 0 &&
-      (!a->res || (!a->res_fp32 && (p.ldr & 7) == 0 && (reinterpret_cast<uintptr_t>(a->res) & 15) == 0)) &&
-      (!a->mask || ((p.ldm & 7) == 0 && (reinterpret_cast<uintptr_t>(a->mask) & 15) == 0))) {
+  if (a->mode != WGRAD && epi_ok) {
     if ((rc = make_map(&t.o, a->out, p.M, p.N, p.ldo, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
     if (a->res && (rc = make_map(&t.r, a->res, p.M, p.N, p.ldr, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
     if (a->mask && (rc = make_map(&t.m, a->mask, p.M, p.N, p.ldm, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
@@ -1271,6 +1331,10 @@ extern "C" int mtl_conv_tc(const mtl_conv_args* a, cudaStream_t stream) {
     if (!a->mask) t.m = t.o;
     p.epi_tma = 1;
     nmaps = (a->res ? 1 : 0) + (a->mask ? 1 : 0);
+  } else if (a->mode == WGRAD && !no_epi_tma && (p.ldo & 3) == 0 && (reinterpret_cast<uintptr_t>(a->out) & 15) == 0) {
+    if ((rc = make_map(&t.o, a->out, p.M, p.N, p.ldo, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B, true))) return rc;
+    t.r = t.o; t.m = t.o;
+    p.epi_tma = 1;
   } else {
     t.o = tmB; t.r = tmB; t.m = tmB;
   }
@@ -1295,30 +1359,18 @@ extern "C" int mtl_conv_tc(const mtl_conv_args* a, cudaStream_t stream) {
       p.res_slots = (blocks - 2) / nmaps;
       if (p.res_slots > MAX_RES_SLOTS) p.res_slots = MAX_RES_SLOTS;
     }
-    p.epi_warp_bytes = 2048 * (2 + p.res_slots * nmaps);
+    p.epi_warp_bytes = 2048 * (2 + p.res_slots * nmaps);     // WGRAD: one 32 x 32 fp32 staging tile
   }
-  // FPROP / DGRAD split-K (needs the TMA epilogue and a zeroed workspace from the caller): fills the
-  // machine when M x N alone yields too few tiles or a ragged last wave.
-  if (a->mode != WGRAD) {
-    int splits = 1;
+  // FPROP / DGRAD split-K (plan_tile): needs the TMA epilogue and a zeroed workspace from the caller
+  if (a->mode != WGRAD && p.splits > 1) {
     const int tiles = p.tiles_m * p.tiles_n;
-    if (p.epi_tma && a->ws) {
-      splits = a->force_splits > 0 ? a->force_splits : pick_splits(tiles, p.k_iters, bn);
-      if (splits > p.k_iters) splits = p.k_iters;
-      if (splits < 1) splits = 1;
-      const int ips = ceil_div(p.k_iters, splits);
-      splits = ceil_div(p.k_iters, ips);
-      const long long need = (long long)tiles * BM * bn * 4 + (long long)tiles * 4;
-      if (splits > 1 && need > a->ws_bytes) {
-        mtl_set_error("gemm_tc: split-K workspace too small (%lld < %lld bytes)", a->ws_bytes, need);
-        return MTL_ERR_ARG;
-      }
+    const long long need = (long long)tiles * BM * bn * 4 + (long long)tiles * 4;
+    if (need > a->ws_bytes) {
+      mtl_set_error("gemm_tc: split-K workspace too small (%lld < %lld bytes)", a->ws_bytes, need);
+      return MTL_ERR_ARG;
     }
-    p.splits = splits;
-    if (splits > 1) {
-      p.ws = reinterpret_cast<float*>(a->ws);
-      p.ws_cnt = reinterpret_cast<int*>(p.ws + (long long)tiles * BM * bn);
-    }
+    p.ws = reinterpret_cast<float*>(a->ws);
+    p.ws_cnt = reinterpret_cast<int*>(p.ws + (long long)tiles * BM * bn);
   }
   if (a->mode == FPROP) return gather ? dispatch_bn<FPROP, true>(bn, t, p, stream)
                                       : dispatch_bn<FPROP, false>(bn, t, p, stream);
@@ -1338,10 +1390,11 @@ extern "C" long long mtl_conv_tc_ws_bytes(const mtl_conv_args* a) {
   const int red = a->mode == FPROP ? a->C : a->K;
   if (M <= 0 || M >= (1ll << 31) || N <= 0) return 0;
   const int k_iters = a->R * a->S * ceil_div(red, BK);
-  const int bn = a->force_bn ? a->force_bn : pick_bn((int)M, N);
-  const int tiles = ceil_div((int)M, BM) * ceil_div(N, bn);
-  int splits = a->force_splits > 0 ? a->force_splits : pick_splits(tiles, k_iters, bn);
-  if (splits > k_iters) splits = k_iters;
+  const long long ldo = a->out_ld ? a->out_ld : N, ldr = a->res_ld ? a->res_ld : N, ldm = a->mask_ld ? a->mask_ld : N;
+  if (!epi_tma_ok(a->out, a->out_fp32, ldo, a->res, a->res_fp32, ldr, a->mask, ldm)) return 0;
+  int bn, splits;
+  plan_tile((int)M, N, k_iters, true, a->force_bn, a->force_splits, &bn, &splits);
   if (splits <= 1) return 0;
+  const int tiles = ceil_div((int)M, BM) * ceil_div(N, bn);
   return (long long)tiles * BM * bn * 4 + (long long)tiles * 4;
 }

@@ -224,6 +224,26 @@ extern "C" int mtl_opt_stats(const mtl_tensor_desc* tensors, int num_tensors, co
   return MTL_OK;
 }
 
+extern "C" int mtl_opt_stats_range(const mtl_tensor_desc* tensors, int t0, int t1, const mtl_chunk_desc* chunks,
+                                   int num_chunks, const float* params, const float* grads, float grad_scale,
+                                   float* stats, cudaStream_t stream) {
+  MTL_CHECK_ARG(tensors && chunks && params && grads && stats && t0 >= 0 && t1 >= t0, "mtl_opt_stats_range: bad argument");
+  if (t1 == t0 || num_chunks == 0) return MTL_OK;
+  cudaError_t e = cudaMemsetAsync(stats + 2 * t0, 0, sizeof(float) * 2 * (t1 - t0), stream);
+  if (e != cudaSuccess) { mtl_set_error("mtl_opt_stats_range: memset: %s", cudaGetErrorString(e)); return MTL_ERR_CUDA; }
+  opt_stats_kernel<<<num_chunks, 256, 0, stream>>>(tensors, chunks, params, grads, grad_scale, stats);
+  MTL_CUDA_LAUNCH_CHECK("opt_stats_kernel");
+  return MTL_OK;
+}
+
+extern "C" int mtl_opt_reg_loss(const mtl_tensor_desc* tensors, int num_tensors, const float* stats, float* reg_loss,
+                                cudaStream_t stream) {
+  MTL_CHECK_ARG(tensors && stats && reg_loss, "mtl_opt_reg_loss: null tensor");
+  opt_reg_loss_kernel<<<1, 256, 0, stream>>>(tensors, num_tensors, stats, reg_loss);
+  MTL_CUDA_LAUNCH_CHECK("opt_reg_loss_kernel");
+  return MTL_OK;
+}
+
 extern "C" int mtl_opt_apply(const mtl_tensor_desc* tensors, const mtl_chunk_desc* chunks, int num_chunks,
                              float* params, float* grads, float* momentum, void* params_bf16,
                              const float* fold_scales, const float* stats, const float* hyper, float grad_scale,

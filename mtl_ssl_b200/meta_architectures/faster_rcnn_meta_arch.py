@@ -185,6 +185,14 @@ class FasterRCNNMetaArch(model.DetectionModel):
         dead = next((p.offset for p in st.params if "/_dead/" in p.name), st.total)
         return st.g[first:dead], st.g[:first]
 
+    def head_tensor_range(self):
+        """[t0, t1): indices (arena order) of the second-stage / aux-head tensors, i.e. the tensors whose
+        gradients are final once backward(part="heads") has run."""
+        ps = self._store.params
+        t0 = next(i for i, p in enumerate(ps) if p.name.startswith(self.second_stage_feature_extractor_scope))
+        t1 = next((i for i, p in enumerate(ps) if "/_dead/" in p.name), len(ps))
+        return t0, t1
+
     @property
     def param_store(self):
         return self._store
@@ -667,6 +675,8 @@ class FasterRCNNMetaArch(model.DetectionModel):
         L.wait("win_bwd", "close_bwd")
         if part == "heads":
             Concurrency.join()
+            return
+        if part == "heads_async":       # the caller orders its consumers after the side streams itself
             return
         self._backward_trunk(pd)
 

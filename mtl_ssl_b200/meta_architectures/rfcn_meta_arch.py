@@ -131,4 +131,6 @@ class RFCNMetaArch(FasterRCNNMetaArch):
         if part == "heads":
             Concurrency.join()
             return
+        if part == "heads_async":
+            return
         self._backward_trunk(pd)

@@ -165,6 +165,11 @@ class ParamStore(object):
             td[i].trainable = int(p.trainable)
             for s in range(0, p.numel, chunk):
                 chunks.append((i, min(chunk, p.numel - s), s))
+        self.chunk_start = [0] * (T + 1)        # first chunk of every tensor (chunks are in tensor order)
+        for j, (t, _, _) in enumerate(chunks):
+            self.chunk_start[t + 1] = j + 1
+        for t in range(1, T + 1):
+            self.chunk_start[t] = max(self.chunk_start[t], self.chunk_start[t - 1])
         cd = (ops.ChunkDesc * len(chunks))()
         for j, (t, ln, st) in enumerate(chunks):
             cd[j].tensor, cd[j].len, cd[j].start = t, ln, st
@@ -189,6 +194,27 @@ class ParamStore(object):
     def apply(self, grad_scale=1.0):
         ops.call("mtl_opt_apply", self.td, self.cd, self.num_chunks, self.w, self.g, self.m, self.wb,
                  self.fold_scales, self.stats, self.hyper, grad_scale)
+
+    # the same two passes restricted to the tensors [t0, t1): the update of a finished gradient bucket can
+    # run while the rest of the backward pass still computes (trainer.py)
+    def _chunk_range(self, t0, t1):
+        c0, c1 = self.chunk_start[t0], self.chunk_start[t1]
+        return self.cd[c0 * ctypes.sizeof(ops.ChunkDesc):], c1 - c0
+
+    def stats_range(self, t0, t1, grad_scale=1.0):
+        cd, n = self._chunk_range(t0, t1)
+        if n:
+            ops.call("mtl_opt_stats_range", self.td, t0, t1, cd, n, self.w, self.g, grad_scale, self.stats)
+
+    def apply_range(self, t0, t1, grad_scale=1.0):
+        cd, n = self._chunk_range(t0, t1)
+        if n:
+            ops.call("mtl_opt_apply", self.td, cd, n, self.w, self.g, self.m, self.wb, self.fold_scales,
+                     self.stats, self.hyper, grad_scale)
+
+    def reg_loss_from_stats(self):
+        ops.call("mtl_opt_reg_loss", self.td, self.num_tensors, self.stats, self.reg_loss)
+        return self.reg_loss
 
     def set_hyper(self, lr, momentum, clip_norm):
         self.hyper.copy_(torch.tensor([lr, momentum, clip_norm, 0.0], dtype=torch.float32))

@@ -96,6 +96,8 @@ class Trainer(object):
         self._loss_host = (torch.zeros(9).pin_memory() if torch.cuda.is_available() else torch.zeros(9))
         self._loss_dev = torch.zeros(9, device=self.device)
         self.launches_per_step = None
+        self.overlap_optimizer = True       # world_size 1: update the head bucket under the trunk backward
+        self._opt_stream = None
 
     # ------------------------------------------------------------------ one step
     def _bind(self, arrays):
@@ -124,7 +126,30 @@ class Trainer(object):
         if mtl is not None and mtl.refine:
             pd = m.predict_with_mtl_results(pd)
         m.loss(pd)
-        m.backward(pd, part="heads" if self.world_size > 1 else None)
+        if self.world_size > 1:
+            m.backward(pd, part="heads")
+            return pd
+        if not self.overlap_optimizer:
+            m.backward(pd)
+            return pd
+        # single replica: the second-stage / aux-head gradients are final here.  Their clip + momentum
+        # update (64 % of the parameters, HBM bound) runs on its own stream underneath the trunk backward,
+        # which is a chain of short latency-bound GEMMs that leaves HBM and half of the SMs idle.
+        from .nets.layers import Concurrency
+        m.backward(pd, part="heads_async")
+        cur = torch.cuda.current_stream()
+        if self._opt_stream is None:
+            self._opt_stream = torch.cuda.Stream()
+        self._opt_stream.wait_stream(cur)
+        for s in (Concurrency._streams or []):
+            self._opt_stream.wait_stream(s)          # head weight-gradient GEMMs run on the side streams
+        t0, t1 = m.head_tensor_range()
+        st = m.param_store
+        with torch.cuda.stream(self._opt_stream):
+            st.stats_range(t0, t1, 1.0)
+            st.apply_range(t0, t1, 1.0)
+        m.backward(None, part="trunk")
+        cur.wait_stream(self._opt_stream)
         return pd
 
     def _backward_trunk(self):
@@ -133,8 +158,17 @@ class Trainer(object):
     def _optimize(self):
         st = self.model.param_store
         gs = data_parallel_scale(self.world_size)
-        st.stats_and_reg_loss(gs)
-        st.apply(gs)
+        if self.world_size == 1 and self.overlap_optimizer:
+            t0, t1 = self.model.head_tensor_range()       # [t0, t1) was updated under the trunk backward
+            T = st.num_tensors
+            for a, b in ((0, t0), (t1, T)):
+                st.stats_range(a, b, gs)
+            st.reg_loss_from_stats()
+            for a, b in ((0, t0), (t1, T)):
+                st.apply_range(a, b, gs)
+        else:
+            st.stats_and_reg_loss(gs)
+            st.apply(gs)
         self._loss_dev[:8].copy_(self.model.workspace.bufs["loss/values"])
         self._loss_dev[8:9].copy_(st.reg_loss)
 

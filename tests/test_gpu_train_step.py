@@ -32,6 +32,7 @@ def _setup(name, replace, H, W, B, seed=0):
     nk = model.num_kept_anchors((B, H, W, 3))
     keys = synthetic.make_sampler_keys(seed + 2, B, nk, cfg.model.faster_rcnn.first_stage_max_proposals)
     tr = Trainer(model, None, H, W, B, gmax=8, use_cuda_graph=False)
+    tr.overlap_optimizer = False       # the parity tests read the raw gradient arena after the backward pass
     return cfg, model, sd, examples, keys, tr
 
 
@@ -89,6 +90,41 @@ def test_losses_and_gradients_match_oracle(name, B):
         if cos < 0.98 or not (0.9 < ng / max(nw, 1e-30) < 1.1):
             bad.append((p.name, cos, ng, nw))
     assert not bad, bad[:10]
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_overlapped_head_optimizer_matches_plain(graph):
+    """Updating the second-stage / aux-head bucket underneath the trunk backward (single replica) must give the
+    same weights, momenta and losses as the plain backward -> optimizer sequence (fp32 atomics reorder sums:
+    tolerance 1e-3 relative on the momenta, i.e. on the clipped gradients)."""
+    H, W = 224, 320
+    got = []
+    for overlap in (False, False, True):          # two plain runs measure the run-to-run noise of the atomics
+        cfg, model, sd, examples, keys, tr = _setup("model12.config", SMALL, H, W, 1)
+        tr.overlap_optimizer = overlap
+        tr.use_graph = graph
+        arrays = tr.host_arrays(examples, keys)
+        losses = tr.step(arrays)
+        st = model.param_store
+        assert not st.g.any()
+        got.append((st.w.clone(), st.m.clone(), st.wb.float().clone(), losses, st))
+
+    def rel(a, b):
+        return float((a - b).norm() / b.norm().clamp_min(1e-20))
+
+    (w0, m0, b0, l0, st), (w1, m1, b1, l1, _), (w2, m2, b2, l2, _) = got
+    noise = rel(m1, m0)
+    assert rel(m2, m0) <= max(4 * noise, 1e-4), (rel(m2, m0), noise)
+    t0, t1 = model.head_tensor_range()
+    for p in st.params[t0:t1]:                   # every tensor of the overlapped bucket, one by one
+        sl = slice(p.offset, p.offset + p.numel)
+        if float(m0[sl].norm()) > 1e-6:
+            assert rel(m2[sl], m0[sl]) <= max(10 * rel(m1[sl], m0[sl]), 1e-3), p.name
+    torch.testing.assert_close(w2, w0, rtol=0, atol=2e-5)       # lr 1e-3 x run-to-run noise of single gradients
+    assert rel(w2, w0) <= max(4 * rel(w1, w0), 1e-7)
+    assert rel(b2, b0) <= 1e-3
+    for k in l0:
+        assert abs(l0[k] - l2[k]) <= 1e-4 * max(1.0, abs(l0[k])), (k, l0[k], l2[k])      # split-K fp32 atomics reorder sums
 
 
 def test_full_size_step_properties():
