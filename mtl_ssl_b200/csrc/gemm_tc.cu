@@ -282,17 +282,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (p.mask) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmM)) : "memory");
     }
   }
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(full_bar(s), 1 + (GATHER ? NUM_GATHER_THREADS : 0));
-      mbar_init(empty_bar(s), 1);
+  {
+    // one barrier per thread (up to 84 of them): a serial init loop would cost ~1 us of prologue
+    constexpr int NBAR = 2 * MAX_STAGES + 4;
+    const int t = threadIdx.x - 64;          // warps 2-4 are idle here
+    if (t >= 0 && t < NBAR) {
+      uint32_t count = 1;
+      if (t < MAX_STAGES) count = 1 + (GATHER ? NUM_GATHER_THREADS : 0);          // full[]
+      else if (t >= 2 * MAX_STAGES + 2) count = EPI_THREADS;                       // tempty[]
+      mbar_init(bar_base + 8u * t, count);
+    } else if (t >= NBAR && t < NBAR + 4 * EPI_GROUPS * MAX_RES_SLOTS) {
+      const int r = t - NBAR;
+      mbar_init(res_bar(r / MAX_RES_SLOTS, r % MAX_RES_SLOTS), 1);
     }
-    for (int a = 0; a < 2; ++a) {
-      mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), EPI_THREADS);
-    }
-    for (int q = 0; q < 4 * EPI_GROUPS; ++q)
-      for (int b = 0; b < MAX_RES_SLOTS; ++b) mbar_init(res_bar(q, b), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -1303,7 +1305,17 @@ extern "C" int mtl_conv_tc(const mtl_conv_args* a, cudaStream_t stream) {
     if (gather) tmB = tmA;
     // split K (pixels) so that about one wave of CTAs is launched
     const int tiles = ceil_div(p.M, BM) * p.taps * ceil_div(a->C, bn);
-    int splits = a->force_splits ? a->force_splits : (mtl_num_sms() + tiles - 1) / tiles;
+    int splits = a->force_splits;
+    if (splits <= 0) {
+      // minimise waves x (K iterations per CTA + drain cost): never spill a few tiles into a second wave
+      const int sms = mtl_num_sms(), drain = bn / 48 + 1;
+      long long best = -1;
+      splits = 1;
+      for (int sp = 1; sp <= p.k_iters && sp <= 64 && (sp == 1 || tiles * sp <= 2 * sms); ++sp) {
+        const long long cost = (long long)ceil_div(tiles * sp, sms) * (ceil_div(p.k_iters, sp) + drain);
+        if (best < 0 || cost < best) { best = cost; splits = sp; }
+      }
+    }
     if (splits > p.k_iters) splits = p.k_iters;
     if (splits < 1) splits = 1;
     const int ips = ceil_div(p.k_iters, splits);

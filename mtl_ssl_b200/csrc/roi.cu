@@ -314,6 +314,53 @@ im2col_f32_kernel(const float* __restrict__ img, int B, int H, int W, int C, int
   }
 }
 
+// The same rows for up to 256 columns (every stem in the zoo: 7x7x3 -> 160, 3x3x3 -> 32): the
+// (r, s, c) decomposition of a column is tabulated once per CTA, one warp walks output pixels and its
+// lanes own the 8-column vectors, so the inner loop has no integer division at all.
+__global__ void __launch_bounds__(256)
+im2col_f32_tab_kernel(const float* __restrict__ img, int B, int H, int W, int C, int R, int S, int stride, int pad_h,
+                      int pad_w, int P, int Q, float m0, float m1, float m2, float m3, float scale,
+                      bf16* __restrict__ out, int ld) {
+  __shared__ int t_off[256];
+  __shared__ short t_rs[256];
+  __shared__ float t_mean[256];
+  const int kk = R * S * C;
+  const float mean[4] = {m0, m1, m2, m3};
+  for (int e = threadIdx.x; e < ld; e += blockDim.x) {
+    if (e < kk) {
+      const int c = e % C, rs = e / C;
+      const int s_ = rs % S, r = rs / S;
+      t_off[e] = (r * W + s_) * C + c;
+      t_rs[e] = (short)((r << 8) | s_);
+      t_mean[e] = mean[c & 3];
+    } else {
+      t_off[e] = 0; t_rs[e] = -1; t_mean[e] = 0.0f;
+    }
+  }
+  __syncthreads();
+  const int nvec = ld >> 3, lane = threadIdx.x & 31;
+  const int npix = B * P * Q, nwarps = gridDim.x * (blockDim.x >> 5);
+  for (int pix = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); pix < npix; pix += nwarps) {
+    const int q = pix % Q, bp = pix / Q;
+    const int p = bp % P, b = bp / P;
+    const int h0 = p * stride - pad_h, w0 = q * stride - pad_w;
+    const long long idx0 = (((long long)b * H + h0) * W + w0) * C;
+    for (int v = lane; v < nvec; v += 32) {
+      float f[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int e = v * 8 + j;
+        const int rs = t_rs[e];
+        const int h = h0 + (rs >> 8), w = w0 + (rs & 255);
+        float val = 0.0f;
+        if (rs >= 0 && h >= 0 && h < H && w >= 0 && w < W) val = (__ldg(img + idx0 + t_off[e]) - t_mean[e]) * scale;
+        f[j] = val;
+      }
+      reinterpret_cast<uint4*>(out + (long long)pix * ld)[v] = pack8(f);
+    }
+  }
+}
+
 // (x - mean[c]) * scale -> bf16 NHWC, for inspection / the oracle's view of the preprocessed image
 __global__ void preprocess_kernel(const float* __restrict__ img, long long total, int C, float m0, float m1,
                                   float m2, float m3, float scale, float* __restrict__ out) {
@@ -519,6 +566,13 @@ extern "C" int mtl_im2col_f32(const float* img, int B, int H, int W, int C, int 
   float m[4] = {0, 0, 0, 0};
   if (mean) for (int c = 0; c < C; ++c) m[c] = mean[c];
   const long long total = (long long)B * P * Q * (ld / 8);
+  if (ld <= 256 && R < 128 && S < 256 && (long long)B * P * Q < (1ll << 31)) {
+    const int grid_t = (int)min(ceil_div_ll((long long)B * P * Q, 8), (long long)mtl_num_sms() * 16);
+    im2col_f32_tab_kernel<<<grid_t, 256, 0, stream>>>(img, B, H, W, C, R, S, stride, pad_h, pad_w, P, Q, m[0], m[1],
+                                                      m[2], m[3], scale, reinterpret_cast<bf16*>(out), ld);
+    MTL_CUDA_LAUNCH_CHECK("im2col_f32_tab_kernel");
+    return MTL_OK;
+  }
   const int grid = (int)min(ceil_div_ll(total, 256), (long long)mtl_num_sms() * 32);
   im2col_f32_kernel<<<grid, 256, 0, stream>>>(img, B, H, W, C, R, S, stride, pad_h, pad_w, P, Q, m[0], m[1], m[2],
                                               m[3], scale, reinterpret_cast<bf16*>(out), ld);
