@@ -61,6 +61,7 @@ struct Params {
   int stages;                // operand pipeline depth (shared memory is carved at launch time)
   int res_slots;             // per epilogue warp: 32x32 residual(+mask) tiles kept in flight by TMA
   int epi_warp_bytes;        // per epilogue warp: 2 output staging tiles + res_slots * slot bytes
+  int cluster;               // 2: CTA pairs with multicast weight tiles (host-side dispatch only)
   float* ws;                 // FPROP/DGRAD split-K: fp32 partial-sum tiles [tiles_m*tiles_n][BN/4][BM][4], all zero between launches
   int* ws_cnt;               // FPROP/DGRAD split-K: arrival counter per output tile, zero between launches
 };
@@ -137,6 +138,18 @@ __device__ __forceinline__ void tma_load_im2col(uint32_t dst, const CUtensorMap*
         "h"((unsigned short)offw), "h"((unsigned short)offh)
       : "memory");
 }
+// The same load delivered to the same shared-memory offset (and mbarrier) of every CTA in `mask` of the cluster.
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                               uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1)
@@ -182,6 +195,13 @@ __device__ __forceinline__ void tcgen05_fence_after() {
 __device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
                : "memory");
+}
+// commit that arrives on the barrier at the same offset in both CTAs of a pair
+__device__ __forceinline__ void tcgen05_commit_mc2(uint32_t bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(bar), "h"((uint16_t)3)
+      : "memory");
 }
 __device__ __forceinline__ void tcgen05_mma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
                                                  uint32_t idesc, uint32_t accumulate) {
@@ -238,7 +258,11 @@ static inline int smem_bytes(int stage_bytes, int stages, int epi_warps, int epi
   return 1024 + stages * stage_bytes + epi_warps * epi_warp_bytes + BAR_BYTES;
 }
 
-template <int MODE, int BN, bool GATHER>
+// CL = 2 (FPROP / DGRAD, TMA operands, no split-K): CTA pairs (thread-block clusters of two) work on
+// vertically adjacent output tiles of the same column block; each CTA fetches half of the shared weight
+// tile and multicasts it into both, which cuts the L2 -> SM operand traffic of a 128 x 256 tile by a third
+// (the big second-stage GEMMs sit on the L2 fabric limit, ~6.1 kB/clk chip-wide, not on the tensor pipe).
+template <int MODE, int BN, bool GATHER, int CL>
 __global__ void __launch_bounds__(384, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR,
@@ -289,6 +313,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (t >= 0 && t < NBAR) {
       uint32_t count = 1;
       if (t < MAX_STAGES) count = 1 + (GATHER ? NUM_GATHER_THREADS : 0);          // full[]
+      else if (t < 2 * MAX_STAGES) count = CL;                                     // empty[]: every CTA of the pair
       else if (t >= 2 * MAX_STAGES + 2) count = EPI_THREADS;                       // tempty[]
       mbar_init(bar_base + 8u * t, count);
     } else if (t >= NBAR && t < NBAR + 4 * EPI_GROUPS * MAX_RES_SLOTS) {
@@ -304,7 +329,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tcgen05_fence_before();
-  __syncthreads();
+  if (CL == 2) cluster_sync_all();      // the peer's barriers must exist before anything is multicast into it
+  else __syncthreads();
   tcgen05_fence_after();
   // Programmatic dependent launch: everything above (barrier init, TMEM allocation) overlaps the
   // tail of the previous kernel in the stream; global memory is only touched after this wait.
@@ -319,10 +345,30 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int ips = (p.k_iters + p.splits - 1) / p.splits;   // K iterations per split
   // tile id -> (split, output tile): WGRAD walks all output tiles of one split first; FPROP/DGRAD keep
   // the splits of one output tile adjacent so that their partial sums meet in L2 at about the same time
+  uint32_t cta_rank = 0;
+  if (CL == 2) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
+  // CL == 2: clusters walk (pair of m-tiles, n-tile); a pair's second m-tile may lie past the matrix (odd
+  // tile count): that CTA still takes part in the multicast protocol but loads a clamped tile and stores nothing
+  const int t_begin = CL == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int t_step = CL == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int t_end = CL == 2 ? ((p.tiles_m + 1) >> 1) * p.tiles_n : total_tiles;
   auto decode_tile = [&](int tile, int& split, int& rem) {
     if (MODE == WGRAD) { split = tile / tiles_mn; rem = tile - split * tiles_mn; }
     else if (p.splits == 1) { split = 0; rem = tile; }
     else { rem = tile / p.splits; split = tile - rem * p.splits; }
+  };
+  auto tile_coords = [&](int tile, int& split, int& m_tile, int& n_tile) {
+    if (CL == 2) {
+      split = 0;
+      const int mp = tile / p.tiles_n;
+      n_tile = tile - mp * p.tiles_n;
+      m_tile = 2 * mp + (int)cta_rank;
+    } else {
+      int rem;
+      decode_tile(tile, split, rem);
+      m_tile = rem / p.tiles_n;
+      n_tile = rem - m_tile * p.tiles_n;
+    }
   };
 
   if (warp == 0) {
@@ -332,10 +378,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t ph = 0;
       constexpr uint32_t tx_bytes =
           (GATHER_A ? 0u : (uint32_t)A_STAGE_BYTES) + (GATHER_B ? 0u : (uint32_t)C::B_STAGE_BYTES);
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        int split, rem;
-        decode_tile(tile, split, rem);
-        const int m_tile = rem / p.tiles_n, n_tile = rem - m_tile * p.tiles_n;
+      for (int tile = t_begin; tile < t_end; tile += t_step) {
+        int split, m_tile, n_tile;
+        tile_coords(tile, split, m_tile, n_tile);
+        if (CL == 2 && m_tile >= p.tiles_m) m_tile = p.tiles_m - 1;     // padding tile of an odd pair
         const int m0 = m_tile * BM;
         const int kb = split * ips, ke = min(kb + ips, p.k_iters);
         int tn0 = 0, tp0 = 0, tq0 = 0;      // (n, p, q) of the tile's first row (im2col TMA base pixel)
@@ -366,7 +412,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               if (p.im2col) tma_load_im2col(sa, &tmA, fb, acol, bw, bh, tn0, offw, offh);
               else tma_load_2d(sa, &tmA, fb, acol, m0);
             }
-            if (MODE == FPROP) {
+            if (CL == 2) {
+              // this CTA's half of the weight tile, delivered to both CTAs of the pair
+              if (MODE == FPROP) {
+                tma_load_2d_mc(sa + A_STAGE_BYTES + cta_rank * (BN / 2) * 128, &tmB, fb, bbase + acol,
+                               n0 + (int)cta_rank * (BN / 2), (uint16_t)3);
+              } else {
+#pragma unroll
+                for (int jj = 0; jj < BN / 128; ++jj) {
+                  const int j = (int)cta_rank * (BN / 128) + jj;
+                  tma_load_2d_mc(sa + A_STAGE_BYTES + j * 8192, &tmB, fb, bbase + j * 64, acol, (uint16_t)3);
+                }
+              }
+            } else if (MODE == FPROP) {
               tma_load_2d(sa + A_STAGE_BYTES, &tmB, fb, bbase + acol, n0);
             } else {
 #pragma unroll
@@ -425,9 +483,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t tcount = 0;
       int s = 0;
       uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
-        int split, rem;
-        decode_tile(tile, split, rem);
+      for (int tile = t_begin; tile < t_end; tile += t_step, ++tcount) {
+        int split, m_tile_, n_tile_;
+        tile_coords(tile, split, m_tile_, n_tile_);
         const int kb = split * ips, ke = min(kb + ips, p.k_iters);
         const uint32_t acc = tcount & 1u, aph = (tcount >> 1) & 1u;
         mbar_wait(tempty_bar(acc), aph ^ 1u);
@@ -444,7 +502,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                      : umma_desc(stage_b(s) + ks * 32, 16, 1024);
             tcgen05_mma_bf16(tmem_d, da, db, idesc, (k > kb || ks > 0) ? 1u : 0u);
           }
-          tcgen05_commit(empty_bar(s));     // frees the smem stage when these MMAs retire
+          // frees the smem stage when these MMAs retire (in both CTAs of a pair: the peer multicasts into it)
+          if (CL == 2) tcgen05_commit_mc2(empty_bar(s));
+          else tcgen05_commit(empty_bar(s));
           if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
         tcgen05_commit(tfull_bar(acc));     // accumulator ready for the epilogue
@@ -459,7 +519,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr int NCH = BN / 32;            // 32-column chunks per tile
     constexpr int CPW = NCH / EPI_GROUPS;   // chunks per warp per tile
     uint32_t tcount = 0;
-    uint32_t gchunk = 0;                    // running chunk counter (output staging buffer parity)
+    uint32_t gchunk = 0;                    // stored-chunk counter (output staging buffer parity)
     // Residual / mask tiles (32 rows x 32 columns bf16) are fetched by TMA into a ring of `res_slots`
     // slots per warp, `res_slots` chunks ahead of their use and across tile boundaries, so the ~1 us
     // HBM round trip of a 500 MB residual stream never sits on the drain path.  Chunks are numbered
@@ -470,22 +530,21 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const bool has_mask = p.mask != nullptr;
     const uint32_t slot_bytes = 2048u * ((has_res ? 1u : 0u) + (has_mask ? 1u : 0u));
     const uint32_t ebase = epi_base + (uint32_t)ew * (uint32_t)p.epi_warp_bytes;
-    int iq_tile = blockIdx.x, iq_c = 0, iq_slot = 0, iq_m0 = 0, iq_n0 = 0;
+    int iq_tile = t_begin, iq_c = 0, iq_slot = 0, iq_m0 = 0, iq_n0 = 0;
     int cq_slot = 0;
     uint32_t slot_ph = 0;
     auto issue_next = [&](int cur_tile) {
       if (R == 0) return;
       if (p.splits > 1 && iq_tile != cur_tile) return;   // split-K: only the finishing CTA reads them
-      if (iq_tile < total_tiles) {
+      if (iq_tile < t_end) {
         if (iq_c == 0) {
-          int sp, rm;
-          decode_tile(iq_tile, sp, rm);
-          const int mt = rm / p.tiles_n;
-          iq_m0 = mt * BM + quad * 32;
-          iq_n0 = (rm - mt * p.tiles_n) * BN;
+          int sp, mt, nt;
+          tile_coords(iq_tile, sp, mt, nt);
+          iq_m0 = mt * BM + quad * 32;       // a padding tile starts past the last row: nothing to fetch
+          iq_n0 = nt * BN;
         }
         const int n0 = iq_n0 + (egrp + iq_c * EPI_GROUPS) * 32;
-        if (n0 < p.N && lane == 0) {
+        if (n0 < p.N && iq_m0 < p.tiles_m * BM && lane == 0) {
           const uint32_t rb = res_bar(ew, iq_slot);
           const uint32_t dst = ebase + 4096u + (uint32_t)iq_slot * slot_bytes;
           mbar_arrive_expect_tx(rb, slot_bytes);
@@ -493,19 +552,29 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (has_mask) tma_load_2d(dst + (has_res ? 2048u : 0u), &tmM, rb, n0, iq_m0);
         }
       }
-      if (++iq_c == CPW) { iq_c = 0; iq_tile += gridDim.x; }
+      if (++iq_c == CPW) { iq_c = 0; iq_tile += t_step; }
       if (++iq_slot == R) iq_slot = 0;
     };
     if (p.splits == 1)
       for (int i = 0; i < R; ++i) issue_next(-1);
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
-      int split, rem;
-      decode_tile(tile, split, rem);
-      const int m_tile = rem / p.tiles_n, n_tile = rem - m_tile * p.tiles_n;
+    for (int tile = t_begin; tile < t_end; tile += t_step, ++tcount) {
+      int split, m_tile, n_tile;
+      tile_coords(tile, split, m_tile, n_tile);
+      const int rem = m_tile * p.tiles_n + n_tile;
       const int m = m_tile * BM + row;
       const uint32_t acc = tcount & 1u, aph = (tcount >> 1) & 1u;
       mbar_wait(tfull_bar(acc), aph);
       tcgen05_fence_after();
+      if (CL == 2 && m_tile >= p.tiles_m) {
+        // padding tile of an odd pair: release the accumulator, keep the residual ring cursors in step
+        tcgen05_fence_before();
+        mbar_arrive(tempty_bar(acc));
+        for (int i = 0; i < CPW; ++i) {
+          if (R && ++cq_slot == R) cq_slot = 0;
+          issue_next(tile);
+        }
+        continue;
+      }
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN;
       long long ncol0;     // first output column of this tile
       int wg_col_in_tap = 0;   // WGRAD: channel offset of this tile inside its filter tap
@@ -630,7 +699,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         };
         if (from_ws) load_acc(egrp);
 #pragma unroll 1
-        for (int c = egrp; c < NCH; c += EPI_GROUPS, ++gchunk) {
+        for (int c = egrp; c < NCH; c += EPI_GROUPS) {
+          const long long n0 = ncol0 + c * 32;
+          const int nvalid = (int)min((long long)32, (long long)p.N - n0);
+          const bool vec = (nvalid == 32);
+          // the bias vector does not depend on the accumulator: fetch it while the TMEM load is in flight
+          float4 bq[8];
+          if (p.bias && vec) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) bq[j] = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + j);
+          }
           tmem_ld_wait();
           float f[32];
 #pragma unroll
@@ -641,20 +719,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tcgen05_fence_before();
             mbar_arrive(tempty_bar(acc));       // accumulator fully drained: the MMA warp may reuse it
           }
-          const long long n0 = ncol0 + c * 32;
           const int slot = cq_slot;
           if (R && ++cq_slot == R) cq_slot = 0;
-          if (n0 >= p.N) { issue_next(tile); continue; }
-          const int nvalid = (int)min((long long)32, (long long)p.N - n0);
-          const bool vec = (nvalid == 32);
+          if (nvalid <= 0) { issue_next(tile); continue; }
           const uint32_t buf = gchunk & 1u;
           if (p.bias) {
             if (vec) {
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
-                const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + j);
-                f[4 * j] += t.x * p.bias_scale; f[4 * j + 1] += t.y * p.bias_scale;
-                f[4 * j + 2] += t.z * p.bias_scale; f[4 * j + 3] += t.w * p.bias_scale;
+                f[4 * j] += bq[j].x * p.bias_scale; f[4 * j + 1] += bq[j].y * p.bias_scale;
+                f[4 * j + 2] += bq[j].z * p.bias_scale; f[4 * j + 3] += bq[j].w * p.bias_scale;
               }
             } else {
 #pragma unroll
@@ -679,13 +753,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               }
             }
           }
-          if (p.relu) {
+          // round to bf16 first: ReLU / ReLU6 / the gradient mask commute with the rounding and cost half as
+          // many instructions on packed pairs
+          uint32_t o[16];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
-            if (p.relu == 2) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] = fminf(f[j], 6.0f);
+          for (int j = 0; j < 16; ++j) {
+            __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+            if (p.relu) {
+              h = __hmax2(h, __float2bfloat162_rn(0.0f));
+              if (p.relu == 2) h = __hmin2(h, __float2bfloat162_rn(6.0f));
             }
+            o[j] = *reinterpret_cast<const uint32_t*>(&h);
           }
           if (has_mask) {      // rows outside the tensor arrive as zeros: dead
             const uint32_t mrow = rrow + (has_res ? 2048u : 0u);
@@ -695,35 +773,32 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const uint32_t w[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
-                if (mask_dead(__uint_as_float(w[q] << 16), p.mask_hi)) f[8 * j + 2 * q] = 0.0f;
-                if (mask_dead(__uint_as_float(w[q] & 0xffff0000u), p.mask_hi)) f[8 * j + 2 * q + 1] = 0.0f;
+                uint32_t keep = 0xffffffffu;
+                if (mask_dead(__uint_as_float(w[q] << 16), p.mask_hi)) keep &= 0xffff0000u;
+                if (mask_dead(__uint_as_float(w[q] & 0xffff0000u), p.mask_hi)) keep &= 0x0000ffffu;
+                o[4 * j + q] &= keep;
               }
             }
           }
           if (R) {
-            __syncwarp();        // every lane has read the slot: refill it with the chunk `R` ahead
+            __syncwarp();        // every lane has read the slot: refill it with the chunk `R` ahead right away
             issue_next(tile);
           }
-          // the TMA store issued two chunks ago must have finished reading this staging buffer
-          if (lane == 0) bulk_wait_read<1>();
-          __syncwarp();
+          // staging buffer `buf` is free: lane 0 waited (end of the previous chunk) for the store issued from
+          // it two chunks ago, and the __syncwarp that followed ordered that wait before these writes
           const uint32_t orow = ebase + buf * 2048u + lane * 64u;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint32_t w[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const __nv_bfloat162 h = __floats2bfloat162_rn(f[8 * j + 2 * q], f[8 * j + 2 * q + 1]);
-              w[q] = *reinterpret_cast<const uint32_t*>(&h);
-            }
-            sts128(orow + ((j ^ swz) << 4), make_uint4(w[0], w[1], w[2], w[3]));
-          }
+          for (int j = 0; j < 4; ++j)
+            sts128(orow + ((j ^ swz) << 4), make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]));
           fence_proxy_async();
-          __syncwarp();
+          __syncwarp();        // staging tile complete
           if (lane == 0) {
             tma_store_2d(&tmO, ebase + buf * 2048u, (int)n0, m0w);
             bulk_commit();
           }
+          if (lane == 0) bulk_wait_read<1>();     // the other staging buffer has been read by its store
+          __syncwarp();
+          ++gchunk;            // counts stored chunks only: consecutive stores always alternate buffers
         }
         continue;     // tempty already signalled
       } else {
@@ -856,7 +931,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tcgen05_fence_before();
       mbar_arrive(tempty_bar(acc));
     }
-    if (p.epi_tma && lane == 0) bulk_wait_all();
+    // the staging tiles must have been read before the CTA's shared memory is released; the global writes
+    // themselves complete before the grid does (and before a dependent grid's griddepcontrol.wait returns)
+    if (p.epi_tma && lane == 0) bulk_wait_read<0>();
   } else if (GATHER && warp >= 8) {
     // ============================ im2col gather warps ==================================
     // Each of the 128 threads owns one 128-byte row (FPROP/DGRAD: one output pixel of the A
@@ -870,10 +947,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int ohw = p.oH * p.oW;
     // The gather is on the critical path of every 3x3 / strided layer: all per-iteration index math
     // is strength-reduced (no divisions inside the K loop; row decode uses multiply-shift division).
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      int split, rem;
-      decode_tile(tile, split, rem);
-      const int m_tile = rem / p.tiles_n, n_tile = rem - m_tile * p.tiles_n;
+    for (int tile = t_begin; tile < t_end; tile += t_step) {
+      int split, m_tile, n_tile;
+      tile_coords(tile, split, m_tile, n_tile);
       const int kb = split * ips, ke = min(kb + ips, p.k_iters);
       if (GATHER_A) {
         const int m = m_tile * BM + g;
@@ -1001,7 +1077,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 
   tcgen05_fence_before();
-  __syncthreads();
+  if (CL == 2) cluster_sync_all();      // no CTA leaves while its peer may still signal or write into it
+  else __syncthreads();
   if (warp == 2) {
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
@@ -1097,11 +1174,11 @@ static int make_im2col_map(CUtensorMap* map, const void* base, int N, int H, int
   return MTL_OK;
 }
 
-template <int MODE, int BN, bool GATHER>
+template <int MODE, int BN, bool GATHER, int CL>
 static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const CUtensorMap& tmR,
                   const CUtensorMap& tmM, const Params& p, cudaStream_t stream) {
   using C = Cfg<BN>;
-  auto kern = tc_gemm_kernel<MODE, BN, GATHER>;
+  auto kern = tc_gemm_kernel<MODE, BN, GATHER, CL>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
@@ -1114,8 +1191,35 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensor
                   p.epi_warp_bytes, smem);
     return MTL_ERR_ARG;
   }
-  const int total = p.tiles_m * p.tiles_n * p.splits;
-  const int grid = total < mtl_num_sms() ? total : mtl_num_sms();
+  int grid;
+  if (CL == 2) {
+    // persistent clusters: never more than can be co-resident (a GPC with an odd SM count strands one SM)
+    static int max_clusters = 0;
+    if (max_clusters == 0) {
+      cudaLaunchConfig_t q;
+      memset(&q, 0, sizeof(q));
+      q.gridDim = dim3(mtl_num_sms() / 2 * 2);
+      q.blockDim = dim3(384);
+      q.dynamicSmemBytes = SMEM_LIMIT;
+      cudaLaunchAttribute qa[1];
+      qa[0].id = cudaLaunchAttributeClusterDimension;
+      qa[0].val.clusterDim.x = 2; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+      q.attrs = qa;
+      q.numAttrs = 1;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, kern, &q) != cudaSuccess || n < 1) {
+        (void)cudaGetLastError();
+        n = mtl_num_sms() / 2 - 2;
+      }
+      max_clusters = n < mtl_num_sms() / 2 ? n : mtl_num_sms() / 2;
+    }
+    const int pairs = ((p.tiles_m + 1) / 2) * p.tiles_n;
+    const int clusters = pairs < max_clusters ? pairs : max_clusters;
+    grid = 2 * clusters;
+  } else {
+    const int total = p.tiles_m * p.tiles_n * p.splits;
+    grid = total < mtl_num_sms() ? total : mtl_num_sms();
+  }
   static const bool no_pdl = getenv("MTL_NO_PDL") != nullptr;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
@@ -1123,11 +1227,20 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensor
   cfg.blockDim = dim3(384);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (!no_pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (CL == 2) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = no_pdl ? 0 : 1;
+  cfg.numAttrs = na;
   cudaError_t le = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmO, tmR, tmM, p);
   if (le != cudaSuccess) {
     mtl_set_error("tc_gemm_kernel: launch failed: %s", cudaGetErrorString(le));
@@ -1142,10 +1255,19 @@ struct Maps { CUtensorMap a, b, o, r, m; };
 
 template <int MODE, bool GATHER>
 static int dispatch_bn(int bn, const Maps& t, const Params& p, cudaStream_t st) {
+  if (p.cluster == 2) {       // FPROP / DGRAD, TMA operands, 128- or 256-wide tiles (chosen by the caller)
+    if (MODE != WGRAD && !GATHER) {
+      constexpr int M2 = (MODE == WGRAD || GATHER) ? FPROP : MODE;     // keeps the dead branch instantiable
+      if (bn == 256) return launch<M2, 256, false, 2>(t.a, t.b, t.o, t.r, t.m, p, st);
+      if (bn == 128) return launch<M2, 128, false, 2>(t.a, t.b, t.o, t.r, t.m, p, st);
+    }
+    mtl_set_error("gemm_tc: CTA pairs need FPROP/DGRAD with TMA operands and BN >= 128");
+    return MTL_ERR_UNSUPPORTED;
+  }
   switch (bn) {
-    case 256: return launch<MODE, 256, GATHER>(t.a, t.b, t.o, t.r, t.m, p, st);
-    case 128: return launch<MODE, 128, GATHER>(t.a, t.b, t.o, t.r, t.m, p, st);
-    case 64: return launch<MODE, 64, GATHER>(t.a, t.b, t.o, t.r, t.m, p, st);
+    case 256: return launch<MODE, 256, GATHER, 1>(t.a, t.b, t.o, t.r, t.m, p, st);
+    case 128: return launch<MODE, 128, GATHER, 1>(t.a, t.b, t.o, t.r, t.m, p, st);
+    case 64: return launch<MODE, 64, GATHER, 1>(t.a, t.b, t.o, t.r, t.m, p, st);
   }
   mtl_set_error("gemm_tc: unsupported BN %d", bn);
   return MTL_ERR_UNSUPPORTED;
@@ -1153,9 +1275,12 @@ static int dispatch_bn(int bn, const Maps& t, const Params& p, cudaStream_t st) 
 
 // Tile width: the widest tile that still yields enough CTAs (measured on B200: for M = 2394 rows
 // 64-wide tiles win by 10-20 %, for >= 100 tiles of width 128 narrower tiles only add operand re-reads).
-static int pick_bn(int M, int N) {
+static int pick_bn(int M, int N, int k_iters) {
   const int sms = mtl_num_sms();
   const int tm = ceil_div(M, BM);
+  // short K loops over few rows (block3 conv3 and its mirror dgrad at batch 1: 19 row tiles, 4 K steps) are
+  // pure drain: two waves of narrow tiles beat half a wave of wide ones (7.8 vs 9.2 us)
+  if (tm <= 32 && k_iters <= 8 && N >= 512 && tm * ceil_div(N, 256) < sms) return 64;
   int bn = N > 128 ? 256 : (N > 64 ? 128 : 64);
   if (bn == 256 && tm * ceil_div(N, 256) < sms / 2) bn = 128;
   if (bn == 128 && tm * ceil_div(N, 128) < (sms * 2) / 5) bn = 64;
@@ -1167,7 +1292,7 @@ static int pick_bn(int M, int N) {
 // (2394 pixels: 13.2 vs 14.3 us) and the RPN 3x3 conv (31 vs 47 us), measured with tools/sweep_conv.py.
 static void plan_tile(int M, int N, int k_iters, bool can_split, int force_bn, int force_splits, int* bn_out,
                       int* splits_out) {
-  int bn = force_bn ? force_bn : pick_bn(M, N);
+  int bn = force_bn ? force_bn : pick_bn(M, N, k_iters);
   int splits = 1;
   if (can_split) {
     if (force_splits > 0) {
@@ -1182,6 +1307,19 @@ static void plan_tile(int M, int N, int k_iters, bool can_split, int force_bn, i
     splits = ceil_div(k_iters, ceil_div(k_iters, splits));     // every split owns at least one K iteration
   }
   *bn_out = bn; *splits_out = splits;
+}
+
+// CTA pairs with multicast weight tiles: worth it once there is at least a full wave of wide tiles
+static int pick_cluster(int M, int N, int bn, int splits, bool gather, int force) {
+  static const bool off = getenv("MTL_NO_CLUSTER") != nullptr;
+  if (gather || splits > 1 || bn < 128 || off || force == 1) return 1;
+  if (force == 2) return 2;
+  // Measured on B200 (tools/sweep_conv.py pairs): within +-2 % of the unpaired schedule on every second-stage
+  // GEMM -- L2 already merges the near-simultaneous requests of neighbouring CTAs for one weight tile -- so
+  // pairs stay opt-in (MTL_CLUSTER=1 / force_cluster=2).
+  static const bool on = getenv("MTL_CLUSTER") != nullptr;
+  (void)M; (void)N;
+  return on && ceil_div(M, BM) * ceil_div(N, bn) >= mtl_num_sms() ? 2 : 1;
 }
 
 // the output (and residual / mask) of an FPROP / DGRAD call can travel through the TMA epilogue
@@ -1222,6 +1360,7 @@ struct mtl_conv_args {
   int force_stages;         // 0 = auto operand pipeline depth
   void* ws;                 // fprop/dgrad split-K workspace (all zero between launches) or null
   long long ws_bytes;
+  int force_cluster;        // 0 auto, 1 never pair CTAs, 2 pair CTAs (fprop/dgrad with TMA operands)
 };
 
 extern "C" int mtl_conv_tc(const mtl_conv_args* a, cudaStream_t stream) {
@@ -1240,7 +1379,7 @@ extern "C" int mtl_conv_tc(const mtl_conv_args* a, cudaStream_t stream) {
   p.out = a->out; p.out_fp32 = a->out_fp32; p.bias = a->bias; p.rowscale = a->rowscale;
   p.res = a->res; p.res_fp32 = a->res_fp32; p.mask = reinterpret_cast<const bf16*>(a->mask);
   p.relu = a->relu; p.mask_hi = a->mask_hi; p.alpha = a->alpha;
-  p.bias_scale = a->bias_scale != 0.0f ? a->bias_scale : 1.0f; p.splits = 1; p.taps = a->R * a->S;
+  p.bias_scale = a->bias_scale != 0.0f ? a->bias_scale : 1.0f; p.splits = 1; p.cluster = 1; p.taps = a->R * a->S;
   CUtensorMap tmA, tmB;
   memset(&tmA, 0, sizeof(tmA)); memset(&tmB, 0, sizeof(tmB));
   int bn, rc;
@@ -1261,12 +1400,14 @@ extern "C" int mtl_conv_tc(const mtl_conv_args* a, cudaStream_t stream) {
     p.ldm = a->mask_ld ? a->mask_ld : a->K;
     epi_ok = epi_tma_ok(a->out, a->out_fp32, p.ldo, a->res, a->res_fp32, p.ldr, a->mask, p.ldm);
     plan_tile(p.M, p.N, p.k_iters, epi_ok && a->ws, a->force_bn, a->force_splits, &bn, &p.splits);
+    p.cluster = pick_cluster(p.M, p.N, bn, p.splits, gather, a->force_cluster);
     if (im2col) {
       p.im_low_h = -a->pad_h; p.im_low_w = -a->pad_w;
       if ((rc = make_im2col_map(&tmA, a->x, a->N, a->H, a->W, a->C, p.im_low_h, p.im_low_w,
                                 a->P + p.im_low_h - a->H, a->Q + p.im_low_w - a->W, BM))) return rc;
     } else if (!gather && (rc = make_map(&tmA, a->x, npq, a->C, a->C, BM))) return rc;
-    if ((rc = make_map(&tmB, a->w, a->K, (long long)p.taps * a->C, (long long)p.taps * a->C, bn))) return rc;
+    // CTA pairs: each CTA fetches (and multicasts) half of the weight tile
+    if ((rc = make_map(&tmB, a->w, a->K, (long long)p.taps * a->C, (long long)p.taps * a->C, bn / p.cluster))) return rc;
     if (gather) tmA = tmB;
   } else if (a->mode == DGRAD) {
     MTL_CHECK_ARG(a->dy && a->w && a->out, "mtl_conv_tc dgrad: null tensor");
@@ -1278,6 +1419,7 @@ extern "C" int mtl_conv_tc(const mtl_conv_args* a, cudaStream_t stream) {
     p.ldm = a->mask_ld ? a->mask_ld : a->C;
     epi_ok = epi_tma_ok(a->out, a->out_fp32, p.ldo, a->res, a->res_fp32, p.ldr, a->mask, p.ldm);
     plan_tile(p.M, p.N, p.k_iters, epi_ok && a->ws, a->force_bn, a->force_splits, &bn, &p.splits);
+    p.cluster = pick_cluster(p.M, p.N, bn, p.splits, gather, a->force_cluster);
     if (im2col) {
       // dx[h] = sum_r dy[h + pad - r*dil]: a stride-1 correlation over dy with mirrored filter offsets
       p.im_low_h = a->pad_h - (a->R - 1) * p.dil; p.im_low_w = a->pad_w - (a->S - 1) * p.dil;

@@ -47,13 +47,14 @@ class ConvArgs(ctypes.Structure):
         ("dy_ld", ctypes.c_longlong), ("out_ld", ctypes.c_longlong), ("res_ld", ctypes.c_longlong),
         ("mask_ld", ctypes.c_longlong), ("bias_scale", ctypes.c_float),
         ("force_stages", ctypes.c_int), ("ws", ctypes.c_void_p), ("ws_bytes", ctypes.c_longlong),
+        ("force_cluster", ctypes.c_int),
     ]
 
 
 # Split-K workspaces (fprop / dgrad): one zero-filled fp32 buffer per CUDA stream -- launches on one stream
 # are ordered, and the kernel leaves the buffer zeroed.  Outgrown buffers are kept alive because CUDA graphs
 # captured earlier still point at them.
-SPLIT_K = True
+SPLIT_K = False     # off by default: fp32-atomic partial sums make the forward pass run-to-run non-deterministic (gain ~1 %)
 _ws_by_stream = {}
 _ws_retired = []
 
@@ -104,7 +105,8 @@ def _geom(a, xshape, wshape, stride, pad, dil, P, Q):
 
 
 def conv_fprop(x, w, stride=1, pad=(0, 0), dil=1, out_hw=None, bias=None, res=None, relu=False,
-               out=None, out_dtype=torch.bfloat16, force_bn=0, bias_scale=1.0, force_splits=0, force_stages=0):
+               out=None, out_dtype=torch.bfloat16, force_bn=0, bias_scale=1.0, force_splits=0, force_stages=0,
+               force_cluster=0):
     """y = relu?(conv(x, w) + bias + res).  x [N,H,W,C] bf16, w [K,R,S,C] bf16."""
     N, H, W, C = x.shape
     K, R, S, C2 = w.shape
@@ -129,13 +131,14 @@ def conv_fprop(x, w, stride=1, pad=(0, 0), dil=1, out_hw=None, bias=None, res=No
     a.alpha = 1.0
     a.bias_scale = float(bias_scale)
     a.force_bn, a.force_splits, a.force_stages = force_bn, force_splits, force_stages
+    a.force_cluster = force_cluster
     _attach_ws(a)
     _launch(a, "mtl_conv_tc(fprop)")
     return out
 
 
 def conv_dgrad(dy, w, x_shape, stride=1, pad=(0, 0), dil=1, res=None, mask=None, out=None,
-               out_dtype=torch.bfloat16, force_bn=0, mask_hi=0.0, force_splits=0, force_stages=0):
+               out_dtype=torch.bfloat16, force_bn=0, mask_hi=0.0, force_splits=0, force_stages=0, force_cluster=0):
     """dx = mask>0 ? (conv_transpose(dy, w) + res) : 0.  dy [N,P,Q,K], w [K,R,S,C]."""
     N, P, Q, K = dy.shape
     K2, R, S, C = w.shape
@@ -159,6 +162,7 @@ def conv_dgrad(dy, w, x_shape, stride=1, pad=(0, 0), dil=1, res=None, mask=None,
         a.mask_hi = float(mask_hi)
     a.alpha = 1.0
     a.force_bn, a.force_splits, a.force_stages = force_bn, force_splits, force_stages
+    a.force_cluster = force_cluster
     _attach_ws(a)
     _launch(a, "mtl_conv_tc(dgrad)")
     return out

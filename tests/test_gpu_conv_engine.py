@@ -128,6 +128,49 @@ def test_split_k_and_residual_ring(case):
         assert not buf.any(), "split-K workspace not left zeroed"
 
 
+PAIR_CASES = [
+    # N, H, W, C, K, R, bn   (stride 1; M = N*H*W rows)
+    (256, 7, 7, 256, 512, 1, 256),      # 98 m-tiles -> 49 pairs, residual + mask rings
+    (255, 7, 7, 128, 512, 3, 256),      # 98 m-tiles with a ragged last tile, TMA im2col operand
+    (101, 7, 7, 192, 384, 1, 128),      # 39 m-tiles: odd -> one padding CTA; C = 3 x 64, N = 3 x 128
+    (65, 7, 7, 64, 200, 3, 128),        # N not a multiple of 32
+    (3, 38, 63, 128, 256, 3, 256),      # trunk-shaped rows, image borders inside the pair
+]
+
+
+@pytest.mark.parametrize("case", PAIR_CASES)
+def test_cta_pairs_with_multicast_weights(case):
+    """FPROP / DGRAD on two-CTA clusters (each CTA multicasts half of the weight tile) against the fp32
+    reference and, bit for bit, against the single-CTA schedule (same tiles, same accumulation order)."""
+    from mtl_ssl_b200 import ops_conv as oc
+    N, H, W, C, K, R, bn = case
+    torch.manual_seed(hash(case) % 1000)
+    pad = (R - 1) // 2
+    dev = "cuda"
+    x = torch.randn(N, H, W, C, device=dev).bfloat16()
+    w = (torch.randn(K, R, R, C, device=dev) / (R * R * C) ** 0.5).bfloat16()
+    bias = torch.randn(K, device=dev)
+    res = torch.randn(N, H, W, K, device=dev).bfloat16()
+    want = torch.relu(ref_conv(x, w, 1, (pad, pad), H, W) + bias + res.float())
+    y2 = oc.conv_fprop(x, w, 1, (pad, pad), 1, (H, W), bias=bias, res=res, relu=True, force_bn=bn, force_cluster=2)
+    y1 = oc.conv_fprop(x, w, 1, (pad, pad), 1, (H, W), bias=bias, res=res, relu=True, force_bn=bn, force_cluster=1)
+    close(y2, want, 1e-2)
+    assert torch.equal(y1, y2)
+    xf = x.float().requires_grad_(True)
+    yr = ref_conv(xf, w.float(), 1, (pad, pad), H, W)
+    dy = torch.randn(N, H, W, K, device=dev).bfloat16()
+    yr.backward(dy.float())
+    mask = torch.randn(N, H, W, C, device=dev).bfloat16()
+    res2 = torch.randn(N, H, W, C, device=dev).bfloat16()
+    want_dx = torch.where(mask.float() > 0, xf.grad + res2.float(), torch.zeros_like(xf.grad))
+    if C >= 128:
+        bnd = 256 if C >= 256 else 128
+        dx2 = oc.conv_dgrad(dy, w, (N, H, W, C), 1, (pad, pad), 1, res=res2, mask=mask, force_bn=bnd, force_cluster=2)
+        dx1 = oc.conv_dgrad(dy, w, (N, H, W, C), 1, (pad, pad), 1, res=res2, mask=mask, force_bn=bnd, force_cluster=1)
+        close(dx2, want_dx, 1e-2)
+        assert torch.equal(dx1, dx2)
+
+
 @pytest.mark.parametrize("R,S", [(1, 1), (3, 3), (1, 7)])
 def test_channel_slices(R, S):
     """Branch outputs written straight into a concat buffer; gradients read from / masked by slices of it."""

@@ -39,23 +39,42 @@ def sweep(mode, N, H, W, C, K, R, res, cfgs):
     dx = torch.empty(N, H, W, C, device="cuda", dtype=torch.bfloat16)
     fl = 2.0 * N * H * W * K * R * R * C
     out = []
-    for bn, sp, st in cfgs:
+    for cfg in cfgs:
+        bn, sp, st = cfg[:3]
+        cl = cfg[3] if len(cfg) > 3 else 0
         def run():
             if mode == "fprop":
                 oc.conv_fprop(x, w, 1, (pad, pad), 1, (H, W), bias=bias, res=r_y if res else None, relu=True, out=y,
-                              force_bn=bn, force_splits=sp, force_stages=st)
+                              force_bn=bn, force_splits=sp, force_stages=st, force_cluster=cl)
             else:
                 oc.conv_dgrad(dy, w, (N, H, W, C), 1, (pad, pad), 1, res=r_x if res & 1 else None,
-                              mask=r_x if res else None, out=dx, force_bn=bn, force_splits=sp, force_stages=st)
+                              mask=r_x if res else None, out=dx, force_bn=bn, force_splits=sp, force_stages=st, force_cluster=cl)
         try:
             us = timed(run)
-            out.append("bn%d/s%d/st%d %.1fus %.0fTF" % (bn, sp, st, us, fl / us / 1e6))
+            out.append("bn%d/s%d/st%d/cl%d %.1fus %.0fTF" % (bn, sp, st, cl, us, fl / us / 1e6))
         except MtlError as e:
             out.append("bn%d/s%d/st%d ERR" % (bn, sp, st))
     print("%-5s N%-4d %dx%d C%-4d K%-4d k%d res%d | %s" % (mode, N, H, W, C, K, R, res, "  ".join(out)), flush=True)
 
 
+def pairs():
+    c = [(0, 1, 0, 1), (0, 1, 0, 2), (128, 1, 0, 1), (128, 1, 0, 2)]
+    for n in (1280, 256, 64):
+        sweep("fprop", n, 7, 7, 512, 512, 3, 0, c)
+        sweep("fprop", n, 7, 7, 512, 2048, 1, 1, c)
+        sweep("fprop", n, 7, 7, 2048, 512, 1, 0, c)
+        sweep("fprop", n, 7, 7, 1024, 2048, 1, 0, c)
+    sweep("dgrad", 256, 7, 7, 512, 512, 3, 2, c)
+    sweep("dgrad", 256, 7, 7, 2048, 512, 1, 3, c)
+    sweep("dgrad", 256, 7, 7, 512, 2048, 1, 2, c)
+    sweep("dgrad", 256, 7, 7, 1024, 2048, 1, 2, c)
+    sweep("fprop", 1, 75, 125, 128, 512, 1, 1, c)
+    sweep("fprop", 1, 150, 250, 64, 256, 1, 1, c)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "pairs":
+        return pairs()
     T = (1, 38, 63)
     # trunk block3 (M = 2394): default vs split-K
     trunk_cfg = [(0, 1, 0), (64, 1, 0), (64, 2, 0), (128, 2, 0), (128, 3, 0), (128, 4, 0), (256, 2, 0), (256, 4, 0), (256, 7, 0)]
