@@ -202,7 +202,9 @@ def run_ours(args, rank, world, local_rank):
         tr._backward_trunk()
     model.param_store.g.zero_()
     c1 = ops.launch_count()
-    launches_per_step = (c1 - c0) + 3          # + optimizer stats, reg-loss, apply
+    # + the optimizer launches not in the count above: stats + apply for the trunk and the dead-variable ranges,
+    # the L2 reduction, and (several replicas: its own graph) stats + apply of the head bucket
+    launches_per_step = (c1 - c0) + (5 if world == 1 else 7)
     sync()
 
     clocks = ClockSampler(local_rank)
@@ -243,6 +245,7 @@ def run_ours(args, rank, world, local_rank):
     # kernel keeps the GPU busy while Python enqueues the step, so no event pair contains host launch latency.
     from mtl_ssl_b200.nets.layers import Concurrency
     Concurrency.enabled = False
+    overlap, tr.overlap_optimizer = tr.overlap_optimizer, False      # keep the optimizer out of the conv timings
     tr._forward_backward(tr.inputs.dev["image"])            # re-warm the single-stream path
     if world > 1:
         tr._backward_trunk()
@@ -256,6 +259,7 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.synchronize()
     prof, ops_conv.PROFILE = ops_conv.PROFILE, None
     Concurrency.enabled = True
+    tr.overlap_optimizer = overlap
     model.param_store.g.zero_()
     conv_ms = sum(p_[2].elapsed_time(p_[3]) for p_ in prof)
     conv_flops = sum(p_[1] for p_ in prof)

@@ -215,12 +215,16 @@ typedef struct mtl_chunk_desc {
 int mtl_opt_chunk_size(void);
 int mtl_opt_stats(const mtl_tensor_desc* tensors, int num_tensors, const mtl_chunk_desc* chunks, int num_chunks,
                   const float* params, const float* grads, float grad_scale, float* stats /* [T,2] */,
-                  float* reg_loss /* [1] or NULL */, mtl_stream_t stream);
+                  float* reg_loss /* [1] or NULL */, const int* chunk_start /* [T+1] first chunk of every tensor */,
+                  float* partials /* [num_chunks,2]: fixed-order (run-to-run and replica-to-replica identical) sums,
+                                     NULL = fp32 atomics */,
+                  mtl_stream_t stream);
 /* the same statistics for the tensors [t0, t1) only (`chunks` = first chunk of tensor t0): lets the update of a
  * finished gradient bucket overlap the rest of the backward pass; mtl_opt_reg_loss then sums the L2 terms. */
 int mtl_opt_stats_range(const mtl_tensor_desc* tensors, int t0, int t1, const mtl_chunk_desc* chunks, int num_chunks,
                         const float* params, const float* grads, float grad_scale, float* stats /* [T,2] */,
-                        mtl_stream_t stream);
+                        const int* chunk_start /* [T+1] */, int chunk0 /* index of chunks[0] */,
+                        float* partials /* [all chunks,2] or NULL */, mtl_stream_t stream);
 int mtl_opt_reg_loss(const mtl_tensor_desc* tensors, int num_tensors, const float* stats, float* reg_loss /* [1] */,
                      mtl_stream_t stream);
 int mtl_opt_apply(const mtl_tensor_desc* tensors, const mtl_chunk_desc* chunks, int num_chunks, float* params,

@@ -53,7 +53,7 @@ __device__ __forceinline__ float block_sum256(float v, float* red) {
 __global__ void __launch_bounds__(256)
 opt_stats_kernel(const mtl_tensor_desc* __restrict__ td, const mtl_chunk_desc* __restrict__ cd,
                  const float* __restrict__ params, const float* __restrict__ grads, float gscale,
-                 float* __restrict__ stats) {
+                 float* __restrict__ stats, float* __restrict__ partials) {
   __shared__ float red[32];
   const mtl_chunk_desc c = cd[blockIdx.x];
   const mtl_tensor_desc t = td[c.tensor];
@@ -84,9 +84,32 @@ opt_stats_kernel(const mtl_tensor_desc* __restrict__ td, const mtl_chunk_desc* _
   const float tw = block_sum256(sw, red);
   const float tg = block_sum256(sg, red);
   if (threadIdx.x == 0) {
-    atomicAdd(stats + c.tensor * 2, tw);
-    if (t.trainable) atomicAdd(stats + c.tensor * 2 + 1, tg);
+    if (partials) {          // deterministic mode: opt_stats_reduce_kernel sums the chunks in a fixed order
+      partials[2 * blockIdx.x] = tw;
+      partials[2 * blockIdx.x + 1] = t.trainable ? tg : 0.0f;
+    } else {
+      atomicAdd(stats + c.tensor * 2, tw);
+      if (t.trainable) atomicAdd(stats + c.tensor * 2 + 1, tg);
+    }
   }
+}
+
+// stats[t] = sum of the chunk partials of tensor t, one warp per tensor, fixed summation order: every
+// data-parallel replica computes bit-identical clip factors from its (bit-identical) all-reduced gradients
+__global__ void __launch_bounds__(256)
+opt_stats_reduce_kernel(const int* __restrict__ chunk_start, int t0, int t1, int chunk0,
+                        const float* __restrict__ partials, float* __restrict__ stats) {
+  const int t = t0 + blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (t >= t1) return;
+  const int lane = threadIdx.x & 31;
+  float a = 0.0f, b = 0.0f;
+  for (int c = chunk_start[t] + lane; c < chunk_start[t + 1]; c += 32) {
+    a += partials[2 * (c - chunk0)];
+    b += partials[2 * (c - chunk0) + 1];
+  }
+  a = warp_sum(a);
+  b = warp_sum(b);
+  if (lane == 0) { stats[2 * t] = a; stats[2 * t + 1] = b; }
 }
 
 // reg_loss[0] = sum_t l2_t * 0.5 * sum w_t^2
@@ -211,12 +234,20 @@ extern "C" int mtl_opt_chunk_size(void) { return CHUNK; }
 
 extern "C" int mtl_opt_stats(const mtl_tensor_desc* tensors, int num_tensors, const mtl_chunk_desc* chunks,
                              int num_chunks, const float* params, const float* grads, float grad_scale,
-                             float* stats, float* reg_loss, cudaStream_t stream) {
+                             float* stats, float* reg_loss, const int* chunk_start, float* partials,
+                             cudaStream_t stream) {
   MTL_CHECK_ARG(tensors && chunks && params && grads && stats, "mtl_opt_stats: null tensor");
-  cudaError_t e = cudaMemsetAsync(stats, 0, sizeof(float) * 2 * num_tensors, stream);
-  if (e != cudaSuccess) { mtl_set_error("mtl_opt_stats: memset: %s", cudaGetErrorString(e)); return MTL_ERR_CUDA; }
-  opt_stats_kernel<<<num_chunks, 256, 0, stream>>>(tensors, chunks, params, grads, grad_scale, stats);
+  MTL_CHECK_ARG(!partials || chunk_start, "mtl_opt_stats: partials need the chunk_start table");
+  if (!partials) {
+    cudaError_t e = cudaMemsetAsync(stats, 0, sizeof(float) * 2 * num_tensors, stream);
+    if (e != cudaSuccess) { mtl_set_error("mtl_opt_stats: memset: %s", cudaGetErrorString(e)); return MTL_ERR_CUDA; }
+  }
+  opt_stats_kernel<<<num_chunks, 256, 0, stream>>>(tensors, chunks, params, grads, grad_scale, stats, partials);
   MTL_CUDA_LAUNCH_CHECK("opt_stats_kernel");
+  if (partials) {
+    opt_stats_reduce_kernel<<<ceil_div(num_tensors, 8), 256, 0, stream>>>(chunk_start, 0, num_tensors, 0, partials, stats);
+    MTL_CUDA_LAUNCH_CHECK("opt_stats_reduce_kernel");
+  }
   if (reg_loss) {
     opt_reg_loss_kernel<<<1, 256, 0, stream>>>(tensors, num_tensors, stats, reg_loss);
     MTL_CUDA_LAUNCH_CHECK("opt_reg_loss_kernel");
@@ -226,13 +257,22 @@ extern "C" int mtl_opt_stats(const mtl_tensor_desc* tensors, int num_tensors, co
 
 extern "C" int mtl_opt_stats_range(const mtl_tensor_desc* tensors, int t0, int t1, const mtl_chunk_desc* chunks,
                                    int num_chunks, const float* params, const float* grads, float grad_scale,
-                                   float* stats, cudaStream_t stream) {
+                                   float* stats, const int* chunk_start, int chunk0, float* partials,
+                                   cudaStream_t stream) {
   MTL_CHECK_ARG(tensors && chunks && params && grads && stats && t0 >= 0 && t1 >= t0, "mtl_opt_stats_range: bad argument");
+  MTL_CHECK_ARG(!partials || chunk_start, "mtl_opt_stats_range: partials need the chunk_start table");
   if (t1 == t0 || num_chunks == 0) return MTL_OK;
-  cudaError_t e = cudaMemsetAsync(stats + 2 * t0, 0, sizeof(float) * 2 * (t1 - t0), stream);
-  if (e != cudaSuccess) { mtl_set_error("mtl_opt_stats_range: memset: %s", cudaGetErrorString(e)); return MTL_ERR_CUDA; }
-  opt_stats_kernel<<<num_chunks, 256, 0, stream>>>(tensors, chunks, params, grads, grad_scale, stats);
+  if (!partials) {
+    cudaError_t e = cudaMemsetAsync(stats + 2 * t0, 0, sizeof(float) * 2 * (t1 - t0), stream);
+    if (e != cudaSuccess) { mtl_set_error("mtl_opt_stats_range: memset: %s", cudaGetErrorString(e)); return MTL_ERR_CUDA; }
+  }
+  opt_stats_kernel<<<num_chunks, 256, 0, stream>>>(tensors, chunks, params, grads, grad_scale, stats,
+                                                   partials ? partials + 2 * (long long)chunk0 : nullptr);
   MTL_CUDA_LAUNCH_CHECK("opt_stats_kernel");
+  if (partials) {
+    opt_stats_reduce_kernel<<<ceil_div(t1 - t0, 8), 256, 0, stream>>>(chunk_start, t0, t1, 0, partials, stats);
+    MTL_CUDA_LAUNCH_CHECK("opt_stats_reduce_kernel");
+  }
   return MTL_OK;
 }
 

@@ -178,6 +178,9 @@ class ParamStore(object):
         self.td = torch.frombuffer(bytearray(bytes(td)), dtype=torch.uint8).to(self.device)
         self.cd = torch.frombuffer(bytearray(bytes(cd)), dtype=torch.uint8).to(self.device)
         self.stats = torch.zeros(T * 2, dtype=torch.float32, device=self.device)
+        # per-chunk partial sums + the chunk table on the device: the per-tensor norms are reduced in a fixed order
+        self.partials = torch.zeros(max(len(chunks), 1) * 2, dtype=torch.float32, device=self.device)
+        self.chunk_start_dev = torch.tensor(self.chunk_start, dtype=torch.int32, device=self.device)
         self.reg_loss = torch.zeros(1, dtype=torch.float32, device=self.device)
         self.hyper = torch.zeros(4, dtype=torch.float32, device=self.device)
 
@@ -188,7 +191,7 @@ class ParamStore(object):
 
     def stats_and_reg_loss(self, grad_scale=1.0):
         ops.call("mtl_opt_stats", self.td, self.num_tensors, self.cd, self.num_chunks, self.w, self.g,
-                 grad_scale, self.stats, self.reg_loss)
+                 grad_scale, self.stats, self.reg_loss, self.chunk_start_dev, self.partials)
         return self.reg_loss
 
     def apply(self, grad_scale=1.0):
@@ -204,7 +207,8 @@ class ParamStore(object):
     def stats_range(self, t0, t1, grad_scale=1.0):
         cd, n = self._chunk_range(t0, t1)
         if n:
-            ops.call("mtl_opt_stats_range", self.td, t0, t1, cd, n, self.w, self.g, grad_scale, self.stats)
+            ops.call("mtl_opt_stats_range", self.td, t0, t1, cd, n, self.w, self.g, grad_scale, self.stats,
+                     self.chunk_start_dev, self.chunk_start[t0], self.partials)
 
     def apply_range(self, t0, t1, grad_scale=1.0):
         cd, n = self._chunk_range(t0, t1)

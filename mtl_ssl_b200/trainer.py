@@ -96,7 +96,8 @@ class Trainer(object):
         self._loss_host = (torch.zeros(9).pin_memory() if torch.cuda.is_available() else torch.zeros(9))
         self._loss_dev = torch.zeros(9, device=self.device)
         self.launches_per_step = None
-        self.overlap_optimizer = True       # world_size 1: update the head bucket under the trunk backward
+        self.overlap_optimizer = True       # update the head bucket under the trunk backward (and its all-reduce)
+        self.graph_opt_heads = None
         self._opt_stream = None
 
     # ------------------------------------------------------------------ one step
@@ -143,11 +144,8 @@ class Trainer(object):
         self._opt_stream.wait_stream(cur)
         for s in (Concurrency._streams or []):
             self._opt_stream.wait_stream(s)          # head weight-gradient GEMMs run on the side streams
-        t0, t1 = m.head_tensor_range()
-        st = m.param_store
         with torch.cuda.stream(self._opt_stream):
-            st.stats_range(t0, t1, 1.0)
-            st.apply_range(t0, t1, 1.0)
+            self._optimize_heads()
         m.backward(None, part="trunk")
         cur.wait_stream(self._opt_stream)
         return pd
@@ -155,10 +153,19 @@ class Trainer(object):
     def _backward_trunk(self):
         self.model.backward(None, part="trunk")
 
+    def _optimize_heads(self):
+        """clip + momentum update of the second-stage / aux-head tensors [t0, t1) (their gradients are final
+        once backward(part="heads") has run / their bucket has been all-reduced)."""
+        st = self.model.param_store
+        gs = data_parallel_scale(self.world_size)
+        t0, t1 = self.model.head_tensor_range()
+        st.stats_range(t0, t1, gs)
+        st.apply_range(t0, t1, gs)
+
     def _optimize(self):
         st = self.model.param_store
         gs = data_parallel_scale(self.world_size)
-        if self.world_size == 1 and self.overlap_optimizer:
+        if self.overlap_optimizer:
             t0, t1 = self.model.head_tensor_range()       # [t0, t1) was updated under the trunk backward
             T = st.num_tensors
             for a, b in ((0, t0), (t1, T)):
@@ -185,11 +192,24 @@ class Trainer(object):
             return
         import torch.distributed as dist
         b_heads, b_trunk = self.model.gradient_buckets()
+        cur = torch.cuda.current_stream()
         self.graph_fb.replay() if graph else self._forward_backward(self.inputs.dev["image"])
         w1 = dist.all_reduce(b_heads, op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
+        if self.overlap_optimizer:
+            # the head bucket's update follows its all-reduce on a side stream, underneath the trunk backward
+            # and the trunk bucket's all-reduce
+            if self._opt_stream is None:
+                self._opt_stream = torch.cuda.Stream()
+            self._opt_stream.wait_stream(cur)
+            with torch.cuda.stream(self._opt_stream):
+                w1.wait()
+                self.graph_opt_heads.replay() if graph else self._optimize_heads()
         self.graph_fb2.replay() if graph else self._backward_trunk()
         w2 = dist.all_reduce(b_trunk, op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
-        w1.wait()
+        if self.overlap_optimizer:
+            cur.wait_stream(self._opt_stream)
+        else:
+            w1.wait()
         w2.wait()
         self.graph_opt.replay() if graph else self._optimize()
 
@@ -244,6 +264,10 @@ class Trainer(object):
             self.graph_fb2 = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph_fb2):
                 self._backward_trunk()
+        if self.world_size > 1 and self.overlap_optimizer:
+            self.graph_opt_heads = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_opt_heads):
+                self._optimize_heads()
         self.graph_opt = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph_opt):
             self._optimize()
