@@ -54,20 +54,48 @@ def pack_groundtruth(examples, num_classes, height, width, gmax):
 
 
 class StaticInputs(object):
-    """Pinned host staging + device buffers of fixed shape; `load()` is the step's only H2D."""
+    """Pinned host staging + device buffers of fixed shape; `load()` is the step's only H2D.
+    Two extra (pinned host, device staging) slots serve the software-pipelined step: the next batch is
+    staged and copied on a side stream while the current step computes, then moved device-to-device
+    into the fixed buffers the CUDA graphs read."""
 
     def __init__(self, device, arrays):
         self.host, self.dev = {}, {}
+        self.host_slots, self.stage_slots = [{}, {}], [{}, {}]
+        cuda = torch.cuda.is_available()
         for k, a in arrays.items():
             t = torch.from_numpy(np.ascontiguousarray(a))
-            self.host[k] = t.pin_memory() if torch.cuda.is_available() else t
+            self.host[k] = t.pin_memory() if cuda else t
             self.dev[k] = torch.empty_like(t, device=device)
         self.nbytes = sum(t.numel() * t.element_size() for t in self.host.values())
+        if cuda:        # allocate the pipelining slots up front: cudaHostAlloc costs milliseconds
+            for hs, ds in zip(self.host_slots, self.stage_slots):
+                for k, t in self.host.items():
+                    hs[k] = torch.empty_like(t).pin_memory()
+                    ds[k] = torch.empty_like(self.dev[k])
 
     def load(self, arrays):
         for k, a in arrays.items():
             self.host[k].copy_(torch.from_numpy(np.ascontiguousarray(a)))
             self.dev[k].copy_(self.host[k], non_blocking=True)
+
+    def stage_async(self, slot, arrays, stream):
+        """host copy into pinned slot `slot`, then H2D into the device staging slot on `stream`."""
+        hs, ds = self.host_slots[slot], self.stage_slots[slot]
+        if not hs:
+            for k, t in self.host.items():
+                hs[k] = torch.empty_like(t).pin_memory()
+                ds[k] = torch.empty_like(self.dev[k])
+        for k, a in arrays.items():
+            hs[k].copy_(torch.from_numpy(np.ascontiguousarray(a)))
+        with torch.cuda.stream(stream):
+            for k in arrays:
+                ds[k].copy_(hs[k], non_blocking=True)
+
+    def commit(self, slot):
+        """device staging slot -> the fixed input buffers (current stream)."""
+        for k, t in self.stage_slots[slot].items():
+            self.dev[k].copy_(t, non_blocking=True)
 
 
 class Trainer(object):
@@ -97,6 +125,13 @@ class Trainer(object):
         self._loss_dev = torch.zeros(9, device=self.device)
         self.launches_per_step = None
         self.overlap_optimizer = True       # update the head bucket under the trunk backward (and its all-reduce)
+        # software-pipelined step (step_pipelined): two slots of hyper-parameter / loss staging, a copy stream
+        pin = torch.cuda.is_available()
+        self._hyper_slots = [torch.zeros(4).pin_memory() if pin else torch.zeros(4) for _ in range(2)]
+        self._loss_slots = [torch.zeros(9).pin_memory() if pin else torch.zeros(9) for _ in range(2)]
+        self._copy_stream = None
+        self._pipe_i = 0
+        self._pending = None
         self.graph_opt_heads = None
         self._opt_stream = None
 
@@ -105,6 +140,9 @@ class Trainer(object):
         if self.inputs is None:
             self.inputs = StaticInputs(self.device, arrays)
         self.inputs.load(arrays)
+        return self._attach()
+
+    def _attach(self):
         d = self.inputs.dev
         m = self.model
         gt = dict(gt=d["gt"], num_gt=d["num_gt"], gt_cls=d["gt_cls"], gt_close=d["gt_close"], gmax=self.gmax,
@@ -238,8 +276,55 @@ class Trainer(object):
         torch.cuda.current_stream().synchronize()
         return self.losses_from_host()
 
-    def losses_from_host(self):
-        v = self._loss_host.tolist()
+    def step_pipelined(self, arrays):
+        """The same training step, software-pipelined against the host: the batch is staged into pinned memory
+        and copied H2D on a side stream while the previous step still computes, and the call returns the losses
+        of the PREVIOUS call (None on the first one; `flush()` returns the last).  Every step still performs its
+        own H2D copy of the inputs and D2H read of its loss vector; only the host no longer idles the GPU."""
+        if self.inputs is None or (self.use_graph and self.graph_fb is None):
+            self._pending = ("done", self.step(arrays))       # first call: allocations + graph capture, synchronous
+            return None
+        st = self.model.param_store
+        slot = self._pipe_i & 1
+        self._pipe_i += 1
+        cur = torch.cuda.current_stream()
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream()
+        # slot reuse is safe: the step that used it two calls ago has finished (its losses were resolved below)
+        self.inputs.stage_async(slot, arrays, self._copy_stream)
+        staged = torch.cuda.Event()
+        staged.record(self._copy_stream)
+        hh = self._hyper_slots[slot]
+        hh[0] = float(self.lr_fn(self.global_step))
+        hh[1] = self.momentum
+        hh[2] = self.clip_norm if self.clip_norm else 0.0
+        cur.wait_event(staged)
+        self.inputs.commit(slot)
+        st.hyper.copy_(hh, non_blocking=True)
+        self._attach()
+        self._run_step_body()
+        self.global_step += 1
+        self._loss_slots[slot].copy_(self._loss_dev, non_blocking=True)
+        done = torch.cuda.Event()
+        done.record(cur)
+        prev, self._pending = self._pending, ("event", done, slot)
+        return self._resolve(prev)
+
+    def flush(self):
+        """Losses of the last step_pipelined() call (waits for it)."""
+        prev, self._pending = self._pending, None
+        return self._resolve(prev)
+
+    def _resolve(self, pending):
+        if pending is None:
+            return None
+        if pending[0] == "done":
+            return pending[1]
+        pending[1].synchronize()
+        return self.losses_from_host(self._loss_slots[pending[2]])
+
+    def losses_from_host(self, buf=None):
+        v = (self._loss_host if buf is None else buf).tolist()
         out = {k: v[i] for i, k in enumerate(LOSS_KEYS)}
         out["regularization_loss"] = v[8]
         # model_deploy.py:198-236: sum of task losses / num_clones + regularisation
