@@ -324,13 +324,25 @@ class FasterRCNNMetaArch(model.DetectionModel):
         return self._anchors(Hf, Wf, image_shape[1], image_shape[2])[2]
 
     # ------------------------------------------------------------------ forward
-    def predict(self, preprocessed_inputs):
-        """fmA:507-609."""
+    def frozen_prefix(self, preprocessed_inputs, tag="s1"):
+        """Activations of the frozen leading layers of the stage-1 trunk (image-only dependency), or None when the
+        feature extractor has no such split; pass the result to predict(prefix=)."""
+        fe = self._feature_extractor
+        if not hasattr(fe, "extract_frozen_prefix"):
+            return None
+        return fe.extract_frozen_prefix(preprocessed_inputs, self.first_stage_feature_extractor_scope, self._ws, tag)
+
+    def predict(self, preprocessed_inputs, prefix=None):
+        """fmA:507-609.  `prefix`: output of frozen_prefix() for these inputs (computed ahead of time)."""
         ws, fe = self._ws, self._feature_extractor
         B, H, W, _ = preprocessed_inputs.shape
         image_shape = (B, H, W, 3)
         self._lanes.reset()
-        feat = fe.extract_proposal_features(preprocessed_inputs, self.first_stage_feature_extractor_scope, ws)
+        if prefix is not None:
+            feat = fe.extract_proposal_features(preprocessed_inputs, self.first_stage_feature_extractor_scope, ws,
+                                                prefix=prefix)
+        else:
+            feat = fe.extract_proposal_features(preprocessed_inputs, self.first_stage_feature_extractor_scope, ws)
         self._lanes.mark("feat")
         _, Hf, Wf, Cf = feat.shape
         anchors, keep_idx, Nk = self._anchors(Hf, Wf, H, W)

@@ -73,13 +73,20 @@ class FasterRCNNResnetV1FeatureExtractor(FasterRCNNFeatureExtractor):
         return next(iter(self._trunks.values()))
 
     # forward / backward ---------------------------------------------------------------------
-    def extract_proposal_features(self, preprocessed_inputs, scope, ws):
+    def extract_frozen_prefix(self, preprocessed_inputs, scope, ws, tag="s1"):
+        """Output of conv1 + the frozen blocks (None if nothing is frozen): feeds extract_proposal_features(prefix=)."""
+        trunk = self._trunks[scope]
+        if trunk.num_frozen_units() == 0:
+            return None
+        return trunk.fwd_prefix(preprocessed_inputs, ws, tag)
+
+    def extract_proposal_features(self, preprocessed_inputs, scope, ws, prefix=None):
         if preprocessed_inputs.dim() != 4:
             raise ValueError("`preprocessed_inputs` must be 4 dimensional, got a tensor of shape %s"
                              % (tuple(preprocessed_inputs.shape),))
         if preprocessed_inputs.shape[1] < 33 or preprocessed_inputs.shape[2] < 33:
             raise ValueError("image size must at least be 33 in both height and width.")
-        return self._trunks[scope].fwd(preprocessed_inputs, ws)
+        return self._trunks[scope].fwd(preprocessed_inputs, ws, prefix)
 
     def backward_proposal_features(self, scope, grad, ws):
         self._trunks[scope].bwd(grad, ws)

@@ -117,18 +117,18 @@ class Stem(object):
         P, Q = (H + 6 - 7) // 2 + 1, (W + 6 - 7) // 2 + 1
         return max_pool_out_hw(P, Q, 3, 2)
 
-    def fwd(self, img, ws):
+    def fwd(self, img, ws, tag=""):
         B, H, W, C = img.shape
         P, Q = (H + 6 - 7) // 2 + 1, (W + 6 - 7) // 2 + 1
         if self.packed is None:
             self.pack(img.device)
-        rows = ws.get(self.scope + "/im2col", (B, P, Q, self.ld))
+        rows = ws.get(self.scope + tag + "/im2col", (B, P, Q, self.ld))
         ops.call("mtl_im2col_f32", img, B, H, W, 3, 7, 7, 2, 3, 3, P, Q, list(self.means), self.scale, rows,
                  self.ld)
-        c1 = ws.get(self.scope + "/conv1", (B, P, Q, 64))
+        c1 = ws.get(self.scope + tag + "/conv1", (B, P, Q, 64))
         oc.conv_fprop(rows, self.packed, bias=self.bn.bias, relu=True, out=c1)
         P2, Q2 = max_pool_out_hw(P, Q, 3, 2)
-        return max_pool(c1, ws.get(self.scope + "/pool1", (B, P2, Q2, 64)), 3, 2)
+        return max_pool(c1, ws.get(self.scope + tag + "/pool1", (B, P2, Q2, 64)), 3, 2)
 
 
 class ResNetV1(object):
@@ -160,9 +160,21 @@ class ResNetV1(object):
                 break
         self.out_channels = cin
 
-    def fwd(self, img, ws):
-        x = self.stem.fwd(img, ws)
-        for u in self.units:
+    def num_frozen_units(self):
+        return next((i for i, u in enumerate(self.units) if u.trainable), len(self.units))
+
+    def fwd_prefix(self, img, ws, tag="s1"):
+        """Stem + the frozen leading units (freeze_layer, fe:117-121).  Their output depends on the image only,
+        never on a weight update, so the trainer may compute it for the NEXT batch while the current step is
+        still in its backward pass (`tag` selects a separate set of activation buffers for that)."""
+        x = self.stem.fwd(img, ws, "" if tag == "s1" else "/" + tag)
+        for u in self.units[:self.num_frozen_units()]:
+            x = u.fwd(x, ws, tag)
+        return x
+
+    def fwd(self, img, ws, prefix=None):
+        x = self.fwd_prefix(img, ws) if prefix is None else prefix
+        for u in self.units[self.num_frozen_units():]:
             x = u.fwd(x, ws, "s1")
         return x
 

@@ -60,7 +60,7 @@ _ws_retired = []
 
 
 def _attach_ws(a):
-    if not SPLIT_K:
+    if not SPLIT_K and a.force_splits <= 1:      # an explicit force_splits always gets its workspace
         return
     f = lib().mtl_conv_tc_ws_bytes
     f.restype = ctypes.c_longlong

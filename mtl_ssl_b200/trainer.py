@@ -132,6 +132,17 @@ class Trainer(object):
         self._copy_stream = None
         self._pipe_i = 0
         self._pending = None
+        # frozen-prefix pipelining (set up by _setup_prefix once the first batch is bound)
+        self.pipeline_prefix = True
+        self._prefix_cur = None         # buffer the step graph reads
+        self._prefix_next = None        # buffer the look-ahead pass writes
+        self._image_next = None
+        self._prefix_stream = None
+        self._prefix_ready = None       # event: look-ahead prefix computed
+        self._prefix_taken = None       # event: it has been copied into _prefix_cur
+        self.graph_prefix = None
+        self.graph_prefix_next = None
+        self._prefix_primed = False
         self.graph_opt_heads = None
         self._opt_stream = None
 
@@ -154,10 +165,19 @@ class Trainer(object):
         m.provide_sampler_keys(d["keys1"], d["keys2"])
         return d["image"]
 
-    def _forward_backward(self, image):
+    # The frozen leading layers (conv1 + block1 under freeze_layer 'block1') depend on the image only: their
+    # activations for the NEXT batch are computed on a side stream while the current step is in its backward
+    # pass ("prefix"), into their own buffers, and handed over by one device-to-device copy at the step start.
+    def _prefix(self, image, tag="s1"):
+        m = self.model
+        return m.frozen_prefix(m.preprocess(image), tag)
+
+    def _forward_backward(self, image, prefix=None):
         m = self.model
         mtl = m._mtl
-        pd = m.predict(m.preprocess(image))
+        if prefix is None and self._prefix_cur is not None:
+            prefix = self._prefix_cur
+        pd = m.predict(m.preprocess(image), prefix=prefix) if prefix is not None else m.predict(m.preprocess(image))
         if mtl is not None and mtl.window:
             pd = m.predict_with_window(pd)
         if mtl is not None and mtl.edgemask:
@@ -197,20 +217,18 @@ class Trainer(object):
         st = self.model.param_store
         gs = data_parallel_scale(self.world_size)
         t0, t1 = self.model.head_tensor_range()
-        st.stats_range(t0, t1, gs)
-        st.apply_range(t0, t1, gs)
+        # ... plus the dead stage-1 block4 copy behind them (trap T4: no task gradient, L2 decay only)
+        st.stats_range(t0, st.num_tensors, gs)
+        st.apply_range(t0, st.num_tensors, gs)
 
     def _optimize(self):
         st = self.model.param_store
         gs = data_parallel_scale(self.world_size)
         if self.overlap_optimizer:
-            t0, t1 = self.model.head_tensor_range()       # [t0, t1) was updated under the trunk backward
-            T = st.num_tensors
-            for a, b in ((0, t0), (t1, T)):
-                st.stats_range(a, b, gs)
+            t0, _ = self.model.head_tensor_range()        # [t0, T) was updated under the trunk backward
+            st.stats_range(0, t0, gs)
             st.reg_loss_from_stats()
-            for a, b in ((0, t0), (t1, T)):
-                st.apply_range(a, b, gs)
+            st.apply_range(0, t0, gs)
         else:
             st.stats_and_reg_loss(gs)
             st.apply(gs)
@@ -220,10 +238,61 @@ class Trainer(object):
     def _allreduce(self):
         allreduce_gradients(self.model.param_store.g, self.world_size, self.pg)
 
-    def _run_step_body(self):
+    def _setup_prefix(self, image):
+        """Allocate the look-ahead buffers (called once, before graph capture)."""
+        if not self.pipeline_prefix or self._prefix_cur is not None:
+            return
+        cur = self._prefix(image, "s1")
+        if cur is None:
+            self.pipeline_prefix = False
+            return
+        self._image_next = torch.empty_like(image)
+        self._image_next.copy_(image)
+        self._prefix_cur = cur
+        self._prefix_next = self._prefix(self._image_next, "s1n")
+        self._prefix_stream = torch.cuda.Stream()
+        self._prefix_ready = torch.cuda.Event()
+        self._prefix_taken = torch.cuda.Event()
+        self._prefix_taken.record()
+
+    def _lookahead_prefix(self, image_src, after=None):
+        """Side stream: frozen prefix of the NEXT batch (`image_src`: device tensor holding its image)."""
+        ps = self._prefix_stream
+        ps.wait_event(self._prefix_taken)          # the previous look-ahead result has been consumed
+        if after is not None:
+            ps.wait_event(after)
+        with torch.cuda.stream(ps):
+            if image_src is not self._image_next:
+                self._image_next.copy_(image_src, non_blocking=True)
+            self.graph_prefix_next.replay() if self.use_graph else self._prefix(self._image_next, "s1n")
+            self._prefix_ready.record(ps)
+
+    def _take_prefix(self):
+        """Main stream: adopt the look-ahead result as this step's prefix."""
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self._prefix_ready)
+        self._prefix_cur.copy_(self._prefix_next, non_blocking=True)
+        self._prefix_taken.record(cur)
+
+    def run_resident_step(self):
+        """One step on the inputs already resident in HBM, with the frozen prefix software-pipelined: the prefix of
+        the next step (same resident image) is computed underneath this step.  Requires one earlier step."""
+        if self._prefix_cur is None:
+            return self._run_step_body()
+        if not self._prefix_primed:
+            self._lookahead_prefix(self.inputs.dev["image"])
+            self._prefix_primed = True
+        self._take_prefix()
+        self._lookahead_prefix(self.inputs.dev["image"])
+        self._run_step_body(lookahead=True)
+
+    def _run_step_body(self, lookahead=False):
         """forward + backward + gradient exchange + optimizer.  With several replicas the backward is cut
         in two: the second-stage bucket is all-reduced (NCCL stream) while the trunk half still computes."""
         graph = self.use_graph
+        if self._prefix_cur is not None and not lookahead:
+            # synchronous: frozen prefix of this batch, then the rest of the step
+            self.graph_prefix.replay() if graph else self._prefix(self.inputs.dev["image"])
         if self.world_size == 1:
             self.graph_fb.replay() if graph else self._forward_backward(self.inputs.dev["image"])
             self.graph_opt.replay() if graph else self._optimize()
@@ -266,6 +335,7 @@ class Trainer(object):
         self._hyper_host[2] = self.clip_norm if self.clip_norm else 0.0
         st.hyper.copy_(self._hyper_host, non_blocking=True)
         image = self._bind(arrays)
+        self._setup_prefix(image)
         if self.use_graph and self.graph_fb is None:
             self._capture(image)
         self._run_step_body()
@@ -299,10 +369,16 @@ class Trainer(object):
         hh[1] = self.momentum
         hh[2] = self.clip_norm if self.clip_norm else 0.0
         cur.wait_event(staged)
+        if self._prefix_cur is not None:
+            # frozen prefix of THIS batch on the side stream (it overlaps the tail of the previous step, which is
+            # still running on the main stream), then adopt it
+            self._lookahead_prefix(self.inputs.stage_slots[slot]["image"], after=staged)
+            self._prefix_primed = True
+            self._take_prefix()
         self.inputs.commit(slot)
         st.hyper.copy_(hh, non_blocking=True)
         self._attach()
-        self._run_step_body()
+        self._run_step_body(lookahead=self._prefix_cur is not None)
         self.global_step += 1
         self._loss_slots[slot].copy_(self._loss_dev, non_blocking=True)
         done = torch.cuda.Event()
@@ -342,6 +418,13 @@ class Trainer(object):
             st.g.zero_()
         st.w.copy_(snap[0]); st.m.copy_(snap[1]); st.wb.copy_(snap[2])
         torch.cuda.synchronize()
+        if self._prefix_cur is not None:
+            self.graph_prefix = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_prefix):
+                self._prefix(image, "s1")
+            self.graph_prefix_next = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_prefix_next):
+                self._prefix(self._image_next, "s1n")
         self.graph_fb = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph_fb):
             self._forward_backward(image)

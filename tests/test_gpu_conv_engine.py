@@ -124,6 +124,7 @@ def test_split_k_and_residual_ring(case):
         close(dx, want_dx, 1e-2)
     dx1 = oc.conv_dgrad(dy, w, (N, H, W, C), stride, (pad, pad), 1, mask=mask, force_bn=bn, force_splits=splits)
     close(dx1, torch.where(mask.float() > 0, xf.grad, torch.zeros_like(xf.grad)), 1e-2)
+    assert splits == 1 or oc._ws_by_stream, "forced split-K did not get a workspace"
     for buf in oc._ws_by_stream.values():
         assert not buf.any(), "split-K workspace not left zeroed"
 

@@ -166,6 +166,24 @@ def test_pipelined_step_matches_synchronous_step(graph):
             assert abs(a[k] - b[k]) <= 2e-3 * max(1.0, abs(a[k])), (k, a[k], b[k])
     # different batches must give different losses (the pipelined path really consumed its own inputs)
     assert abs(seqs[1][0]["total_loss"] - seqs[1][1]["total_loss"]) > 1e-4
+    # device-resident replay with the frozen prefix computed one step ahead == repeated synchronous steps
+    finals = []
+    for mode in ("sync", "resident"):
+        cfg, model, sd, examples, keys, tr = _setup("model12.config", SMALL, H, W, 1)
+        tr.overlap_optimizer = True
+        tr.use_graph = graph
+        tr.lr_fn = lambda step: 1e-5
+        arrays = tr.host_arrays(examples, keys)
+        tr.step(arrays)
+        for _ in range(3):
+            if mode == "sync":
+                tr.step(arrays)
+            else:
+                tr.run_resident_step()
+        torch.cuda.synchronize()
+        finals.append((tr._loss_dev.cpu().clone(), model.param_store.w.clone()))
+    torch.testing.assert_close(finals[0][0], finals[1][0], rtol=2e-3, atol=2e-3)
+    torch.testing.assert_close(finals[0][1], finals[1][1], rtol=0, atol=1e-6)
 
 
 def test_full_size_step_properties():
