@@ -30,6 +30,8 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 CONFIG = os.path.join(ROOT, "tests", "golden", "configs", "model12.config")
+WORKLOAD = ("Faster R-CNN ResNet-101 + 3 aux heads + refiner, model12.config, 600x1000, "
+            "train step (fwd+bwd+allreduce+clip+momentum)")
 H, W = 600, 1000
 
 
@@ -151,8 +153,8 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": "images/sec", "value": value, "unit": "images/sec", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / value, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "Faster R-CNN ResNet-101 + 3 aux heads + refiner, model12.config, 600x1000, "
-                                   "CPU restatement"},
+            "config": {"workload": WORKLOAD, "global_batch": 1, "per_gpu_batch": 1, "parallelism": "cpu",
+                       "note": "fp32 CPU restatement of the same step (oracle/model.py), one image per step"},
             "cpu_baseline": {"value": value, "unit": "images/sec", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -305,8 +307,7 @@ def run_ours(args, rank, world, local_rank):
         "metric": "images/sec", "value": value, "unit": "images/sec", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "Faster R-CNN ResNet-101 + 3 aux heads + refiner, model12.config, 600x1000, "
-                               "train step (fwd+bwd+allreduce+clip+momentum)",
+        "config": {"workload": WORKLOAD,
                    "global_batch": B * world, "per_gpu_batch": B, "parallelism": "dp%d" % world,
                    "l2_flush": "none needed: one step touches %.1f GB of activations+weights (>> 126 MB L2)"
                                % ((model.workspace.nbytes() + st.total * 14) / 1e9),
