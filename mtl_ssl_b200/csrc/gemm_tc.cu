@@ -1450,7 +1450,13 @@ extern "C" int mtl_conv_tc(const mtl_conv_args* a, cudaStream_t stream) {
     int splits = a->force_splits;
     if (splits <= 0) {
       // minimise waves x (K iterations per CTA + drain cost): never spill a few tiles into a second wave
-      const int sms = mtl_num_sms(), drain = bn / 48 + 1;
+      // short reductions (the trunk at batch 1) run beside the latency-bound dgrad chain that feeds them: leave
+      // that chain its SMs instead of grabbing the whole machine for a few microseconds (MTL_WGRAD_SMALL_CTAS)
+      // measured on the full step: 7.51 -> 7.37 ms with a cap anywhere in 32..72; 0 switches it off
+      static const int small_cap = getenv("MTL_WGRAD_SMALL_CTAS") ? atoi(getenv("MTL_WGRAD_SMALL_CTAS")) : 64;
+      const int sms = (small_cap > 0 && p.k_iters <= 64) ? (small_cap < mtl_num_sms() ? small_cap : mtl_num_sms())
+                                                         : mtl_num_sms();
+      const int drain = bn / 48 + 1;
       long long best = -1;
       splits = 1;
       for (int sp = 1; sp <= p.k_iters && sp <= 64 && (sp == 1 || tiles * sp <= 2 * sms); ++sp) {
