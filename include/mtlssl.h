@@ -62,6 +62,7 @@ typedef struct mtl_conv_args {
   void* ws;                 /* fprop/dgrad split-K workspace (zero filled; left zeroed) or NULL = never split */
   long long ws_bytes;
   int force_cluster;        /* 0 auto, 1 never, 2 always: CTA pairs sharing multicast weight tiles (fprop/dgrad) */
+  int max_ctas;             /* 0 = whole GPU; else size the persistent grid for this many SMs (overlapped side work) */
 } mtl_conv_args;
 int mtl_conv_tc(const mtl_conv_args* args /* host */, mtl_stream_t stream);
 /* bytes of zeroed workspace mtl_conv_tc would use to split the K loop of this fprop/dgrad (0 = no split) */

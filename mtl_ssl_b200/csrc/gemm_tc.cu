@@ -62,6 +62,7 @@ struct Params {
   int res_slots;             // per epilogue warp: 32x32 residual(+mask) tiles kept in flight by TMA
   int epi_warp_bytes;        // per epilogue warp: 2 output staging tiles + res_slots * slot bytes
   int cluster;               // 2: CTA pairs with multicast weight tiles (host-side dispatch only)
+  int max_ctas;              // host-side: grid cap (0 = number of SMs)
   float* ws;                 // FPROP/DGRAD split-K: fp32 partial-sum tiles [tiles_m*tiles_n][BN/4][BM][4], all zero between launches
   int* ws_cnt;               // FPROP/DGRAD split-K: arrival counter per output tile, zero between launches
 };
@@ -1218,7 +1219,8 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensor
     grid = 2 * clusters;
   } else {
     const int total = p.tiles_m * p.tiles_n * p.splits;
-    grid = total < mtl_num_sms() ? total : mtl_num_sms();
+    const int cap = (p.max_ctas > 0 && p.max_ctas < mtl_num_sms()) ? p.max_ctas : mtl_num_sms();
+    grid = total < cap ? total : cap;
   }
   static const bool no_pdl = getenv("MTL_NO_PDL") != nullptr;
   cudaLaunchConfig_t cfg;
@@ -1361,6 +1363,8 @@ struct mtl_conv_args {
   void* ws;                 // fprop/dgrad split-K workspace (all zero between launches) or null
   long long ws_bytes;
   int force_cluster;        // 0 auto, 1 never pair CTAs, 2 pair CTAs (fprop/dgrad with TMA operands)
+  int max_ctas;             // 0 = whole GPU; otherwise the persistent grid (and wgrad's split-K) is sized for this many
+                            // SMs: work that overlaps a latency-bound chain on another stream leaves it room
 };
 
 extern "C" int mtl_conv_tc(const mtl_conv_args* a, cudaStream_t stream) {
@@ -1379,7 +1383,7 @@ extern "C" int mtl_conv_tc(const mtl_conv_args* a, cudaStream_t stream) {
   p.out = a->out; p.out_fp32 = a->out_fp32; p.bias = a->bias; p.rowscale = a->rowscale;
   p.res = a->res; p.res_fp32 = a->res_fp32; p.mask = reinterpret_cast<const bf16*>(a->mask);
   p.relu = a->relu; p.mask_hi = a->mask_hi; p.alpha = a->alpha;
-  p.bias_scale = a->bias_scale != 0.0f ? a->bias_scale : 1.0f; p.splits = 1; p.cluster = 1; p.taps = a->R * a->S;
+  p.bias_scale = a->bias_scale != 0.0f ? a->bias_scale : 1.0f; p.splits = 1; p.cluster = 1; p.max_ctas = a->max_ctas; p.taps = a->R * a->S;
   CUtensorMap tmA, tmB;
   memset(&tmA, 0, sizeof(tmA)); memset(&tmB, 0, sizeof(tmB));
   int bn, rc;
@@ -1454,8 +1458,9 @@ extern "C" int mtl_conv_tc(const mtl_conv_args* a, cudaStream_t stream) {
       // that chain its SMs instead of grabbing the whole machine for a few microseconds (MTL_WGRAD_SMALL_CTAS)
       // measured on the full step: 7.51 -> 7.37 ms with a cap anywhere in 32..72; 0 switches it off
       static const int small_cap = getenv("MTL_WGRAD_SMALL_CTAS") ? atoi(getenv("MTL_WGRAD_SMALL_CTAS")) : 64;
-      const int sms = (small_cap > 0 && p.k_iters <= 64) ? (small_cap < mtl_num_sms() ? small_cap : mtl_num_sms())
-                                                         : mtl_num_sms();
+      int sms = (small_cap > 0 && p.k_iters <= 64) ? (small_cap < mtl_num_sms() ? small_cap : mtl_num_sms())
+                                                   : mtl_num_sms();
+      if (a->max_ctas > 0 && a->max_ctas < sms) sms = a->max_ctas;
       const int drain = bn / 48 + 1;
       long long best = -1;
       splits = 1;

@@ -47,8 +47,14 @@ class ConvArgs(ctypes.Structure):
         ("dy_ld", ctypes.c_longlong), ("out_ld", ctypes.c_longlong), ("res_ld", ctypes.c_longlong),
         ("mask_ld", ctypes.c_longlong), ("bias_scale", ctypes.c_float),
         ("force_stages", ctypes.c_int), ("ws", ctypes.c_void_p), ("ws_bytes", ctypes.c_longlong),
-        ("force_cluster", ctypes.c_int),
+        ("force_cluster", ctypes.c_int), ("max_ctas", ctypes.c_int),
     ]
+
+
+# Grid cap applied to every conv launched while it is set (0 = whole GPU): side-stream work that overlaps a
+# latency-bound chain (the frozen-prefix look-ahead of the trainer) is sized to leave that chain its SMs.
+CTA_CAP = 0
+
 
 
 # Split-K workspaces (fprop / dgrad): one zero-filled fp32 buffer per CUDA stream -- launches on one stream
@@ -131,7 +137,7 @@ def conv_fprop(x, w, stride=1, pad=(0, 0), dil=1, out_hw=None, bias=None, res=No
     a.alpha = 1.0
     a.bias_scale = float(bias_scale)
     a.force_bn, a.force_splits, a.force_stages = force_bn, force_splits, force_stages
-    a.force_cluster = force_cluster
+    a.force_cluster, a.max_ctas = force_cluster, CTA_CAP
     _attach_ws(a)
     _launch(a, "mtl_conv_tc(fprop)")
     return out
@@ -162,7 +168,7 @@ def conv_dgrad(dy, w, x_shape, stride=1, pad=(0, 0), dil=1, res=None, mask=None,
         a.mask_hi = float(mask_hi)
     a.alpha = 1.0
     a.force_bn, a.force_splits, a.force_stages = force_bn, force_splits, force_stages
-    a.force_cluster = force_cluster
+    a.force_cluster, a.max_ctas = force_cluster, CTA_CAP
     _attach_ws(a)
     _launch(a, "mtl_conv_tc(dgrad)")
     return out
@@ -185,5 +191,6 @@ def conv_wgrad(dy, x, dw, stride=1, pad=(0, 0), dil=1, rowscale=None, alpha=1.0,
     a.alpha = float(alpha)
     a.force_bn = force_bn
     a.force_splits = force_splits
+    a.max_ctas = CTA_CAP
     _launch(a, "mtl_conv_tc(wgrad)")
     return dw

@@ -170,7 +170,16 @@ class Trainer(object):
     # pass ("prefix"), into their own buffers, and handed over by one device-to-device copy at the step start.
     def _prefix(self, image, tag="s1"):
         m = self.model
-        return m.frozen_prefix(m.preprocess(image), tag)
+        if tag == "s1":
+            return m.frozen_prefix(m.preprocess(image), tag)
+        # look-ahead pass: runs beside the current step's main chain, on a share of the SMs
+        from . import ops_conv
+        import os
+        old, ops_conv.CTA_CAP = ops_conv.CTA_CAP, int(os.environ.get("MTL_PREFIX_CTAS", "0"))
+        try:
+            return m.frozen_prefix(m.preprocess(image), tag)
+        finally:
+            ops_conv.CTA_CAP = old
 
     def _forward_backward(self, image, prefix=None):
         m = self.model
