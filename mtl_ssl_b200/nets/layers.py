@@ -20,7 +20,7 @@ class Concurrency(object):
     optimizer), so they are launched on side streams and overlap the dgrad chain.  Under CUDA-graph
     capture the stream waits become graph edges, i.e. the captured step keeps the concurrency."""
     enabled = True
-    num_streams = 2
+    num_streams = int(__import__("os").environ.get("MTL_WGRAD_STREAMS", "4"))
     _streams = None
     _idx = 0
 
