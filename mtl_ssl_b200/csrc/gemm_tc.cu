@@ -1454,11 +1454,13 @@ extern "C" int mtl_conv_tc(const mtl_conv_args* a, cudaStream_t stream) {
     int splits = a->force_splits;
     if (splits <= 0) {
       // minimise waves x (K iterations per CTA + drain cost): never spill a few tiles into a second wave
-      // short reductions (the trunk at batch 1) run beside the latency-bound dgrad chain that feeds them: leave
+      // reductions of up to 256 K steps (the trunk at batch 1, the 64- and 256-ROI tails) run beside the dgrad chain
+      // that feeds them: leave
       // that chain its SMs instead of grabbing the whole machine for a few microseconds (MTL_WGRAD_SMALL_CTAS)
       // measured on the full step: 7.51 -> 7.37 ms with a cap anywhere in 32..72; 0 switches it off
       static const int small_cap = getenv("MTL_WGRAD_SMALL_CTAS") ? atoi(getenv("MTL_WGRAD_SMALL_CTAS")) : 64;
-      int sms = (small_cap > 0 && p.k_iters <= 64) ? (small_cap < mtl_num_sms() ? small_cap : mtl_num_sms())
+      static const int small_k = getenv("MTL_WGRAD_SMALL_K") ? atoi(getenv("MTL_WGRAD_SMALL_K")) : 256;
+      int sms = (small_cap > 0 && p.k_iters <= small_k) ? (small_cap < mtl_num_sms() ? small_cap : mtl_num_sms())
                                                    : mtl_num_sms();
       if (a->max_ctas > 0 && a->max_ctas < sms) sms = a->max_ctas;
       const int drain = bn / 48 + 1;
