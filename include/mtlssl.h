@@ -94,6 +94,23 @@ int mtl_nms(const float* boxes /* [B,N,4] */, const float* scores /* [B,N] or NU
             float* out_scores /* [B,max] or NULL */, int* out_idx /* [B,max] or NULL */, int* num_out /* [B] */,
             mtl_stream_t stream);
 
+/* ---- second-stage detections (meta_architectures/faster_rcnn_meta_arch.py:1387-1469,
+ *      core/post_processing.py:25-312).  mtl_detection_decode produces the per-(image, class) NMS inputs in
+ *      class-major layout [B,K,P]; mtl_rank_sort_desc + mtl_nms run with B*K as their batch; the two functions
+ *      below merge the per-class survivors and keep the top max_total detections (zero padded). ------------- */
+int mtl_detection_decode(const float* box_encodings /* [B*P,K,4] */, const float* class_logits /* [B*P,K+1] */,
+                         const float* proposals /* [B,P,4] abs */, const int* num_proposals /* [B] */, int B, int P,
+                         int K, float img_h, float img_w, float score_thresh, int score_mode /* 0 id, 1 softmax, 2 sigmoid */,
+                         float* boxes_norm /* [B,K,P,4] clipped, window frame */, float* scores /* [B,K,P] */,
+                         unsigned long long* keys /* [B,K,P] */, float* decoded_abs /* [B,K,P,4] or NULL */,
+                         mtl_stream_t stream);
+int mtl_detection_merge_keys(const float* cls_scores /* [B,K,M] */, const int* cls_num /* [B,K] */, int B, int K, int M,
+                             unsigned long long* keys /* [B,K*M] */, mtl_stream_t stream);
+int mtl_detection_gather(const float* cls_boxes /* [B,K,M,4] */, const float* cls_scores /* [B,K,M] */,
+                         const int* order /* [B,K*M] */, const int* num_valid /* [B] */, int B, int K, int M, int T,
+                         float* det_boxes /* [B,T,4] */, float* det_scores /* [B,T] */, float* det_classes /* [B,T] */,
+                         float* num_detections /* [B] */, mtl_stream_t stream);
+
 /* ---- matching / sampling / targets (core/region_similarity_calculator.py:57-74,
  *      matchers/argmax_matcher.py:102-175, core/target_assigner.py:99-213,
  *      core/balanced_positive_negative_sampler.py:50-91) ----------------------------------- */

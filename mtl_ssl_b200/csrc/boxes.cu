@@ -143,6 +143,92 @@ __global__ void rpn_decode_kernel(const float* __restrict__ rpn_out, long long l
   keys[o] = valid ? (((u64)__float_as_uint(sc) << 32) | (u64)(0xffffffffu - (unsigned)j)) : 0ull;
 }
 
+// ------------------------------------------------------------------ second-stage detections
+// meta_architectures/faster_rcnn_meta_arch.py:1387-1469 (_postprocess_box_classifier) up to the per-class NMS
+// input: decode the per-class refined encodings against the proposals (box coder :92-118), convert the class
+// logits (SOFTMAX / SIGMOID / IDENTITY), drop the background column, then per class (post_processing.py:106-143)
+// filter score > threshold, clip to the image window, drop zero-area boxes, change to the window frame.
+// Layout out: class-major [B, K, P] so that (image, class) pairs are the batch dimension of the NMS kernels.
+__global__ void detection_decode_kernel(const float* __restrict__ enc, const float* __restrict__ logits,
+                                        const float4* __restrict__ proposals, const int* __restrict__ num_props,
+                                        int P, int K, float img_h, float img_w, float score_thresh, int score_mode,
+                                        float4* __restrict__ boxes_n, float* __restrict__ scores,
+                                        u64* __restrict__ keys, float4* __restrict__ decoded_abs) {
+  const int b = blockIdx.z, k = blockIdx.y;
+  const int pidx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pidx >= P) return;
+  const long long r = (long long)b * P + pidx;                 // row of the [B*P, ...] head outputs
+  const float4 an = proposals[r];
+  const float wa = an.w - an.y, ha = an.z - an.x;
+  const float yca = an.x + ha / 2.0f, xca = an.y + wa / 2.0f;
+  const float* e = enc + (r * K + k) * 4;
+  const float ty = e[0] / 10.0f, tx = e[1] / 10.0f, th = e[2] / 5.0f, tw = e[3] / 5.0f;
+  const float w = expf(tw) * wa, h = expf(th) * ha;
+  const float yc = ty * ha + yca, xc = tx * wa + xca;
+  float ymin = yc - h / 2.0f, xmin = xc - w / 2.0f, ymax = yc + h / 2.0f, xmax = xc + w / 2.0f;
+  const long long o = ((long long)b * K + k) * P + pidx;
+  if (decoded_abs) decoded_abs[o] = make_float4(ymin, xmin, ymax, xmax);
+  const float* l = logits + r * (K + 1);
+  float sc;
+  if (score_mode == 1) {                 // SOFTMAX over background + classes
+    float m = l[0];
+    for (int c = 1; c <= K; ++c) m = fmaxf(m, l[c]);
+    float sum = 0.0f;
+    for (int c = 0; c <= K; ++c) sum += expf(l[c] - m);
+    sc = expf(l[k + 1] - m) / sum;
+  } else if (score_mode == 2) {          // SIGMOID
+    sc = 1.0f / (1.0f + expf(-l[k + 1]));
+  } else {
+    sc = l[k + 1];
+  }
+  ymin = fmaxf(fminf(ymin, img_h), 0.0f);
+  ymax = fmaxf(fminf(ymax, img_h), 0.0f);
+  xmin = fmaxf(fminf(xmin, img_w), 0.0f);
+  xmax = fmaxf(fminf(xmax, img_w), 0.0f);
+  const float area = (ymax - ymin) * (xmax - xmin);
+  const bool valid = pidx < num_props[b] && sc > score_thresh && area > 0.0f;
+  boxes_n[o] = make_float4(ymin / img_h, xmin / img_w, ymax / img_h, xmax / img_w);
+  scores[o] = sc;
+  keys[o] = valid ? (((u64)__float_as_uint(sc) << 32) | (u64)(0xffffffffu - (unsigned)pidx)) : 0ull;
+}
+
+// concatenate the per-class NMS survivors in class order (post_processing.py:144-148): key of candidate
+// (class k, rank r) = (score, position k*M + r) so that sort_by_field's ties keep the concatenation order
+__global__ void detection_merge_keys_kernel(const float* __restrict__ cls_scores, const int* __restrict__ cls_num,
+                                            int K, int M, u64* __restrict__ keys) {
+  const int b = blockIdx.y;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= K * M) return;
+  const int k = j / M, r = j - k * M;
+  const bool valid = r < cls_num[b * K + k];
+  const float sc = cls_scores[((long long)b * K + k) * M + r];
+  keys[(long long)b * K * M + j] = valid ? (((u64)__float_as_uint(sc) << 32) | (u64)(0xffffffffu - (unsigned)j)) : 0ull;
+}
+
+// top max_total of the merged list, zero padded (post_processing.py:149-164, :281-312)
+__global__ void detection_gather_kernel(const float4* __restrict__ cls_boxes, const float* __restrict__ cls_scores,
+                                        const int* __restrict__ order, const int* __restrict__ num_valid, int K,
+                                        int M, int T, float4* __restrict__ det_boxes, float* __restrict__ det_scores,
+                                        float* __restrict__ det_classes, float* __restrict__ num_det) {
+  const int b = blockIdx.y;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = min(num_valid[b], T);
+  if (t == 0) num_det[b] = (float)n;
+  if (t >= T) return;
+  const long long o = (long long)b * T + t;
+  if (t < n) {
+    const int j = order[(long long)b * K * M + t];
+    const long long src = (long long)b * K * M + j;
+    det_boxes[o] = cls_boxes[src];
+    det_scores[o] = cls_scores[src];
+    det_classes[o] = (float)(j / M);
+  } else {
+    det_boxes[o] = make_float4(0, 0, 0, 0);
+    det_scores[o] = 0.0f;
+    det_classes[o] = 0.0f;
+  }
+}
+
 // score/box inputs that are already decoded (generic NMS front end): key construction only
 __global__ void make_keys_kernel(const float4* __restrict__ boxes, const float* __restrict__ scores, int N,
                                  float score_thresh, int require_area, u64* __restrict__ keys) {
@@ -739,6 +825,47 @@ extern "C" int mtl_nms(const float* boxes, const float* scores, const int* order
                                             iou_thresh, max_out, reinterpret_cast<float4*>(out_boxes), out_scores,
                                             out_idx, num_out);
   MTL_CUDA_LAUNCH_CHECK("nms_kernel");
+  return MTL_OK;
+}
+
+extern "C" int mtl_detection_decode(const float* box_encodings, const float* class_logits, const float* proposals,
+                                    const int* num_proposals, int B, int P, int K, float img_h, float img_w,
+                                    float score_thresh, int score_mode, float* boxes_norm, float* scores,
+                                    unsigned long long* keys, float* decoded_abs, cudaStream_t stream) {
+  MTL_CHECK_ARG(box_encodings && class_logits && proposals && num_proposals && boxes_norm && scores && keys,
+                "mtl_detection_decode: null tensor");
+  MTL_CHECK_ARG(B > 0 && P > 0 && K > 0 && K < 65536 && B < 65536, "mtl_detection_decode: bad shape");
+  MTL_CHECK_ARG(score_mode >= 0 && score_mode <= 2, "mtl_detection_decode: score_mode 0 identity, 1 softmax, 2 sigmoid");
+  dim3 grid(ceil_div(P, 128), K, B);
+  detection_decode_kernel<<<grid, 128, 0, stream>>>(box_encodings, class_logits,
+                                                    reinterpret_cast<const float4*>(proposals), num_proposals, P, K,
+                                                    img_h, img_w, score_thresh, score_mode,
+                                                    reinterpret_cast<float4*>(boxes_norm), scores, keys,
+                                                    reinterpret_cast<float4*>(decoded_abs));
+  MTL_CUDA_LAUNCH_CHECK("detection_decode_kernel");
+  return MTL_OK;
+}
+
+extern "C" int mtl_detection_merge_keys(const float* cls_scores, const int* cls_num, int B, int K, int M,
+                                        unsigned long long* keys, cudaStream_t stream) {
+  MTL_CHECK_ARG(cls_scores && cls_num && keys && B > 0 && K > 0 && M > 0, "mtl_detection_merge_keys: bad args");
+  dim3 grid(ceil_div(K * M, 256), B);
+  detection_merge_keys_kernel<<<grid, 256, 0, stream>>>(cls_scores, cls_num, K, M, keys);
+  MTL_CUDA_LAUNCH_CHECK("detection_merge_keys_kernel");
+  return MTL_OK;
+}
+
+extern "C" int mtl_detection_gather(const float* cls_boxes, const float* cls_scores, const int* order,
+                                    const int* num_valid, int B, int K, int M, int T, float* det_boxes,
+                                    float* det_scores, float* det_classes, float* num_detections,
+                                    cudaStream_t stream) {
+  MTL_CHECK_ARG(cls_boxes && cls_scores && order && num_valid && det_boxes && det_scores && det_classes &&
+                num_detections && B > 0 && K > 0 && M > 0 && T > 0, "mtl_detection_gather: bad args");
+  dim3 grid(ceil_div(T, 128), B);
+  detection_gather_kernel<<<grid, 128, 0, stream>>>(reinterpret_cast<const float4*>(cls_boxes), cls_scores, order,
+                                                    num_valid, K, M, T, reinterpret_cast<float4*>(det_boxes),
+                                                    det_scores, det_classes, num_detections);
+  MTL_CUDA_LAUNCH_CHECK("detection_gather_kernel");
   return MTL_OK;
 }
 

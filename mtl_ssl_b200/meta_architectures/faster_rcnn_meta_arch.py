@@ -625,6 +625,53 @@ class FasterRCNNMetaArch(model.DetectionModel):
                 loss_dict[k] = losses[i]
         return loss_dict
 
+    # ------------------------------------------------------------------ detections
+    def postprocess(self, prediction_dict):
+        """fmA:996-1053 second-stage branch -> `_postprocess_box_classifier` (fmA:1387-1469): decode the refined
+        per-class boxes against the proposals, convert the class scores, per-class NMS
+        (`second_stage_post_processing.batch_non_max_suppression`), top `max_total_detections`, zero padded.
+        Returns detection_boxes [B,T,4] (normalised to the image), detection_scores, detection_classes
+        (0-based, float32) [B,T] and num_detections [B] (float32), all device tensors."""
+        if self._first_stage_only:
+            raise NotImplementedError("postprocess of first_stage_only models (RPN proposals) is not built yet")
+        pd, ws = prediction_dict, self._ws
+        nms_cfg = self._second_stage_nms_fn
+        mode = {"IDENTITY": 0, "SOFTMAX": 1, "SIGMOID": 2}[str(self._second_stage_score_conversion_fn)]
+        enc = pd["refined_box_encodings"].contiguous().float()
+        logits = pd["class_predictions_with_background"].contiguous().float()
+        props = pd["proposal_boxes"]
+        B, P = props.shape[0], props.shape[1]
+        K = self.num_classes
+        H, W = pd["image_shape"][1], pd["image_shape"][2]
+        M = min(int(nms_cfg.max_detections_per_class), P)
+        T = int(nms_cfg.max_total_detections)
+        f32, i32 = torch.float32, torch.int32
+        boxes_n = ws.get("det_pp/boxes", (B, K, P, 4), f32)
+        scores = ws.get("det_pp/scores", (B, K, P), f32)
+        keys = ws.get("det_pp/keys", (B, K, P), torch.int64)
+        ops.call("mtl_detection_decode", enc, logits, props, pd["num_proposals"], B, P, K, float(H), float(W),
+                 float(nms_cfg.score_threshold), mode, boxes_n, scores, keys, None)
+        order = ws.get("det_pp/order", (B * K, P), i32)
+        nvalid = ws.get("det_pp/nvalid", (B * K,), i32)
+        ops.call("mtl_rank_sort_desc", keys, B * K, P, order, nvalid, ws.get("det_pp/rank_ws", (B * K, P), i32))
+        cls_b = ws.get("det_pp/cls_boxes", (B, K, M, 4), f32)
+        cls_s = ws.get("det_pp/cls_scores", (B, K, M), f32)
+        cls_n = ws.get("det_pp/cls_num", (B * K,), i32)
+        ops.call("mtl_nms", boxes_n, scores, order, nvalid, B * K, P, float(nms_cfg.iou_threshold), M, cls_b, cls_s,
+                 None, cls_n)
+        keys2 = ws.get("det_pp/keys2", (B, K * M), torch.int64)
+        ops.call("mtl_detection_merge_keys", cls_s, cls_n, B, K, M, keys2)
+        order2 = ws.get("det_pp/order2", (B, K * M), i32)
+        nvalid2 = ws.get("det_pp/nvalid2", (B,), i32)
+        ops.call("mtl_rank_sort_desc", keys2, B, K * M, order2, nvalid2, ws.get("det_pp/rank_ws2", (B, K * M), i32))
+        det_b = ws.get("det_pp/det_boxes", (B, T, 4), f32)
+        det_s = ws.get("det_pp/det_scores", (B, T), f32)
+        det_c = ws.get("det_pp/det_classes", (B, T), f32)
+        det_n = ws.get("det_pp/num_detections", (B,), f32)
+        ops.call("mtl_detection_gather", cls_b, cls_s, order2, nvalid2, B, K, M, T, det_b, det_s, det_c, det_n)
+        return {"detection_boxes": det_b, "detection_scores": det_s, "detection_classes": det_c,
+                "num_detections": det_n}
+
     # ------------------------------------------------------------------ backward
     def backward(self, prediction_dict=None, part=None):
         """Explicit reverse pass: accumulates d(sum of task losses)/d(weights) into the gradient

@@ -139,3 +139,47 @@ def multiclass_non_max_suppression(boxes, scores, score_thresh, iou_thresh, max_
     if max_total_size:
         order = order[:max_total_size]
     return ob[order], os_[order], oc[order]
+
+
+def second_stage_postprocess(refined_box_encodings, class_logits, proposal_boxes, num_proposals, image_hw,
+                             score_thresh, iou_thresh, max_per_class, max_total, score_mode="softmax",
+                             decoded=None, scores=None):
+    """meta_architectures/faster_rcnn_meta_arch.py:1387-1469 (`_postprocess_box_classifier`) +
+    core/post_processing.py:167-312 (`batch_multiclass_non_max_suppression` with clip_window = image,
+    change_coordinate_frame=True, num_valid_boxes = num_proposals): per image decode the [P,K,4] refined encodings
+    against the proposals (`_batch_decode_boxes`, fmA:1471-1497), convert the logits, drop the background column,
+    run the per-class NMS and zero-pad to `max_total`.
+    `decoded` [B,P,K,4] / `scores` [B,P,K]: use these instead of recomputing them (index-level device parity)."""
+    enc = np.asarray(refined_box_encodings, F)
+    logits = np.asarray(class_logits, F)
+    props = np.asarray(proposal_boxes, F)
+    Bn, P = props.shape[0], props.shape[1]
+    K = enc.shape[1]
+    enc = enc.reshape(Bn, P, K, 4)
+    logits = logits.reshape(Bn, P, K + 1)
+    if decoded is None:
+        decoded = np.zeros((Bn, P, K, 4), F)
+        for b in range(Bn):
+            for k in range(K):
+                decoded[b, :, k] = B.box_decode(enc[b, :, k], props[b])
+    if scores is None:
+        if score_mode == "softmax":
+            conv = softmax(logits, -1)
+        elif score_mode == "sigmoid":
+            conv = (F(1) / (F(1) + np.exp(-logits))).astype(F)
+        else:
+            conv = logits
+        scores = conv[:, :, 1:]
+    H, W = image_hw
+    out_b = np.zeros((Bn, max_total, 4), F)
+    out_s = np.zeros((Bn, max_total), F)
+    out_c = np.zeros((Bn, max_total), F)
+    out_n = np.zeros((Bn,), F)
+    for b in range(Bn):
+        n = int(num_proposals[b])
+        bb, ss, cc = multiclass_non_max_suppression(decoded[b, :n], scores[b, :n], score_thresh, iou_thresh,
+                                                    max_per_class, max_total, clip_window=(0, 0, H, W),
+                                                    change_coordinate_frame=True)
+        m = len(ss)
+        out_b[b, :m], out_s[b, :m], out_c[b, :m], out_n[b] = bb, ss, cc, m
+    return out_b, out_s, out_c, out_n

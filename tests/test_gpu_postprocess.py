@@ -1,0 +1,116 @@
+"""GPU parity of the second-stage detection path (first slice: `postprocess` of
+meta_architectures/faster_rcnn_meta_arch.py:996-1053 / :1387-1469 + core/post_processing.py:25-312) through the C ABI:
+decode / score conversion against the oracle to fp32 rounding, then -- on the device's own decoded boxes and
+scores -- per-class NMS, merge and top-k bit-exact against oracle/postprocess.py."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _inputs(seed, B, P, K, H, W):
+    rng = np.random.default_rng(seed)
+    props = np.zeros((B, P, 4), np.float32)
+    y0, x0 = rng.uniform(0, H * 0.8, (B, P)), rng.uniform(0, W * 0.8, (B, P))
+    props[..., 0], props[..., 1] = y0, x0
+    props[..., 2], props[..., 3] = y0 + rng.uniform(4, H * 0.5, (B, P)), x0 + rng.uniform(4, W * 0.5, (B, P))
+    enc = rng.normal(0, 1.5, (B * P, K, 4)).astype(np.float32)
+    logits = rng.normal(0, 2.0, (B * P, K + 1)).astype(np.float32)
+    return props, enc, logits
+
+
+@pytest.mark.parametrize("B,P,K,nprop,mode", [(2, 64, 5, (64, 40), 1), (1, 256, 20, (199,), 1), (3, 33, 3, (33, 1, 0), 2)])
+def test_detection_chain_matches_oracle(B, P, K, nprop, mode):
+    from mtl_ssl_b200 import ops
+    from oracle import postprocess as PP
+    from oracle import boxes as OB
+    H, W, thr, iou, M, T = 200.0, 300.0, 0.05, 0.4, 10, 30
+    props, enc, logits = _inputs(B * 100 + P, B, P, K, H, W)
+    dev = "cuda"
+    t = lambda a, dt=None: torch.from_numpy(np.ascontiguousarray(a)).to(dev) if dt is None else torch.from_numpy(a).to(dev, dt)
+    d_props, d_enc, d_logits = t(props), t(enc), t(logits)
+    d_np = torch.tensor(nprop, dtype=torch.int32, device=dev)
+    boxes_n = torch.empty(B, K, P, 4, device=dev)
+    scores = torch.empty(B, K, P, device=dev)
+    keys = torch.empty(B, K, P, dtype=torch.int64, device=dev)
+    dec = torch.empty(B, K, P, 4, device=dev)
+    ops.call("mtl_detection_decode", d_enc, d_logits, d_props, d_np, B, P, K, H, W, thr, mode, boxes_n, scores, keys, dec)
+    # --- stage 1: decode + score conversion vs the oracle (exp / softmax to fp32 rounding)
+    dec_h = dec.cpu().numpy().transpose(0, 2, 1, 3)            # [B,P,K,4]
+    sc_h = scores.cpu().numpy().transpose(0, 2, 1)             # [B,P,K]
+    for b in range(B):
+        for k in range(K):
+            want = OB.box_decode(enc.reshape(B, P, K, 4)[b, :, k], props[b])
+            np.testing.assert_allclose(dec_h[b, :, k], want, rtol=2e-6, atol=1e-3)
+    lg = logits.reshape(B, P, K + 1)
+    want_s = PP.softmax(lg)[..., 1:] if mode == 1 else 1.0 / (1.0 + np.exp(-lg[..., 1:]))
+    np.testing.assert_allclose(sc_h, want_s, rtol=2e-6, atol=1e-7)
+    # --- stage 2: NMS / merge / top-k, index exact on the device's own boxes and scores
+    order = torch.empty(B * K, P, dtype=torch.int32, device=dev)
+    nvalid = torch.empty(B * K, dtype=torch.int32, device=dev)
+    ops.call("mtl_rank_sort_desc", keys, B * K, P, order, nvalid, torch.empty(B * K, P, dtype=torch.int32, device=dev))
+    cls_b = torch.empty(B, K, M, 4, device=dev)
+    cls_s = torch.empty(B, K, M, device=dev)
+    cls_n = torch.empty(B * K, dtype=torch.int32, device=dev)
+    ops.call("mtl_nms", boxes_n, scores, order, nvalid, B * K, P, iou, M, cls_b, cls_s, None, cls_n)
+    keys2 = torch.empty(B, K * M, dtype=torch.int64, device=dev)
+    ops.call("mtl_detection_merge_keys", cls_s, cls_n, B, K, M, keys2)
+    order2 = torch.empty(B, K * M, dtype=torch.int32, device=dev)
+    nvalid2 = torch.empty(B, dtype=torch.int32, device=dev)
+    ops.call("mtl_rank_sort_desc", keys2, B, K * M, order2, nvalid2, torch.empty(B, K * M, dtype=torch.int32, device=dev))
+    det_b = torch.empty(B, T, 4, device=dev)
+    det_s = torch.empty(B, T, device=dev)
+    det_c = torch.empty(B, T, device=dev)
+    det_n = torch.empty(B, device=dev)
+    ops.call("mtl_detection_gather", cls_b, cls_s, order2, nvalid2, B, K, M, T, det_b, det_s, det_c, det_n)
+    wb, ws_, wc, wn = PP.second_stage_postprocess(enc, logits, props, list(nprop), (H, W), thr, iou, M, T,
+                                                  decoded=dec_h, scores=sc_h)
+    assert np.array_equal(det_n.cpu().numpy(), wn), (det_n.cpu().numpy(), wn)
+    assert np.array_equal(det_c.cpu().numpy(), wc)
+    assert np.array_equal(det_s.cpu().numpy(), ws_)
+    assert np.array_equal(det_b.cpu().numpy(), wb)
+
+
+def test_meta_arch_postprocess_after_forward():
+    """model.postprocess(prediction_dict) on a real forward pass equals the oracle bit for bit when the oracle is fed the
+    device's decoded boxes / converted scores (a random-init head gives near-equal scores, so recomputing exp() on the
+    host could legitimately reorder neighbours)."""
+    import test_gpu_train_step as T
+    from mtl_ssl_b200 import ops
+    from oracle import postprocess as PP
+    H, W = 224, 320
+    cfg, model, sd, examples, keys, tr = T._setup("model12.config", T.SMALL, H, W, 1)
+    arrays = tr.host_arrays(examples, keys)
+    image = tr._bind(arrays)
+    pd = model.predict(model.preprocess(image))
+    det = model.postprocess(pd)
+    torch.cuda.synchronize()
+    nms = cfg.model.faster_rcnn.second_stage_post_processing.batch_non_max_suppression
+    enc = pd["refined_box_encodings"].contiguous().float()
+    logits = pd["class_predictions_with_background"].contiguous().float()
+    props, nprop = pd["proposal_boxes"], pd["num_proposals"]
+    B, P, K = props.shape[0], props.shape[1], model.num_classes
+    M, Tt = min(nms.max_detections_per_class, P), nms.max_total_detections
+    dev = enc.device
+    boxes_n = torch.empty(B, K, P, 4, device=dev)
+    scores = torch.empty(B, K, P, device=dev)
+    k64 = torch.empty(B, K, P, dtype=torch.int64, device=dev)
+    dec = torch.empty(B, K, P, 4, device=dev)
+    ops.call("mtl_detection_decode", enc, logits, props, nprop, B, P, K, float(H), float(W), float(nms.score_threshold),
+             1, boxes_n, scores, k64, dec)
+    wb, ws_, wc, wn = PP.second_stage_postprocess(
+        enc.cpu().numpy(), logits.cpu().numpy(), props.cpu().numpy(), nprop.cpu().numpy(), (H, W), nms.score_threshold,
+        nms.iou_threshold, M, Tt, decoded=dec.cpu().numpy().transpose(0, 2, 1, 3),
+        scores=scores.cpu().numpy().transpose(0, 2, 1))
+    n = int(det["num_detections"][0].item())
+    assert det["detection_boxes"].shape == (1, Tt, 4)
+    assert 0 < n <= Tt
+    assert np.array_equal(det["num_detections"].cpu().numpy(), wn)
+    assert np.array_equal(det["detection_scores"].cpu().numpy(), ws_)
+    assert np.array_equal(det["detection_classes"].cpu().numpy(), wc)
+    assert np.array_equal(det["detection_boxes"].cpu().numpy(), wb)
+    s = det["detection_scores"][0].cpu().numpy()
+    b = det["detection_boxes"][0].cpu().numpy()
+    assert np.all(np.diff(s[:n]) <= 0) and not s[n:].any()
+    assert b[:n].min() >= 0 and b[:n].max() <= 1 and not b[n:].any()

@@ -303,3 +303,22 @@ def test_position_sensitive_equal_channels_and_single_bin():
     ref = ON.crop_and_resize(img2, torch.from_numpy(b6), torch.from_numpy(bi), (2, 2)).mean((1, 2))
     torch.testing.assert_close(got, ref)
     assert want.shape == (3, 1)
+
+
+def test_second_stage_postprocess_hand_case():
+    """fmA:1387-1469 + post_processing.py:25-164 on a case small enough to do by hand: zero encodings (decoded boxes ==
+    proposals), IDENTITY scores, threshold 0.25, IoU 0.5.  Class 0: A .9 keeps, B .8 suppressed by A (IoU 100/105),
+    C .3 keeps; class 1: only C .7 passes the threshold.  Merged by score: A/c0, C/c1, C/c0; boxes in the window frame."""
+    from oracle import postprocess as PP
+    props = np.array([[[0, 0, 10, 10], [0, 0, 10, 10.5], [20, 20, 30, 30]]], np.float32)
+    enc = np.zeros((3, 2, 4), np.float32)
+    logits = np.array([[0, .9, .1], [0, .8, .2], [0, .3, .7]], np.float32)
+    b, s, c, n = PP.second_stage_postprocess(enc, logits, props, [3], (40, 40), 0.25, 0.5, 10, 5, score_mode="identity")
+    assert n.tolist() == [3.0]
+    np.testing.assert_allclose(s[0], [.9, .7, .3, 0, 0])
+    assert c[0].tolist() == [0, 1, 0, 0, 0]
+    np.testing.assert_allclose(b[0, :3], np.array([[0, 0, 10, 10], [20, 20, 30, 30], [20, 20, 30, 30]], np.float32) / 40)
+    assert not b[0, 3:].any()
+    # num_valid_boxes: only the first proposal is valid -> one detection
+    b, s, c, n = PP.second_stage_postprocess(enc, logits, props, [1], (40, 40), 0.25, 0.5, 10, 5, score_mode="identity")
+    assert n.tolist() == [1.0] and s[0, 0] == np.float32(.9)
