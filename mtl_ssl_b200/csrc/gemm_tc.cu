@@ -9,13 +9,16 @@
 // (/root/reference/slim/nets/resnet_v1.py:107-126, resnet_utils.py:77-122); there is no
 // reference kernel to mirror, so the design below is new.
 //
-// Data path: weight / plain-matrix operands arrive by TMA (cp.async.bulk.tensor,
-// 128-byte swizzle) issued by one producer thread; im2col operands (3x3, strided,
-// padded, or transposed gathers) are staged into the same swizzled shared-memory
-// layout by four gather warps with 16-byte cp.async + zero fill.  One thread issues
-// tcgen05.mma (M=128, N=BN, K=16) into a double-buffered TMEM accumulator; four
-// epilogue warps drain it with tcgen05.ld and apply bias / residual / ReLU / mask
-// (FPROP, DGRAD) or a scaled fp32 red.global.add (WGRAD).
+// Data path: weight / plain-matrix operands arrive by TMA (cp.async.bulk.tensor, 128-byte swizzle) issued by
+// one producer thread from a division-free loop; stride-1 R x S filters use TMA im2col loads, strided / odd
+// geometries are staged into the same swizzled layout by four gather warps (16-byte cp.async + zero fill).
+// One thread issues tcgen05.mma (M=128, N=BN, K=16) into a double-buffered TMEM accumulator.  Eight epilogue
+// warps (two groups taking alternate 32-column chunks; four in the gather variants) drain it with
+// tcgen05.ld and apply bias / residual / ReLU / mask; bf16 outputs, residuals and masks move as 32 x 32
+// tiles through swizzled shared memory by TMA (stores, and a ring of prefetched loads), WGRAD's fp32 tile
+// leaves by TMA reduce-add.  Shared memory (operand stages vs. epilogue ring) is carved at launch time.
+// Optional schedules, off by default (see DESIGN.md 2 / profiles/r1_final.md): fp32-workspace split-K for
+// FPROP / DGRAD with a last-arriver epilogue; CTA pairs (clusters of 2) multicasting the weight tile.
 #include "common.cuh"
 #include <cuda.h>
 #include <stdlib.h>
