@@ -94,6 +94,15 @@ int mtl_nms(const float* boxes /* [B,N,4] */, const float* scores /* [B,N] or NU
             float* out_scores /* [B,max] or NULL */, int* out_idx /* [B,max] or NULL */, int* num_out /* [B] */,
             mtl_stream_t stream);
 
+/* ---- inference-time proposal path (fmA:586-590 anchors clipped, not pruned; fmA:1111-1131 the NMS output is
+ *      the proposal set, no minibatch sampling) ------------------------------------------------------------ */
+int mtl_clip_boxes(const float* boxes /* [N,4] */, int N, float wy0, float wx0, float wy1, float wx1,
+                   float* out /* [N,4] */, mtl_stream_t stream);
+int mtl_proposals_from_nms(const float* nms_boxes /* [B,M,4] */, const float* nms_scores /* [B,M] */,
+                           const int* nms_num /* [B] */, int B, int M, float img_h, float img_w,
+                           float* out_abs /* [B,M,4] */, float* out_norm /* [B,M,4] */,
+                           float* out_scores /* [B,M] or NULL */, int* num_out /* [B] */, mtl_stream_t stream);
+
 /* ---- second-stage detections (meta_architectures/faster_rcnn_meta_arch.py:1387-1469,
  *      core/post_processing.py:25-312).  mtl_detection_decode produces the per-(image, class) NMS inputs in
  *      class-major layout [B,K,P]; mtl_rank_sort_desc + mtl_nms run with B*K as their batch; the two functions

@@ -143,6 +143,39 @@ __global__ void rpn_decode_kernel(const float* __restrict__ rpn_out, long long l
   keys[o] = valid ? (((u64)__float_as_uint(sc) << 32) | (u64)(0xffffffffu - (unsigned)j)) : 0ull;
 }
 
+// ------------------------------------------------------------------ inference-time proposal path
+// fmA:586-590: anchors are clipped to the image window instead of pruned (box_list_ops.clip_to_window; every grid
+// anchor has its centre inside the image, so none is dropped).  One thread per box, run once per shape.
+__global__ void clip_boxes_kernel(const float4* __restrict__ boxes, int N, float wy0, float wx0, float wy1, float wx1,
+                                  float4* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const float4 b = boxes[i];
+  out[i] = make_float4(fmaxf(fminf(b.x, wy1), wy0), fmaxf(fminf(b.y, wx1), wx0), fmaxf(fminf(b.z, wy1), wy0),
+                       fmaxf(fminf(b.w, wx1), wx0));
+}
+
+// fmA:1111-1131 without the training-time minibatch sampling: the NMS output IS the proposal set (zero padded to
+// max_proposals); normalise by the image size (to_normalized_coordinates, check_range=False).
+__global__ void proposals_from_nms_kernel(const float4* __restrict__ nms_boxes, const float* __restrict__ nms_scores,
+                                          const int* __restrict__ nms_num, int M, float img_h, float img_w,
+                                          float4* __restrict__ out_abs, float4* __restrict__ out_norm,
+                                          float* __restrict__ out_scores, int* __restrict__ num_out) {
+  const int b = blockIdx.y;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j == 0) num_out[b] = nms_num[b];
+  if (j >= M) return;
+  const long long o = (long long)b * M + j;
+  // same arithmetic as the training path (gather_sampled): scale by the reciprocal, absolute = round trip
+  // (box_list_ops.to_normalized_coordinates / ops.normalized_to_image_coordinates, fmA:682-683, :1124-1131)
+  const float ys = 1.0f / img_h, xs = 1.0f / img_w;
+  const float4 v = nms_boxes[o];
+  const float4 nr = make_float4(ys * v.x, xs * v.y, ys * v.z, xs * v.w);
+  out_norm[o] = nr;
+  out_abs[o] = make_float4(img_h * nr.x, img_w * nr.y, img_h * nr.z, img_w * nr.w);
+  if (out_scores) out_scores[o] = nms_scores[o];
+}
+
 // ------------------------------------------------------------------ second-stage detections
 // meta_architectures/faster_rcnn_meta_arch.py:1387-1469 (_postprocess_box_classifier) up to the per-class NMS
 // input: decode the per-class refined encodings against the proposals (box coder :92-118), convert the class
@@ -825,6 +858,29 @@ extern "C" int mtl_nms(const float* boxes, const float* scores, const int* order
                                             iou_thresh, max_out, reinterpret_cast<float4*>(out_boxes), out_scores,
                                             out_idx, num_out);
   MTL_CUDA_LAUNCH_CHECK("nms_kernel");
+  return MTL_OK;
+}
+
+extern "C" int mtl_clip_boxes(const float* boxes, int N, float wy0, float wx0, float wy1, float wx1, float* out,
+                              cudaStream_t stream) {
+  MTL_CHECK_ARG(boxes && out && N >= 0, "mtl_clip_boxes: bad args");
+  if (N == 0) return MTL_OK;
+  clip_boxes_kernel<<<ceil_div(N, 256), 256, 0, stream>>>(reinterpret_cast<const float4*>(boxes), N, wy0, wx0, wy1,
+                                                         wx1, reinterpret_cast<float4*>(out));
+  MTL_CUDA_LAUNCH_CHECK("clip_boxes_kernel");
+  return MTL_OK;
+}
+
+extern "C" int mtl_proposals_from_nms(const float* nms_boxes, const float* nms_scores, const int* nms_num, int B,
+                                      int M, float img_h, float img_w, float* out_abs, float* out_norm,
+                                      float* out_scores, int* num_out, cudaStream_t stream) {
+  MTL_CHECK_ARG(nms_boxes && nms_scores && nms_num && out_abs && out_norm && num_out && B > 0 && M > 0,
+                "mtl_proposals_from_nms: bad args");
+  dim3 grid(ceil_div(M, 128), B);
+  proposals_from_nms_kernel<<<grid, 128, 0, stream>>>(reinterpret_cast<const float4*>(nms_boxes), nms_scores, nms_num,
+                                                      M, img_h, img_w, reinterpret_cast<float4*>(out_abs),
+                                                      reinterpret_cast<float4*>(out_norm), out_scores, num_out);
+  MTL_CUDA_LAUNCH_CHECK("proposals_from_nms_kernel");
   return MTL_OK;
 }
 

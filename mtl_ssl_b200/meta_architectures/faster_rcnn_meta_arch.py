@@ -316,7 +316,10 @@ class FasterRCNNMetaArch(model.DetectionModel):
                 nk = int(num.item())
                 self._anchor_cache[key] = (kept[:nk].contiguous(), keep[:nk].contiguous(), nk)
             else:
-                raise ValueError("first_stage_clip_window / inference-time anchor clipping is not built yet")
+                # inference (or first_stage_clip_window): clip, keep every anchor (fmA:586-590)
+                clipped = torch.empty_like(allb)
+                ops.call("mtl_clip_boxes", allb, n, 0.0, 0.0, float(H), float(W), clipped)
+                self._anchor_cache[key] = (clipped, None, n)
         return self._anchor_cache[key]
 
     def num_kept_anchors(self, image_shape):
@@ -355,9 +358,11 @@ class FasterRCNNMetaArch(model.DetectionModel):
         pd.update({
             "rpn_box_predictor_features": rpn_feat, "rpn_features_to_crop": feat, "image_shape": image_shape,
             "anchors": anchors,
-            "rpn_box_encodings": lambda: rp[BOX_ENCODINGS]().squeeze(2)[:, keep_idx.long()],
+            "rpn_box_encodings": lambda: (rp[BOX_ENCODINGS]().squeeze(2) if keep_idx is None
+                                          else rp[BOX_ENCODINGS]().squeeze(2)[:, keep_idx.long()]),
             "rpn_objectness_predictions_with_background":
-                lambda: rp[CLASS_PREDICTIONS_WITH_BACKGROUND]()[:, keep_idx.long()],
+                lambda: (rp[CLASS_PREDICTIONS_WITH_BACKGROUND]() if keep_idx is None
+                         else rp[CLASS_PREDICTIONS_WITH_BACKGROUND]()[:, keep_idx.long()]),
             "_rpn_out": rpn_out, "_rpn_layout": lay, "_keep_idx": keep_idx, "_Nk": Nk, "_feat_hw": (Hf, Wf),
         })
         pd.update(self._predict_second_stage(pd))
@@ -385,6 +390,15 @@ class FasterRCNNMetaArch(model.DetectionModel):
         nms_n = ws.get("rpn/nms_num", (B,), torch.int32)
         ops.call("mtl_nms", boxes, scores, order, nvalid, B, Nk, self._first_stage_nms_iou_threshold, M, nms_b,
                  nms_s, None, nms_n)
+        if not (self._is_training and not self._hard_example_miner):
+            # inference: the NMS output is the proposal set (fmA:1111-1131), P == first_stage_max_proposals
+            prop_abs = ws.get("det/prop_abs", (B, P, 4), torch.float32)
+            prop_norm = ws.get("det/prop_norm", (B, P, 4), torch.float32)
+            prop_sc = ws.get("det/prop_scores", (B, P), torch.float32)
+            nprop = ws.get("det/num_proposals", (B,), torch.int32)
+            ops.call("mtl_proposals_from_nms", nms_b, nms_s, nms_n, B, M, float(H), float(W), prop_abs, prop_norm,
+                     prop_sc, nprop)
+            return prop_norm, prop_abs, prop_sc, nprop
         gt = self._format_groundtruth_data(pd["image_shape"])
         # _sample_box_classifier_minibatch (fmA:1268-1302): detector assignment on the unpadded proposals
         match = ws.get("det/sample_match", (B, M), torch.int32)

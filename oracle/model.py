@@ -292,10 +292,13 @@ class Oracle(object):
         return outs
 
     # ------------------------------------------------------------------ forward
-    def forward(self, images, examples, keys, H, W, proposal_inputs=None):
+    def forward(self, images, examples, keys, H, W, proposal_inputs=None, inference=False):
         """proposal_inputs: optional (rpn_box [B,N,4], rpn_cls [B,N,2]) numpy arrays used INSTEAD of the
         oracle's own RPN outputs for the (non-differentiable) proposal selection, so that index-level
-        parity can be checked on identical inputs."""
+        parity can be checked on identical inputs.
+        inference=True: the is_training=False graph (fmA:586-590 anchors clipped instead of pruned; fmA:1111-1131 no
+        minibatch sampling, max_num_proposals = first_stage_max_proposals, fmA:475-477); returns after the
+        second-stage box classifier (what `postprocess` consumes); `examples` / `keys` are not used."""
         cfg, p = self.cfg, self.p
         B = images.shape[0]
         K = cfg["num_classes"]
@@ -314,10 +317,16 @@ class Oracle(object):
         box = box.reshape(B, Hf * Wf * A, 4)
         cls = cls.reshape(B, Hf * Wf * A, 2)
         anchors_all = OB.grid_anchors(Hf, Wf, cfg["scales"], cfg["aspect_ratios"], (256, 256), (16, 16), (0, 0))
-        anchors, keep = OB.prune_outside_window(anchors_all, (0, 0, H, W))        # fmA:930-976
-        keep_t = torch.from_numpy(keep).long()
+        if inference:
+            anchors, keep = OB.clip_to_window(anchors_all, (0, 0, H, W))             # fmA:586-590
+            assert len(keep) == len(anchors_all), "a grid anchor lies completely outside the image"
+        else:
+            anchors, keep = OB.prune_outside_window(anchors_all, (0, 0, H, W))        # fmA:930-976
+        keep_t = torch.from_numpy(np.asarray(keep)).long()
         rpn_box, rpn_cls = box[:, keep_t], cls[:, keep_t]
         P, M = cfg["second_stage_batch_size"], cfg["first_stage_max_proposals"]
+        if inference:
+            P = M
         # ---- _postprocess_rpn + minibatch sampling (no gradient: fmA:1109-1110)
         gts = []
         prop_norm = np.zeros((B, P, 4), np.float32)
@@ -325,6 +334,17 @@ class Oracle(object):
         nprop = np.zeros((B,), np.int64)
         nms_out = []
         for b in range(B):
+            if inference:
+                src_box = proposal_inputs[0][b] if proposal_inputs is not None else rpn_box[b].detach().numpy()
+                src_cls = proposal_inputs[1][b] if proposal_inputs is not None else rpn_cls[b].detach().numpy()
+                pb, ps, n = OP.rpn_postprocess_single(src_box, src_cls, anchors, (H, W), cfg["nms_score_threshold"],
+                                                      cfg["nms_iou_threshold"], M)
+                nms_out.append((pb, ps, n))
+                nprop[b] = n
+                nb = OB.to_normalized_coordinates(pb[:n], H, W)
+                prop_norm[b, :n] = nb
+                prop_abs[b, :n] = OB.to_absolute_coordinates(nb, H, W)
+                continue
             ex = examples[b]
             gt_abs = OB.to_absolute_coordinates(np.asarray(ex["groundtruth_boxes"], np.float32).reshape(-1, 4), H, W)
             oh = np.asarray(ex["groundtruth_classes"], np.float32)
@@ -368,6 +388,8 @@ class Oracle(object):
                                ["BoxEncodingPredictor", "ClassPredictor"])
         out["refined_box_encodings"] = bx.reshape(B * P, K, 4)
         out["class_predictions_with_background"] = cl
+        if inference:
+            return out
         if mtl.get("closeness"):
             if rfcn:
                 f2 = feat.detach() if stop else feat

@@ -114,3 +114,70 @@ def test_meta_arch_postprocess_after_forward():
     b = det["detection_boxes"][0].cpu().numpy()
     assert np.all(np.diff(s[:n]) <= 0) and not s[n:].any()
     assert b[:n].min() >= 0 and b[:n].max() <= 1 and not b[n:].any()
+
+
+def test_inference_mode_predict_and_postprocess():
+    """is_training=False graph (fmA:586-590 clipped anchors, fmA:1111-1131 unsampled proposals, max_num_proposals =
+    first_stage_max_proposals) against oracle/model.py `forward(inference=True)`: proposal selection index-exact on the
+    device's own RPN outputs, head outputs to bf16 rounding, then `postprocess` bit-exact on the device's decode."""
+    import test_gpu_train_step as T
+    from helpers import load_config, oracle_config, randomize_bn
+    from mtl_ssl_b200 import ops
+    from mtl_ssl_b200.builders import model_builder
+    from mtl_ssl_b200.data import synthetic
+    from oracle.model import Oracle
+    from oracle import postprocess as PP
+    H, W, B = 224, 320, 1
+    cfg = load_config("model12.config", T.SMALL)
+    model = model_builder.build(cfg.model, False, device="cuda", seed=0)
+    sd = randomize_bn(model.param_store.state_dict(), 0)
+    model.param_store.load_state_dict(sd)
+    K = cfg.model.faster_rcnn.num_classes
+    ex = synthetic.make_batch(7, B, H, W, K, max_boxes=4, num_windows=16)
+    images = np.stack([e["image"] for e in ex]).astype(np.float32)
+    image = torch.from_numpy(images).cuda()
+    assert model.max_num_proposals == cfg.model.faster_rcnn.first_stage_max_proposals
+    pd = model.predict(model.preprocess(image))
+    det = model.postprocess(pd)
+    torch.cuda.synchronize()
+    P = model.max_num_proposals
+    # every anchor is kept (clipped), none pruned
+    Hf, Wf = pd["_feat_hw"]
+    assert pd["anchors"].shape[0] == Hf * Wf * 12
+    assert float(pd["anchors"].min()) >= 0 and float(pd["anchors"][:, 2].max()) <= H and float(pd["anchors"][:, 3].max()) <= W
+    orc = Oracle({k: v for k, v in sd.items() if "/_pad/" not in k}, oracle_config(cfg), bf16=True)
+    prop_in = (pd["rpn_box_encodings"].cpu().numpy(), pd["rpn_objectness_predictions_with_background"].cpu().numpy())
+    with torch.no_grad():
+        out = orc.forward(torch.from_numpy(images), None, None, H, W, proposal_inputs=prop_in, inference=True)
+    assert np.array_equal(pd["num_proposals"].cpu().numpy(), out["nprop"])
+    n = int(out["nprop"][0])
+    assert 0 < n <= P
+    np.testing.assert_allclose(pd["proposal_boxes"].cpu().numpy(), out["prop_abs"], rtol=1e-5, atol=1e-3)
+
+    def cos(a, b):
+        a, b = a.reshape(-1).double(), b.reshape(-1).double()
+        return float(a @ b / (a.norm() * b.norm()).clamp_min(1e-30))
+
+    enc = pd["refined_box_encodings"].float().cpu()[:n]
+    cls = pd["class_predictions_with_background"].float().cpu()[:n]
+    assert cos(enc, out["refined_box_encodings"].float()[:n]) > 0.999
+    assert cos(cls, out["class_predictions_with_background"].float()[:n]) > 0.999
+    # detections: exact against the oracle on the device's decoded boxes / scores
+    nms = cfg.model.faster_rcnn.second_stage_post_processing.batch_non_max_suppression
+    e32 = pd["refined_box_encodings"].contiguous().float()
+    l32 = pd["class_predictions_with_background"].contiguous().float()
+    M, Tt = min(nms.max_detections_per_class, P), nms.max_total_detections
+    boxes_n = torch.empty(B, K, P, 4, device="cuda")
+    scores = torch.empty(B, K, P, device="cuda")
+    k64 = torch.empty(B, K, P, dtype=torch.int64, device="cuda")
+    dec = torch.empty(B, K, P, 4, device="cuda")
+    ops.call("mtl_detection_decode", e32, l32, pd["proposal_boxes"], pd["num_proposals"], B, P, K, float(H), float(W),
+             float(nms.score_threshold), 1, boxes_n, scores, k64, dec)
+    wb, ws_, wc, wn = PP.second_stage_postprocess(
+        e32.cpu().numpy(), l32.cpu().numpy(), pd["proposal_boxes"].cpu().numpy(), pd["num_proposals"].cpu().numpy(),
+        (H, W), nms.score_threshold, nms.iou_threshold, M, Tt, decoded=dec.cpu().numpy().transpose(0, 2, 1, 3),
+        scores=scores.cpu().numpy().transpose(0, 2, 1))
+    assert np.array_equal(det["num_detections"].cpu().numpy(), wn) and wn[0] > 0
+    assert np.array_equal(det["detection_scores"].cpu().numpy(), ws_)
+    assert np.array_equal(det["detection_classes"].cpu().numpy(), wc)
+    assert np.array_equal(det["detection_boxes"].cpu().numpy(), wb)
