@@ -141,3 +141,52 @@ def test_decode_round_trip_feeds_the_trainer(tmp_path):
     bad["image/object/class/label"] = np.asarray([K + 1] * len(bad["image/object/class/label"]), np.int64)
     with pytest.raises(ValueError):
         T.decode_example(T.serialize_example(bad), K)
+
+
+def test_horizontal_flip_reference_vectors():
+    """preprocessor_test.py:47-66, :165-184 (testRandomHorizontalFlip): image columns reversed, boxes mirrored; plus the
+    fork's window boxes and the edge-mask axis trap (T16)."""
+    from mtl_ssl_b200.data import augment as A
+    r = np.array([[128, 128, 128, 128], [0, 0, 128, 128], [0, 128, 128, 128], [192, 192, 128, 128]], np.float32)
+    g = np.array([[0, 0, 128, 128], [0, 0, 128, 128], [0, 128, 192, 192], [192, 192, 128, 192]], np.float32)
+    b = np.array([[128, 128, 192, 0], [0, 0, 128, 192], [0, 128, 128, 0], [192, 192, 192, 128]], np.float32)
+    img = np.stack([r, g, b], -1)
+    em = np.arange(2 * 3 * 4, dtype=np.float32).reshape(2, 3, 4)
+    ex = dict(image=img, groundtruth_boxes=np.array([[0.0, 0.25, 0.75, 1.0], [0.25, 0.5, 0.75, 1.0]], np.float32),
+              window_boxes=np.array([[0.1, 0.2, 0.3, 0.6]], np.float32), groundtruth_edgemask=em)
+    f = A.horizontal_flip(ex)
+    want_r = (np.array([[0, 0, 0, 0], [0, 0, -1, -1], [0, 0, 0, -1], [0, 0, 0.5, 0.5]], np.float32) + 1) * 128
+    assert np.array_equal(f["image"][..., 0], want_r)                       # expectedImagesAfterMirroring, red plane
+    assert np.array_equal(f["image"], img[:, ::-1])
+    np.testing.assert_allclose(f["groundtruth_boxes"], [[0.0, 0.0, 0.75, 0.75], [0.25, 0.0, 0.75, 0.5]])
+    np.testing.assert_allclose(f["window_boxes"], [[0.1, 0.4, 0.3, 0.8]], rtol=1e-6)
+    assert np.array_equal(f["groundtruth_edgemask"], em[:, ::-1, :])        # the reference reverses the mask ROWS
+    assert np.array_equal(A.horizontal_flip(ex, reference_edgemask_axis=False)["groundtruth_edgemask"], em[:, :, ::-1])
+    # probability 1/2, never without boxes
+    rng = np.random.default_rng(0)
+    flips = sum(A.random_horizontal_flip(ex, rng) is not ex for _ in range(2000))
+    assert 900 < flips < 1100
+    empty = dict(ex, groundtruth_boxes=np.zeros((0, 4), np.float32))
+    assert all(A.random_horizontal_flip(empty, rng) is empty for _ in range(50))
+    assert [len(x) for x in A.batches(range(7), 3)] == [3, 3]
+    assert [len(x) for x in A.batches(range(7), 3, drop_remainder=False)] == [3, 3, 1]
+
+
+def test_input_examples_from_pipeline_config(tmp_path):
+    from helpers import load_config
+    from mtl_ssl_b200.data import augment as A
+    K, H, W = 20, 64, 80
+    examples = synthetic.make_batch(5, 3, H, W, K, max_boxes=3, num_windows=8)
+    p = str(tmp_path / "train.record")
+    T.write_tfrecords(p, [T.encode_example(e) for e in examples])
+    cfg = load_config("model12.config", (("../data/voc/voc2007_trainval.record", p),))
+    reader = cfg.train_input_reader
+    assert reader.tf_record_input_reader.input_path == p and reader.shuffle is True      # proto default
+    got = list(A.input_examples(reader, K, options=("random_horizontal_flip",), seed=1, epochs=2))
+    assert len(got) == 6
+    areas = sorted(float(np.prod(e["groundtruth_boxes"][:, 2:] - e["groundtruth_boxes"][:, :2], 1).sum()) for e in got)
+    want = sorted(float(np.prod(e["groundtruth_boxes"][:, 2:] - e["groundtruth_boxes"][:, :2], 1).sum())
+                  for e in examples) * 2
+    np.testing.assert_allclose(areas, sorted(want), rtol=1e-5)            # flips preserve box areas
+    with pytest.raises(NotImplementedError):
+        next(A.input_examples(reader, K, options=("random_crop_image",)))
