@@ -1,0 +1,88 @@
+"""Generates tests/golden/eval_reference.npz by RUNNING the reference's NumPy evaluator
+(/root/reference/object_detection/utils/{object_detection_evaluation,per_image_evaluation,metrics}.py) in this
+container on seeded random detections.  The reference is Python-2 / NumPy-1.x code: the aliases it needs (np.bool,
+np.float, np.NAN, xrange) and a stub for the pycocotools import are injected here, nothing in the reference is modified.
+Run from the repo root:  python tests/golden/make_eval_golden.py"""
+import builtins
+import os
+import sys
+import types
+
+import numpy as np
+
+np.bool, np.float, np.NAN = bool, float, np.nan
+builtins.xrange = range
+for name in ("pycocotools", "pycocotools.coco", "pycocotools.cocoeval"):
+    sys.modules[name] = types.ModuleType(name)
+sys.modules["pycocotools.coco"].COCO = object
+sys.modules["pycocotools.cocoeval"].COCOeval = object
+sys.path.insert(0, "/root/reference")
+from object_detection.utils import object_detection_evaluation as ref_ode      # noqa: E402
+from object_detection.utils import metrics as ref_metrics                      # noqa: E402
+
+
+def scenario(seed, num_class, num_images, subsets, nms_iou, nms_max):
+    rng = np.random.default_rng(seed)
+    ev = ref_ode.ObjectDetectionEvaluation(num_class, matching_iou_threshold=0.5, nms_iou_threshold=nms_iou,
+                                           nms_max_output_boxes=nms_max, subset_names=subsets)
+    data = []
+    for i in range(num_images):
+        g = int(rng.integers(0, 6))
+        y0, x0 = rng.uniform(0, 60, g), rng.uniform(0, 60, g)
+        gb = np.stack([y0, x0, y0 + rng.uniform(5, 40, g), x0 + rng.uniform(5, 40, g)], 1)
+        gc = rng.integers(0, num_class, g)
+        sub = ["|".join(s for s in subsets if rng.random() < 0.7) for _ in range(g)]
+        n = int(rng.integers(0, 12))
+        # detections: jittered copies of ground truth + random boxes, a few degenerate, some tied scores
+        src = rng.integers(0, max(g, 1), n)
+        jit = rng.normal(0, 4.0, (n, 4))
+        db = (gb[src] + jit) if g else np.abs(rng.normal(30, 15, (n, 4)))
+        rnd = rng.random(n) < 0.3
+        ry, rx = rng.uniform(0, 60, n), rng.uniform(0, 60, n)
+        db[rnd] = np.stack([ry, rx, ry + rng.uniform(5, 40, n), rx + rng.uniform(5, 40, n)], 1)[rnd]
+        if n:
+            db[rng.random(n) < 0.05, 2] = 0.0                       # ymax < ymin: invalid
+        ds = np.round(rng.random(n), 1)                              # ties on purpose
+        dc = np.where(rng.random(n) < 0.8, gc[src] if g else rng.integers(0, num_class, n), rng.integers(0, num_class, n))
+        data.append((gb, gc, sub, db, ds, dc))
+        ev.add_single_ground_truth_image_info("img%d" % i, gb, gc, sub if i % 2 else None if subsets == ("default",) else sub)
+        ev.add_single_detected_image_info("img%d" % i, db, ds, dc)
+    ap, mean_ap, prec, rec, corloc, mean_corloc = ev.evaluate()
+    return data, {s: ap[s] for s in subsets}, mean_ap, corloc, mean_corloc
+
+
+def main():
+    out = {}
+    cases = [(0, 3, 12, ("default",), 1.0, 10000), (1, 4, 20, ("default", "small"), 1.0, 10000),
+             (2, 2, 15, ("default",), 0.6, 5), (3, 5, 30, ("a", "b", "c"), 0.3, 10000)]
+    for ci, (seed, C, N, subsets, nms_iou, nms_max) in enumerate(cases):
+        data, ap, mean_ap, corloc, mean_corloc = scenario(seed, C, N, subsets, nms_iou, nms_max)
+        out["case%d/meta" % ci] = np.array([seed, C, N, nms_max], np.int64)
+        out["case%d/nms_iou" % ci] = np.array(nms_iou)
+        out["case%d/subsets" % ci] = np.array(subsets)
+        for i, (gb, gc, sub, db, ds, dc) in enumerate(data):
+            p = "case%d/img%d/" % (ci, i)
+            out[p + "gb"], out[p + "gc"], out[p + "sub"] = gb, gc, np.array(sub, dtype="U32")
+            out[p + "db"], out[p + "ds"], out[p + "dc"] = db, ds, dc
+        for s in subsets:
+            out["case%d/ap/%s" % (ci, s)] = ap[s]
+            out["case%d/map/%s" % (ci, s)] = np.array(mean_ap[s])
+        out["case%d/corloc" % ci] = corloc
+        out["case%d/mean_corloc" % ci] = np.array(mean_corloc)
+    # curve-level vectors
+    rng = np.random.default_rng(9)
+    for k in range(4):
+        n = int(rng.integers(1, 40))
+        sc = np.round(rng.random(n), 2)
+        lb = rng.random(n) < 0.5
+        num_gt = int(lb.sum() + rng.integers(0, 5))
+        p, r = ref_metrics.compute_precision_recall(sc, lb, num_gt)
+        out["curve%d/scores" % k], out["curve%d/labels" % k], out["curve%d/num_gt" % k] = sc, lb, np.array(num_gt)
+        out["curve%d/precision" % k], out["curve%d/recall" % k] = p, r
+        out["curve%d/ap" % k] = np.array(ref_metrics.compute_average_precision(p, r))
+    np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "eval_reference.npz"), **out)
+    print("wrote eval_reference.npz with %d arrays" % len(out))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,100 @@
+"""CPU tests of the VOC-style detection metrics: the reference's own unit-test vectors
+(utils/metrics_test.py:24-75, utils/object_detection_evaluation_test.py:26-130) and golden outputs of the reference
+evaluator RUN in this container on seeded random detections (tests/golden/make_eval_golden.py -> eval_reference.npz:
+subsets / difficult boxes, tied scores, invalid boxes, per-class NMS)."""
+import os
+
+import numpy as np
+import pytest
+
+from mtl_ssl_b200.utils import detection_evaluation as E
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "eval_reference.npz")
+
+
+def test_metrics_reference_vectors():
+    np.testing.assert_allclose(E.compute_cor_loc(np.array([100, 1, 5, 1, 1]), np.array([10, 0, 1, 0, 0])),
+                               [0.1, 0, 0.2, 0, 0])
+    got = E.compute_cor_loc(np.array([100, 0, 0, 1, 1]), np.array([10, 0, 1, 0, 0]))
+    np.testing.assert_allclose(got, [0.1, np.nan, np.nan, 0, 0], equal_nan=True)
+    scores = np.array([0.4, 0.3, 0.6, 0.2, 0.7, 0.1])
+    labels = np.array([0, 1, 1, 0, 0, 1], bool)
+    tp = np.array([0, 1, 1, 2, 2, 3], float)
+    p, r = E.compute_precision_recall(scores, labels, 10)
+    np.testing.assert_allclose(p, tp / np.arange(1, 7))
+    np.testing.assert_allclose(r, tp / 10)
+    precision = np.array([0.8, 0.76, 0.9, 0.65, 0.7, 0.5, 0.55, 0])
+    recall = np.array([0.3, 0.3, 0.4, 0.4, 0.45, 0.45, 0.5, 0.5])
+    want = np.sum(np.array([0.3, 0, 0.1, 0, 0.05, 0, 0.05, 0]) * np.array([0.9, 0.9, 0.9, 0.7, 0.7, 0.55, 0.55, 0]))
+    assert abs(E.compute_average_precision(precision, recall) - want) < 1e-12
+    p, r = E.compute_precision_recall(scores, np.zeros(6, bool), 0)
+    assert p is None and r is None and np.isnan(E.compute_average_precision(p, r))
+    assert E.compute_average_precision(np.array([]), np.array([])) == 0.0
+    with pytest.raises(ValueError):
+        E.compute_precision_recall(scores, labels, 2)                 # more true positives than ground truth
+    with pytest.raises(ValueError):
+        E.compute_average_precision(np.array([0.5, 0.5]), np.array([0.4, 0.3]))
+
+
+def test_object_detection_evaluation_reference_case():
+    ev = E.ObjectDetectionEvaluation(3)
+    ev.add_single_ground_truth_image_info("img1", np.array([[0, 0, 1, 1], [0, 0, 2, 2], [0, 0, 3, 3]], float),
+                                          np.array([0, 2, 0]))
+    ev.add_single_ground_truth_image_info("img2", np.array([[10, 10, 11, 11], [500, 500, 510, 510], [10, 10, 12, 12]],
+                                                           float), np.array([0, 0, 2]),
+                                          np.array(["default", "", "default"]))
+    ev.add_single_ground_truth_image_info("img3", np.array([[0, 0, 1, 1]], float), np.array([1]))
+    ev.add_single_detected_image_info("img2", np.array([[10, 10, 11, 11], [100, 100, 120, 120], [100, 100, 220, 220]],
+                                                       float), np.array([0.7, 0.8, 0.9]), np.array([0, 0, 2]))
+    assert ev.num_gt_instances_per_class["default"].tolist() == [3, 1, 2]
+    assert ev.num_gt_imgs_per_class.tolist() == [2, 1, 2]
+    assert ev.groundtruth_subset["default"]["img2"].tolist() == [True, False, True]
+    np.testing.assert_allclose(ev.scores_per_class["default"][0][0], [0.8, 0.7])
+    assert ev.tp_fp_labels_per_class["default"][0][0].tolist() == [False, True]
+    np.testing.assert_allclose(ev.scores_per_class["default"][2][0], [0.9])
+    assert ev.tp_fp_labels_per_class["default"][2][0].tolist() == [False]
+    assert ev.num_images_correctly_detected_per_class.tolist() == [0, 0, 0]
+    ap, mean_ap, prec, rec, corloc, mean_corloc = ev.evaluate()
+    np.testing.assert_allclose(ap["default"], [1.0 / 6.0, 0, 0])
+    assert abs(mean_ap["default"] - 1.0 / 18) < 1e-12 and mean_corloc == 0.0
+    np.testing.assert_allclose(prec["default"][0], [0, 0.5])
+    np.testing.assert_allclose(rec["default"][0], [0, 1.0 / 3.0])
+    assert len(prec["default"][1]) == 0
+    np.testing.assert_allclose(prec["default"][2], [0])
+    # adding the same image twice is ignored; length mismatch is an error
+    ev.add_single_detected_image_info("img2", np.zeros((1, 4)), np.zeros(1), np.zeros(1, int))
+    assert len(ev.scores_per_class["default"][0]) == 1
+    with pytest.raises(ValueError):
+        ev.add_single_detected_image_info("img9", np.zeros((2, 4)), np.zeros(1), np.zeros(2, int))
+    with pytest.raises(ValueError):
+        ev.add_single_ground_truth_image_info("img9", np.zeros((1, 4)), np.zeros(1, int), ["nosuchsubset"])
+    with pytest.raises(NotImplementedError):
+        E.PerImageEvaluation(3, nms_type="soft-linear")
+
+
+def test_against_reference_evaluator_outputs():
+    g = np.load(GOLD)
+    ncase = len([k for k in g.files if k.endswith("/meta")])
+    assert ncase == 4
+    for ci in range(ncase):
+        seed, C, N, nms_max = [int(v) for v in g["case%d/meta" % ci]]
+        subsets = tuple(str(s) for s in g["case%d/subsets" % ci])
+        ev = E.ObjectDetectionEvaluation(C, matching_iou_threshold=0.5, nms_iou_threshold=float(g["case%d/nms_iou" % ci]),
+                                         nms_max_output_boxes=nms_max, subset_names=subsets)
+        for i in range(N):
+            p = "case%d/img%d/" % (ci, i)
+            sub = [str(s) for s in g[p + "sub"]]
+            sub_arg = sub if (i % 2 or subsets != ("default",)) else None          # as in make_eval_golden.py
+            ev.add_single_ground_truth_image_info("img%d" % i, g[p + "gb"], g[p + "gc"], sub_arg)
+            ev.add_single_detected_image_info("img%d" % i, g[p + "db"], g[p + "ds"], g[p + "dc"])
+        ap, mean_ap, _, _, corloc, mean_corloc = ev.evaluate()
+        for s in subsets:
+            np.testing.assert_allclose(ap[s], g["case%d/ap/%s" % (ci, s)], rtol=1e-12, atol=0, equal_nan=True)
+            np.testing.assert_allclose(mean_ap[s], g["case%d/map/%s" % (ci, s)], rtol=1e-12, equal_nan=True)
+        np.testing.assert_allclose(corloc, g["case%d/corloc" % ci], rtol=1e-12, equal_nan=True)
+        np.testing.assert_allclose(mean_corloc, g["case%d/mean_corloc" % ci], rtol=1e-12, equal_nan=True)
+    for k in range(4):
+        p, r = E.compute_precision_recall(g["curve%d/scores" % k], g["curve%d/labels" % k], int(g["curve%d/num_gt" % k]))
+        np.testing.assert_allclose(p, g["curve%d/precision" % k], rtol=1e-13)
+        np.testing.assert_allclose(r, g["curve%d/recall" % k], rtol=1e-13)
+        np.testing.assert_allclose(E.compute_average_precision(p, r), g["curve%d/ap" % k], rtol=1e-12)
