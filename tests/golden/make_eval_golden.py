@@ -80,6 +80,37 @@ def main():
         out["curve%d/scores" % k], out["curve%d/labels" % k], out["curve%d/num_gt" % k] = sc, lb, np.array(num_gt)
         out["curve%d/precision" % k], out["curve%d/recall" % k] = p, r
         out["curve%d/ap" % k] = np.array(ref_metrics.compute_average_precision(p, r))
+    # auxiliary-task metrics (utils/mtl_util.py): skimage is absent here and only used by the edge-mask metric, which
+    # is therefore not exported
+    sk = types.ModuleType("skimage"); skt = types.ModuleType("skimage.transform")
+    skt.resize = lambda *a, **k: (_ for _ in ()).throw(RuntimeError("skimage.resize is stubbed"))
+    sys.modules["skimage"], sys.modules["skimage.transform"] = sk, skt
+    from object_detection.utils import mtl_util as ref_mtl
+    rng = np.random.default_rng(21)
+    K1, nimg = 6, 5
+    res = {"groundtruth_boxes": [], "detection_boxes": [], "window_classes_gt": [], "window_classes_dt": [],
+           "closeness_gt": [], "closeness_dt": []}
+    for i in range(nimg):
+        g, d, nw = int(rng.integers(1, 5)), int(rng.integers(2, 8)), int(rng.integers(2, 6))
+        y0, x0 = rng.uniform(0, 0.6, g), rng.uniform(0, 0.6, g)
+        gb = np.stack([y0, x0, y0 + rng.uniform(0.1, 0.4, g), x0 + rng.uniform(0.1, 0.4, g)], 1)
+        y0, x0 = rng.uniform(0, 0.6, d), rng.uniform(0, 0.6, d)
+        db = np.stack([y0, x0, y0 + rng.uniform(0.1, 0.4, d), x0 + rng.uniform(0.1, 0.4, d)], 1)
+        wl = np.round(rng.random((nw, K1)) * (rng.random((nw, K1)) < 0.5), 3)
+        wl[:, 0] = np.maximum(wl[:, 0], 0.1)                                  # at least one positive label per window
+        cl = np.round(rng.random((g, K1)) * (rng.random((g, K1)) < 0.4), 3)
+        res["groundtruth_boxes"].append(gb); res["detection_boxes"].append(db)
+        res["window_classes_gt"].append([" ".join(str(v) for v in row) for row in wl])
+        res["window_classes_dt"].append(rng.normal(0, 2, (nw, K1)))
+        res["closeness_gt"].append([" ".join(str(v) for v in row) for row in cl])
+        res["closeness_dt"].append(rng.normal(0, 2, (d, K1)))
+        for k in ("groundtruth_boxes", "detection_boxes", "window_classes_dt", "closeness_dt"):
+            out["mtl/img%d/%s" % (i, k)] = res[k][-1]
+        out["mtl/img%d/window_classes_gt" % i] = np.array(res["window_classes_gt"][-1], dtype="U128")
+        out["mtl/img%d/closeness_gt" % i] = np.array(res["closeness_gt"][-1], dtype="U128")
+    m = ref_mtl.get_mtl_metrics(res)
+    out["mtl/n"] = np.array(nimg)
+    out["mtl/window_map"], out["mtl/closeness_diff"] = np.array(m["mtl/window_map"]), np.array(m["mtl/closeness_diff"])
     np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "eval_reference.npz"), **out)
     print("wrote eval_reference.npz with %d arrays" % len(out))
 

@@ -98,3 +98,42 @@ def test_against_reference_evaluator_outputs():
         np.testing.assert_allclose(p, g["curve%d/precision" % k], rtol=1e-13)
         np.testing.assert_allclose(r, g["curve%d/recall" % k], rtol=1e-13)
         np.testing.assert_allclose(E.compute_average_precision(p, r), g["curve%d/ap" % k], rtol=1e-12)
+
+
+def test_mtl_metrics_against_reference_outputs():
+    """utils/mtl_util.py:20-87 (window mAP, closeness arg-max agreement) on the vectors the reference produced here;
+    the edge-mask accuracy (skimage resize, absent: parity unpinned) by construction."""
+    from mtl_ssl_b200.utils import mtl_metrics as M
+    g = np.load(GOLD)
+    n = int(g["mtl/n"])
+    res = {k: [] for k in ("groundtruth_boxes", "detection_boxes", "window_classes_gt", "window_classes_dt",
+                           "closeness_gt", "closeness_dt")}
+    for i in range(n):
+        for k in res:
+            v = g["mtl/img%d/%s" % (i, k)]
+            res[k].append([str(s) for s in v] if v.dtype.kind == "U" else v)
+    m = M.get_mtl_metrics(res)
+    np.testing.assert_allclose(m["mtl/window_map"], g["mtl/window_map"], rtol=1e-12)
+    np.testing.assert_allclose(m["mtl/closeness_diff"], g["mtl/closeness_diff"], rtol=1e-12)
+    assert 0.0 < m["mtl/window_map"] <= 1.0 and "mtl/edgemask_ap" not in m
+    # numeric label rows (what data/tfrecord.py decodes to) give the same numbers as the record's text rows
+    res2 = dict(res)
+    res2["window_classes_gt"] = [[M._label_row(r) for r in rows] for rows in res["window_classes_gt"]]
+    res2["closeness_gt"] = [[M._label_row(r) for r in rows] for rows in res["closeness_gt"]]
+    m2 = M.get_mtl_metrics(res2)
+    assert m2 == m
+    # edge mask: a prediction whose foreground logit wins exactly on the ground-truth foreground scores 1.0
+    fg = np.zeros((64, 64), np.float32)
+    fg[16:48, 8:40] = 1
+    gt = np.stack([fg, np.ones_like(fg)])
+    logits = np.stack([-(fg * 2 - 1), fg * 2 - 1], -1)[None] * 3.0            # [1, 64, 64, 2] at the mask resolution
+    perfect = M.get_mtl_metrics({"edgemask_gt": [gt], "edgemask_dt": [logits], "groundtruth_boxes": [],
+                                 "detection_boxes": []})
+    assert perfect["mtl/edgemask_ap"] == 1.0
+    coarse = logits[:, ::2, ::2]                                              # half resolution: only the border can differ
+    acc = M.get_mtl_metrics({"edgemask_gt": [gt], "edgemask_dt": [coarse], "groundtruth_boxes": [],
+                             "detection_boxes": []})["mtl/edgemask_ap"]
+    assert 0.95 < acc <= 1.0
+    inverted = M.get_mtl_metrics({"edgemask_gt": [gt], "edgemask_dt": [-logits], "groundtruth_boxes": [],
+                                  "detection_boxes": []})["mtl/edgemask_ap"]
+    assert inverted == 0.0
