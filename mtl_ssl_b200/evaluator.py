@@ -1,0 +1,78 @@
+"""Evaluation loop on a B200: inference-mode model -> `predict` -> `postprocess` -> PASCAL-VOC and MTL metrics.
+Host side of /root/reference/object_detection/evaluator.py:100-230 (`_extract_prediction_tensors`: which tensors are
+collected per image) and eval_util.py; every array leaves the device once per image.
+
+Collected per image, as in the reference: detections in ABSOLUTE image coordinates (eval_util.py
+`result_dict_for_single_example` scales the normalised boxes by the image size), ground truth likewise, and for the
+auxiliary tasks `window_class_predictions` on the ground-truth windows, `closeness_predictions` (one row per PROPOSAL --
+the reference indexes these rows with a detection index, mtl_util.py:66-73 with evaluator.py:224; reproduced as is,
+trap T17) and `edgemask_predictions`."""
+import numpy as np
+import torch
+
+from . import eval_util
+from .utils import mtl_metrics
+
+
+def run_inference(model, example):
+    """One example dict (data/synthetic.py / data/tfrecord.py format) through the inference-mode model.
+    Returns the per-image result dict (NumPy)."""
+    if model._is_training:
+        raise ValueError("evaluation needs a model built with is_training=False")
+    dev = model.device
+    image = torch.from_numpy(np.ascontiguousarray(example["image"], np.float32))[None].to(dev)
+    H, W = image.shape[1], image.shape[2]
+    pd = model.predict(model.preprocess(image))
+    mtl = model._mtl
+    if mtl is not None and mtl.window and example.get("window_boxes") is not None:
+        wb = torch.from_numpy(np.asarray(example["window_boxes"], np.float32))[None].to(dev)
+        pd = model.predict_with_window(pd, window_boxes_normalized=wb, _keep=False)
+    if mtl is not None and mtl.edgemask:
+        pd = model.predict_edgemask(pd)
+    det = model.postprocess(pd)
+    torch.cuda.synchronize()          # the auxiliary heads ran on side streams ("lanes"): wait for all of them
+    n = int(det["num_detections"][0].item())
+    scale = np.array([H, W, H, W], np.float32)
+    K = model.num_classes
+    out = {
+        "detection_boxes": det["detection_boxes"][0, :n].cpu().numpy() * scale,
+        "detection_scores": det["detection_scores"][0, :n].cpu().numpy(),
+        "detection_classes": det["detection_classes"][0, :n].cpu().numpy().astype(np.int64) + 1,     # label_id_offset
+        "groundtruth_boxes": np.asarray(example["groundtruth_boxes"], np.float32).reshape(-1, 4) * scale,
+        "groundtruth_classes": np.asarray(example["groundtruth_classes"]).reshape(-1, K).argmax(1) + 1,
+    }
+    for k in ("groundtruth_difficult", "groundtruth_subset"):
+        if k in example:
+            out["difficult" if k == "groundtruth_difficult" else k] = np.asarray(example[k])
+    if "window_class_predictions" in pd and example.get("window_classes") is not None:
+        out["window_classes_gt"] = list(np.asarray(example["window_classes"], np.float32))
+        out["window_classes_dt"] = pd["window_class_predictions"].float().cpu().numpy().reshape(len(out["window_classes_gt"]), -1)
+    if "closeness_predictions" in pd and example.get("groundtruth_closeness") is not None:
+        out["closeness_gt"] = list(np.asarray(example["groundtruth_closeness"], np.float32))
+        cd = pd["closeness_predictions"].float().cpu().numpy()
+        if n > len(cd):      # more detections than proposals (small configs): rows past P read as zero logits, where the
+            cd = np.pad(cd, ((0, n - len(cd)), (0, 0)))          # reference (max 300 of each) would index out of range
+        out["closeness_dt"] = cd
+    if "edgemask_predictions" in pd and example.get("groundtruth_edgemask") is not None:
+        out["edgemask_gt"] = np.asarray(example["groundtruth_edgemask"], np.float32)
+        out["edgemask_dt"] = pd["edgemask_predictions"].float().cpu().numpy()
+    return out
+
+
+def evaluate(model, examples, categories, iou_thres=0.5, corloc_summary=True):
+    """Runs `examples` through the model and returns {metric name: value}: the PASCAL-VOC metrics of eval_util plus
+    'mtl/window_map', 'mtl/closeness_diff', 'mtl/edgemask_ap' for the auxiliary heads the config enables."""
+    lists = {}
+    for i, ex in enumerate(examples):
+        r = run_inference(model, ex)
+        r["image_id"] = str(i)
+        for k, v in r.items():
+            lists.setdefault(k, []).append(v)
+    metrics = eval_util.evaluate_detection_results_pascal_voc(lists, categories, iou_thres=iou_thres,
+                                                              corloc_summary=corloc_summary)
+    has_dets = all(len(d) for d in lists["detection_boxes"]) and all(len(g) for g in lists["groundtruth_boxes"])
+    aux = {k: v for k, v in lists.items() if k.split("_")[0] in ("window", "edgemask") or
+           (k.startswith("closeness") and has_dets)}
+    aux["groundtruth_boxes"], aux["detection_boxes"] = lists["groundtruth_boxes"], lists["detection_boxes"]
+    metrics.update(mtl_metrics.get_mtl_metrics(aux))
+    return metrics

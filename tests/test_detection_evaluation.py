@@ -137,3 +137,27 @@ def test_mtl_metrics_against_reference_outputs():
     inverted = M.get_mtl_metrics({"edgemask_gt": [gt], "edgemask_dt": [-logits], "groundtruth_boxes": [],
                                   "detection_boxes": []})["mtl/edgemask_ap"]
     assert inverted == 0.0
+
+
+def test_eval_util_pascal_metric_assembly():
+    """eval_util.py:233-372: label offset, `difficult` -> not in any subset, metric names."""
+    from mtl_ssl_b200 import eval_util
+    cats = [{"id": 1, "name": "a"}, {"id": 2, "name": "b"}]
+    gb = np.array([[0, 0, 10, 10], [20, 20, 40, 40], [50, 50, 60, 60]], float)
+    gc = np.array([1, 2, 1])
+    lists = {"detection_boxes": [gb[:2]], "detection_scores": [np.array([.9, .8])], "detection_classes": [gc[:2]],
+             "image_id": ["7"], "groundtruth_boxes": [gb], "groundtruth_classes": [gc],
+             "difficult": [np.array([0, 0, 1])]}
+    m = eval_util.evaluate_detection_results_pascal_voc(lists, cats, corloc_summary=True)
+    assert m["Subset default    mAP@0.5IOU"] == 1.0 and m["Subset default    mAP@0.5IOU/b"] == 1.0
+    assert m["CorLoc/CorLoc@0.5IOU"] == 1.0 and m["PerformanceByCategory/CorLoc@0.5IOU/a"] == 1.0
+    lists["difficult"] = [np.array([0, 0, 0])]                     # now the third box counts: recall of class a is 1/2
+    m = eval_util.evaluate_detection_results_pascal_voc(lists, cats)
+    assert m["Subset default    mAP@0.5IOU/a"] == 0.5 and abs(m["Subset default    mAP@0.5IOU"] - 0.75) < 1e-12
+    lists["groundtruth_subset"] = [np.array(["easy", "easy|hard", "hard"])]
+    m = eval_util.evaluate_detection_results_pascal_voc(lists, cats)
+    assert m["Subset easy       mAP@0.5IOU/a"] == 1.0 and m["Subset hard       mAP@0.5IOU/b"] == 1.0
+    # in subset 'hard' box 0 is difficult: its detection is dropped, the remaining class-a box is missed
+    assert m["Subset hard       mAP@0.5IOU/a"] == 0.0
+    with pytest.raises(ValueError):
+        eval_util.evaluate_detection_results_pascal_voc({"detection_boxes": []}, cats)

@@ -181,3 +181,46 @@ def test_inference_mode_predict_and_postprocess():
     assert np.array_equal(det["detection_scores"].cpu().numpy(), ws_)
     assert np.array_equal(det["detection_classes"].cpu().numpy(), wc)
     assert np.array_equal(det["detection_boxes"].cpu().numpy(), wb)
+
+
+def test_evaluation_loop_metrics():
+    """evaluator.evaluate: inference-mode model -> predict -> postprocess -> PASCAL-VOC + MTL metrics on synthetic
+    examples (random weights: the values are small, the point is that every stage connects and the bookkeeping is right)."""
+    import test_gpu_train_step as T
+    from helpers import load_config, randomize_bn
+    from mtl_ssl_b200 import evaluator
+    from mtl_ssl_b200.builders import model_builder
+    from mtl_ssl_b200.data import synthetic
+    from mtl_ssl_b200.utils.detection_evaluation import ObjectDetectionEvaluation
+    H, W = 224, 320
+    cfg = load_config("model12.config", T.SMALL)
+    model = model_builder.build(cfg.model, False, device="cuda", seed=0)
+    model.param_store.load_state_dict(randomize_bn(model.param_store.state_dict(), 0))
+    K = cfg.model.faster_rcnn.num_classes
+    examples = synthetic.make_batch(31, 3, H, W, K, max_boxes=4, num_windows=16)
+    cats = [{"id": i + 1, "name": "class%d" % (i + 1)} for i in range(K)]
+    m = evaluator.evaluate(model, examples, cats)
+    key = "Subset {:10} mAP@{}IOU".format("default", 0.5)
+    assert key in m and (np.isnan(m[key]) or 0.0 <= m[key] <= 1.0)
+    assert "CorLoc/CorLoc@0.5IOU" in m
+    for k in ("mtl/window_map", "mtl/closeness_diff", "mtl/edgemask_ap"):
+        assert k in m and 0.0 <= m[k] <= 1.0, (k, m.get(k))
+    # the per-image results are in absolute pixels and feed the evaluator directly
+    r = evaluator.run_inference(model, examples[0])
+    assert len(r["detection_boxes"]) == len(r["detection_scores"]) == len(r["detection_classes"]) > 0
+    assert r["detection_boxes"][:, [0, 2]].max() <= H + 1e-3 and r["detection_boxes"][:, [1, 3]].max() <= W + 1e-3
+    assert r["detection_classes"].min() >= 1 and r["detection_classes"].max() <= K
+    assert r["window_classes_dt"].shape == (16, K + 1) and r["closeness_dt"].shape[1] == K + 1
+    assert r["edgemask_dt"].shape[-1] == 2 and np.abs(r["edgemask_dt"]).max() <= 1.0          # tanh head (mp:111)
+    ev = ObjectDetectionEvaluation(K)
+    ev.add_single_ground_truth_image_info(0, r["groundtruth_boxes"], r["groundtruth_classes"] - 1)
+    ev.add_single_detected_image_info(0, r["detection_boxes"], r["detection_scores"], r["detection_classes"] - 1)
+    ap = ev.evaluate()[0]["default"]
+    present = np.unique(r["groundtruth_classes"] - 1)
+    assert np.all(np.isfinite(ap[present])) and np.all(np.isnan(np.delete(ap, present)))
+    # a perfect detector scores mAP 1: detections = ground truth
+    lists = {"detection_boxes": [r["groundtruth_boxes"]], "detection_scores": [np.ones(len(r["groundtruth_boxes"]))],
+             "detection_classes": [r["groundtruth_classes"]], "image_id": ["0"],
+             "groundtruth_boxes": [r["groundtruth_boxes"]], "groundtruth_classes": [r["groundtruth_classes"]]}
+    from mtl_ssl_b200 import eval_util
+    assert eval_util.evaluate_detection_results_pascal_voc(lists, cats)[key] == 1.0
