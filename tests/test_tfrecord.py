@@ -190,3 +190,57 @@ def test_input_examples_from_pipeline_config(tmp_path):
     np.testing.assert_allclose(areas, sorted(want), rtol=1e-5)            # flips preserve box areas
     with pytest.raises(NotImplementedError):
         next(A.input_examples(reader, K, options=("random_crop_image",)))
+
+
+def test_prefetch_loader_order_errors_and_shutdown(tmp_path):
+    from mtl_ssl_b200.data import loader as L
+    from mtl_ssl_b200.trainer import pack_groundtruth
+    K, H, W = 20, 64, 80
+    examples = synthetic.make_batch(8, 6, H, W, K, max_boxes=3, num_windows=8)
+    p = str(tmp_path / "t.record")
+    T.write_tfrecords(p, [T.encode_example(e) for e in examples])
+
+    def pack(group, keys):
+        a = pack_groundtruth(group, K, H, W, 8)
+        a["image"] = np.stack([e["image"] for e in group]).astype(np.float32)
+        a["keys1"], a["keys2"] = keys
+        return a
+    keys_fn = L.sampler_keys_fn(3, 2, 50, 10)
+    got = list(L.PrefetchLoader(T.TfRecordDataset(p, K), pack, keys_fn, batch_size=2, depth=2))
+    assert len(got) == 3
+    for i, a in enumerate(got):
+        want = pack(examples[2 * i:2 * i + 2], keys_fn(i))
+        for k in want:
+            np.testing.assert_allclose(a[k], want[k], atol=5e-4, err_msg=k)
+    assert not np.array_equal(got[0]["keys1"], got[1]["keys1"])          # fresh sampler keys every step
+    # an exception in the producer surfaces in the consumer
+
+    def bad():
+        yield examples[0]
+        yield examples[1]
+        raise RuntimeError("decode failed")
+    it = L.PrefetchLoader(bad(), pack, keys_fn, batch_size=1, depth=1)
+    next(it); next(it)
+    with pytest.raises(RuntimeError):
+        next(it)
+    # closing a loader whose queue is full does not hang
+    it = L.PrefetchLoader(iter(examples * 50), pack, keys_fn, batch_size=1, depth=1)
+    next(it)
+    it.close()
+    assert not it._thread.is_alive()
+
+    class FakeTrainer(object):
+        def __init__(self):
+            self.pending, self.n = None, 0
+
+        def step_pipelined(self, arrays):
+            prev, self.pending = self.pending, {"total_loss": float(arrays["image"].mean())}
+            self.n += 1
+            return prev
+
+        def flush(self):
+            prev, self.pending = self.pending, None
+            return prev
+    ft = FakeTrainer()
+    losses = L.train_loop(ft, L.PrefetchLoader(iter(examples), pack, keys_fn, batch_size=2, depth=2))
+    assert ft.n == 3 and len(losses) == 3
