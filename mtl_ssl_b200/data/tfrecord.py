@@ -29,12 +29,58 @@ for _i in range(256):
     _TABLE.append(_c)
 
 
-def crc32c(data):
-    """CRC-32C of a bytes-like object (reflected, init / final xor 0xFFFFFFFF)."""
-    c = 0xFFFFFFFF
+_TABLE_NP = np.array(_TABLE, dtype=np.uint32)
+
+
+def _crc_update_slow(c, data):
     for b in bytes(data):
         c = _TABLE[(c ^ b) & 0xFF] ^ (c >> 8)
-    return c ^ 0xFFFFFFFF
+    return c
+
+
+def _gf2_apply(cols, v):
+    """Matrix (32 columns as integers) times bit-vector v over GF(2)."""
+    out, j = 0, 0
+    while v:
+        if v & 1:
+            out ^= cols[j]
+        v >>= 1
+        j += 1
+    return out
+
+
+def _zero_advance_matrix(nbytes):
+    """Columns of the linear map "CRC register after `nbytes` zero bytes" (the register update is linear over GF(2))."""
+    cols = [_TABLE[(1 << j) & 0xFF] ^ ((1 << j) >> 8) for j in range(32)]       # one zero byte
+    result = [1 << j for j in range(32)]                                        # identity
+    n = nbytes
+    while n:
+        if n & 1:
+            result = [_gf2_apply(cols, c) for c in result]
+        cols = [_gf2_apply(cols, c) for c in cols]
+        n >>= 1
+    return result
+
+
+def crc32c(data):
+    """CRC-32C of a bytes-like object (reflected, init / final xor 0xFFFFFFFF).  Large buffers (checkpoint tensors)
+    are cut into equal lanes whose registers advance together in NumPy; the lanes are then chained with the
+    zero-advance operator: R(s, A||B) = R(0, B) xor Z(R(s, A), len B)."""
+    buf = np.frombuffer(bytes(data), dtype=np.uint8) if not isinstance(data, np.ndarray) else data.view(np.uint8).reshape(-1)
+    n = buf.size
+    if n < (1 << 16):
+        return _crc_update_slow(0xFFFFFFFF, buf.tobytes()) ^ 0xFFFFFFFF
+    lanes = int(min(8192, n >> 10))
+    chunk = n // lanes
+    body = buf[:lanes * chunk].reshape(lanes, chunk)
+    regs = np.zeros(lanes, np.uint32)
+    for j in range(chunk):
+        regs = _TABLE_NP[(regs ^ body[:, j]) & 0xFF] ^ (regs >> 8)
+    adv = _zero_advance_matrix(chunk)
+    state = 0xFFFFFFFF
+    for r in regs.tolist():
+        state = _gf2_apply(adv, state) ^ r
+    return _crc_update_slow(state, buf[lanes * chunk:].tobytes()) ^ 0xFFFFFFFF
 
 
 def masked_crc32c(data):

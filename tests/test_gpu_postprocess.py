@@ -224,3 +224,51 @@ def test_evaluation_loop_metrics():
              "groundtruth_boxes": [r["groundtruth_boxes"]], "groundtruth_classes": [r["groundtruth_classes"]]}
     from mtl_ssl_b200 import eval_util
     assert eval_util.evaluate_detection_results_pascal_voc(lists, cats)[key] == 1.0
+
+
+def test_tf_checkpoint_round_trip_through_a_model(tmp_path):
+    """save_tf_checkpoint -> load_tf_checkpoint restores every variable (detection naming, TF layouts), and an
+    ImageNet-style checkpoint (stage scopes stripped) initialises all block4 copies from the same keys (T5, T14)."""
+    import test_gpu_train_step as T
+    from helpers import load_config, randomize_bn
+    from mtl_ssl_b200.builders import model_builder
+    from mtl_ssl_b200.utils import checkpoint_io, tf_checkpoint
+    cfg = load_config("model12.config", T.SMALL)
+    a = model_builder.build(cfg.model, True, device="cuda", seed=0)
+    a.param_store.load_state_dict(randomize_bn(a.param_store.state_dict(), 0))
+    prefix = str(tmp_path / "model.ckpt-7")
+    names = checkpoint_io.save_tf_checkpoint(a, prefix, extra={"global_step": np.asarray(7, np.int64)})
+    assert "global_step" in names and not any("/_dead/" in n or "/_pad/" in n for n in names)
+    r = tf_checkpoint.CheckpointReader(prefix)
+    w = "FirstStageFeatureExtractor/resnet_v1_50/block2/unit_1/bottleneck_v1/conv2/weights"
+    assert r.get_variable_to_shape_map()[w] == [3, 3, 128, 128]                      # HWIO on disk
+    b = model_builder.build(cfg.model, True, device="cuda", seed=1)
+    n, missing = checkpoint_io.load_tf_checkpoint(b, prefix)
+    assert not missing and n > 300
+    sa, sb = a.param_store.state_dict(), b.param_store.state_dict()
+    for k in sa:
+        if "/_pad/" in k:
+            continue
+        assert torch.equal(sa[k].cpu(), sb[k].cpu()), k
+    assert torch.equal(a.param_store.by_name[w].wb, b.param_store.by_name[w].wb)     # folded bf16 copy rebuilt
+    # classification-style checkpoint: first-stage trunk + ONE block4, stage scopes stripped
+    cls = {}
+    for k, v in sa.items():
+        for sc in ("FirstStageFeatureExtractor/", "SecondStageFeatureExtractor/"):
+            if k.startswith(sc) and "/_dead/" not in k and "/_pad/" not in k and "/resnet_v1_50/" in "/" + k:
+                cls[k[len(sc):]] = tf_checkpoint.native_to_tf(k, v.cpu().numpy())
+    prefix2 = str(tmp_path / "resnet_v1_50.ckpt")
+    tf_checkpoint.write_checkpoint(prefix2, cls)
+    c = model_builder.build(cfg.model, True, device="cuda", seed=2)
+    n2, missing2 = checkpoint_io.load_tf_checkpoint(c, prefix2, from_detection_checkpoint=False)
+    assert not missing2
+    sc_ = c.param_store.state_dict()
+    k2 = "resnet_v1_50/block4/unit_2/bottleneck_v1/conv2/weights"
+    for scope in ("SecondStageFeatureExtractor/", "ClosenessBoxPredictor/", "WindowBoxPredictor/",
+                  "FirstStageFeatureExtractor/_dead/"):
+        assert torch.equal(sc_[scope + k2].cpu(), sa["SecondStageFeatureExtractor/" + k2].cpu()), scope
+    k1 = "FirstStageFeatureExtractor/resnet_v1_50/block3/unit_3/bottleneck_v1/conv1/BatchNorm/moving_variance"
+    assert torch.equal(sc_[k1].cpu(), sa[k1].cpu())
+    # heads are not in a classification checkpoint: untouched (still the seed-2 initialisation)
+    kh = "SecondStageBoxPredictor/ClassPredictor/weights"
+    assert not torch.equal(sc_[kh].cpu(), sa[kh].cpu())
