@@ -15,7 +15,7 @@ keeping the class and method names a caller of the reference uses (`ObjectDetect
   * difficult boxes do not count as ground-truth instances for recall but do count for CorLoc;
   * boxes with ymin >= ymax or xmin >= xmax are discarded; per-class NMS before matching is the reference's
     `np_box_list_ops.non_max_suppression` (IoU threshold 1.0 by default = "keep the best `max_output` boxes").
-Only nms_type 'standard' is built (the fork's soft-NMS variants raise NotImplementedError)."""
+nms_type 'soft-linear' / 'soft-gaussian' (the fork's addition) decay the scores of overlapping boxes instead."""
 import logging
 
 import numpy as np
@@ -109,14 +109,52 @@ def _standard_nms(boxes, scores, max_output, iou_threshold, score_threshold=-10.
     return np.asarray(chosen, int)
 
 
+def _soft_nms(boxes, scores, max_output, iou_threshold, kind, sigma, score_threshold=-10.0):
+    """np_box_list_ops.soft_non_max_suppression:258-363 (Bodla et al. 2017) -> (kept indices ranked, their DECAYED
+    scores).  kind 2: linear (score *= 1 - IoU where IoU >= threshold), kind 3: gaussian (score *= exp(-IoU^2 / sigma)).
+    The best remaining box is taken repeatedly (first index among equal scores, after the initial descending sort) and
+    decays every box still in the pool; finally boxes with score > max(0, score_threshold) are re-ranked."""
+    keep = np.nonzero(scores > score_threshold)[0]
+    if keep.size == 0:
+        return keep, scores[keep]
+    ranked = keep[np.argsort(scores[keep])[::-1]]
+    if iou_threshold == 1.0:
+        ranked = ranked[:max_output]
+        return ranked, scores[ranked]
+    b = boxes[ranked]
+    sc = np.array(scores[ranked], dtype=scores.dtype)
+    pool = np.ones(len(ranked), bool)
+    taken = 0
+    for _ in range(len(ranked)):
+        if taken >= max_output:
+            break
+        cand = np.where(pool, sc, -np.inf)
+        j = int(np.argmax(cand))                       # first maximum, like the reference's strict `>` scan
+        if not (pool[j] and sc[j] > score_threshold):
+            break
+        taken += 1
+        pool[j] = False
+        rest = np.nonzero(pool)[0]
+        if rest.size == 0:
+            break
+        iou = _iou_matrix(b[j][None], b[rest])[0]
+        if kind == 2:
+            w = 1.0 - np.where(iou < iou_threshold, 0.0, iou)
+        else:
+            w = np.exp(-np.square(iou) / sigma)
+        sc[rest] = sc[rest] * w
+    alive = np.nonzero(sc > max(0.0, score_threshold))[0]
+    order = alive[np.argsort(sc[alive])[::-1]][:max_output]
+    return ranked[order], sc[order]
+
+
 # ----------------------------------------------------------------------------- one image
 class PerImageEvaluation(object):
     def __init__(self, num_groundtruth_classes, matching_iou_threshold=0.5, nms_type="standard", nms_iou_threshold=1.0,
                  nms_max_output_boxes=100, soft_nms_sigma=0.5):
-        if nms_type != "standard":
-            if nms_type in ("soft-linear", "soft-gaussian"):
-                raise NotImplementedError("soft NMS in the evaluator is not built")
+        if nms_type not in ("standard", "soft-linear", "soft-gaussian"):
             raise ValueError("Cannot identify NMS type.")
+        self.nms_type, self.soft_nms_sigma = nms_type, soft_nms_sigma
         if nms_iou_threshold < 0.0 or nms_iou_threshold > 1.0:
             raise ValueError("IOU threshold must be in [0, 1]")
         self.num_groundtruth_classes = num_groundtruth_classes
@@ -149,8 +187,13 @@ class PerImageEvaluation(object):
     def _label_class(self, boxes, scores, gt_boxes, gt_hard):
         if boxes.size == 0:
             return np.array([], float), np.array([], bool)
-        keep = _standard_nms(boxes, scores, self.nms_max_output_boxes, self.nms_iou_threshold)
-        boxes, scores = boxes[keep], scores[keep]
+        if self.nms_type == "standard":
+            keep = _standard_nms(boxes, scores, self.nms_max_output_boxes, self.nms_iou_threshold)
+            boxes, scores = boxes[keep], scores[keep]
+        else:
+            keep, scores = _soft_nms(boxes, scores, self.nms_max_output_boxes, self.nms_iou_threshold,
+                                     2 if self.nms_type == "soft-linear" else 3, self.soft_nms_sigma)
+            boxes = boxes[keep]
         if gt_boxes.size == 0:
             return scores, np.zeros(len(scores), bool)
         iou = _iou_matrix(boxes, gt_boxes)

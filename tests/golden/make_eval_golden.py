@@ -21,10 +21,11 @@ from object_detection.utils import object_detection_evaluation as ref_ode      #
 from object_detection.utils import metrics as ref_metrics                      # noqa: E402
 
 
-def scenario(seed, num_class, num_images, subsets, nms_iou, nms_max):
+def scenario(seed, num_class, num_images, subsets, nms_iou, nms_max, nms_type="standard", sigma=0.5):
     rng = np.random.default_rng(seed)
-    ev = ref_ode.ObjectDetectionEvaluation(num_class, matching_iou_threshold=0.5, nms_iou_threshold=nms_iou,
-                                           nms_max_output_boxes=nms_max, subset_names=subsets)
+    ev = ref_ode.ObjectDetectionEvaluation(num_class, matching_iou_threshold=0.5, nms_type=nms_type,
+                                           nms_iou_threshold=nms_iou, nms_max_output_boxes=nms_max,
+                                           soft_nms_sigma=sigma, subset_names=subsets)
     data = []
     for i in range(num_images):
         g = int(rng.integers(0, 6))
@@ -53,10 +54,14 @@ def scenario(seed, num_class, num_images, subsets, nms_iou, nms_max):
 
 def main():
     out = {}
-    cases = [(0, 3, 12, ("default",), 1.0, 10000), (1, 4, 20, ("default", "small"), 1.0, 10000),
-             (2, 2, 15, ("default",), 0.6, 5), (3, 5, 30, ("a", "b", "c"), 0.3, 10000)]
-    for ci, (seed, C, N, subsets, nms_iou, nms_max) in enumerate(cases):
-        data, ap, mean_ap, corloc, mean_corloc = scenario(seed, C, N, subsets, nms_iou, nms_max)
+    cases = [(0, 3, 12, ("default",), 1.0, 10000, "standard", 0.5), (1, 4, 20, ("default", "small"), 1.0, 10000, "standard", 0.5),
+             (2, 2, 15, ("default",), 0.6, 5, "standard", 0.5), (3, 5, 30, ("a", "b", "c"), 0.3, 10000, "standard", 0.5),
+             (4, 3, 25, ("default",), 0.3, 10000, "soft-linear", 0.5), (5, 3, 25, ("default",), 0.5, 10000, "soft-gaussian", 0.3),
+             (6, 2, 20, ("default",), 0.4, 4, "soft-gaussian", 0.5)]
+    for ci, (seed, C, N, subsets, nms_iou, nms_max, nms_type, sigma) in enumerate(cases):
+        data, ap, mean_ap, corloc, mean_corloc = scenario(seed, C, N, subsets, nms_iou, nms_max, nms_type, sigma)
+        out["case%d/nms_type" % ci] = np.array(nms_type)
+        out["case%d/sigma" % ci] = np.array(sigma)
         out["case%d/meta" % ci] = np.array([seed, C, N, nms_max], np.int64)
         out["case%d/nms_iou" % ci] = np.array(nms_iou)
         out["case%d/subsets" % ci] = np.array(subsets)

@@ -68,19 +68,20 @@ def test_object_detection_evaluation_reference_case():
         ev.add_single_detected_image_info("img9", np.zeros((2, 4)), np.zeros(1), np.zeros(2, int))
     with pytest.raises(ValueError):
         ev.add_single_ground_truth_image_info("img9", np.zeros((1, 4)), np.zeros(1, int), ["nosuchsubset"])
-    with pytest.raises(NotImplementedError):
-        E.PerImageEvaluation(3, nms_type="soft-linear")
+    with pytest.raises(ValueError):
+        E.PerImageEvaluation(3, nms_type="soft-cubic")
 
 
 def test_against_reference_evaluator_outputs():
     g = np.load(GOLD)
     ncase = len([k for k in g.files if k.endswith("/meta")])
-    assert ncase == 4
+    assert ncase == 7                                  # 4 x standard NMS, soft-linear, 2 x soft-gaussian
     for ci in range(ncase):
         seed, C, N, nms_max = [int(v) for v in g["case%d/meta" % ci]]
         subsets = tuple(str(s) for s in g["case%d/subsets" % ci])
-        ev = E.ObjectDetectionEvaluation(C, matching_iou_threshold=0.5, nms_iou_threshold=float(g["case%d/nms_iou" % ci]),
-                                         nms_max_output_boxes=nms_max, subset_names=subsets)
+        ev = E.ObjectDetectionEvaluation(C, matching_iou_threshold=0.5, nms_type=str(g["case%d/nms_type" % ci]),
+                                         nms_iou_threshold=float(g["case%d/nms_iou" % ci]), nms_max_output_boxes=nms_max,
+                                         soft_nms_sigma=float(g["case%d/sigma" % ci]), subset_names=subsets)
         for i in range(N):
             p = "case%d/img%d/" % (ci, i)
             sub = [str(s) for s in g[p + "sub"]]
