@@ -255,3 +255,71 @@ def test_prefetch_loader_order_errors_and_shutdown(tmp_path):
     ft = FakeTrainer()
     losses = L.train_loop(ft, L.PrefetchLoader(iter(examples), pack, keys_fn, batch_size=2, depth=2))
     assert ft.n == 3 and len(losses) == 3
+
+
+_VOC_XML = """<annotation><folder>VOC2007</folder><filename>%s</filename>
+<size><width>256</width><height>256</height><depth>3</depth></size>
+<object><name>person</name><pose>Left</pose><truncated>0</truncated><difficult>1</difficult>
+<bndbox><xmin>64</xmin><ymin>64</ymin><xmax>192</xmax><ymax>192</ymax></bndbox></object>
+<object><name>notperson</name><pose>Frontal</pose><truncated>1</truncated><difficult>0</difficult>
+<bndbox><xmin>10</xmin><ymin>20</ymin><xmax>110</xmax><ymax>220</ymax></bndbox></object></annotation>"""
+
+
+def test_pascal_voc_records_reference_expectations(tmp_path):
+    """create_pascal_tf_record_test.py:39-113 (`test_dict_to_tf_example`: the standard keys of one 256x256 image with a
+    'person' box 64..192) + XML parsing, the aux-label keys, the VOC directory reader and the decoder round trip."""
+    from PIL import Image
+    from mtl_ssl_b200.data import pascal_voc as V
+    root = tmp_path / "VOC2007"
+    for d in ("JPEGImages", "Annotations", "ImageSets/Main"):
+        os.makedirs(str(root / d))
+    name = "tmp_image.jpg"
+    rng = np.random.default_rng(0)
+    Image.fromarray(rng.integers(0, 256, (256, 256, 3), dtype=np.uint8), "RGB").save(str(root / "JPEGImages" / name))
+    data = {"folder": "", "filename": name, "size": {"height": 256, "width": 256},
+            "object": [{"difficult": 1, "bndbox": {"xmin": 64, "ymin": 64, "xmax": 192, "ymax": 192}, "name": "person",
+                        "truncated": 0, "pose": ""}]}
+    label_map = {"background": 0, "person": 1, "notperson": 2}
+    ex = T.parse_example(V.dict_to_tf_example(data, str(root), label_map, image_subdirectory="JPEGImages"))
+    assert ex["image/height"].tolist() == [256] and ex["image/width"].tolist() == [256]
+    assert ex["image/filename"] == [name.encode()] and ex["image/source_id"] == [name.encode()]
+    assert ex["image/format"] == [b"jpeg"]
+    for k, v in (("xmin", 0.25), ("ymin", 0.25), ("xmax", 0.75), ("ymax", 0.75)):
+        assert ex["image/object/bbox/" + k].tolist() == [v]
+    assert ex["image/object/class/text"] == [b"person"] and ex["image/object/class/label"].tolist() == [1]
+    assert ex["image/object/difficult"].tolist() == [1] and ex["image/object/truncated"].tolist() == [0]
+    assert ex["image/object/view"] == [b""] and ex["image/object/subset"] == [b"all"]
+    assert len(ex["image/key/sha256"][0]) == 64
+    # the fork's keys: 64 windows with K+1 soft labels, one closeness row per object, a [2,64,64] edge mask
+    assert len(ex["image/window/labels/text"]) == len(ex["image/window/bbox/ymin"]) == 64
+    assert len(ex["image/object/closeness/text"]) == 1
+    assert ex["image/edgemask/height"].tolist() == [64] and len(ex["image/edgemask/masks"]) == 2 * 64 * 64
+    with pytest.raises(ValueError):                                       # PNG on disk: "Image format not JPEG"
+        Image.fromarray(np.zeros((8, 8, 3), np.uint8)).save(str(root / "JPEGImages" / "p.jpg"), format="PNG")
+        V.dict_to_tf_example(dict(data, filename="p.jpg"), str(root), label_map)
+    # XML -> dict -> example, the directory reader, and the record decoder agree
+    open(str(root / "Annotations" / "tmp_image.xml"), "w").write(_VOC_XML % name)
+    open(str(root / "ImageSets" / "Main" / "trainval.txt"), "w").write("tmp_image\n")
+    parsed = V.parse_annotation(str(root / "Annotations" / "tmp_image.xml"))
+    assert [o["name"] for o in parsed["object"]] == ["person", "notperson"] and parsed["size"]["width"] == "256"
+    assert parsed["object"][1]["bndbox"] == {"xmin": "10", "ymin": "20", "xmax": "110", "ymax": "220"}
+    ds = V.VocDataset(str(root), "trainval", label_map, num_classes=2, seed=3, num_windows=16)
+    (e,) = list(ds)
+    assert len(ds) == 1 and e["image"].shape == (256, 256, 3) and e["groundtruth_difficult"].tolist() == [True, False]
+    np.testing.assert_allclose(e["groundtruth_boxes"], [[0.25, 0.25, 0.75, 0.75], [20 / 256, 10 / 256, 220 / 256, 110 / 256]])
+    assert e["groundtruth_classes"].tolist() == [[1, 0], [0, 1]]
+    assert e["window_boxes"].shape == (16, 4) and e["window_classes"].shape == (16, 3)
+    assert e["groundtruth_closeness"].shape == (2, 3) and e["groundtruth_edgemask"].shape == (2, 64, 64)
+    # the XML's <folder> is joined under the devkit root, like the reference (`data['folder']/JPEGImages/<file>`)
+    rec = V.dict_to_tf_example(parsed, str(tmp_path), label_map, num_classes=2, rng=np.random.default_rng(3),
+                               num_windows=16)
+    d = T.decode_example(rec, 2)
+    np.testing.assert_allclose(d["groundtruth_boxes"], e["groundtruth_boxes"], rtol=1e-6)
+    np.testing.assert_array_equal(d["groundtruth_classes"], e["groundtruth_classes"])
+    np.testing.assert_allclose(d["window_boxes"], e["window_boxes"], rtol=1e-6)
+    np.testing.assert_allclose(d["window_classes"], e["window_classes"], atol=5e-4)
+    np.testing.assert_allclose(d["groundtruth_closeness"], e["groundtruth_closeness"], atol=5e-4)
+    np.testing.assert_array_equal(d["groundtruth_edgemask"], e["groundtruth_edgemask"])
+    assert d["groundtruth_difficult"].tolist() == [True, False] and d["groundtruth_subset"] == ["all", "all"]
+    only_easy = list(V.VocDataset(str(root), "trainval", label_map, 2, ignore_difficult_instances=True))[0]
+    assert only_easy["groundtruth_classes"].tolist() == [[0, 1]]
