@@ -322,3 +322,44 @@ def test_second_stage_postprocess_hand_case():
     # num_valid_boxes: only the first proposal is valid -> one detection
     b, s, c, n = PP.second_stage_postprocess(enc, logits, props, [1], (40, 40), 0.25, 0.5, 10, 5, score_mode="identity")
     assert n.tolist() == [1.0] and s[0, 0] == np.float32(.9)
+
+
+def test_aux_labels_against_reference_record_writer():
+    """N1 pinned: window soft labels, closeness labels and the 64x64 edge mask of data/aux_labels.py against the outputs
+    of the reference's record writer (create_pascal_tf_record.py:121-421) RUN in this container under recording stubs
+    for TensorFlow (tests/golden/make_aux_golden.py -> aux_reference.npz).  The reference samples its windows from
+    Python's global RNG; the labels are recomputed here for exactly those windows."""
+    import os
+    from mtl_ssl_b200.data import aux_labels as A
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "aux_reference.npz"))
+    K = int(g["num_classes"])
+    rows = lambda arr: np.array([[float(t) for t in str(s).split()] for s in arr], np.float64)
+    n_windows = 0
+    for c in range(int(g["num_cases"])):
+        p = "case%d/" % c
+        H, W = [float(v) for v in g[p + "hw"]]
+        boxes, classes = g[p + "boxes"], g[p + "classes"]
+        # closeness: one row per object, K+1 columns, rounded to 3 decimals by get_string_label
+        want = rows(g[p + "closeness"])
+        got = A.closeness_labels(boxes, classes, H, W, K)
+        assert got.shape == want.shape == (len(boxes), K + 1)
+        np.testing.assert_allclose(got, want, atol=1e-6)
+        # edge mask: [2, 64, 64] = (foreground, weight plane)
+        eh, ew = [int(v) for v in g[p + "edgemask_hw"]]
+        want_em = g[p + "edgemask"].reshape(-1, eh, ew)
+        got_em = A.edgemask(boxes, H, W)
+        assert got_em.shape == want_em.shape == (2, 64, 64)
+        np.testing.assert_array_equal(got_em[0], want_em[0])
+        np.testing.assert_allclose(got_em[1], want_em[1], rtol=1e-6)
+        # window soft labels for the reference's own windows
+        wl = rows(g[p + "window_labels"])
+        assert wl.shape == (64, K + 1)
+        for i in range(64):
+            window = [g[p + "window_ymin"][i] * H, g[p + "window_xmin"][i] * W, g[p + "window_ymax"][i] * H,
+                      g[p + "window_xmax"][i] * W]
+            lab, bg = A.window_label(boxes, classes, window, K)
+            # the window travelled through float32 and a divide / multiply by the image size: allow one rounding step
+            np.testing.assert_allclose(lab, wl[i], atol=1.001e-3)
+            assert abs(lab.sum() - 1.0) < 5e-3 and bg < 1.0
+            n_windows += 1
+    assert n_windows == 6 * 64
