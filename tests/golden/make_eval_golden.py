@@ -116,6 +116,48 @@ def main():
     m = ref_mtl.get_mtl_metrics(res)
     out["mtl/n"] = np.array(nimg)
     out["mtl/window_map"], out["mtl/closeness_diff"] = np.array(m["mtl/window_map"]), np.array(m["mtl/closeness_diff"])
+    # metric assembly of eval_util.evaluate_detection_results_pascal_voc (label offset, `difficult`, subsets, names);
+    # matplotlib / TensorFlow / the label-map protobuf are absent: stubbed, the PR-curve plot is switched off
+    for name in ("matplotlib", "matplotlib.pyplot", "matplotlib.backends", "matplotlib.backends.backend_agg",
+                 "matplotlib.figure", "tensorflow", "global_utils", "global_utils.custom_utils",
+                 "object_detection.utils.label_map_util", "object_detection.utils.visualization_utils"):
+        sys.modules[name] = types.ModuleType(name)
+    sys.modules["matplotlib"].use = lambda *a, **k: None
+    sys.modules["matplotlib.backends.backend_agg"].FigureCanvasAgg = object
+    sys.modules["matplotlib.figure"].Figure = object
+    sys.modules["tensorflow"].contrib = types.SimpleNamespace(slim=None)
+    quiet = types.SimpleNamespace(**{k: (lambda *a, **kw: None) for k in ("info", "infov", "warn", "warning", "error")})
+    sys.modules["global_utils.custom_utils"].log = quiet
+    sys.modules["object_detection.utils.label_map_util"].create_category_index = \
+        lambda categories: {c["id"]: c for c in categories}
+    from object_detection import eval_util as ref_eval
+    ref_eval.visualize_pr_curve = lambda *a, **k: None
+    rng = np.random.default_rng(33)
+    C, nimg = 4, 14
+    cats = [{"id": i + 1, "name": "cat%d" % (i + 1)} for i in range(C)]
+    lists = {k: [] for k in ("detection_boxes", "detection_scores", "detection_classes", "image_id", "groundtruth_boxes",
+                             "groundtruth_classes", "difficult", "groundtruth_subset")}
+    for i in range(nimg):
+        g_, n_ = int(rng.integers(1, 6)), int(rng.integers(1, 10))
+        y0, x0 = rng.uniform(0, 60, g_), rng.uniform(0, 60, g_)
+        gb = np.stack([y0, x0, y0 + rng.uniform(5, 40, g_), x0 + rng.uniform(5, 40, g_)], 1)
+        src = rng.integers(0, g_, n_)
+        db = gb[src] + rng.normal(0, 4.0, (n_, 4))
+        gc = rng.integers(1, C + 1, g_)
+        lists["groundtruth_boxes"].append(gb); lists["groundtruth_classes"].append(gc)
+        lists["difficult"].append((rng.random(g_) < 0.25).astype(np.int64))
+        lists["groundtruth_subset"].append(np.array(["|".join(s for s in ("all", "big") if s == "all" or rng.random() < 0.5)
+                                                     for _ in range(g_)]))
+        lists["detection_boxes"].append(db); lists["detection_scores"].append(np.round(rng.random(n_), 2))
+        lists["detection_classes"].append(np.where(rng.random(n_) < 0.8, gc[src], rng.integers(1, C + 1, n_)))
+        lists["image_id"].append(str(1000 + i))
+    m = ref_eval.evaluate_detection_results_pascal_voc(lists, cats, corloc_summary=True)
+    out["voc/n"] = np.array(nimg)
+    for k in lists:
+        for i, v in enumerate(lists[k]):
+            out["voc/%s/%d" % (k, i)] = np.asarray(v)
+    out["voc/metric_names"] = np.array(sorted(m), dtype="U128")
+    out["voc/metric_values"] = np.array([m[k] for k in sorted(m)], np.float64)
     np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "eval_reference.npz"), **out)
     print("wrote eval_reference.npz with %d arrays" % len(out))
 

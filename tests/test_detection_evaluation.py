@@ -162,3 +162,23 @@ def test_eval_util_pascal_metric_assembly():
     assert m["Subset hard       mAP@0.5IOU/a"] == 0.0
     with pytest.raises(ValueError):
         eval_util.evaluate_detection_results_pascal_voc({"detection_boxes": []}, cats)
+
+
+def test_eval_util_against_reference_function_outputs():
+    """eval_util.evaluate_detection_results_pascal_voc of the reference, RUN here under stubs for matplotlib / TensorFlow
+    (tests/golden/make_eval_golden.py): identical metric names and values on random detections with `difficult` flags and
+    two subsets."""
+    from mtl_ssl_b200 import eval_util
+    g = np.load(GOLD)
+    n = int(g["voc/n"])
+    keys = ("detection_boxes", "detection_scores", "detection_classes", "image_id", "groundtruth_boxes",
+            "groundtruth_classes", "difficult", "groundtruth_subset")
+    lists = {k: [g["voc/%s/%d" % (k, i)] for i in range(n)] for k in keys}
+    lists["image_id"] = [str(v) for v in lists["image_id"]]
+    lists["groundtruth_subset"] = [np.array([str(s) for s in v]) for v in lists["groundtruth_subset"]]
+    cats = [{"id": i + 1, "name": "cat%d" % (i + 1)} for i in range(4)]
+    m = eval_util.evaluate_detection_results_pascal_voc(lists, cats, corloc_summary=True)
+    names = [str(s) for s in g["voc/metric_names"]]
+    assert sorted(m) == names
+    np.testing.assert_allclose([m[k] for k in names], g["voc/metric_values"], rtol=1e-12, equal_nan=True)
+    assert any(k.startswith("Subset big") for k in names) and any(k.startswith("Subset all") for k in names)
