@@ -6,8 +6,6 @@ thread that drives the GPU; `Trainer.step_pipelined` then overlaps the H2D copy 
 import queue
 import threading
 
-import numpy as np
-
 from . import augment, synthetic
 
 
