@@ -397,3 +397,38 @@ def test_losses_against_reference_loss_classes_run_on_a_numpy_tf_shim():
     filled = np.where(np.isnan(tn), g["loc/pred"], tn)
     l = ON.smooth_l1(T(g["loc/pred"]), T(filled), T(g["loc/weights"]), sigma=1.0).numpy()
     np.testing.assert_allclose(l, g["loc/ignore_nan"], rtol=2e-5, atol=1e-6)
+
+
+def test_target_assigner_against_reference_code_run_on_the_tf_shim():
+    """core/target_assigner.py `TargetAssigner.assign` of the reference (IouSimilarity, ArgMaxMatcher incl. force-match,
+    FasterRcnnBoxCoder, the dead crowd / ignore branch T6, and the fork's `extension=True` closeness targets
+    `_create_mtl_targets`), EXECUTED here on tests/golden/tf_numpy_shim.py (make_assign_golden.py ->
+    assign_reference.npz), against oracle/assign.py: matches and class targets bit-exact, box encodings to fp32
+    rounding (log / divide)."""
+    import os
+    from oracle import assign as OA
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "assign_reference.npz"))
+    saw_forced = False
+    for c in range(int(g["num_cases"])):
+        p = "det%d/" % c
+        got = OA.assign_detection(g[p + "props"], g[p + "gt"], g[p + "cls"], g[p + "closeness"])
+        assert np.array_equal(got["match"], g[p + "match"])
+        assert np.array_equal(got["cls_targets"], g[p + "cls_targets"])
+        assert np.array_equal(got["cls_weights"], g[p + "cls_weights"])
+        assert np.array_equal(got["reg_weights"], g[p + "reg_weights"])
+        np.testing.assert_allclose(got["reg_targets"], g[p + "reg_targets"], rtol=2e-5, atol=2e-6)
+        assert np.array_equal(got["closeness_targets"], g[p + "closeness_targets"])          # gathered, not computed
+        assert got["closeness_targets"][got["match"] < 0].sum() == 0 and (got["match"] >= 0).any()
+        r = "rpn%d/" % c
+        got = OA.assign_proposal(g[p + "props"], g[p + "gt"])
+        assert np.array_equal(got["match"], g[r + "match"])
+        assert np.array_equal(got["cls_targets"].reshape(-1), g[r + "cls_targets"].reshape(-1))
+        assert np.array_equal(got["cls_weights"], g[r + "cls_weights"])
+        assert np.array_equal(got["reg_weights"], g[r + "reg_weights"])
+        np.testing.assert_allclose(got["reg_targets"], g[r + "reg_targets"], rtol=2e-5, atol=2e-6)
+        # 0.7 / 0.3 thresholds: ignored anchors (-2) carry zero class weight, and every ground-truth box owns an anchor
+        assert (got["cls_weights"][got["match"] == -2] == 0).all()
+        assert set(range(len(g[p + "gt"]))) <= set(got["match"][got["match"] >= 0].tolist())
+        iou_best = None
+        saw_forced = saw_forced or bool(((got["match"] >= 0) & (g[r + "cls_weights"] > 0)).any())
+    assert saw_forced
