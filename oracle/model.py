@@ -477,7 +477,18 @@ class Oracle(object):
             obj_l = obj_l + obj.sum() / norm
         losses["first_stage_localization_loss"] = cfg["first_stage_localization_loss_weight"] * loc_l / B
         losses["first_stage_objectness_loss"] = cfg["first_stage_objectness_loss_weight"] * obj_l / B
-        # _loss_box_classifier
+        losses.update(self.loss_second_stage(out, examples))
+        return losses
+
+    def loss_second_stage(self, out, examples):
+        """fmA `_loss_box_classifier` :1670-1793 (incl. closeness), `_loss_refined_classifier` :1795-1837,
+        `_loss_window_class` :1839-1858, `_loss_edgemask` :1860-1881.  Pinned against those methods executed on the
+        NumPy TF shim (tests/golden/make_stage2_loss_golden.py)."""
+        cfg, mtl = self.cfg, self.cfg["mtl"]
+        B = len(examples)
+        K1 = cfg["num_classes"] + 1
+        P = cfg["second_stage_batch_size"]
+        losses = {}
         cls_t, reg_t, reg_w, cls_w, close_t = [], [], [], [], []
         for b in range(B):
             gt_abs, gt_cls_bg, gt_close = out["gts"][b]

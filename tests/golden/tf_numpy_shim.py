@@ -218,6 +218,17 @@ def make_tf():
     tf.cond = lambda pred, true_fn=None, false_fn=None, fn1=None, fn2=None, **k: \
         (true_fn or fn1)() if bool(np.asarray(pred)) else (false_fn or fn2)()
     tf.setdiff1d = _setdiff1d
+    tf.AUTO_REUSE = "AUTO_REUSE"
+    tf.add_to_collection = lambda *a, **k: None
+    tf.summary = types.SimpleNamespace(scalar=lambda *a, **k: None, histogram=lambda *a, **k: None,
+                                       image=lambda *a, **k: None)
+    tf.pad = _w(lambda x, paddings, mode="CONSTANT", constant_values=0:
+                np.pad(np.asarray(x), [tuple(int(v) for v in p) for p in np.asarray(paddings)], constant_values=constant_values))
+    tf.one_hot = _w(lambda idx, depth, on_value=1.0, off_value=0.0, dtype=np.float32, axis=-1:
+                    np.where(np.arange(int(depth)) == np.asarray(idx)[..., None], on_value, off_value).astype(dtype))
+    tf.random_shuffle = _w(lambda x, seed=None: np.random.permutation(np.asarray(x)))
+    tf.slice = _w(lambda x, begin, size: np.asarray(x)[tuple(slice(int(b), None if int(s) < 0 else int(b) + int(s))
+                                                         for b, s in zip(_ints(begin), _ints(size)))])
     tf.nn = types.SimpleNamespace()
     tf.image = types.SimpleNamespace()
     tf.app = types.SimpleNamespace(flags=types.SimpleNamespace())

@@ -432,3 +432,40 @@ def test_target_assigner_against_reference_code_run_on_the_tf_shim():
         iou_best = None
         saw_forced = saw_forced or bool(((got["match"] >= 0) & (g[r + "cls_weights"] > 0)).any())
     assert saw_forced
+
+
+def test_second_stage_losses_against_reference_meta_arch_methods_run_on_the_tf_shim():
+    """fmA `_loss_box_classifier` (:1670-1793, with the closeness loss), `_loss_refined_classifier` (:1795-1837),
+    `_loss_window_class` (:1839-1858) and `_loss_edgemask` (:1860-1881) of the reference, EXECUTED here as unbound
+    methods on the NumPy TF shim (tests/golden/make_stage2_loss_golden.py -> stage2_loss_reference.npz), against
+    `Oracle.loss_second_stage`: the normalisers (T15), the padding indicator for short proposal lists, the class-selected
+    box code (T12), the closeness column drop and its two normalisers (T11), the edge-mask label construction.
+    Tolerance 2e-5 relative (fp32 log-softmax / bilinear resize sums)."""
+    import os
+    import torch
+    from oracle.model import Oracle
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "stage2_loss_reference.npz"))
+    K, P, B, ncases = [int(v) for v in g["meta"]]
+    cfg = dict(architecture="resnet_v1_101", num_classes=K, second_stage_batch_size=P,
+               second_stage_localization_loss_weight=2.0, second_stage_classification_loss_weight=1.0,
+               mtl=dict(window=True, closeness=True, edgemask=True, refine=True, window_class_loss_weight=1.0,
+                        closeness_loss_weight=0.3, edgemask_loss_weight=1.0, refined_classification_loss_weight=1.0))
+    o = Oracle({}, cfg, bf16=False)
+    T = torch.from_numpy
+    short = False
+    for c in range(ncases):
+        p = "case%d/" % c
+        nprop = g[p + "nprop"]
+        short = short or bool((nprop < P).any())
+        out = dict(gts=[(g[p + "gt%d" % b], g[p + "cls%d" % b], g[p + "close%d" % b]) for b in range(B)],
+                   prop_abs=g[p + "props"], nprop=nprop, refined_box_encodings=T(g[p + "enc"]),
+                   class_predictions_with_background=T(g[p + "logits"]), closeness_predictions=T(g[p + "close_pred"]),
+                   mtl_refined_class_predictions_with_background=T(g[p + "refined"]),
+                   window_class_predictions=T(g[p + "win_pred"]), edgemask_predictions=T(g[p + "em_pred"]))
+        examples = [dict(window_classes=g[p + "win_lab"][b], groundtruth_edgemask=g[p + "em_gt"][b]) for b in range(B)]
+        got = o.loss_second_stage(out, examples)
+        want = {k[len(p) + 5:]: float(g[k]) for k in g.files if k.startswith(p + "loss/")}
+        assert set(got) == set(want) and len(want) == 6
+        for k, v in want.items():
+            np.testing.assert_allclose(float(got[k]), v, rtol=2e-5, err_msg=p + k)
+    assert short                                                    # a padded proposal list was exercised
