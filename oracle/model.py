@@ -292,6 +292,28 @@ class Oracle(object):
         return outs
 
     # ------------------------------------------------------------------ forward
+    def training_proposals(self, rpn_box, rpn_cls, anchors, gt_abs, gt_cls_bg, key, H, W):
+        """`_postprocess_rpn` in training mode for one image (fmA:1055-1132): decode / score filter / clip / NMS ->
+        `_unpad_proposals_and_sample_box_classifier_batch` (fmA:1134-1216) with `_sample_box_classifier_minibatch`
+        (:1268-1302: detector assignment, the all-ignored guard, balanced sampling that keeps score order) -> zero pad to
+        second_stage_batch_size -> normalise by the image size (:1123-1131).  Pinned against those methods executed on
+        the NumPy TF shim (tests/golden/make_graph_golden.py).
+        Returns (normalised boxes [P,4], scores [P], count, (nms boxes, nms scores, nms count))."""
+        cfg = self.cfg
+        P, M = cfg["second_stage_batch_size"], cfg["first_stage_max_proposals"]
+        pb, ps, n = OP.rpn_postprocess_single(rpn_box, rpn_cls, anchors, (H, W), cfg["nms_score_threshold"],
+                                              cfg["nms_iou_threshold"], M)
+        t = OA.assign_detection(pb[:n], gt_abs, gt_cls_bg)
+        cls_w = t["cls_weights"] + np.float32(t["cls_weights"].sum() == 0)      # fmA:1296
+        pos = t["cls_targets"].argmax(1) > 0
+        sel = OA.balanced_subsample(cls_w > 0, P, pos, cfg["second_stage_balance_fraction"], np.asarray(key)[:n])
+        idx = np.nonzero(sel)[0][:P]
+        boxes = np.zeros((P, 4), np.float32)
+        scores = np.zeros((P,), np.float32)
+        boxes[:len(idx)] = OB.to_normalized_coordinates(pb[idx], H, W)
+        scores[:len(idx)] = ps[idx]
+        return boxes, scores, len(idx), (pb, ps, n)
+
     def forward(self, images, examples, keys, H, W, proposal_inputs=None, inference=False):
         """proposal_inputs: optional (rpn_box [B,N,4], rpn_cls [B,N,2]) numpy arrays used INSTEAD of the
         oracle's own RPN outputs for the (non-differentiable) proposal selection, so that index-level
@@ -352,18 +374,11 @@ class Oracle(object):
             gts.append((gt_abs, gt_cls_bg, np.asarray(ex["groundtruth_closeness"], np.float32)))
             src_box = proposal_inputs[0][b] if proposal_inputs is not None else rpn_box[b].detach().numpy()
             src_cls = proposal_inputs[1][b] if proposal_inputs is not None else rpn_cls[b].detach().numpy()
-            pb, ps, n = OP.rpn_postprocess_single(src_box, src_cls, anchors,
-                                                  (H, W), cfg["nms_score_threshold"], cfg["nms_iou_threshold"], M)
-            nms_out.append((pb, ps, n))
-            t = OA.assign_detection(pb[:n], gt_abs, gt_cls_bg)
-            pos = t["cls_targets"].argmax(1) > 0
-            sel = OA.balanced_subsample(t["cls_weights"] > 0, P, pos, cfg["second_stage_balance_fraction"],
-                                        keys[1][b][:n])
-            idx = np.nonzero(sel)[0][:P]
-            nprop[b] = len(idx)
-            nb = OB.to_normalized_coordinates(pb[idx], H, W)
-            prop_norm[b, :len(idx)] = nb
-            prop_abs[b, :len(idx)] = OB.to_absolute_coordinates(nb, H, W)          # fmA:682-683
+            nb, _, cnt, nms = self.training_proposals(src_box, src_cls, anchors, gt_abs, gt_cls_bg, keys[1][b], H, W)
+            nms_out.append(nms)
+            nprop[b] = cnt
+            prop_norm[b] = nb
+            prop_abs[b, :cnt] = OB.to_absolute_coordinates(nb[:cnt], H, W)        # fmA:682-683
         c = cfg["initial_crop_size"]
         mk = cfg["maxpool_kernel_size"]
 
@@ -420,17 +435,9 @@ class Oracle(object):
             w = p["EdgeMaskPredictor/BoxEncodingPredictor/weights"].reshape(2, -1)
             out["edgemask_predictions"] = torch.tanh(feat @ w.t() + p["EdgeMaskPredictor/BoxEncodingPredictor/biases"])
         if mtl.get("refine"):
-            src = [cl]
+            ew = close = None
             if mtl.get("window"):
-                pn = prop_norm                                              # fmA:783-803
-                ymin, xmin, ymax, xmax = [pn[..., i] for i in range(4)]
-                F32 = np.float32
-                exp = []
-                for e in range(5):
-                    exp.append(np.stack([ymin - (ymin / F32(4)) * F32(e), xmin - (xmin / F32(4)) * F32(e),
-                                         ymax + ((F32(1) - ymax) / F32(4)) * F32(e),
-                                         xmax + ((F32(1) - xmax) / F32(4)) * F32(e)], -1).astype(F32))
-                exp = np.stack(exp)                                         # [5,B,P,4]
+                exp = self.expanded_windows(prop_norm)                      # [5,B,P,4]
                 ebi = np.broadcast_to(np.arange(B)[None, :, None], (5, B, P)).reshape(-1).astype(np.int64)
                 with torch.no_grad():
                     if rfcn:
@@ -440,33 +447,58 @@ class Oracle(object):
                         em = crops_of(exp.reshape(-1, 4), ebi)
                         ew = self.head(tail(em, "WindowBoxPredictor/" + self.arch), "WindowBoxPredictor",
                                        ["ClassPredictor"])[0]
-                src.append(ew.reshape(5, B * P, K1).permute(1, 0, 2).reshape(B * P, 5 * K1))
             if mtl.get("closeness"):
-                cm = out["closeness_predictions"].detach().mean(0, keepdim=True)
-                src.append(cm.expand(B * P, K1))
-            net = torch.cat([s.detach() for s in src], 1)
-            ref = net @ p["MTLClassRefiner/fc1/weights"].t() + p["MTLClassRefiner/fc1/biases"]
-            if mtl.get("refine_residue"):
-                ref = ref + cl
+                close = out["closeness_predictions"]
+            ref, net = self.refine_logits(cl, ew, close)
             out["mtl_refined_class_predictions_with_background"] = ref
             out["refine_in"] = net
         return out
 
+    @staticmethod
+    def expanded_windows(prop_norm):
+        """fmA:783-803: per proposal five boxes growing linearly from the proposal (i = 0) to the whole image (i = 4);
+        returned [5, B, P, 4], the order in which `predict_with_mtl_results` flattens them into one window list."""
+        F32 = np.float32
+        ymin, xmin, ymax, xmax = [np.asarray(prop_norm, F32)[..., i] for i in range(4)]
+        exp = []
+        for e in range(5):
+            exp.append(np.stack([ymin - (ymin / F32(4)) * F32(e), xmin - (xmin / F32(4)) * F32(e),
+                                 ymax + ((F32(1) - ymax) / F32(4)) * F32(e),
+                                 xmax + ((F32(1) - xmax) / F32(4)) * F32(e)], -1).astype(F32))
+        return np.stack(exp)
+
+    def refine_logits(self, cl, ew, close):
+        """fmA:805-846: refiner input = [class logits | the five window logit rows of the SAME proposal, window-major
+        ([5, B*P, K+1] -> [B*P, 5(K+1)]) | closeness logits averaged over all proposals and tiled], all without
+        gradient; one FC layer (`refine_num_fc_layers: 0` in every shipped config) plus the residue.
+        `ew`: [5*B*P, K+1] window logits in `expanded_windows` order, or None; `close`: [B*P, K+1] or None."""
+        mtl, p = self.cfg["mtl"], self.p
+        n, K1 = cl.shape
+        src = [cl]
+        if ew is not None:
+            src.append(ew.reshape(5, n, K1).permute(1, 0, 2).reshape(n, 5 * K1))
+        if close is not None:
+            src.append(close.detach().mean(0, keepdim=True).expand(n, K1))
+        net = torch.cat([s.detach() for s in src], 1)
+        ref = net @ p["MTLClassRefiner/fc1/weights"].t() + p["MTLClassRefiner/fc1/biases"]
+        if mtl.get("refine_residue"):
+            ref = ref + cl
+        return ref, net
+
     # ------------------------------------------------------------------ losses
-    def loss(self, out, examples, keys, H, W):
-        cfg, mtl = self.cfg, self.cfg["mtl"]
-        B = len(examples)
-        K = cfg["num_classes"]
-        K1 = K + 1
-        P = cfg["second_stage_batch_size"]
+    def loss_first_stage(self, out, keys):
+        """fmA `_loss_rpn` :1591-1668 (T1 sigma 3, T15 per-image normaliser = number of sampled anchors, then batch
+        mean).  Pinned against that method executed on the NumPy TF shim (tests/golden/make_graph_golden.py)."""
+        cfg = self.cfg
         anchors = out["anchors"]
+        B = len(out["gts"])
         losses = {}
         loc_l = obj_l = 0.0
-        for b in range(B):                                                   # _loss_rpn
+        for b in range(B):
             t = OA.assign_proposal(anchors, out["gts"][b][0])
             s = OA.balanced_subsample(t["cls_weights"] > 0, cfg["first_stage_minibatch_size"],
                                       t["cls_targets"][:, 0] > 0, cfg["first_stage_positive_balance_fraction"],
-                                      keys[0][b])
+                                      keys[b])
             sf = torch.from_numpy(s.astype(np.float32))
             norm = sf.sum()
             loc = ON.smooth_l1(out["rpn_box"][b], torch.from_numpy(t["reg_targets"]),
@@ -477,6 +509,10 @@ class Oracle(object):
             obj_l = obj_l + obj.sum() / norm
         losses["first_stage_localization_loss"] = cfg["first_stage_localization_loss_weight"] * loc_l / B
         losses["first_stage_objectness_loss"] = cfg["first_stage_objectness_loss_weight"] * obj_l / B
+        return losses
+
+    def loss(self, out, examples, keys, H, W):
+        losses = self.loss_first_stage(out, keys[0])
         losses.update(self.loss_second_stage(out, examples))
         return losses
 

@@ -29,7 +29,7 @@ class Dim(object):
 
 class Shape(object):
     def __init__(self, dims):
-        self.dims = [int(d) for d in dims]
+        self.dims = [None if getattr(d, "value", d) is None else int(d) for d in dims]
 
     ndims = property(lambda self: len(self.dims))
 
@@ -65,9 +65,18 @@ class Shape(object):
         return self
 
 
+class DimInt(int):
+    """An element of `tensor.shape`: an int NumPy accepts, with TF's `.value`."""
+    value = property(lambda self: int(self))
+
+
 class ShapeTuple(tuple):
-    """`tensor.shape` as TF exposes it (ndims / as_list) while staying the plain tuple NumPy expects."""
+    """`tensor.shape` as TF exposes it (ndims / as_list / [i].value) while staying the plain tuple NumPy expects."""
+    def __new__(cls, dims=()):
+        return tuple.__new__(cls, (DimInt(d) for d in dims))
+
     ndims = property(lambda self: len(self))
+    dims = property(lambda self: list(self))
 
     def as_list(self):
         return list(self)
@@ -83,6 +92,14 @@ class TT(np.ndarray):
 
     def set_shape(self, shape):
         return None
+
+    # TF tensors are immutable: `x /= s` in the reference rebinds the name to a NEW tensor.  ndarray would write through
+    # views (e.g. the rows `tf.unstack` returns) into the caller's data, so the augmented assignments copy instead.
+    __iadd__ = lambda self, o: self + o
+    __isub__ = lambda self, o: self - o
+    __imul__ = lambda self, o: self * o
+    __itruediv__ = lambda self, o: self / o
+    __ifloordiv__ = lambda self, o: self // o
 
 
 def t(a, dtype=None):
@@ -159,10 +176,11 @@ def make_tf():
     tf = types.ModuleType("tensorflow")
     tf.float32, tf.float64, tf.int32, tf.int64, tf.bool, tf.string = np.float32, np.float64, np.int32, np.int64, np.bool_, np.str_
     tf.Tensor, tf.Variable, tf.SparseTensor = TT, type("Variable", (), {}), type("SparseTensor", (), {})
-    tf.TensorShape = Shape
+    tf.TensorShape, tf.Dimension = Shape, Dim
     tf.name_scope = lambda *a, **k: _Ctx("scope")
     tf.variable_scope = lambda *a, **k: _Ctx("scope")
     tf.control_dependencies = lambda *a, **k: _Ctx()
+    tf.device = lambda *a, **k: _Ctx()
     for n in ("assert_equal", "Assert", "assert_less", "assert_greater", "assert_less_equal", "assert_greater_equal",
               "assert_non_negative", "no_op", "group"):
         setattr(tf, n, lambda *a, **k: None)
@@ -179,7 +197,15 @@ def make_tf():
     tf.shape = _w(lambda x, out_type=np.int32: np.asarray(np.shape(x), out_type))
     tf.size = _w(lambda x, out_type=np.int32: np.asarray(np.size(x), out_type))
     tf.rank = _w(lambda x: np.asarray(np.ndim(x), np.int32))
-    tf.reshape = _w(lambda x, shape: np.reshape(x, _ints(shape)))
+    def _reshape(x, shape):
+        x, shape = np.asarray(x), list(_ints(shape))
+        if x.size == 0 and -1 in shape and 0 in shape:
+            # TF's ReshapeOp: when the requested shape holds a zero, the missing dimension is inferred from the NON-ZERO
+            # dimensions of input and request
+            nz = lambda dims: int(np.prod([d for d in dims if d not in (0, -1)] or [1]))
+            shape[shape.index(-1)] = nz(x.shape) // nz(shape)
+        return np.reshape(x, shape)
+    tf.reshape = _w(_reshape)
     tf.expand_dims = _w(lambda x, axis=None, dim=None: np.expand_dims(x, axis if axis is not None else dim))
     def _squeeze(x, axis=None, squeeze_dims=None):
         ax = axis if axis is not None else squeeze_dims
@@ -195,7 +221,11 @@ def make_tf():
     tf.boolean_mask = _w(lambda x, mask, **k: np.asarray(x)[np.asarray(mask).astype(bool)])
     tf.where = _w(_where)
     tf.dynamic_stitch = _w(_dynamic_stitch)
-    tf.range = _w(lambda *a, **k: np.arange(*[int(v) for v in a], dtype=k.get("dtype", np.int32)))
+    def _range(*a, start=None, limit=None, delta=None, dtype=np.int32):
+        if limit is not None:
+            a = (0 if start is None else start, limit) + (() if delta is None else (delta,))
+        return np.arange(*[int(v) for v in a], dtype=dtype)
+    tf.range = _w(_range)
     tf.ones = _w(lambda shape, dtype=np.float32: np.ones(_ints(shape), dtype))
     tf.zeros = _w(lambda shape, dtype=np.float32: np.zeros(_ints(shape), dtype))
     tf.ones_like = _w(lambda x, dtype=None: np.ones_like(x, dtype=dtype))

@@ -469,3 +469,93 @@ def test_second_stage_losses_against_reference_meta_arch_methods_run_on_the_tf_s
         for k, v in want.items():
             np.testing.assert_allclose(float(got[k]), v, rtol=2e-5, err_msg=p + k)
     assert short                                                    # a padded proposal list was exercised
+
+
+def _graph_golden():
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "graph_reference.npz"))
+
+
+def test_rpn_graph_code_against_reference_meta_arch_methods_run_on_the_tf_shim():
+    """fmA `_remove_invalid_anchors_and_predictions` (:930-976), `_postprocess_rpn` in training mode (:1055-1132, through
+    `batch_multiclass_non_max_suppression`, `_format_groundtruth_data`, `_unpad_proposals_and_sample_box_classifier_batch`,
+    `_sample_box_classifier_minibatch`) and `_loss_rpn` (:1591-1668) of the reference, EXECUTED on the NumPy TF shim with a
+    keyed shuffle in place of `tf.random_shuffle` (tests/golden/make_graph_golden.py), against the oracle methods the
+    device path is compared with: kept anchor indices / proposal counts bit-exact, proposal boxes and scores to fp32
+    rounding of exp / divide (1e-5), the two RPN losses 2e-5 relative."""
+    import torch
+    from oracle import boxes as OB
+    from oracle.model import Oracle
+    g = _graph_golden()
+    K, P, M, MB, H, W, Hf, Wf, ncases = [int(v) for v in g["rpn_meta"]]
+    cfg = dict(architecture="resnet_v1_101", num_classes=K, second_stage_batch_size=P, first_stage_max_proposals=M,
+               nms_score_threshold=0.0, nms_iou_threshold=0.7, second_stage_balance_fraction=0.25,
+               first_stage_minibatch_size=MB, first_stage_positive_balance_fraction=0.5,
+               first_stage_localization_loss_weight=2.0, first_stage_objectness_loss_weight=1.0, mtl={})
+    o = Oracle({}, cfg, bf16=False)
+    short = False
+    for c in range(ncases):
+        p = "rpn%d/" % c
+        anchors, keep = OB.prune_outside_window(g[p + "anchors_all"], (0, 0, H, W))
+        assert 0 < len(keep) < len(g[p + "anchors_all"])
+        assert np.array_equal(anchors, g[p + "anchors"])
+        assert np.array_equal(g[p + "enc"][:, keep], g[p + "enc_kept"])
+        assert np.array_equal(g[p + "logits"][:, keep], g[p + "logits_kept"])
+        B = g[p + "enc"].shape[0]
+        gts = []
+        for b in range(B):
+            gt_abs = OB.to_absolute_coordinates(g[p + "gt%d" % b] / np.array([H, W, H, W], np.float32), H, W)
+            np.testing.assert_allclose(gt_abs, g[p + "gt_abs%d" % b], rtol=0, atol=0)       # _format_groundtruth_data
+            cls_bg = np.concatenate([np.zeros((len(gt_abs), 1), np.float32), g[p + "cls%d" % b]], 1)
+            gts.append((gt_abs, cls_bg, None))
+            boxes, scores, cnt, _ = o.training_proposals(g[p + "enc_kept"][b], g[p + "logits_kept"][b], anchors, gt_abs,
+                                                         cls_bg, g[p + "keys2"][b], H, W)
+            assert cnt == int(g[p + "nprop"][b])
+            short = short or cnt < P
+            np.testing.assert_allclose(boxes, g[p + "prop_norm"][b], rtol=1e-5, atol=1e-6)
+            np.testing.assert_allclose(scores, g[p + "prop_scores"][b], rtol=1e-5, atol=1e-7)
+            assert (boxes[cnt:] == 0).all() and (np.diff(scores[:cnt]) <= 0).all()           # score order kept
+        out = dict(anchors=anchors, gts=gts, rpn_box=torch.from_numpy(g[p + "enc_kept"]),
+                   rpn_cls=torch.from_numpy(g[p + "logits_kept"]))
+        got = o.loss_first_stage(out, g[p + "keys1"])
+        for k in ("first_stage_localization_loss", "first_stage_objectness_loss"):
+            np.testing.assert_allclose(float(got[k]), float(g[p + "loss/" + k]), rtol=2e-5, err_msg=p + k)
+    assert short
+
+
+def test_refiner_input_assembly_against_reference_predict_with_mtl_results_run_on_the_tf_shim():
+    """fmA `predict_with_mtl_results` (:764-846) EXECUTED on the shim with a recording `predict_with_window`
+    (logits = fixed linear map of the window box) and `slim.fully_connected` = x @ W + b: the five expanded windows per
+    proposal and their flattening order, the [5, P, K+1] -> [P, 5(K+1)] transposition, the global closeness mean, the
+    concatenation order and the residue -- against `Oracle.expanded_windows` / `Oracle.refine_logits` (batch 1, T9)."""
+    import torch
+    from oracle.model import Oracle
+    g = _graph_golden()
+    props, cls, close = g["refine/props"], g["refine/cls"], g["refine/close"]
+    P, K1 = cls.shape
+    exp = Oracle.expanded_windows(props)                                      # [5, 1, P, 4]
+    assert g["refine/windows"].shape == (1, 5 * P, 4)
+    np.testing.assert_allclose(exp.reshape(1, 5 * P, 4), g["refine/windows"], rtol=0, atol=1e-7)
+    assert np.array_equal(exp[0, 0], props[0])                                # i = 0 is the proposal itself
+    np.testing.assert_allclose(exp[4], np.broadcast_to(np.float32([0, 0, 1, 1]), exp[4].shape), atol=1e-6)
+    o = Oracle({"MTLClassRefiner/fc1/weights": torch.from_numpy(g["refine/fcw"].T.copy()),
+                "MTLClassRefiner/fc1/biases": torch.from_numpy(g["refine/fcb"])},
+               dict(architecture="resnet_v1_101", mtl=dict(refine_residue=True)), bf16=False)
+    ew = torch.from_numpy(exp.reshape(-1, 4) @ g["refine/wmat"])
+    ref, net = o.refine_logits(torch.from_numpy(cls), ew, torch.from_numpy(close))
+    np.testing.assert_allclose(net[:, K1:6 * K1].reshape(P, 5, K1).numpy(), g["refine/expand_window_class_predictions"],
+                               rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(ref.numpy(), g["refine/refined"], rtol=1e-5, atol=1e-5)
+
+
+def test_roi_crop_box_index_map_against_reference_run_on_the_tf_shim():
+    """fmA `_compute_second_stage_input_feature_maps` (:1304-1348) with recording stand-ins for crop_and_resize and
+    max_pool2d: rank-3 proposals [B, P, 4] are flattened batch-major with box_ind = image index; a [1, n, 4] list reads
+    image 0 throughout (T9); crop size and pool window come from the config."""
+    g = _graph_golden()
+    boxes = g["crop/boxes"]
+    B, P, _ = boxes.shape
+    assert np.array_equal(g["crop/flat_boxes"], boxes.reshape(-1, 4))
+    assert np.array_equal(g["crop/box_ind"], np.repeat(np.arange(B), P))      # what Oracle.forward builds (`bi`)
+    assert np.array_equal(g["crop/size_pool"], [14, 14, 2, 2])
+    assert (g["crop/box_ind_rank3_batch1"] == 0).all() and len(g["crop/box_ind_rank3_batch1"]) == B * P
