@@ -559,3 +559,37 @@ def test_roi_crop_box_index_map_against_reference_run_on_the_tf_shim():
     assert np.array_equal(g["crop/box_ind"], np.repeat(np.arange(B), P))      # what Oracle.forward builds (`bi`)
     assert np.array_equal(g["crop/size_pool"], [14, 14, 2, 2])
     assert (g["crop/box_ind_rank3_batch1"] == 0).all() and len(g["crop/box_ind_rank3_batch1"]) == B * P
+
+
+def test_oracle_full_step_runs_on_cpu_and_is_deterministic():
+    """The whole restated step (forward, the eight losses, L2, autograd backward) on a 224x320 image with the
+    model12 graph: guards the oracle's own plumbing on the CPU-only driver run (the values are what the -m gpu
+    parity tests compare the device path with)."""
+    import torch
+    from helpers import load_config, oracle_config
+    from mtl_ssl_b200.data import synthetic
+    from oracle.model import Oracle
+    import oracle.refparams as refparams
+    H, W, B = 224, 320, 1
+    cfg = load_config("model12.config", (("min_dimension: 600", "min_dimension: 224"),
+                                         ("max_dimension: 1024", "max_dimension: 320"),
+                                         ("first_stage_max_proposals: 300", "first_stage_max_proposals: 100"),
+                                         ("second_stage_batch_size: 256", "second_stage_batch_size: 16")))
+    ocfg = oracle_config(cfg)
+    params, l2 = refparams.build_params(ocfg, seed=0)
+    examples = synthetic.make_batch(1, B, H, W, ocfg["num_classes"], max_boxes=4, num_windows=8)
+    keys = synthetic.make_sampler_keys(2, B, refparams.num_kept_anchors(ocfg, H, W), ocfg["first_stage_max_proposals"])
+    img = torch.from_numpy(np.stack([e["image"] for e in examples]))
+    totals = []
+    for _ in range(2):
+        orc = Oracle(params, ocfg, bf16=True)
+        orc.require_grad([k for k in params if refparams.is_trainable(k)])
+        out = orc.forward(img, examples, keys, H, W)
+        losses = orc.loss(out, examples, keys, H, W)
+        assert len(losses) == 8 and all(np.isfinite(float(v.detach())) for v in losses.values())
+        totals.append(float((sum(losses.values()) + orc.regularization_loss(l2)).detach()))
+    assert totals[0] == totals[1]
+    (sum(losses.values()) + orc.regularization_loss(l2)).backward()
+    g = orc.p["SecondStageBoxPredictor/ClassPredictor/weights"].grad
+    assert g is not None and np.isfinite(g.numpy()).all() and float(g.abs().sum()) > 0
+    assert int(out["nprop"][0]) == 16 and out["prop_norm"].shape == (1, 16, 4)
