@@ -111,6 +111,11 @@ class Trainer(object):
         self.global_step = 0
         self.device = model.device
         if train_config is not None:
+            # trainer.py:387-410 of the reference post-processes the gradients with four optional knobs that no shipped
+            # config sets; they are refused rather than silently ignored
+            for knob in ("grad_multiplier", "divide_grad_by_batch", "bias_grad_multiplier", "freeze_variables"):
+                if getattr(train_config, knob, None):
+                    raise ValueError("train_config.%s is not supported on the B200 path" % knob)
             self.lr_fn, momentum = learning_schedules.from_optimizer_config(train_config.optimizer)
             clip_norm = train_config.gradient_clipping_by_norm
         else:

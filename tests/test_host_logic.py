@@ -174,3 +174,19 @@ def test_data_parallel_gradient_exchange_gloo_world2(tmp_path):
                               stderr=subprocess.STDOUT, text=True) for r in range(2)]
     outs = [p.communicate(timeout=120)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
+
+
+def test_trainer_refuses_gradient_knobs_it_does_not_implement():
+    """trainer.py:387-410 of the reference: grad_multiplier / divide_grad_by_batch / bias_grad_multiplier /
+    freeze_variables are optional gradient post-processing steps; no shipped config sets them and the B200 path does not
+    implement them, so a config that does is refused at construction instead of training differently."""
+    from mtl_ssl_b200.builders import model_builder
+    from mtl_ssl_b200.trainer import Trainer
+    model = model_builder.build(load_config("model12.config").model, True, device=None)
+    for line in ("bias_grad_multiplier: 2.0", "freeze_variables: '.*conv1.*'", "grad_multiplier: 0.5",
+                 "divide_grad_by_batch: true"):
+        cfg = load_config("model12.config", (("gradient_clipping_by_norm: 10.0",
+                                              "gradient_clipping_by_norm: 10.0\n  " + line),))
+        assert getattr(cfg.train_config, line.split(":")[0])
+        with pytest.raises(ValueError, match=line.split(":")[0]):
+            Trainer(model, cfg.train_config, 600, 1000, 1)
