@@ -287,9 +287,42 @@ def crop_case(out):
     out["crop/box_ind_rank3_batch1"] = RECORD["crop"][1]
 
 
+def postprocess_case(out):
+    """`postprocess` (second stage, fmA:1038-1053) -> `_postprocess_box_classifier` :1387-1469 with the configs'
+    second-stage NMS (post_processing_builder: score_threshold 0.0 / 0.3, IoU 0.6, per class = total) and the SOFTMAX
+    score converter, num_proposals shorter than max_num_proposals for one image."""
+    import functools
+    pp = M["object_detection.core.post_processing"]
+    rng = np.random.default_rng(53)
+    K, P, B, H, W = 4, 24, 2, 160, 224
+    for case, (thr, max_det) in enumerate(((0.0, 20), (0.3, 100))):
+        s = types.SimpleNamespace(num_classes=K, max_num_proposals=P, _first_stage_only=False, _parallel_iterations=1,
+                                  _mtl=types.SimpleNamespace(refine=False))
+        s._box_coder = coder.FasterRcnnBoxCoder(scale_factors=[10.0, 10.0, 5.0, 5.0])
+        s._second_stage_score_conversion_fn = _softmax
+        s._second_stage_nms_fn = functools.partial(pp.batch_multiclass_non_max_suppression, score_thresh=thr,
+                                                   iou_thresh=0.6, max_size_per_class=max_det, max_total_size=max_det)
+        s._batch_decode_boxes = lambda e, a: Arch._batch_decode_boxes(s, e, a)
+        s._postprocess_box_classifier = lambda *a, **k: Arch._postprocess_box_classifier(s, *a, **k)
+        props = np.stack([rand_boxes(rng, P, H, W) for _ in range(B)])
+        nprop = np.array([P, 17], np.int32)
+        props[1, 17:] = 0
+        enc = rng.normal(0, 1.5, (B * P, K, 4)).astype(F)
+        logits = rng.normal(0, 2.5, (B * P, K + 1)).astype(F)
+        d = Arch.postprocess(s, dict(image_shape=t(np.array([B, H, W, 3], np.int32)), refined_box_encodings=t(enc),
+                                     class_predictions_with_background=t(logits), proposal_boxes=t(props),
+                                     num_proposals=t(nprop)))
+        p = "post%d/" % case
+        out[p + "props"], out[p + "nprop"], out[p + "enc"], out[p + "logits"] = props, nprop, enc, logits
+        out[p + "params"] = np.array([thr, 0.6, max_det, H, W], np.float64)
+        for k in ("detection_boxes", "detection_scores", "detection_classes", "num_detections"):
+            out[p + k] = np.asarray(d[k], F)
+
+
 def main():
     out = {}
     rpn_cases(out)
+    postprocess_case(out)
     refine_case(out)
     crop_case(out)
     np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "graph_reference.npz"), **out)

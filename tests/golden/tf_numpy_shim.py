@@ -217,7 +217,14 @@ def make_tf():
     tf.split = lambda value, num_or_size_splits, axis=0, **k: _split(value, num_or_size_splits, axis)
     tf.transpose = _w(lambda x, perm=None: np.transpose(x, perm))
     tf.tile = _w(lambda x, m: np.tile(x, _ints(m)))
-    tf.gather = _w(lambda params, indices, axis=0, **k: np.take(np.asarray(params), np.asarray(indices).astype(np.int64), axis))
+    def _gather(params, indices, axis=0, **k):
+        params, indices = np.asarray(params), np.asarray(indices).astype(np.int64)
+        if params.size == 0 and axis == 0:
+            # TF's GatherOp skips the copy (and with it the bounds check) when the slices are empty: the dummy
+            # [n/q, q, 0, 0] masks of batch_multiclass_non_max_suppression are gathered with box indices >= n/q
+            return np.zeros(indices.shape + params.shape[1:], params.dtype)
+        return np.take(params, indices, axis)
+    tf.gather = _w(_gather)
     tf.boolean_mask = _w(lambda x, mask, **k: np.asarray(x)[np.asarray(mask).astype(bool)])
     tf.where = _w(_where)
     tf.dynamic_stitch = _w(_dynamic_stitch)

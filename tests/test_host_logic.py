@@ -190,3 +190,17 @@ def test_trainer_refuses_gradient_knobs_it_does_not_implement():
         assert getattr(cfg.train_config, line.split(":")[0])
         with pytest.raises(ValueError, match=line.split(":")[0]):
             Trainer(model, cfg.train_config, 600, 1000, 1)
+
+
+def test_resize_to_range_output_sizes_match_reference_vectors():
+    """core/preprocessor_test.py:1398-1427 (`testResizeToRangePreservesStaticSpatialShape`) and :1514-1526
+    (`testResizeToRangeSameMinMax`): the output size rule of `resize_to_range` (host arithmetic in front of the
+    bilinear resize kernel)."""
+    from mtl_ssl_b200.core.preprocessor import _compute_new_static_size
+    for (h, w), want in zip(([60, 40], [15, 30], [15, 50]), ([75, 50], [50, 100], [30, 100])):
+        assert list(_compute_new_static_size(h, w, 50, 100)) == want
+    for (h, w) in ([312, 312], [299, 299]):
+        assert list(_compute_new_static_size(h, w, 320, 320)) == [320, 320]
+    # the two workloads of BASELINE.json: VOC-shape and COCO-shape inputs are already in range
+    assert list(_compute_new_static_size(600, 1000, 600, 1024)) == [600, 1000]
+    assert list(_compute_new_static_size(300, 300, 600, 1024)) == [600, 600]          # model51: 300x300 upsampled

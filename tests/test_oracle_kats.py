@@ -593,3 +593,24 @@ def test_oracle_full_step_runs_on_cpu_and_is_deterministic():
     g = orc.p["SecondStageBoxPredictor/ClassPredictor/weights"].grad
     assert g is not None and np.isfinite(g.numpy()).all() and float(g.abs().sum()) > 0
     assert int(out["nprop"][0]) == 16 and out["prop_norm"].shape == (1, 16, 4)
+
+
+def test_second_stage_postprocess_against_reference_meta_arch_run_on_the_tf_shim():
+    """fmA `postprocess` -> `_postprocess_box_classifier` (:1387-1469) -> `batch_multiclass_non_max_suppression`
+    (post_processing.py:167-312: clip to the image, change_coordinate_frame, num_valid_boxes = num_proposals, per-class
+    NMS, merge, top max_total, zero padding) EXECUTED on the shim, against oracle/postprocess.py
+    `second_stage_postprocess`: detection counts and classes exact, boxes / scores to fp32 rounding of exp / softmax."""
+    from oracle import postprocess as OP
+    g = _graph_golden()
+    for c in range(2):
+        p = "post%d/" % c
+        thr, iou, max_det, H, W = [float(v) for v in g[p + "params"]]
+        b, s, cl, n = OP.second_stage_postprocess(g[p + "enc"], g[p + "logits"], g[p + "props"], g[p + "nprop"],
+                                                  (int(H), int(W)), thr, iou, int(max_det), int(max_det))
+        assert np.array_equal(n, g[p + "num_detections"]) and (n > 0).all()
+        assert np.array_equal(cl, g[p + "detection_classes"])
+        np.testing.assert_allclose(s, g[p + "detection_scores"], rtol=1e-5, atol=1e-7)
+        np.testing.assert_allclose(b, g[p + "detection_boxes"], rtol=1e-5, atol=2e-6)
+        assert b.max() <= 1.0 + 1e-6 and b.min() >= 0.0                 # normalised to the clip window
+    assert (g["post0/num_detections"] == 20).all()                      # the top-20 cut was exercised
+    assert (g["post1/num_detections"] < 100).any()                      # ... and the zero padding
