@@ -10,8 +10,9 @@ Restates the label semantics of
   :325-358            closeness: per other-class object 1 - centre distance / image diagonal, max per
                       class, background 1 when nothing else is present, normalised by the sum;
   :375-421            64x64 foreground mask + per-box 1/area weight plane normalised to mean 1.
-The reference writes these into TFRecords offline; here they are produced on the fly for synthetic
-batches.  No reference test covers this code: parity unpinned.
+The reference writes these into TFRecords offline; here they are produced on the fly (synthetic batches,
+data/pascal_voc.py, data/mscoco.py).  No reference TEST covers this code; it is pinned to outputs of the
+reference's two record writers run under recording stubs (tests/golden/make_aux_golden.py, make_coco_aux_golden.py).
 """
 import math
 

@@ -5,9 +5,9 @@ Restates the data flow of /root/reference/object_detection/create_records/create
 (`dict_to_tf_example`: boxes normalised by the image size, class ids from the label map, difficult / truncated / pose,
 the single area subset 'all', window boxes + soft labels, closeness labels, 64x64 edge mask) on top of
 data/aux_labels.py, and of utils/dataset_util.py `recursive_parse_xml_to_dict` (every tag a key, 'object' a list).
-The standard keys are pinned to create_pascal_tf_record_test.py:39-113; the auxiliary labels are the restatement of
-aux_labels.py (unpinned: the reference has no test for them; its window sampling draws from NumPy's global RNG, here
-from an explicit generator)."""
+The standard keys are pinned to create_pascal_tf_record_test.py:39-113; the auxiliary labels (aux_labels.py) to outputs
+of the reference writer run under recording stubs (tests/golden/make_aux_golden.py); its window sampling draws from the
+global RNG, here from an explicit generator."""
 import hashlib
 import io
 import os

@@ -614,3 +614,48 @@ def test_second_stage_postprocess_against_reference_meta_arch_run_on_the_tf_shim
         assert b.max() <= 1.0 + 1e-6 and b.min() >= 0.0                 # normalised to the clip window
     assert (g["post0/num_detections"] == 20).all()                      # the top-20 cut was exercised
     assert (g["post1/num_detections"] < 100).any()                      # ... and the zero padding
+
+
+def test_coco_examples_against_reference_mscoco_record_writer():
+    """N1, COCO twin: data/mscoco.py against outputs of create_mscoco_tf_record.py `dict_to_tf_example` (:87-477) RUN here
+    under recording stubs (tests/golden/make_coco_aux_golden.py): ground-truth boxes clamped into the image, auxiliary
+    labels from the RAW boxes of all annotations, indexed by the raw (sparse) category id."""
+    import os
+    from mtl_ssl_b200.data import aux_labels as A, mscoco
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "coco_aux_reference.npz"))
+    class_indices = [int(v) for v in g["class_indices"]]
+    kmax = max(class_indices)
+    cats = {c: {"id": c, "name": "c%d" % c} for c in class_indices}
+    label_map = {"c%d" % c: c for c in class_indices}
+    rows = lambda arr: np.array([[float(t) for t in str(s).split()] for s in arr], np.float64)
+    clamped = False
+    for c in range(int(g["num_cases"])):
+        p = "case%d/" % c
+        H, W = [int(v) for v in g[p + "hw"]]
+        anns = [dict(bbox=[float(v) for v in bb], category_id=int(ci), iscrowd=int(cr), image_id=0, id=i)
+                for i, (bb, ci, cr) in enumerate(zip(g[p + "bbox"], g[p + "category_id"], g[p + "iscrowd"]))]
+        ex = mscoco.annotations_to_example(anns, np.zeros((H, W, 3), np.uint8), cats, label_map, kmax,
+                                           np.random.default_rng(0), 64, kmax)
+        want_gt = np.stack([g[p + "gt_" + k] for k in ("ymin", "xmin", "ymax", "xmax")], 1)
+        np.testing.assert_allclose(ex["groundtruth_boxes"], want_gt, rtol=1e-6, atol=1e-7)
+        clamped = clamped or bool((g[p + "bbox"][:, :2] < 0).any())
+        assert ex["groundtruth_boxes"].min() >= 0 and ex["groundtruth_boxes"].max() <= 1
+        assert np.array_equal(ex["groundtruth_labels"], g[p + "gt_label"])
+        assert np.array_equal(ex["groundtruth_is_crowd"].astype(int), g[p + "gt_is_crowd"])
+        want = rows(g[p + "closeness"])
+        assert ex["groundtruth_closeness"].shape == want.shape == (len(want_gt), kmax + 1)
+        np.testing.assert_allclose(ex["groundtruth_closeness"], want, atol=1e-6)
+        eh, ew = [int(v) for v in g[p + "edgemask_hw"]]
+        want_em = g[p + "edgemask"].reshape(-1, eh, ew)
+        np.testing.assert_array_equal(ex["groundtruth_edgemask"][0], want_em[0])
+        np.testing.assert_allclose(ex["groundtruth_edgemask"][1], want_em[1], rtol=1e-6)
+        wl = rows(g[p + "window_labels"])
+        assert wl.shape == (64, kmax + 1) and ex["window_classes"].shape == (64, kmax + 1)
+        raw = mscoco._raw_boxes(anns)
+        for i in range(64):
+            window = [g[p + "window_ymin"][i] * H, g[p + "window_xmin"][i] * W, g[p + "window_ymax"][i] * H,
+                      g[p + "window_xmax"][i] * W]
+            lab, bg = A.window_label(raw, g[p + "category_id"], window, kmax)
+            np.testing.assert_allclose(lab, wl[i], atol=1.001e-3)
+        assert mscoco.get_image_id("/x/COCO_val2014_%012d.jpg" % int(str(g[p + "source_id"]))) == int(str(g[p + "source_id"]))
+    assert clamped

@@ -323,3 +323,54 @@ def test_pascal_voc_records_reference_expectations(tmp_path):
     assert d["groundtruth_difficult"].tolist() == [True, False] and d["groundtruth_subset"] == ["all", "all"]
     only_easy = list(V.VocDataset(str(root), "trainval", label_map, 2, ignore_difficult_instances=True))[0]
     assert only_easy["groundtruth_classes"].tolist() == [[0, 1]]
+
+
+def test_mscoco_records_and_dataset_reader(tmp_path):
+    """create_mscoco_tf_record.py:87-477 key set through data/mscoco.py: annotation JSON -> CocoIndex (no pycocotools) ->
+    record -> decoder, and the directory reader; the label values themselves are pinned in
+    test_oracle_kats.py::test_coco_examples_against_reference_mscoco_record_writer."""
+    import json
+    from PIL import Image
+    from mtl_ssl_b200.data import mscoco as C
+    img_dir = tmp_path / "images" / "val2017"
+    os.makedirs(str(img_dir))
+    fname = "%012d.jpg" % 139
+    rng = np.random.default_rng(0)
+    Image.fromarray(rng.integers(0, 256, (200, 320, 3), dtype=np.uint8), "RGB").save(str(img_dir / fname))
+    ann = {"images": [{"id": 139, "file_name": fname, "height": 200, "width": 320}],
+           "categories": [{"id": 1, "name": "person"}, {"id": 3, "name": "car"}, {"id": 90, "name": "toothbrush"}],
+           "annotations": [{"id": 7, "image_id": 139, "category_id": 3, "iscrowd": 0, "bbox": [240.0, 20.0, 108.0, 60.0]},
+                           {"id": 8, "image_id": 139, "category_id": 90, "iscrowd": 1, "bbox": [160.0, 100.0, 80.0, 50.0]},
+                           {"id": 9, "image_id": 139, "category_id": 1, "iscrowd": 0, "bbox": [100.0, 50.0, 0.0, 30.0]}]}
+    open(str(tmp_path / "instances_val2017.json"), "w").write(json.dumps(ann))
+    coco = C.CocoIndex(str(tmp_path / "instances_val2017.json"))
+    assert coco.getAnnIds(imgIds=139) == [7, 8, 9] and coco.loadCats(3)[0]["name"] == "car"
+    assert C.boundary_check([-8.0, 20.0, 108.0, 60.0], 320, 200) == (0, 20.0, 108.0, 60.0)
+    assert C.boundary_check([240.0, 20.0, 108.0, 60.0], 320, 200) == (240.0, 20.0, 80.0, 60.0)
+    label_map = coco.label_map_dict()
+    rec = C.dict_to_tf_example(label_map, str(img_dir / fname), coco, sorted(label_map.values()),
+                               rng=np.random.default_rng(1), num_windows=16)
+    ex = T.parse_example(rec)
+    assert ex["image/source_id"] == [b"139"] and ex["image/format"] == [b"jpg"]
+    assert ex["image/height"].tolist() == [200] and ex["image/width"].tolist() == [320]
+    # the third box has zero width (COCO holds a few): dropped from the ground truth, still seen by the auxiliary labels
+    assert ex["image/object/class/text"] == [b"car", b"toothbrush"] and ex["image/object/class/label"].tolist() == [3, 90]
+    assert ex["image/object/is_crowd"].tolist() == [0, 1]
+    np.testing.assert_allclose(ex["image/object/bbox/xmin"], [0.75, 0.5])
+    np.testing.assert_allclose(ex["image/object/bbox/xmax"], [1.0, 0.75])
+    assert len(ex["image/object/closeness/text"]) == 2 and len(ex["image/window/labels/text"]) == 16
+    assert len(ex["image/window/labels/text"][0].split()) == 91 and len(ex["image/object/closeness/text"][0].split()) == 91
+    d = T.decode_example(rec, 90)
+    assert d["groundtruth_classes"].shape == (2, 90) and d["groundtruth_classes"][0, 2] == 1 and d["groundtruth_classes"][1, 89] == 1
+    assert d["window_classes"].shape == (16, 91) and d["groundtruth_closeness"].shape == (2, 91)
+    assert d["groundtruth_edgemask"].shape == (2, 64, 64)
+    ds = C.CocoDataset(coco, str(img_dir), num_classes=90, seed=1, num_windows=16)
+    (e,) = list(ds)
+    assert len(ds) == 1 and e["image"].shape == (200, 320, 3)
+    np.testing.assert_allclose(e["groundtruth_boxes"], d["groundtruth_boxes"], rtol=1e-6)
+    np.testing.assert_array_equal(e["groundtruth_classes"], d["groundtruth_classes"])
+    np.testing.assert_allclose(e["window_classes"], d["window_classes"], atol=5e-4)
+    np.testing.assert_allclose(e["groundtruth_closeness"], d["groundtruth_closeness"], atol=5e-4)
+    # an image without annotations has no windows (`create_multi_object` returns [])
+    empty = C.annotations_to_example([], np.zeros((50, 60, 3), np.uint8), {}, label_map, 90, np.random.default_rng(0))
+    assert empty["window_boxes"].shape == (0, 4) and empty["groundtruth_boxes"].shape == (0, 4)
