@@ -61,3 +61,70 @@ def evaluate_detection_results_pascal_voc(result_lists, categories, label_id_off
             if idx in by_id:
                 metrics["PerformanceByCategory/CorLoc@{}IOU/{}".format(iou_thres, by_id[idx])] = corloc[idx]
     return metrics
+
+
+COCO_METRIC_NAMES = ("AP", "AP_IoU50", "AP_IoU75", "AP_small", "AP_medium", "AP_large",
+                     "AR_max1", "AR_max10", "AR_max100", "AR_small", "AR_medium", "AR_large")
+
+
+def evaluate_detection_results_coco(result_lists, categories, label_id_offset=1, iou_thres=0.5, corloc_summary=False,
+                                    nms_type="standard", nms_thres=1.0, soft_nms_sigma=0.5, eval_config=None,
+                                    eval_ann_filename=None):
+    """eval_util.py:393-548 of the reference: MS-COCO metrics through `CocoEvaluation` (pycocotools restated in
+    utils/coco_evaluation.py).  `eval_config.coco_eval_options` selects the metric indices (0..11, default [0] = AP),
+    all-categories only (eval_class_type 0) or per category as well (1), and the annotation file the ground truth is
+    read from (`eval_ann_filename` overrides it; it may also be a data.mscoco.CocoIndex).
+    Returns {'COCO_Eval/<All | category name>/<metric name>': value}; {} when the annotation file is missing."""
+    from .utils.coco_evaluation import CocoEvaluation
+    need = ["detection_boxes", "detection_scores", "detection_classes", "image_id", "groundtruth_boxes",
+            "groundtruth_classes"]
+    if not set(need).issubset(result_lists):
+        raise ValueError("result_lists does not have expected key set.")
+    n = len(result_lists[need[0]])
+    if any(len(result_lists[k]) != n for k in need):
+        raise ValueError("Inconsistent list sizes in result_lists")
+    cats = copy.deepcopy(categories)
+    for c in cats:
+        c["id"] -= label_id_offset
+    num_classes = max(c["id"] for c in cats) + 1
+    ids = result_lists["image_id"]
+    image_ids = [int(i) for i in ids] if all(str(i).isdigit() for i in ids) else list(range(n))
+    ev = CocoEvaluation(num_classes, matching_iou_threshold=iou_thres, nms_type=nms_type, nms_iou_threshold=nms_thres,
+                        soft_nms_sigma=soft_nms_sigma)
+    for k, image_id in enumerate(image_ids):
+        ev.add_single_ground_truth_image_info(image_id, result_lists["groundtruth_boxes"][k],
+                                              np.asarray(result_lists["groundtruth_classes"][k], int) - label_id_offset)
+        ev.add_single_detected_image_info(image_id, result_lists["detection_boxes"][k],
+                                          result_lists["detection_scores"][k],
+                                          np.asarray(result_lists["detection_classes"][k], int) - label_id_offset)
+    metric_index, class_type, ann = [0], 1, "../data/mscoco/annotations/instances_eval2014.json"
+    opts = getattr(eval_config, "coco_eval_options", None) if eval_config is not None else None
+    if opts is not None:
+        metric_index = list(opts.eval_metric_index) or [0]
+        class_type = opts.eval_class_type
+        ann = opts.eval_ann_filename or ann
+    if eval_ann_filename is not None:
+        ann = eval_ann_filename
+    if min(metric_index) < 0 or max(metric_index) > 11:
+        raise ValueError("eval_metric_index")
+    if class_type < 0 or class_type > 1:
+        raise ValueError("eval_class_type")
+    cat_index = [0] if class_type == 0 else list(range(num_classes + 1))
+    coco_metrics = ev.evaluate(cat_index, ann)
+    metrics = {}
+    if coco_metrics is None:
+        return metrics
+    by_id = {c["id"]: c["name"] for c in cats}
+    for cat_id in range(num_classes + 1):
+        if cat_id == 0:
+            name = "All"
+        elif cat_id - 1 in by_id:
+            name = by_id[cat_id - 1]
+        else:
+            continue
+        if cat_id not in cat_index or cat_id not in coco_metrics:
+            continue
+        for mi, mname in enumerate(COCO_METRIC_NAMES):
+            if mi in metric_index:
+                metrics["COCO_Eval/%s/%s" % (name, mname)] = coco_metrics[cat_id][mi]
+    return metrics

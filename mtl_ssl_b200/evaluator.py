@@ -59,17 +59,32 @@ def run_inference(model, example):
     return out
 
 
-def evaluate(model, examples, categories, iou_thres=0.5, corloc_summary=True):
-    """Runs `examples` through the model and returns {metric name: value}: the PASCAL-VOC metrics of eval_util plus
-    'mtl/window_map', 'mtl/closeness_diff', 'mtl/edgemask_ap' for the auxiliary heads the config enables."""
+EVAL_METRICS_FN_DICT = {                      # evaluator.py:40-43 of the reference
+    "pascal_voc_metrics": eval_util.evaluate_detection_results_pascal_voc,
+    "coco_metrics": eval_util.evaluate_detection_results_coco,
+}
+
+
+def evaluate(model, examples, categories, iou_thres=0.5, corloc_summary=True, metrics_set="pascal_voc_metrics",
+             eval_config=None, eval_ann_filename=None):
+    """Runs `examples` through the model and returns {metric name: value}: the detection metrics of eval_util
+    (`metrics_set` as in eval.proto: 'pascal_voc_metrics' or 'coco_metrics'; for COCO the examples carry the image id in
+    'source_id' and the ground truth is read from the annotation file) plus 'mtl/window_map', 'mtl/closeness_diff',
+    'mtl/edgemask_ap' for the auxiliary heads the config enables."""
+    if metrics_set not in EVAL_METRICS_FN_DICT:
+        raise ValueError("Metric not found: {}".format(metrics_set))
     lists = {}
     for i, ex in enumerate(examples):
         r = run_inference(model, ex)
-        r["image_id"] = str(i)
+        r["image_id"] = str(ex.get("source_id", i)) if metrics_set == "coco_metrics" else str(i)
         for k, v in r.items():
             lists.setdefault(k, []).append(v)
-    metrics = eval_util.evaluate_detection_results_pascal_voc(lists, categories, iou_thres=iou_thres,
-                                                              corloc_summary=corloc_summary)
+    if metrics_set == "coco_metrics":
+        metrics = eval_util.evaluate_detection_results_coco(lists, categories, iou_thres=iou_thres,
+                                                            eval_config=eval_config, eval_ann_filename=eval_ann_filename)
+    else:
+        metrics = eval_util.evaluate_detection_results_pascal_voc(lists, categories, iou_thres=iou_thres,
+                                                                  corloc_summary=corloc_summary)
     has_dets = all(len(d) for d in lists["detection_boxes"]) and all(len(g) for g in lists["groundtruth_boxes"])
     aux = {k: v for k, v in lists.items() if k.split("_")[0] in ("window", "edgemask") or
            (k.startswith("closeness") and has_dets)}

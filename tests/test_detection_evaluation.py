@@ -182,3 +182,109 @@ def test_eval_util_against_reference_function_outputs():
     assert sorted(m) == names
     np.testing.assert_allclose([m[k] for k in names], g["voc/metric_values"], rtol=1e-12, equal_nan=True)
     assert any(k.startswith("Subset big") for k in names) and any(k.startswith("Subset all") for k in names)
+
+
+# ----------------------------------------------------------------------------- MS-COCO metrics (pycocotools restated)
+def _xywh_iou_box(gt, iou):
+    """A box [x, y, w, h] sharing gt's top-left corner and height whose IoU with gt is `iou` (narrower box)."""
+    return [gt[0], gt[1], gt[2] * iou, gt[3]]
+
+
+def test_coco_bbox_eval_hand_computed_cases():
+    """COCOeval('bbox') restated in utils/coco_evaluation.py (parity unpinned: pycocotools is absent), on cases small
+    enough to compute by hand:
+    A  one image, two ground-truth boxes; detections: 0.9 -> exact hit, 0.8 -> miss, 0.7 -> IoU 0.62 with the second box.
+       IoU thresholds .5/.55/.6 see tp,fp,tp: precision envelope [1, 2/3, 2/3] at recalls [.5, .5, 1] -> the 101-point
+       mean is (51 + 50 * 2/3) / 101; the seven higher thresholds see tp,fp,fp -> 51 / 101.
+    B  a crowd region absorbs any number of detections without penalty and does not count as ground truth.
+    C  area ranges: a 20x20 ground truth counts only for 'small'; a detection matched to an out-of-range ground truth
+       is ignored, an unmatched detection outside the range as well.
+    D  max detections: with the hit ranked second, AR_max1 = 0 and AR_max10 = 1."""
+    from mtl_ssl_b200.utils.coco_evaluation import CocoBBoxEval, bbox_iou
+    g1, g2 = [10.0, 10.0, 100.0, 100.0], [200.0, 50.0, 120.0, 100.0]
+    np.testing.assert_allclose(bbox_iou([_xywh_iou_box(g2, 0.62)], [g2], [0]), [[0.62]], rtol=1e-12)
+    gts = [dict(id=1, image_id=1, category_id=1, bbox=g1, area=100.0 * 100.0, iscrowd=0),
+           dict(id=2, image_id=1, category_id=1, bbox=g2, area=120.0 * 100.0, iscrowd=0)]
+    dts = [dict(image_id=1, category_id=1, bbox=g1, score=0.9),
+           dict(image_id=1, category_id=1, bbox=[400.0, 300.0, 100.0, 100.0], score=0.8),
+           dict(image_id=1, category_id=1, bbox=_xywh_iou_box(g2, 0.62), score=0.7)]
+    s = CocoBBoxEval(gts, dts).run()
+    hi, lo = (51 + 50 * 2.0 / 3.0) / 101, 51.0 / 101
+    np.testing.assert_allclose(s[1], hi, rtol=1e-9)                      # AP50
+    np.testing.assert_allclose(s[2], lo, rtol=1e-9)                      # AP75
+    np.testing.assert_allclose(s[0], (3 * hi + 7 * lo) / 10, rtol=1e-9)  # AP@[.5:.95]
+    assert s[3] == -1 and s[4] == -1                                     # no small / medium ground truth
+    np.testing.assert_allclose(s[5], s[0], rtol=1e-12)                   # everything is 'large'
+    np.testing.assert_allclose(s[6], 0.5, rtol=1e-12)                    # AR_max1: the best detection finds one of two
+    np.testing.assert_allclose(s[8], (3 * 1.0 + 7 * 0.5) / 10, rtol=1e-12)
+    # perfect detections
+    s = CocoBBoxEval(gts, [dict(image_id=1, category_id=1, bbox=g["bbox"], score=0.5 + 0.1 * i)
+                           for i, g in enumerate(gts)]).run()
+    np.testing.assert_allclose(s[[0, 1, 2, 5, 7, 8]], 1.0, rtol=1e-12)
+    # B: crowd
+    crowd = dict(id=3, image_id=1, category_id=1, bbox=[0.0, 300.0, 300.0, 200.0], area=60000.0, iscrowd=1)
+    inside = [dict(image_id=1, category_id=1, bbox=[10.0 + 40 * i, 320.0, 30.0, 60.0], score=0.95 - 0.01 * i)
+              for i in range(4)]                                         # four detections inside the crowd region
+    s = CocoBBoxEval(gts + [crowd], inside + [dict(image_id=1, category_id=1, bbox=g["bbox"], score=0.5)
+                                               for g in gts]).run()
+    np.testing.assert_allclose(s[[0, 1, 2]], 1.0, rtol=1e-12)            # ranked above the hits, yet no false positive
+    s_fp = CocoBBoxEval(gts, inside + [dict(image_id=1, category_id=1, bbox=g["bbox"], score=0.5) for g in gts]).run()
+    assert s_fp[1] < 0.4                                                 # without the crowd annotation they are
+    # C: area ranges
+    small = dict(id=4, image_id=2, category_id=1, bbox=[5.0, 5.0, 20.0, 20.0], area=400.0, iscrowd=0)
+    dsmall = dict(image_id=2, category_id=1, bbox=[5.0, 5.0, 20.0, 20.0], score=0.6)
+    stray = dict(image_id=2, category_id=1, bbox=[100.0, 100.0, 200.0, 200.0], score=0.9)   # large, unmatched
+    s = CocoBBoxEval([small], [dsmall, stray]).run()
+    np.testing.assert_allclose(s[3], 1.0, rtol=1e-12)                    # small: the stray detection is out of range
+    np.testing.assert_allclose(s[1], 0.5, rtol=1e-9)                     # all areas: fp ranked first -> precision 1/2
+    assert s[4] == -1 and s[5] == -1 and s[9] == 1.0
+    # D: max detections
+    s = CocoBBoxEval([small], [dsmall, dict(stray, bbox=[100.0, 100.0, 10.0, 10.0])]).run()
+    assert s[6] == 0.0 and s[7] == 1.0 and s[8] == 1.0
+    # per-category restriction and categories without ground truth
+    other = dict(id=5, image_id=1, category_id=2, bbox=g1, area=1e4, iscrowd=0)
+    s2 = CocoBBoxEval(gts + [other], dts, cat_ids=[2]).run()
+    assert s2[0] == 0.0 and s2[8] == 0.0
+    s12 = CocoBBoxEval(gts + [other], dts).run()
+    np.testing.assert_allclose(s12[1], (hi + 0.0) / 2, rtol=1e-9)        # mean over the two categories
+
+
+def test_coco_evaluation_wrapper_and_eval_util(tmp_path):
+    """`CocoEvaluation` (object_detection_evaluation.py:294-427) + `evaluate_detection_results_coco`
+    (eval_util.py:393-548): [ymin,xmin,ymax,xmax] -> [x,y,w,h], category = class + 1, at most 100 rows per image in
+    descending score, ground truth from the annotation file, metric names 'COCO_Eval/<All|name>/<metric>'."""
+    import json
+    from mtl_ssl_b200 import eval_util
+    from mtl_ssl_b200.data.mscoco import CocoIndex
+    from mtl_ssl_b200.utils.coco_evaluation import CocoEvaluation
+    ann = {"images": [{"id": 1, "file_name": "1.jpg", "height": 480, "width": 640},
+                      {"id": 2, "file_name": "2.jpg", "height": 480, "width": 640}],
+           "categories": [{"id": 1, "name": "a"}, {"id": 2, "name": "b"}],
+           "annotations": [{"id": 1, "image_id": 1, "category_id": 1, "bbox": [10.0, 20.0, 100.0, 50.0], "area": 5000.0, "iscrowd": 0},
+                           {"id": 2, "image_id": 2, "category_id": 2, "bbox": [30.0, 40.0, 200.0, 150.0], "area": 30000.0, "iscrowd": 0}]}
+    path = str(tmp_path / "instances_eval.json")
+    open(path, "w").write(json.dumps(ann))
+    ev = CocoEvaluation(2)
+    ev.add_single_detected_image_info(1, np.array([[20.0, 10.0, 70.0, 110.0]]), np.array([0.9]), np.array([0]))
+    np.testing.assert_allclose(ev.detection_result, [[1, 10.0, 20.0, 100.0, 50.0, 0.9, 1]])
+    many = np.tile(np.array([[40.0, 30.0, 190.0, 230.0]]), (150, 1)) + np.arange(150)[:, None] * 1e-3
+    ev.add_single_detected_image_info(2, many, np.linspace(0.1, 0.8, 150), np.ones(150, int))
+    assert len(ev.detection_result) == 101 and ev.detection_result[1, 5] == 0.8       # best 100, descending
+    assert (np.diff(ev.detection_result[1:, 5]) <= 0).all() and (ev.detection_result[1:, 6] == 2).all()
+    m = ev.evaluate([0, 1, 2], path)
+    assert sorted(m) == [0, 1, 2] and all(len(v) == 12 for v in m.values())
+    np.testing.assert_allclose([m[0][1], m[1][1]], 1.0, rtol=1e-12)
+    assert ev.evaluate([0], str(tmp_path / "missing.json")) is None
+    with pytest.raises(ValueError):
+        ev.add_single_detected_image_info(3, np.zeros((2, 4)), np.zeros(1), np.zeros(2))
+    lists = dict(image_id=["1", "2"], groundtruth_boxes=[np.array([[20.0, 10.0, 70.0, 110.0]]), np.array([[40.0, 30.0, 190.0, 230.0]])],
+                 groundtruth_classes=[np.array([1]), np.array([2])],
+                 detection_boxes=[np.array([[20.0, 10.0, 70.0, 110.0]]), np.array([[40.0, 30.0, 190.0, 230.0], [0.0, 0.0, 50.0, 50.0]])],
+                 detection_scores=[np.array([0.9]), np.array([0.6, 0.7])], detection_classes=[np.array([1]), np.array([2, 2])])
+    cats = [{"id": 1, "name": "a"}, {"id": 2, "name": "b"}]
+    got = eval_util.evaluate_detection_results_coco(lists, cats, label_id_offset=1, eval_ann_filename=CocoIndex(path))
+    assert sorted(got) == ["COCO_Eval/All/AP", "COCO_Eval/a/AP", "COCO_Eval/b/AP"]
+    np.testing.assert_allclose(got["COCO_Eval/a/AP"], 1.0)
+    np.testing.assert_allclose(got["COCO_Eval/b/AP"], 0.5, rtol=1e-9)     # false positive ranked above the hit
+    np.testing.assert_allclose(got["COCO_Eval/All/AP"], 0.75, rtol=1e-9)
+    assert eval_util.evaluate_detection_results_coco(lists, cats, 1, eval_ann_filename=str(tmp_path / "none.json")) == {}
