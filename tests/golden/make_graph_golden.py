@@ -319,8 +319,52 @@ def postprocess_case(out):
             out[p + k] = np.asarray(d[k], F)
 
 
+def _crop_and_resize(image, boxes, box_ind, crop_size, extrapolation_value=0.0, **k):
+    """tf.image.crop_and_resize (bilinear) restated: y = y1 (H-1) + i (y2 - y1)(H-1)/(ch-1) (centre when ch == 1),
+    samples outside [0, H-1] give the extrapolation value."""
+    image, boxes, box_ind = np.asarray(image, F), np.asarray(boxes, F), np.asarray(box_ind).astype(int)
+    ch, cw = [int(v) for v in crop_size]
+    _, H, W, C = image.shape
+    out_ = np.full((len(boxes), ch, cw, C), 0.0 if extrapolation_value is None else extrapolation_value, F)   # None -> op default 0
+    for n, (y1, x1, y2, x2) in enumerate(boxes):
+        for i in range(ch):
+            y = y1 * (H - 1) + i * (y2 - y1) * (H - 1) / (ch - 1) if ch > 1 else 0.5 * (y1 + y2) * (H - 1)
+            if y < 0 or y > H - 1:
+                continue
+            t0, t1, ly = int(np.floor(y)), int(np.ceil(y)), y - np.floor(y)
+            for j in range(cw):
+                x = x1 * (W - 1) + j * (x2 - x1) * (W - 1) / (cw - 1) if cw > 1 else 0.5 * (x1 + x2) * (W - 1)
+                if x < 0 or x > W - 1:
+                    continue
+                l0, l1, lx = int(np.floor(x)), int(np.ceil(x)), x - np.floor(x)
+                im = image[box_ind[n]]
+                top = im[t0, l0] + (im[t0, l1] - im[t0, l0]) * F(lx)
+                bot = im[t1, l0] + (im[t1, l1] - im[t1, l0]) * F(lx)
+                out_[n, i, j] = top + (bot - top) * F(ly)
+    return t(out_)
+
+
+def psroi_case(out):
+    """utils/ops.py:462-609 `position_sensitive_crop_regions` (global_pool=True, the R-FCN configs' 3x3 bins of an
+    18x18 crop): bin geometry, channel-group order, bin / spatial averaging -- with the crop_and_resize above."""
+    ops_mod = M["object_detection.utils.ops"]
+    tf.image.crop_and_resize = _crop_and_resize
+    tf.add_n = lambda xs, **k: t(sum(np.asarray(x, F) for x in xs))
+    rng = np.random.default_rng(59)
+    D, R = 5, 7
+    fmap = rng.normal(0, 1, (2, 9, 11, 9 * D)).astype(F)
+    y0, x0 = rng.uniform(0, 0.6, R), rng.uniform(0, 0.6, R)
+    boxes = np.stack([y0, x0, y0 + rng.uniform(0.1, 0.4, R), x0 + rng.uniform(0.1, 0.4, R)], 1).astype(F)
+    boxes[0] = [-0.1, 0.2, 0.5, 1.1]                                  # partly outside: extrapolation 0
+    box_ind = rng.integers(0, 2, R).astype(np.int32)
+    got = ops_mod.position_sensitive_crop_regions(t(fmap), t(boxes), t(box_ind), [18, 18], [3, 3], global_pool=True)
+    out["psroi/fmap"], out["psroi/boxes"], out["psroi/box_ind"] = fmap, boxes, box_ind
+    out["psroi/out"] = np.asarray(got, F)
+
+
 def main():
     out = {}
+    psroi_case(out)
     rpn_cases(out)
     postprocess_case(out)
     refine_case(out)

@@ -133,6 +133,10 @@ def _ints(shape):
     return [int(s) for s in np.asarray(shape).reshape(-1)]
 
 
+def _axis(a):
+    return tuple(int(v) for v in a) if isinstance(a, (list, tuple, np.ndarray)) else a
+
+
 def _where(cond, x=None, y=None):
     cond = np.asarray(cond)
     if x is None:
@@ -248,7 +252,7 @@ def make_tf():
     for n, f in (("reduce_max", np.max), ("reduce_min", np.min), ("reduce_sum", np.sum), ("reduce_mean", np.mean),
                  ("reduce_any", np.any), ("reduce_all", np.all)):
         setattr(tf, n, _w(lambda x, axis=None, keep_dims=False, keepdims=False, reduction_indices=None, f=f:
-                          f(np.asarray(x), axis=axis if axis is not None else reduction_indices,
+                          f(np.asarray(x), axis=_axis(axis if axis is not None else reduction_indices),
                             keepdims=bool(keep_dims or keepdims))))
     tf.argmax = _w(lambda x, axis=0, output_type=np.int64, dimension=None:
                    np.argmax(np.asarray(x), axis if dimension is None else dimension).astype(output_type))

@@ -659,3 +659,21 @@ def test_coco_examples_against_reference_mscoco_record_writer():
             np.testing.assert_allclose(lab, wl[i], atol=1.001e-3)
         assert mscoco.get_image_id("/x/COCO_val2014_%012d.jpg" % int(str(g[p + "source_id"]))) == int(str(g[p + "source_id"]))
     assert clamped
+
+
+def test_position_sensitive_crop_against_reference_ops_run_on_the_tf_shim():
+    """utils/ops.py:462-609 `position_sensitive_crop_regions` (global_pool=True, 3x3 bins of an 18x18 crop as in the
+    R-FCN configs) EXECUTED on the shim over random features (the bilinear crop inside is a NumPy restatement written
+    independently of the oracle's): bin geometry, channel-group order, the two averaging steps and the zero extrapolation
+    outside the map -- against `Oracle.psroi`; this also cross-checks oracle/nn.py `crop_and_resize` with a second
+    implementation.  fp32 summation order differs: 2e-6 absolute."""
+    import torch
+    from oracle.model import Oracle
+    g = _graph_golden()
+    o = Oracle({}, dict(architecture="resnet_v1_101", mtl={}), bf16=False)
+    D = g["psroi/fmap"].shape[-1] // 9
+    got = o.psroi(torch.from_numpy(g["psroi/fmap"]), g["psroi/boxes"], g["psroi/box_ind"].astype(np.int64), D, (3, 3),
+                  (18, 18)).numpy()
+    want = g["psroi/out"].reshape(len(g["psroi/boxes"]), D)
+    assert np.abs(want).max() > 0.05
+    np.testing.assert_allclose(got, want, rtol=1e-5, atol=2e-6)
