@@ -14,9 +14,12 @@ from . import eval_util
 from .utils import mtl_metrics
 
 
-def run_inference(model, example):
+def run_inference(model, example, use_refiner=False):
     """One example dict (data/synthetic.py / data/tfrecord.py format) through the inference-mode model.
-    Returns the per-image result dict (NumPy)."""
+    Returns the per-image result dict (NumPy).
+    use_refiner: run `predict_with_mtl_results` on the inference proposals when the config enables the class refiner, so
+    that `postprocess` scores the refined logits -- what the reference's evaluator does (evaluator.py:151-152,
+    fmA:1040-1043).  Off by default until the path has been run on a GPU."""
     if model._is_training:
         raise ValueError("evaluation needs a model built with is_training=False")
     dev = model.device
@@ -29,6 +32,8 @@ def run_inference(model, example):
         pd = model.predict_with_window(pd, window_boxes_normalized=wb, _keep=False)
     if mtl is not None and mtl.edgemask:
         pd = model.predict_edgemask(pd)
+    if use_refiner and mtl is not None and mtl.refine:
+        pd = model.predict_with_mtl_results(pd)
     det = model.postprocess(pd)
     torch.cuda.synchronize()          # the auxiliary heads ran on side streams ("lanes"): wait for all of them
     n = int(det["num_detections"][0].item())
@@ -66,7 +71,7 @@ EVAL_METRICS_FN_DICT = {                      # evaluator.py:40-43 of the refere
 
 
 def evaluate(model, examples, categories, iou_thres=0.5, corloc_summary=True, metrics_set="pascal_voc_metrics",
-             eval_config=None, eval_ann_filename=None):
+             eval_config=None, eval_ann_filename=None, use_refiner=False):
     """Runs `examples` through the model and returns {metric name: value}: the detection metrics of eval_util
     (`metrics_set` as in eval.proto: 'pascal_voc_metrics' or 'coco_metrics'; for COCO the examples carry the image id in
     'source_id' and the ground truth is read from the annotation file) plus 'mtl/window_map', 'mtl/closeness_diff',
@@ -75,7 +80,7 @@ def evaluate(model, examples, categories, iou_thres=0.5, corloc_summary=True, me
         raise ValueError("Metric not found: {}".format(metrics_set))
     lists = {}
     for i, ex in enumerate(examples):
-        r = run_inference(model, ex)
+        r = run_inference(model, ex, use_refiner)
         r["image_id"] = str(ex.get("source_id", i)) if metrics_set == "coco_metrics" else str(i)
         for k, v in r.items():
             lists.setdefault(k, []).append(v)

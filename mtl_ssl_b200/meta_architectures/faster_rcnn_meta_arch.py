@@ -652,7 +652,10 @@ class FasterRCNNMetaArch(model.DetectionModel):
         nms_cfg = self._second_stage_nms_fn
         mode = {"IDENTITY": 0, "SOFTMAX": 1, "SIGMOID": 2}[str(self._second_stage_score_conversion_fn)]
         enc = pd["refined_box_encodings"].contiguous().float()
-        logits = pd["class_predictions_with_background"].contiguous().float()
+        if self._mtl is not None and self._mtl.refine and "mtl_refined_class_predictions_with_background" in pd:
+            logits = pd["mtl_refined_class_predictions_with_background"].contiguous().float()      # fmA:1040-1043
+        else:
+            logits = pd["class_predictions_with_background"].contiguous().float()
         props = pd["proposal_boxes"]
         B, P = props.shape[0], props.shape[1]
         K = self.num_classes

@@ -314,13 +314,17 @@ class Oracle(object):
         scores[:len(idx)] = ps[idx]
         return boxes, scores, len(idx), (pb, ps, n)
 
-    def forward(self, images, examples, keys, H, W, proposal_inputs=None, inference=False):
+    def forward(self, images, examples, keys, H, W, proposal_inputs=None, inference=False, inference_mtl=False):
         """proposal_inputs: optional (rpn_box [B,N,4], rpn_cls [B,N,2]) numpy arrays used INSTEAD of the
         oracle's own RPN outputs for the (non-differentiable) proposal selection, so that index-level
         parity can be checked on identical inputs.
         inference=True: the is_training=False graph (fmA:586-590 anchors clipped instead of pruned; fmA:1111-1131 no
         minibatch sampling, max_num_proposals = first_stage_max_proposals, fmA:475-477); returns after the
-        second-stage box classifier (what `postprocess` consumes); `examples` / `keys` are not used."""
+        second-stage box classifier (what `postprocess` consumes); `examples` / `keys` are not used.
+        inference_mtl=True: continue like the reference's evaluator (evaluator.py:145-152) through the closeness head and
+        `predict_with_mtl_results` on the inference proposals, so that `postprocess` scores the refined logits
+        (fmA:1040-1043); the window / edge-mask heads run only when `examples` is given (they need the ground-truth
+        windows)."""
         cfg, p = self.cfg, self.p
         B = images.shape[0]
         K = cfg["num_classes"]
@@ -403,7 +407,7 @@ class Oracle(object):
                                ["BoxEncodingPredictor", "ClassPredictor"])
         out["refined_box_encodings"] = bx.reshape(B * P, K, 4)
         out["class_predictions_with_background"] = cl
-        if inference:
+        if inference and not inference_mtl:
             return out
         if mtl.get("closeness"):
             if rfcn:
@@ -416,7 +420,9 @@ class Oracle(object):
                 out["closeness_predictions"] = self.head(tail(m2, "ClosenessBoxPredictor/" + self.arch),
                                                          "ClosenessBoxPredictor", ["ClassPredictor"])[0]
         win_feat = None
-        if mtl.get("window"):
+        if rfcn and mtl.get("window") and mtl.get("refine") and examples is None:
+            win_feat = self.block4(feat, "WindowBoxPredictor/" + self.arch)
+        if mtl.get("window") and examples is not None:
             wb = np.stack([np.asarray(e["window_boxes"], np.float32) for e in examples])
             nw = wb.shape[1]
             wbi = np.repeat(np.arange(B), nw).astype(np.int64)

@@ -677,3 +677,41 @@ def test_position_sensitive_crop_against_reference_ops_run_on_the_tf_shim():
     want = g["psroi/out"].reshape(len(g["psroi/boxes"]), D)
     assert np.abs(want).max() > 0.05
     np.testing.assert_allclose(got, want, rtol=1e-5, atol=2e-6)
+
+
+def test_oracle_inference_graph_with_refiner_runs_on_cpu():
+    """`Oracle.forward(inference=True, inference_mtl=True)`: the evaluator's graph (evaluator.py:145-152): clipped anchors,
+    unsampled proposals, closeness head and class refiner over the 5 expanded windows of every inference proposal; the
+    refined logits are what `postprocess` scores (fmA:1040-1043)."""
+    import torch
+    from helpers import load_config, oracle_config
+    from mtl_ssl_b200.data import synthetic
+    from oracle import postprocess as OP
+    from oracle.model import Oracle
+    import oracle.refparams as refparams
+    H, W = 224, 320
+    cfg = load_config("model12.config", (("min_dimension: 600", "min_dimension: 224"),
+                                         ("max_dimension: 1024", "max_dimension: 320"),
+                                         ("first_stage_max_proposals: 300", "first_stage_max_proposals: 24"),
+                                         ("second_stage_batch_size: 256", "second_stage_batch_size: 16")))
+    ocfg = oracle_config(cfg)
+    params, _ = refparams.build_params(ocfg, seed=0)
+    examples = synthetic.make_batch(1, 1, H, W, ocfg["num_classes"], max_boxes=4, num_windows=8)
+    img = torch.from_numpy(np.stack([e["image"] for e in examples]))
+    orc = Oracle(params, ocfg, bf16=True)
+    with torch.no_grad():
+        plain = orc.forward(img, None, None, H, W, inference=True)
+        out = orc.forward(img, None, None, H, W, inference=True, inference_mtl=True)
+    M, K1 = 24, ocfg["num_classes"] + 1
+    assert "mtl_refined_class_predictions_with_background" not in plain
+    ref = out["mtl_refined_class_predictions_with_background"]
+    assert ref.shape == (M, K1) and out["closeness_predictions"].shape == (M, K1)
+    assert out["refine_in"].shape == (M, K1 + 5 * K1 + K1) and "window_class_predictions" not in out
+    assert torch.equal(out["class_predictions_with_background"], plain["class_predictions_with_background"])
+    # residue: refined = FC(refiner input) + original logits, so the two differ by the FC output only
+    delta = (ref - out["class_predictions_with_background"]).abs().max()
+    assert 0 < float(delta) < 10
+    n = int(out["nprop"][0])
+    b, s, c, nd = OP.second_stage_postprocess(out["refined_box_encodings"].numpy(), ref.numpy(), out["prop_abs"],
+                                              out["nprop"], (H, W), 0.0, 0.6, 100, 100)
+    assert 0 < nd[0] <= 100 and n > 0
