@@ -70,26 +70,36 @@ EVAL_METRICS_FN_DICT = {                      # evaluator.py:40-43 of the refere
 }
 
 
-def evaluate(model, examples, categories, iou_thres=0.5, corloc_summary=True, metrics_set="pascal_voc_metrics",
-             eval_config=None, eval_ann_filename=None, use_refiner=False):
-    """Runs `examples` through the model and returns {metric name: value}: the detection metrics of eval_util
-    (`metrics_set` as in eval.proto: 'pascal_voc_metrics' or 'coco_metrics'; for COCO the examples carry the image id in
-    'source_id' and the ground truth is read from the annotation file) plus 'mtl/window_map', 'mtl/closeness_diff',
-    'mtl/edgemask_ap' for the auxiliary heads the config enables."""
+def detection_metrics(lists, categories, eval_config=None, metrics_set=None, iou_thres=None, corloc_summary=True,
+                      eval_ann_filename=None):
+    """The metric call of the reference's evaluator (evaluator.py:312-323): `eval_config` (eval.proto) supplies
+    metrics_set, iou_threshold, nms_type, nms_threshold, soft_nms_sigma and coco_eval_options; explicit arguments win."""
+    g = lambda name, default: getattr(eval_config, name, default) if eval_config is not None else default
+    metrics_set = metrics_set or g("metrics_set", "pascal_voc_metrics")
     if metrics_set not in EVAL_METRICS_FN_DICT:
         raise ValueError("Metric not found: {}".format(metrics_set))
+    kw = dict(iou_thres=g("iou_threshold", 0.5) if iou_thres is None else iou_thres, nms_type=g("nms_type", "standard"),
+              nms_thres=g("nms_threshold", 1.0), soft_nms_sigma=g("soft_nms_sigma", 0.5))
+    if metrics_set == "coco_metrics":
+        return eval_util.evaluate_detection_results_coco(lists, categories, eval_config=eval_config,
+                                                         eval_ann_filename=eval_ann_filename, **kw)
+    return eval_util.evaluate_detection_results_pascal_voc(lists, categories, corloc_summary=corloc_summary, **kw)
+
+
+def evaluate(model, examples, categories, iou_thres=None, corloc_summary=True, metrics_set=None, eval_config=None,
+             eval_ann_filename=None, use_refiner=False):
+    """Runs `examples` through the model and returns {metric name: value}: the detection metrics of eval_util
+    (`metrics_set` as in eval.proto: 'pascal_voc_metrics' or 'coco_metrics', taken from `eval_config` when not given; for
+    COCO the examples carry the image id in 'source_id' and the ground truth is read from the annotation file) plus
+    'mtl/window_map', 'mtl/closeness_diff', 'mtl/edgemask_ap' for the auxiliary heads the config enables."""
+    coco = (metrics_set or getattr(eval_config, "metrics_set", "pascal_voc_metrics")) == "coco_metrics"
     lists = {}
     for i, ex in enumerate(examples):
         r = run_inference(model, ex, use_refiner)
-        r["image_id"] = str(ex.get("source_id", i)) if metrics_set == "coco_metrics" else str(i)
+        r["image_id"] = str(ex.get("source_id", i)) if coco else str(i)
         for k, v in r.items():
             lists.setdefault(k, []).append(v)
-    if metrics_set == "coco_metrics":
-        metrics = eval_util.evaluate_detection_results_coco(lists, categories, iou_thres=iou_thres,
-                                                            eval_config=eval_config, eval_ann_filename=eval_ann_filename)
-    else:
-        metrics = eval_util.evaluate_detection_results_pascal_voc(lists, categories, iou_thres=iou_thres,
-                                                                  corloc_summary=corloc_summary)
+    metrics = detection_metrics(lists, categories, eval_config, metrics_set, iou_thres, corloc_summary, eval_ann_filename)
     has_dets = all(len(d) for d in lists["detection_boxes"]) and all(len(g) for g in lists["groundtruth_boxes"])
     aux = {k: v for k, v in lists.items() if k.split("_")[0] in ("window", "edgemask") or
            (k.startswith("closeness") and has_dets)}

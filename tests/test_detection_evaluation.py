@@ -288,3 +288,34 @@ def test_coco_evaluation_wrapper_and_eval_util(tmp_path):
     np.testing.assert_allclose(got["COCO_Eval/b/AP"], 0.5, rtol=1e-9)     # false positive ranked above the hit
     np.testing.assert_allclose(got["COCO_Eval/All/AP"], 0.75, rtol=1e-9)
     assert eval_util.evaluate_detection_results_coco(lists, cats, 1, eval_ann_filename=str(tmp_path / "none.json")) == {}
+
+
+def test_detection_metrics_follow_the_pipeline_eval_config(tmp_path):
+    """evaluator.py:312-323: the metric function and its options come from `eval_config` -- model22.config (COCO) asks for
+    'coco_metrics', all twelve metric indices, all-categories only; model12.config (VOC) for the PASCAL metrics."""
+    import json
+    from helpers import load_config
+    from mtl_ssl_b200 import evaluator
+    lists = dict(image_id=["1"], groundtruth_boxes=[np.array([[20.0, 10.0, 70.0, 110.0]])], groundtruth_classes=[np.array([1])],
+                 detection_boxes=[np.array([[20.0, 10.0, 70.0, 110.0]])], detection_scores=[np.array([0.9])],
+                 detection_classes=[np.array([1])])
+    cats = [{"id": 1, "name": "a"}, {"id": 2, "name": "b"}]
+    ann = {"images": [{"id": 1, "file_name": "1.jpg", "height": 480, "width": 640}],
+           "categories": [{"id": 1, "name": "a"}, {"id": 2, "name": "b"}],
+           "annotations": [{"id": 1, "image_id": 1, "category_id": 1, "bbox": [10.0, 20.0, 100.0, 50.0], "area": 5000.0, "iscrowd": 0}]}
+    path = str(tmp_path / "instances.json")
+    open(path, "w").write(json.dumps(ann))
+    coco_cfg = load_config("model22.config").eval_config
+    assert coco_cfg.metrics_set == "coco_metrics" and list(coco_cfg.coco_eval_options.eval_metric_index) == list(range(12))
+    m = evaluator.detection_metrics(lists, cats, coco_cfg, eval_ann_filename=path)
+    assert sorted(m) == sorted("COCO_Eval/All/" + n for n in
+                               ("AP", "AP_IoU50", "AP_IoU75", "AP_small", "AP_medium", "AP_large", "AR_max1", "AR_max10",
+                                "AR_max100", "AR_small", "AR_medium", "AR_large"))
+    # tp / (tp + fp + eps), as pycocotools: "1" is 1 - 2e-16
+    assert abs(m["COCO_Eval/All/AP"] - 1.0) < 1e-12 and abs(m["COCO_Eval/All/AP_medium"] - 1.0) < 1e-12
+    assert m["COCO_Eval/All/AP_small"] == -1.0
+    voc_cfg = load_config("model12.config").eval_config
+    m = evaluator.detection_metrics(lists, cats, voc_cfg)
+    assert m["Subset default    mAP@0.5IOU/a"] == 1.0 and "CorLoc/CorLoc@0.5IOU" in m
+    with pytest.raises(ValueError):
+        evaluator.detection_metrics(lists, cats, metrics_set="open_images_metrics")
