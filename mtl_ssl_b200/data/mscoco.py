@@ -156,4 +156,6 @@ class CocoDataset(object):
         for i in self.ids:
             anns = self.coco.loadAnns(self.coco.getAnnIds(imgIds=i))
             img = np.asarray(Image.open(os.path.join(self.image_dir, self.coco.imgs[i]["file_name"])).convert("RGB"))
-            yield annotations_to_example(anns, img, self.coco.cats, self.label_map, self.K, rng, self.num_windows)
+            ex = annotations_to_example(anns, img, self.coco.cats, self.label_map, self.K, rng, self.num_windows)
+            ex["source_id"], ex["filename"] = str(i), self.coco.imgs[i]["file_name"]       # image id for the COCO metrics
+            yield ex

@@ -366,7 +366,7 @@ def test_mscoco_records_and_dataset_reader(tmp_path):
     assert d["groundtruth_edgemask"].shape == (2, 64, 64)
     ds = C.CocoDataset(coco, str(img_dir), num_classes=90, seed=1, num_windows=16)
     (e,) = list(ds)
-    assert len(ds) == 1 and e["image"].shape == (200, 320, 3)
+    assert len(ds) == 1 and e["image"].shape == (200, 320, 3) and e["source_id"] == "139" == d["source_id"]
     np.testing.assert_allclose(e["groundtruth_boxes"], d["groundtruth_boxes"], rtol=1e-6)
     np.testing.assert_array_equal(e["groundtruth_classes"], d["groundtruth_classes"])
     np.testing.assert_allclose(e["window_classes"], d["window_classes"], atol=5e-4)
