@@ -204,3 +204,35 @@ def test_resize_to_range_output_sizes_match_reference_vectors():
     # the two workloads of BASELINE.json: VOC-shape and COCO-shape inputs are already in range
     assert list(_compute_new_static_size(600, 1000, 600, 1024)) == [600, 1000]
     assert list(_compute_new_static_size(300, 300, 600, 1024)) == [600, 600]          # model51: 300x300 upsampled
+
+
+def test_label_map_util_reference_vectors(tmp_path):
+    """utils/label_map_util_test.py:37-167: name -> id dictionary, ids below 1 refused, first item per id kept,
+    display names, default categories, category index; plus the two label maps shipped with the reference's data/."""
+    from mtl_ssl_b200.utils import label_map_util as L
+    path = str(tmp_path / "label_map.pbtxt")
+    open(path, "w").write("item {\n  id:2\n  name:'cat'\n}\nitem {\n  id:1\n  name:'dog'\n}\n")
+    d = L.get_label_map_dict(path)
+    assert d == {"dog": 1, "cat": 2} and L.get_class_indices(d) == [1, 2] and L.get_index_map_dict(d) == {1: "dog", 2: "cat", 0: "bg"}
+    open(path, "w").write("item {\n id:0\n name:'class that should not be indexed at zero'\n}\nitem {\n id:2\n name:'cat'\n}\n")
+    with pytest.raises(ValueError):
+        L.load_labelmap(path)
+    lm = L.load_labelmap("item {\n id:2\n name:'cat'\n}\nitem {\n id:1\n name:'child'\n}\nitem {\n id:1\n name:'person'\n}\n"
+                         "item {\n id:1\n name:'n00007846'\n}\n")
+    assert L.convert_label_map_to_categories(lm, max_num_classes=3) == [{"id": 2, "name": "cat"}, {"id": 1, "name": "child"}]
+    assert L.convert_label_map_to_categories(None, max_num_classes=3) == \
+        [{"name": "category_1", "id": 1}, {"name": "category_2", "id": 2}, {"name": "category_3", "id": 3}]
+    gen = "".join("item {\n id: %d\n name: 'label_%d'\n display_name: '%d'\n}\n" % (i, i, i) for i in range(1, 5))
+    assert L.convert_label_map_to_categories(L.load_labelmap(gen), max_num_classes=3) == \
+        [{"name": "1", "id": 1}, {"name": "2", "id": 2}, {"name": "3", "id": 3}]
+    assert L.convert_label_map_to_categories(L.load_labelmap(gen), 2, use_display_name=False) == \
+        [{"name": "label_1", "id": 1}, {"name": "label_2", "id": 2}]
+    assert L.create_category_index([{"name": "1", "id": 1}, {"name": "2", "id": 2}]) == \
+        {1: {"name": "1", "id": 1}, 2: {"name": "2", "id": 2}}
+    # the shape of the maps under the reference's data/ directory (pascal: 20 dense ids; mscoco: 80 names on ids 1..90)
+    voc = "".join("item {\n  id: %d\n  name: 'c%d'\n}\n\n" % (i, i) for i in range(1, 21))
+    assert len(L.convert_label_map_to_categories(L.load_labelmap(voc), 20)) == 20
+    coco = "".join('item {\n  name: "/m/%02d"\n  id: %d\n  display_name: "thing %d"\n}\n' % (i, i, i)
+                   for i in list(range(1, 12)) + [13, 90])
+    cats = L.convert_label_map_to_categories(L.load_labelmap(coco), 90)
+    assert cats[-1] == {"id": 90, "name": "thing 90"} and len(cats) == 13
