@@ -58,7 +58,7 @@ def test_inference_refiner_matches_oracle_and_feeds_postprocess():
     assert _cos(pd["closeness_predictions"].float().cpu()[:n], out["closeness_predictions"].float()[:n]) > 0.999
     assert _cos(ref[:n], out["mtl_refined_class_predictions_with_background"].float()[:n]) > 0.999
     assert _cos((ref - cls)[:n], (out["mtl_refined_class_predictions_with_background"]
-                                  - out["class_predictions_with_background"]).float()[:n]) > 0.99
+                                  - out["class_predictions_with_background"]).float()[:n]) > 0.98
     assert float((ref - cls)[:n].abs().max()) > 1e-3               # the refiner changed the logits ...
     assert not torch.equal(det["detection_scores"], plain["detection_scores"])      # ... and the detections follow
     nd = int(det["num_detections"][0].item())
