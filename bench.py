@@ -40,6 +40,28 @@ def algorithmic_flops_per_image():
     return 4.92e12
 
 
+def dominant_conv_group(records, peak):
+    """records: (mode, algorithmic flops, milliseconds, (N,H,W,C,K,R,stride,P,Q)) per tcgen05 launch of one step.
+    Groups launches of identical mode + geometry and returns the roofline entry of the group with the largest total
+    time (the step's dominant kernel): achieved = its algorithmic FLOPs / its summed launch durations."""
+    groups = {}
+    for mode, flops, ms, geom in records:
+        g = groups.setdefault((int(mode), tuple(int(v) for v in geom)), [0.0, 0.0, 0])
+        g[0] += float(flops); g[1] += float(ms); g[2] += 1
+    if not groups:
+        return None
+    (mode, geom), (flops, ms, n) = max(groups.items(), key=lambda kv: kv[1][1])
+    if ms <= 0:
+        return None
+    N, H_, W_, C, K, R, stride, P, Q = geom
+    achieved = flops / (ms * 1e-3) / 1e12
+    total_ms = sum(g[1] for g in groups.values())
+    return {"kernel": "tc_gemm_kernel %s %dx%d/%d C%d->K%d on %dx%dx%d" % (("fprop", "dgrad", "wgrad")[mode], R, R, stride, C,
+                                                                           K, N, H_, W_),
+            "launches": n, "avg_us": ms * 1e3 / n, "share_of_conv_time": ms / total_ms, "achieved": achieved,
+            "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None}
+
+
 # ------------------------------------------------------------------------------------------ clocks
 class ClockSampler(object):
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
@@ -298,6 +320,10 @@ def run_ours(args, rank, world, local_rank):
     if not peak:
         peak, peak_src = 1400.0, "fallback (B200_PROFILING.md sustained)"
     achieved = conv_flops / (conv_ms * 1e-3) / 1e12
+    try:
+        dominant = dominant_conv_group([(m, f, a.elapsed_time(b), g_) for m, f, a, b, g_ in prof], peak)
+    except Exception as e:                                   # never lose the bench line over the breakdown
+        dominant = {"error": repr(e)}
     images = B * world * args.steps
     value = images / (ms_dev * 1e-3)
     e2e_value = images / (ms_e2e * 1e-3)
@@ -320,7 +346,7 @@ def run_ours(args, rank, world, local_rank):
         "clocks": clk,
         "roofline": {"bound": "tensor", "kernel": "tc_gemm_kernel (all %d conv/FC launches of one step)" % len(prof),
                      "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                     "peak_source": peak_src, "traffic": None,
+                     "peak_source": peak_src, "traffic": None, "dominant": dominant,
                      "conv_ms_per_step": conv_ms, "conv_share_of_step": conv_ms / step_ms,
                      "by_mode": {k: {"tflops": v[0] / (v[1] * 1e-3) / 1e12, "ms": v[1], "launches": v[2]}
                                  for k, v in by_mode.items()},

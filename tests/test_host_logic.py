@@ -236,3 +236,16 @@ def test_label_map_util_reference_vectors(tmp_path):
                    for i in list(range(1, 12)) + [13, 90])
     cats = L.convert_label_map_to_categories(L.load_labelmap(coco), 90)
     assert cats[-1] == {"id": 90, "name": "thing 90"} and len(cats) == 13
+
+
+def test_bench_dominant_conv_group():
+    """bench.py's breakdown of the live per-launch timings: the (mode, geometry) group with the largest summed
+    duration, its algorithmic rate and its fraction of the peak."""
+    import bench
+    geom_a, geom_b = (1280, 7, 7, 512, 512, 3, 1, 7, 7), (1, 38, 63, 1024, 256, 1, 1, 38, 63)
+    recs = [(0, 2e12, 1.0, geom_a)] * 3 + [(0, 1e11, 0.5, geom_b)] * 4 + [(2, 2e12, 0.9, geom_a)] * 3
+    d = bench.dominant_conv_group(recs, 1400.0)
+    assert d["launches"] == 3 and d["kernel"].startswith("tc_gemm_kernel fprop 3x3/1 C512->K512 on 1280x7x7")
+    assert abs(d["achieved"] - 2000.0) < 1e-9 and abs(d["frac"] - 2000.0 / 1400.0) < 1e-12
+    assert abs(d["avg_us"] - 1000.0) < 1e-9 and abs(d["share_of_conv_time"] - 3.0 / 7.7) < 1e-12
+    assert bench.dominant_conv_group([], 1400.0) is None
