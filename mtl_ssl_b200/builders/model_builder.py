@@ -66,6 +66,10 @@ def build_anchor_generator(cfg):
     if which != "grid_anchor_generator":
         raise ValueError("B200 path supports grid_anchor_generator only (got %s)" % which)
     g = cfg.grid_anchor_generator
+    # the fork's paired height/width scales and left-top alignment (grid_anchor_generator.py:39-42, proto fields 9-12)
+    # are used by no shipped config and have no device kernel: refused rather than ignored
+    if g.use_hw_scales or g.align_lefttop:
+        raise ValueError("grid_anchor_generator.use_hw_scales / align_lefttop are not supported on the B200 path")
     return GridAnchorGenerator(scales=[float(s) for s in g.scales],
                                aspect_ratios=[float(a) for a in g.aspect_ratios],
                                base_anchor_size=[g.height, g.width],

@@ -249,3 +249,13 @@ def test_bench_dominant_conv_group():
     assert abs(d["achieved"] - 2000.0) < 1e-9 and abs(d["frac"] - 2000.0 / 1400.0) < 1e-12
     assert abs(d["avg_us"] - 1000.0) < 1e-9 and abs(d["share_of_conv_time"] - 3.0 / 7.7) < 1e-12
     assert bench.dominant_conv_group([], 1400.0) is None
+
+
+def test_builder_refuses_anchor_options_without_a_kernel():
+    """grid_anchor_generator.proto fields 9-12 (the fork's `use_hw_scales` / `align_lefttop`): no shipped config sets
+    them; the builder refuses them instead of generating the default anchors."""
+    from mtl_ssl_b200.builders import model_builder
+    for line in ("use_hw_scales: true", "align_lefttop: true"):
+        cfg = load_config("model12.config", (("grid_anchor_generator {", "grid_anchor_generator {\n        " + line),))
+        with pytest.raises(ValueError, match="use_hw_scales"):
+            model_builder.build(cfg.model, True, device=None)
