@@ -259,3 +259,23 @@ def test_builder_refuses_anchor_options_without_a_kernel():
         cfg = load_config("model12.config", (("grid_anchor_generator {", "grid_anchor_generator {\n        " + line),))
         with pytest.raises(ValueError, match="use_hw_scales"):
             model_builder.build(cfg.model, True, device=None)
+
+
+def test_every_fixture_config_builds_in_training_and_inference_mode():
+    """builders/model_builder.py:68-380 for every config under tests/golden/configs (and, in the build container, all 18
+    of the reference's configs/test/*.config): the host-side model description builds without a device in both modes;
+    max_num_proposals follows fmA:475-477 (second_stage_batch_size when training, first_stage_max_proposals otherwise)."""
+    from mtl_ssl_b200.builders import model_builder
+    from mtl_ssl_b200.protos import text_format
+    paths = [os.path.join(CONFIG_DIR, n) for n in sorted(os.listdir(CONFIG_DIR)) if n.endswith(".config")]
+    ref_dir = "/root/reference/object_detection/configs/test"
+    if os.path.isdir(ref_dir):
+        paths += [os.path.join(ref_dir, n) for n in sorted(os.listdir(ref_dir)) if n.endswith(".config")]
+        assert len(paths) >= 18
+    for path in paths:
+        cfg = text_format.load_pipeline_config(path)
+        fr = cfg.model.faster_rcnn
+        for training in (True, False):
+            m = model_builder.build(cfg.model, training, device=None)
+            assert m.max_num_proposals == (fr.second_stage_batch_size if training else fr.first_stage_max_proposals)
+            assert m.num_classes == fr.num_classes and len(m.param_store.params) > 30
