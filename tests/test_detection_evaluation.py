@@ -319,3 +319,37 @@ def test_detection_metrics_follow_the_pipeline_eval_config(tmp_path):
     assert m["Subset default    mAP@0.5IOU/a"] == 1.0 and "CorLoc/CorLoc@0.5IOU" in m
     with pytest.raises(ValueError):
         evaluator.detection_metrics(lists, cats, metrics_set="open_images_metrics")
+
+
+def test_evaluate_loop_plumbing_with_a_stubbed_inference(monkeypatch, tmp_path):
+    """evaluator.evaluate around a stubbed `run_inference` (the device part is covered by the -m gpu tests): per-image
+    results are collected into lists, image ids come from 'source_id' for the COCO metrics, the PASCAL and the COCO metric
+    sets are both reachable, and the switch for the refiner is passed through."""
+    import json
+    from mtl_ssl_b200 import evaluator
+    from mtl_ssl_b200.data.mscoco import CocoIndex
+    seen = []
+
+    def fake(model, ex, use_refiner=False):
+        seen.append(use_refiner)
+        b = np.asarray(ex["boxes"], np.float32)
+        return dict(detection_boxes=b, detection_scores=np.linspace(0.9, 0.5, len(b)).astype(np.float32),
+                    detection_classes=np.asarray(ex["classes"]), groundtruth_boxes=b,
+                    groundtruth_classes=np.asarray(ex["classes"]))
+
+    monkeypatch.setattr(evaluator, "run_inference", fake)
+    examples = [dict(source_id="11", boxes=[[20.0, 10.0, 70.0, 110.0]], classes=[1]),
+                dict(source_id="12", boxes=[[40.0, 30.0, 190.0, 230.0], [5.0, 5.0, 50.0, 60.0]], classes=[2, 1])]
+    cats = [{"id": 1, "name": "a"}, {"id": 2, "name": "b"}]
+    m = evaluator.evaluate(None, examples, cats)
+    assert m["Subset default    mAP@0.5IOU"] == 1.0 and m["CorLoc/CorLoc@0.5IOU"] == 1.0 and seen == [False, False]
+    anns, k = [], 0
+    for ex in examples:
+        for (y0, x0, y1, x1), c in zip(ex["boxes"], ex["classes"]):
+            k += 1
+            anns.append(dict(id=k, image_id=int(ex["source_id"]), category_id=c, bbox=[x0, y0, x1 - x0, y1 - y0],
+                             area=(x1 - x0) * (y1 - y0), iscrowd=0))
+    coco = CocoIndex({"images": [{"id": 11, "file_name": "a.jpg"}, {"id": 12, "file_name": "b.jpg"}],
+                      "categories": cats, "annotations": anns})
+    m = evaluator.evaluate(None, examples, cats, metrics_set="coco_metrics", eval_ann_filename=coco, use_refiner=True)
+    assert abs(m["COCO_Eval/All/AP"] - 1.0) < 1e-12 and abs(m["COCO_Eval/b/AP"] - 1.0) < 1e-12 and seen[-2:] == [True, True]
