@@ -715,3 +715,27 @@ def test_oracle_inference_graph_with_refiner_runs_on_cpu():
     b, s, c, nd = OP.second_stage_postprocess(out["refined_box_encodings"].numpy(), ref.numpy(), out["prop_abs"],
                                               out["nprop"], (H, W), 0.0, 0.6, 100, 100)
     assert 0 < nd[0] <= 100 and n > 0
+
+
+def test_nms_and_iou_against_torchvision_ops():
+    """A third, independent implementation of the greedy-NMS rule the TF 1.7 kernel follows (suppress iff IoU > thr,
+    candidates by descending score): torchvision.ops.nms / box_iou on the CPU.  oracle/postprocess.py already agrees
+    with the reference's own NumPy NMS (np_reference.npz); this guards the restatement from a second side."""
+    import pytest
+    tv = pytest.importorskip("torchvision.ops")
+    import torch
+    from oracle import boxes as OB, postprocess as OP
+    rng = np.random.default_rng(77)
+    for n, thr in ((400, 0.7), (1500, 0.5), (300, 0.3)):
+        y0, x0 = rng.uniform(0, 500, n), rng.uniform(0, 800, n)
+        b = np.stack([y0, x0, y0 + rng.uniform(5, 250, n), x0 + rng.uniform(5, 300, n)], 1).astype(np.float32)
+        s = rng.random(n).astype(np.float32)
+        xyxy = torch.from_numpy(b[:, [1, 0, 3, 2]].copy())
+        want = tv.nms(xyxy, torch.from_numpy(s), thr).numpy()
+        got = OP.nms_vectorized(b, s, n, thr)
+        iou_tv = tv.box_iou(xyxy, xyxy).numpy()
+        # (a pair whose IoU sits within float rounding of the threshold could legitimately flip: none in these draws)
+        assert np.array_equal(got, want)
+        assert np.array_equal(OP.tf_non_max_suppression(b[:200], s[:200], 50, thr),
+                              tv.nms(xyxy[:200], torch.from_numpy(s[:200]), thr).numpy()[:50])
+        np.testing.assert_allclose(OB.iou(b[:64], b[64:160]), iou_tv[:64, 64:160], rtol=1e-5, atol=1e-7)
