@@ -72,10 +72,23 @@ def sampler_keys_fn(seed, batch_size, num_anchors, num_proposals):
     return fn
 
 
-def train_loop(trainer, loader, num_steps=None, log_every=0, log=print):
-    """Minimal caller of the hot path (the loop of trainer.py:379-429 without checkpoints / summaries): feeds the
-    loader's batches to Trainer.step_pipelined and returns the list of per-step loss dicts."""
+def train_loop(trainer, loader, num_steps=None, log_every=0, log=print, checkpoint_prefix=None, save_every=0):
+    """Minimal caller of the hot path (the loop of trainer.py:379-429 without summaries): feeds the loader's batches to
+    Trainer.step_pipelined and returns the list of per-step loss dicts.  With `checkpoint_prefix` the training state
+    (variables, momentum slots, global_step; utils/checkpoint_io.save_training_checkpoint) is written as
+    `<prefix>-<global_step>` every `save_every` steps and at the end, the role of the Saver in slim.learning.train."""
     out = []
+
+    def save():
+        import torch
+        from ..utils import checkpoint_io
+        r = trainer.flush()                       # the pipelined step in flight belongs to the saved state
+        if r is not None:
+            out.append(r)
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+        checkpoint_io.save_training_checkpoint(trainer, "%s-%d" % (checkpoint_prefix, trainer.global_step))
+
     for step, arrays in enumerate(loader):
         if num_steps is not None and step >= num_steps:
             break
@@ -84,7 +97,11 @@ def train_loop(trainer, loader, num_steps=None, log_every=0, log=print):
             out.append(r)
             if log_every and len(out) % log_every == 0:
                 log("step %d: total_loss %.4f" % (len(out), r["total_loss"]))
+        if checkpoint_prefix and save_every and (step + 1) % save_every == 0:
+            save()
     r = trainer.flush()
     if r is not None:
         out.append(r)
+    if checkpoint_prefix:
+        save()
     return out

@@ -68,3 +68,54 @@ def save_tf_checkpoint(model, prefix, extra=None):
         tensors[k] = np.asarray(v)
     tf_checkpoint.write_checkpoint(prefix, tensors)
     return sorted(tensors)
+
+
+# ----------------------------------------------------------------------------- training state (resume)
+def save_training_checkpoint(trainer, prefix):
+    """Everything `tf.train.Saver` would write for the reference's training graph (trainer.py:431-447): the model
+    variables, the MomentumOptimizer slot of every trainable variable under TF's slot name `<variable>/Momentum`, and
+    `global_step` (int64) -- so that training resumes with the same update sequence."""
+    model = trainer.model
+    extra = {}
+    for p in model.param_store.params:
+        if "/_pad/" in p.name or not p.trainable:
+            continue
+        extra[_tf_name(p.name) + "/Momentum"] = tf_checkpoint.native_to_tf(
+            p.name, p.m.detach().cpu().numpy().astype(np.float32))
+    extra["global_step"] = np.asarray(int(trainer.global_step), np.int64)
+    return save_tf_checkpoint(model, prefix, extra)
+
+
+def restore_training_checkpoint(trainer, prefix):
+    """Inverse of save_training_checkpoint; a checkpoint without optimizer slots (e.g. written by `save_tf_checkpoint`
+    or by a different optimizer) restores the variables and leaves the momenta at zero, as a fresh Saver restore of a
+    fine-tune checkpoint would.  Returns (tensors set, momentum slots set, global_step)."""
+    import torch
+    model = trainer.model
+    n, _ = load_tf_checkpoint(model, prefix, from_detection_checkpoint=True)
+    reader = tf_checkpoint.CheckpointReader(prefix)
+    slots = 0
+    for p in model.param_store.params:
+        key = _tf_name(p.name) + "/Momentum"
+        if "/_pad/" in p.name or not p.trainable or not reader.has_tensor(key):
+            continue
+        v = tf_checkpoint.tf_to_native(p.name, reader.get_tensor(key)).astype(np.float32)
+        if tuple(v.shape) != tuple(p.shape):
+            raise ValueError("%s: checkpoint shape %s, model shape %s" % (key, v.shape, tuple(p.shape)))
+        p.m.copy_(torch.from_numpy(np.ascontiguousarray(v)).to(p.m.device))
+        slots += 1
+    if reader.has_tensor("global_step"):
+        trainer.global_step = int(reader.get_tensor("global_step"))
+    return n, slots, trainer.global_step
+
+
+def latest_checkpoint(directory, basename="model.ckpt"):
+    """`tf.train.latest_checkpoint` by file name: the `<basename>-<step>` prefix with the largest step, or None."""
+    import os
+    import re
+    best, best_step = None, -1
+    for f in os.listdir(directory):
+        m = re.match(re.escape(basename) + r"-(\d+)\.index$", f)
+        if m and int(m.group(1)) > best_step:
+            best, best_step = os.path.join(directory, f[:-len(".index")]), int(m.group(1))
+    return best

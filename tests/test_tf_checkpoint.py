@@ -105,3 +105,98 @@ def test_layout_conversion_and_name_map(tmp_path):
         C.state_dict_from_checkpoint(C.CheckpointReader(prefix), name_map,
                                      shapes={"WindowBoxPredictor/resnet_v1_101/block4/unit_1/bottleneck_v1/conv2/weights":
                                              (32, 3, 3, 8)})
+
+
+def test_training_state_round_trip_with_momentum_slots_and_global_step(tmp_path):
+    """save_training_checkpoint / restore_training_checkpoint: variables + `<variable>/Momentum` slots (TF layouts)
+    + global_step through the tensor-bundle format, on a stand-in parameter store (CPU tensors; the device store has the
+    same attributes and is covered by the -m gpu round trip of the variables)."""
+    import types
+    import torch
+    from mtl_ssl_b200.utils import checkpoint_io as C, tf_checkpoint as T
+
+    def make(seed):
+        g = torch.Generator().manual_seed(seed)
+        specs = [("Scope/conv/weights", (8, 3, 3, 4), True), ("Scope/conv/biases", (8,), True),
+                 ("Scope/fc/weights", (5, 16), True), ("Scope/frozen/weights", (4, 1, 1, 4), False),
+                 ("Scope/_pad/x", (3,), True)]
+        params = [types.SimpleNamespace(name=n, shape=s, trainable=t, w=torch.randn(s, generator=g),
+                                        m=torch.randn(s, generator=g)) for n, s, t in specs]
+        st = types.SimpleNamespace(params=params, bns=[])
+        st.state_dict = lambda: {p.name: p.w.clone() for p in params}
+
+        def load(sd, strict=True):
+            for p in params:
+                if p.name in sd:
+                    p.w.copy_(sd[p.name].reshape(p.shape))
+        st.load_state_dict = load
+        model = types.SimpleNamespace(param_store=st)
+        return types.SimpleNamespace(model=model, global_step=0), params
+
+    tr_a, pa = make(1)
+    tr_a.global_step = 12345
+    names = C.save_training_checkpoint(tr_a, str(tmp_path / "model.ckpt-12345"))
+    assert "global_step" in names and "Scope/conv/weights/Momentum" in names and "Scope/fc/weights/Momentum" in names
+    assert "Scope/frozen/weights/Momentum" not in names and not any("_pad" in n for n in names)
+    r = T.CheckpointReader(str(tmp_path / "model.ckpt-12345"))
+    assert r.get_variable_to_shape_map()["Scope/conv/weights/Momentum"] == [3, 3, 4, 8]        # HWIO like the variable
+    assert r.get_variable_to_shape_map()["Scope/fc/weights/Momentum"] == [16, 5] and int(r.get_tensor("global_step")) == 12345
+    tr_b, pb = make(2)
+    n, slots, step = C.restore_training_checkpoint(tr_b, str(tmp_path / "model.ckpt-12345"))
+    assert (n, slots, step) == (4, 3, 12345) and tr_b.global_step == 12345
+    for a, b in zip(pa, pb):
+        if "_pad" in a.name:
+            continue
+        assert torch.equal(a.w, b.w)
+        assert torch.equal(a.m, b.m) == a.trainable
+    # a variables-only checkpoint leaves the momenta and the step alone
+    C.save_tf_checkpoint(tr_a.model, str(tmp_path / "weights_only"))
+    tr_c, pc = make(3)
+    before = [p.m.clone() for p in pc]
+    assert C.restore_training_checkpoint(tr_c, str(tmp_path / "weights_only"))[1:] == (0, 0)
+    assert all(torch.equal(x, p.m) for x, p in zip(before, pc))
+
+
+def test_train_loop_writes_and_resumes_checkpoints(tmp_path):
+    """data/loader.train_loop with `checkpoint_prefix`: `<prefix>-<global_step>` every `save_every` steps and at the
+    end (the Saver's role in slim.learning.train), `latest_checkpoint` picks the newest, a second trainer resumes from it."""
+    import types
+    import torch
+    from mtl_ssl_b200.data import loader
+    from mtl_ssl_b200.utils import checkpoint_io as C
+
+    class FakeTrainer(object):
+        def __init__(self):
+            self.w, self.m = torch.zeros(4), torch.zeros(4)
+            p = types.SimpleNamespace(name="S/fc/biases", shape=(4,), trainable=True, w=self.w, m=self.m)
+            st = types.SimpleNamespace(params=[p], bns=[])
+            st.state_dict = lambda: {"S/fc/biases": self.w.clone()}
+            st.load_state_dict = lambda sd, strict=True: self.w.copy_(sd["S/fc/biases"])
+            self.model = types.SimpleNamespace(param_store=st)
+            self.global_step, self._pending = 0, None
+
+        def step_pipelined(self, arrays):            # losses come back one call later, like Trainer.step_pipelined
+            prev, self._pending = self._pending, {"total_loss": float(arrays)}
+            self.global_step += 1
+            self.m.mul_(0.9).add_(float(arrays))
+            self.w.sub_(0.1 * self.m)
+            return prev
+
+        def flush(self):
+            prev, self._pending = self._pending, None
+            return prev
+
+    tr = FakeTrainer()
+    prefix = str(tmp_path / "model.ckpt")
+    out = loader.train_loop(tr, iter([1.0, 2.0, 3.0, 4.0, 5.0]), checkpoint_prefix=prefix, save_every=2)
+    assert [r["total_loss"] for r in out] == [1.0, 2.0, 3.0, 4.0, 5.0]
+    steps = sorted(int(f.split("-")[-1][:-len(".index")]) for f in os.listdir(str(tmp_path)) if f.endswith(".index"))
+    assert steps == [2, 4, 5] and C.latest_checkpoint(str(tmp_path)) == prefix + "-5"
+    assert C.latest_checkpoint(str(tmp_path), "other") is None
+    tr2 = FakeTrainer()
+    assert C.restore_training_checkpoint(tr2, C.latest_checkpoint(str(tmp_path))) == (1, 1, 5)
+    assert torch.equal(tr2.w, tr.w) and torch.equal(tr2.m, tr.m)
+    # resumed and uninterrupted runs end in the same state
+    loader.train_loop(tr2, iter([6.0, 7.0]))
+    loader.train_loop(tr, iter([6.0, 7.0]))
+    assert torch.equal(tr2.w, tr.w) and tr2.global_step == tr.global_step == 7
