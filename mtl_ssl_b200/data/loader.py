@@ -72,36 +72,64 @@ def sampler_keys_fn(seed, batch_size, num_anchors, num_proposals):
     return fn
 
 
-def train_loop(trainer, loader, num_steps=None, log_every=0, log=print, checkpoint_prefix=None, save_every=0):
-    """Minimal caller of the hot path (the loop of trainer.py:379-429 without summaries): feeds the loader's batches to
-    Trainer.step_pipelined and returns the list of per-step loss dicts.  With `checkpoint_prefix` the training state
-    (variables, momentum slots, global_step; utils/checkpoint_io.save_training_checkpoint) is written as
-    `<prefix>-<global_step>` every `save_every` steps and at the end, the role of the Saver in slim.learning.train."""
+def train_loop(trainer, loader, num_steps=None, log_every=0, log=print, checkpoint_prefix=None, save_every=0,
+               check_numerics=True, jsonl_path=None, images_per_step=None):
+    """Minimal caller of the hot path (the loop of trainer.py:379-429 / slim.learning.train without TF summaries): feeds
+    the loader's batches to Trainer.step_pipelined and returns the list of per-step loss dicts.
+    * `checkpoint_prefix`: the training state (variables, momentum slots, global_step;
+      utils/checkpoint_io.save_training_checkpoint) is written as `<prefix>-<global_step>` every `save_every` steps and at
+      the end, the role of the Saver in slim.learning.train;
+    * `check_numerics`: a non-finite loss raises FloatingPointError('LossTensor is inf or nan.'), the
+      `tf.check_numerics` of trainer.py:207-209, on the loss vector the step already copied to the host;
+    * `jsonl_path`: one JSON line per step with the reference's loss keys, `sec/batch` and `instances/sec`
+      (the console line of learning.py:509-519; `images_per_step` defaults to the trainer's global batch)."""
+    import json
+    import math
+    import time
     out = []
+    if images_per_step is None:
+        images_per_step = getattr(trainer, "B", 1) * getattr(trainer, "world_size", 1)
+    jf = open(jsonl_path, "a") if jsonl_path else None
+    last = [time.perf_counter()]
+
+    def record(r):
+        now = time.perf_counter()
+        dt, last[0] = now - last[0], now
+        if check_numerics and not all(math.isfinite(float(v)) for v in r.values()):
+            raise FloatingPointError("LossTensor is inf or nan. (step %d: %s)" % (len(out) + 1, r))
+        out.append(r)
+        if jf is not None:
+            row = dict(r, step=len(out), **{"sec/batch": dt, "instances/sec": images_per_step / dt if dt > 0 else None})
+            jf.write(json.dumps(row) + "\n")
+            jf.flush()
+        if log_every and len(out) % log_every == 0:
+            log("step %d: total_loss %.4f (%.3f sec/batch)" % (len(out), r["total_loss"], dt))
 
     def save():
         import torch
         from ..utils import checkpoint_io
         r = trainer.flush()                       # the pipelined step in flight belongs to the saved state
         if r is not None:
-            out.append(r)
+            record(r)
         if torch.cuda.is_available():
             torch.cuda.synchronize()
         checkpoint_io.save_training_checkpoint(trainer, "%s-%d" % (checkpoint_prefix, trainer.global_step))
 
-    for step, arrays in enumerate(loader):
-        if num_steps is not None and step >= num_steps:
-            break
-        r = trainer.step_pipelined(arrays)
+    try:
+        for step, arrays in enumerate(loader):
+            if num_steps is not None and step >= num_steps:
+                break
+            r = trainer.step_pipelined(arrays)
+            if r is not None:
+                record(r)
+            if checkpoint_prefix and save_every and (step + 1) % save_every == 0:
+                save()
+        r = trainer.flush()
         if r is not None:
-            out.append(r)
-            if log_every and len(out) % log_every == 0:
-                log("step %d: total_loss %.4f" % (len(out), r["total_loss"]))
-        if checkpoint_prefix and save_every and (step + 1) % save_every == 0:
+            record(r)
+        if checkpoint_prefix:
             save()
-    r = trainer.flush()
-    if r is not None:
-        out.append(r)
-    if checkpoint_prefix:
-        save()
+    finally:
+        if jf is not None:
+            jf.close()
     return out

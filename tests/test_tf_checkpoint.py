@@ -200,3 +200,33 @@ def test_train_loop_writes_and_resumes_checkpoints(tmp_path):
     loader.train_loop(tr2, iter([6.0, 7.0]))
     loader.train_loop(tr, iter([6.0, 7.0]))
     assert torch.equal(tr2.w, tr.w) and tr2.global_step == tr.global_step == 7
+
+
+def test_train_loop_numerics_check_and_jsonl_log(tmp_path):
+    """train_loop's failure detection (`tf.check_numerics` on the losses, trainer.py:207-209) and per-step JSONL log
+    (loss keys + sec/batch + instances/sec, learning.py:509-519)."""
+    import json
+    from mtl_ssl_b200.data import loader
+
+    class T(object):
+        B, world_size, global_step = 2, 4, 0
+
+        def __init__(self):
+            self._p = None
+
+        def step_pipelined(self, a):
+            prev, self._p = self._p, {"first_stage_objectness_loss": a, "total_loss": a + 1.0}
+            return prev
+
+        def flush(self):
+            prev, self._p = self._p, None
+            return prev
+
+    path = str(tmp_path / "train.jsonl")
+    out = loader.train_loop(T(), iter([0.5, 0.25, 0.125]), jsonl_path=path)
+    rows = [json.loads(l) for l in open(path)]
+    assert [r["step"] for r in rows] == [1, 2, 3] and [r["total_loss"] for r in rows] == [1.5, 1.25, 1.125] and len(out) == 3
+    assert all(r["sec/batch"] >= 0 and (r["instances/sec"] is None or r["instances/sec"] > 0) for r in rows)
+    with pytest.raises(FloatingPointError, match="LossTensor is inf or nan"):
+        loader.train_loop(T(), iter([0.5, float("nan"), 0.1]))
+    assert len(loader.train_loop(T(), iter([0.5, float("inf")]), check_numerics=False)) == 2
