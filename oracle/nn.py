@@ -4,7 +4,6 @@ TensorFlow-1.7 kernels and reference loss classes used on the hot path.
 torch is used here only as a CPU fp32 array library with autograd, so that the same
 restatement also yields reference gradients.  Paths relative to /root/reference/.
 """
-import math
 
 import numpy as np
 import torch

@@ -2,7 +2,6 @@
 
 The variable table (names, shapes, initialisers, L2 weights) is read from the host-side model
 description built with device=None (no CUDA involved); values are drawn here on the CPU."""
-import numpy as np
 import torch
 
 

@@ -1,5 +1,5 @@
 """Developer tool (GPU): per-shape table of the tcgen05 conv launches of one full-size training step."""
-import os, sys, json
+import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch

@@ -1,6 +1,6 @@
 """Developer tool (GPU): sweep tile width / split-K / pipeline depth of the conv engine on the layer shapes of
 the ResNet-101 step.  usage: sweep_conv.py [quick]"""
-import os, sys, itertools
+import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
