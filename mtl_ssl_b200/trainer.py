@@ -37,8 +37,8 @@ def pack_groundtruth(examples, num_classes, height, width, gmax):
             raise ValueError("maximum box coordinate value is larger than 1.01")
         out["num_gt"][b] = g
         out["gt"][b, :g] = bx * scale
-        oh = np.asarray(ex["groundtruth_classes"], np.float32).reshape(g, -1)
-        if g:
+        if g:                                    # (an image without boxes has nothing to check or copy)
+            oh = np.asarray(ex["groundtruth_classes"], np.float32).reshape(g, -1)
             if not np.all((oh.sum(1) == 1) & (oh.max(1) == 1)):
                 raise ValueError("groundtruth classes must be one-hot on the B200 path")
             out["gt_cls"][b, :g] = oh.argmax(1) + 1

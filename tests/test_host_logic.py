@@ -279,3 +279,63 @@ def test_every_fixture_config_builds_in_training_and_inference_mode():
             m = model_builder.build(cfg.model, training, device=None)
             assert m.max_num_proposals == (fr.second_stage_batch_size if training else fr.first_stage_max_proposals)
             assert m.num_classes == fr.num_classes and len(m.param_store.params) > 30
+
+
+def test_shape_bucket_trainer_bookkeeping():
+    """shape_buckets.ShapeBucketTrainer with stand-in trainers (the device side is tests/test_gpu_zz_shape_buckets.py):
+    one trainer + workspace per image shape installed in the model before every call, a shared global_step, the losses
+    of the previous call handed back in call order across a shape switch, least-recently-used eviction."""
+    import types
+    from mtl_ssl_b200.shape_buckets import ShapeBucketTrainer
+    log = []
+
+    class FakeWs(object):
+        def __init__(self, device):
+            self.device = device
+
+    class FakeTrainer(object):
+        def __init__(self, model, train_config, H, W, B, gmax=64):
+            self.model, self.hw, self.global_step, self._pending, self.ws_at_build = model, (H, W), 0, None, model._ws
+
+        def host_arrays(self, examples, keys):
+            return {"image": np.stack([e["image"] for e in examples]), "keys1": keys[0], "keys2": keys[1]}
+
+        def step_pipelined(self, arrays):
+            assert self.model._ws is self.ws_at_build                     # its own workspace is installed
+            log.append((self.hw, self.global_step))
+            prev, self._pending = self._pending, {"total_loss": float(self.global_step)}
+            self.global_step += 1
+            return prev
+
+        def flush(self):
+            prev, self._pending = self._pending, None
+            return prev
+
+    model = types.SimpleNamespace(device="cpu", _ws=None, num_classes=3)
+    bt = ShapeBucketTrainer(model, None, batch_size=1, max_buckets=2, trainer_cls=FakeTrainer, workspace_cls=FakeWs)
+    def batch(h, w):
+        ex = [dict(image=np.zeros((h, w, 3), np.float32), groundtruth_boxes=np.zeros((0, 4), np.float32),
+                   groundtruth_classes=np.zeros((0, 3), np.float32))]
+        return bt.host_arrays(ex, (np.zeros((1, 5), np.float32), np.zeros((1, 4), np.float32)))
+    a = batch(32, 48)
+    assert a.hw == (32, 48) and a["image"].shape == (1, 32, 48, 3) and a["gt"].shape == (1, 64, 4)
+    seq = [(32, 48), (32, 48), (40, 40), (32, 48), (24, 64), (40, 40)]
+    got = [bt.step_pipelined(batch(h, w)) for h, w in seq] + [bt.flush()]
+    assert got[0] is None and [r["total_loss"] for r in got[1:]] == [0.0, 1.0, 2.0, 3.0, 4.0, 5.0]      # call order kept
+    assert log == [(hw, i) for i, hw in enumerate(seq)] and bt.global_step == 6
+    # (40,40) was least recently used when (24,64) arrived: evicted, rebuilt on its next use -> (32,48) evicted then
+    assert bt.evictions == 2 and list(bt.buckets) == [(24, 64), (40, 40)]
+    assert bt.flush() is None
+    with pytest.raises(ValueError, match="different sizes"):
+        bt.host_arrays([dict(image=np.zeros((8, 8, 3))), dict(image=np.zeros((8, 9, 3)))], (None, None))
+
+
+def test_pack_groundtruth_accepts_images_without_boxes():
+    """COCO holds images without annotations: packing must give num_gt = 0, not fail."""
+    from mtl_ssl_b200.trainer import pack_groundtruth
+    ex = [dict(groundtruth_boxes=np.zeros((0, 4), np.float32), groundtruth_classes=np.zeros((0, 3), np.float32)),
+          dict(groundtruth_boxes=np.array([[0.1, 0.2, 0.5, 0.6]], np.float32),
+               groundtruth_classes=np.array([[0, 1, 0]], np.float32))]
+    out = pack_groundtruth(ex, 3, 100, 200, 4)
+    assert out["num_gt"].tolist() == [0, 1] and out["gt_cls"][1, 0] == 2 and not out["gt"][0].any()
+    np.testing.assert_allclose(out["gt"][1, 0], [10, 40, 50, 120], rtol=1e-6)
