@@ -281,8 +281,8 @@ class FasterRCNNMetaArch(model.DetectionModel):
             ng[b] = g
             # to_absolute_coordinates -> scale(y_scale=H, x_scale=W) in float32 (blo:73-99)
             gt[b, :g] = bx * np.array([H, W, H, W], np.float32)
-            oh = _np(classes_list[b]).astype(np.float32).reshape(g, -1)
-            if g:
+            if g:                                # (an image without boxes has no classes to check)
+                oh = _np(classes_list[b]).astype(np.float32).reshape(g, -1)
                 if not np.all((oh.sum(1) == 1) & (oh.max(1) == 1)):
                     raise ValueError("groundtruth classes must be one-hot on the B200 path (trap T12)")
                 gc[b, :g] = oh.argmax(1) + 1
