@@ -53,10 +53,14 @@ def build_image_resizer(cfg):
         r = cfg.keep_aspect_ratio_resizer
         if not r.min_dimension <= r.max_dimension:
             raise ValueError("min_dimension > max_dimension")
-        return lambda img: preprocessor.resize_to_range(img, r.min_dimension, r.max_dimension)
+        fn = lambda img: preprocessor.resize_to_range(img, r.min_dimension, r.max_dimension)
+        fn.static_size = lambda h, w: tuple(preprocessor._compute_new_static_size(h, w, r.min_dimension, r.max_dimension))
+        return fn
     if which == "fixed_shape_resizer":
         r = cfg.fixed_shape_resizer
-        return lambda img: preprocessor.resize_image(img, r.height, r.width)
+        fn = lambda img: preprocessor.resize_image(img, r.height, r.width)
+        fn.static_size = lambda h, w: (int(r.height), int(r.width))
+        return fn
     raise ValueError("Invalid image resizer option.")
 
 

@@ -104,6 +104,11 @@ class Trainer(object):
                  clip_norm=10.0):
         self.model = model
         self.H, self.W, self.B = height, width, batch_size
+        # the ground truth is packed in pixels of the INPUT size: the model's image resizer must leave it unchanged
+        static_size = getattr(getattr(model, "_image_resizer_fn", None), "static_size", None)
+        if static_size is not None and tuple(static_size(height, width)) != (height, width):
+            raise ValueError("Trainer needs images at their resized size: the config's image resizer maps %dx%d to "
+                             "%dx%d" % ((height, width) + tuple(static_size(height, width))))
         self.gmax = gmax
         self.world_size = world_size
         self.pg = process_group

@@ -1,0 +1,106 @@
+"""Host-orchestration dry run WITHOUT a GPU: every C-ABI call keeps its argument-count / type marshalling
+(`ops.call` against the signatures parsed from include/mtlssl.h, `mtl_conv_args` filling) but the library entry point
+is replaced by a stub that returns 0, CUDA streams / events by inert stand-ins, and tensors live on the CPU.  Kernel
+outputs are therefore meaningless (zeros); what a dry run checks is the Python side of the hot path -- buffer shapes,
+dictionary keys, call sequences, lane / stream bookkeeping -- for code paths that could not be exercised on a device yet.
+Test infrastructure only (the product path still fails loudly without the CUDA library, see
+test_product_path_fails_loudly_without_cuda)."""
+import contextlib
+
+import torch
+
+
+class FakeStream(object):
+    cuda_stream = 0
+
+    def wait_event(self, e):
+        pass
+
+    def wait_stream(self, s):
+        pass
+
+    def synchronize(self):
+        pass
+
+    def record_event(self, e=None):
+        return e or FakeEvent()
+
+
+class FakeEvent(object):
+    def __init__(self, *a, **k):
+        pass
+
+    def record(self, stream=None):
+        pass
+
+    def wait(self, stream=None):
+        pass
+
+    def synchronize(self):
+        pass
+
+    def query(self):
+        return True
+
+    def elapsed_time(self, other):
+        return 0.0
+
+
+class _FakeLib(object):
+    """Any symbol -> a function returning 0; the conv workspace query returns 0 bytes."""
+
+    def __init__(self, log):
+        self._log = log
+
+    _CONST = {"mtl_opt_chunk_size": 8192, "mtl_device_sm_count": 148, "mtl_abi_version": 1, "mtl_launch_count": 0}
+
+    def __getattr__(self, name):
+        def fn(*a):
+            if name in self._CONST:
+                return self._CONST[name]
+            self._log.append(name)
+            return 0
+        return fn
+
+
+@contextlib.contextmanager
+def _no_stream(s):
+    yield
+
+
+def install(monkeypatch):
+    """Returns the list that records the name of every C-ABI entry point 'launched'."""
+    from mtl_ssl_b200 import _lib, ops, ops_conv
+    log = []
+    fake = _FakeLib(log)
+    cur = FakeStream()
+    monkeypatch.setattr(torch.cuda, "Stream", lambda *a, **k: FakeStream())
+    monkeypatch.setattr(torch.cuda, "Event", FakeEvent)
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda *a, **k: cur)
+    monkeypatch.setattr(torch.cuda, "stream", _no_stream)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self, *a, **k: self)
+    monkeypatch.setattr(_lib, "lib", lambda: fake)
+    for mod in (ops, ops_conv):
+        if hasattr(mod, "lib"):
+            monkeypatch.setattr(mod, "lib", lambda: fake)
+    monkeypatch.setattr(ops, "_bound", {})
+
+    def _fn(name):
+        def f(*cargs):
+            log.append(name)
+            return 0
+        return f
+    monkeypatch.setattr(ops, "_fn", _fn)
+    # the one kernel whose OUTPUT the host reads back to size later buffers: keep every anchor
+    real_call = ops.call
+
+    def call(name, *args, **kw):
+        real_call(name, *args, **kw)
+        if name == "mtl_prune_outside_window":
+            allb, n, keep, kept, num = args[0], args[1], args[6], args[7], args[8]
+            keep.copy_(torch.arange(n, dtype=keep.dtype))
+            kept.copy_(allb)
+            num.fill_(n)
+    monkeypatch.setattr(ops, "call", call)
+    return log

@@ -1,0 +1,114 @@
+"""Host orchestration of the hot path executed WITHOUT a GPU (tests/dryrun.py): every C-ABI call is marshalled against
+the signatures of include/mtlssl.h, the library entry point is a stub, tensors live on the CPU.  Checks the Python side
+-- buffer shapes, dictionary keys, call sequences, stream bookkeeping -- of paths that the -m gpu tests cover numerically,
+and of the two paths written after this round's GPU budget was spent (refiner at inference time, shape buckets)."""
+import numpy as np
+import pytest
+import torch
+
+import dryrun
+from helpers import load_config
+
+SMALL = (("type: 'faster_rcnn_resnet101'", "type: 'faster_rcnn_resnet50'"),
+         ("min_dimension: 600", "min_dimension: 224"), ("max_dimension: 1024", "max_dimension: 320"),
+         ("first_stage_max_proposals: 300", "first_stage_max_proposals: 100"),
+         ("second_stage_batch_size: 256", "second_stage_batch_size: 32"))
+
+
+def _batches(model, trainer, shapes, K=20, M=100):
+    from mtl_ssl_b200.data import synthetic
+    for i, hw in enumerate(shapes):
+        ex = synthetic.make_batch(60 + i, 1, hw[0], hw[1], K, max_boxes=4, num_windows=16)
+        ky = synthetic.make_sampler_keys(70 + i, 1, model.num_kept_anchors((1, hw[0], hw[1], 3)), M)
+        yield trainer.host_arrays(ex, ky)
+
+
+@pytest.mark.parametrize("name", ["model12.config", "model42.config", "model52.config", "model62.config"])
+def test_training_step_call_sequence(monkeypatch, name):
+    """One eager training step per architecture family: Faster R-CNN ResNet, R-FCN, MobileNet, Inception-ResNet-v2."""
+    from mtl_ssl_b200.builders import model_builder
+    from mtl_ssl_b200.trainer import Trainer
+    log = dryrun.install(monkeypatch)
+    cfg = load_config(name, SMALL[1:] if name[5] in "56" else SMALL)
+    model = model_builder.build(cfg.model, True, device="cpu", seed=0)
+    tr = Trainer(model, cfg.train_config, 224, 320, 1, gmax=8, use_cuda_graph=False)
+    (arrays,) = list(_batches(model, tr, [(224, 320)], cfg.model.faster_rcnn.num_classes))
+    del log[:]
+    losses = tr.step(arrays)
+    assert set(losses) >= {"first_stage_localization_loss", "refined_classification_loss", "total_loss"}
+    launched = set(log)
+    assert {"mtl_conv_tc", "mtl_rpn_decode", "mtl_nms", "mtl_iou_match", "mtl_balanced_sample", "mtl_rpn_loss",
+            "mtl_box_classifier_loss", "mtl_opt_stats", "mtl_opt_apply"} <= launched or \
+        {"mtl_opt_stats_range", "mtl_opt_apply"} <= launched
+    assert ("mtl_psroi_fwd" in launched) == (name == "model42.config")
+    assert ("mtl_dwconv3x3_fwd" in launched) == (name == "model52.config")
+    assert tr.global_step == 1 and log.count("mtl_conv_tc") > 50
+
+
+def test_inference_with_refiner_call_sequence(monkeypatch):
+    """evaluator.run_inference(use_refiner=True): closeness head, 5 x P expanded windows through the window tail, refiner
+    concat + FC, then `postprocess` (which reads the refined logits, fmA:1040-1043)."""
+    from mtl_ssl_b200 import evaluator
+    from mtl_ssl_b200.builders import model_builder
+    from mtl_ssl_b200.data import synthetic
+    log = dryrun.install(monkeypatch)
+    cfg = load_config("model12.config", SMALL)
+    model = model_builder.build(cfg.model, False, device="cpu", seed=0)
+    ex = synthetic.make_batch(7, 1, 224, 320, 20, max_boxes=4, num_windows=16)
+    del log[:]
+    r0 = evaluator.run_inference(model, ex[0])
+    plain = list(log)
+    del log[:]
+    r1 = evaluator.run_inference(model, ex[0], use_refiner=True)
+    assert "mtl_expand_windows" not in plain and "mtl_refine_concat" not in plain
+    for k in ("mtl_expand_windows", "mtl_refine_concat", "mtl_fc_fwd", "mtl_detection_decode", "mtl_detection_gather"):
+        assert k in log, k
+    assert log.index("mtl_refine_concat") < log.index("mtl_detection_decode")        # refined logits feed postprocess
+    assert log.count("mtl_crop_and_resize_fwd") == plain.count("mtl_crop_and_resize_fwd") + 1     # the 5 x P windows
+    assert r1["closeness_dt"].shape == (100, 21) and r1["window_classes_dt"].shape == (16, 21)
+    assert set(r0) == set(r1)
+
+
+def test_mixed_shape_training_loop_with_checkpoints(monkeypatch, tmp_path):
+    """shape_buckets.ShapeBucketTrainer under data.loader.train_loop: two image shapes alternate over one model, the
+    training state is saved and restored through the TF checkpoint format (real ParamStore, CPU tensors)."""
+    from mtl_ssl_b200.builders import model_builder
+    from mtl_ssl_b200.data import loader
+    from mtl_ssl_b200.shape_buckets import ShapeBucketTrainer
+    from mtl_ssl_b200.trainer import Trainer
+    from mtl_ssl_b200.utils import checkpoint_io
+    dryrun.install(monkeypatch)
+    cfg = load_config("model12.config", SMALL)
+    model = model_builder.build(cfg.model, True, device="cpu", seed=0)
+    bt = ShapeBucketTrainer(model, cfg.train_config, batch_size=1, max_buckets=2, use_cuda_graph=False, gmax=8)
+    shapes = [(224, 320), (224, 288), (224, 320), (320, 224)]
+    prefix = str(tmp_path / "model.ckpt")
+    out = loader.train_loop(bt, _batches(model, bt, shapes), checkpoint_prefix=prefix, save_every=2)
+    assert len(out) == 4 and bt.global_step == 4 and bt.evictions == 1 and list(bt.buckets) == [(224, 320), (320, 224)]
+    assert checkpoint_io.latest_checkpoint(str(tmp_path)) == prefix + "-4"
+    model.param_store.m.fill_(0.25)
+    model2 = model_builder.build(cfg.model, True, device="cpu", seed=1)
+    tr2 = Trainer(model2, cfg.train_config, 224, 320, 1, gmax=8, use_cuda_graph=False)
+    checkpoint_io.save_training_checkpoint(bt, prefix + "-5")
+    n, slots, step = checkpoint_io.restore_training_checkpoint(tr2, prefix + "-5")
+    assert step == 4 and slots == sum(1 for p in model.param_store.params if p.trainable and "/_pad/" not in p.name)
+    assert torch.equal(model2.param_store.w, model.param_store.w)
+    trainable = [p for p in model2.param_store.params if p.trainable and "/_pad/" not in p.name]
+    assert all(bool((p.m == 0.25).all()) for p in trainable)
+    # a shape the config's resizer would change is refused with a clear message (ground truth is packed per input size)
+    with pytest.raises(ValueError, match="resized size"):
+        Trainer(model, cfg.train_config, 256, 288, 1)
+
+
+def test_evaluation_loop_call_sequence(monkeypatch):
+    """evaluator.evaluate on the inference-mode graph: metrics assemble from (empty) detections without a device."""
+    from mtl_ssl_b200 import evaluator
+    from mtl_ssl_b200.builders import model_builder
+    from mtl_ssl_b200.data import synthetic
+    dryrun.install(monkeypatch)
+    cfg = load_config("model12.config", SMALL)
+    model = model_builder.build(cfg.model, False, device="cpu", seed=0)
+    examples = synthetic.make_batch(31, 2, 224, 320, 20, max_boxes=4, num_windows=16)
+    cats = [{"id": i + 1, "name": "class%d" % (i + 1)} for i in range(20)]
+    m = evaluator.evaluate(model, examples, cats, use_refiner=True)
+    assert "Subset default    mAP@0.5IOU" in m and "mtl/window_map" in m and "mtl/edgemask_ap" in m
