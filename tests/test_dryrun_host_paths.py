@@ -112,3 +112,35 @@ def test_evaluation_loop_call_sequence(monkeypatch):
     cats = [{"id": i + 1, "name": "class%d" % (i + 1)} for i in range(20)]
     m = evaluator.evaluate(model, examples, cats, use_refiner=True)
     assert "Subset default    mAP@0.5IOU" in m and "mtl/window_map" in m and "mtl/edgemask_ap" in m
+
+
+def test_bench_json_line_contract(monkeypatch, capsys):
+    """bench.py `run_ours` end to end in dry-run mode (eager, one replica): the ONE JSON line carries every key of the
+    driver's contract plus `roofline` (with the dominant launch group) -- values are meaningless here, the point is that
+    the script reaches its print statement whatever was edited last."""
+    import json
+    import types
+    import bench
+    import mtl_ssl_b200.builders.model_builder as mb
+    from mtl_ssl_b200 import ops
+    log = dryrun.install(monkeypatch)
+    monkeypatch.setattr(torch.cuda, "set_device", lambda *a, **k: None)
+    monkeypatch.setattr(torch.cuda, "_sleep", lambda *a, **k: None, raising=False)
+    monkeypatch.setattr(dryrun.FakeEvent, "elapsed_time", lambda self, other: 1.0)       # 1 ms per event pair
+    real_build = mb.build
+    monkeypatch.setattr(mb, "build", lambda cfg, tr, device=None, seed=0: real_build(cfg, tr, device="cpu", seed=seed))
+    monkeypatch.setattr(ops, "launch_count", lambda: len(log))
+    args = types.SimpleNamespace(steps=2, warmup=1, batch_per_gpu=0, no_graph=True, skip_cpu=True, gpus=1, impl="ours")
+    bench.run_ours(args, 0, 1, 0)
+    line = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline"):
+        assert k in line, k
+    assert line["metric"] == "images/sec" and line["n_gpus"] == 1 and line["steps"] == 2 and line["warmup"] >= 3
+    assert line["config"]["workload"].startswith("Faster R-CNN ResNet-101") and line["vs_baseline"] is None
+    assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(line["e2e"])
+    assert line["e2e"]["h2d_bytes_per_step"] > 7e6
+    r = line["roofline"]
+    assert {"bound", "achieved", "peak", "unit", "frac", "traffic", "dominant"} <= set(r) and r["bound"] == "tensor"
+    assert r["dominant"]["kernel"].startswith("tc_gemm_kernel ") and r["dominant"]["launches"] >= 1
+    assert 380 <= line["gpu_launches_per_step"] <= 480            # 431 on the device
