@@ -144,3 +144,67 @@ def test_bench_json_line_contract(monkeypatch, capsys):
     assert {"bound", "achieved", "peak", "unit", "frac", "traffic", "dominant"} <= set(r) and r["bound"] == "tensor"
     assert r["dominant"]["kernel"].startswith("tc_gemm_kernel ") and r["dominant"]["launches"] >= 1
     assert 380 <= line["gpu_launches_per_step"] <= 480            # 431 on the device
+
+
+_DP_WORKER = r"""
+import os, sys
+sys.path.insert(0, %(root)r); sys.path.insert(0, os.path.join(%(root)r, "tests"))
+import pytest, torch, torch.distributed as dist
+import dryrun
+from helpers import load_config
+mp = pytest.MonkeyPatch()
+dryrun.install(mp)
+dist.init_process_group("gloo", rank=int(os.environ["RANK"]), world_size=2)
+rank = dist.get_rank()
+from mtl_ssl_b200.builders import model_builder
+from mtl_ssl_b200.data import synthetic
+from mtl_ssl_b200.trainer import Trainer
+SMALL = %(small)r
+cfg = load_config("model12.config", SMALL)
+model = model_builder.build(cfg.model, True, device="cpu", seed=0)
+st = model.param_store
+for overlap in (True, False):
+    tr = Trainer(model, cfg.train_config, 224, 320, 1, gmax=8, use_cuda_graph=False, world_size=2)
+    tr.overlap_optimizer = overlap
+    # the stubbed kernels leave the gradient arena untouched: plant rank-specific values where the two halves of the
+    # backward pass would have written them, and look at what the exchange made of them
+    fb, bt = tr._forward_backward, tr._backward_trunk
+    heads, trunk = model.gradient_buckets()
+    def fb2(image, prefix=None):
+        r = fb(image, prefix)
+        st.g.fill_(float(rank + 1))
+        trunk.fill_(-1.0)                      # not final yet: must not be exchanged with the head bucket
+        return r
+    def bt2():
+        bt()
+        trunk.fill_(float(10 * (rank + 1)))
+    tr._forward_backward, tr._backward_trunk = fb2, bt2
+    ex = synthetic.make_batch(60 + rank, 1, 224, 320, 20, max_boxes=4, num_windows=16)
+    ky = synthetic.make_sampler_keys(70 + rank, 1, model.num_kept_anchors((1, 224, 320, 3)), 100)
+    tr.step(tr.host_arrays(ex, ky))
+    assert heads.numel() + trunk.numel() <= st.total and heads.numel() > 0 and trunk.numel() > 0
+    assert bool((heads == 3.0).all()), heads.unique()            # 1 + 2: summed over the two replicas, once
+    assert bool((trunk == 30.0).all()), trunk.unique()           # 10 + 20
+    dead = st.g[heads.numel() + trunk.numel():]
+    assert dead.numel() > 0 and bool((dead == float(rank + 1)).all())      # the dead block4 copy is not exchanged (T4)
+    st.g.zero_()
+dist.destroy_process_group()
+print("rank", rank, "ok")
+"""
+
+
+def test_two_replica_step_exchanges_each_gradient_bucket_once_gloo(tmp_path):
+    """The N > 1 step body of Trainer (head bucket all-reduced under the trunk backward, trunk bucket after it, the
+    dead stage-1 block4 copy skipped) on two gloo processes in dry-run mode: every exchanged element is summed exactly
+    once, with and without the overlapped head optimizer."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "dp_worker.py"
+    script.write_text(_DP_WORKER % dict(root=root, small=SMALL))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29541", WORLD_SIZE="2")
+    procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r)), stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=600)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), "\n".join(outs)
