@@ -68,6 +68,17 @@ def _no_stream(s):
     yield
 
 
+class FakeGraph(object):
+    """torch.cuda.CUDAGraph stand-in: the body runs once inside `torch.cuda.graph(g)` (as the Python side of a real
+    capture does), `replay()` only counts."""
+
+    def __init__(self):
+        self.replays = 0
+
+    def replay(self):
+        self.replays += 1
+
+
 def install(monkeypatch):
     """Returns the list that records the name of every C-ABI entry point 'launched'."""
     from mtl_ssl_b200 import _lib, ops, ops_conv
@@ -79,6 +90,8 @@ def install(monkeypatch):
     monkeypatch.setattr(torch.cuda, "current_stream", lambda *a, **k: cur)
     monkeypatch.setattr(torch.cuda, "stream", _no_stream)
     monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    monkeypatch.setattr(torch.cuda, "CUDAGraph", FakeGraph)
+    monkeypatch.setattr(torch.cuda, "graph", _no_stream)
     monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self, *a, **k: self)
     monkeypatch.setattr(_lib, "lib", lambda: fake)
     for mod in (ops, ops_conv):

@@ -69,7 +69,8 @@ def test_inference_with_refiner_call_sequence(monkeypatch):
     assert set(r0) == set(r1)
 
 
-def test_mixed_shape_training_loop_with_checkpoints(monkeypatch, tmp_path):
+@pytest.mark.parametrize("graph", [False, True])
+def test_mixed_shape_training_loop_with_checkpoints(monkeypatch, tmp_path, graph):
     """shape_buckets.ShapeBucketTrainer under data.loader.train_loop: two image shapes alternate over one model, the
     training state is saved and restored through the TF checkpoint format (real ParamStore, CPU tensors)."""
     from mtl_ssl_b200.builders import model_builder
@@ -80,17 +81,19 @@ def test_mixed_shape_training_loop_with_checkpoints(monkeypatch, tmp_path):
     dryrun.install(monkeypatch)
     cfg = load_config("model12.config", SMALL)
     model = model_builder.build(cfg.model, True, device="cpu", seed=0)
-    bt = ShapeBucketTrainer(model, cfg.train_config, batch_size=1, max_buckets=2, use_cuda_graph=False, gmax=8)
+    bt = ShapeBucketTrainer(model, cfg.train_config, batch_size=1, max_buckets=2, use_cuda_graph=graph, gmax=8)
     shapes = [(224, 320), (224, 288), (224, 320), (320, 224)]
     prefix = str(tmp_path / "model.ckpt")
-    out = loader.train_loop(bt, _batches(model, bt, shapes), checkpoint_prefix=prefix, save_every=2)
+    model.param_store.m.fill_(0.25)                # (the stubbed optimizer never touches the momenta)
+    out = loader.train_loop(bt, _batches(model, bt, shapes), checkpoint_prefix=prefix)       # one save, at the end
     assert len(out) == 4 and bt.global_step == 4 and bt.evictions == 1 and list(bt.buckets) == [(224, 320), (320, 224)]
     assert checkpoint_io.latest_checkpoint(str(tmp_path)) == prefix + "-4"
-    model.param_store.m.fill_(0.25)
+    if graph:                  # every bucket captured its own graphs; the revisited shape replayed them
+        assert all(tr.graph_fb is not None and tr.graph_opt is not None for tr, _ in bt.buckets.values())
+        assert bt.buckets[(224, 320)][0].graph_fb.replays >= 1
     model2 = model_builder.build(cfg.model, True, device="cpu", seed=1)
     tr2 = Trainer(model2, cfg.train_config, 224, 320, 1, gmax=8, use_cuda_graph=False)
-    checkpoint_io.save_training_checkpoint(bt, prefix + "-5")
-    n, slots, step = checkpoint_io.restore_training_checkpoint(tr2, prefix + "-5")
+    n, slots, step = checkpoint_io.restore_training_checkpoint(tr2, prefix + "-4")
     assert step == 4 and slots == sum(1 for p in model.param_store.params if p.trainable and "/_pad/" not in p.name)
     assert torch.equal(model2.param_store.w, model.param_store.w)
     trainable = [p for p in model2.param_store.params if p.trainable and "/_pad/" not in p.name]
