@@ -211,3 +211,23 @@ def test_two_replica_step_exchanges_each_gradient_bucket_once_gloo(tmp_path):
                               stderr=subprocess.STDOUT, text=True) for r in range(2)]
     outs = [p.communicate(timeout=600)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), "\n".join(outs)
+
+
+@pytest.mark.parametrize("name", ["model42.config", "model52.config", "model22.config", "model11.config"])
+def test_inference_with_refiner_other_architectures(monkeypatch, name):
+    """R-FCN (PS-ROI windows), MobileNet, the COCO config (K = 90, crop 14 + max pool) and a baseline config without
+    auxiliary heads (nothing to refine) through evaluator.run_inference(use_refiner=True)."""
+    from mtl_ssl_b200 import evaluator
+    from mtl_ssl_b200.builders import model_builder
+    from mtl_ssl_b200.data import synthetic
+    log = dryrun.install(monkeypatch)
+    cfg = load_config(name, SMALL[1:] if name[5] in "56" else SMALL)
+    K = cfg.model.faster_rcnn.num_classes
+    model = model_builder.build(cfg.model, False, device="cpu", seed=0)
+    ex = synthetic.make_batch(7, 1, 224, 320, K, max_boxes=4, num_windows=16)
+    del log[:]
+    r = evaluator.run_inference(model, ex[0], use_refiner=True)
+    refines = bool(cfg.model.mtl.refine)
+    assert ("mtl_refine_concat" in log) == refines and ("mtl_expand_windows" in log) == (refines and bool(cfg.model.mtl.window))
+    assert ("mtl_psroi_fwd" in log) == (name == "model42.config")
+    assert "mtl_detection_gather" in log and r["detection_boxes"].shape[1:] == (4,)
