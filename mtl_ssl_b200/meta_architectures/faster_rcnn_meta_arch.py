@@ -323,8 +323,14 @@ class FasterRCNNMetaArch(model.DetectionModel):
         return self._anchor_cache[key]
 
     def num_kept_anchors(self, image_shape):
-        Hf, Wf = self._feature_extractor.feature_map_shape(image_shape[1], image_shape[2])
-        return self._anchors(Hf, Wf, image_shape[1], image_shape[2])[2]
+        """Anchors that survive the window pruning for INPUT images of `image_shape` [B,H,W,3] (the image resizer of
+        `preprocess` is applied to the size first): the length of the first-stage sampler keys."""
+        H, W = int(image_shape[1]), int(image_shape[2])
+        static_size = getattr(self._image_resizer_fn, "static_size", None)
+        if static_size is not None:
+            H, W = (int(v) for v in static_size(H, W))
+        Hf, Wf = self._feature_extractor.feature_map_shape(H, W)
+        return self._anchors(Hf, Wf, H, W)[2]
 
     # ------------------------------------------------------------------ forward
     def frozen_prefix(self, preprocessed_inputs, tag="s1"):

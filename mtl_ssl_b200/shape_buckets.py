@@ -71,7 +71,9 @@ class ShapeBucketTrainer(object):
         else:                                             # packing needs no device state: do not build the bucket here
             from .trainer import pack_groundtruth
             import numpy as np
-            arrays = pack_groundtruth(examples, self.model.num_classes, h, w, self._kw.get("gmax", 64))
+            static_size = getattr(getattr(self.model, "_image_resizer_fn", None), "static_size", None)
+            hr, wr = (h, w) if static_size is None else static_size(h, w)       # as Trainer.host_arrays packs it
+            arrays = pack_groundtruth(examples, self.model.num_classes, hr, wr, self._kw.get("gmax", 64))
             arrays["image"] = np.stack([e["image"] for e in examples]).astype(np.float32)
             arrays["keys1"], arrays["keys2"] = keys
         out = BucketArrays(arrays)

@@ -104,11 +104,11 @@ class Trainer(object):
                  clip_norm=10.0):
         self.model = model
         self.H, self.W, self.B = height, width, batch_size
-        # the ground truth is packed in pixels of the INPUT size: the model's image resizer must leave it unchanged
+        # (height, width) is the size of the images as they arrive; `model.preprocess` resizes them on the device with
+        # the config's image resizer (fmA:479-505), and everything downstream -- anchors, absolute ground-truth boxes,
+        # the clip window -- lives in pixels of the RESIZED image (fmA:1218-1266 scales by the preprocessed shape)
         static_size = getattr(getattr(model, "_image_resizer_fn", None), "static_size", None)
-        if static_size is not None and tuple(static_size(height, width)) != (height, width):
-            raise ValueError("Trainer needs images at their resized size: the config's image resizer maps %dx%d to "
-                             "%dx%d" % ((height, width) + tuple(static_size(height, width))))
+        self.Hr, self.Wr = (height, width) if static_size is None else tuple(int(v) for v in static_size(height, width))
         self.gmax = gmax
         self.world_size = world_size
         self.pg = process_group
@@ -171,7 +171,7 @@ class Trainer(object):
         for k in ("win_boxes", "win_cls", "edgemask"):
             if k in d:
                 gt[k] = d[k]
-        m._gt, m._gt_shape, m._groundtruth_dirty = gt, (self.B, self.H, self.W, 3), False
+        m._gt, m._gt_shape, m._groundtruth_dirty = gt, (self.B, self.Hr, self.Wr, 3), False
         m.provide_sampler_keys(d["keys1"], d["keys2"])
         return d["image"]
 
@@ -340,7 +340,7 @@ class Trainer(object):
         self.graph_opt.replay() if graph else self._optimize()
 
     def host_arrays(self, examples, keys):
-        arrays = pack_groundtruth(examples, self.model.num_classes, self.H, self.W, self.gmax)
+        arrays = pack_groundtruth(examples, self.model.num_classes, self.Hr, self.Wr, self.gmax)
         arrays["image"] = np.stack([e["image"] for e in examples]).astype(np.float32)
         arrays["keys1"], arrays["keys2"] = keys
         return arrays

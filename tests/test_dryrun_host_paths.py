@@ -98,9 +98,32 @@ def test_mixed_shape_training_loop_with_checkpoints(monkeypatch, tmp_path, graph
     assert torch.equal(model2.param_store.w, model.param_store.w)
     trainable = [p for p in model2.param_store.params if p.trainable and "/_pad/" not in p.name]
     assert all(bool((p.m == 0.25).all()) for p in trainable)
-    # a shape the config's resizer would change is refused with a clear message (ground truth is packed per input size)
-    with pytest.raises(ValueError, match="resized size"):
-        Trainer(model, cfg.train_config, 256, 288, 1)
+
+
+def test_raw_size_images_are_resized_on_the_device(monkeypatch):
+    """BASELINE.json configs[0]: model51.config UNCHANGED (MobileNet, min_dimension 600) on two 300x300 images.  The
+    trainer takes the images as they arrive; `preprocess` resizes them on the device (mtl_resize_bilinear_f32) and the
+    anchors, the absolute ground-truth boxes and the sampler keys all belong to the resized 600x600 image."""
+    from mtl_ssl_b200.builders import model_builder
+    from mtl_ssl_b200.data import synthetic
+    from mtl_ssl_b200.trainer import Trainer
+    log = dryrun.install(monkeypatch)
+    cfg = load_config("model51.config")
+    model = model_builder.build(cfg.model, True, device="cpu", seed=0)
+    assert model._image_resizer_fn.static_size(300, 300) == (600, 600)
+    tr = Trainer(model, cfg.train_config, 300, 300, 2, gmax=8, use_cuda_graph=False)
+    assert (tr.H, tr.W, tr.Hr, tr.Wr) == (300, 300, 600, 600)
+    K, M = cfg.model.faster_rcnn.num_classes, cfg.model.faster_rcnn.first_stage_max_proposals
+    nk = model.num_kept_anchors((2, 300, 300, 3))
+    assert nk == 38 * 38 * 12                    # dry run keeps every anchor of the 600x600 -> 38x38 map
+    ex = synthetic.make_batch(3, 2, 300, 300, K, max_boxes=4, num_windows=16)
+    arrays = tr.host_arrays(ex, synthetic.make_sampler_keys(4, 2, nk, M))
+    assert arrays["image"].shape == (2, 300, 300, 3)
+    np.testing.assert_allclose(arrays["gt"][0, 0], np.asarray(ex[0]["groundtruth_boxes"][0]) * 600.0, rtol=1e-6)
+    del log[:]
+    tr.step(arrays)
+    assert log.count("mtl_resize_bilinear_f32") >= 1 and model._gt_shape == (2, 600, 600, 3)
+    assert model._last_pd["image_shape"] == (2, 600, 600, 3) and model._last_pd["_feat_hw"] == (38, 38)
 
 
 def test_evaluation_loop_call_sequence(monkeypatch):
