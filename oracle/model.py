@@ -13,7 +13,9 @@ Follows, line by line where cited:
   object_detection/core/box_predictor.py :430-611, :682-755; core/mask_predictor.py :90-119
   slim/deployment/model_deploy.py :198-307 (total loss = task losses + L2 terms)
 The reference cannot run here (Python 2 + TF 1.7); TF kernels are restated in oracle/nn.py.
-The aux heads / refine / closeness have no reference tests: parity unpinned.
+The aux heads / refine / closeness have no reference TESTS; the graph code around them (proposal sampling, the losses
+with their normalisers, the refiner's input assembly, target assignment) is pinned by executing the reference's own
+methods on a NumPy TensorFlow stand-in (tests/golden/make_*_golden.py, tests/test_oracle_kats.py).
 
 Weights come as a dict {TF variable name: tensor}, conv / FC weights in [K, R, S, C] layout
 (TF's HWIO transposed).  `bf16=True` mirrors the device path's rounding points (weights with the
