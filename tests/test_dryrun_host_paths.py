@@ -214,6 +214,18 @@ for overlap in (True, False):
     dead = st.g[heads.numel() + trunk.numel():]
     assert dead.numel() > 0 and bool((dead == float(rank + 1)).all())      # the dead block4 copy is not exchanged (T4)
     st.g.zero_()
+# the captured variant (stand-in graphs): capture of the two backward halves, the head optimizer and the trunk optimizer,
+# then pipelined steps with the all-reduces issued between the replays
+for overlap in (True, False):
+    tr = Trainer(model, cfg.train_config, 224, 320, 1, gmax=8, use_cuda_graph=True, world_size=2)
+    tr.overlap_optimizer = overlap
+    ex = synthetic.make_batch(80 + rank, 1, 224, 320, 20, max_boxes=4, num_windows=16)
+    ky = synthetic.make_sampler_keys(90 + rank, 1, model.num_kept_anchors((1, 224, 320, 3)), 100)
+    arrays = tr.host_arrays(ex, ky)
+    outs = [tr.step_pipelined(arrays) for _ in range(3)] + [tr.flush()]
+    assert outs[0] is None and all(o is not None and "total_loss" in o for o in outs[1:])
+    assert tr.graph_fb.replays >= 2 and tr.graph_fb2.replays >= 2 and tr.graph_opt.replays >= 2
+    assert (tr.graph_opt_heads is not None) == overlap and tr.global_step == 3
 dist.destroy_process_group()
 print("rank", rank, "ok")
 """
