@@ -266,3 +266,36 @@ def test_inference_with_refiner_other_architectures(monkeypatch, name):
     assert ("mtl_refine_concat" in log) == refines and ("mtl_expand_windows" in log) == (refines and bool(cfg.model.mtl.window))
     assert ("mtl_psroi_fwd" in log) == (name == "model42.config")
     assert "mtl_detection_gather" in log and r["detection_boxes"].shape[1:] == (4,)
+
+
+def test_full_size_step_launches_what_the_committed_profile_shows(monkeypatch):
+    """BASELINE configs[1] (model12.config unchanged, 600x1000, batch 1): the step issues as many tcgen05 conv launches
+    as the committed ncu launch list holds `tc_gemm_kernel` rows (profiles/r1_launches_step_final.csv: 374), so the
+    profile the roofline numbers come from still describes the code."""
+    import collections
+    import csv
+    import os
+    from mtl_ssl_b200.builders import model_builder
+    from mtl_ssl_b200.data import synthetic
+    from mtl_ssl_b200.trainer import Trainer
+    log = dryrun.install(monkeypatch)
+    cfg = load_config("model12.config")
+    model = model_builder.build(cfg.model, True, device="cpu", seed=0)
+    tr = Trainer(model, cfg.train_config, 600, 1000, 1, gmax=16, use_cuda_graph=False)
+    ex = synthetic.make_batch(1, 1, 600, 1000, 20, max_boxes=8, num_windows=64)
+    ky = synthetic.make_sampler_keys(2, 1, model.num_kept_anchors((1, 600, 1000, 3)), 300)
+    arrays = tr.host_arrays(ex, ky)
+    # bench.py's e2e.h2d_bytes_per_step (7 297 896 on the device): same arrays, except that the dry run keeps all
+    # 28 728 anchors where the device prunes to 13 965 (first-stage sampler keys, 4 bytes each)
+    assert sum(v.nbytes for v in arrays.values()) - (28728 - 13965) * 4 == 7297896
+    tr.step(arrays)
+    del log[:]
+    tr.step(arrays)
+    c = collections.Counter(log)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    rows = list(csv.reader(open(os.path.join(root, "profiles", "r1_launches_step_final.csv"))))
+    ki = rows[0].index("Kernel Name")
+    profiled = collections.Counter("tc_gemm" if "tc_gemm_kernel" in r[ki] else "other" for r in rows[1:] if len(r) > ki)
+    assert c["mtl_conv_tc"] == profiled["tc_gemm"] == 374
+    assert c["mtl_nms"] == 1 and c["mtl_crop_and_resize_fwd"] == 3 and c["mtl_expand_windows"] == 1
+    assert abs(sum(c.values()) - (profiled["tc_gemm"] + profiled["other"])) <= 16      # a few library copies / casts differ
