@@ -299,3 +299,29 @@ def test_full_size_step_launches_what_the_committed_profile_shows(monkeypatch):
     assert c["mtl_conv_tc"] == profiled["tc_gemm"] == 374
     assert c["mtl_nms"] == 1 and c["mtl_crop_and_resize_fwd"] == 3 and c["mtl_expand_windows"] == 1
     assert abs(sum(c.values()) - (profiled["tc_gemm"] + profiled["other"])) <= 16      # a few library copies / casts differ
+
+
+def test_algorithmic_flops_of_the_step_match_the_roofline_basis(monkeypatch):
+    """2.90 TFLOP forward + 2.02 TFLOP backward per 600x1000 image.  The per-launch algorithmic FLOPs that
+    bench.py divides by the measured kernel time (ops_conv.PROFILE) sum to that figure over the 374 launches of a step,
+    and to bench.algorithmic_flops_per_image() which `roofline.step_tflops` uses."""
+    import bench
+    from mtl_ssl_b200 import ops_conv
+    from mtl_ssl_b200.builders import model_builder
+    from mtl_ssl_b200.data import synthetic
+    from mtl_ssl_b200.trainer import Trainer
+    dryrun.install(monkeypatch)
+    cfg = load_config("model12.config")
+    model = model_builder.build(cfg.model, True, device="cpu", seed=0)
+    tr = Trainer(model, cfg.train_config, 600, 1000, 1, gmax=16, use_cuda_graph=False)
+    ex = synthetic.make_batch(1, 1, 600, 1000, 20, max_boxes=8, num_windows=64)
+    ky = synthetic.make_sampler_keys(2, 1, model.num_kept_anchors((1, 600, 1000, 3)), 300)
+    arrays = tr.host_arrays(ex, ky)
+    tr.step(arrays)
+    monkeypatch.setattr(ops_conv, "PROFILE", [])
+    tr.step(arrays)
+    prof = ops_conv.PROFILE
+    by_mode = [sum(p[1] for p in prof if p[0] == m) / 1e12 for m in range(3)]            # fprop, dgrad, wgrad
+    assert len(prof) == 374
+    assert abs(by_mode[0] - 2.90) < 0.005 and abs(by_mode[1] + by_mode[2] - 2.02) < 0.005
+    assert abs(sum(by_mode) * 1e12 - bench.algorithmic_flops_per_image()) < 1e-3 * bench.algorithmic_flops_per_image()
