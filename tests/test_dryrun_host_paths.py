@@ -325,3 +325,30 @@ def test_algorithmic_flops_of_the_step_match_the_roofline_basis(monkeypatch):
     assert len(prof) == 374
     assert abs(by_mode[0] - 2.90) < 0.005 and abs(by_mode[1] + by_mode[2] - 2.02) < 0.005
     assert abs(sum(by_mode) * 1e12 - bench.algorithmic_flops_per_image()) < 1e-3 * bench.algorithmic_flops_per_image()
+
+
+@pytest.mark.parametrize("name,B", [("model22.config", 2), ("model42.config", 1), ("model62.config", 1)])
+def test_coco_shape_inputs_of_the_other_baseline_configs(monkeypatch, name, B):
+    """BASELINE.json configs[2..4] (Faster R-CNN ResNet-101 + aux heads at 2 images per GPU, R-FCN, Inception-ResNet-v2)
+    on COCO-shape 800x1333 inputs with the configs UNCHANGED: their `keep_aspect_ratio_resizer` (600 / 1024) brings the
+    images to 600x1000 on the device, the stride-16 map is 38x63, one step runs host-side end to end."""
+    from mtl_ssl_b200 import ops_conv
+    from mtl_ssl_b200.builders import model_builder
+    from mtl_ssl_b200.data import synthetic
+    from mtl_ssl_b200.trainer import Trainer
+    log = dryrun.install(monkeypatch)
+    cfg = load_config(name)
+    K = cfg.model.faster_rcnn.num_classes
+    model = model_builder.build(cfg.model, True, device="cpu", seed=0)
+    H, W = 800, 1333
+    tr = Trainer(model, cfg.train_config, H, W, B, gmax=32, use_cuda_graph=False)
+    assert (tr.Hr, tr.Wr) == (600, 1000)
+    ex = synthetic.make_batch(1, B, H, W, K, max_boxes=8, num_windows=64)
+    ky = synthetic.make_sampler_keys(2, B, model.num_kept_anchors((B, H, W, 3)), 300)
+    monkeypatch.setattr(ops_conv, "PROFILE", [])
+    losses = tr.step(tr.host_arrays(ex, ky))
+    assert "total_loss" in losses and model._last_pd["_feat_hw"] == (38, 63)
+    assert model._last_pd["image_shape"] == (B, 600, 1000, 3) and "mtl_resize_bilinear_f32" in log
+    flops = sum(p[1] for p in ops_conv.PROFILE) / 1e12
+    if name == "model22.config":          # 2 images of the VOC-shape workload, K = 90, 14x14 crops + 2x2 max pool
+        assert 9.5 < flops < 10.0 and model.workspace.nbytes() < 9e9
