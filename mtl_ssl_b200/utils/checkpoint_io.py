@@ -14,7 +14,17 @@ from . import tf_checkpoint
 
 
 def _tf_name(name):
-    return name.replace("/_dead/", "/")
+    """Model variable name -> the name the reference's DETECTION graph gives that variable.
+    * the dead stage-1 copy of block4 lives directly under the first-stage scope there;
+    * Inception-ResNet-v2 (trap T18): the second-stage tails call `slim.repeat(net, 9, block8)` inside a fresh
+      `InceptionResnetV2` variable scope (incres fe:133-170), so TF names that scope `Repeat`, while the same layers are
+      `Repeat_2` in the classification network -- which is why the reference overrides
+      `restore_from_classification_checkpoint_fn` (incres fe:173-248).  This framework keeps the classification name
+      internally (the ImageNet map then needs no special case) and translates for detection checkpoints here."""
+    name = name.replace("/_dead/", "/")
+    if "/InceptionResnetV2/Repeat_2/" in name and not name.startswith("FirstStageFeatureExtractor/"):
+        name = name.replace("/InceptionResnetV2/Repeat_2/", "/InceptionResnetV2/Repeat/")
+    return name
 
 
 def variable_name_map(model, from_detection_checkpoint=True):

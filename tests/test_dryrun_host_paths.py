@@ -352,3 +352,79 @@ def test_coco_shape_inputs_of_the_other_baseline_configs(monkeypatch, name, B):
     flops = sum(p[1] for p in ops_conv.PROFILE) / 1e12
     if name == "model22.config":          # 2 images of the VOC-shape workload, K = 90, 14x14 crops + 2x2 max pool
         assert 9.5 < flops < 10.0 and model.workspace.nbytes() < 9e9
+
+
+@pytest.mark.parametrize("name", ["model12.config", "model52.config", "model62.config", "model42.config"])
+def test_classification_checkpoint_name_map_for_every_backbone(monkeypatch, tmp_path, name):
+    """trainer.py:311-356 + `restore_map` (fmA:1947-2013; incres fe:173-248): an ImageNet-classification checkpoint
+    (stage scopes stripped) initialises the first-stage trunk and EVERY copy of the second-stage tail (main, closeness,
+    window, and the dead stage-1 copy: T5, T14) -- for ResNet, MobileNet, Inception-ResNet-v2 and the R-FCN variant.
+    Real ParamStore on CPU tensors (dry run); the TF layouts go through the tensor-bundle writer / reader."""
+    from mtl_ssl_b200.builders import model_builder
+    from mtl_ssl_b200.utils import checkpoint_io, tf_checkpoint
+    dryrun.install(monkeypatch)
+    cfg = load_config(name, SMALL[1:] if name[5] in "56" else SMALL)
+    model = model_builder.build(cfg.model, True, device="cpu", seed=0)
+    name_map = checkpoint_io.variable_name_map(model, from_detection_checkpoint=False)
+    st = model.param_store
+    shapes = {p.name: tuple(p.shape) for p in st.params}
+    for b in st.bns:
+        if b.scope is not None:
+            for k in ("gamma", "beta", "moving_mean", "moving_variance"):
+                shapes[b.scope + "/" + k] = (b.channels,)
+    assert len(name_map) > 50 and not any(k.split("/")[0].endswith(("FeatureExtractor", "Predictor")) for k in name_map)
+    rng = np.random.default_rng(0)
+    ckpt = {}
+    for ck, targets in name_map.items():
+        shp = shapes[targets[0]]
+        assert all(shapes[t] == shp for t in targets), ck              # every copy has the checkpoint tensor's shape
+        v = rng.standard_normal(shp).astype(np.float32)
+        if ck.endswith("moving_variance"):
+            v = np.abs(v) + 0.5
+        ckpt[ck] = tf_checkpoint.native_to_tf(ck, v)
+    shared = [ck for ck, t in name_map.items() if len(t) > 1]
+    multi = max(len(name_map[ck]) for ck in shared) if shared else 1
+    mtl = cfg.model.mtl
+    # main tail + the aux scopes' own tails + (ResNet only: slim builds block4 inside the first-stage scope too, where it
+    # is dead; the MobileNet / Inception-ResNet bases stop at the stride-16 endpoint)
+    has_dead = any("/_dead/" in p.name for p in st.params)
+    assert has_dead == ("resnet" in cfg.model.faster_rcnn.feature_extractor.type)
+    copies = 1 + int(has_dead) + int(bool(mtl.closeness)) + int(bool(mtl.window))
+    assert multi == copies, (multi, copies)
+    prefix = str(tmp_path / "imagenet.ckpt")
+    tf_checkpoint.write_checkpoint(prefix, ckpt)
+    n, missing = checkpoint_io.load_tf_checkpoint(model, prefix, from_detection_checkpoint=False)
+    assert not missing and n == sum(len(t) for t in name_map.values())
+    sd = st.state_dict()
+    for ck, targets in name_map.items():
+        want = tf_checkpoint.tf_to_native(ck, ckpt[ck])
+        for t in targets:
+            np.testing.assert_array_equal(sd[t].numpy().reshape(want.shape), want, err_msg=t)
+    heads = [p.name for p in st.params if "BoxPredictor/" in p.name and p.name not in
+             {t for ts in name_map.values() for t in ts} and "/_pad/" not in p.name]
+    assert heads                                                         # predictor layers are not in such a checkpoint
+
+
+def test_detection_checkpoint_uses_the_reference_graph_names_for_inception_resnet(monkeypatch, tmp_path):
+    """Trap T18: in the reference's detection graph the second-stage block8 stack of Inception-ResNet-v2 is named
+    `<scope>/InceptionResnetV2/Repeat/...` (a fresh variable scope restarts slim.repeat's counter; incres fe:133-170,
+    :173-248), in a classification checkpoint `InceptionResnetV2/Repeat_2/...`.  Detection checkpoints written / read here
+    use the former, the ImageNet map the latter."""
+    from mtl_ssl_b200.builders import model_builder
+    from mtl_ssl_b200.utils import checkpoint_io, tf_checkpoint
+    dryrun.install(monkeypatch)
+    cfg = load_config("model62.config", SMALL[1:])
+    a = model_builder.build(cfg.model, True, device="cpu", seed=0)
+    prefix = str(tmp_path / "model.ckpt-1")
+    names = checkpoint_io.save_tf_checkpoint(a, prefix)
+    for scope in ("SecondStageFeatureExtractor", "ClosenessBoxPredictor", "WindowBoxPredictor"):
+        assert scope + "/InceptionResnetV2/Repeat/block8_1/Branch_0/Conv2d_1x1/weights" in names
+        assert not any(n.startswith(scope + "/InceptionResnetV2/Repeat_2/") for n in names)
+    assert "FirstStageFeatureExtractor/InceptionResnetV2/Repeat_1/block17_1/Branch_0/Conv2d_1x1/weights" in names
+    b = model_builder.build(cfg.model, True, device="cpu", seed=1)
+    n, missing = checkpoint_io.load_tf_checkpoint(b, prefix)
+    assert not missing
+    sa, sb = a.param_store.state_dict(), b.param_store.state_dict()
+    assert all(torch.equal(sa[k], sb[k]) for k in sa if "/_pad/" not in k)
+    cls_map = checkpoint_io.variable_name_map(a, from_detection_checkpoint=False)
+    assert len(cls_map["InceptionResnetV2/Repeat_2/block8_1/Branch_0/Conv2d_1x1/weights"]) == 3
