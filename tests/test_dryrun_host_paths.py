@@ -115,7 +115,7 @@ def test_raw_size_images_are_resized_on_the_device(monkeypatch):
     assert (tr.H, tr.W, tr.Hr, tr.Wr) == (300, 300, 600, 600)
     K, M = cfg.model.faster_rcnn.num_classes, cfg.model.faster_rcnn.first_stage_max_proposals
     nk = model.num_kept_anchors((2, 300, 300, 3))
-    assert nk == 38 * 38 * 12                    # dry run keeps every anchor of the 600x600 -> 38x38 map
+    assert 0 < nk < 38 * 38 * 12                 # anchors of the 600x600 -> 38x38 map that lie inside the image
     ex = synthetic.make_batch(3, 2, 300, 300, K, max_boxes=4, num_windows=16)
     arrays = tr.host_arrays(ex, synthetic.make_sampler_keys(4, 2, nk, M))
     assert arrays["image"].shape == (2, 300, 300, 3)
@@ -285,9 +285,9 @@ def test_full_size_step_launches_what_the_committed_profile_shows(monkeypatch):
     ex = synthetic.make_batch(1, 1, 600, 1000, 20, max_boxes=8, num_windows=64)
     ky = synthetic.make_sampler_keys(2, 1, model.num_kept_anchors((1, 600, 1000, 3)), 300)
     arrays = tr.host_arrays(ex, ky)
-    # bench.py's e2e.h2d_bytes_per_step (7 297 896 on the device): same arrays, except that the dry run keeps all
-    # 28 728 anchors where the device prunes to 13 965 (first-stage sampler keys, 4 bytes each)
-    assert sum(v.nbytes for v in arrays.values()) - (28728 - 13965) * 4 == 7297896
+    # bench.py's e2e.h2d_bytes_per_step on the device; 13 965 of the 28 728 anchors lie inside the image
+    assert model.num_kept_anchors((1, 600, 1000, 3)) == 13965
+    assert sum(v.nbytes for v in arrays.values()) == 7297896
     tr.step(arrays)
     del log[:]
     tr.step(arrays)
