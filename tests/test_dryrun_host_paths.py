@@ -428,3 +428,21 @@ def test_detection_checkpoint_uses_the_reference_graph_names_for_inception_resne
     assert all(torch.equal(sa[k], sb[k]) for k in sa if "/_pad/" not in k)
     cls_map = checkpoint_io.variable_name_map(a, from_detection_checkpoint=False)
     assert len(cls_map["InceptionResnetV2/Repeat_2/block8_1/Branch_0/Conv2d_1x1/weights"]) == 3
+
+
+def test_every_gpu_test_body_executes_in_dry_run_mode():
+    """`python -O -m pytest tests -m gpu --assert=plain --dry-run-gpu`: the bodies of ALL -m gpu tests run on the CPU with
+    stubbed kernels and stripped numerical asserts (tests/conftest.py).  What this catches before a GPU is spent on it:
+    C-ABI calls with the wrong number / kind of arguments, missing prediction-dict keys, shape mismatches between host
+    buffers, API drift between the tests and the product -- in particular for the device tests written after this
+    round's GPU budget was gone (tests/test_gpu_zz_*.py)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-O", "-m", "pytest", os.path.join(root, "tests"), "-m", "gpu", "--assert=plain",
+                        "--dry-run-gpu", "-q", "-x", "-p", "no:cacheprovider"], cwd=root, stdout=subprocess.PIPE,
+                       stderr=subprocess.STDOUT, text=True, timeout=1500)
+    tail = "\n".join(r.stdout.strip().splitlines()[-15:])
+    assert r.returncode == 0, tail
+    assert " passed" in tail and "failed" not in tail and "error" not in tail.lower(), tail
