@@ -56,10 +56,19 @@ def dominant_conv_group(records, peak):
     N, H_, W_, C, K, R, stride, P, Q = geom
     achieved = flops / (ms * 1e-3) / 1e12
     total_ms = sum(g[1] for g in groups.values())
-    return {"kernel": "tc_gemm_kernel %s %dx%d/%d C%d->K%d on %dx%dx%d" % (("fprop", "dgrad", "wgrad")[mode], R, R, stride, C,
-                                                                           K, N, H_, W_),
-            "launches": n, "avg_us": ms * 1e3 / n, "share_of_conv_time": ms / total_ms, "achieved": achieved,
-            "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None}
+    name = "tc_gemm_kernel %s %dx%d/%d C%d->K%d on %dx%dx%d" % (("fprop", "dgrad", "wgrad")[mode], R, R, stride, C, K, N,
+                                                                H_, W_)
+    out = {"kernel": name, "launches": n, "avg_us": ms * 1e3 / n, "share_of_conv_time": ms / total_ms,
+           "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
+           "traffic": None}
+    try:        # DRAM bytes per launch of this kernel from the committed ncu --set full capture, when there is one
+        t = json.load(open(os.path.join(ROOT, "profiles", "r1_kernel_traffic.json"))).get(name)
+        if t:
+            out["traffic"] = t["dram_bytes_read"] + t["dram_bytes_write"]
+            out["traffic_source"] = "profiles/r1_kernel_traffic.json (%s)" % t.get("capture", "ncu --set full")
+    except Exception:
+        pass
+    return out
 
 
 # ------------------------------------------------------------------------------------------ clocks

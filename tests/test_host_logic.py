@@ -339,3 +339,13 @@ def test_pack_groundtruth_accepts_images_without_boxes():
     out = pack_groundtruth(ex, 3, 100, 200, 4)
     assert out["num_gt"].tolist() == [0, 1] and out["gt_cls"][1, 0] == 2 and not out["gt"][0].any()
     np.testing.assert_allclose(out["gt"][1, 0], [10, 40, 50, 120], rtol=1e-6)
+
+
+def test_bench_dominant_group_carries_the_committed_dram_traffic():
+    """roofline.dominant.traffic: dram bytes read + written per launch from the committed ncu capture of that kernel."""
+    import bench
+    geom = (1280, 7, 7, 512, 512, 3, 1, 7, 7)
+    d = bench.dominant_conv_group([(0, 2e12, 1.0, geom)] * 3 + [(0, 1e9, 0.1, (1, 38, 63, 64, 64, 1, 1, 38, 63))], 1400.0)
+    assert d["traffic"] == 69021440 + 24559872 and "f_c3x3" in d["traffic_source"]
+    d = bench.dominant_conv_group([(1, 2e12, 1.0, (7, 9, 9, 64, 64, 3, 1, 9, 9))], 1400.0)
+    assert d["traffic"] is None and d["kernel"].startswith("tc_gemm_kernel dgrad")
