@@ -128,3 +128,40 @@ def evaluate_detection_results_coco(result_lists, categories, label_id_offset=1,
             if mi in metric_index:
                 metrics["COCO_Eval/%s/%s" % (name, mname)] = coco_metrics[cat_id][mi]
     return metrics
+
+
+def save_detection_results_for_submission(result_lists, categories, summary_dir, metrics_set):
+    """eval_util.py:884-930 of the reference (`eval_config.submission_format_output`): the evaluation servers' formats.
+    'coco_metrics'       -> <summary_dir>/detection_results/detection_results.json, one
+                            {"image_id", "category_id", "bbox": [x, y, w, h] (1 decimal), "score" (3 decimals)} per detection
+    'pascal_voc_metrics' -> <summary_dir>/detection_results/comp4_det_test_<class>.txt, lines
+                            '<image> <score> <xmin> <ymin> <xmax> <ymax>' (image ids without .jpg / .png)
+    Boxes are the absolute [ymin, xmin, ymax, xmax] of evaluator.run_inference.  Returns the list of files written."""
+    import os
+    out_dir = os.path.join(summary_dir, "detection_results")
+    os.makedirs(out_dir, exist_ok=True)
+    ids = result_lists["image_id"]
+    dets = list(zip(ids, result_lists["detection_boxes"], result_lists["detection_scores"],
+                    result_lists["detection_classes"]))
+    if metrics_set == "coco_metrics":
+        path = os.path.join(out_dir, "detection_results.json")
+        rows = []
+        for image_name, boxes, scores, classes in dets:
+            for (t, l, b, r), score, class_id in zip(boxes, scores, classes):
+                rows.append('{"image_id":%s,"category_id":%d,"bbox":[%.1f,%.1f,%.1f,%.1f],"score":%.3f}'
+                            % (image_name, class_id, l, t, r - l, b - t, score))
+        with open(path, "w") as f:
+            f.write("[" + ",".join(rows) + "]")
+        return [path]
+    if metrics_set == "pascal_voc_metrics":
+        files = {c["id"]: open(os.path.join(out_dir, "comp4_det_test_" + c["name"] + ".txt"), "w") for c in categories}
+        try:
+            for image_name, boxes, scores, classes in dets:
+                image_name = str(image_name).replace(".jpg", "").replace(".png", "")
+                for (t, l, b, r), score, class_id in zip(boxes, scores, classes):
+                    files[int(class_id)].write("%s %f %f %f %f %f\n" % (image_name, score, l, t, r, b))
+        finally:
+            for f in files.values():
+                f.close()
+        return [f.name for f in files.values()]
+    raise ValueError("Metric not found: {}".format(metrics_set))

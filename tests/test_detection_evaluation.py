@@ -353,3 +353,24 @@ def test_evaluate_loop_plumbing_with_a_stubbed_inference(monkeypatch, tmp_path):
                       "categories": cats, "annotations": anns})
     m = evaluator.evaluate(None, examples, cats, metrics_set="coco_metrics", eval_ann_filename=coco, use_refiner=True)
     assert abs(m["COCO_Eval/All/AP"] - 1.0) < 1e-12 and abs(m["COCO_Eval/b/AP"] - 1.0) < 1e-12 and seen[-2:] == [True, True]
+
+
+def test_submission_format_writers(tmp_path):
+    """eval_util.py:884-930 (`submission_format_output`): COCO result JSON ([x, y, w, h], raw category ids) and PASCAL
+    comp4 files (xmin ymin xmax ymax, image id without extension)."""
+    import json
+    from mtl_ssl_b200 import eval_util
+    lists = dict(image_id=["139", "285"], detection_boxes=[np.array([[20.0, 10.0, 70.5, 110.25]]), np.array([[1.0, 2.0, 3.0, 5.0], [0.0, 0.0, 9.0, 9.0]])],
+                 detection_scores=[np.array([0.98765]), np.array([0.5, 0.25])], detection_classes=[np.array([3]), np.array([90, 1])])
+    (path,) = eval_util.save_detection_results_for_submission(lists, [], str(tmp_path), "coco_metrics")
+    rows = json.load(open(path))
+    assert rows[0] == {"image_id": 139, "category_id": 3, "bbox": [10.0, 20.0, 100.2, 50.5], "score": 0.988}
+    assert [r["category_id"] for r in rows] == [3, 90, 1] and rows[1]["bbox"] == [2.0, 1.0, 3.0, 2.0]
+    cats = [{"id": 1, "name": "aeroplane"}, {"id": 3, "name": "bird"}, {"id": 90, "name": "x"}]
+    lists["image_id"] = ["000139.jpg", "000285.png"]
+    files = eval_util.save_detection_results_for_submission(lists, cats, str(tmp_path), "pascal_voc_metrics")
+    assert sorted(os.path.basename(f) for f in files) == ["comp4_det_test_aeroplane.txt", "comp4_det_test_bird.txt", "comp4_det_test_x.txt"]
+    bird = open(os.path.join(str(tmp_path), "detection_results", "comp4_det_test_bird.txt")).read()
+    assert bird == "000139 0.987650 10.000000 20.000000 110.250000 70.500000\n"
+    with pytest.raises(ValueError):
+        eval_util.save_detection_results_for_submission(lists, cats, str(tmp_path), "other")
