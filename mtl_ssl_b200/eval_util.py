@@ -165,3 +165,41 @@ def save_detection_results_for_submission(result_lists, categories, summary_dir,
                 f.close()
         return [f.name for f in files.values()]
     raise ValueError("Metric not found: {}".format(metrics_set))
+
+
+def main_metric(metrics, metrics_set="pascal_voc_metrics", main_subset=""):
+    """The scalar `save_best_ckpt` ranks checkpoints by (eval_util.py:932-962): for PASCAL the mAP of
+    `eval_config.main_subset` (default: the subset named 'all'), for COCO 'COCO_Eval/All/AP'.  -> (key, value)."""
+    if metrics_set == "coco_metrics":
+        return "COCO_Eval/All/AP", float(metrics["COCO_Eval/All/AP"])
+    if metrics_set != "pascal_voc_metrics":
+        raise ValueError("Metric not found: {}".format(metrics_set))
+    for key in metrics:
+        if "/" in key:
+            continue
+        if (not main_subset and "Subset all" in key) or (main_subset and main_subset in key):
+            return key, float(metrics[key])
+    raise KeyError("no mAP entry for subset %r among %s" % (main_subset or "all", [k for k in metrics if "/" not in k]))
+
+
+def save_best_checkpoint(metrics, checkpoint_file, save_fn, metrics_set="pascal_voc_metrics", main_subset=""):
+    """`save_best_ckpt` (eval_util.py:932-990): keep `<dir of checkpoint_file>/best/model.ckpt` + summary.json for the
+    checkpoint with the highest main metric so far (a NaN metric never replaces a stored one).  `save_fn(prefix)`
+    writes the checkpoint (e.g. functools.partial(checkpoint_io.save_tf_checkpoint, model)).  Returns True if saved."""
+    import json
+    import math
+    import os
+    _, value = main_metric(metrics, metrics_set, main_subset)
+    best = os.path.join(os.path.dirname(checkpoint_file), "best")
+    summary_path = os.path.join(best, "summary.json")
+    if os.path.exists(summary_path):
+        with open(summary_path) as f:
+            old = json.load(f)
+        if "mAP" in old and (math.isnan(value) or value < old["mAP"]):
+            return False
+    os.makedirs(best, exist_ok=True)
+    out = dict({k: float(v) for k, v in metrics.items()}, checkpoint_file=checkpoint_file, mAP=value)
+    with open(summary_path, "w") as f:
+        json.dump(out, f, indent=2, sort_keys=True)
+    save_fn(os.path.join(best, "model.ckpt"))
+    return True

@@ -374,3 +374,27 @@ def test_submission_format_writers(tmp_path):
     assert bird == "000139 0.987650 10.000000 20.000000 110.250000 70.500000\n"
     with pytest.raises(ValueError):
         eval_util.save_detection_results_for_submission(lists, cats, str(tmp_path), "other")
+
+
+def test_main_metric_and_best_checkpoint_bookkeeping(tmp_path):
+    """eval_util.py:932-990 (`save_best_ckpt`): the ranking metric per metrics_set / main_subset, the best/ directory with
+    summary.json, replaced only by a higher (non-NaN) value."""
+    import json
+    from mtl_ssl_b200 import eval_util
+    m = {"Subset all        mAP@0.5IOU": 0.61, "Subset all        mAP@0.5IOU/cat": 0.7, "Subset big        mAP@0.5IOU": 0.8,
+         "CorLoc/CorLoc@0.5IOU": 0.9}
+    assert eval_util.main_metric(m) == ("Subset all        mAP@0.5IOU", 0.61)
+    assert eval_util.main_metric(m, main_subset="big")[1] == 0.8
+    assert eval_util.main_metric({"COCO_Eval/All/AP": 0.33, "COCO_Eval/All/AP_IoU50": 0.5}, "coco_metrics") == ("COCO_Eval/All/AP", 0.33)
+    with pytest.raises(KeyError):
+        eval_util.main_metric({"Subset default    mAP@0.5IOU": 0.5})
+    saved = []
+    ck = str(tmp_path / "model.ckpt-100")
+    assert eval_util.save_best_checkpoint(m, ck, saved.append) is True
+    assert saved == [str(tmp_path / "best" / "model.ckpt")]
+    s = json.load(open(str(tmp_path / "best" / "summary.json")))
+    assert s["mAP"] == 0.61 and s["checkpoint_file"] == ck and s["CorLoc/CorLoc@0.5IOU"] == 0.9
+    assert eval_util.save_best_checkpoint(dict(m, **{"Subset all        mAP@0.5IOU": 0.5}), ck, saved.append) is False
+    assert eval_util.save_best_checkpoint(dict(m, **{"Subset all        mAP@0.5IOU": float("nan")}), ck, saved.append) is False
+    assert eval_util.save_best_checkpoint(dict(m, **{"Subset all        mAP@0.5IOU": 0.7}), ck, saved.append) is True
+    assert len(saved) == 2 and json.load(open(str(tmp_path / "best" / "summary.json")))["mAP"] == 0.7
