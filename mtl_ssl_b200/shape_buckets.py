@@ -44,8 +44,10 @@ class ShapeBucketTrainer(object):
         else:
             while len(self.buckets) >= self.max_buckets:
                 _, (old, _ws) = self.buckets.popitem(last=False)
-                if old is self._last:
-                    raise RuntimeError("the bucket in flight cannot be evicted")      # cannot happen: it is the newest
+                if old is self._last:          # max_buckets == 1: `_switch` has already flushed its step
+                    if old.flush() is not None:
+                        raise RuntimeError("a bucket with a step in flight cannot be evicted")
+                    self._last = None
                 self.evictions += 1
             ws = self._workspace_cls(self.model.device)
             self.model._ws = ws                            # the trainer's first step allocates into ITS workspace

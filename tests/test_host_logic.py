@@ -328,6 +328,12 @@ def test_shape_bucket_trainer_bookkeeping():
     assert bt.flush() is None
     with pytest.raises(ValueError, match="different sizes"):
         bt.host_arrays([dict(image=np.zeros((8, 8, 3))), dict(image=np.zeros((8, 9, 3)))], (None, None))
+    # a single bucket: every shape switch rebuilds it, the losses still come back in call order
+    del log[:]
+    one = ShapeBucketTrainer(model, None, batch_size=1, max_buckets=1, trainer_cls=FakeTrainer, workspace_cls=FakeWs)
+    bt = one
+    got = [one.step_pipelined(batch(h, w)) for h, w in [(32, 48), (40, 40), (32, 48)]] + [one.flush()]
+    assert got[0] is None and [r["total_loss"] for r in got[1:]] == [0.0, 1.0, 2.0] and one.evictions == 2
 
 
 def test_pack_groundtruth_accepts_images_without_boxes():
