@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900)]      # first run on a device: never hang the suite
 
 
 def _cos(a, b):

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900)]      # first run on a device: never hang the suite
 
 
 @pytest.mark.parametrize("src,dst", [((300, 300), (600, 600)), ((750, 1000), (600, 800)), ((37, 53), (224, 320)),
