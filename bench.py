@@ -1,21 +1,26 @@
 #!/usr/bin/env python
-"""Benchmark of the hot path: images/sec of one full Faster R-CNN ResNet-101 (+3 aux heads + refiner)
-training step (forward, 8 losses, explicit backward, gradient all-reduce, clip + momentum update).
+"""Benchmark of the hot path: images/sec of one full Faster R-CNN / R-FCN multi-task training step (forward, 8 losses,
+explicit backward, gradient all-reduce, clip + momentum update).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c1..c5]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Workload (BASELINE.json configs[1]): tests/golden/configs/model12.config unchanged (ResNet-101, K=20,
-12 anchors/location, 300 proposals, 256+256+64 trained ROIs + 1280 forward-only refine ROIs),
-synthetic 600x1000 images, per-GPU batch = the config's train_config.batch_size (1), random-init
-weights, bf16 tensor-core convolutions with fp32 accumulation and fp32 master weights.
+Workloads = BASELINE.json `configs` (the shipped config files unchanged, synthetic inputs, random-init weights):
+    c1  model51.config  Faster R-CNN MobileNet-v1 baseline (no aux heads), 2 x 300x300 per replica (-> 600x600)
+    c2  model12.config  Faster R-CNN ResNet-101 + 3 aux heads + refiner, 600x1000, 1 image per replica   [DEFAULT]
+    c3  model22.config  the same on COCO shapes: K=90, crop 14 + 2x2 max pool, 800x1333 (-> 600x1000), 2 per replica
+    c4  model42.config  R-FCN ResNet-101 + aux heads (position-sensitive ROI pooling), 800x1333, 1 per replica
+    c5  model62.config  Faster R-CNN Inception-ResNet-v2 + 3 aux heads, 800x1333, 4 per replica
+bf16 tensor-core convolutions with fp32 accumulation and fp32 master weights.
 
-Prints ONE JSON line (rank 0).  `value` = device-resident throughput (CUDA-graph replays, inputs in
-HBM); `e2e` = the same step through the public API (Trainer.step) with pinned-host inputs copied
-H2D and the loss vector read back D2H every step.  `roofline` is measured live: every tcgen05 conv
-launch of one eager step is bracketed by CUDA events; achieved = algorithmic FLOPs / kernel time.
-`--impl reference` times the CPU restatement of the reference path (oracle/, torch fp32 on all host
-threads): the reference itself is Python-2/TF-1.7 graph code and cannot run in this image.
+Prints ONE JSON line (rank 0).  `value` = device-resident throughput (CUDA-graph replays, inputs in HBM; the frozen
+conv1 + block1 prefix of the next step is computed underneath the current one -- on the same resident image, nothing is
+skipped); `e2e` = the same step through the public API (Trainer.step_pipelined) with pinned-host inputs copied H2D and
+the loss vector read back D2H every step.  `roofline` is measured live: every tcgen05 conv launch of one eager step is
+bracketed by CUDA events; achieved = algorithmic FLOPs / kernel time.  `loss_parity` (1 GPU): the device's losses on the
+first batch, from the initial weights, against the CPU oracle on the same weights and inputs.
+`--impl reference` times the CPU restatement of the reference path (oracle/, torch fp32 on all host threads) on the
+same weights and inputs: the reference itself is Python-2 / TF-1.7 graph code and cannot run in this image.
 """
 import argparse
 import json
@@ -29,15 +34,66 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-CONFIG = os.path.join(ROOT, "tests", "golden", "configs", "model12.config")
-WORKLOAD = ("Faster R-CNN ResNet-101 + 3 aux heads + refiner, model12.config, 600x1000, "
-            "train step (fwd+bwd+allreduce+clip+momentum)")
-H, W = 600, 1000
+STEP = "train step (fwd+bwd+allreduce+clip+momentum)"
+CONFIGS = {
+    "c1": dict(file="model51.config", H=300, W=300, batch=2, bn="randomize",
+               workload="Faster R-CNN MobileNet-v1 baseline (no aux heads), model51.config, 2 x 300x300 -> 600x600, " + STEP),
+    "c2": dict(file="model12.config", H=600, W=1000, batch=1, bn="synthetic",
+               workload="Faster R-CNN ResNet-101 + 3 aux heads + refiner, model12.config, 600x1000, " + STEP),
+    "c3": dict(file="model22.config", H=800, W=1333, batch=2, bn="synthetic",
+               workload="Faster R-CNN ResNet-101 + 3 aux heads + refiner, model22.config (K=90, crop 14 + maxpool), "
+                        "COCO-shape 800x1333 -> 600x1000, 2 images per GPU, " + STEP),
+    "c4": dict(file="model42.config", H=800, W=1333, batch=1, bn="synthetic",
+               workload="R-FCN ResNet-101 + aux heads (PS-ROI), model42.config, COCO-shape 800x1333 -> 600x1000, " + STEP),
+    "c5": dict(file="model62.config", H=800, W=1333, batch=4, bn="randomize",
+               workload="Faster R-CNN Inception-ResNet-v2 + 3 aux heads, model62.config, COCO-shape 800x1333 -> 600x1000, "
+                        "4 images per GPU, " + STEP),
+}
+# 2*MACs of every conv / FC of one train step per image (fwd + bwd), where the survey states it
+SURVEY_FLOPS_PER_IMAGE = {"c2": 4.92e12}
 
 
 def algorithmic_flops_per_image():
-    """2*MACs of every conv/FC of one train step at 600x1000 (fwd 2.90 T + bwd 2.02 T)."""
-    return 4.92e12
+    """2*MACs of every conv/FC of one train step of the default workload (c2) at 600x1000
+    (fwd 2.90 T + bwd 2.02 T)."""
+    return SURVEY_FLOPS_PER_IMAGE["c2"]
+
+
+def workload_config(key, B, world):
+    """The `config` object of the JSON line: identical in both arms (ours / reference) for one workload."""
+    c = CONFIGS[key]
+    return {"workload": c["workload"], "bench_config": key, "config_file": c["file"], "input_hw": [c["H"], c["W"]],
+            "per_gpu_batch": B, "global_batch": B * world, "parallelism": "dp%d" % world,
+            "l2_flush": "none needed: one step touches several GB of activations + weights (>> 126 MB L2)"}
+
+
+def initial_state(key, seed=0):
+    """(parsed config, host state dict {TF variable name: fp32 tensor}): the weights BOTH arms start from.  Built on the
+    host exactly as ParamStore.finalize draws them; frozen batch-norm statistics chosen so that random-init activations
+    stay O(1) (utils/synthetic_init.py for the ResNets, tests/helpers.randomize_bn for MobileNet / Inception-ResNet)."""
+    from helpers import load_config, randomize_bn
+    from mtl_ssl_b200.builders import model_builder
+    from mtl_ssl_b200.utils import synthetic_init
+    c = CONFIGS[key]
+    cfg = load_config(c["file"])
+    table = model_builder.build(cfg.model, True, device=None, seed=seed)
+    if c["bn"] == "synthetic":
+        synthetic_init.apply_host(table.param_store)
+    sd = table.param_store.host_state_dict(seed)
+    if c["bn"] == "randomize":
+        sd = randomize_bn(sd, seed)
+    return cfg, sd, table
+
+
+def first_batch(key, cfg, nk, B, rank=0, i=0):
+    """Seeded synthetic batch + sampler keys number `i` of `rank` (the same function feeds both arms).
+    nk: anchors kept by the window pruning = length of the first-stage sampler keys."""
+    from mtl_ssl_b200.data import synthetic
+    c = CONFIGS[key]
+    fr = cfg.model.faster_rcnn
+    ex = synthetic.make_batch(1234 + rank * 100 + i, B, c["H"], c["W"], fr.num_classes, max_boxes=8, num_windows=64)
+    keys = synthetic.make_sampler_keys(99 + rank * 100 + i, B, nk, fr.first_stage_max_proposals)
+    return ex, keys
 
 
 def dominant_conv_group(records, peak):
@@ -61,13 +117,15 @@ def dominant_conv_group(records, peak):
     out = {"kernel": name, "launches": n, "avg_us": ms * 1e3 / n, "share_of_conv_time": ms / total_ms,
            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
            "traffic": None}
-    try:        # DRAM bytes per launch of this kernel from the committed ncu --set full capture, when there is one
-        t = json.load(open(os.path.join(ROOT, "profiles", "r1_kernel_traffic.json"))).get(name)
-        if t:
-            out["traffic"] = t["dram_bytes_read"] + t["dram_bytes_write"]
-            out["traffic_source"] = "profiles/r1_kernel_traffic.json (%s)" % t.get("capture", "ncu --set full")
-    except Exception:
-        pass
+    for fn in ("r2_kernel_traffic.json", "r1_kernel_traffic.json"):
+        try:        # DRAM bytes per launch of this kernel from the committed ncu --set full capture, when there is one
+            t = json.load(open(os.path.join(ROOT, "profiles", fn))).get(name)
+            if t:
+                out["traffic"] = t["dram_bytes_read"] + t["dram_bytes_write"]
+                out["traffic_source"] = "profiles/%s (%s)" % (fn, t.get("capture", "ncu --set full"))
+                break
+        except Exception:
+            pass
     return out
 
 
@@ -123,71 +181,99 @@ class ClockSampler(object):
 
 
 # ------------------------------------------------------------------------------------------ CPU arm
-def oracle_sample(threads, rois=16, refine=True, full_image=True):
-    """One bounded CPU sample of the reference path (oracle/model.py, fp32): the COMPLETE stage-1
-    network + RPN + proposal path at 600x1000, but `rois` ROIs per second-stage head instead of
-    256 (and rois//4 windows).  Returns (seconds_stage1_part, seconds_per_roi_equivalent, detail)."""
-    import numpy as np
-    import torch
-    from helpers import load_config, oracle_config
-    from mtl_ssl_b200.data import synthetic
-    from oracle.model import Oracle
-    import oracle.refparams as refparams
-    torch.set_num_threads(threads)
-    cfg = load_config("model12.config", (("second_stage_batch_size: 256", "second_stage_batch_size: %d" % rois),))
-    ocfg = oracle_config(cfg)
-    params, l2 = refparams.build_params(ocfg, seed=0)
-    nwin = max(rois // 4, 1)
-    examples = synthetic.make_batch(1, 1, H, W, ocfg["num_classes"], max_boxes=8, num_windows=nwin)
-    orc = Oracle(params, ocfg, bf16=False)
-    orc.require_grad([k for k in params if refparams.is_trainable(k)])
-    img = torch.from_numpy(np.stack([e["image"] for e in examples]))
-    nk = refparams.num_kept_anchors(ocfg, H, W)
-    keys = synthetic.make_sampler_keys(2, 1, nk, ocfg["first_stage_max_proposals"])
-    t0 = time.perf_counter()
-    out = orc.forward(img, examples, keys, H, W)
-    losses = orc.loss(out, examples, keys, H, W)
-    total = sum(losses.values()) + orc.regularization_loss(l2)
-    total.backward()
-    dt = time.perf_counter() - t0
-    # ROI-equivalents processed: main + closeness (fwd+bwd), windows (fwd+bwd), 5x refine (fwd only ~ 1/3)
-    return dt, float(total.detach()), dict(rois=rois, windows=nwin)
+class CpuReference(object):
+    """The CPU restatement of the reference step (oracle/model.py, fp32, torch-CPU on all host threads) on the
+    workload's own weights and first batch."""
 
+    def __init__(self, key, threads):
+        import torch
+        from helpers import oracle_config
+        torch.set_num_threads(threads)
+        self.key, self.threads = key, threads
+        self.cfg, self.sd, self.table = initial_state(key)
+        self.B = CONFIGS[key]["batch"]
+        self.ocfg = oracle_config(self.cfg)
+        st = self.table.param_store
+        # (the dead stage-1 block4 copy takes no part in the forward pass but its L2 terms are in the total loss, trap T4)
+        self.params = {k: v for k, v in self.sd.items() if "/_pad/" not in k}
+        self.l2 = {p.name: p.l2 for p in st.params if p.name in self.params}
+        self.trainable = [p.name for p in st.params if p.trainable and p.name in self.params]
+        resizer = getattr(self.table, "_image_resizer_fn", None)
+        c = CONFIGS[key]
+        self.Hr, self.Wr = (c["H"], c["W"]) if resizer is None else tuple(int(v) for v in resizer.static_size(c["H"], c["W"]))
+        # anchors inside the resized image (fmA:930-976), counted with the oracle's own anchor code (no device here)
+        from oracle import boxes as OB
+        hf, wf = self.table._feature_extractor.feature_map_shape(self.Hr, self.Wr)
+        anchors = OB.grid_anchors(hf, wf, self.ocfg["scales"], self.ocfg["aspect_ratios"], (256, 256), (16, 16), (0, 0))
+        self.nk = len(OB.prune_outside_window(anchors, (0, 0, self.Hr, self.Wr))[1])
+        self.examples, self.keys = first_batch(key, self.cfg, self.nk, self.B)
 
-_CPU_WARM = [False]
+    def images(self):
+        import numpy as np
+        import torch
+        from oracle import nn as ON
+        c = CONFIGS[self.key]
+        img = torch.from_numpy(np.stack([e["image"] for e in self.examples]).astype(np.float32))
+        if (self.Hr, self.Wr) != (c["H"], c["W"]):
+            img = ON.resize_bilinear(img, (self.Hr, self.Wr))          # model.preprocess (fmA:479-505)
+        return img
 
+    def step(self):
+        """One complete training step (forward, 8 losses + L2, autograd backward).  -> (seconds, losses dict)."""
+        from oracle.model import Oracle
+        orc = Oracle(self.params, self.ocfg, bf16=False)
+        orc.require_grad(self.trainable)
+        t0 = time.perf_counter()
+        img = self.images()
+        out = orc.forward(img, self.examples, self.keys, self.Hr, self.Wr)
+        losses = orc.loss(out, self.examples, self.keys, self.Hr, self.Wr)
+        reg = orc.regularization_loss(self.l2)
+        total = sum(losses.values()) + reg
+        total.backward()
+        dt = time.perf_counter() - t0
+        ld = {k: float(v.detach()) for k, v in losses.items()}
+        ld["regularization_loss"] = float(reg.detach())
+        ld["total_loss"] = float(total.detach())
+        return dt, ld
 
-def cpu_reference_throughput(threads, budget_s=25.0):
-    """images/sec of the CPU restatement: one discarded warm-up pass (8 ROIs per head), then ONE complete
-    step of the real workload (256 ROIs per head, 64 windows, 1280 refine windows) timed end to end."""
-    if not _CPU_WARM[0]:
-        oracle_sample(threads, 8)
-        _CPU_WARM[0] = True
-    t_full, loss, _ = oracle_sample(threads, 256)
-    return 1.0 / t_full, dict(full_step_s=t_full, loss=loss)
+    def mirror_losses(self, proposal_inputs):
+        """Forward + losses with the device's bf16 rounding points mirrored, on the device's RPN outputs."""
+        import torch
+        from oracle.model import Oracle
+        orc = Oracle(self.params, self.ocfg, bf16=True)
+        with torch.no_grad():
+            out = orc.forward(self.images(), self.examples, self.keys, self.Hr, self.Wr, proposal_inputs=proposal_inputs)
+            losses = orc.loss(out, self.examples, self.keys, self.Hr, self.Wr)
+        return {k: float(v) for k, v in losses.items()}, out
+
+    def sample_text(self, detail):
+        c = CONFIGS[self.key]
+        return ("oracle/model.py fp32 torch-CPU restatement of the reference step (the TF1/py2 reference cannot run here) "
+                "on the workload's own initial weights and first batch; sample = one complete %dx%d training step of %d "
+                "image(s) (forward, 8 losses + L2, autograd backward): %s" % (c["H"], c["W"], self.B, json.dumps(detail)))
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    vals = []
-    detail = None
+    ref = CpuReference(args.config, threads)
+    ref.step()                                       # discarded warm-up pass (thread pools, allocator)
+    times, losses = [], None
     for i in range(args.warmup + args.steps):
-        v, detail = cpu_reference_throughput(threads)
+        dt, losses = ref.step()
         if i >= args.warmup:
-            vals.append(v)
-    value = sum(vals) / len(vals)
-    sample = ("oracle/model.py fp32 torch-CPU restatement of the reference step (TF1/py2 reference cannot run "
-              "here); sample = one complete 600x1000 training step (forward, 8 losses + L2, autograd backward) after one "
-              "discarded warm-up pass: %s" % json.dumps(detail))
+            times.append(dt)
+    B = ref.B
+    value = B * len(times) / sum(times)
     line = {"impl": "reference", "metric": "images/sec", "value": value, "unit": "images/sec", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / value, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "global_batch": 1, "per_gpu_batch": 1, "parallelism": "cpu",
-                       "note": "fp32 CPU restatement of the same step (oracle/model.py), one image per step"},
-            "cpu_baseline": {"value": value, "unit": "images/sec", "cores": threads, "kind": "port", "sample": sample},
-            "e2e": {"value": value, "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * sum(times) / len(times),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args.config, B, world),
+            "cpu_baseline": {"value": value, "unit": "images/sec", "cores": threads, "kind": "port",
+                             "sample": ref.sample_text({"step_s": sum(times) / len(times)})},
+            "e2e": {"value": value, "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "losses": losses}
     print(json.dumps(line), flush=True)
 
 
@@ -196,26 +282,25 @@ def run_ours(args, rank, world, local_rank):
     import numpy as np
     import torch
     import torch.distributed as dist
-    from helpers import load_config
     from mtl_ssl_b200 import ops, ops_conv
     from mtl_ssl_b200.builders import model_builder
-    from mtl_ssl_b200.data import synthetic
+    from mtl_ssl_b200.meta_architectures.faster_rcnn_meta_arch import LOSS_KEYS
     from mtl_ssl_b200.trainer import Trainer
-    from mtl_ssl_b200.utils import synthetic_init
 
     torch.cuda.set_device(local_rank)
     dev = "cuda:%d" % local_rank
-    cfg = load_config("model12.config")
-    B = args.batch_per_gpu or cfg.train_config.batch_size
+    args.config = getattr(args, "config", "c2")
+    c = CONFIGS[args.config]
+    H, W = c["H"], c["W"]
+    cfg, sd0, table = initial_state(args.config)
+    B = args.batch_per_gpu or c["batch"]
     model = model_builder.build(cfg.model, True, device=dev, seed=0)      # identical weights on every rank
-    synthetic_init.apply(model.param_store)
-    K = cfg.model.faster_rcnn.num_classes
-    nk = model.num_kept_anchors((B, H, W, 3))
+    model.param_store.load_state_dict(sd0)
     tr = Trainer(model, cfg.train_config, H, W, B, gmax=16, use_cuda_graph=not args.no_graph, world_size=world)
     pool = []
+    nk = model.num_kept_anchors((B, H, W, 3))
     for i in range(4):
-        ex = synthetic.make_batch(1234 + rank * 100 + i, B, H, W, K, max_boxes=8, num_windows=64)
-        keys = synthetic.make_sampler_keys(99 + rank * 100 + i, B, nk, cfg.model.faster_rcnn.first_stage_max_proposals)
+        ex, keys = first_batch(args.config, cfg, nk, B, rank, i)
         pool.append(tr.host_arrays(ex, keys))
 
     def sync():
@@ -224,21 +309,26 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda.synchronize()
 
     # ---- warm-up (also captures the CUDA graphs)
-    l0 = ops.launch_count()
     for i in range(max(args.warmup, 3)):
         losses = tr.step(pool[i % len(pool)])
     sync()
     # kernels per step, counted by the library itself during one eager replay of the step body
+    st = model.param_store
+    snap = (st.w.clone(), st.m.clone(), st.wb.clone())
     c0 = ops.launch_count()
     tr._prefix(tr.inputs.dev["image"])                      # frozen conv1 + block1 (pipelined one step ahead)
-    tr._forward_backward(tr.inputs.dev["image"])
+    tr._forward_backward(tr.inputs.dev["image"])            # (one replica: includes the head bucket's update)
     if world > 1:
+        if tr.overlap_optimizer:
+            tr._optimize_heads()
         tr._backward_trunk()
-    model.param_store.g.zero_()
+    tr._optimize()
     c1 = ops.launch_count()
-    # + the optimizer launches not in the count above: stats, fixed-order norm reduction, L2 reduction and apply for
-    # the trunk range, and (several replicas: its own graph) stats + reduction + apply of the head bucket
-    launches_per_step = (c1 - c0) + (4 if world == 1 else 7)
+    launches_per_step = c1 - c0
+    torch.cuda.synchronize()
+    st.w.copy_(snap[0]); st.m.copy_(snap[1]); st.wb.copy_(snap[2])      # this pass skipped the gradient exchange: undo it
+    st.g.zero_()
+    del snap
     sync()
 
     clocks = ClockSampler(local_rank)
@@ -246,7 +336,6 @@ def run_ours(args, rank, world, local_rank):
         clocks.start()
         time.sleep(0.3)
     # ---- timed region 1: device-resident (inputs already in HBM), K steps
-    st = model.param_store
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync()
     e0.record()
@@ -336,18 +425,25 @@ def run_ours(args, rank, world, local_rank):
     images = B * world * args.steps
     value = images / (ms_dev * 1e-3)
     e2e_value = images / (ms_e2e * 1e-3)
-    h2d = tr.inputs.nbytes
+    h2d = tr.inputs.nbytes + tr._hyper_host.numel() * tr._hyper_host.element_size()
+    d2h = tr._loss_host.numel() * tr._loss_host.element_size()
     step_ms = ms_dev / args.steps
+    # algorithmic FLOPs of one step: SURVEY 8(d)'s figure where it states one, else the sum over the step's conv / FC
+    # launches (2*N*P*Q*K*R*S*C each -- the same count the survey's figure is made of; tests/test_zz_dryrun_host_paths)
+    survey = SURVEY_FLOPS_PER_IMAGE.get(args.config)
+    step_flops = survey * B if survey else conv_flops
+    cfg_line = workload_config(args.config, B, world)
     line = {
         "metric": "images/sec", "value": value, "unit": "images/sec", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": WORKLOAD,
-                   "global_batch": B * world, "per_gpu_batch": B, "parallelism": "dp%d" % world,
-                   "l2_flush": "none needed: one step touches %.1f GB of activations+weights (>> 126 MB L2)"
-                               % ((model.workspace.nbytes() + st.total * 14) / 1e9),
-                   "cuda_graph": bool(tr.use_graph)},
-        "e2e": {"value": e2e_value, "unit": "images/sec", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 36,
+        "config": cfg_line,
+        "schedule": {"cuda_graph": bool(tr.use_graph), "timed_region_ms": ms_dev,
+                     "resident_step": "CUDA-graph replays on the batch resident in HBM; the frozen conv1 + block1 prefix "
+                                      "of the NEXT step runs on a side stream under the current one (same resident image; "
+                                      "every step still executes its own prefix, nothing is cached or skipped)",
+                     "touched_gb_per_step": (model.workspace.nbytes() + st.total * 14) / 1e9},
+        "e2e": {"value": e2e_value, "unit": "images/sec", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps, "api": "Trainer.step_pipelined (batch i+1 staged while step i runs)",
                 "synchronous_step_value": images / (ms_e2e_sync * 1e-3)},
         "gpu_launches": launches_per_step * args.steps * 2,
@@ -357,18 +453,50 @@ def run_ours(args, rank, world, local_rank):
                      "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                      "peak_source": peak_src, "traffic": None, "dominant": dominant,
                      "conv_ms_per_step": conv_ms, "conv_share_of_step": conv_ms / step_ms,
+                     "note": "achieved = per-launch rate of a serialised single-stream pass; step_tflops = the timed "
+                             "multi-stream step's algorithmic rate (step_frac = step_tflops / peak)",
                      "by_mode": {k: {"tflops": v[0] / (v[1] * 1e-3) / 1e12, "ms": v[1], "launches": v[2]}
                                  for k, v in by_mode.items()},
-                     "step_tflops": algorithmic_flops_per_image() * B / (step_ms * 1e-3) / 1e12},
+                     "step_flops": step_flops, "step_flops_source": "SURVEY 8(d)" if survey else "sum over launches",
+                     "launch_flops": conv_flops,
+                     "step_tflops": step_flops / (step_ms * 1e-3) / 1e12,
+                     "step_frac": step_flops / (step_ms * 1e-3) / 1e12 / peak},
         "losses": losses,
     }
     if world == 1 and not args.skip_cpu:
+        # ---- loss parity + CPU baseline: both arms start from the same weights (sd0) and use the same first batch
         threads = os.cpu_count() or 1
-        v, detail = cpu_reference_throughput(threads)
+        ref = CpuReference(args.config, threads)
+        st.load_state_dict(sd0)
+        st.m.zero_(); st.g.zero_()
+        tr.overlap_optimizer = False
+        image = tr._bind(pool[0])
+        tr._prefix(image)
+        pd = tr._forward_backward(image)
+        torch.cuda.synchronize()
+        dev_l = dict(zip(LOSS_KEYS, model.workspace.bufs["loss/values"].cpu().tolist()))
+        prop_in = (pd["rpn_box_encodings"].cpu().numpy(),
+                   pd["rpn_objectness_predictions_with_background"].cpu().numpy())
+        want, out = ref.mirror_losses(prop_in)
+        dev_total = sum(dev_l[k] for k in want)
+        orc_total = sum(want.values())
+        ref.step()                                   # discarded warm-up pass
+        dt, fp32 = ref.step()
+        fp32_task = fp32["total_loss"] - fp32["regularization_loss"]
+        line["loss_parity"] = {
+            "device_total": dev_total, "oracle_total": orc_total, "abs_diff": abs(dev_total - orc_total), "tol": 1e-3,
+            "ok": bool(abs(dev_total - orc_total) <= 1e-3 * max(1.0, abs(orc_total))
+                       and np.array_equal(pd["num_proposals"].cpu().numpy(), out["nprop"])),
+            "oracle": "oracle/model.py with the device's bf16 rounding points mirrored, on the device's RPN outputs "
+                      "(proposal counts identical: %s); sum of the task losses of fmA:1514-1589, same initial weights and "
+                      "batch on both sides" % bool(np.array_equal(pd["num_proposals"].cpu().numpy(), out["nprop"])),
+            "max_loss_abs_diff": max(abs(dev_l[k] - v) for k, v in want.items()),
+            "oracle_fp32_total": fp32_task, "fp32_abs_diff": abs(dev_total - fp32_task),
+            "fp32_note": "plain fp32 oracle with its OWN proposals (the reference's arithmetic; the cpu_baseline step)",
+            "device_losses": {k: dev_l[k] for k in want}, "oracle_losses": want}
+        v = ref.B / dt
         line["cpu_baseline"] = {"value": v, "unit": "images/sec", "cores": threads, "kind": "port",
-                                "sample": "oracle/model.py (fp32 torch-CPU restatement; the TF1/py2 reference cannot "
-                                          "run here): one complete 600x1000 training step (forward, losses, "
-                                          "autograd backward) after a discarded warm-up pass: %s" % json.dumps(detail)}
+                                "sample": ref.sample_text({"step_s": dt, "total_loss": fp32["total_loss"]})}
     print(json.dumps(line), flush=True)
 
 
@@ -378,6 +506,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
     ap.add_argument("--batch-per-gpu", type=int, default=0)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")

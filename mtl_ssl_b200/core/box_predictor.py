@@ -20,7 +20,8 @@ def _round8(n):
 class _FusedHead(object):
     """[sum(outs) (+pad to 8), cin] weight group + bias group, fprop / wgrad / dgrad via the conv engine."""
 
-    def __init__(self, store, scope, names_outs, cin, hp, trainable):
+    def __init__(self, store, scope, names_outs, cin, hp, trainable, fc=False):
+        """fc=True: the reference builds these outputs with slim.fully_connected (variables [cin, n], bp:482-496)."""
         self.outs = [n for _, n in names_outs]
         self.n_out = sum(self.outs)
         self.n_pad = _round8(self.n_out)
@@ -29,7 +30,7 @@ class _FusedHead(object):
         wspecs, bspecs = [], []
         for name, n in names_outs:
             wspecs.append(dict(name="%s/%s/weights" % (scope, name), shape=(n, 1, 1, cin), l2=hp.l2_weight,
-                               trainable=trainable, init=hp.init))
+                               trainable=trainable, init=hp.init, tf_kind="fc" if fc else None))
             bspecs.append(dict(name="%s/%s/biases" % (scope, name), shape=(n,), l2=0.0, trainable=trainable))
         if self.n_pad > self.n_out:
             wspecs.append(dict(name="%s/_pad/weights" % scope, shape=(self.n_pad - self.n_out, 1, 1, cin),
@@ -147,7 +148,7 @@ class MaskRCNNBoxPredictor(BoxPredictor):
         else:
             outs = [("BoxEncodingPredictor", self._num_classes * self._box_code_size),
                     ("ClassPredictor", self._num_classes + 1)]
-        self._heads[scope] = _FusedHead(store, scope, outs, in_channels, self._hp, self._is_training)
+        self._heads[scope] = _FusedHead(store, scope, outs, in_channels, self._hp, self._is_training, fc=True)
 
     def layout(self, scope):
         head = self._heads[scope]

@@ -17,13 +17,19 @@ class Hyperparams(object):
             l2 = hp.regularizer.l2_regularizer.weight
         elif reg == "l1_regularizer":
             raise ValueError("l1_regularizer is not supported on the B200 path")
+        # hyperparams_builder._build_initializer (hyperparams_builder.py:118-146): every parameter is passed on, an
+        # unknown / missing initializer is an error
         ini = hp.initializer.WhichOneof("initializer_oneof")
         if ini == "truncated_normal_initializer":
-            init = ("truncated_normal", hp.initializer.truncated_normal_initializer.stddev)
+            t = hp.initializer.truncated_normal_initializer
+            init = ("truncated_normal", t.stddev, t.mean)
         elif ini == "variance_scaling_initializer":
-            init = ("variance_scaling",)
+            v = hp.initializer.variance_scaling_initializer
+            mode = {0: "FAN_IN", 1: "FAN_OUT", 2: "FAN_AVG"}.get(v.mode, v.mode) if isinstance(v.mode, int) else str(v.mode)
+            init = ("variance_scaling", float(v.factor), mode, bool(v.uniform))
         elif ini == "random_normal_initializer":
-            init = ("normal", hp.initializer.random_normal_initializer.stddev)
+            r = hp.initializer.random_normal_initializer
+            init = ("normal", r.stddev, r.mean)
         else:
-            init = ("variance_scaling",)
+            raise ValueError("Unknown initializer function: {}".format(ini))
         return Hyperparams(l2, init, hp.op, hp.activation)

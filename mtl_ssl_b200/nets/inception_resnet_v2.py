@@ -226,6 +226,7 @@ class InceptionResnetV2Trunk(object):
         # Conv2d_1a_3x3 (3x3/2 on RGB): GEMM over im2col rows of 64 = 27 + zero pad (packed variable layout)
         self.conv1a = Conv2d(store, scope + "/Conv2d_1a_3x3", 64, 32, 1, 1, relu=True, l2=l2, trainable=t,
                              init=("packed_conv", 27, 0.1), bn_eps=EPS, bn_scale=False)
+        self.conv1a.weight.tf_kind = ("packed_conv", 3, 3, 3)      # TF: Conv2d_1a_3x3/weights [3,3,3,32]
         nodes = [c("Conv2d_2a_3x3", 32, 32, 3), c("Conv2d_2b_3x3", 32, 64, 3),
                  PoolNode(scope + "/MaxPool_3a_3x3", "max", 2, "SAME"),
                  c("Conv2d_3b_1x1", 64, 80), c("Conv2d_4a_3x3", 80, 192, 3),

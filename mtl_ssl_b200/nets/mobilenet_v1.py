@@ -28,6 +28,7 @@ class MobilenetV1Trunk(object):
         self.conv0 = Conv2d(store, scope + "/Conv2d_0", 64, 32, 1, 1, relu=2, l2=l2, trainable=trainable, init=INIT,
                             bn_eps=1e-3)
         self.conv0.weight.init = ("packed_conv", 27, 0.09)
+        self.conv0.weight.tf_kind = ("packed_conv", 3, 3, 3)       # TF: MobilenetV1/Conv2d_0/weights [3,3,3,32]
         self.layers = []
         cin = 32
         for i, (depth, stride) in enumerate(DEFS[:11]):

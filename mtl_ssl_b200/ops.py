@@ -12,7 +12,7 @@ import ctypes
 
 import torch
 
-from ._lib import lib, check
+from ._lib import lib, check, MtlError
 
 def _parse_header():
     """Derive every signature from include/mtlssl.h so that header and bindings cannot drift."""
@@ -82,6 +82,9 @@ def _conv(c, v):
         if v is None:
             return None
         if isinstance(v, torch.Tensor):
+            if not v.is_cuda and isinstance(lib(), ctypes.CDLL):
+                # a host pointer handed to a kernel is an illegal address on the device: refuse it here, loudly
+                raise MtlError("host tensor (shape %s) passed to a device kernel" % (tuple(v.shape),))
             return v.data_ptr()
         return int(v)
     if c in "iIl":

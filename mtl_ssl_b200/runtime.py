@@ -24,8 +24,12 @@ ALIGN = 64
 class Param(object):
     """One named tensor inside the arenas; `.w`/.g/.m are fp32 views, `.wb` the bf16 compute view."""
 
-    def __init__(self, name, shape, l2, trainable, init, fold=None, grad_mult=1.0):
+    def __init__(self, name, shape, l2, trainable, init, fold=None, grad_mult=1.0, tf_kind=None):
         self.name = name
+        # how the reference's TF graph stores this variable when it differs from what the rank implies (see
+        # utils/tf_checkpoint.tf_to_native): "fc" = slim.fully_connected [in, out] kept here as a [out,1,1,in] GEMM
+        # operand; ("packed_conv", R, S, C) = conv [R,S,C,K] kept as im2col rows [K,1,1,ld] with R*S*C real columns
+        self.tf_kind = tf_kind
         self.shape = tuple(int(s) for s in shape)
         self.numel = int(np.prod(self.shape))
         self.l2 = float(l2)
@@ -68,11 +72,11 @@ class ParamStore(object):
         self.finalized = False
         self.post_load_hooks = []   # callables run after weights change outside the optimizer
 
-    def add(self, name, shape, l2=0.0, trainable=True, init=("zeros",), fold=None, grad_mult=1.0):
+    def add(self, name, shape, l2=0.0, trainable=True, init=("zeros",), fold=None, grad_mult=1.0, tf_kind=None):
         assert not self.finalized
         if name in self.by_name:
             raise ValueError("duplicate variable %s" % name)
-        p = Param(name, shape, l2, trainable, init, fold, grad_mult)
+        p = Param(name, shape, l2, trainable, init, fold, grad_mult, tf_kind)
         self.params.append(p)
         self.by_name[name] = p
         self.groups.append([p])
@@ -123,6 +127,23 @@ class ParamStore(object):
         self.finalized = True
         self.fold()
         return self
+
+    def host_state_dict(self, seed=0):
+        """The state `finalize(device, seed)` + `state_dict()` would produce, built on the host without a device
+        (same generator, same draw order): lets a CPU checker start from exactly the weights a device run starts from."""
+        gen = torch.Generator().manual_seed(seed)
+        out = {}
+        for p in self.params:
+            out[p.name] = _init_tensor(p, gen).float()
+        for b in self.bns:
+            if b.scope is None:
+                continue
+            if b.has_gamma:
+                out[b.scope + "/gamma"] = b.gamma.clone()
+            out[b.scope + "/beta"] = b.beta.clone()
+            out[b.scope + "/moving_mean"] = b.mean.clone()
+            out[b.scope + "/moving_variance"] = b.var.clone()
+        return out
 
     def group_view(self, ps, rows, cols, arena="wb"):
         """View a contiguous group as one [rows, cols] matrix (rows may include zero padding)."""
@@ -271,31 +292,50 @@ class ParamStore(object):
             b.bias.copy_(bi.to(self.device))
 
 
+def _fans(p):
+    """(fan_in, fan_out) as slim.variance_scaling_initializer computes them from the TF variable shape
+    ([R,S,C,K] conv / [in,out] FC), expressed on this framework's [K,R,S,C] / [out,in] layout."""
+    fan_in = p.numel // p.shape[0]
+    fan_out = p.shape[0] * (p.numel // (p.shape[0] * p.shape[-1])) if len(p.shape) == 4 else p.shape[0]
+    return fan_in, fan_out
+
+
 def _init_tensor(p, gen):
     kind = p.init[0]
     if kind == "zeros":
         return torch.zeros(p.shape)
     if kind == "const":
         return torch.full(p.shape, float(p.init[1]))
-    if kind == "truncated_normal":          # tf.truncated_normal_initializer(stddev): resample |z| > 2
-        return _trunc_normal(p.shape, float(p.init[1]), gen)
+    if kind == "truncated_normal":          # tf.truncated_normal_initializer(mean, stddev): resample |z| > 2
+        mean = float(p.init[2]) if len(p.init) > 2 else 0.0
+        return _trunc_normal(p.shape, float(p.init[1]), gen) + mean
     if kind == "variance_scaling":
-        # slim.variance_scaling_initializer() defaults: factor 2.0, FAN_IN, truncated normal with
-        # stddev sqrt(1.3 * factor / fan_in) (tf.contrib.layers initializers.py)
-        fan_in = p.numel // p.shape[0]
-        return _trunc_normal(p.shape, math.sqrt(1.3 * 2.0 / fan_in), gen)
+        # slim.variance_scaling_initializer(factor=2.0, mode='FAN_IN', uniform=False) (tf.contrib.layers
+        # initializers.py): n = fan_in | fan_out | their mean; uniform: U(-l, l) with l = sqrt(3 * factor / n);
+        # otherwise truncated normal with stddev sqrt(1.3 * factor / n)
+        factor = float(p.init[1]) if len(p.init) > 1 else 2.0
+        mode = p.init[2] if len(p.init) > 2 else "FAN_IN"
+        uniform = bool(p.init[3]) if len(p.init) > 3 else False
+        fan_in, fan_out = _fans(p)
+        if mode not in ("FAN_IN", "FAN_OUT", "FAN_AVG"):
+            raise TypeError("Unknown mode %s [FAN_IN, FAN_OUT, FAN_AVG]" % (mode,))
+        n = {"FAN_IN": float(fan_in), "FAN_OUT": float(fan_out), "FAN_AVG": (fan_in + fan_out) / 2.0}[mode]
+        if uniform:
+            lim = math.sqrt(3.0 * factor / n)
+            return (torch.rand(p.shape, generator=gen) * 2 - 1) * lim
+        return _trunc_normal(p.shape, math.sqrt(1.3 * factor / n), gen)
     if kind == "packed_conv":           # [K, ld] rows holding `real` truncated-normal columns, zero padding
         real, std = int(p.init[1]), float(p.init[2])
         t = torch.zeros(p.shape)
         t.view(p.shape[0], -1)[:, :real] = _trunc_normal((p.shape[0], real), std, gen)
         return t
-    if kind == "xavier":                # slim default: xavier_initializer (uniform)
-        fan_in = p.numel // p.shape[0]
-        fan_out = p.shape[0] * (p.numel // (p.shape[0] * p.shape[-1])) if len(p.shape) == 4 else p.shape[0]
+    if kind == "xavier":                # slim default: xavier_initializer (uniform) == factor 1.0, FAN_AVG, uniform
+        fan_in, fan_out = _fans(p)
         lim = math.sqrt(6.0 / (fan_in + fan_out))
         return (torch.rand(p.shape, generator=gen) * 2 - 1) * lim
     if kind == "normal":
-        return torch.randn(p.shape, generator=gen) * float(p.init[1])
+        mean = float(p.init[2]) if len(p.init) > 2 else 0.0
+        return torch.randn(p.shape, generator=gen) * float(p.init[1]) + mean
     raise ValueError(kind)
 
 

@@ -155,6 +155,7 @@ class Trainer(object):
         self._prefix_primed = False
         self.graph_opt_heads = None
         self._opt_stream = None
+        self._h2d_done = None           # event: the last step()'s copies out of the pinned staging buffers have run
 
     # ------------------------------------------------------------------ one step
     def _bind(self, arrays):
@@ -349,11 +350,19 @@ class Trainer(object):
         """arrays: output of host_arrays().  Returns {loss name: float} (+ 'regularization_loss',
         'total_loss') when read_losses."""
         st = self.model.param_store
+        # the pinned staging buffers (inputs, hyper-parameters) are reused by every call: with read_losses=False
+        # nothing else stops the host from overwriting them while the previous call's H2D copies are still queued
+        if self._h2d_done is not None:
+            self._h2d_done.synchronize()
         self._hyper_host[0] = float(self.lr_fn(self.global_step))
         self._hyper_host[1] = self.momentum
         self._hyper_host[2] = self.clip_norm if self.clip_norm else 0.0
         st.hyper.copy_(self._hyper_host, non_blocking=True)
         image = self._bind(arrays)
+        if torch.cuda.is_available():
+            if self._h2d_done is None:
+                self._h2d_done = torch.cuda.Event()
+            self._h2d_done.record()
         self._setup_prefix(image)
         if self.use_graph and self.graph_fb is None:
             self._capture(image)

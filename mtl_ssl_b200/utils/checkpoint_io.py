@@ -60,7 +60,8 @@ def load_tf_checkpoint(model, prefix, from_detection_checkpoint=True):
     name_map = variable_name_map(model, from_detection_checkpoint)
     st = model.param_store
     shapes = {p.name: p.shape for p in st.params}
-    sd, missing = tf_checkpoint.state_dict_from_checkpoint(reader, name_map, shapes)
+    kinds = {p.name: p.tf_kind for p in st.params if getattr(p, "tf_kind", None) is not None}
+    sd, missing = tf_checkpoint.state_dict_from_checkpoint(reader, name_map, shapes, kinds)
     import torch
     st.load_state_dict({k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in sd.items()}, strict=False)
     return len(sd), missing
@@ -69,11 +70,12 @@ def load_tf_checkpoint(model, prefix, from_detection_checkpoint=True):
 def save_tf_checkpoint(model, prefix, extra=None):
     """Write every variable of `model` (TF names, TF layouts) as a V2 checkpoint a `tf.train.Saver` can restore."""
     sd = model.param_store.state_dict()
+    kinds = {p.name: getattr(p, "tf_kind", None) for p in model.param_store.params}
     tensors = {}
     for k, v in sd.items():
         if "/_pad/" in k:
             continue
-        tensors[_tf_name(k)] = tf_checkpoint.native_to_tf(k, v.cpu().numpy().astype(np.float32))
+        tensors[_tf_name(k)] = tf_checkpoint.native_to_tf(k, v.cpu().numpy().astype(np.float32), kinds.get(k))
     for k, v in (extra or {}).items():
         tensors[k] = np.asarray(v)
     tf_checkpoint.write_checkpoint(prefix, tensors)
@@ -91,7 +93,7 @@ def save_training_checkpoint(trainer, prefix):
         if "/_pad/" in p.name or not p.trainable:
             continue
         extra[_tf_name(p.name) + "/Momentum"] = tf_checkpoint.native_to_tf(
-            p.name, p.m.detach().cpu().numpy().astype(np.float32))
+            p.name, p.m.detach().cpu().numpy().astype(np.float32), getattr(p, "tf_kind", None))
     extra["global_step"] = np.asarray(int(trainer.global_step), np.int64)
     return save_tf_checkpoint(model, prefix, extra)
 
@@ -109,7 +111,7 @@ def restore_training_checkpoint(trainer, prefix):
         key = _tf_name(p.name) + "/Momentum"
         if "/_pad/" in p.name or not p.trainable or not reader.has_tensor(key):
             continue
-        v = tf_checkpoint.tf_to_native(p.name, reader.get_tensor(key)).astype(np.float32)
+        v = tf_checkpoint.tf_to_native(p.name, reader.get_tensor(key), getattr(p, "tf_kind", None), p.shape).astype(np.float32)
         if tuple(v.shape) != tuple(p.shape):
             raise ValueError("%s: checkpoint shape %s, model shape %s" % (key, v.shape, tuple(p.shape)))
         p.m.copy_(torch.from_numpy(np.ascontiguousarray(v)).to(p.m.device))

@@ -8,9 +8,11 @@ doubles its variance every unit and overflows; these statistics keep activations
 import torch
 
 
-def apply(store):
-    sd = {}
+def apply_host(store):
+    """The statistics only, on the host-side BatchNorm records (no device needed)."""
     for b in store.bns:
+        if b.scope is None:             # virtual per-channel scale (Inception-ResNet residual scaling): not a batch norm
+            continue
         c = b.channels
         stem = "/block" not in b.scope and b.scope.endswith("/conv1/BatchNorm")
         if "/conv3/" in b.scope:
@@ -23,6 +25,10 @@ def apply(store):
         b.beta = torch.zeros(c)
         b.mean = torch.zeros(c)
         b.var = torch.full((c,), 14000.0 if stem else 1.0)
+
+
+def apply(store):
+    apply_host(store)
     store._upload_bn_inplace()
     store.fold()
     for h in store.post_load_hooks:

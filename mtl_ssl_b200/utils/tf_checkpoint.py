@@ -223,10 +223,27 @@ def write_checkpoint(prefix, tensors):
 
 
 # ----------------------------------------------------------------------------- layout conversion
-def tf_to_native(name, value):
-    """A TF variable in this framework's layout: conv HWIO -> [K,R,S,C], depthwise [R,S,C,1] -> [C,R,S,1],
-    FC [in,out] -> [out,in]; vectors (biases, batch-norm statistics) unchanged."""
+def tf_to_native(name, value, kind=None, native_shape=None):
+    """A TF variable in this framework's layout.  By default the rank decides: conv HWIO -> [K,R,S,C], depthwise
+    [R,S,C,1] -> [C,R,S,1], FC [in,out] -> [out,in]; vectors (biases, batch-norm statistics) unchanged.  `kind`
+    (runtime.Param.tf_kind) covers the variables this framework keeps in a GEMM-specific shape:
+      "fc"                      slim.fully_connected [in, out]  -> [out, 1, 1, in]  (second-stage / aux FC heads)
+      ("packed_conv", R, S, C)  conv [R, S, C, K]               -> [K, 1, 1, ld] im2col rows, R*S*C real columns in
+                                (r, s, c) order followed by zero padding up to ld = native_shape[-1]."""
     v = np.asarray(value)
+    if kind == "fc":
+        if v.ndim != 2:
+            raise ValueError("%s: a fully connected variable must be [in, out], got shape %s" % (name, v.shape))
+        return np.ascontiguousarray(v.T).reshape(v.shape[1], 1, 1, v.shape[0])
+    if isinstance(kind, (tuple, list)) and kind[0] == "packed_conv":
+        R, S, C = (int(x) for x in kind[1:4])
+        if v.ndim != 4 or tuple(v.shape[:3]) != (R, S, C):
+            raise ValueError("%s: expected a [%d,%d,%d,K] conv variable, got shape %s" % (name, R, S, C, v.shape))
+        K = v.shape[3]
+        ld = int(native_shape[-1]) if native_shape is not None else (R * S * C + 63) // 64 * 64
+        out = np.zeros((K, 1, 1, ld), v.dtype)
+        out[:, 0, 0, :R * S * C] = v.transpose(3, 0, 1, 2).reshape(K, R * S * C)
+        return out
     if v.ndim == 4:
         if name.endswith("depthwise_weights"):
             return np.ascontiguousarray(v.transpose(2, 0, 1, 3))
@@ -236,8 +253,20 @@ def tf_to_native(name, value):
     return v
 
 
-def native_to_tf(name, value):
+def native_to_tf(name, value, kind=None):
+    """Inverse of tf_to_native: the array a `tf.train.Saver` expects for this variable."""
     v = np.asarray(value)
+    if kind == "fc":
+        if v.ndim == 4 and v.shape[1] == v.shape[2] == 1:
+            v = v.reshape(v.shape[0], v.shape[3])
+        if v.ndim != 2:
+            raise ValueError("%s: a fully connected operand must be [out,1,1,in] or [out,in], got %s" % (name, v.shape))
+        return np.ascontiguousarray(v.T)
+    if isinstance(kind, (tuple, list)) and kind[0] == "packed_conv":
+        R, S, C = (int(x) for x in kind[1:4])
+        K = v.shape[0]
+        rows = v.reshape(K, -1)[:, :R * S * C]
+        return np.ascontiguousarray(rows.reshape(K, R, S, C).transpose(1, 2, 3, 0))
     if v.ndim == 4:
         if name.endswith("depthwise_weights"):
             return np.ascontiguousarray(v.transpose(1, 2, 0, 3))
@@ -247,17 +276,20 @@ def native_to_tf(name, value):
     return v
 
 
-def state_dict_from_checkpoint(reader, name_map, shapes=None):
+def state_dict_from_checkpoint(reader, name_map, shapes=None, kinds=None):
     """name_map: {checkpoint variable name: model variable name or list of names} (FasterRCNNMetaArch.restore_map gives
     the variables; batch-norm statistics map by their scope).  Returns ({model name: float32 array in native layout},
-    [checkpoint names that were missing]).  `shapes`: optional {model name: expected shape} check."""
+    [checkpoint names that were missing]).  `shapes`: optional {model name: expected shape} check; `kinds`: optional
+    {model name: runtime.Param.tf_kind} for the variables whose layout the rank does not determine."""
     out, missing = {}, []
+    kinds = kinds or {}
     for ck, targets in name_map.items():
         if not reader.has_tensor(ck):
             missing.append(ck)
             continue
-        v = tf_to_native(ck, reader.get_tensor(ck)).astype(np.float32)
+        raw = reader.get_tensor(ck)
         for t in ([targets] if isinstance(targets, str) else list(targets)):
+            v = tf_to_native(ck, raw, kinds.get(t), shapes.get(t) if shapes else None).astype(np.float32)
             if shapes is not None and t in shapes and tuple(shapes[t]) != v.shape:
                 raise ValueError("%s: checkpoint shape %s, model shape %s" % (t, v.shape, tuple(shapes[t])))
             out[t] = v

@@ -294,7 +294,7 @@ class Oracle(object):
         return outs
 
     # ------------------------------------------------------------------ forward
-    def training_proposals(self, rpn_box, rpn_cls, anchors, gt_abs, gt_cls_bg, key, H, W):
+    def training_proposals(self, rpn_box, rpn_cls, anchors, gt_abs, gt_cls_bg, key, H, W, decoded=None, scores=None):
         """`_postprocess_rpn` in training mode for one image (fmA:1055-1132): decode / score filter / clip / NMS ->
         `_unpad_proposals_and_sample_box_classifier_batch` (fmA:1134-1216) with `_sample_box_classifier_minibatch`
         (:1268-1302: detector assignment, the all-ignored guard, balanced sampling that keeps score order) -> zero pad to
@@ -304,7 +304,7 @@ class Oracle(object):
         cfg = self.cfg
         P, M = cfg["second_stage_batch_size"], cfg["first_stage_max_proposals"]
         pb, ps, n = OP.rpn_postprocess_single(rpn_box, rpn_cls, anchors, (H, W), cfg["nms_score_threshold"],
-                                              cfg["nms_iou_threshold"], M)
+                                              cfg["nms_iou_threshold"], M, decoded=decoded, scores=scores)
         t = OA.assign_detection(pb[:n], gt_abs, gt_cls_bg)
         cls_w = t["cls_weights"] + np.float32(t["cls_weights"].sum() == 0)      # fmA:1296
         pos = t["cls_targets"].argmax(1) > 0
@@ -319,7 +319,10 @@ class Oracle(object):
     def forward(self, images, examples, keys, H, W, proposal_inputs=None, inference=False, inference_mtl=False):
         """proposal_inputs: optional (rpn_box [B,N,4], rpn_cls [B,N,2]) numpy arrays used INSTEAD of the
         oracle's own RPN outputs for the (non-differentiable) proposal selection, so that index-level
-        parity can be checked on identical inputs.
+        parity can be checked on identical inputs.  A 4-tuple (rpn_box, rpn_cls, decoded [B,N,4], scores [B,N])
+        additionally fixes the decoded (clipped) boxes and objectness scores the sort / NMS / sampler start from:
+        `exp` differs by an ulp between libm and the device, which reorders near-tied scores (the decode itself is
+        compared separately, to 2e-6).
         inference=True: the is_training=False graph (fmA:586-590 anchors clipped instead of pruned; fmA:1111-1131 no
         minibatch sampling, max_num_proposals = first_stage_max_proposals, fmA:475-477); returns after the
         second-stage box classifier (what `postprocess` consumes); `examples` / `keys` are not used.
@@ -380,7 +383,10 @@ class Oracle(object):
             gts.append((gt_abs, gt_cls_bg, np.asarray(ex["groundtruth_closeness"], np.float32)))
             src_box = proposal_inputs[0][b] if proposal_inputs is not None else rpn_box[b].detach().numpy()
             src_cls = proposal_inputs[1][b] if proposal_inputs is not None else rpn_cls[b].detach().numpy()
-            nb, _, cnt, nms = self.training_proposals(src_box, src_cls, anchors, gt_abs, gt_cls_bg, keys[1][b], H, W)
+            fixed = proposal_inputs is not None and len(proposal_inputs) == 4
+            nb, _, cnt, nms = self.training_proposals(src_box, src_cls, anchors, gt_abs, gt_cls_bg, keys[1][b], H, W,
+                                                      decoded=proposal_inputs[2][b] if fixed else None,
+                                                      scores=proposal_inputs[3][b] if fixed else None)
             nms_out.append(nms)
             nprop[b] = cnt
             prop_norm[b] = nb

@@ -1,7 +1,13 @@
 """shape_buckets.ShapeBucketTrainer on a device: two image shapes alternate over ONE model (shared parameters, momenta and
 global_step; one workspace + CUDA graphs per shape) and reproduce the losses of plain single-shape trainers that hand the
-optimizer state from one to the next.  Written at the end of round 1 after the GPU budget was spent: this file sorts last
-so that its first run on a device cannot mask the established parity tests."""
+optimizer state from one to the next.
+
+Round-2 note (tools/debug_buckets.py on a B200): the first version of this test initialised the models WITHOUT
+normalised batch-norm statistics -- activations overflowed into losses of ~1e5, and the run-to-run noise of the fp32
+atomics in the backward pass, amplified by two chaotic update steps, made even two runs of the PLAIN trainer differ by
+1.5e-2 in `edgemask_loss` at the third step (0.6647 vs 0.6544), above this test's 2e-3 bar.  The bucket trainer itself
+was not at fault.  The models now start from `randomize_bn` statistics (losses O(1), as in tests/test_gpu_train_step.py)
+and the tolerance is tied to the measured noise of two plain runs."""
 import numpy as np
 import pytest
 import torch
@@ -12,7 +18,7 @@ pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900)]      # first run on a d
 @pytest.mark.parametrize("graph", [False, True])
 def test_two_shapes_share_one_model(graph):
     import test_gpu_train_step as T
-    from helpers import load_config
+    from helpers import load_config, randomize_bn
     from mtl_ssl_b200.builders import model_builder
     from mtl_ssl_b200.data import synthetic
     from mtl_ssl_b200.shape_buckets import ShapeBucketTrainer
@@ -27,23 +33,34 @@ def test_two_shapes_share_one_model(graph):
         ky = synthetic.make_sampler_keys(70 + i, 1, model.num_kept_anchors((1, hw[0], hw[1], 3)), M)
         return ex, ky
 
-    # ---- reference: a fresh model + plain eager trainer per step, parameters and momenta carried over by hand
-    want, state = [], None
-    for i, hw in enumerate(shapes):
+    def fresh_model():
         model = model_builder.build(cfg.model, True, device="cuda", seed=0)
-        st = model.param_store
-        if state is not None:
-            st.w.copy_(state[0]); st.m.copy_(state[1])
-            st.fold()
-        tr = Trainer(model, None, hw[0], hw[1], 1, use_cuda_graph=False, **kw)
-        tr.global_step = i
-        ex, ky = batch(model, i, hw)
-        want.append(tr.step(tr.host_arrays(ex, ky)))
-        torch.cuda.synchronize()
-        state = (st.w.clone(), st.m.clone())
-        del tr, model
+        model.param_store.load_state_dict(randomize_bn(model.param_store.state_dict(), 0))
+        return model
+
+    # ---- reference: a fresh model + plain eager trainer per step, parameters and momenta carried over by hand
+    def plain():
+        out, state = [], None
+        for i, hw in enumerate(shapes):
+            model = fresh_model()
+            st = model.param_store
+            if state is not None:
+                st.w.copy_(state[0]); st.m.copy_(state[1])
+                st.fold()
+            tr = Trainer(model, None, hw[0], hw[1], 1, use_cuda_graph=False, **kw)
+            tr.global_step = i
+            ex, ky = batch(model, i, hw)
+            out.append(tr.step(tr.host_arrays(ex, ky)))
+            torch.cuda.synchronize()
+            state = (st.w.clone(), st.m.clone())
+            del tr, model
+        return out, state
+
+    want, state = plain()
+    again, state2 = plain()             # run-to-run noise of the plain path (fp32 atomics in the backward pass)
+    noise = {k: max(abs(a[k] - b[k]) for a, b in zip(want, again)) for k in want[0]}
     # ---- one model, one bucket per shape
-    model = model_builder.build(cfg.model, True, device="cuda", seed=0)
+    model = fresh_model()
     bt = ShapeBucketTrainer(model, None, batch_size=1, max_buckets=4, use_cuda_graph=graph, **kw)
     got = []
     for i, hw in enumerate(shapes):
@@ -54,9 +71,17 @@ def test_two_shapes_share_one_model(graph):
     got.append(bt.flush())
     torch.cuda.synchronize()
     assert len(got) == 3 and bt.global_step == 3 and sorted(bt.buckets) == [(224, 288), (224, 320)]
+    assert all(abs(v) < 1e3 for v in want[0].values()), want[0]          # a well-conditioned start (see the note above)
     for a, b in zip(want, got):
         for k in a:
-            assert np.isfinite(b[k]) and abs(a[k] - b[k]) <= 2e-3 * max(1.0, abs(a[k])), (k, a[k], b[k])
+            assert np.isfinite(b[k]) and abs(a[k] - b[k]) <= max(2e-3 * max(1.0, abs(a[k])), 4 * noise[k]), \
+                (k, a[k], b[k], noise[k])
     assert abs(got[0]["total_loss"] - got[1]["total_loss"]) > 1e-4
     torch.testing.assert_close(model.param_store.w, state[0], rtol=0, atol=1e-5)
-    torch.testing.assert_close(model.param_store.m, state[1], rtol=1e-2, atol=1e-3)
+
+    def rel(a, b):
+        return float((a - b).norm() / b.norm().clamp_min(1e-20))
+
+    # the momenta are the (clipped) gradients: compared as a whole against the noise two plain runs show
+    assert rel(model.param_store.m, state[1]) <= max(4 * rel(state2[1], state[1]), 1e-3), \
+        (rel(model.param_store.m, state[1]), rel(state2[1], state[1]))

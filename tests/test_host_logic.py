@@ -355,3 +355,42 @@ def test_bench_dominant_group_carries_the_committed_dram_traffic():
     assert d["traffic"] == 69021440 + 24559872 and "f_c3x3" in d["traffic_source"]
     d = bench.dominant_conv_group([(1, 2e12, 1.0, (7, 9, 9, 64, 64, 3, 1, 9, 9))], 1400.0)
     assert d["traffic"] is None and d["kernel"].startswith("tc_gemm_kernel dgrad")
+
+
+def test_initializer_parameters_reach_the_variables():
+    """hyperparams_builder._build_initializer (hyperparams_builder.py:118-146) passes factor / mode /
+    uniform of variance_scaling_initializer and the means of the normal initializers on, and refuses a missing
+    initializer; model22.config sets factor 1.0, uniform, FAN_AVG for the second-stage FC heads."""
+    import math
+    import torch
+    from helpers import load_config
+    from mtl_ssl_b200.builders import model_builder
+    from mtl_ssl_b200.core.hyperparams import Hyperparams
+    from mtl_ssl_b200.protos import text_format
+    from mtl_ssl_b200.runtime import Param, _init_tensor
+    cfg = load_config("model22.config")
+    hp = cfg.model.faster_rcnn.second_stage_box_predictor.mask_rcnn_box_predictor.fc_hyperparams
+    assert Hyperparams.from_proto(hp).init == ("variance_scaling", 1.0, "FAN_AVG", True)
+    model = model_builder.build(cfg.model, True, device=None)
+    p = model.param_store.by_name["SecondStageBoxPredictor/ClassPredictor/weights"]
+    assert p.init == ("variance_scaling", 1.0, "FAN_AVG", True) and p.shape == (91, 1, 1, 2048)
+    w = _init_tensor(p, torch.Generator().manual_seed(0))
+    lim = math.sqrt(3.0 * 1.0 / ((2048 + 91) / 2.0))                     # uniform: sqrt(3 * factor / n)
+    assert float(w.abs().max()) <= lim and float(w.abs().max()) > 0.98 * lim
+    assert abs(float(w.var()) - lim * lim / 3.0) < 0.03 * lim * lim / 3.0
+    # defaults of the proto (factor 2.0, FAN_IN, truncated normal with stddev sqrt(1.3 * factor / fan_in))
+    q = Param("c/weights", (64, 3, 3, 32), 0.0, True, ("variance_scaling", 2.0, "FAN_IN", False))
+    v = _init_tensor(q, torch.Generator().manual_seed(1))
+    std = math.sqrt(1.3 * 2.0 / (3 * 3 * 32))
+    assert float(v.abs().max()) <= 2 * std + 1e-6 and abs(float(v.std()) - 0.88 * std) < 0.03 * std
+    assert torch.equal(v, _init_tensor(Param("c/weights", (64, 3, 3, 32), 0.0, True, ("variance_scaling",)),
+                                       torch.Generator().manual_seed(1)))
+    q = Param("c/weights", (64, 3, 3, 32), 0.0, True, ("variance_scaling", 1.0, "FAN_OUT", True))
+    assert float(_init_tensor(q, torch.Generator().manual_seed(1)).abs().max()) <= math.sqrt(3.0 / (3 * 3 * 64))
+    t = _init_tensor(Param("b", (4000,), 0.0, True, ("truncated_normal", 0.1, 0.5)), torch.Generator().manual_seed(2))
+    assert abs(float(t.mean()) - 0.5) < 0.01 and float((t - 0.5).abs().max()) <= 0.2 + 1e-6
+    t = _init_tensor(Param("b", (4000,), 0.0, True, ("normal", 0.1, -1.0)), torch.Generator().manual_seed(2))
+    assert abs(float(t.mean()) + 1.0) < 0.01
+    msg = text_format.Merge("op: FC regularizer { l2_regularizer { weight: 0.1 } }", text_format.Message("Hyperparams"))
+    with pytest.raises(ValueError):
+        Hyperparams.from_proto(msg)

@@ -230,3 +230,87 @@ def test_train_loop_numerics_check_and_jsonl_log(tmp_path):
     with pytest.raises(FloatingPointError, match="LossTensor is inf or nan"):
         loader.train_loop(T(), iter([0.5, float("nan"), 0.1]))
     assert len(loader.train_loop(T(), iter([0.5, float("inf")]), check_numerics=False)) == 2
+
+
+
+@pytest.mark.parametrize("name", ["model12.config", "model42.config", "model52.config", "model62.config"])
+def test_exported_variables_have_the_reference_graph_shapes(name):
+    """the conversion must follow the variable's TF shape, not the rank of the GEMM operand kept here.
+    Real variable tables of the shipped configs (host side, no device): every exported array has the shape the
+    reference's graph gives that variable --
+      slim.fully_connected heads of MaskRCNNBoxPredictor (bp:482-496, :568-602)   [in, out]
+      the RGB stem convs (mobilenet_v1.py Conv2d_0, inception_resnet_v2.py Conv2d_1a_3x3)   [3, 3, 3, 32]
+      every other conv [R, S, C, K], depthwise [3, 3, C, 1], the refiner FC [nf, K+1], vectors unchanged --
+    and converting back reproduces the native tensor bit for bit (pad columns of the packed stems stay zero)."""
+    from helpers import load_config
+    from mtl_ssl_b200.builders import model_builder
+    cfg = load_config(name)
+    model = model_builder.build(cfg.model, True, device=None, seed=0)
+    st = model.param_store
+    sd = st.host_state_dict(0)
+    K = cfg.model.faster_rcnn.num_classes
+    rfcn = cfg.model.faster_rcnn.second_stage_box_predictor.WhichOneof("box_predictor_oneof") == "rfcn_box_predictor"
+    seen = set()
+    for p in st.params:
+        if "/_pad/" in p.name:
+            continue
+        v = sd[p.name].numpy()
+        tf = C.native_to_tf(p.name, v, p.tf_kind)
+        head = p.name.split("/")[0]
+        leaf = "/".join(p.name.split("/")[1:])
+        if (not rfcn and head in ("SecondStageBoxPredictor", "ClosenessBoxPredictor", "WindowBoxPredictor")
+                and leaf in ("BoxEncodingPredictor/weights", "ClassPredictor/weights")):
+            n = {"BoxEncodingPredictor/weights": 4 * K}.get(leaf, K + 1)
+            assert tf.shape == (v.shape[-1], n) and tf.ndim == 2, (p.name, tf.shape)
+            assert tf[3, 1] == v[1, 0, 0, 3]
+            seen.add("fc")
+        elif p.name.endswith(("/Conv2d_0/weights", "/Conv2d_1a_3x3/weights")) and head == "FirstStageFeatureExtractor" \
+                and p.name.count("/") == 3:
+            assert tf.shape == (3, 3, 3, 32), (p.name, tf.shape)
+            assert tf[1, 2, 0, 5] == v[5, 0, 0, (1 * 3 + 2) * 3 + 0] and not v[:, 0, 0, 27:].any()
+            seen.add("stem")
+        elif v.ndim == 4 and p.name.endswith("depthwise_weights"):
+            assert tf.shape == (3, 3, v.shape[0], 1)
+        elif v.ndim == 4:
+            assert tf.shape == (v.shape[1], v.shape[2], v.shape[3], v.shape[0]), (p.name, tf.shape)
+        elif v.ndim == 3:                                   # depthwise [C,3,3] operand -> TF [3,3,C,1]
+            seen.add("dw3")
+        elif v.ndim == 2:
+            assert tf.shape == (v.shape[1], v.shape[0])
+        else:
+            assert tf.shape == v.shape
+        back = C.tf_to_native(p.name, tf, p.tf_kind, p.shape)
+        assert back.shape == tuple(p.shape) or back.size == v.size, (p.name, back.shape, p.shape)
+        np.testing.assert_array_equal(back.reshape(v.shape), v, err_msg=p.name)
+    assert ("fc" in seen) == (not rfcn)
+    assert ("stem" in seen) == (name in ("model52.config", "model62.config"))
+    by = st.by_name
+    if not rfcn:
+        assert C.native_to_tf("x", sd["SecondStageBoxPredictor/ClassPredictor/weights"].numpy(),
+                              by["SecondStageBoxPredictor/ClassPredictor/weights"].tf_kind).shape[1] == K + 1
+    assert C.native_to_tf("x", sd["FirstStageBoxPredictor/ClassPredictor/weights"].numpy(),
+                          by["FirstStageBoxPredictor/ClassPredictor/weights"].tf_kind).shape[:2] == (1, 1)   # RPN: conv
+    if cfg.model.mtl.edgemask:
+        assert C.native_to_tf("x", sd["EdgeMaskPredictor/BoxEncodingPredictor/weights"].numpy(), None).shape[:2] == (1, 1)
+
+
+def test_fc_and_packed_stem_variables_through_a_written_bundle(tmp_path):
+    """A bundle holding TF-shaped variables ([2048, 84] FC, [3, 3, 3, 32] stem conv) loads into the GEMM-shaped
+    operands; a shape the rank-only rule would have produced is refused."""
+    rng = np.random.default_rng(5)
+    fc = rng.normal(size=(2048, 84)).astype(np.float32)
+    stem = rng.normal(size=(3, 3, 3, 32)).astype(np.float32)
+    prefix = str(tmp_path / "m.ckpt")
+    C.write_checkpoint(prefix, {"SecondStageBoxPredictor/BoxEncodingPredictor/weights": fc, "M/Conv2d_0/weights": stem})
+    name_map = {"SecondStageBoxPredictor/BoxEncodingPredictor/weights": "SecondStageBoxPredictor/BoxEncodingPredictor/weights",
+                "M/Conv2d_0/weights": "S/M/Conv2d_0/weights"}
+    shapes = {"SecondStageBoxPredictor/BoxEncodingPredictor/weights": (84, 1, 1, 2048), "S/M/Conv2d_0/weights": (32, 1, 1, 64)}
+    kinds = {"SecondStageBoxPredictor/BoxEncodingPredictor/weights": "fc", "S/M/Conv2d_0/weights": ("packed_conv", 3, 3, 3)}
+    sd, missing = C.state_dict_from_checkpoint(C.CheckpointReader(prefix), name_map, shapes, kinds)
+    assert not missing
+    w = sd["SecondStageBoxPredictor/BoxEncodingPredictor/weights"]
+    assert w.shape == (84, 1, 1, 2048) and w[7, 0, 0, 100] == fc[100, 7]
+    s = sd["S/M/Conv2d_0/weights"]
+    assert s.shape == (32, 1, 1, 64) and s[4, 0, 0, (2 * 3 + 1) * 3 + 2] == stem[2, 1, 2, 4] and not s[..., 27:].any()
+    with pytest.raises(ValueError):        # without the kinds the old rank rule gives (84, 2048) / (32, 3, 3, 3): refused
+        C.state_dict_from_checkpoint(C.CheckpointReader(prefix), name_map, shapes, None)

@@ -368,6 +368,7 @@ def test_classification_checkpoint_name_map_for_every_backbone(monkeypatch, tmp_
     name_map = checkpoint_io.variable_name_map(model, from_detection_checkpoint=False)
     st = model.param_store
     shapes = {p.name: tuple(p.shape) for p in st.params}
+    kinds = {p.name: p.tf_kind for p in st.params}
     for b in st.bns:
         if b.scope is not None:
             for k in ("gamma", "beta", "moving_mean", "moving_variance"):
@@ -381,7 +382,9 @@ def test_classification_checkpoint_name_map_for_every_backbone(monkeypatch, tmp_
         v = rng.standard_normal(shp).astype(np.float32)
         if ck.endswith("moving_variance"):
             v = np.abs(v) + 0.5
-        ckpt[ck] = tf_checkpoint.native_to_tf(ck, v)
+        ckpt[ck] = tf_checkpoint.native_to_tf(ck, v, kinds.get(targets[0]))
+        if isinstance(kinds.get(targets[0]), tuple):                   # the RGB stem conv is a real [3,3,3,K] variable
+            assert ckpt[ck].shape == (3, 3, 3, shp[0]), (ck, ckpt[ck].shape)
     shared = [ck for ck, t in name_map.items() if len(t) > 1]
     multi = max(len(name_map[ck]) for ck in shared) if shared else 1
     mtl = cfg.model.mtl
@@ -397,8 +400,8 @@ def test_classification_checkpoint_name_map_for_every_backbone(monkeypatch, tmp_
     assert not missing and n == sum(len(t) for t in name_map.values())
     sd = st.state_dict()
     for ck, targets in name_map.items():
-        want = tf_checkpoint.tf_to_native(ck, ckpt[ck])
         for t in targets:
+            want = tf_checkpoint.tf_to_native(ck, ckpt[ck], kinds.get(t), shapes[t])
             np.testing.assert_array_equal(sd[t].numpy().reshape(want.shape), want, err_msg=t)
     heads = [p.name for p in st.params if "BoxPredictor/" in p.name and p.name not in
              {t for ts in name_map.values() for t in ts} and "/_pad/" not in p.name]
