@@ -422,6 +422,19 @@ def run_ours(args, rank, world, local_rank):
         dominant = dominant_conv_group([(m, f, a.elapsed_time(b), g_) for m, f, a, b, g_ in prof], peak)
     except Exception as e:                                   # never lose the bench line over the breakdown
         dominant = {"error": repr(e)}
+    try:        # per-geometry table of the serialised pass (developer aid; summarised under profiles/)
+        groups = {}
+        for m, f, a, b, g_ in prof:
+            k = "%s N%d %dx%d C%d->K%d %dx%d/%d" % (("fprop", "dgrad", "wgrad")[m], g_[0], g_[1], g_[2], g_[3], g_[4], g_[5],
+                                                   g_[5], g_[6])
+            d = groups.setdefault(k, [0, 0.0, 0.0])
+            d[0] += 1; d[1] += a.elapsed_time(b) * 1e3; d[2] += f
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", "layers_%s.json" % args.config), "w") as fh:
+            json.dump({k: {"launches": v[0], "us": v[1], "tflops": v[2] / v[1] / 1e6} for k, v in groups.items()}, fh,
+                      indent=1)
+    except Exception:
+        pass
     images = B * world * args.steps
     value = images / (ms_dev * 1e-3)
     e2e_value = images / (ms_e2e * 1e-3)

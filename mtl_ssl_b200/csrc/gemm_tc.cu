@@ -68,6 +68,7 @@ struct Params {
   int max_ctas;              // host-side: grid cap (0 = number of SMs)
   float* ws;                 // FPROP/DGRAD split-K: fp32 partial-sum tiles [tiles_m*tiles_n][BN/4][BM][4], all zero between launches
   int* ws_cnt;               // FPROP/DGRAD split-K: arrival counter per output tile, zero between launches
+  int nprod;                 // TMA producer threads (1..3), K steps round-robin
 };
 
 // ----------------------------------------------------------------------------- PTX helpers
@@ -375,11 +376,21 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   };
 
-  if (warp == 0) {
-    // ============================ TMA producer (one thread) ============================
-    if (lane == 0) {
-      int s = 0;
-      uint32_t ph = 0;
+  if (warp == 0 || warp == 2 || warp == 3) {
+    // ============================ TMA producers (one thread in each of up to three warps) ====
+    // One K step of DGRAD / WGRAD issues five or six TMA loads (the MN-major operand arrives in 64-column boxes);
+    // with a single issuing thread those steps took longer than the 512 cycles their four MMAs need (measured on
+    // B200, profiles/r2_kloop.md: dgrad 3x3 on 256 ROI tiles 79 -> 61 us, wgrad 86 -> 63 us with two producers;
+    // FPROP, two loads per step, gains 5-15 %; a third producer adds nothing).  The otherwise idle warps 2 and 3
+    // join warp 0 and take the K steps round-robin: step g of this CTA belongs to producer g % NPROD, lives in stage
+    // g % STAGES and is signalled on that stage's barrier, so no ordering between the producers is needed.
+    const int NPROD = p.nprod;
+    const int prod = warp == 0 ? 0 : warp - 1;
+    if (lane == 0 && prod < NPROD) {
+      int g = prod;                 // CTA-wide index of the next K step this producer issues
+      int G0 = 0;                   // CTA-wide index of the current tile's first K step
+      int s = prod;                 // g % STAGES (STAGES >= 3 = NPROD)
+      uint32_t ph = 0;              // (g / STAGES) & 1
       constexpr uint32_t tx_bytes =
           (GATHER_A ? 0u : (uint32_t)A_STAGE_BYTES) + (GATHER_B ? 0u : (uint32_t)C::B_STAGE_BYTES);
       for (int tile = t_begin; tile < t_end; tile += t_step) {
@@ -388,6 +399,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (CL == 2 && m_tile >= p.tiles_m) m_tile = p.tiles_m - 1;     // padding tile of an odd pair
         const int m0 = m_tile * BM;
         const int kb = split * ips, ke = min(kb + ips, p.k_iters);
+        int k = kb + (g - G0);      // this producer's first K step inside the tile
+        G0 += ke - kb;
+        if (k >= ke) continue;
         int tn0 = 0, tp0 = 0, tq0 = 0;      // (n, p, q) of the tile's first row (im2col TMA base pixel)
         if (MODE != WGRAD && p.im2col) {
           tn0 = fast_div(m0, p.div_ohw);
@@ -395,26 +409,28 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tp0 = fast_div(r2, p.div_ow);
           tq0 = r2 - tp0 * p.oW;
         }
-        // The issue loop is the critical path of the short trunk GEMMs (one thread, dependent integer
-        // chains): every coordinate is carried incrementally, no division inside the K loop.
+        // Coordinates are carried incrementally (no division inside the K loop), NPROD steps at a time.
         if (MODE == FPROP || MODE == DGRAD) {
-          int tap = 0, chunk = kb;
-          if (kb >= p.cpt) { tap = kb / p.cpt; chunk = kb - tap * p.cpt; }
+          int tap = 0, chunk = k;
+          if (k >= p.cpt) { tap = k / p.cpt; chunk = k - tap * p.cpt; }
           int fr = 0, fs = tap;
           if (tap >= p.S) { fr = tap / p.S; fs = tap - fr * p.S; }
           const int ntap = (MODE == FPROP) ? p.gC : p.ntot;    // B-matrix columns per filter tap
           int acol = chunk * BK;
           int bbase = tap * ntap + (MODE == FPROP ? 0 : n_tile * BN);
-          int offh = (MODE == FPROP ? fr : p.R - 1 - fr) * p.dil;
-          int offw = (MODE == FPROP ? fs : p.S - 1 - fs) * p.dil;
           const int bw = tq0 + p.im_low_w, bh = tp0 + p.im_low_h, n0 = n_tile * BN;
-          for (int k = kb; k < ke; ++k) {
+          for (; k < ke; k += NPROD, g += NPROD) {
             mbar_wait(empty_bar(s), ph ^ 1u);
             const uint32_t fb = full_bar(s), sa = stage_a(s);
             mbar_arrive_expect_tx(fb, tx_bytes);
             if (!GATHER_A) {
-              if (p.im2col) tma_load_im2col(sa, &tmA, fb, acol, bw, bh, tn0, offw, offh);
-              else tma_load_2d(sa, &tmA, fb, acol, m0);
+              if (p.im2col) {
+                const int offh = (MODE == FPROP ? fr : p.R - 1 - fr) * p.dil;
+                const int offw = (MODE == FPROP ? fs : p.S - 1 - fs) * p.dil;
+                tma_load_im2col(sa, &tmA, fb, acol, bw, bh, tn0, offw, offh);
+              } else {
+                tma_load_2d(sa, &tmA, fb, acol, m0);
+              }
             }
             if (CL == 2) {
               // this CTA's half of the weight tile, delivered to both CTAs of the pair
@@ -435,21 +451,22 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               for (int j = 0; j < BN / 64; ++j)
                 tma_load_2d(sa + A_STAGE_BYTES + j * 8192, &tmB, fb, bbase + j * 64, acol);
             }
-            acol += BK;
-            if (++chunk == p.cpt) {
-              chunk = 0; acol = 0; bbase += ntap;
-              if (++fs == p.S) { fs = 0; ++fr; }
-              offh = (MODE == FPROP ? fr : p.R - 1 - fr) * p.dil;
-              offw = (MODE == FPROP ? fs : p.S - 1 - fs) * p.dil;
+            for (int j = 0; j < NPROD; ++j) {
+              acol += BK;
+              if (++chunk == p.cpt) {
+                chunk = 0; acol = 0; bbase += ntap;
+                if (++fs == p.S) { fs = 0; ++fr; }
+              }
             }
-            if (++s == STAGES) { s = 0; ph ^= 1u; }
+            s += NPROD;
+            if (s >= STAGES) { s -= STAGES; ph ^= 1u; }
           }
         } else {
           const int nper = (p.ntot + BN - 1) / BN;   // n-tiles per tap
           const int tap = n_tile / nper;
           const int ci0 = (n_tile - tap * nper) * BN;
           const int fr = tap / p.S, fs = tap - fr * p.S;
-          for (int k = kb; k < ke; ++k) {
+          for (; k < ke; k += NPROD, g += NPROD) {
             mbar_wait(empty_bar(s), ph ^ 1u);
             const uint32_t fb = full_bar(s), sa = stage_a(s);
             mbar_arrive_expect_tx(fb, tx_bytes);
@@ -472,7 +489,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                   tma_load_2d(sa + A_STAGE_BYTES + j * 8192, &tmB, fb, ci0 + j * 64, p0);
               }
             }
-            if (++s == STAGES) { s = 0; ph ^= 1u; }
+            s += NPROD;
+            if (s >= STAGES) { s -= STAGES; ph ^= 1u; }
           }
         }
       }
@@ -487,6 +505,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t tcount = 0;
       int s = 0;
       uint32_t ph = 0;
+      // The issue loop of this one thread bounds every K step (measured: 0.28 us per step whatever the tile width and
+      // with the operand loads switched off, profiles/r2_kloop.md), so it carries no address arithmetic: the low word
+      // of a shared-memory descriptor is (address >> 4) | LBO << 16 and all stage / K-slice addresses are below
+      // 256 KB, i.e. advancing a descriptor is a 32-bit add on its low word; the high word (SBO, version, 128-byte
+      // swizzle) never changes.
+      constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
+      constexpr uint32_t KS_A = (A_MN ? 2048u : 32u) >> 4, KS_B = (B_MN ? 2048u : 32u) >> 4;
+      const uint32_t sstep = (uint32_t)C::STAGE_BYTES >> 4;
+      const uint32_t lo_a0 = ((stage_a(0) >> 4) & 0x3fffu) | ((A_MN ? (8192u >> 4) : 1u) << 16);
+      const uint32_t lo_b0 = ((stage_b(0) >> 4) & 0x3fffu) | ((B_MN ? (8192u >> 4) : 1u) << 16);
+      uint32_t lo_a = lo_a0, lo_b = lo_b0;
+      auto desc = [&](uint32_t lo) { return (static_cast<uint64_t>(DESC_HI) << 32) | lo; };
       for (int tile = t_begin; tile < t_end; tile += t_step, ++tcount) {
         int split, m_tile_, n_tile_;
         tile_coords(tile, split, m_tile_, n_tile_);
@@ -495,21 +525,20 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_wait(tempty_bar(acc), aph ^ 1u);
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
+        uint32_t accum = 0u;
         for (int k = kb; k < ke; ++k) {
           mbar_wait(full_bar(s), ph);
           tcgen05_fence_after();
+          tcgen05_mma_bf16(tmem_d, desc(lo_a), desc(lo_b), idesc, accum);
+          accum = 1u;
 #pragma unroll
-          for (int ks = 0; ks < BK / 16; ++ks) {
-            const uint64_t da = A_MN ? umma_desc(stage_a(s) + ks * 2048, 8192, 1024)
-                                     : umma_desc(stage_a(s) + ks * 32, 16, 1024);
-            const uint64_t db = B_MN ? umma_desc(stage_b(s) + ks * 2048, 8192, 1024)
-                                     : umma_desc(stage_b(s) + ks * 32, 16, 1024);
-            tcgen05_mma_bf16(tmem_d, da, db, idesc, (k > kb || ks > 0) ? 1u : 0u);
-          }
+          for (uint32_t ks = 1; ks < BK / 16; ++ks)
+            tcgen05_mma_bf16(tmem_d, desc(lo_a + ks * KS_A), desc(lo_b + ks * KS_B), idesc, 1u);
           // frees the smem stage when these MMAs retire (in both CTAs of a pair: the peer multicasts into it)
           if (CL == 2) tcgen05_commit_mc2(empty_bar(s));
           else tcgen05_commit(empty_bar(s));
-          if (++s == STAGES) { s = 0; ph ^= 1u; }
+          lo_a += sstep; lo_b += sstep;
+          if (++s == STAGES) { s = 0; ph ^= 1u; lo_a = lo_a0; lo_b = lo_b0; }
         }
         tcgen05_commit(tfull_bar(acc));     // accumulator ready for the epilogue
       }
@@ -1386,6 +1415,8 @@ extern "C" int mtl_conv_tc(const mtl_conv_args* a, cudaStream_t stream) {
   p.out = a->out; p.out_fp32 = a->out_fp32; p.bias = a->bias; p.rowscale = a->rowscale;
   p.res = a->res; p.res_fp32 = a->res_fp32; p.mask = reinterpret_cast<const bf16*>(a->mask);
   p.relu = a->relu; p.mask_hi = a->mask_hi; p.alpha = a->alpha;
+  static const int nprod_env = getenv("MTL_NPROD") ? atoi(getenv("MTL_NPROD")) : 2;
+  p.nprod = nprod_env < 1 ? 1 : (nprod_env > 3 ? 3 : nprod_env);
   p.bias_scale = a->bias_scale != 0.0f ? a->bias_scale : 1.0f; p.splits = 1; p.cluster = 1; p.max_ctas = a->max_ctas; p.taps = a->R * a->S;
   CUtensorMap tmA, tmB;
   memset(&tmA, 0, sizeof(tmA)); memset(&tmB, 0, sizeof(tmB));

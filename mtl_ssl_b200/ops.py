@@ -99,7 +99,23 @@ def _conv(c, v):
     raise ValueError(c)
 
 
+# tools/timeline.py sets this to a list: (kernel name, stream handle, start event, end event, 0.0) per call
+TIMELINE = None
+
+
 def call(name, *args, stream=None):
+    if TIMELINE is not None and stream is None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s = torch.cuda.current_stream()
+        e0.record(s)
+        _call(name, args, s.cuda_stream)
+        e1.record(s)
+        TIMELINE.append((name, s.cuda_stream, e0, e1, 0.0))
+        return
+    _call(name, args, stream)
+
+
+def _call(name, args, stream):
     sig = _SIGS[name]
     if len(args) != len(sig):
         raise TypeError("%s expects %d arguments, got %d" % (name, len(sig), len(args)))

@@ -17,7 +17,20 @@ FPROP, DGRAD, WGRAD = 0, 1, 2
 PROFILE = None
 
 
+# tools/timeline.py sets this to a list: (label, stream handle, start event, end event) per launch, any stream
+TIMELINE = None
+
+
 def _launch(a, what):
+    if TIMELINE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s = torch.cuda.current_stream()
+        e0.record(s)
+        check(lib().mtl_conv_tc(ctypes.byref(a), cur_stream()), what)
+        e1.record(s)
+        TIMELINE.append(("conv%d N%d %dx%d C%d K%d R%d s%d" % (a.mode, a.N, a.H, a.W, a.C, a.K, a.R, a.stride),
+                         s.cuda_stream, e0, e1, 2.0 * a.N * a.P * a.Q * a.K * a.R * a.S * a.C))
+        return
     if PROFILE is None:
         check(lib().mtl_conv_tc(ctypes.byref(a), cur_stream()), what)
         return

@@ -72,9 +72,26 @@ def pairs():
     sweep("fprop", 1, 150, 250, 64, 256, 1, 1, c)
 
 
+def kloop():
+    """Per-K-iteration cost of the operand pipeline at the trunk's row count (M = 2394): time against the K depth for each
+    tile width (slope = cost of one 64-deep K step, intercept = launch + fill + drain), and against the stage count."""
+    T = (1, 38, 63)
+    for bn in (64, 128, 256):
+        for C in (256, 512, 1024, 2048, 4096):
+            sweep("fprop", *T, C, 256, 1, 0, [(bn, 1, 0)])
+    for bn in (64, 128, 256):
+        sweep("fprop", *T, 1024, 256, 1, 0, [(bn, 1, st) for st in ((3, 4, 6, 8) if bn < 256 else (3, 4))])
+        sweep("fprop", *T, 256, 256, 3, 0, [(bn, 1, st) for st in ((3, 4, 6, 8) if bn < 256 else (3, 4))])
+    # wide output, short K (block3 conv3): drain-bound side
+    for bn in (64, 128, 256):
+        sweep("fprop", *T, 256, 1024, 1, 1, [(bn, 1, 0)])
+
+
 def main():
     if len(sys.argv) > 1 and sys.argv[1] == "pairs":
         return pairs()
+    if len(sys.argv) > 1 and sys.argv[1] == "kloop":
+        return kloop()
     T = (1, 38, 63)
     # trunk block3 (M = 2394): default vs split-K
     trunk_cfg = [(0, 1, 0), (64, 1, 0), (64, 2, 0), (128, 2, 0), (128, 3, 0), (128, 4, 0), (256, 2, 0), (256, 4, 0), (256, 7, 0)]
