@@ -316,13 +316,8 @@ def run_ours(args, rank, world, local_rank):
     st = model.param_store
     snap = (st.w.clone(), st.m.clone(), st.wb.clone())
     c0 = ops.launch_count()
-    tr._prefix(tr.inputs.dev["image"])                      # frozen conv1 + block1 (pipelined one step ahead)
-    tr._forward_backward(tr.inputs.dev["image"])            # (one replica: includes the head bucket's update)
-    if world > 1:
-        if tr.overlap_optimizer:
-            tr._optimize_heads()
-        tr._backward_trunk()
-    tr._optimize()
+    tr.finish()
+    tr.eager_pass()                                         # prefix + forward + backward + both optimizer buckets
     c1 = ops.launch_count()
     launches_per_step = c1 - c0
     torch.cuda.synchronize()
@@ -383,25 +378,20 @@ def run_ours(args, rank, world, local_rank):
     # off for this pass (overlapping kernels share SMs and would inflate each other's duration), (b) a spin
     # kernel keeps the GPU busy while Python enqueues the step, so no event pair contains host launch latency.
     from mtl_ssl_b200.nets.layers import Concurrency
-    Concurrency.enabled = False
-    overlap, tr.overlap_optimizer = tr.overlap_optimizer, False      # keep the optimizer out of the conv timings
-    tr._prefix(tr.inputs.dev["image"])
-    tr._forward_backward(tr.inputs.dev["image"])            # re-warm the single-stream path
-    if world > 1:
-        tr._backward_trunk()
-    model.param_store.g.zero_()
+    tr.finish()
+    Concurrency.enabled = False                             # every launch of the pass on one stream
+    snap = (st.w.clone(), st.m.clone(), st.wb.clone())
+    tr.eager_pass()                                         # re-warm the single-stream path
     torch.cuda.synchronize()
     ops_conv.PROFILE = []
     torch.cuda._sleep(int(60e-3 * 1.9e9))                   # ~60 ms head start for the host
-    tr._prefix(tr.inputs.dev["image"])
-    tr._forward_backward(tr.inputs.dev["image"])
-    if world > 1:
-        tr._backward_trunk()
+    tr.eager_pass()
     torch.cuda.synchronize()
     prof, ops_conv.PROFILE = ops_conv.PROFILE, None
     Concurrency.enabled = True
-    tr.overlap_optimizer = overlap
+    st.w.copy_(snap[0]); st.m.copy_(snap[1]); st.wb.copy_(snap[2])
     model.param_store.g.zero_()
+    del snap
     conv_ms = sum(p_[2].elapsed_time(p_[3]) for p_ in prof)
     conv_flops = sum(p_[1] for p_ in prof)
     by_mode = {}
@@ -480,6 +470,7 @@ def run_ours(args, rank, world, local_rank):
         # ---- loss parity + CPU baseline: both arms start from the same weights (sd0) and use the same first batch
         threads = os.cpu_count() or 1
         ref = CpuReference(args.config, threads)
+        tr.finish()
         st.load_state_dict(sd0)
         st.m.zero_(); st.g.zero_()
         tr.overlap_optimizer = False

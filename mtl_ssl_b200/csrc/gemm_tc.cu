@@ -71,6 +71,15 @@ struct Params {
   int nprod;                 // TMA producer threads (1..3), K steps round-robin
 };
 
+// One problem of a grouped launch (see mtl_conv_tc_group_*): its tensor maps, parameters and the first CTA-wide tile
+// index it owns.  The array lives in global memory; TMA takes the maps by their (64-byte aligned) global address.
+struct alignas(128) GroupEntry {
+  CUtensorMap tmA, tmB, tmO, tmR, tmM;
+  Params p;
+  int tile_begin;            // first tile id of this problem in the concatenated tile space of the group
+  int tiles;                 // its tile count (tiles_m * tiles_n * splits)
+};
+
 // ----------------------------------------------------------------------------- PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -271,9 +280,13 @@ template <int MODE, int BN, bool GATHER, int CL>
 __global__ void __launch_bounds__(384, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR,
-               const __grid_constant__ CUtensorMap tmM, const Params p) {
+               const __grid_constant__ CUtensorMap tmM, const __grid_constant__ Params p0,
+               const GroupEntry* __restrict__ grp, const int ngrp) {
+  // grp == nullptr: one problem, described by the kernel parameters.  Otherwise a grouped launch: `ngrp` independent
+  // problems of the same kernel instance and shared-memory carve share one persistent grid; the CTA-wide tile index
+  // runs over the concatenation of their tile spaces (tile t belongs to CTA t % gridDim.x), p0 = the first problem.
   using C = Cfg<BN>;
-  const int STAGES = p.stages;
+  const int STAGES = p0.stages;
   constexpr bool A_MN = (MODE == WGRAD);
   constexpr bool B_MN = (MODE != FPROP);
   // which operand the gather warps stage (the other always comes by TMA)
@@ -288,7 +301,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t epi_base = smem_base + STAGES * C::STAGE_BYTES;
-  const uint32_t bar_base = epi_base + (uint32_t)(4 * EPI_GROUPS) * (uint32_t)p.epi_warp_bytes;
+  const uint32_t bar_base = epi_base + (uint32_t)(4 * EPI_GROUPS) * (uint32_t)p0.epi_warp_bytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (MAX_STAGES + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * MAX_STAGES + a); };
@@ -305,10 +318,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (threadIdx.x == 32) {      // descriptors are kernel parameters: fetch them while the previous kernel drains
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
-    if (p.epi_tma) {
+    if (p0.epi_tma && !grp) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmO)) : "memory");
-      if (p.res) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmR)) : "memory");
-      if (p.mask) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmM)) : "memory");
+      if (p0.res) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmR)) : "memory");
+      if (p0.mask) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmM)) : "memory");
     }
   }
   {
@@ -345,35 +358,49 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
 
-  const int tiles_mn = p.tiles_m * p.tiles_n;
-  const int total_tiles = tiles_mn * p.splits;
-  const int ips = (p.k_iters + p.splits - 1) / p.splits;   // K iterations per split
-  // tile id -> (split, output tile): WGRAD walks all output tiles of one split first; FPROP/DGRAD keep
-  // the splits of one output tile adjacent so that their partial sums meet in L2 at about the same time
   uint32_t cta_rank = 0;
   if (CL == 2) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
-  // CL == 2: clusters walk (pair of m-tiles, n-tile); a pair's second m-tile may lie past the matrix (odd
-  // tile count): that CTA still takes part in the multicast protocol but loads a clamped tile and stores nothing
-  const int t_begin = CL == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-  const int t_step = CL == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-  const int t_end = CL == 2 ? ((p.tiles_m + 1) >> 1) * p.tiles_n : total_tiles;
-  auto decode_tile = [&](int tile, int& split, int& rem) {
-    if (MODE == WGRAD) { split = tile / tiles_mn; rem = tile - split * tiles_mn; }
-    else if (p.splits == 1) { split = 0; rem = tile; }
-    else { rem = tile / p.splits; split = tile - rem * p.splits; }
-  };
-  auto tile_coords = [&](int tile, int& split, int& m_tile, int& n_tile) {
-    if (CL == 2) {
-      split = 0;
-      const int mp = tile / p.tiles_n;
-      n_tile = tile - mp * p.tiles_n;
-      m_tile = 2 * mp + (int)cta_rank;
-    } else {
-      int rem;
-      decode_tile(tile, split, rem);
-      m_tile = rem / p.tiles_n;
-      n_tile = rem - m_tile * p.tiles_n;
-    }
+  const int ngj = grp ? ngrp : 1;
+  // Per-problem view of a role's tile loop.  `p` is a by-value copy (only the fields a role touches are loaded, once
+  // per problem); tile id -> (split, output tile): WGRAD walks all output tiles of one split first; FPROP/DGRAD keep
+  // the splits of one output tile adjacent so that their partial sums meet in L2 at about the same time.
+  // CL == 2: clusters walk (pair of m-tiles, n-tile); a pair's second m-tile may lie past the matrix (odd tile
+  // count): that CTA still takes part in the multicast protocol but loads a clamped tile and stores nothing.
+#define TC_PROBLEM_SETUP(gj)                                                                                          \
+  const Params* const pp_ = grp ? &grp[gj].p : &p0;                                                                   \
+  const Params p = *pp_;                                                                                              \
+  const CUtensorMap* const tmA_p = grp ? &grp[gj].tmA : &tmA;                                                         \
+  const CUtensorMap* const tmB_p = grp ? &grp[gj].tmB : &tmB;                                                         \
+  const CUtensorMap* const tmO_p = grp ? &grp[gj].tmO : &tmO;                                                         \
+  const CUtensorMap* const tmR_p = grp ? &grp[gj].tmR : &tmR;                                                         \
+  const CUtensorMap* const tmM_p = grp ? &grp[gj].tmM : &tmM;                                                         \
+  (void)tmA_p; (void)tmB_p; (void)tmO_p; (void)tmR_p; (void)tmM_p;                                                    \
+  const int tiles_mn = p.tiles_m * p.tiles_n;                                                                         \
+  const int total_tiles = tiles_mn * p.splits;                                                                        \
+  const int ips = (p.k_iters + p.splits - 1) / p.splits;   /* K iterations per split */                               \
+  const int gsz_ = (int)gridDim.x;                                                                                    \
+  const int t_begin = CL == 2 ? (int)(blockIdx.x >> 1)                                                                \
+                              : (grp ? (((int)blockIdx.x - grp[gj].tile_begin) % gsz_ + gsz_) % gsz_ : (int)blockIdx.x); \
+  const int t_step = CL == 2 ? (int)(gridDim.x >> 1) : gsz_;                                                          \
+  const int t_end = CL == 2 ? ((p.tiles_m + 1) >> 1) * p.tiles_n : total_tiles;                                       \
+  (void)ips; (void)t_begin; (void)t_step; (void)t_end;                                                                \
+  auto decode_tile = [&](int tile, int& split, int& rem) {                                                            \
+    if (MODE == WGRAD) { split = tile / tiles_mn; rem = tile - split * tiles_mn; }                                    \
+    else if (p.splits == 1) { split = 0; rem = tile; }                                                                \
+    else { rem = tile / p.splits; split = tile - rem * p.splits; }                                                    \
+  };                                                                                                                  \
+  auto tile_coords = [&](int tile, int& split, int& m_tile, int& n_tile) {                                            \
+    if (CL == 2) {                                                                                                    \
+      split = 0;                                                                                                      \
+      const int mp = tile / p.tiles_n;                                                                                \
+      n_tile = tile - mp * p.tiles_n;                                                                                 \
+      m_tile = 2 * mp + (int)cta_rank;                                                                                \
+    } else {                                                                                                          \
+      int rem;                                                                                                        \
+      decode_tile(tile, split, rem);                                                                                  \
+      m_tile = rem / p.tiles_n;                                                                                       \
+      n_tile = rem - m_tile * p.tiles_n;                                                                              \
+    }                                                                                                                 \
   };
 
   if (warp == 0 || warp == 2 || warp == 3) {
@@ -384,7 +411,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // FPROP, two loads per step, gains 5-15 %; a third producer adds nothing).  The otherwise idle warps 2 and 3
     // join warp 0 and take the K steps round-robin: step g of this CTA belongs to producer g % NPROD, lives in stage
     // g % STAGES and is signalled on that stage's barrier, so no ordering between the producers is needed.
-    const int NPROD = p.nprod;
+    const int NPROD = p0.nprod;
     const int prod = warp == 0 ? 0 : warp - 1;
     if (lane == 0 && prod < NPROD) {
       int g = prod;                 // CTA-wide index of the next K step this producer issues
@@ -393,6 +420,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t ph = 0;              // (g / STAGES) & 1
       constexpr uint32_t tx_bytes =
           (GATHER_A ? 0u : (uint32_t)A_STAGE_BYTES) + (GATHER_B ? 0u : (uint32_t)C::B_STAGE_BYTES);
+      for (int gj = 0; gj < ngj; ++gj) {
+      TC_PROBLEM_SETUP(gj)
       for (int tile = t_begin; tile < t_end; tile += t_step) {
         int split, m_tile, n_tile;
         tile_coords(tile, split, m_tile, n_tile);
@@ -427,29 +456,29 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               if (p.im2col) {
                 const int offh = (MODE == FPROP ? fr : p.R - 1 - fr) * p.dil;
                 const int offw = (MODE == FPROP ? fs : p.S - 1 - fs) * p.dil;
-                tma_load_im2col(sa, &tmA, fb, acol, bw, bh, tn0, offw, offh);
+                tma_load_im2col(sa, tmA_p, fb, acol, bw, bh, tn0, offw, offh);
               } else {
-                tma_load_2d(sa, &tmA, fb, acol, m0);
+                tma_load_2d(sa, tmA_p, fb, acol, m0);
               }
             }
             if (CL == 2) {
               // this CTA's half of the weight tile, delivered to both CTAs of the pair
               if (MODE == FPROP) {
-                tma_load_2d_mc(sa + A_STAGE_BYTES + cta_rank * (BN / 2) * 128, &tmB, fb, bbase + acol,
+                tma_load_2d_mc(sa + A_STAGE_BYTES + cta_rank * (BN / 2) * 128, tmB_p, fb, bbase + acol,
                                n0 + (int)cta_rank * (BN / 2), (uint16_t)3);
               } else {
 #pragma unroll
                 for (int jj = 0; jj < BN / 128; ++jj) {
                   const int j = (int)cta_rank * (BN / 128) + jj;
-                  tma_load_2d_mc(sa + A_STAGE_BYTES + j * 8192, &tmB, fb, bbase + j * 64, acol, (uint16_t)3);
+                  tma_load_2d_mc(sa + A_STAGE_BYTES + j * 8192, tmB_p, fb, bbase + j * 64, acol, (uint16_t)3);
                 }
               }
             } else if (MODE == FPROP) {
-              tma_load_2d(sa + A_STAGE_BYTES, &tmB, fb, bbase + acol, n0);
+              tma_load_2d(sa + A_STAGE_BYTES, tmB_p, fb, bbase + acol, n0);
             } else {
 #pragma unroll
               for (int j = 0; j < BN / 64; ++j)
-                tma_load_2d(sa + A_STAGE_BYTES + j * 8192, &tmB, fb, bbase + j * 64, acol);
+                tma_load_2d(sa + A_STAGE_BYTES + j * 8192, tmB_p, fb, bbase + j * 64, acol);
             }
             for (int j = 0; j < NPROD; ++j) {
               acol += BK;
@@ -471,8 +500,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint32_t fb = full_bar(s), sa = stage_a(s);
             mbar_arrive_expect_tx(fb, tx_bytes);
             const int p0 = k * BK;
-            tma_load_2d(sa, &tmA, fb, m0, p0);
-            tma_load_2d(sa + 8192, &tmA, fb, m0 + 64, p0);
+            tma_load_2d(sa, tmA_p, fb, m0, p0);
+            tma_load_2d(sa + 8192, tmA_p, fb, m0 + 64, p0);
             if (!GATHER_B) {
               if (p.im2col) {
                 const int pn = fast_div(p0, p.div_ohw);
@@ -481,18 +510,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int pq = r2 - pp * p.oW;
 #pragma unroll
                 for (int j = 0; j < BN / 64; ++j)
-                  tma_load_im2col(sa + A_STAGE_BYTES + j * 8192, &tmB, fb, ci0 + j * 64, pq + p.im_low_w,
+                  tma_load_im2col(sa + A_STAGE_BYTES + j * 8192, tmB_p, fb, ci0 + j * 64, pq + p.im_low_w,
                                   pp + p.im_low_h, pn, fs * p.dil, fr * p.dil);
               } else {
 #pragma unroll
                 for (int j = 0; j < BN / 64; ++j)
-                  tma_load_2d(sa + A_STAGE_BYTES + j * 8192, &tmB, fb, ci0 + j * 64, p0);
+                  tma_load_2d(sa + A_STAGE_BYTES + j * 8192, tmB_p, fb, ci0 + j * 64, p0);
               }
             }
             s += NPROD;
             if (s >= STAGES) { s -= STAGES; ph ^= 1u; }
           }
         }
+      }
       }
     }
   } else if (warp == 1) {
@@ -517,6 +547,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t lo_b0 = ((stage_b(0) >> 4) & 0x3fffu) | ((B_MN ? (8192u >> 4) : 1u) << 16);
       uint32_t lo_a = lo_a0, lo_b = lo_b0;
       auto desc = [&](uint32_t lo) { return (static_cast<uint64_t>(DESC_HI) << 32) | lo; };
+      for (int gj = 0; gj < ngj; ++gj) {
+      TC_PROBLEM_SETUP(gj)
       for (int tile = t_begin; tile < t_end; tile += t_step, ++tcount) {
         int split, m_tile_, n_tile_;
         tile_coords(tile, split, m_tile_, n_tile_);
@@ -542,6 +574,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         tcgen05_commit(tfull_bar(acc));     // accumulator ready for the epilogue
       }
+      }
     }
   } else if (warp >= 4 && (warp < 8 || !GATHER)) {
     // ============================ epilogue warps =======================================
@@ -558,14 +591,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // HBM round trip of a 500 MB residual stream never sits on the drain path.  Chunks are numbered
     // in processing order; chunk g lives in slot g % res_slots.  iq_* is the issue cursor, cq_slot /
     // slot_ph the consume cursor and the expected phase bit of every slot's barrier.
+    // (A grouped launch re-primes the ring at every problem: all its problems share the carve, i.e. the slot count
+    // and which of residual / mask exist, and the issue and consume cursors meet again at each problem's end.)
+    const uint32_t ebase = epi_base + (uint32_t)ew * (uint32_t)p0.epi_warp_bytes;
+    int iq_slot = 0, cq_slot = 0;
+    uint32_t slot_ph = 0;
+    for (int gj = 0; gj < ngj; ++gj) {
+    TC_PROBLEM_SETUP(gj)
     const int R = (MODE != WGRAD && p.epi_tma) ? p.res_slots : 0;
     const bool has_res = p.res != nullptr;
     const bool has_mask = p.mask != nullptr;
     const uint32_t slot_bytes = 2048u * ((has_res ? 1u : 0u) + (has_mask ? 1u : 0u));
-    const uint32_t ebase = epi_base + (uint32_t)ew * (uint32_t)p.epi_warp_bytes;
-    int iq_tile = t_begin, iq_c = 0, iq_slot = 0, iq_m0 = 0, iq_n0 = 0;
-    int cq_slot = 0;
-    uint32_t slot_ph = 0;
+    int iq_tile = t_begin, iq_c = 0, iq_m0 = 0, iq_n0 = 0;
     auto issue_next = [&](int cur_tile) {
       if (R == 0) return;
       if (p.splits > 1 && iq_tile != cur_tile) return;   // split-K: only the finishing CTA reads them
@@ -581,8 +618,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint32_t rb = res_bar(ew, iq_slot);
           const uint32_t dst = ebase + 4096u + (uint32_t)iq_slot * slot_bytes;
           mbar_arrive_expect_tx(rb, slot_bytes);
-          if (has_res) tma_load_2d(dst, &tmR, rb, n0, iq_m0);
-          if (has_mask) tma_load_2d(dst + (has_res ? 2048u : 0u), &tmM, rb, n0, iq_m0);
+          if (has_res) tma_load_2d(dst, tmR_p, rb, n0, iq_m0);
+          if (has_mask) tma_load_2d(dst + (has_res ? 2048u : 0u), tmM_p, rb, n0, iq_m0);
         }
       }
       if (++iq_c == CPW) { iq_c = 0; iq_tile += t_step; }
@@ -648,7 +685,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) {
-              tma_reduce_add_2d(&tmO, ebase, (int)(ncol0 + c * 32), m_tile * BM + quad * 32);
+              tma_reduce_add_2d(tmO_p, ebase, (int)(ncol0 + c * 32), m_tile * BM + quad * 32);
               bulk_commit();
             }
           }
@@ -826,7 +863,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           fence_proxy_async();
           __syncwarp();        // staging tile complete
           if (lane == 0) {
-            tma_store_2d(&tmO, ebase + buf * 2048u, (int)n0, m0w);
+            tma_store_2d(tmO_p, ebase + buf * 2048u, (int)n0, m0w);
             bulk_commit();
           }
           if (lane == 0) bulk_wait_read<1>();     // the other staging buffer has been read by its store
@@ -964,9 +1001,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tcgen05_fence_before();
       mbar_arrive(tempty_bar(acc));
     }
+    }
     // the staging tiles must have been read before the CTA's shared memory is released; the global writes
     // themselves complete before the grid does (and before a dependent grid's griddepcontrol.wait returns)
-    if (p.epi_tma && lane == 0) bulk_wait_read<0>();
+    if (p0.epi_tma && lane == 0) bulk_wait_read<0>();
   } else if (GATHER && warp >= 8) {
     // ============================ im2col gather warps ==================================
     // Each of the 128 threads owns one 128-byte row (FPROP/DGRAD: one output pixel of the A
@@ -977,9 +1015,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t pending_first = 0;    // oldest iteration whose full-barrier arrive is outstanding
     int s = 0, pf_s = 0;           // stage of iteration `it` / of iteration `pending_first`
     uint32_t ph = 0;
-    const int ohw = p.oH * p.oW;
     // The gather is on the critical path of every 3x3 / strided layer: all per-iteration index math
     // is strength-reduced (no divisions inside the K loop; row decode uses multiply-shift division).
+    for (int gj = 0; gj < ngj; ++gj) {
+    TC_PROBLEM_SETUP(gj)
+    const int ohw = p.oH * p.oW;
     for (int tile = t_begin; tile < t_end; tile += t_step) {
       int split, m_tile, n_tile;
       tile_coords(tile, split, m_tile, n_tile);
@@ -1101,6 +1141,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
+    }
     cp_async_wait<0>();
     fence_proxy_async();
     for (; pending_first < it; ++pending_first) {
@@ -1109,6 +1150,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   }
 
+#undef TC_PROBLEM_SETUP
   tcgen05_fence_before();
   if (CL == 2) cluster_sync_all();      // no CTA leaves while its peer may still signal or write into it
   else __syncthreads();
@@ -1209,7 +1251,8 @@ static int make_im2col_map(CUtensorMap* map, const void* base, int N, int H, int
 
 template <int MODE, int BN, bool GATHER, int CL>
 static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const CUtensorMap& tmR,
-                  const CUtensorMap& tmM, const Params& p, cudaStream_t stream) {
+                  const CUtensorMap& tmM, const Params& p, cudaStream_t stream, const GroupEntry* grp = nullptr,
+                  int ngrp = 0, int group_tiles = 0) {
   using C = Cfg<BN>;
   auto kern = tc_gemm_kernel<MODE, BN, GATHER, CL>;
   static bool attr_set = false;
@@ -1250,7 +1293,7 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensor
     const int clusters = pairs < max_clusters ? pairs : max_clusters;
     grid = 2 * clusters;
   } else {
-    const int total = p.tiles_m * p.tiles_n * p.splits;
+    const int total = grp ? group_tiles : p.tiles_m * p.tiles_n * p.splits;
     const int cap = (p.max_ctas > 0 && p.max_ctas < mtl_num_sms()) ? p.max_ctas : mtl_num_sms();
     grid = total < cap ? total : cap;
   }
@@ -1275,7 +1318,8 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensor
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  cudaError_t le = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmO, tmR, tmM, p);
+  if (CL == 2 && grp) { mtl_set_error("gemm_tc: grouped launches do not pair CTAs"); return MTL_ERR_UNSUPPORTED; }
+  cudaError_t le = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmO, tmR, tmM, p, grp, ngrp);
   if (le != cudaSuccess) {
     mtl_set_error("tc_gemm_kernel: launch failed: %s", cudaGetErrorString(le));
     (void)cudaGetLastError();
@@ -1288,7 +1332,8 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensor
 struct Maps { CUtensorMap a, b, o, r, m; };
 
 template <int MODE, bool GATHER>
-static int dispatch_bn(int bn, const Maps& t, const Params& p, cudaStream_t st) {
+static int dispatch_bn(int bn, const Maps& t, const Params& p, cudaStream_t st, const GroupEntry* grp = nullptr,
+                       int ngrp = 0, int group_tiles = 0) {
   if (p.cluster == 2) {       // FPROP / DGRAD, TMA operands, 128- or 256-wide tiles (chosen by the caller)
     if (MODE != WGRAD && !GATHER) {
       constexpr int M2 = (MODE == WGRAD || GATHER) ? FPROP : MODE;     // keeps the dead branch instantiable
@@ -1299,9 +1344,9 @@ static int dispatch_bn(int bn, const Maps& t, const Params& p, cudaStream_t st) 
     return MTL_ERR_UNSUPPORTED;
   }
   switch (bn) {
-    case 256: return launch<MODE, 256, GATHER, 1>(t.a, t.b, t.o, t.r, t.m, p, st);
-    case 128: return launch<MODE, 128, GATHER, 1>(t.a, t.b, t.o, t.r, t.m, p, st);
-    case 64: return launch<MODE, 64, GATHER, 1>(t.a, t.b, t.o, t.r, t.m, p, st);
+    case 256: return launch<MODE, 256, GATHER, 1>(t.a, t.b, t.o, t.r, t.m, p, st, grp, ngrp, group_tiles);
+    case 128: return launch<MODE, 128, GATHER, 1>(t.a, t.b, t.o, t.r, t.m, p, st, grp, ngrp, group_tiles);
+    case 64: return launch<MODE, 64, GATHER, 1>(t.a, t.b, t.o, t.r, t.m, p, st, grp, ngrp, group_tiles);
   }
   mtl_set_error("gemm_tc: unsupported BN %d", bn);
   return MTL_ERR_UNSUPPORTED;
@@ -1399,7 +1444,16 @@ struct mtl_conv_args {
                             // SMs: work that overlaps a latency-bound chain on another stream leaves it room
 };
 
-extern "C" int mtl_conv_tc(const mtl_conv_args* a, cudaStream_t stream) {
+// Everything mtl_conv_tc decides on the host for one problem: kernel parameters, tensor maps, tile width, operand path.
+struct mtl_conv_plan {
+  tc::Params p;
+  tc::Maps t;
+  int bn;
+  bool gather;
+  int mode;
+};
+
+static int plan_conv(const mtl_conv_args* a, mtl_conv_plan* out) {
   using namespace tc;
   MTL_CHECK_ARG(a != nullptr, "mtl_conv_tc: null args");
   MTL_CHECK_ARG(a->C % 8 == 0 && a->K % 8 == 0, "mtl_conv_tc: C and K must be multiples of 8 (C=%d K=%d)", a->C, a->K);
@@ -1573,12 +1627,115 @@ extern "C" int mtl_conv_tc(const mtl_conv_args* a, cudaStream_t stream) {
     p.ws = reinterpret_cast<float*>(a->ws);
     p.ws_cnt = reinterpret_cast<int*>(p.ws + (long long)tiles * BM * bn);
   }
-  if (a->mode == FPROP) return gather ? dispatch_bn<FPROP, true>(bn, t, p, stream)
-                                      : dispatch_bn<FPROP, false>(bn, t, p, stream);
-  if (a->mode == DGRAD) return gather ? dispatch_bn<DGRAD, true>(bn, t, p, stream)
-                                      : dispatch_bn<DGRAD, false>(bn, t, p, stream);
-  return gather ? dispatch_bn<WGRAD, true>(bn, t, p, stream)
-                : dispatch_bn<WGRAD, false>(bn, t, p, stream);
+  out->p = p; out->t = t; out->bn = bn; out->gather = gather; out->mode = a->mode;
+  return MTL_OK;
+}
+
+static int run_plan(const mtl_conv_plan& pl, cudaStream_t stream, const tc::GroupEntry* grp = nullptr, int ngrp = 0,
+                    int group_tiles = 0) {
+  using namespace tc;
+  const int bn = pl.bn;
+  const bool gather = pl.gather;
+  if (pl.mode == FPROP) return gather ? dispatch_bn<FPROP, true>(bn, pl.t, pl.p, stream, grp, ngrp, group_tiles)
+                                      : dispatch_bn<FPROP, false>(bn, pl.t, pl.p, stream, grp, ngrp, group_tiles);
+  if (pl.mode == DGRAD) return gather ? dispatch_bn<DGRAD, true>(bn, pl.t, pl.p, stream, grp, ngrp, group_tiles)
+                                      : dispatch_bn<DGRAD, false>(bn, pl.t, pl.p, stream, grp, ngrp, group_tiles);
+  return gather ? dispatch_bn<WGRAD, true>(bn, pl.t, pl.p, stream, grp, ngrp, group_tiles)
+                : dispatch_bn<WGRAD, false>(bn, pl.t, pl.p, stream, grp, ngrp, group_tiles);
+}
+
+extern "C" int mtl_conv_tc(const mtl_conv_args* a, cudaStream_t stream) {
+  mtl_conv_plan pl;
+  int rc = plan_conv(a, &pl);
+  if (rc) return rc;
+  return run_plan(pl, stream);
+}
+
+// ---------------------------------------------------------------------------------------- grouped launches
+// Several INDEPENDENT problems of one kernel instance (same mode, tile width, operand path and shared-memory carve)
+// in one persistent launch.  The trunk's weight-gradient GEMMs at batch 1 are the case: 81 launches of 8-54 CTAs, each
+// paying ~4 us of launch / fill / drain for 3-10 us of MMA work next to a latency-bound dgrad chain, become one grid
+// whose CTAs walk the concatenated tile space (K never split: every tile of dw is written by exactly one CTA, which
+// also makes the sums reproducible).
+//   mtl_conv_tc_group_entry_bytes()            size of one table entry (128-byte aligned)
+//   mtl_conv_tc_group_build(args, n, target_k_iters, host_table, info)
+//        plans the n problems and writes the table into HOST memory (n entries); info[0..3] = total tiles, tile
+//        width, mode, operand path.  K is split into pieces of about `target_k_iters` 64-deep steps (0: never).
+//        The caller copies the table to device memory (any 128-byte aligned allocation) and keeps both alive.
+//   mtl_conv_tc_group_launch(host_table, dev_table, n, info, max_ctas, stream)
+extern "C" long long mtl_conv_tc_group_entry_bytes() { return (long long)sizeof(tc::GroupEntry); }
+
+// Problems with equal keys can share a grouped launch (kernel instance + shared-memory carve); < 0: planning failed.
+extern "C" long long mtl_conv_tc_group_key(const mtl_conv_args* a) {
+  mtl_conv_args b = *a;
+  b.force_splits = 1; b.force_cluster = 1;
+  if (b.mode != tc::WGRAD) b.ws = nullptr;
+  mtl_conv_plan pl;
+  if (plan_conv(&b, &pl)) return -1;
+  const tc::Params& p = pl.p;
+  return (long long)pl.mode | ((long long)pl.bn << 4) | ((long long)(pl.gather ? 1 : 0) << 16) |
+         ((long long)p.stages << 20) | ((long long)p.res_slots << 24) | ((long long)p.epi_tma << 28) |
+         ((long long)(p.res != nullptr) << 29) | ((long long)(p.mask != nullptr) << 30) |
+         ((long long)(p.epi_warp_bytes >> 10) << 32);
+}
+
+extern "C" int mtl_conv_tc_group_build(const mtl_conv_args* args, int n, int target_k_iters, void* host_table,
+                                       int* info) {
+  using namespace tc;
+  MTL_CHECK_ARG(args && n > 0 && host_table && info, "mtl_conv_tc_group_build: bad args");
+  GroupEntry* tab = reinterpret_cast<GroupEntry*>(host_table);
+  int tile = 0;
+  mtl_conv_plan first;
+  for (int i = 0; i < n; ++i) {
+    mtl_conv_args a = args[i];
+    if (a.mode == WGRAD) {
+      const long long npq = (long long)a.N * a.P * a.Q;
+      const int k_iters = (int)ceil_div_ll(npq, BK);
+      a.force_splits = target_k_iters > 0 ? (k_iters + target_k_iters / 2) / target_k_iters : 1;
+      if (a.force_splits < 1) a.force_splits = 1;
+    } else {
+      a.force_splits = 1;       // FPROP / DGRAD split-K needs a workspace and a last-arriver epilogue: not in groups
+      a.ws = nullptr;
+    }
+    a.force_cluster = 1;
+    mtl_conv_plan pl;
+    int rc = plan_conv(&a, &pl);
+    if (rc) return rc;
+    if (i == 0) first = pl;
+    const Params &p = pl.p, &q = first.p;
+    if (pl.mode != first.mode || pl.bn != first.bn || pl.gather != first.gather || p.stages != q.stages ||
+        p.epi_warp_bytes != q.epi_warp_bytes || p.res_slots != q.res_slots || p.epi_tma != q.epi_tma ||
+        (p.res != nullptr) != (q.res != nullptr) || (p.mask != nullptr) != (q.mask != nullptr) || p.cluster != 1 ||
+        (pl.mode != WGRAD && p.splits != 1)) {
+      mtl_set_error("mtl_conv_tc_group_build: problem %d does not share problem 0's kernel instance / carve "
+                    "(mode %d/%d bn %d/%d gather %d/%d stages %d/%d)", i, pl.mode, first.mode, pl.bn, first.bn,
+                    (int)pl.gather, (int)first.gather, p.stages, q.stages);
+      return MTL_ERR_UNSUPPORTED;
+    }
+    GroupEntry& e = tab[i];
+    memset(&e, 0, sizeof(e));
+    e.tmA = pl.t.a; e.tmB = pl.t.b; e.tmO = pl.t.o; e.tmR = pl.t.r; e.tmM = pl.t.m;
+    e.p = p;
+    e.tile_begin = tile;
+    e.tiles = p.tiles_m * p.tiles_n * p.splits;
+    tile += e.tiles;
+  }
+  info[0] = tile; info[1] = first.bn; info[2] = first.mode; info[3] = first.gather ? 1 : 0;
+  return MTL_OK;
+}
+
+extern "C" int mtl_conv_tc_group_launch(const void* host_table, const void* dev_table, int n, const int* info,
+                                        int max_ctas, cudaStream_t stream) {
+  using namespace tc;
+  MTL_CHECK_ARG(host_table && dev_table && n > 0 && info, "mtl_conv_tc_group_launch: bad args");
+  MTL_CHECK_ARG((reinterpret_cast<uintptr_t>(dev_table) & 127) == 0, "mtl_conv_tc_group_launch: table must be 128-byte aligned");
+  const GroupEntry* tab = reinterpret_cast<const GroupEntry*>(host_table);
+  mtl_conv_plan pl;
+  pl.p = tab[0].p;
+  pl.p.max_ctas = max_ctas;
+  pl.t.a = tab[0].tmA; pl.t.b = tab[0].tmB; pl.t.o = tab[0].tmO; pl.t.r = tab[0].tmR; pl.t.m = tab[0].tmM;
+  pl.bn = info[1]; pl.mode = info[2]; pl.gather = info[3] != 0;
+  return run_plan(pl, stream, reinterpret_cast<const GroupEntry*>(dev_table), n, info[0]);
 }
 
 // Bytes of zeroed split-K workspace mtl_conv_tc would use for this FPROP / DGRAD problem (0: it would not

@@ -24,6 +24,7 @@ import numpy as np
 import torch
 
 from .. import ops
+from .. import ops_conv
 from ..core import model
 from ..core.standard_fields import (BoxListFields as fields, BOX_ENCODINGS, CLASS_PREDICTIONS,
                                     CLASS_PREDICTIONS_WITH_BACKGROUND, MASK_PREDICTIONS)
@@ -152,6 +153,12 @@ class FasterRCNNMetaArch(model.DetectionModel):
         self._ws = Workspace(device)
         self._store = ParamStore()
         self._anchor_cache = {}
+        self._trunk_wgrads = {}         # workspace id -> ops_conv.WgradCollector (grouped trunk weight gradients)
+        self._wgrad_chunk_ctas = int(__import__("os").environ.get("MTL_WGRAD_CHUNK_CTAS", "64"))
+        self._head_wgrads = {}          # workspace id -> collector of the second-stage weight-gradient GEMMs
+        self.group_head_wgrads = False  # set by the trainer's deferred schedule (plain backward(): immediate launches)
+        self.defer_head_wgrads = False
+        self.supports_deferred_heads = True
         self._sampler_keys = None
         self._lanes = _Lanes()
         for pred in (second_stage_mask_rcnn_box_predictor, window_box_predictor, closeness_box_predictor):
@@ -343,6 +350,20 @@ class FasterRCNNMetaArch(model.DetectionModel):
 
     def predict(self, preprocessed_inputs, prefix=None):
         """fmA:507-609.  `prefix`: output of frozen_prefix() for these inputs (computed ahead of time)."""
+        return self.predict_second_stage(self.predict_first_stage(preprocessed_inputs, prefix))
+
+    def predict_second_stage(self, pd):
+        """Second half of `predict` (fmA:604-609): ROI crops, box-classifier tails and heads.  Split from the first half
+        so that a trainer can run work that must precede every use of a second-stage weight (the previous step's
+        deferred head update, trainer.py) beside the first half."""
+        self._lanes.mark("feat")        # (re-recorded here: the two halves may be captured into different CUDA graphs)
+        pd.update(self._predict_second_stage(pd))
+        return pd
+
+    def predict_first_stage(self, preprocessed_inputs, prefix=None):
+        """First half of `predict`: feature extractor, RPN head, anchors, and -- no second-stage variable is involved
+        yet -- `_postprocess_rpn` (proposal decode, NMS, minibatch sampling), whose result `_predict_second_stage`
+        picks up from the dictionary."""
         ws, fe = self._ws, self._feature_extractor
         B, H, W, _ = preprocessed_inputs.shape
         image_shape = (B, H, W, 3)
@@ -371,7 +392,7 @@ class FasterRCNNMetaArch(model.DetectionModel):
                          else rp[CLASS_PREDICTIONS_WITH_BACKGROUND]()[:, keep_idx.long()]),
             "_rpn_out": rpn_out, "_rpn_layout": lay, "_keep_idx": keep_idx, "_Nk": Nk, "_feat_hw": (Hf, Wf),
         })
-        pd.update(self._predict_second_stage(pd))
+        pd["_proposals"] = self._postprocess_rpn(pd)
         return pd
 
     def _postprocess_rpn(self, pd):
@@ -450,7 +471,7 @@ class FasterRCNNMetaArch(model.DetectionModel):
         ws, fe, mtl = self._ws, self._feature_extractor, self._mtl
         B = pd["image_shape"][0]
         P = self.max_num_proposals
-        prop_norm, prop_abs, prop_sc, nprop = self._postprocess_rpn(pd)
+        prop_norm, prop_abs, prop_sc, nprop = pd["_proposals"] if "_proposals" in pd else self._postprocess_rpn(pd)
         feat = pd["rpn_features_to_crop"]
         maps, pre_pool = self._compute_second_stage_input_feature_maps(
             feat, prop_norm.view(B * P, 4), self._box_ind(B, P, "props"), "props")
@@ -712,6 +733,28 @@ class FasterRCNNMetaArch(model.DetectionModel):
         stop_aux = mtl is not None and mtl.stop_gradient_for_aux_tasks
         dfeat = ws.get("bwd/dfeat_f32", feat.shape, torch.float32, zero=True)
         L = self._lanes
+        # The weight-gradient GEMMs of the second-stage tails and heads are collected (ops_conv.WgradCollector) and run
+        # as grouped launches: at the end of this half of the backward pass, or -- `defer_head_wgrads` -- when the
+        # trainer calls flush_head_wgrads(), which it does underneath the NEXT step's trunk forward pass.
+        hcol = self._head_wgrads.setdefault(id(ws), ops_conv.WgradCollector(target_k_iters=56)) \
+            if (self.group_head_wgrads and ops_conv.WgradCollector.enabled and part in ("heads", "heads_async")) else None
+        if hcol is not None:
+            hcol.__enter__()
+        try:
+            return self._backward_heads(pd, part, ws, fe, mtl, feat, B, Hf, Wf, C, P, stop_aux, dfeat, L)
+        finally:
+            if hcol is not None:
+                hcol.__exit__(None, None, None)
+                if not self.defer_head_wgrads:
+                    self.flush_head_wgrads()
+
+    def flush_head_wgrads(self, max_ctas=0):
+        """Run the second-stage weight-gradient GEMMs collected by the last backward(part="heads*")."""
+        col = self._head_wgrads.get(id(self._ws))
+        if col is not None:
+            col.flush(max_ctas=max_ctas)
+
+    def _backward_heads(self, pd, part, ws, fe, mtl, feat, B, Hf, Wf, C, P, stop_aux, dfeat, L):
         # refiner FC (inputs are behind stop_gradient: weights / bias only)
         if mtl is not None and mtl.refine:
             K1 = self.num_classes + 1
@@ -766,17 +809,36 @@ class FasterRCNNMetaArch(model.DetectionModel):
         ws, fe = self._ws, self._feature_extractor
         feat = pd["rpn_features_to_crop"]
         dfeat = ws.bufs["bwd/dfeat_f32"]
-        # RPN head and conv; the conv's dgrad epilogue merges the fp32 ROI/edgemask gradient and
-        # applies the ReLU mask of the trunk output
-        rpn_feat = pd["rpn_box_predictor_features"]
-        d_rpn_feat = ws.get("bwd/d_rpn_feat", rpn_feat.shape)
-        self._first_stage_box_predictor.backward(self.first_stage_box_predictor_scope, rpn_feat,
-                                                 ws.bufs["rpn/d_out"], d_rpn_feat,
-                                                 rpn_feat if self._rpn_conv.relu else None)
-        self._rpn_conv.wgrad(feat, d_rpn_feat)
-        gfeat = self._rpn_conv.dgrad(d_rpn_feat, feat.shape, ws.get("bwd/g_feat", feat.shape), res=dfeat, mask=feat,
-                                     mask_hi=fe.feature_mask_hi)
-        fe.backward_proposal_features(self.first_stage_feature_extractor_scope, gfeat, ws)
+        # Weight gradients only feed the optimizer: where every gradient tensor of the chain keeps its own buffer until
+        # the end of the pass (`deferred_wgrad_safe`), the RPN + trunk dgrad chain runs first and undisturbed, then all
+        # of its weight-gradient GEMMs run as a few grouped, machine-filling launches (ops_conv.WgradCollector).
+        import contextlib
+        col = None
+        if getattr(fe, "deferred_wgrad_safe", False) and ops_conv.WgradCollector.enabled:
+            col = self._trunk_wgrads.setdefault(id(ws), ops_conv.WgradCollector())
+        with (col if col is not None else contextlib.nullcontext()):
+            # RPN head and conv; the conv's dgrad epilogue merges the fp32 ROI/edgemask gradient and
+            # applies the ReLU mask of the trunk output
+            rpn_feat = pd["rpn_box_predictor_features"]
+            d_rpn_feat = ws.get("bwd/d_rpn_feat", rpn_feat.shape)
+            self._first_stage_box_predictor.backward(self.first_stage_box_predictor_scope, rpn_feat,
+                                                     ws.bufs["rpn/d_out"], d_rpn_feat,
+                                                     rpn_feat if self._rpn_conv.relu else None)
+            self._rpn_conv.wgrad(feat, d_rpn_feat)
+            gfeat = self._rpn_conv.dgrad(d_rpn_feat, feat.shape, ws.get("bwd/g_feat", feat.shape), res=dfeat,
+                                         mask=feat, mask_hi=fe.feature_mask_hi)
+            if col is not None:
+                # every 6 bottleneck units the collected weight-gradient problems go to a side stream as one grouped
+                # launch sized for 64 SMs; the dgrad chain (<= 76 CTAs per layer at batch 1) keeps the rest
+                def chunk(j):
+                    with torch.cuda.stream(Concurrency.fork()):
+                        col.flush(max_ctas=self._wgrad_chunk_ctas, key=j)
+                fe.backward_proposal_features(self.first_stage_feature_extractor_scope, gfeat, ws, every=6,
+                                              checkpoint=chunk)
+            else:
+                fe.backward_proposal_features(self.first_stage_feature_extractor_scope, gfeat, ws)
+        if col is not None:
+            col.flush(key=0)                # the last chunk has the machine to itself
         Concurrency.join()      # side-stream weight-gradient GEMMs must land before the optimizer
 
     def _crop_backward(self, pd, dmaps, maps, pre_pool, boxes, box_ind, dfeat, tag):

@@ -22,13 +22,14 @@ class RFCNMetaArch(FasterRCNNMetaArch):
         super(RFCNMetaArch, self).__init__(second_stage_mask_rcnn_box_predictor=second_stage_rfcn_box_predictor,
                                            **kwargs)
         self._rfcn_box_predictor = second_stage_rfcn_box_predictor
+        self.supports_deferred_heads = False      # its backward() keeps the plain schedule (trainer.py)
 
     def _predict_second_stage(self, pd):
         """rfcn:208-310."""
         ws, fe, mtl = self._ws, self._feature_extractor, self._mtl
         B = pd["image_shape"][0]
         P = self.max_num_proposals
-        prop_norm, prop_abs, prop_sc, nprop = self._postprocess_rpn(pd)
+        prop_norm, prop_abs, prop_sc, nprop = pd["_proposals"] if "_proposals" in pd else self._postprocess_rpn(pd)
         feat = pd["rpn_features_to_crop"]
         boxes, bi = prop_norm.view(B * P, 4), self._box_ind(B, P, "props")
         self._lanes.mark("crops")

@@ -37,6 +37,7 @@ class FasterRCNNResnetV1FeatureExtractor(FasterRCNNFeatureExtractor):
         self.classifier_depth = 2048
         self.feature_mask_hi = 0.0           # activations are plain ReLU
         self.supports_dx_extra = True
+        self.deferred_wgrad_safe = True      # every gradient tensor of the trunk's backward pass has its own buffer
 
     def preprocess(self, resized_inputs):
         """fe:74-90 subtracts the ImageNet channel means.  On the B200 path the subtraction is
@@ -88,8 +89,8 @@ class FasterRCNNResnetV1FeatureExtractor(FasterRCNNFeatureExtractor):
             raise ValueError("image size must at least be 33 in both height and width.")
         return self._trunks[scope].fwd(preprocessed_inputs, ws, prefix)
 
-    def backward_proposal_features(self, scope, grad, ws):
-        self._trunks[scope].bwd(grad, ws)
+    def backward_proposal_features(self, scope, grad, ws, every=0, checkpoint=None):
+        self._trunks[scope].bwd(grad, ws, every, checkpoint)
 
     def extract_box_classifier_features(self, proposal_feature_maps, scope, ws, tag="main", keep=True):
         return self._tails[scope].fwd(proposal_feature_maps, ws, tag, keep)

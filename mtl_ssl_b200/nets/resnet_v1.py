@@ -178,11 +178,16 @@ class ResNetV1(object):
             x = u.fwd(x, ws, "s1")
         return x
 
-    def bwd(self, g, ws):
-        """g: gradient w.r.t. the trunk output, already masked by (output > 0)."""
+    def bwd(self, g, ws, every=0, checkpoint=None):
+        """g: gradient w.r.t. the trunk output, already masked by (output > 0).  `checkpoint(j)` is called after every
+        `every` units (deferred weight-gradient work is handed to a side stream in chunks while the chain goes on)."""
         first_trainable = next(i for i, u in enumerate(self.units) if u.trainable)
+        n = 0
         for i in range(len(self.units) - 1, first_trainable - 1, -1):
             g = self.units[i].bwd(g, ws, "s1", need_dx=i > first_trainable)
+            n += 1
+            if every and checkpoint is not None and n % every == 0 and i > first_trainable:
+                checkpoint(n // every)
         return None
 
 

@@ -42,6 +42,21 @@ def _launch(a, what):
     PROFILE.append((a.mode, flops, e0, e1, (a.N, a.H, a.W, a.C, a.K, a.R, a.stride, a.P, a.Q)))
 
 
+def _log_group(grp, launch):
+    """PROFILE / TIMELINE records of one grouped launch (one kernel, the group's summed algorithmic FLOPs)."""
+    if TIMELINE is None and PROFILE is None:
+        return launch()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s = torch.cuda.current_stream()
+    e0.record(s)
+    launch()
+    e1.record(s)
+    if TIMELINE is not None:
+        TIMELINE.append(("conv%d group of %d" % (grp.mode, grp.n), s.cuda_stream, e0, e1, grp.flops))
+    if PROFILE is not None:
+        PROFILE.append((grp.mode, grp.flops, e0, e1, (grp.n, 0, 0, 0, 0, 0, 0, 0, 0)))
+
+
 class ConvArgs(ctypes.Structure):
     _fields_ = [
         ("mode", ctypes.c_int),
@@ -94,6 +109,99 @@ def _attach_ws(a):
         buf = torch.zeros((max(need, 8 << 20) + 3) // 4, device="cuda", dtype=torch.float32)
         _ws_by_stream[key] = buf
     a.ws, a.ws_bytes = buf.data_ptr(), buf.numel() * 4
+
+
+class ConvGroup(object):
+    """Independent problems of ONE kernel instance (same mtl_conv_tc_group_key) as one persistent launch: the CTAs walk
+    the concatenated tile space.  Built once from the problems' ConvArgs (the table of tensor maps + parameters is planned
+    on the host and copied to the device); `launch()` only enqueues the kernel, so it can be captured into a CUDA graph.
+    The buffers the arguments point at must stay where they are (the workspace / parameter arenas do)."""
+
+    def __init__(self, arg_list, target_k_iters=0):
+        n = len(arg_list)
+        f = lib().mtl_conv_tc_group_entry_bytes
+        f.restype = ctypes.c_longlong
+        eb = int(f())
+        arr = (ConvArgs * n)()
+        for i, a in enumerate(arg_list):
+            ctypes.memmove(ctypes.byref(arr, i * ctypes.sizeof(ConvArgs)), ctypes.byref(a), ctypes.sizeof(ConvArgs))
+        self.n = n
+        self.mode = int(arg_list[0].mode)
+        self.flops = sum(2.0 * a.N * a.P * a.Q * a.K * a.R * a.S * a.C for a in arg_list)
+        self.signature = tuple((a.x, a.w, a.dy, a.out, a.N, a.H, a.W, a.C, a.K, a.R, a.stride) for a in arg_list)
+        self.host = torch.zeros(n * eb + 128, dtype=torch.uint8)
+        off = (-self.host.data_ptr()) % 128
+        self.host_ptr = self.host.data_ptr() + off
+        self.info = (ctypes.c_int * 4)()
+        check(lib().mtl_conv_tc_group_build(arr, n, int(target_k_iters), ctypes.c_void_p(self.host_ptr), self.info),
+              "mtl_conv_tc_group_build")
+        self.total_tiles = int(self.info[0])
+        dev = torch.empty(n * eb + 128, dtype=torch.uint8, device="cuda" if torch.cuda.is_available() else "cpu")
+        doff = (-dev.data_ptr()) % 128
+        dev[doff:doff + n * eb].copy_(self.host[off:off + n * eb])
+        if torch.cuda.is_available():
+            torch.cuda.current_stream().synchronize()    # (the host table is pageable memory)
+        self.dev, self.dev_ptr = dev, dev.data_ptr() + doff
+
+    def launch(self, max_ctas=0):
+        _log_group(self, lambda: check(lib().mtl_conv_tc_group_launch(
+            ctypes.c_void_p(self.host_ptr), ctypes.c_void_p(self.dev_ptr), self.n, self.info, int(max_ctas),
+            cur_stream()), "mtl_conv_tc_group_launch"))
+
+
+def group_key(a):
+    f = lib().mtl_conv_tc_group_key
+    f.restype = ctypes.c_longlong
+    return int(f(ctypes.byref(a)))
+
+
+class WgradCollector(object):
+    """Defers the weight-gradient GEMMs issued while it is active and runs them as grouped launches at `flush()`.
+    Weight gradients feed only the optimizer, so a backward chain can run first and undisturbed (at batch 1 the trunk's
+    dgrad chain is latency bound and its 81 wgrad launches used to compete with it for SMs), then all of its weight
+    gradients run as a few machine-filling launches.  Groups are planned at the first flush and reused while the
+    problems (pointers + geometry) stay the same -- they do: every operand lives in a persistent arena."""
+    active = None
+    enabled = not __import__("os").environ.get("MTL_NO_WGRAD_GROUP")
+
+    def __init__(self, target_k_iters=48):
+        self.target = target_k_iters
+        self.pending = []
+        self.groups = None
+
+    def __enter__(self):
+        if WgradCollector.enabled:
+            assert WgradCollector.active is None
+            WgradCollector.active = self
+            self.pending = []
+        return self
+
+    def __exit__(self, *exc):
+        if WgradCollector.active is self:
+            WgradCollector.active = None
+        return False
+
+    def add(self, a):
+        self.pending.append(a)
+
+    def flush(self, max_ctas=0, key=0):
+        """Run everything collected since the last flush.  `key` names the flush point: a pass that flushes several
+        times (chunks of a backward chain) plans one set of groups per point."""
+        args, self.pending = self.pending, []
+        if not args:
+            return
+        if self.groups is None:
+            self.groups = {}
+        sig = tuple((a.x, a.dy, a.out, a.N, a.H, a.W, a.C, a.K, a.R, a.stride) for a in args)
+        cur = self.groups.get(key)
+        if cur is None or cur[0] != sig:
+            buckets = {}
+            for a in args:
+                buckets.setdefault(group_key(a), []).append(a)
+            cur = (sig, [ConvGroup(v, self.target) for _, v in sorted(buckets.items())])
+            self.groups[key] = cur
+        for g in cur[1]:
+            g.launch(max_ctas)
 
 
 def out_size(h, k, stride, pad_beg, pad_end, dil=1):
@@ -205,5 +313,8 @@ def conv_wgrad(dy, x, dw, stride=1, pad=(0, 0), dil=1, rowscale=None, alpha=1.0,
     a.force_bn = force_bn
     a.force_splits = force_splits
     a.max_ctas = CTA_CAP
+    if WgradCollector.active is not None and force_splits == 0 and force_bn == 0:
+        WgradCollector.active.add(a)
+        return dw
     _launch(a, "mtl_conv_tc(wgrad)")
     return dw

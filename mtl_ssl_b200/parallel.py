@@ -13,7 +13,11 @@ def data_parallel_scale(world_size):
     return 1.0 / float(world_size)
 
 
-def allreduce_gradients(flat_grads, world_size, group=None):
+def allreduce_gradients(flat_grads, world_size, group=None, async_op=False):
+    """Sum one gradient bucket (a contiguous view of the gradient arena) over the replicas, in place.
+    async_op=True returns the work handle (None with a single replica): the caller overlaps the exchange with compute
+    and calls `.wait()` on the stream that consumes the sum."""
     if world_size > 1:
-        dist.all_reduce(flat_grads, op=dist.ReduceOp.SUM, group=group)
-    return flat_grads
+        work = dist.all_reduce(flat_grads, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+        return work if async_op else flat_grads
+    return None if async_op else flat_grads

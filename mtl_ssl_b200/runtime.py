@@ -204,6 +204,9 @@ class ParamStore(object):
         self.chunk_start_dev = torch.tensor(self.chunk_start, dtype=torch.int32, device=self.device)
         self.reg_loss = torch.zeros(1, dtype=torch.float32, device=self.device)
         self.hyper = torch.zeros(4, dtype=torch.float32, device=self.device)
+        # learning rate / momentum / clip norm of the step whose head-bucket update is still pending (trainer.py runs
+        # that update underneath the next step's trunk forward pass, after `hyper` already holds the next step's values)
+        self.hyper_heads = torch.zeros(4, dtype=torch.float32, device=self.device)
 
     # ------------------------------------------------------------------ kernels
     def fold(self):
@@ -231,11 +234,11 @@ class ParamStore(object):
             ops.call("mtl_opt_stats_range", self.td, t0, t1, cd, n, self.w, self.g, grad_scale, self.stats,
                      self.chunk_start_dev, self.chunk_start[t0], self.partials)
 
-    def apply_range(self, t0, t1, grad_scale=1.0):
+    def apply_range(self, t0, t1, grad_scale=1.0, hyper=None):
         cd, n = self._chunk_range(t0, t1)
         if n:
             ops.call("mtl_opt_apply", self.td, cd, n, self.w, self.g, self.m, self.wb, self.fold_scales,
-                     self.stats, self.hyper, grad_scale)
+                     self.stats, self.hyper if hyper is None else hyper, grad_scale)
 
     def reg_loss_from_stats(self):
         ops.call("mtl_opt_reg_loss", self.td, self.num_tensors, self.stats, self.reg_loss)

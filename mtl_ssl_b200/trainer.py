@@ -156,6 +156,18 @@ class Trainer(object):
         self.graph_opt_heads = None
         self._opt_stream = None
         self._h2d_done = None           # event: the last step()'s copies out of the pinned staging buffers have run
+        # Deferred head update (see _run_step_deferred): the weight-gradient GEMMs of the second-stage tails / heads, the
+        # all-reduce of that gradient bucket and its clip + momentum update run underneath the NEXT step's trunk
+        # forward pass + proposal chain (a latency-bound stretch that leaves most SMs idle at batch 1).
+        import os
+        self.defer_heads = os.environ.get("MTL_NO_DEFER_HEADS") is None
+        self._deferred_ctas = int(os.environ.get("MTL_DEFERRED_CTAS", "48"))
+        self._heads_pending = False     # a head update is waiting for the next step (or finish())
+        self._head_stats_valid = False  # the head tensors' squared norms (regularisation loss) match the current weights
+        model.param_store.post_load_hooks.append(self._weights_replaced)
+        self._pd = None
+        self.graph_fa = None
+        self.graph_hw = None
 
     # ------------------------------------------------------------------ one step
     def _bind(self, arrays):
@@ -228,6 +240,128 @@ class Trainer(object):
         cur.wait_stream(self._opt_stream)
         return pd
 
+    # ------------------------------------------------------------------ deferred-head schedule
+    def _deferred(self):
+        return bool(self.defer_heads and self.overlap_optimizer and
+                    getattr(self.model, "supports_deferred_heads", False))
+
+    def _stage_a(self, image, prefix=None):
+        """Trunk forward, RPN head, proposal chain: touches first-stage variables only."""
+        m = self.model
+        if prefix is None and self._prefix_cur is not None:
+            prefix = self._prefix_cur
+        pre = m.preprocess(image)
+        self._pd = m.predict_first_stage(pre, prefix=prefix) if prefix is not None else m.predict_first_stage(pre)
+
+    def _stage_b(self):
+        """Second-stage forward, the eight losses, the whole backward pass; the second-stage weight-gradient GEMMs are
+        only collected (model.flush_head_wgrads runs them, see _stage_c)."""
+        m = self.model
+        mtl = m._mtl
+        pd = m.predict_second_stage(self._pd)
+        if mtl is not None and mtl.window:
+            pd = m.predict_with_window(pd)
+        if mtl is not None and mtl.edgemask:
+            pd = m.predict_edgemask(pd)
+        if mtl is not None and mtl.refine:
+            pd = m.predict_with_mtl_results(pd)
+        m.loss(pd)
+        m.group_head_wgrads = m.defer_head_wgrads = True
+        try:
+            m.backward(pd, part="heads")
+        finally:
+            m.group_head_wgrads = m.defer_head_wgrads = False
+        m.backward(None, part="trunk")
+        self._pd = pd
+        return pd
+
+    def _stage_c(self):
+        """The deferred second-stage weight gradients, as grouped launches sized to leave the trunk chain its SMs."""
+        self.model.flush_head_wgrads(max_ctas=self._deferred_ctas)
+
+    def _optimize_heads_deferred(self):
+        st = self.model.param_store
+        gs = data_parallel_scale(self.world_size)
+        t0, _ = self.model.head_tensor_range()
+        st.stats_range(t0, st.num_tensors, gs)
+        st.apply_range(t0, st.num_tensors, gs, hyper=st.hyper_heads)
+        # the regularisation loss of the NEXT step is made of the squared norms of the weights that step computes with:
+        # refresh the head tensors' entries now (the trunk's are refreshed by that step's own trunk update)
+        st.stats_range(t0, st.num_tensors, gs)
+
+    def _launch_deferred(self, cur):
+        """Side stream: head weight gradients -> (several replicas: all-reduce of that bucket) -> head update."""
+        graph = self.use_graph and self.graph_hw is not None
+        if self._opt_stream is None:
+            self._opt_stream = torch.cuda.Stream()
+        self._opt_stream.wait_stream(cur)
+        with torch.cuda.stream(self._opt_stream):
+            self.graph_hw.replay() if graph else self._stage_c()
+            if self.world_size > 1:
+                allreduce_gradients(self.model.gradient_buckets()[0], self.world_size, self.pg)
+            self.graph_opt_heads.replay() if graph else self._optimize_heads_deferred()
+        self._head_stats_valid = True
+
+    def _weights_replaced(self):
+        self._head_stats_valid = False
+
+    def finish(self):
+        """Apply a pending deferred head update now (before reading or saving weights, evaluating, or handing the model
+        to another trainer).  No-op when nothing is pending."""
+        if self._heads_pending:
+            cur = torch.cuda.current_stream()
+            self._launch_deferred(cur)
+            cur.wait_stream(self._opt_stream)
+            self._heads_pending = False
+
+    def _run_step_deferred(self, lookahead, defer):
+        """trunk forward + proposals (A) || previous step's head update (C)  ->  second stage, losses, backward (B)  ->
+        [all-reduce of the trunk bucket]  ->  trunk update (D).  The head update of THIS step stays pending."""
+        graph = self.use_graph
+        cur = torch.cuda.current_stream()
+        image = self.inputs.dev["image"]
+        if self._prefix_cur is not None and not lookahead:
+            self.graph_prefix.replay() if graph else self._prefix(image)
+        had = self._heads_pending
+        if had:
+            self._launch_deferred(cur)
+        elif not self._head_stats_valid:
+            # first step (or the weights were replaced): no head update precedes this step, so nothing has computed
+            # the head tensors' squared norms that the regularisation loss sums
+            st = self.model.param_store
+            st.stats_range(self.model.head_tensor_range()[0], st.num_tensors, data_parallel_scale(self.world_size))
+            self._head_stats_valid = True
+        self.graph_fa.replay() if graph else self._stage_a(image)
+        if had:
+            cur.wait_stream(self._opt_stream)      # every second-stage weight is final from here on
+            self._heads_pending = False
+        self.graph_fb.replay() if graph else self._stage_b()
+        if self.world_size > 1:
+            allreduce_gradients(self.model.gradient_buckets()[1], self.world_size, self.pg)
+        self.graph_opt.replay() if graph else self._optimize()
+        self._heads_pending = True
+        if not defer:
+            self.finish()
+
+    def eager_pass(self, image=None):
+        """One whole step body launched eagerly on the current stream(s), no gradient exchange (bench.py: launch
+        count and per-launch timings)."""
+        image = self.inputs.dev["image"] if image is None else image
+        self._prefix(image)
+        if self._deferred():
+            self._stage_a(image)
+            self._stage_b()
+            self._optimize()
+            self._stage_c()
+            self._optimize_heads_deferred()
+            return
+        self._forward_backward(image)
+        if self.world_size > 1:
+            if self.overlap_optimizer:
+                self._optimize_heads()
+            self._backward_trunk()
+        self._optimize()
+
     def _backward_trunk(self):
         self.model.backward(None, part="trunk")
 
@@ -254,6 +388,7 @@ class Trainer(object):
             st.apply(gs)
         self._loss_dev[:8].copy_(self.model.workspace.bufs["loss/values"])
         self._loss_dev[8:9].copy_(st.reg_loss)
+        st.hyper_heads.copy_(st.hyper)          # what a deferred head update of THIS step will use
 
     def _allreduce(self):
         allreduce_gradients(self.model.param_store.g, self.world_size, self.pg)
@@ -298,17 +433,20 @@ class Trainer(object):
         """One step on the inputs already resident in HBM, with the frozen prefix software-pipelined: the prefix of
         the next step (same resident image) is computed underneath this step.  Requires one earlier step."""
         if self._prefix_cur is None:
-            return self._run_step_body()
+            return self._run_step_body(defer=True)
         if not self._prefix_primed:
             self._lookahead_prefix(self.inputs.dev["image"])
             self._prefix_primed = True
         self._take_prefix()
         self._lookahead_prefix(self.inputs.dev["image"])
-        self._run_step_body(lookahead=True)
+        self._run_step_body(lookahead=True, defer=True)
 
-    def _run_step_body(self, lookahead=False):
+    def _run_step_body(self, lookahead=False, defer=False):
         """forward + backward + gradient exchange + optimizer.  With several replicas the backward is cut
-        in two: the second-stage bucket is all-reduced (NCCL stream) while the trunk half still computes."""
+        in two: the second-stage bucket is all-reduced (NCCL stream) while the trunk half still computes.
+        `defer`: leave the head update pending for the next call (deferred-head schedule only)."""
+        if self._deferred():
+            return self._run_step_deferred(lookahead, defer)
         graph = self.use_graph
         if self._prefix_cur is not None and not lookahead:
             # synchronous: frozen prefix of this batch, then the rest of the step
@@ -317,11 +455,10 @@ class Trainer(object):
             self.graph_fb.replay() if graph else self._forward_backward(self.inputs.dev["image"])
             self.graph_opt.replay() if graph else self._optimize()
             return
-        import torch.distributed as dist
         b_heads, b_trunk = self.model.gradient_buckets()
         cur = torch.cuda.current_stream()
         self.graph_fb.replay() if graph else self._forward_backward(self.inputs.dev["image"])
-        w1 = dist.all_reduce(b_heads, op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
+        w1 = allreduce_gradients(b_heads, self.world_size, self.pg, async_op=True)
         if self.overlap_optimizer:
             # the head bucket's update follows its all-reduce on a side stream, underneath the trunk backward
             # and the trunk bucket's all-reduce
@@ -332,7 +469,7 @@ class Trainer(object):
                 w1.wait()
                 self.graph_opt_heads.replay() if graph else self._optimize_heads()
         self.graph_fb2.replay() if graph else self._backward_trunk()
-        w2 = dist.all_reduce(b_trunk, op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
+        w2 = allreduce_gradients(b_trunk, self.world_size, self.pg, async_op=True)
         if self.overlap_optimizer:
             cur.wait_stream(self._opt_stream)
         else:
@@ -406,7 +543,7 @@ class Trainer(object):
         self.inputs.commit(slot)
         st.hyper.copy_(hh, non_blocking=True)
         self._attach()
-        self._run_step_body(lookahead=self._prefix_cur is not None)
+        self._run_step_body(lookahead=self._prefix_cur is not None, defer=True)
         self.global_step += 1
         self._loss_slots[slot].copy_(self._loss_dev, non_blocking=True)
         done = torch.cuda.Event()
@@ -415,8 +552,10 @@ class Trainer(object):
         return self._resolve(prev)
 
     def flush(self):
-        """Losses of the last step_pipelined() call (waits for it)."""
+        """Losses of the last step_pipelined() call (waits for it); a pending deferred head update is applied, so the
+        weights are final when this returns."""
         prev, self._pending = self._pending, None
+        self.finish()
         return self._resolve(prev)
 
     def _resolve(self, pending):
@@ -439,10 +578,16 @@ class Trainer(object):
         """Warm up eagerly (allocates every workspace buffer, fills the anchor cache), then capture."""
         st = self.model.param_store
         snap = (st.w.clone(), st.m.clone(), st.wb.clone())
+        deferred = self._deferred()
         for _ in range(2):
-            self._forward_backward(image)
-            if self.world_size > 1:
-                self._backward_trunk()
+            if deferred:
+                self._stage_a(image)
+                self._stage_b()
+                self._stage_c()             # (plans the grouped launches: not allowed while capturing)
+            else:
+                self._forward_backward(image)
+                if self.world_size > 1:
+                    self._backward_trunk()
             st.g.zero_()
         st.w.copy_(snap[0]); st.m.copy_(snap[1]); st.wb.copy_(snap[2])
         torch.cuda.synchronize()
@@ -453,6 +598,24 @@ class Trainer(object):
             self.graph_prefix_next = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph_prefix_next):
                 self._prefix(self._image_next, "s1n")
+        if deferred:
+            self.graph_fa = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_fa):
+                self._stage_a(image)
+            self.graph_fb = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_fb):
+                self._stage_b()
+            self.graph_hw = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_hw):
+                self._stage_c()
+            self.graph_opt_heads = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_opt_heads):
+                self._optimize_heads_deferred()
+            self.graph_opt = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_opt):
+                self._optimize()
+            torch.cuda.synchronize()
+            return
         self.graph_fb = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph_fb):
             self._forward_backward(image)

@@ -235,3 +235,44 @@ def test_avgpool3x3_same_fwd_bwd():
     dx = torch.empty_like(x)
     ops.call("mtl_avgpool3x3_same", dy, N, H, W, C, 1, dx)
     close(dx.cpu(), xr.grad.permute(0, 2, 3, 1), 1e-2)
+
+
+def test_grouped_wgrad_launches_match_individual_problems():
+    """ops_conv.WgradCollector / ConvGroup: independent weight-gradient problems of one kernel instance share a persistent
+    launch (the CTAs walk the concatenated tile space, K split per problem).  A bottleneck unit's three GEMMs at the
+    trunk's size and at ROI-tile size, a 3x3 with C = 128 (another tile width -> its own group) and a strided 3x3 (gather
+    path -> its own group); every result against the fp32 reference, twice (the second flush reuses the planned groups
+    and accumulates)."""
+    from mtl_ssl_b200 import ops_conv as oc
+    dev = "cuda"
+    torch.manual_seed(7)
+    probs = [  # N, H, W, C, K, R, stride, pad
+        (1, 38, 63, 1024, 256, 1, 1, 0), (1, 38, 63, 256, 256, 3, 1, 1), (1, 38, 63, 256, 1024, 1, 1, 0),
+        (64, 7, 7, 512, 512, 3, 1, 1), (64, 7, 7, 512, 2048, 1, 1, 0), (64, 7, 7, 1024, 512, 1, 1, 0),
+        (1, 75, 125, 128, 128, 3, 1, 1), (1, 75, 125, 128, 512, 1, 1, 0),
+        (2, 19, 23, 128, 128, 3, 2, 1), (3, 9, 11, 192, 72, 3, 1, 1),
+    ]
+    data = []
+    for (N, H, W, C, K, R, stride, pad) in probs:
+        P = (H + 2 * pad - R) // stride + 1
+        Q = (W + 2 * pad - R) // stride + 1
+        x = torch.randn(N, H, W, C, device=dev).bfloat16()
+        dy = (torch.randn(N, P, Q, K, device=dev) / (N * P * Q) ** 0.5).bfloat16()
+        rs = torch.rand(K, device=dev) + 0.5
+        xf = x.float().requires_grad_(True)
+        wf = torch.zeros(K, R, R, C, device=dev, requires_grad=True)
+        ref_conv(xf, wf, stride, (pad, pad), P, Q).backward(dy.float())
+        data.append((x, dy, rs, torch.zeros(K, R, R, C, device=dev), wf.grad * rs[:, None, None, None], stride, pad))
+    col = oc.WgradCollector(target_k_iters=24)
+    for rep in (1, 2):
+        with col:
+            for x, dy, rs, dw, _want, stride, pad in data:
+                oc.conv_wgrad(dy, x, dw, stride, (pad, pad), 1, rowscale=rs)
+            assert not any(d[3].any() for d in data) or rep == 2         # deferred: nothing has run yet
+        col.flush()
+        torch.cuda.synchronize()
+        for x, dy, rs, dw, want, stride, pad in data:
+            close(dw, want * rep, 3e-3)
+    sig, groups = col.groups[0]
+    assert len(groups) >= 3 and sum(g.n for g in groups) == len(probs)
+    assert max(g.n for g in groups) >= 5

@@ -26,7 +26,11 @@ def test_two_shapes_share_one_model(graph):
     cfg = load_config("model12.config", T.SMALL)
     K, M = cfg.model.faster_rcnn.num_classes, cfg.model.faster_rcnn.first_stage_max_proposals
     shapes = [(224, 320), (224, 288), (224, 320)]
-    kw = dict(gmax=8, learning_rate=1e-5)
+    # A tiny learning rate: the fp32 atomics of the backward pass make two runs' weights differ in the last bits, and at
+    # 1e-5 that was enough to flip a near-tie in the proposal selection of the third step now and then (one of three
+    # runs on a B200: `second_stage_localization_loss` 0.893 or 0.948 in the PLAIN path as well as in the bucket path).
+    # What the test checks -- which trainer's buffers and whose optimizer state each step used -- does not need big steps.
+    kw = dict(gmax=8, learning_rate=1e-7)
 
     def batch(model, i, hw):
         ex = synthetic.make_batch(60 + i, 1, hw[0], hw[1], K, max_boxes=4, num_windows=16)
@@ -72,12 +76,14 @@ def test_two_shapes_share_one_model(graph):
     torch.cuda.synchronize()
     assert len(got) == 3 and bt.global_step == 3 and sorted(bt.buckets) == [(224, 288), (224, 320)]
     assert all(abs(v) < 1e3 for v in want[0].values()), want[0]          # a well-conditioned start (see the note above)
-    for a, b in zip(want, got):
+    for i, (a, b) in enumerate(zip(want, got)):
         for k in a:
             assert np.isfinite(b[k]) and abs(a[k] - b[k]) <= max(2e-3 * max(1.0, abs(a[k])), 4 * noise[k]), \
-                (k, a[k], b[k], noise[k])
+                ("step %d" % i, k, a[k], b[k], noise[k], want, got)
     assert abs(got[0]["total_loss"] - got[1]["total_loss"]) > 1e-4
-    torch.testing.assert_close(model.param_store.w, state[0], rtol=0, atol=1e-5)
+    torch.testing.assert_close(model.param_store.w, state[0], rtol=0, atol=2e-7)
+    w0 = fresh_model().param_store.w
+    assert float((model.param_store.w - w0).abs().max()) > 1e-6            # three updates did move the weights
 
     def rel(a, b):
         return float((a - b).norm() / b.norm().clamp_min(1e-20))

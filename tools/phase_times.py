@@ -31,8 +31,16 @@ torch.cuda.synchronize()
 torch.cuda._sleep(int(80e-3 * 1.9e9))
 mark("start")
 fe = m._feature_extractor
+# marks inside predict(): after the trunk, after the RPN head, after the proposal chain
+_epf, _ppr, _rpnf = fe.extract_proposal_features, m._postprocess_rpn, m._rpn_conv.fwd
+def epf(*a, **k):
+    r = _epf(*a, **k); mark("  trunk forward (stem + block1-3)"); return r
+def ppr(*a, **k):
+    mark("  rpn conv + heads"); r = _ppr(*a, **k); mark("  proposals (decode, sort, nms, sample)"); return r
+fe.extract_proposal_features, m._postprocess_rpn = epf, ppr
 # replicate predict() with marks
-pd = m.predict(m.preprocess(image)); mark("predict (trunk+rpn+proposals+main tail+closeness)")
+pd = m.predict(m.preprocess(image)); mark("  crops + main tail + closeness tail launch")
+fe.extract_proposal_features, m._postprocess_rpn = _epf, _ppr
 pd = m.predict_with_window(pd); mark("predict_with_window")
 pd = m.predict_edgemask(pd); mark("predict_edgemask")
 pd = m.predict_with_mtl_results(pd); mark("predict_with_mtl_results (refine 1280 ROIs)")
