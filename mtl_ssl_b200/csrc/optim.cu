@@ -49,7 +49,9 @@ __device__ __forceinline__ float block_sum256(float v, float* red) {
   return t;
 }
 
-// stats[t*2+0] += sum w^2 ; stats[t*2+1] += sum (g*mult*gscale + l2*w)^2
+// stats[t*2+0] += sum w^2 ; stats[t*2+1] += sum ((g*gscale + l2*w) * mult)^2
+// (the reference multiplies the gradient of the TOTAL loss, regularisation included: trainer.py:387-402 acts on
+//  grads_and_vars of optimize_clones, model_deploy.py:265-307)
 __global__ void __launch_bounds__(256)
 opt_stats_kernel(const mtl_tensor_desc* __restrict__ td, const mtl_chunk_desc* __restrict__ cd,
                  const float* __restrict__ params, const float* __restrict__ grads, float gscale,
@@ -59,15 +61,15 @@ opt_stats_kernel(const mtl_tensor_desc* __restrict__ td, const mtl_chunk_desc* _
   const mtl_tensor_desc t = td[c.tensor];
   const long long base = t.offset + c.start;
   float sw = 0.0f, sg = 0.0f;
-  const float gm = t.grad_mult * gscale;
+  const float gm = gscale, tm = t.grad_mult, l2 = t.l2_weight;
   for (int i = threadIdx.x * 4; i < c.len; i += 256 * 4) {
     if (i + 4 <= c.len && (base & 3) == 0) {
       const float4 w = *reinterpret_cast<const float4*>(params + base + i);
       sw += w.x * w.x + w.y * w.y + w.z * w.z + w.w * w.w;
       if (t.trainable) {
         const float4 g = *reinterpret_cast<const float4*>(grads + base + i);
-        const float a = g.x * gm + t.l2_weight * w.x, b = g.y * gm + t.l2_weight * w.y;
-        const float cc = g.z * gm + t.l2_weight * w.z, d = g.w * gm + t.l2_weight * w.w;
+        const float a = (g.x * gm + l2 * w.x) * tm, b = (g.y * gm + l2 * w.y) * tm;
+        const float cc = (g.z * gm + l2 * w.z) * tm, d = (g.w * gm + l2 * w.w) * tm;
         sg += a * a + b * b + cc * cc + d * d;
       }
     } else {
@@ -75,7 +77,7 @@ opt_stats_kernel(const mtl_tensor_desc* __restrict__ td, const mtl_chunk_desc* _
         const float w = params[base + e];
         sw += w * w;
         if (t.trainable) {
-          const float a = grads[base + e] * gm + t.l2_weight * w;
+          const float a = (grads[base + e] * gm + l2 * w) * tm;
           sg += a * a;
         }
       }
@@ -138,7 +140,7 @@ opt_apply_kernel(const mtl_tensor_desc* __restrict__ td, const mtl_chunk_desc* _
     const float norm = sqrtf(stats[c.tensor * 2 + 1]);
     factor = clip / fmaxf(norm, clip);                  // tf.clip_by_norm
   }
-  const float gm = t.grad_mult * gscale;
+  const float gm = gscale, tm = t.grad_mult;
   if ((base & 3) == 0 && (c.len & 3) == 0 && (t.scale_off < 0 || (t.row_len & 3) == 0)) {
     // vector path: 4 parameters per thread, 16-byte loads / stores (8-byte for the bf16 copy)
     for (int i = threadIdx.x * 4; i < c.len; i += 256 * 4) {
@@ -152,7 +154,7 @@ opt_apply_kernel(const mtl_tensor_desc* __restrict__ td, const mtl_chunk_desc* _
       float mv[4] = {m4.x, m4.y, m4.z, m4.w};
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const float g = (gv[e] * gm + t.l2_weight * wv[e]) * factor;
+        const float g = (gv[e] * gm + t.l2_weight * wv[e]) * tm * factor;
         mv[e] = momentum * mv[e] + g;
         wv[e] = wv[e] - lr * mv[e];
       }
@@ -171,7 +173,7 @@ opt_apply_kernel(const mtl_tensor_desc* __restrict__ td, const mtl_chunk_desc* _
   for (int i = threadIdx.x; i < c.len; i += 256) {
     const long long o = base + i;
     const float w = params[o];
-    const float g = (grads[o] * gm + t.l2_weight * w) * factor;
+    const float g = (grads[o] * gm + t.l2_weight * w) * tm * factor;
     const float m = momentum * mom[o] + g;
     const float nw = w - lr * m;
     mom[o] = m;

@@ -724,8 +724,8 @@ class FasterRCNNMetaArch(model.DetectionModel):
         trunk + RPN variables in the arena), part="trunk" the RPN + trunk half; the trainer all-reduces
         the first half's gradient bucket while the second half computes."""
         pd = prediction_dict or self._last_pd
-        if part == "trunk":
-            return self._backward_trunk(pd)
+        if part in ("trunk", "trunk_hi", "trunk_lo"):
+            return self._backward_trunk(pd, None if part == "trunk" else part[6:])
         ws, fe, mtl = self._ws, self._feature_extractor, self._mtl
         feat = pd["rpn_features_to_crop"]
         B, Hf, Wf, C = feat.shape
@@ -805,41 +805,60 @@ class FasterRCNNMetaArch(model.DetectionModel):
             return
         self._backward_trunk(pd)
 
-    def _backward_trunk(self, pd):
+    def _backward_trunk(self, pd, half=None):
+        """half=None: the whole RPN + trunk backward.  "hi" / "lo": its two halves (RPN and the later trunk units, then
+        the earlier ones), for a trainer that exchanges the first half's gradient bucket while the second computes."""
         ws, fe = self._ws, self._feature_extractor
         feat = pd["rpn_features_to_crop"]
         dfeat = ws.bufs["bwd/dfeat_f32"]
         # Weight gradients only feed the optimizer: where every gradient tensor of the chain keeps its own buffer until
-        # the end of the pass (`deferred_wgrad_safe`), the RPN + trunk dgrad chain runs first and undisturbed, then all
-        # of its weight-gradient GEMMs run as a few grouped, machine-filling launches (ops_conv.WgradCollector).
+        # the end of the pass (`deferred_wgrad_safe`), the weight-gradient GEMMs of the RPN + trunk are collected and run
+        # as grouped launches (ops_conv.WgradCollector) instead of 81 launches of 8-54 CTAs each.
         import contextlib
         col = None
         if getattr(fe, "deferred_wgrad_safe", False) and ops_conv.WgradCollector.enabled:
             col = self._trunk_wgrads.setdefault(id(ws), ops_conv.WgradCollector())
+        if half is not None and col is None:
+            raise ValueError("the split trunk backward needs the grouped weight-gradient path")
+
+        def chunk(j):
+            # every 6 bottleneck units the collected weight-gradient problems go to a side stream as one grouped
+            # launch sized for 64 SMs; the dgrad chain (<= 76 CTAs per layer at batch 1) keeps the rest
+            with torch.cuda.stream(Concurrency.fork()):
+                col.flush(max_ctas=self._wgrad_chunk_ctas, key=j)
+
         with (col if col is not None else contextlib.nullcontext()):
-            # RPN head and conv; the conv's dgrad epilogue merges the fp32 ROI/edgemask gradient and
-            # applies the ReLU mask of the trunk output
-            rpn_feat = pd["rpn_box_predictor_features"]
-            d_rpn_feat = ws.get("bwd/d_rpn_feat", rpn_feat.shape)
-            self._first_stage_box_predictor.backward(self.first_stage_box_predictor_scope, rpn_feat,
-                                                     ws.bufs["rpn/d_out"], d_rpn_feat,
-                                                     rpn_feat if self._rpn_conv.relu else None)
-            self._rpn_conv.wgrad(feat, d_rpn_feat)
-            gfeat = self._rpn_conv.dgrad(d_rpn_feat, feat.shape, ws.get("bwd/g_feat", feat.shape), res=dfeat,
-                                         mask=feat, mask_hi=fe.feature_mask_hi)
+            if half != "lo":
+                # RPN head and conv; the conv's dgrad epilogue merges the fp32 ROI/edgemask gradient and
+                # applies the ReLU mask of the trunk output
+                rpn_feat = pd["rpn_box_predictor_features"]
+                d_rpn_feat = ws.get("bwd/d_rpn_feat", rpn_feat.shape)
+                self._first_stage_box_predictor.backward(self.first_stage_box_predictor_scope, rpn_feat,
+                                                         ws.bufs["rpn/d_out"], d_rpn_feat,
+                                                         rpn_feat if self._rpn_conv.relu else None)
+                self._rpn_conv.wgrad(feat, d_rpn_feat)
+                self._g_feat = self._rpn_conv.dgrad(d_rpn_feat, feat.shape, ws.get("bwd/g_feat", feat.shape), res=dfeat,
+                                                    mask=feat, mask_hi=fe.feature_mask_hi)
             if col is not None:
-                # every 6 bottleneck units the collected weight-gradient problems go to a side stream as one grouped
-                # launch sized for 64 SMs; the dgrad chain (<= 76 CTAs per layer at batch 1) keeps the rest
-                def chunk(j):
-                    with torch.cuda.stream(Concurrency.fork()):
-                        col.flush(max_ctas=self._wgrad_chunk_ctas, key=j)
-                fe.backward_proposal_features(self.first_stage_feature_extractor_scope, gfeat, ws, every=6,
-                                              checkpoint=chunk)
+                fe.backward_proposal_features(self.first_stage_feature_extractor_scope, self._g_feat, ws, every=6,
+                                              checkpoint=chunk, part=half)
             else:
-                fe.backward_proposal_features(self.first_stage_feature_extractor_scope, gfeat, ws)
+                fe.backward_proposal_features(self.first_stage_feature_extractor_scope, self._g_feat, ws)
         if col is not None:
-            col.flush(key=0)                # the last chunk has the machine to itself
-        Concurrency.join()      # side-stream weight-gradient GEMMs must land before the optimizer
+            if half == "hi":
+                chunk(100)                  # everything of this half: its bucket is exchanged next
+            else:
+                col.flush(key=0)            # the last chunk has the machine to itself
+        Concurrency.join()      # side-stream weight-gradient GEMMs must land before the optimizer / the exchange
+
+    def gradient_buckets3(self):
+        """(second-stage bucket, trunk "hi" bucket = later trunk units + RPN, trunk "lo" bucket = the rest): contiguous
+        views of the gradient arena in the order the backward pass finishes them."""
+        st = self._store
+        heads, trunk = self.gradient_buckets()
+        pre = self._feature_extractor.trunk_split_variable(self.first_stage_feature_extractor_scope)
+        cut = next(p.offset for p in st.params if p.name.startswith(pre))
+        return heads, trunk[cut:], trunk[:cut]
 
     def _crop_backward(self, pd, dmaps, maps, pre_pool, boxes, box_ind, dfeat, tag):
         ws = self._ws

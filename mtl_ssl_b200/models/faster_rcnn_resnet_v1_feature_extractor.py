@@ -89,8 +89,13 @@ class FasterRCNNResnetV1FeatureExtractor(FasterRCNNFeatureExtractor):
             raise ValueError("image size must at least be 33 in both height and width.")
         return self._trunks[scope].fwd(preprocessed_inputs, ws, prefix)
 
-    def backward_proposal_features(self, scope, grad, ws, every=0, checkpoint=None):
-        self._trunks[scope].bwd(grad, ws, every, checkpoint)
+    def backward_proposal_features(self, scope, grad, ws, every=0, checkpoint=None, part=None):
+        self._trunks[scope].bwd(grad, ws, every, checkpoint, part)
+
+    def trunk_split_variable(self, scope):
+        """Name prefix of the first variable of the "hi" half of the trunk's backward pass (see ResNetV1.bwd)."""
+        t = self._trunks[scope]
+        return t.units[t.split_unit()].scope + "/"
 
     def extract_box_classifier_features(self, proposal_feature_maps, scope, ws, tag="main", keep=True):
         return self._tails[scope].fwd(proposal_feature_maps, ws, tag, keep)

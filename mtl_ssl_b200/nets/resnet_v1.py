@@ -178,17 +178,31 @@ class ResNetV1(object):
             x = u.fwd(x, ws, "s1")
         return x
 
-    def bwd(self, g, ws, every=0, checkpoint=None):
+    def bwd(self, g, ws, every=0, checkpoint=None, part=None):
         """g: gradient w.r.t. the trunk output, already masked by (output > 0).  `checkpoint(j)` is called after every
-        `every` units (deferred weight-gradient work is handed to a side stream in chunks while the chain goes on)."""
+        `every` units (deferred weight-gradient work is handed to a side stream in chunks while the chain goes on).
+        part="hi" stops after the unit `split_unit()` (its input gradient is kept), part="lo" resumes there: with
+        several replicas the gradient bucket of the units already done is exchanged while the rest still computes."""
         first_trainable = next(i for i, u in enumerate(self.units) if u.trainable)
-        n = 0
-        for i in range(len(self.units) - 1, first_trainable - 1, -1):
+        last = len(self.units) - 1
+        split = self.split_unit()
+        hi = last if part in (None, "hi") else split - 1
+        lo = first_trainable if part in (None, "lo") else split
+        if part == "lo":
+            g = self._g_split
+        for i in range(hi, lo - 1, -1):
             g = self.units[i].bwd(g, ws, "s1", need_dx=i > first_trainable)
-            n += 1
+            n = last - i + 1
             if every and checkpoint is not None and n % every == 0 and i > first_trainable:
                 checkpoint(n // every)
+        if part == "hi":
+            self._g_split = g
         return None
+
+    def split_unit(self):
+        """Index of the first unit of the "hi" half of the backward pass: the middle of the trainable units."""
+        first_trainable = next(i for i, u in enumerate(self.units) if u.trainable)
+        return first_trainable + (len(self.units) - first_trainable + 1) // 2
 
 
 class Block4(object):

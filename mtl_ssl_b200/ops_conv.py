@@ -172,8 +172,7 @@ class WgradCollector(object):
     def __enter__(self):
         if WgradCollector.enabled:
             assert WgradCollector.active is None
-            WgradCollector.active = self
-            self.pending = []
+            WgradCollector.active = self        # (what an earlier, unflushed pass collected stays pending)
         return self
 
     def __exit__(self, *exc):

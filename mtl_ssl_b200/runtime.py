@@ -208,6 +208,20 @@ class ParamStore(object):
         # that update underneath the next step's trunk forward pass, after `hyper` already holds the next step's values)
         self.hyper_heads = torch.zeros(4, dtype=torch.float32, device=self.device)
 
+    def set_gradient_policy(self, multiplier=None, frozen=None):
+        """Per-variable gradient post-processing of the reference trainer (object_detection/trainer.py:387-410,
+        utils/variables_helper.py:58-118), applied by the optimizer kernels from the per-tensor table:
+        `multiplier(name) -> float` scales the gradient of the total loss (task + L2 term) before the per-tensor clip;
+        `frozen(name) -> bool` removes the variable from the update altogether (no momentum, no decay; it still
+        counts in the regularisation loss, trap T4).  Rebuilds the device tables: call before the first step."""
+        for p in self.params:
+            if multiplier is not None:
+                p.grad_mult = float(multiplier(p.name))
+            if frozen is not None and frozen(p.name):
+                p.trainable = False
+        if self.finalized:
+            self._build_tables()
+
     # ------------------------------------------------------------------ kernels
     def fold(self):
         """(Re)build the bf16 compute copy from the fp32 masters (after init / load)."""

@@ -116,11 +116,7 @@ class Trainer(object):
         self.global_step = 0
         self.device = model.device
         if train_config is not None:
-            # trainer.py:387-410 of the reference post-processes the gradients with four optional knobs that no shipped
-            # config sets; they are refused rather than silently ignored
-            for knob in ("grad_multiplier", "divide_grad_by_batch", "bias_grad_multiplier", "freeze_variables"):
-                if getattr(train_config, knob, None):
-                    raise ValueError("train_config.%s is not supported on the B200 path" % knob)
+            self._apply_gradient_knobs(train_config)
             self.lr_fn, momentum = learning_schedules.from_optimizer_config(train_config.optimizer)
             clip_norm = train_config.gradient_clipping_by_norm
         else:
@@ -168,6 +164,28 @@ class Trainer(object):
         self._pd = None
         self.graph_fa = None
         self.graph_hw = None
+
+    def _apply_gradient_knobs(self, tc):
+        """trainer.py:387-410 of the reference: `grad_multiplier` / `divide_grad_by_batch` scale every gradient,
+        `bias_grad_multiplier` additionally those of variables matching '.*/biases', `freeze_variables` (regular
+        expressions, `re.match` on the variable name as variables_helper.filter_variables does) drops variables from
+        the update; all before the per-tensor clip.  They become per-tensor entries of the optimizer table."""
+        import re
+        gm = float(getattr(tc, "grad_multiplier", 0.0) or 0.0)
+        div = bool(getattr(tc, "divide_grad_by_batch", False))
+        bm = float(getattr(tc, "bias_grad_multiplier", 0.0) or 0.0)
+        freeze = [r for r in (getattr(tc, "freeze_variables", None) or []) if r]
+        if not (gm or div or bm or freeze):
+            return
+        base = (gm if gm else 1.0) / (float(tc.batch_size) if div else 1.0)
+
+        def mult(name):
+            return base * (bm if bm and re.match(".*/biases", name) else 1.0)
+
+        def frozen(name):
+            return any(re.match(r, name) for r in freeze)
+
+        self.model.param_store.set_gradient_policy(mult, frozen)
 
     # ------------------------------------------------------------------ one step
     def _bind(self, arrays):
@@ -271,9 +289,14 @@ class Trainer(object):
             m.backward(pd, part="heads")
         finally:
             m.group_head_wgrads = m.defer_head_wgrads = False
-        m.backward(None, part="trunk")
+        # several replicas: the RPN + later trunk units first, so that their gradient bucket travels while the earlier
+        # units still compute (_stage_b2)
+        m.backward(None, part="trunk" if self.world_size == 1 else "trunk_hi")
         self._pd = pd
         return pd
+
+    def _stage_b2(self):
+        self.model.backward(None, part="trunk_lo")
 
     def _stage_c(self):
         """The deferred second-stage weight gradients, as grouped launches sized to leave the trunk chain its SMs."""
@@ -337,7 +360,13 @@ class Trainer(object):
             self._heads_pending = False
         self.graph_fb.replay() if graph else self._stage_b()
         if self.world_size > 1:
-            allreduce_gradients(self.model.gradient_buckets()[1], self.world_size, self.pg)
+            # trunk bucket in two pieces, in the order the backward pass finishes them: only the second is exposed
+            _, b_hi, b_lo = self.model.gradient_buckets3()
+            w_hi = allreduce_gradients(b_hi, self.world_size, self.pg, async_op=True)
+            self.graph_fb2.replay() if graph else self._stage_b2()
+            w_lo = allreduce_gradients(b_lo, self.world_size, self.pg, async_op=True)
+            w_hi.wait()
+            w_lo.wait()
         self.graph_opt.replay() if graph else self._optimize()
         self._heads_pending = True
         if not defer:
@@ -351,6 +380,8 @@ class Trainer(object):
         if self._deferred():
             self._stage_a(image)
             self._stage_b()
+            if self.world_size > 1:
+                self._stage_b2()
             self._optimize()
             self._stage_c()
             self._optimize_heads_deferred()
@@ -583,6 +614,8 @@ class Trainer(object):
             if deferred:
                 self._stage_a(image)
                 self._stage_b()
+                if self.world_size > 1:
+                    self._stage_b2()
                 self._stage_c()             # (plans the grouped launches: not allowed while capturing)
             else:
                 self._forward_backward(image)
@@ -605,6 +638,10 @@ class Trainer(object):
             self.graph_fb = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph_fb):
                 self._stage_b()
+            if self.world_size > 1:
+                self.graph_fb2 = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph_fb2):
+                    self._stage_b2()
             self.graph_hw = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph_hw):
                 self._stage_c()

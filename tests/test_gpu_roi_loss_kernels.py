@@ -361,3 +361,42 @@ def test_psroi_fwd_bwd_matches_oracle():
     dmap = torch.zeros(B, H, W, Ct, device="cuda")
     ops.call("mtl_psroi_bwd", dout.cuda(), 16, 3, B, H, W, Ct, c0, D, 3, 3, 18, 18, boxes.cuda(), bi.cuda(), R, dmap)
     torch.testing.assert_close(dmap.cpu(), fr.grad, rtol=1e-4, atol=1e-5)
+
+
+
+def test_gradient_multipliers_and_frozen_variables():
+    """trainer.py:387-410 of the reference: scalar / bias gradient multipliers act on the gradient of the
+    total loss (task + L2 term) BEFORE the per-tensor clip, frozen variables (regular expressions) take no update at all;
+    here through ParamStore.set_gradient_policy and Trainer._apply_gradient_knobs."""
+    import types
+    from mtl_ssl_b200.runtime import ParamStore
+    from mtl_ssl_b200.trainer import Trainer
+    store = ParamStore()
+    a = store.add("Net/conv/weights", (8, 3, 3, 16), l2=1e-2, init=("normal", 1.0))
+    b = store.add("Net/conv/biases", (8,), init=("normal", 1.0))
+    c = store.add("Net/frozen_me/weights", (4, 40), l2=1e-3, init=("normal", 1.0))
+    store.finalize("cuda", seed=3)
+    tc = types.SimpleNamespace(grad_multiplier=3.0, divide_grad_by_batch=True, batch_size=2, bias_grad_multiplier=2.0,
+                               freeze_variables=["", "Net/frozen.*"])
+    holder = types.SimpleNamespace(model=types.SimpleNamespace(param_store=store))
+    Trainer._apply_gradient_knobs(holder, tc)
+    assert a.grad_mult == 1.5 and b.grad_mult == 3.0 and not c.trainable and a.trainable
+    ps = [a, b, c]
+    w0 = [p.w.cpu().clone() for p in ps]
+    gen = torch.Generator().manual_seed(4)
+    grads = [torch.randn(p.shape, generator=gen) * s for p, s in zip(ps, [20.0, 0.3, 1.0])]
+    lr, mu, clip = 0.1, 0.9, 10.0
+    store.set_hyper(lr, mu, clip)
+    for p, gr in zip(ps, grads):
+        p.g.copy_(gr.cuda())
+    reg = store.stats_and_reg_loss(1.0)
+    store.apply(1.0)
+    np.testing.assert_allclose(reg.item(), sum(p.l2 * 0.5 * (w ** 2).sum() for p, w in zip(ps, w0)).item(), rtol=1e-5)
+    for p, w, gr in zip(ps, w0, grads):
+        if not p.trainable:
+            torch.testing.assert_close(p.w.cpu(), w, rtol=0, atol=0)            # frozen: untouched
+            continue
+        g = (gr + p.l2 * w) * p.grad_mult
+        g = g * clip / max(g.norm().item(), clip)
+        torch.testing.assert_close(p.w.cpu(), w - lr * g, rtol=1e-5, atol=1e-6)
+    assert float((grads[0] + a.l2 * w0[0]).norm()) * 1.5 > clip          # the clip acted on the multiplied gradient

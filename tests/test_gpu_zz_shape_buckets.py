@@ -82,8 +82,9 @@ def test_two_shapes_share_one_model(graph):
                 ("step %d" % i, k, a[k], b[k], noise[k], want, got)
     assert abs(got[0]["total_loss"] - got[1]["total_loss"]) > 1e-4
     torch.testing.assert_close(model.param_store.w, state[0], rtol=0, atol=2e-7)
-    w0 = fresh_model().param_store.w
-    assert float((model.param_store.w - w0).abs().max()) > 1e-6            # three updates did move the weights
+    # (at this learning rate most fp32 weights do not move by an ulp: the momenta below, which accumulate all three
+    # steps' clipped gradients across the two trainers, are what shows that the optimizer state was handed over)
+    assert float(model.param_store.m.abs().max()) > 1e-3
 
     def rel(a, b):
         return float((a - b).norm() / b.norm().clamp_min(1e-20))

@@ -176,20 +176,34 @@ def test_data_parallel_gradient_exchange_gloo_world2(tmp_path):
     assert all(p.returncode == 0 for p in procs), outs
 
 
-def test_trainer_refuses_gradient_knobs_it_does_not_implement():
+def test_trainer_gradient_knobs_become_per_tensor_table_entries():
     """trainer.py:387-410 of the reference: grad_multiplier / divide_grad_by_batch / bias_grad_multiplier /
-    freeze_variables are optional gradient post-processing steps; no shipped config sets them and the B200 path does not
-    implement them, so a config that does is refused at construction instead of training differently."""
+    freeze_variables.  No shipped config sets them; a config that does gets them as per-tensor entries of the optimizer
+    table (multiplier on the total gradient before the clip, frozen = no update), with the reference's matching rule
+    (`re.match` of each regular expression on the variable name, variables_helper.py:27-55).  The arithmetic on the
+    device is checked by tests/test_gpu_roi_loss_kernels.py::test_gradient_multipliers_and_frozen_variables."""
     from mtl_ssl_b200.builders import model_builder
     from mtl_ssl_b200.trainer import Trainer
-    model = model_builder.build(load_config("model12.config").model, True, device=None)
-    for line in ("bias_grad_multiplier: 2.0", "freeze_variables: '.*conv1.*'", "grad_multiplier: 0.5",
-                 "divide_grad_by_batch: true"):
+
+    def build(*lines):
         cfg = load_config("model12.config", (("gradient_clipping_by_norm: 10.0",
-                                              "gradient_clipping_by_norm: 10.0\n  " + line),))
-        assert getattr(cfg.train_config, line.split(":")[0])
-        with pytest.raises(ValueError, match=line.split(":")[0]):
-            Trainer(model, cfg.train_config, 600, 1000, 1)
+                                              "gradient_clipping_by_norm: 10.0\n  " + "\n  ".join(lines)),))
+        model = model_builder.build(cfg.model, True, device=None)
+        Trainer(model, cfg.train_config, 600, 1000, 1)
+        return model.param_store
+
+    st = build("bias_grad_multiplier: 2.0")
+    assert all(p.grad_mult == (2.0 if p.name.endswith("/biases") else 1.0) for p in st.params)
+    assert any(p.name.endswith("/biases") for p in st.params)
+    st = build("grad_multiplier: 0.5", "divide_grad_by_batch: true")          # batch_size 1 in model12.config
+    assert all(p.grad_mult == 0.5 for p in st.params)
+    st = build("freeze_variables: '.*block2.*'", "freeze_variables: 'FirstStageBoxPredictor/Conv'")
+    frozen = [p.name for p in st.params if not p.trainable]
+    assert any("/block2/" in n for n in frozen) and "FirstStageBoxPredictor/Conv/weights" in frozen
+    base = model_builder.build(load_config("model12.config").model, True, device=None).param_store
+    newly = set(frozen) - {p.name for p in base.params if not p.trainable}
+    assert newly and all("/block2/" in n or n.startswith("FirstStageBoxPredictor/Conv") for n in newly)
+    assert "FirstStageBoxPredictor/ClassPredictor/weights" not in newly       # re.match anchors at the start
 
 
 def test_resize_to_range_output_sizes_match_reference_vectors():
