@@ -157,13 +157,15 @@ class Trainer(object):
         # forward pass + proposal chain (a latency-bound stretch that leaves most SMs idle at batch 1).
         import os
         self.defer_heads = os.environ.get("MTL_NO_DEFER_HEADS") is None
-        self._deferred_ctas = int(os.environ.get("MTL_DEFERRED_CTAS", "48"))
+        self._deferred_ctas = int(os.environ.get("MTL_DEFERRED_CTAS", "48" if world_size == 1 else "72"))
         self._heads_pending = False     # a head update is waiting for the next step (or finish())
         self._head_stats_valid = False  # the head tensors' squared norms (regularisation loss) match the current weights
         model.param_store.post_load_hooks.append(self._weights_replaced)
         self._pd = None
         self.graph_fa = None
         self.graph_hw = None
+        self.graph_ft = None
+        self.graph_ft2 = None
 
     def _apply_gradient_knobs(self, tc):
         """trainer.py:387-410 of the reference: `grad_multiplier` / `divide_grad_by_batch` scale every gradient,
@@ -272,8 +274,8 @@ class Trainer(object):
         self._pd = m.predict_first_stage(pre, prefix=prefix) if prefix is not None else m.predict_first_stage(pre)
 
     def _stage_b(self):
-        """Second-stage forward, the eight losses, the whole backward pass; the second-stage weight-gradient GEMMs are
-        only collected (model.flush_head_wgrads runs them, see _stage_c)."""
+        """Second-stage forward, the eight losses, the second-stage half of the backward pass; its weight-gradient
+        GEMMs are only collected (model.flush_head_wgrads runs them, see _stage_c)."""
         m = self.model
         mtl = m._mtl
         pd = m.predict_second_stage(self._pd)
@@ -289,17 +291,20 @@ class Trainer(object):
             m.backward(pd, part="heads")
         finally:
             m.group_head_wgrads = m.defer_head_wgrads = False
-        # several replicas: the RPN + later trunk units first, so that their gradient bucket travels while the earlier
-        # units still compute (_stage_b2)
-        m.backward(None, part="trunk" if self.world_size == 1 else "trunk_hi")
         self._pd = pd
         return pd
 
-    def _stage_b2(self):
+    def _stage_t(self):
+        """RPN + trunk backward.  Several replicas: the RPN and the later trunk units only, so that their gradient
+        bucket travels while the earlier units still compute (_stage_t2)."""
+        self.model.backward(None, part="trunk" if self.world_size == 1 else "trunk_hi")
+
+    def _stage_t2(self):
         self.model.backward(None, part="trunk_lo")
 
     def _stage_c(self):
-        """The deferred second-stage weight gradients, as grouped launches sized to leave the trunk chain its SMs."""
+        """The collected second-stage weight gradients, as grouped launches sized to leave the latency-bound trunk
+        chains beside them their SMs."""
         self.model.flush_head_wgrads(max_ctas=self._deferred_ctas)
 
     def _optimize_heads_deferred(self):
@@ -312,63 +317,75 @@ class Trainer(object):
         # refresh the head tensors' entries now (the trunk's are refreshed by that step's own trunk update)
         st.stats_range(t0, st.num_tensors, gs)
 
-    def _launch_deferred(self, cur):
-        """Side stream: head weight gradients -> (several replicas: all-reduce of that bucket) -> head update."""
-        graph = self.use_graph and self.graph_hw is not None
-        if self._opt_stream is None:
-            self._opt_stream = torch.cuda.Stream()
-        self._opt_stream.wait_stream(cur)
-        with torch.cuda.stream(self._opt_stream):
-            self.graph_hw.replay() if graph else self._stage_c()
-            if self.world_size > 1:
-                allreduce_gradients(self.model.gradient_buckets()[0], self.world_size, self.pg)
-            self.graph_opt_heads.replay() if graph else self._optimize_heads_deferred()
-        self._head_stats_valid = True
-
     def _weights_replaced(self):
         self._head_stats_valid = False
 
     def finish(self):
-        """Apply a pending deferred head update now (before reading or saving weights, evaluating, or handing the model
-        to another trainer).  No-op when nothing is pending."""
+        """Wait for a head update that is still in flight on the side stream (before reading or saving weights,
+        evaluating, or handing the model to another trainer).  No-op when nothing is pending."""
         if self._heads_pending:
-            cur = torch.cuda.current_stream()
-            self._launch_deferred(cur)
-            cur.wait_stream(self._opt_stream)
+            torch.cuda.current_stream().wait_stream(self._opt_stream)
             self._heads_pending = False
 
     def _run_step_deferred(self, lookahead, defer):
-        """trunk forward + proposals (A) || previous step's head update (C)  ->  second stage, losses, backward (B)  ->
-        [all-reduce of the trunk bucket]  ->  trunk update (D).  The head update of THIS step stays pending."""
+        """main stream:  A trunk forward + proposals -> [wait for the previous head update] -> B second stage, losses,
+                         second-stage backward -> T trunk backward (+ exchange of the trunk bucket in two pieces) ->
+                         D trunk update
+        side stream:     C the second-stage weight-gradient GEMMs (grouped launches on a share of the SMs), the exchange
+                         of the second-stage bucket and its update -- after D, i.e. underneath the NEXT step's A, a
+                         latency-bound chain that leaves most SMs idle at batch 1 (several replicas: the weight
+                         gradients start right after B, underneath T).
+        Nothing on the main stream waits for the side stream until the next step needs a second-stage weight."""
         graph = self.use_graph
         cur = torch.cuda.current_stream()
         image = self.inputs.dev["image"]
+        if self._opt_stream is None:
+            self._opt_stream = torch.cuda.Stream()
+        side = self._opt_stream
         if self._prefix_cur is not None and not lookahead:
             self.graph_prefix.replay() if graph else self._prefix(image)
-        had = self._heads_pending
-        if had:
-            self._launch_deferred(cur)
-        elif not self._head_stats_valid:
+        if not self._heads_pending and not self._head_stats_valid:
             # first step (or the weights were replaced): no head update precedes this step, so nothing has computed
             # the head tensors' squared norms that the regularisation loss sums
             st = self.model.param_store
             st.stats_range(self.model.head_tensor_range()[0], st.num_tensors, data_parallel_scale(self.world_size))
             self._head_stats_valid = True
         self.graph_fa.replay() if graph else self._stage_a(image)
-        if had:
-            cur.wait_stream(self._opt_stream)      # every second-stage weight is final from here on
+        if self._heads_pending:
+            cur.wait_stream(side)               # every second-stage weight is final from here on
             self._heads_pending = False
         self.graph_fb.replay() if graph else self._stage_b()
+        early = self.world_size > 1
+        if early:
+            # several replicas: the side stream also has the head bucket's exchange to fit in before the next step's
+            # second stage, so the weight gradients start now, underneath the trunk backward
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                self.graph_hw.replay() if graph else self._stage_c()
+        self.graph_ft.replay() if graph else self._stage_t()
         if self.world_size > 1:
             # trunk bucket in two pieces, in the order the backward pass finishes them: only the second is exposed
             _, b_hi, b_lo = self.model.gradient_buckets3()
             w_hi = allreduce_gradients(b_hi, self.world_size, self.pg, async_op=True)
-            self.graph_fb2.replay() if graph else self._stage_b2()
+            self.graph_ft2.replay() if graph else self._stage_t2()
             w_lo = allreduce_gradients(b_lo, self.world_size, self.pg, async_op=True)
             w_hi.wait()
             w_lo.wait()
         self.graph_opt.replay() if graph else self._optimize()
+        # (the head bucket is exchanged AFTER the trunk pieces were issued: collectives of one communicator run in
+        # issue order, and the trunk's are the ones the main stream waits for)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            if not early:
+                # one replica: measured best with all of it underneath the next step's trunk forward + proposal chain
+                # (same box, B200: 7.30 ms/step against 7.58 with the weight gradients under the trunk backward and
+                # 7.66-7.69 with the round-1 schedule)
+                self.graph_hw.replay() if graph else self._stage_c()
+            if self.world_size > 1:
+                allreduce_gradients(self.model.gradient_buckets()[0], self.world_size, self.pg)
+            self.graph_opt_heads.replay() if graph else self._optimize_heads_deferred()
         self._heads_pending = True
+        self._head_stats_valid = True
         if not defer:
             self.finish()
 
@@ -380,10 +397,11 @@ class Trainer(object):
         if self._deferred():
             self._stage_a(image)
             self._stage_b()
-            if self.world_size > 1:
-                self._stage_b2()
-            self._optimize()
             self._stage_c()
+            self._stage_t()
+            if self.world_size > 1:
+                self._stage_t2()
+            self._optimize()
             self._optimize_heads_deferred()
             return
         self._forward_backward(image)
@@ -614,9 +632,10 @@ class Trainer(object):
             if deferred:
                 self._stage_a(image)
                 self._stage_b()
-                if self.world_size > 1:
-                    self._stage_b2()
                 self._stage_c()             # (plans the grouped launches: not allowed while capturing)
+                self._stage_t()
+                if self.world_size > 1:
+                    self._stage_t2()
             else:
                 self._forward_backward(image)
                 if self.world_size > 1:
@@ -638,13 +657,16 @@ class Trainer(object):
             self.graph_fb = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph_fb):
                 self._stage_b()
-            if self.world_size > 1:
-                self.graph_fb2 = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(self.graph_fb2):
-                    self._stage_b2()
             self.graph_hw = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph_hw):
                 self._stage_c()
+            self.graph_ft = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_ft):
+                self._stage_t()
+            if self.world_size > 1:
+                self.graph_ft2 = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph_ft2):
+                    self._stage_t2()
             self.graph_opt_heads = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph_opt_heads):
                 self._optimize_heads_deferred()

@@ -207,7 +207,7 @@ for overlap in (True, False):
     tr._forward_backward, tr._backward_trunk = fb2, bt2
     # deferred-head schedule (overlap on): one pass fills both buckets; the trunk bucket is exchanged right after it,
     # the head bucket in finish() -- after the deferred weight-gradient launches, before the head update
-    sb, sb_lo = tr._stage_b, tr._stage_b2
+    sb, sb_lo = tr._stage_t, tr._stage_t2
     _, t_hi, t_lo = model.gradient_buckets3()
     assert t_hi.numel() + t_lo.numel() == trunk.numel() and t_hi.numel() > 0 and t_lo.numel() > 0
     def sb2():
@@ -219,7 +219,7 @@ for overlap in (True, False):
     def sb3():
         sb_lo()
         t_lo.fill_(float(10 * (rank + 1)))
-    tr._stage_b, tr._stage_b2 = sb2, sb3
+    tr._stage_t, tr._stage_t2 = sb2, sb3
     assert tr._deferred() == overlap
     ex = synthetic.make_batch(60 + rank, 1, 224, 320, 20, max_boxes=4, num_windows=16)
     ky = synthetic.make_sampler_keys(70 + rank, 1, model.num_kept_anchors((1, 224, 320, 3)), 100)
@@ -243,7 +243,7 @@ for overlap in (True, False):
     assert tr.graph_fb.replays >= 2 and tr.graph_opt.replays >= 2
     if overlap:         # deferred heads: first-stage graph, second-stage + backward graphs, deferred wgrads, head update
         assert tr.graph_fa.replays >= 2 and tr.graph_hw.replays >= 2 and tr.graph_opt_heads.replays >= 2
-        assert tr.graph_fb2.replays >= 2
+        assert tr.graph_ft.replays >= 2 and tr.graph_ft2.replays >= 2
         assert not tr._heads_pending                                  # flush() applied the last head update
     else:
         assert tr.graph_fb2.replays >= 2 and tr.graph_opt_heads is None

@@ -67,6 +67,49 @@ for graph in (False, True):
               % (graph, float(dw_ref.norm()), err), flush=True)
         assert err < 2e-3, err
     dist.barrier()
+# the pipelined API (deferred head update: its weight gradients, the all-reduce of that bucket and its optimizer pass run
+# under the NEXT step's trunk forward; the trunk bucket travels in two pieces): replicas must stay bit-identical, and the
+# losses of every step must equal those of the synchronous API on the same batches
+for graph in (False, True):
+    seqs = []
+    for mode in ("sync", "pipe"):
+        model = build()
+        nk = model.num_kept_anchors((B, H, W, 3))
+        tr = Trainer(model, cfg.train_config, H, W, B, gmax=16, use_cuda_graph=graph, world_size=world)
+        # a vanishing learning rate: with random-init weights thousands of anchors have nearly equal scores, and the
+        # last-bit run-to-run noise of the fp32 atomics, scaled by a real learning rate, flips a proposal now and then
+        # (observed: second_stage_localization_loss 0.0 vs 0.0075 at one of four steps) -- in ANY two runs, whatever
+        # the API.  What is compared here is the plumbing: same batches, same order of updates, same optimizer state.
+        tr.lr_fn = lambda step: 1e-8
+        out = []
+        for i in range(4):
+            b = batch(10 * rank + i, tr, nk)
+            r = tr.step(b) if mode == "sync" else tr.step_pipelined(b)
+            if r is not None:
+                out.append(r)
+        if mode == "pipe":
+            out.append(tr.flush())
+        torch.cuda.synchronize()
+        assert len(out) == 4 and not tr._heads_pending
+        got_w = model.param_store.w.clone()
+        ref = got_w.clone()
+        dist.broadcast(ref, 0)
+        assert torch.equal(ref, got_w), "ranks diverged (%s, graph=%s)" % (mode, graph)
+        got_m = model.param_store.m.clone()
+        ref = got_m.clone()
+        dist.broadcast(ref, 0)
+        assert torch.equal(ref, got_m), "momenta diverged (%s, graph=%s)" % (mode, graph)
+        seqs.append((out, got_w, got_m))
+    for a, b in zip(seqs[0][0], seqs[1][0]):
+        for k in a:
+            assert abs(a[k] - b[k]) <= 1e-4 * max(1.0, abs(a[k])), (k, a[k], b[k])
+    rel = float((seqs[0][1] - seqs[1][1]).norm() / seqs[0][1].norm())
+    relm = float((seqs[0][2] - seqs[1][2]).norm() / seqs[0][2].norm())
+    if rank == 0:
+        print("graph=%s  pipelined vs synchronous API over 4 steps: losses equal, weights differ by %.2e, momenta "
+              "(= the accumulated clipped gradients of all four steps) by %.2e (relative)" % (graph, rel, relm), flush=True)
+    assert rel < 1e-6 and relm < 2e-3
+    dist.barrier()
 if rank == 0:
     print("dp_check ok")
 dist.destroy_process_group()
