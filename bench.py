@@ -232,7 +232,7 @@ class CpuReference(object):
         total.backward()
         dt = time.perf_counter() - t0
         ld = {k: float(v.detach()) for k, v in losses.items()}
-        ld["regularization_loss"] = float(reg.detach())
+        ld["regularization_loss"] = float(reg.detach()) if hasattr(reg, "detach") else float(reg)   # (0.0: no L2 term)
         ld["total_loss"] = float(total.detach())
         return dt, ld
 

@@ -49,7 +49,7 @@ def batches(examples, batch_size, drop_remainder=True):
         yield group
 
 
-def input_examples(train_input_reader, num_classes, options=(), seed=0, epochs=None):
+def input_examples(train_input_reader, num_classes, options=(), seed=0, epochs=None, start_epoch=0):
     """Examples of the pipeline config's `train_input_reader { tf_record_input_reader { input_path: ... } }`, shuffled
     per file when `shuffle` is set, augmented by the `data_augmentation_options` named in `options`
     (only random_horizontal_flip is built), repeated `epochs` times (None = forever)."""
@@ -62,9 +62,11 @@ def input_examples(train_input_reader, num_classes, options=(), seed=0, epochs=N
     unknown = [o for o in options if o != "random_horizontal_flip"]
     if unknown:
         raise NotImplementedError("data augmentation options not built: %s" % unknown)
-    rng = np.random.default_rng(seed)
-    epoch = 0
-    while epochs is None or epoch < epochs:
+    # `start_epoch`: a resumed run passes global_step * batch // records-per-epoch so that record order and flips go on
+    # from where they were instead of replaying epoch 0 (the augmentation generator is seeded by (seed, start_epoch))
+    rng = np.random.default_rng([seed, start_epoch])
+    epoch = start_epoch
+    while epochs is None or epoch < start_epoch + epochs:
         ds = TfRecordDataset(paths, num_classes, shuffle=bool(train_input_reader.shuffle),      # proto default: true
                              seed=seed + epoch)
         for e in ds:

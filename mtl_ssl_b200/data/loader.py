@@ -65,10 +65,13 @@ class PrefetchLoader(object):
         self._thread.join(timeout=5)
 
 
-def sampler_keys_fn(seed, batch_size, num_anchors, num_proposals):
-    """Per-step explicit sampler keys (uniform [0,1) per anchor / proposal), seeded by (seed, step)."""
+def sampler_keys_fn(seed, batch_size, num_anchors, num_proposals, start_step=0, rank=0):
+    """Per-step explicit sampler keys (uniform [0,1) per anchor / proposal), seeded by (seed, rank, global step).
+    `start_step`: the trainer's global_step when the loader is (re)built -- a run resumed from a checkpoint continues
+    the key sequence instead of replaying the keys of steps 0..k; `rank`: data-parallel replicas draw different keys."""
     def fn(step):
-        return synthetic.make_sampler_keys(seed * 1000003 + step, batch_size, num_anchors, num_proposals)
+        return synthetic.make_sampler_keys((seed * 1000003 + rank) * 1000033 + start_step + step, batch_size,
+                                           num_anchors, num_proposals)
     return fn
 
 

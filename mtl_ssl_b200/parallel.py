@@ -21,3 +21,13 @@ def allreduce_gradients(flat_grads, world_size, group=None, async_op=False):
         work = dist.all_reduce(flat_grads, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
         return work if async_op else flat_grads
     return None if async_op else flat_grads
+
+
+def average_losses(task_losses, world_size, group=None):
+    """The logged task losses of a data-parallel step: sum over the replicas / num_replicas, in place (what the
+    reference's TotalLoss is made of: every clone's loss is divided by num_clones and the clones are summed,
+    model_deploy.py:221-225).  The regularisation term is identical on every replica and is not exchanged."""
+    if world_size > 1:
+        dist.all_reduce(task_losses, op=dist.ReduceOp.SUM, group=group)
+        task_losses.mul_(1.0 / float(world_size))
+    return task_losses

@@ -17,7 +17,7 @@ import numpy as np
 import torch
 
 from .meta_architectures.faster_rcnn_meta_arch import LOSS_KEYS
-from .parallel import allreduce_gradients, data_parallel_scale
+from .parallel import allreduce_gradients, average_losses, data_parallel_scale
 from .utils import learning_schedules
 
 
@@ -383,6 +383,7 @@ class Trainer(object):
                 self.graph_hw.replay() if graph else self._stage_c()
             if self.world_size > 1:
                 allreduce_gradients(self.model.gradient_buckets()[0], self.world_size, self.pg)
+                average_losses(self._loss_dev[:8], self.world_size, self.pg)      # logged values only: off the main stream
             self.graph_opt_heads.replay() if graph else self._optimize_heads_deferred()
         self._heads_pending = True
         self._head_stats_valid = True
@@ -525,6 +526,7 @@ class Trainer(object):
             w1.wait()
         w2.wait()
         self.graph_opt.replay() if graph else self._optimize()
+        average_losses(self._loss_dev[:8], self.world_size, self.pg)
 
     def host_arrays(self, examples, keys):
         arrays = pack_groundtruth(examples, self.model.num_classes, self.Hr, self.Wr, self.gmax)
@@ -594,9 +596,12 @@ class Trainer(object):
         self._attach()
         self._run_step_body(lookahead=self._prefix_cur is not None, defer=True)
         self.global_step += 1
-        self._loss_slots[slot].copy_(self._loss_dev, non_blocking=True)
+        # (several replicas, deferred schedule: the replica-averaged losses are produced on the side stream)
+        ls = self._opt_stream if (self.world_size > 1 and self._deferred()) else cur
+        with torch.cuda.stream(ls):
+            self._loss_slots[slot].copy_(self._loss_dev, non_blocking=True)
         done = torch.cuda.Event()
-        done.record(cur)
+        done.record(ls)
         prev, self._pending = self._pending, ("event", done, slot)
         return self._resolve(prev)
 
@@ -619,7 +624,9 @@ class Trainer(object):
         v = (self._loss_host if buf is None else buf).tolist()
         out = {k: v[i] for i, k in enumerate(LOSS_KEYS)}
         out["regularization_loss"] = v[8]
-        # model_deploy.py:198-236: sum of task losses / num_clones + regularisation
+        # model_deploy.py:198-236: sum over the clones of (task losses / num_clones) + regularisation; with several
+        # replicas the eight task losses were averaged over the replicas on the device (parallel.average_losses), so
+        # every rank reports the same, global value
         out["total_loss"] = sum(v[:8]) + v[8]
         return out
 

@@ -201,7 +201,7 @@ class CheckpointReader(object):
             raise ValueError("%s: data file does not hold %d bytes at offset %d" % (name, e["size"], e["offset"]))
         if self.check_crc and e["crc32c"] is not None and masked_crc32c(raw.tobytes()) != e["crc32c"]:
             raise ValueError("%s: tensor checksum mismatch" % name)
-        return raw.view(dt.newbyteorder("<")).astype(dt).reshape(e["shape"])
+        return raw.view(dt.newbyteorder("<")).astype(dt).reshape(tuple(e["shape"]))
 
 
 def write_checkpoint(prefix, tensors):

@@ -314,3 +314,60 @@ def test_fc_and_packed_stem_variables_through_a_written_bundle(tmp_path):
     assert s.shape == (32, 1, 1, 64) and s[4, 0, 0, (2 * 3 + 1) * 3 + 2] == stem[2, 1, 2, 4] and not s[..., 27:].any()
     with pytest.raises(ValueError):        # without the kinds the old rank rule gives (84, 2048) / (32, 3, 3, 3): refused
         C.state_dict_from_checkpoint(C.CheckpointReader(prefix), name_map, shapes, None)
+
+
+def test_reader_against_the_independently_assembled_bundle_fixture():
+    """N4: tests/golden/tf_bundle_fixture.* was assembled from the published tensor-bundle / LevelDB
+    table format by tests/golden/make_bundle_fixture.py with NONE of this module's code (protobuf runtime for the two
+    protos, its own table builder with 16-entry restart intervals, several data blocks and shortened index separators,
+    a bit-by-bit CRC-32C).  The reader must find every variable, with dtype, shape (incl. the 0-d int64 global_step)
+    and values, verify all checksums, and convert the layouts a model needs."""
+    import os
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    prefix = os.path.join(here, "tf_bundle_fixture")
+    exp = np.load(prefix + "_expected.npz")
+    r = C.CheckpointReader(prefix)                       # check_crc=True: every block trailer
+    names = {k.replace("|", "/"): k for k in exp.files}
+    assert set(r.get_variable_to_shape_map()) == set(names) and len(names) == 32
+    for n, k in names.items():
+        a = r.get_tensor(n)                              # verifies the tensor's own CRC
+        assert a.dtype == exp[k].dtype and a.shape == exp[k].shape and np.array_equal(a, exp[k]), n
+    assert r.get_tensor("global_step").shape == () and int(r.get_tensor("global_step")) == 123456
+    # layouts: HWIO conv -> [K,R,S,C]; slim.fully_connected [in,out] -> GEMM operand [out,1,1,in]; RGB stem conv
+    # [3,3,3,32] -> packed im2col rows [32,1,1,64]; depthwise [3,3,C,1] -> [C,3,3,1]; Momentum slot like its variable
+    scope = "FirstStageFeatureExtractor/resnet_v1_101/block3/unit_7/bottleneck_v1/conv2"
+    name_map = {scope + "/weights": scope + "/weights", scope + "/BatchNorm/moving_variance": scope + "/BatchNorm/moving_variance",
+                "SecondStageBoxPredictor/ClassPredictor/weights": "SecondStageBoxPredictor/ClassPredictor/weights",
+                "FirstStageFeatureExtractor/MobilenetV1/Conv2d_0/weights": "FirstStageFeatureExtractor/MobilenetV1/Conv2d_0/weights",
+                "FirstStageFeatureExtractor/MobilenetV1/Conv2d_1_depthwise/depthwise_weights":
+                    "FirstStageFeatureExtractor/MobilenetV1/Conv2d_1_depthwise/depthwise_weights",
+                "not/in/the/file": "x"}
+    shapes = {scope + "/weights": (24, 3, 3, 16), "SecondStageBoxPredictor/ClassPredictor/weights": (21, 1, 1, 40),
+              "FirstStageFeatureExtractor/MobilenetV1/Conv2d_0/weights": (32, 1, 1, 64)}
+    kinds = {"SecondStageBoxPredictor/ClassPredictor/weights": "fc",
+             "FirstStageFeatureExtractor/MobilenetV1/Conv2d_0/weights": ("packed_conv", 3, 3, 3)}
+    sd, missing = C.state_dict_from_checkpoint(r, name_map, shapes, kinds)
+    assert missing == ["not/in/the/file"]
+    w = exp[names[scope + "/weights"]]
+    assert sd[scope + "/weights"][5, 1, 2, 7] == w[1, 2, 7, 5]
+    fc = exp[names["SecondStageBoxPredictor/ClassPredictor/weights"]]
+    assert sd["SecondStageBoxPredictor/ClassPredictor/weights"][3, 0, 0, 17] == fc[17, 3]
+    stem = exp[names["FirstStageFeatureExtractor/MobilenetV1/Conv2d_0/weights"]]
+    assert sd["FirstStageFeatureExtractor/MobilenetV1/Conv2d_0/weights"][9, 0, 0, (2 * 3 + 0) * 3 + 1] == stem[2, 0, 1, 9]
+    dw = exp[names["FirstStageFeatureExtractor/MobilenetV1/Conv2d_1_depthwise/depthwise_weights"]]
+    assert sd["FirstStageFeatureExtractor/MobilenetV1/Conv2d_1_depthwise/depthwise_weights"].shape == (32, 3, 3, 1)
+    assert sd["FirstStageFeatureExtractor/MobilenetV1/Conv2d_1_depthwise/depthwise_weights"][4, 1, 2, 0] == dw[1, 2, 4, 0]
+    mom = C.tf_to_native(scope + "/weights", r.get_tensor(scope + "/weights/Momentum"))
+    assert mom.shape == (24, 3, 3, 16)
+    # a flipped byte in the data file is caught by the tensor checksum
+    import shutil, tempfile
+    d = tempfile.mkdtemp()
+    for ext in (".index", ".data-00000-of-00001"):
+        shutil.copy(prefix + ext, os.path.join(d, "b" + ext))
+    raw = bytearray(open(os.path.join(d, "b.data-00000-of-00001"), "rb").read())
+    raw[100] ^= 0x40
+    open(os.path.join(d, "b.data-00000-of-00001"), "wb").write(bytes(raw))
+    bad = C.CheckpointReader(os.path.join(d, "b"))
+    with pytest.raises(ValueError):
+        for n in names:
+            bad.get_tensor(n)
