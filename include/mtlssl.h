@@ -67,6 +67,17 @@ typedef struct mtl_conv_args {
 int mtl_conv_tc(const mtl_conv_args* args /* host */, mtl_stream_t stream);
 /* bytes of zeroed workspace mtl_conv_tc would use to split the K loop of this fprop/dgrad (0 = no split) */
 long long mtl_conv_tc_ws_bytes(const mtl_conv_args* args /* host */);
+/* Grouped launch: n INDEPENDENT problems of one kernel instance (equal mtl_conv_tc_group_key) in one persistent grid
+ * whose CTAs walk the concatenated tile space (the trunk's 81 weight-gradient GEMMs at batch 1 become a few launches).
+ * build() plans the problems into a table in HOST memory (n x entry_bytes, 128-byte aligned; info[4] = total tiles, tile
+ * width, mode, operand path; K of a weight-gradient problem is cut into pieces of ~target_k_iters 64-deep steps, 0 =
+ * never); the caller copies the table to device memory once and keeps both alive; launch() only enqueues. */
+long long mtl_conv_tc_group_entry_bytes(void);
+long long mtl_conv_tc_group_key(const mtl_conv_args* args /* host */);
+int mtl_conv_tc_group_build(const mtl_conv_args* args /* host */, int n, int target_k_iters, void* host_table /* host */,
+                            int* info /* host */);
+int mtl_conv_tc_group_launch(const void* host_table /* host */, const void* dev_table, int n, const int* info /* host */,
+                             int max_ctas, mtl_stream_t stream);
 
 /* ---- anchors (object_detection/anchor_generators/grid_anchor_generator.py:96-214) ------ */
 int mtl_grid_anchors(int Hf, int Wf, const float* scales /* host */, int num_scales,
@@ -167,6 +178,19 @@ int mtl_avgpool_fwd(const void* x /* bf16 [R,HW,C] */, int R, int HW, int C, voi
 int mtl_avgpool_bwd(const void* dy, int dy_fp32, long long ldy, const void* relu_mask /* bf16 [R,HW,C] or NULL */,
                     float mask_hi /* > 0: ReLU6-style upper bound */, int R, int HW, int C,
                     void* dx /* bf16 [R,HW,C] */, mtl_stream_t stream);
+/* Fused MaskRCNNBoxPredictor head (core/box_predictor.py:470-500, :568-602): spatial average over the ROI grid + the
+ * fully connected layer(s) in one kernel per ROI batch; w = the head's weight rows [n, C] bf16 (box and class matrices
+ * back to back), out = fp32 logits [R, ldo]. */
+int mtl_head_fwd(const void* x /* bf16 [R,HW,C] */, int R, int HW, int C, const void* w /* bf16 [n,C] */,
+                 const float* bias /* [n] or NULL */, int n, void* pooled /* bf16 [R,C] out */,
+                 float* out /* [R,ldo] */, long long ldo, mtl_stream_t stream);
+/* Its backward: bf16 copy of the logit gradient (operand of the weight-gradient GEMM), bias gradient (+=), and -- dx not
+ * NULL -- the gradient w.r.t. x: (d_out x w) / HW broadcast over the grid, zero where x <= 0 (or >= mask_hi > 0). */
+int mtl_head_bwd(const float* d_out /* [R,ldd] */, long long ldd, int n, const void* w /* bf16 [n,C] */,
+                 const void* x /* bf16 [R,HW,C] ReLU mask or NULL */, float mask_hi, int R, int HW, int C,
+                 void* dyb /* bf16 [R,n] out */, float* db /* [n] += or NULL */, void* dx /* bf16 [R,HW,C] or NULL */,
+                 mtl_stream_t stream);
+
 int mtl_im2col_f32(const float* img /* [B,H,W,C<=4] */, int B, int H, int W, int C, int R, int S, int stride,
                    int pad_h, int pad_w, int P, int Q, const float* mean /* host [C] or NULL */, float scale,
                    void* out /* bf16 [B*P*Q, ld] */, int ld, mtl_stream_t stream);

@@ -13,6 +13,12 @@ from ..nets.layers import Concurrency
 from .standard_fields import (BOX_ENCODINGS, CLASS_PREDICTIONS, CLASS_PREDICTIONS_WITH_BACKGROUND)
 
 
+# MaskRCNNBoxPredictor: fused pool + FC forward and fused backward (csrc/head.cu); MTL_NO_FUSED_HEAD=1 restores the
+# separate avgpool / tcgen05 GEMM / cast / colsum / avgpool_bwd launches (kept for A/B measurements)
+FUSED_HEAD = not __import__("os").environ.get("MTL_NO_FUSED_HEAD")
+FUSED_HEAD_MAX_OUT = 128      # wider heads (K = 90: 456 columns) re-read too many weight bytes per ROI: tensor-core GEMM
+
+
 def _round8(n):
     return (n + 7) // 8 * 8
 
@@ -160,9 +166,14 @@ class MaskRCNNBoxPredictor(BoxPredictor):
         head = self._heads[scope]
         R, H, W, C = image_features.shape
         pooled = ws.get("%s/%s/pooled" % (scope, tag), (R, 1, 1, C))
-        ops.call("mtl_avgpool_fwd", image_features, R, H * W, C, pooled)
         out = ws.get("%s/%s/head_out" % (scope, tag), (R, 1, 1, head.n_pad), torch.float32)
-        head.fwd(pooled, out)
+        if FUSED_HEAD and head.n_pad <= FUSED_HEAD_MAX_OUT:
+            # spatial average + both FC layers in one kernel per ROI batch (csrc/head.cu)
+            ops.call("mtl_head_fwd", image_features, R, H * W, C, head.w_bf16(), head.bias(), head.n_pad, pooled, out,
+                     head.n_pad)
+        else:
+            ops.call("mtl_avgpool_fwd", image_features, R, H * W, C, pooled)
+            head.fwd(pooled, out)
         self._saved[(scope, tag)] = (image_features, pooled)
         return out.view(R, head.n_pad)
 
@@ -193,6 +204,16 @@ class MaskRCNNBoxPredictor(BoxPredictor):
         feats, pooled = self._saved[(scope, tag)]
         R, H, W, C = feats.shape
         dyb = ws.get("%s/%s/d_head_bf16" % (scope, tag), (R, 1, 1, head.n_pad))
+        if FUSED_HEAD and head.n_pad <= FUSED_HEAD_MAX_OUT and d_out.stride(-1) == 1 and d_out.shape[-1] == head.n_pad:
+            # logit gradient -> bf16 operand of the weight-gradient GEMM, bias gradient, pooled-feature gradient and
+            # its broadcast over the ROI grid under the ReLU mask: one kernel; the weight gradient stays a GEMM
+            g = ws.get("%s/%s/d_feat" % (scope, tag), feats.shape) if need_dx else None
+            ops.call("mtl_head_bwd", d_out, d_out.stride(0), head.n_pad, head.w_bf16(), feats, self._feature_mask_hi,
+                     R, H * W, C, dyb, head.bias_grad() if head.trainable else None, g)
+            if head.trainable:
+                with torch.cuda.stream(Concurrency.fork()):
+                    oc.conv_wgrad(dyb, pooled, head.w_grad())
+            return g
         ops.call("mtl_cast_f32_bf16", d_out, d_out.numel(), 1.0, dyb)
         dpool = ws.get("%s/%s/d_pooled" % (scope, tag), (R, 1, 1, C)) if need_dx else None
         head.bwd(pooled, dyb, dpool)

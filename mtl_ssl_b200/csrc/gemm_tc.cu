@@ -69,6 +69,7 @@ struct Params {
   float* ws;                 // FPROP/DGRAD split-K: fp32 partial-sum tiles [tiles_m*tiles_n][BN/4][BM][4], all zero between launches
   int* ws_cnt;               // FPROP/DGRAD split-K: arrival counter per output tile, zero between launches
   int nprod;                 // TMA producer threads (1..3), K steps round-robin
+  int epi_fast;              // FPROP/DGRAD: the streamlined drain (64-column stores, compile-time flags) applies
 };
 
 // One problem of a grouped launch (see mtl_conv_tc_group_*): its tensor maps, parameters and the first CTA-wide tile

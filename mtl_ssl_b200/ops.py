@@ -156,4 +156,5 @@ def launch_count():
 def exported_symbols():
     """Names this module binds (used by the CPU test that checks the .so exports them all)."""
     return sorted(_SIGS) + ["mtl_conv_tc", "mtl_conv_tc_ws_bytes", "mtl_last_error_string", "mtl_abi_version",
-                            "mtl_device_sm_count", "mtl_opt_chunk_size", "mtl_launch_count"]
+                            "mtl_device_sm_count", "mtl_opt_chunk_size", "mtl_launch_count", "mtl_conv_tc_group_entry_bytes",
+                            "mtl_conv_tc_group_key"]

@@ -294,10 +294,14 @@ class Trainer(object):
         self._pd = pd
         return pd
 
+    def _split_trunk(self):
+        """Several replicas and a trunk whose backward pass can be cut in two (the ResNets): its gradient bucket is
+        exchanged in two pieces, the first while the second half still computes."""
+        return self.world_size > 1 and bool(getattr(self.model._feature_extractor, "deferred_wgrad_safe", False))
+
     def _stage_t(self):
-        """RPN + trunk backward.  Several replicas: the RPN and the later trunk units only, so that their gradient
-        bucket travels while the earlier units still compute (_stage_t2)."""
-        self.model.backward(None, part="trunk" if self.world_size == 1 else "trunk_hi")
+        """RPN + trunk backward.  Split mode: the RPN and the later trunk units only (_stage_t2 does the rest)."""
+        self.model.backward(None, part="trunk_hi" if self._split_trunk() else "trunk")
 
     def _stage_t2(self):
         self.model.backward(None, part="trunk_lo")
@@ -363,7 +367,7 @@ class Trainer(object):
             with torch.cuda.stream(side):
                 self.graph_hw.replay() if graph else self._stage_c()
         self.graph_ft.replay() if graph else self._stage_t()
-        if self.world_size > 1:
+        if self._split_trunk():
             # trunk bucket in two pieces, in the order the backward pass finishes them: only the second is exposed
             _, b_hi, b_lo = self.model.gradient_buckets3()
             w_hi = allreduce_gradients(b_hi, self.world_size, self.pg, async_op=True)
@@ -371,6 +375,8 @@ class Trainer(object):
             w_lo = allreduce_gradients(b_lo, self.world_size, self.pg, async_op=True)
             w_hi.wait()
             w_lo.wait()
+        elif self.world_size > 1:
+            allreduce_gradients(self.model.gradient_buckets()[1], self.world_size, self.pg)
         self.graph_opt.replay() if graph else self._optimize()
         # (the head bucket is exchanged AFTER the trunk pieces were issued: collectives of one communicator run in
         # issue order, and the trunk's are the ones the main stream waits for)
@@ -400,7 +406,7 @@ class Trainer(object):
             self._stage_b()
             self._stage_c()
             self._stage_t()
-            if self.world_size > 1:
+            if self._split_trunk():
                 self._stage_t2()
             self._optimize()
             self._optimize_heads_deferred()
@@ -641,7 +647,7 @@ class Trainer(object):
                 self._stage_b()
                 self._stage_c()             # (plans the grouped launches: not allowed while capturing)
                 self._stage_t()
-                if self.world_size > 1:
+                if self._split_trunk():
                     self._stage_t2()
             else:
                 self._forward_backward(image)
@@ -670,7 +676,7 @@ class Trainer(object):
             self.graph_ft = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph_ft):
                 self._stage_t()
-            if self.world_size > 1:
+            if self._split_trunk():
                 self.graph_ft2 = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(self.graph_ft2):
                     self._stage_t2()

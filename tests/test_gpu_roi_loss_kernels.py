@@ -400,3 +400,45 @@ def test_gradient_multipliers_and_frozen_variables():
         g = g * clip / max(g.norm().item(), clip)
         torch.testing.assert_close(p.w.cpu(), w - lr * g, rtol=1e-5, atol=1e-6)
     assert float((grads[0] + a.l2 * w0[0]).norm()) * 1.5 > clip          # the clip acted on the multiplied gradient
+
+
+@pytest.mark.parametrize("R,HW,C,n,mask_hi", [(37, 49, 2048, 104, 0.0), (64, 16, 1024, 24, 6.0), (5, 9, 1536, 456, 0.0)])
+def test_fused_head_forward_and_backward(R, HW, C, n, mask_hi):
+    """csrc/head.cu: spatial average + FC layers (bp:470-500, :568-602) in one kernel, and their backward (logit gradient
+    -> bf16 GEMM operand, bias gradient, pooled-feature gradient broadcast over the ROI grid under the ReLU / ReLU6 mask)
+    against the same computation in torch fp32 with the device's rounding points (pooled features and their gradient are
+    bf16 tensors).  R odd: the last block holds one ROI; n = 456: the COCO box + class head."""
+    from mtl_ssl_b200 import ops
+    g = torch.Generator().manual_seed(R + n)
+    x = bf(torch.relu(torch.randn(R, HW, C, generator=g)) * (7.0 if mask_hi else 1.0)).cuda()
+    w = bf(torch.randn(n, C, generator=g) * 0.02).cuda()
+    bias = torch.randn(n, generator=g).cuda()
+    pooled = torch.empty(R, C, dtype=torch.bfloat16, device="cuda")
+    ld = n + 8
+    out = torch.zeros(R, ld, device="cuda")
+    ops.call("mtl_head_fwd", x, R, HW, C, w, bias, n, pooled, out, ld)
+    want_p = (x.float().sum(1) * (1.0 / HW)).to(torch.bfloat16)
+    # (sum order: positions ascending in both; the final scaling may round differently by one bf16 ulp)
+    torch.testing.assert_close(pooled.float(), want_p.float(), rtol=1e-2, atol=1e-6)
+    want_o = pooled.float() @ w.float().t() + bias
+    torch.testing.assert_close(out[:, :n], want_o, rtol=1e-4, atol=1e-4)
+    assert not out[:, n:].any()
+    d_out = torch.randn(R, ld, generator=g).cuda() * 0.1
+    dyb = torch.empty(R, n, dtype=torch.bfloat16, device="cuda")
+    db = torch.full((n,), 0.5, device="cuda")
+    dx = torch.empty(R, HW, C, dtype=torch.bfloat16, device="cuda")
+    ops.call("mtl_head_bwd", d_out, ld, n, w, x, mask_hi, R, HW, C, dyb, db, dx)
+    want_dy = d_out[:, :n].to(torch.bfloat16)
+    assert torch.equal(dyb, want_dy)
+    torch.testing.assert_close(db, 0.5 + want_dy.float().sum(0), rtol=1e-4, atol=1e-4)
+    dp = (want_dy.float() @ w.float()).to(torch.bfloat16).float() * (1.0 / HW)
+    alive = x.float() > 0
+    if mask_hi:
+        alive &= x.float() < mask_hi
+    want_dx = torch.where(alive, dp[:, None, :].expand(R, HW, C), torch.zeros(())).to(torch.bfloat16)
+    torch.testing.assert_close(dx.float(), want_dx.float().cuda() if not want_dx.is_cuda else want_dx.float(),
+                               rtol=2e-2, atol=1e-6)
+    assert torch.equal(dx == 0, want_dx.cuda() == 0) or float(((dx == 0) != (want_dx.cuda() == 0)).float().mean()) < 1e-4
+    # without a gradient for the features / the biases
+    ops.call("mtl_head_bwd", d_out, ld, n, w, None, 0.0, R, HW, C, dyb, None, None)
+    assert torch.equal(dyb, want_dy)

@@ -117,7 +117,9 @@ def test_cabi_library_exports_every_declared_symbol():
     assert set(ops._SIGS) <= declared
     # ... and the binding generator parsed every declaration (a ';' inside a parameter comment would drop one)
     hand_bound = {"mtl_conv_tc", "mtl_conv_tc_ws_bytes", "mtl_last_error_string", "mtl_abi_version",
-                  "mtl_device_sm_count", "mtl_opt_chunk_size", "mtl_launch_count", "mtl_set_error", "mtl_count_launch"}
+                  "mtl_device_sm_count", "mtl_opt_chunk_size", "mtl_launch_count", "mtl_set_error", "mtl_count_launch",
+                  "mtl_conv_tc_group_entry_bytes", "mtl_conv_tc_group_key", "mtl_conv_tc_group_build",
+                  "mtl_conv_tc_group_launch"}
     assert declared - set(ops._SIGS) <= hand_bound, sorted(declared - set(ops._SIGS) - hand_bound)
     assert h.mtl_abi_version() == 1
     # no torch / C++ types cross the boundary: undefined symbols must not reference at:: / c10::

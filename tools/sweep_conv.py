@@ -87,7 +87,21 @@ def kloop():
         sweep("fprop", *T, 256, 1024, 1, 1, [(bn, 1, 0)])
 
 
+def conv3():
+    """Second-stage conv3 (K loop of 8 steps, 2048 outputs, residual + ReLU): what a 128 x 256 tile costs beyond its
+    2.2 us of MMAs -- residual on / off, tile width, CTA pairs, and the K depth (slope = K step, intercept = drain)."""
+    c = [(0, 1, 0, 1), (0, 1, 0, 2), (128, 1, 0, 1), (128, 1, 0, 2), (256, 1, 3, 1), (256, 1, 2, 1)]
+    for n in (1280, 256):
+        for res in (1, 0):
+            sweep("fprop", n, 7, 7, 512, 2048, 1, res, c)
+    for C in (128, 256, 512, 1024, 2048):
+        sweep("fprop", 1280, 7, 7, C, 2048, 1, 1, [(0, 1, 0, 1)])
+        sweep("fprop", 1280, 7, 7, C, 2048, 1, 0, [(0, 1, 0, 1)])
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "conv3":
+        return conv3()
     if len(sys.argv) > 1 and sys.argv[1] == "pairs":
         return pairs()
     if len(sys.argv) > 1 and sys.argv[1] == "kloop":
