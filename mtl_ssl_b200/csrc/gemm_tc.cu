@@ -21,6 +21,7 @@
 // FPROP / DGRAD with a last-arriver epilogue; CTA pairs (clusters of 2) multicasting the weight tile.
 #include "common.cuh"
 #include <cuda.h>
+#include <type_traits>
 #include <stdlib.h>
 #include <string.h>
 
@@ -599,6 +600,189 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t slot_ph = 0;
     for (int gj = 0; gj < ngj; ++gj) {
     TC_PROBLEM_SETUP(gj)
+    if (MODE != WGRAD && BN >= 128 && p.epi_fast) {
+      // ---------------- streamlined drain (host: TMA epilogue, no split-K, N a multiple of 64) ----------------
+      // The generic drain below spends ~490 warp instructions per 32 x 32 chunk (ncu source view, second-stage
+      // conv3: 190 of them useful), mostly run-time flag tests, rematerialised addresses and register moves, and with
+      // two epilogue warps per scheduler it is issue-latency bound: a 128 x 256 tile takes 4.3 us to drain against
+      // 2.2 us of MMAs in a K loop of 8 steps.  Here the flags are compile-time, a warp owns 64-column PAIRS of
+      // chunks (two TMEM loads in flight, one 32 x 64 staging tile, one TMA store of full 128-byte rows per pair)
+      // and the residual / mask ring keeps its 32-column slots and its order (pair q, half h -> chunk 2q + h).
+      constexpr int EG = EPI_GROUPS;
+      constexpr int PPW = BN / (64 * EG);          // pairs per warp per tile
+      constexpr int CPT = 2 * PPW;                 // ring chunks per warp per tile
+      const int R = p.res_slots;
+      const int Nn = p.N;
+      const int m_lim = p.tiles_m * BM;
+      auto drain = [&](auto BIAS_, auto RES_, auto MASK_, auto RELU_) {
+        constexpr bool BIAS = decltype(BIAS_)::value, RES = decltype(RES_)::value, MASK = decltype(MASK_)::value;
+        constexpr int RELU = decltype(RELU_)::value;
+        constexpr bool RING = RES || MASK;
+        constexpr uint32_t SLOT = 2048u * ((RES ? 1u : 0u) + (MASK ? 1u : 0u));
+        const float bscale = p.bias_scale;
+        const float mhi = p.mask_hi;
+        const float* const bias = p.bias;
+        const uint32_t ring = ebase + 4096u;
+        const uint32_t rbar0 = res_bar(ew, 0);
+        const uint32_t swz = ((uint32_t)(lane >> 1) & 3u);
+        const uint32_t srow = ebase + (uint32_t)lane * 128u;
+        const uint32_t sx = (uint32_t)lane & 7u;
+        int iq_tile = t_begin, iq_c = 0, iq_m0 = 0, iq_n0 = 0;
+        auto issue_next = [&]() {
+          if (!RING) return;
+          if (iq_tile < t_end) {
+            if (iq_c == 0) {
+              int sp, mt, nt;
+              tile_coords(iq_tile, sp, mt, nt);
+              iq_m0 = mt * BM + quad * 32;       // a padding tile starts past the last row: nothing to fetch
+              iq_n0 = nt * BN + egrp * 64;
+            }
+            const int n0 = iq_n0 + (iq_c >> 1) * (64 * EG) + (iq_c & 1) * 32;
+            if (n0 < Nn && iq_m0 < m_lim && lane == 0) {
+              const uint32_t rb = rbar0 + 8u * (uint32_t)iq_slot;
+              const uint32_t dst = ring + (uint32_t)iq_slot * SLOT;
+              mbar_arrive_expect_tx(rb, SLOT);
+              if (RES) tma_load_2d(dst, tmR_p, rb, n0, iq_m0);
+              if (MASK) tma_load_2d(dst + (RES ? 2048u : 0u), tmM_p, rb, n0, iq_m0);
+            }
+          }
+          if (++iq_c == CPT) { iq_c = 0; iq_tile += t_step; }
+          if (++iq_slot == R) iq_slot = 0;
+        };
+        if (RING)
+          for (int i = 0; i < R; ++i) issue_next();
+        for (int tile = t_begin; tile < t_end; tile += t_step, ++tcount) {
+          int split, m_tile, n_tile;
+          tile_coords(tile, split, m_tile, n_tile);
+          const uint32_t acc = tcount & 1u, aph = (tcount >> 1) & 1u;
+          mbar_wait(tfull_bar(acc), aph);
+          tcgen05_fence_after();
+          if (CL == 2 && m_tile >= p.tiles_m) {
+            tcgen05_fence_before();
+            mbar_arrive(tempty_bar(acc));
+            for (int i = 0; i < CPT; ++i) {
+              if (RING && ++cq_slot == R) cq_slot = 0;
+              issue_next();
+            }
+            continue;
+          }
+          const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN + egrp * 64;
+          const int m0w = m_tile * BM + quad * 32;
+          const int ncol0 = n_tile * BN + egrp * 64;
+          uint32_t va[32], vb[32];
+          tmem_ld32(taddr, va);
+          tmem_ld32(taddr + 32, vb);
+#pragma unroll 1
+          for (int i = 0; i < PPW; ++i) {
+            const int n0 = ncol0 + i * (64 * EG);
+            tmem_ld_wait();
+            if (i == PPW - 1) {
+              // both halves of the last pair are in registers: the MMA warp may reuse the accumulator
+              tcgen05_fence_before();
+              mbar_arrive(tempty_bar(acc));
+            }
+            if (n0 >= Nn) {        // tile columns past the matrix (N is a multiple of 64: whole pairs)
+              for (int h = 0; h < 2; ++h) {
+                if (RING && ++cq_slot == R) cq_slot = 0;
+                issue_next();
+              }
+              if (i + 1 < PPW) { tmem_ld32(taddr + (i + 1) * (64 * EG), va); tmem_ld32(taddr + (i + 1) * (64 * EG) + 32, vb); }
+              continue;
+            }
+            uint32_t o[32];        // the pair's 64 outputs, packed bf16
+            auto half = [&](uint32_t (&v)[32], auto H_) {
+              constexpr int h = decltype(H_)::value;
+              float f[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+              if (BIAS) {
+                const float4* bq = reinterpret_cast<const float4*>(bias + n0 + h * 32);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const float4 b = __ldg(bq + j);
+                  f[4 * j] += b.x * bscale; f[4 * j + 1] += b.y * bscale;
+                  f[4 * j + 2] += b.z * bscale; f[4 * j + 3] += b.w * bscale;
+                }
+              }
+              uint32_t rrow = 0;
+              if (RING) {
+                const int slot = cq_slot;
+                if (++cq_slot == R) cq_slot = 0;
+                mbar_wait(rbar0 + 8u * (uint32_t)slot, (slot_ph >> slot) & 1u);
+                slot_ph ^= 1u << slot;
+                rrow = ring + (uint32_t)slot * SLOT + (uint32_t)lane * 64u;
+              }
+              if (RES) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const uint4 t = lds128(rrow + ((j ^ swz) << 4));
+                  const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+                  for (int q = 0; q < 4; ++q) {
+                    f[8 * j + 2 * q] += __uint_as_float(w[q] << 16);
+                    f[8 * j + 2 * q + 1] += __uint_as_float(w[q] & 0xffff0000u);
+                  }
+                }
+              }
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                __nv_bfloat162 hh = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+                if (RELU) hh = __hmax2(hh, __float2bfloat162_rn(0.0f));
+                if (RELU == 2) hh = __hmin2(hh, __float2bfloat162_rn(6.0f));
+                o[16 * h + j] = *reinterpret_cast<const uint32_t*>(&hh);
+              }
+              if (MASK) {
+                const uint32_t mrow = rrow + (RES ? 2048u : 0u);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const uint4 t = lds128(mrow + ((j ^ swz) << 4));
+                  const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+                  for (int q = 0; q < 4; ++q) {
+                    uint32_t keep = 0xffffffffu;
+                    if (mask_dead(__uint_as_float(w[q] << 16), mhi)) keep &= 0xffff0000u;
+                    if (mask_dead(__uint_as_float(w[q] & 0xffff0000u), mhi)) keep &= 0x0000ffffu;
+                    o[16 * h + 4 * j + q] &= keep;
+                  }
+                }
+              }
+              if (RING) {
+                __syncwarp();        // every lane has read the slot: refill it with the chunk `R` ahead
+                issue_next();
+              }
+            };
+            half(va, std::integral_constant<int, 0>{});
+            if (i + 1 < PPW) tmem_ld32(taddr + (i + 1) * (64 * EG), va);
+            half(vb, std::integral_constant<int, 1>{});
+            if (i + 1 < PPW) tmem_ld32(taddr + (i + 1) * (64 * EG) + 32, vb);
+            if (lane == 0) bulk_wait_read<0>();     // the previous pair's store has read the staging tile
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              sts128(srow + (((uint32_t)j ^ sx) << 4), make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]));
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(tmO_p, ebase, n0, m0w);
+              bulk_commit();
+            }
+          }
+        }
+        if (lane == 0) bulk_wait_read<0>();       // the next problem (or the generic drain) may reuse the staging tile
+        __syncwarp();
+      };
+      using T_ = std::true_type; using F_ = std::false_type;
+      using I0 = std::integral_constant<int, 0>; using I1 = std::integral_constant<int, 1>; using I2 = std::integral_constant<int, 2>;
+      const bool hr = p.res != nullptr, hm = p.mask != nullptr;
+      if (MODE == FPROP) {          // host guarantees: bias, no mask
+        if (hr) { if (p.relu == 0) drain(T_{}, T_{}, F_{}, I0{}); else if (p.relu == 1) drain(T_{}, T_{}, F_{}, I1{}); else drain(T_{}, T_{}, F_{}, I2{}); }
+        else    { if (p.relu == 0) drain(T_{}, F_{}, F_{}, I0{}); else if (p.relu == 1) drain(T_{}, F_{}, F_{}, I1{}); else drain(T_{}, F_{}, F_{}, I2{}); }
+      } else {                      // DGRAD: no bias, no activation
+        if (hr) { if (hm) drain(F_{}, T_{}, T_{}, I0{}); else drain(F_{}, T_{}, F_{}, I0{}); }
+        else    { if (hm) drain(F_{}, F_{}, T_{}, I0{}); else drain(F_{}, F_{}, F_{}, I0{}); }
+      }
+      continue;
+    }
     const int R = (MODE != WGRAD && p.epi_tma) ? p.res_slots : 0;
     const bool has_res = p.res != nullptr;
     const bool has_mask = p.mask != nullptr;
@@ -1580,6 +1764,13 @@ static int plan_conv(const mtl_conv_args* a, mtl_conv_plan* out) {
   p.epi_tma = 0;
   int nmaps = 0;
   if (a->mode != WGRAD && epi_ok) {
+    // streamlined drain (see the kernel): whole 64-column pairs, no split-K, the flag combinations of the conv layers
+    static const bool no_fast = getenv("MTL_NO_FAST_EPI") != nullptr;
+    p.epi_fast = !no_fast && bn >= 128 && p.splits == 1 && (p.N % 64) == 0 &&
+                 (a->mode == FPROP ? (a->bias != nullptr && a->mask == nullptr)
+                                   : (a->bias == nullptr && a->relu == 0));
+    if (p.epi_fast) { if ((rc = make_map(&t.o, a->out, p.M, p.N, p.ldo, 32, 64, CU_TENSOR_MAP_SWIZZLE_128B))) return rc; }
+    else
     if ((rc = make_map(&t.o, a->out, p.M, p.N, p.ldo, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
     if (a->res && (rc = make_map(&t.r, a->res, p.M, p.N, p.ldr, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
     if (a->mask && (rc = make_map(&t.m, a->mask, p.M, p.N, p.ldm, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
