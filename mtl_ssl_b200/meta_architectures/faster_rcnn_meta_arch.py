@@ -748,11 +748,46 @@ class FasterRCNNMetaArch(model.DetectionModel):
                 if not self.defer_head_wgrads:
                     self.flush_head_wgrads()
 
-    def flush_head_wgrads(self, max_ctas=0):
-        """Run the second-stage weight-gradient GEMMs collected by the last backward(part="heads*")."""
+    def flush_head_wgrads(self, max_ctas=0, piece=None, pieces=1):
+        """Run the second-stage weight-gradient GEMMs collected by the last backward(part="heads*"); piece k of
+        `pieces`: only those writing into head_exchange_pieces(pieces)[k] (the last piece also runs any leftovers)."""
         col = self._head_wgrads.get(id(self._ws))
-        if col is not None:
+        if col is None:
+            return
+        if piece is None or pieces <= 1:
             col.flush(max_ctas=max_ctas)
+            return
+        g = self.head_exchange_pieces(pieces)[piece][0]
+        lo = g.data_ptr()
+        col.flush(max_ctas=max_ctas, key=("piece", piece, pieces), out_range=(lo, lo + g.numel() * g.element_size()))
+        if piece == pieces - 1:
+            col.flush(max_ctas=max_ctas, key=("piece", "rest", pieces))
+
+    def head_exchange_pieces(self, pieces):
+        """The second-stage gradient bucket cut at tensor boundaries into `pieces` contiguous parts of about equal
+        size, arena order: [(gradient view, (first tensor index, end tensor index))].  With several replicas each part
+        is exchanged as soon as its weight-gradient GEMMs are done, while the next part's still run."""
+        cached = getattr(self, "_head_pieces", None)
+        if cached is not None and cached[0] == pieces:
+            return cached[1]
+        st = self._store
+        t0, t1 = self.head_tensor_range()
+        ps = st.params
+        first = ps[t0].offset
+        end = ps[t1].offset if t1 < len(ps) else st.total
+        cuts, out = [t0], []
+        for k in range(1, pieces):
+            want = first + (end - first) * k // pieces
+            t = min(range(cuts[-1] + 1, t1), key=lambda i: abs(ps[i].offset - want), default=None)
+            if t is not None and t > cuts[-1]:
+                cuts.append(t)
+        cuts.append(t1)
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            lo = ps[a].offset
+            hi = ps[b].offset if b < len(ps) else st.total
+            out.append((st.g[lo:min(hi, end)], (a, b)))
+        self._head_pieces = (pieces, out)
+        return out
 
     def _backward_heads(self, pd, part, ws, fe, mtl, feat, B, Hf, Wf, C, P, stop_aux, dfeat, L):
         # refiner FC (inputs are behind stop_gradient: weights / bias only)

@@ -183,10 +183,16 @@ class WgradCollector(object):
     def add(self, a):
         self.pending.append(a)
 
-    def flush(self, max_ctas=0, key=0):
+    def flush(self, max_ctas=0, key=0, out_range=None):
         """Run everything collected since the last flush.  `key` names the flush point: a pass that flushes several
-        times (chunks of a backward chain) plans one set of groups per point."""
-        args, self.pending = self.pending, []
+        times (chunks of a backward chain) plans one set of groups per point.  out_range=(lo, hi): only the GEMMs whose
+        output (device address) lies in [lo, hi) -- a piece of the gradient arena -- run now, the others stay pending."""
+        if out_range is None:
+            args, self.pending = self.pending, []
+        else:
+            lo, hi = out_range
+            args = [a for a in self.pending if lo <= a.out < hi]
+            self.pending = [a for a in self.pending if not lo <= a.out < hi]
         if not args:
             return
         if self.groups is None:

@@ -157,7 +157,16 @@ class Trainer(object):
         # forward pass + proposal chain (a latency-bound stretch that leaves most SMs idle at batch 1).
         import os
         self.defer_heads = os.environ.get("MTL_NO_DEFER_HEADS") is None
-        self._deferred_ctas = int(os.environ.get("MTL_DEFERRED_CTAS", "48" if world_size == 1 else "72"))
+        self._deferred_ctas = int(os.environ.get("MTL_DEFERRED_CTAS", "48"))
+        # several replicas: the deferred weight gradients run after the trunk update as with one replica (measured on
+        # 2 B200s, same box: 7.52-7.60 ms/step against 7.61-7.67 with them right after the second-stage backward,
+        # MTL_HW_EARLY=1, which also needs 72 CTAs to finish in time)
+        self._hw_late = os.environ.get("MTL_HW_EARLY") is None
+        # several replicas, late placement: the head bucket is exchanged in this many pieces, each as soon as its
+        # weight-gradient GEMMs are done (the next piece's GEMMs hide the exchange)
+        self._head_pieces = max(1, int(os.environ.get("MTL_HEAD_PIECES", "3"))) if world_size > 1 else 1
+        self.graph_hw_pieces = None
+        self._no_split = os.environ.get("MTL_NO_SPLIT_TRUNK") is not None
         self._heads_pending = False     # a head update is waiting for the next step (or finish())
         self._head_stats_valid = False  # the head tensors' squared norms (regularisation loss) match the current weights
         model.param_store.post_load_hooks.append(self._weights_replaced)
@@ -297,7 +306,8 @@ class Trainer(object):
     def _split_trunk(self):
         """Several replicas and a trunk whose backward pass can be cut in two (the ResNets): its gradient bucket is
         exchanged in two pieces, the first while the second half still computes."""
-        return self.world_size > 1 and bool(getattr(self.model._feature_extractor, "deferred_wgrad_safe", False))
+        return (self.world_size > 1 and not self._no_split and
+                bool(getattr(self.model._feature_extractor, "deferred_wgrad_safe", False)))
 
     def _stage_t(self):
         """RPN + trunk backward.  Split mode: the RPN and the later trunk units only (_stage_t2 does the rest)."""
@@ -306,10 +316,13 @@ class Trainer(object):
     def _stage_t2(self):
         self.model.backward(None, part="trunk_lo")
 
-    def _stage_c(self):
+    def _stage_c(self, piece=None):
         """The collected second-stage weight gradients, as grouped launches sized to leave the latency-bound trunk
-        chains beside them their SMs."""
-        self.model.flush_head_wgrads(max_ctas=self._deferred_ctas)
+        chains beside them their SMs (piece k: those of the k-th piece of the head bucket only)."""
+        self.model.flush_head_wgrads(max_ctas=self._deferred_ctas, piece=piece, pieces=self._head_pieces)
+
+    def _piecewise_heads(self):
+        return self.world_size > 1 and self._hw_late and self._head_pieces > 1
 
     def _optimize_heads_deferred(self):
         st = self.model.param_store
@@ -359,7 +372,7 @@ class Trainer(object):
             cur.wait_stream(side)               # every second-stage weight is final from here on
             self._heads_pending = False
         self.graph_fb.replay() if graph else self._stage_b()
-        early = self.world_size > 1
+        early = self.world_size > 1 and not self._hw_late
         if early:
             # several replicas: the side stream also has the head bucket's exchange to fit in before the next step's
             # second stage, so the weight gradients start now, underneath the trunk backward
@@ -382,13 +395,21 @@ class Trainer(object):
         # issue order, and the trunk's are the ones the main stream waits for)
         side.wait_stream(cur)
         with torch.cuda.stream(side):
-            if not early:
+            if self._piecewise_heads():
+                works = []
+                for k, (g, _) in enumerate(self.model.head_exchange_pieces(self._head_pieces)):
+                    self.graph_hw_pieces[k].replay() if graph else self._stage_c(k)
+                    works.append(allreduce_gradients(g, self.world_size, self.pg, async_op=True))
+                for w in works:
+                    w.wait()
+            elif not early:
                 # one replica: measured best with all of it underneath the next step's trunk forward + proposal chain
                 # (same box, B200: 7.30 ms/step against 7.58 with the weight gradients under the trunk backward and
                 # 7.66-7.69 with the round-1 schedule)
                 self.graph_hw.replay() if graph else self._stage_c()
-            if self.world_size > 1:
+            if self.world_size > 1 and not self._piecewise_heads():
                 allreduce_gradients(self.model.gradient_buckets()[0], self.world_size, self.pg)
+            if self.world_size > 1:
                 average_losses(self._loss_dev[:8], self.world_size, self.pg)      # logged values only: off the main stream
             self.graph_opt_heads.replay() if graph else self._optimize_heads_deferred()
         self._heads_pending = True
@@ -645,7 +666,11 @@ class Trainer(object):
             if deferred:
                 self._stage_a(image)
                 self._stage_b()
-                self._stage_c()             # (plans the grouped launches: not allowed while capturing)
+                if self._piecewise_heads():     # (plans the grouped launches: not allowed while capturing)
+                    for k in range(len(self.model.head_exchange_pieces(self._head_pieces))):
+                        self._stage_c(k)
+                else:
+                    self._stage_c()
                 self._stage_t()
                 if self._split_trunk():
                     self._stage_t2()
@@ -670,9 +695,17 @@ class Trainer(object):
             self.graph_fb = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph_fb):
                 self._stage_b()
-            self.graph_hw = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph_hw):
-                self._stage_c()
+            if self._piecewise_heads():
+                self.graph_hw_pieces = []
+                for k in range(len(self.model.head_exchange_pieces(self._head_pieces))):
+                    gk = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(gk):
+                        self._stage_c(k)
+                    self.graph_hw_pieces.append(gk)
+            else:
+                self.graph_hw = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph_hw):
+                    self._stage_c()
             self.graph_ft = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph_ft):
                 self._stage_t()
