@@ -63,6 +63,11 @@ typedef struct mtl_conv_args {
   long long ws_bytes;
   int force_cluster;        /* 0 auto, 1 never, 2 always: CTA pairs sharing multicast weight tiles (fprop/dgrad) */
   int max_ctas;             /* 0 = whole GPU; else size the persistent grid for this many SMs (overlapped side work) */
+  float* pool_out;          /* fprop with residual + ReLU, forward-only tails (core/box_predictor.py:470-476 reduce_mean over
+                             * the ROI grid follows): y is NOT stored; instead pool_out[(2g + s) * K + k] = sum of y[row, k]
+                             * (bf16-rounded) over the rows of 32-row group g that lie in its first (s = 0) / second (s = 1)
+                             * window of pool_hw consecutive rows; [2 * ceil(N*P*Q / 32), K] fp32; NULL = store y */
+  int pool_hw;              /* rows per pooling window (P*Q of one ROI), >= 32 */
 } mtl_conv_args;
 int mtl_conv_tc(const mtl_conv_args* args /* host */, mtl_stream_t stream);
 /* bytes of zeroed workspace mtl_conv_tc would use to split the K loop of this fprop/dgrad (0 = no split) */
@@ -184,6 +189,10 @@ int mtl_avgpool_bwd(const void* dy, int dy_fp32, long long ldy, const void* relu
 int mtl_head_fwd(const void* x /* bf16 [R,HW,C] */, int R, int HW, int C, const void* w /* bf16 [n,C] */,
                  const float* bias /* [n] or NULL */, int n, void* pooled /* bf16 [R,C] out */,
                  float* out /* [R,ldo] */, long long ldo, mtl_stream_t stream);
+/* mtl_head_fwd on the partial row sums mtl_conv_tc wrote with pool_out (the tail's last conv never stores its output) */
+int mtl_head_fwd_pooled(const float* part /* [2*ceil(R*HW/32), C] */, int R, int HW, int C, const void* w /* [n,C] bf16 */,
+                        const float* bias /* [n] or NULL */, int n, void* pooled /* [R,C] bf16 */,
+                        float* out /* [R,ldo] */, long long ldo, mtl_stream_t stream);
 /* Its backward: bf16 copy of the logit gradient (operand of the weight-gradient GEMM), bias gradient (+=), and -- dx not
  * NULL -- the gradient w.r.t. x: (d_out x w) / HW broadcast over the grid, zero where x <= 0 (or >= mask_hi > 0). */
 int mtl_head_bwd(const float* d_out /* [R,ldd] */, long long ldd, int n, const void* w /* bf16 [n,C] */,

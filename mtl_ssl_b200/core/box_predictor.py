@@ -9,7 +9,7 @@ import torch
 
 from .. import ops
 from .. import ops_conv as oc
-from ..nets.layers import Concurrency
+from ..nets.layers import Concurrency, PooledTail
 from .standard_fields import (BOX_ENCODINGS, CLASS_PREDICTIONS, CLASS_PREDICTIONS_WITH_BACKGROUND)
 
 
@@ -156,6 +156,10 @@ class MaskRCNNBoxPredictor(BoxPredictor):
                     ("ClassPredictor", self._num_classes + 1)]
         self._heads[scope] = _FusedHead(store, scope, outs, in_channels, self._hp, self._is_training, fc=True)
 
+    def accepts_pooled_tail(self, scope):
+        """The fused head kernel serves this head (narrow enough): a forward-only tail may skip writing its maps."""
+        return FUSED_HEAD and self._heads[scope].n_pad <= FUSED_HEAD_MAX_OUT
+
     def layout(self, scope):
         head = self._heads[scope]
         if len(head.outs) == 1:
@@ -167,6 +171,12 @@ class MaskRCNNBoxPredictor(BoxPredictor):
         R, H, W, C = image_features.shape
         pooled = ws.get("%s/%s/pooled" % (scope, tag), (R, 1, 1, C))
         out = ws.get("%s/%s/head_out" % (scope, tag), (R, 1, 1, head.n_pad), torch.float32)
+        if isinstance(image_features, PooledTail):
+            # forward-only tail whose last conv already summed the ROI grid (never stored its output)
+            ops.call("mtl_head_fwd_pooled", image_features.part, R, H * W, C, head.w_bf16(), head.bias(), head.n_pad,
+                     pooled, out, head.n_pad)
+            self._saved[(scope, tag)] = None
+            return out.view(R, head.n_pad)
         if FUSED_HEAD and head.n_pad <= FUSED_HEAD_MAX_OUT:
             # spatial average + both FC layers in one kernel per ROI batch (csrc/head.cu)
             ops.call("mtl_head_fwd", image_features, R, H * W, C, head.w_bf16(), head.bias(), head.n_pad, pooled, out,

@@ -71,6 +71,8 @@ struct Params {
   int* ws_cnt;               // FPROP/DGRAD split-K: arrival counter per output tile, zero between launches
   int nprod;                 // TMA producer threads (1..3), K steps round-robin
   int epi_fast;              // FPROP/DGRAD: the streamlined drain (64-column stores, compile-time flags) applies
+  float* pool;               // FPROP (streamlined drain): per 32-row group partial row sums instead of the output tensor
+  int pool_hw;               //   rows per pooling window (>= 32): pool[(2g + s) * N + n], s = first / second window of group g
 };
 
 // One problem of a grouped launch (see mtl_conv_tc_group_*): its tensor maps, parameters and the first CTA-wide tile
@@ -185,6 +187,11 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   uint4 v;
   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
   return v;
 }
 __device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
@@ -614,8 +621,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int R = p.res_slots;
       const int Nn = p.N;
       const int m_lim = p.tiles_m * BM;
-      auto drain = [&](auto BIAS_, auto RES_, auto MASK_, auto RELU_) {
+      auto drain = [&](auto BIAS_, auto RES_, auto MASK_, auto RELU_, auto POOL_) {
         constexpr bool BIAS = decltype(BIAS_)::value, RES = decltype(RES_)::value, MASK = decltype(MASK_)::value;
+        constexpr bool POOL = decltype(POOL_)::value;
         constexpr int RELU = decltype(RELU_)::value;
         constexpr bool RING = RES || MASK;
         constexpr uint32_t SLOT = 2048u * ((RES ? 1u : 0u) + (MASK ? 1u : 0u));
@@ -755,11 +763,38 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (i + 1 < PPW) tmem_ld32(taddr + (i + 1) * (64 * EG), va);
             half(vb, std::integral_constant<int, 1>{});
             if (i + 1 < PPW) tmem_ld32(taddr + (i + 1) * (64 * EG) + 32, vb);
-            if (lane == 0) bulk_wait_read<0>();     // the previous pair's store has read the staging tile
+            if (!POOL && lane == 0) bulk_wait_read<0>();     // the previous pair's store has read the staging tile
             __syncwarp();
 #pragma unroll
             for (int j = 0; j < 8; ++j)
               sts128(srow + (((uint32_t)j ^ sx) << 4), make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]));
+            if (POOL) {
+              // Fused spatial mean (forward-only tails): the 32 x 64 tile is not stored; lane l sums columns 2l, 2l+1
+              // down the rows of the group's first / second pooling window (a window has >= 32 rows: at most two per
+              // group) and writes the two partial sums.  Fixed summation order: deterministic.
+              __syncwarp();
+              const int rows_ok = min(32, p.M - m0w);
+              if (rows_ok > 0) {
+                const int hw = p.pool_hw;
+                const int b = min((m0w / hw + 1) * hw - m0w, rows_ok);
+                const uint32_t unit = (uint32_t)lane >> 2, wsel = ((uint32_t)lane & 3u) * 4u;
+                float s00 = 0.0f, s01 = 0.0f, s10 = 0.0f, s11 = 0.0f;
+                // fully unrolled (all 32 loads in flight; b and rows_ok are warp-uniform: predicated adds, same
+                // ascending order as a loop)
+#pragma unroll
+                for (int r = 0; r < 32; ++r) {
+                  const uint32_t w = lds32(ebase + (uint32_t)r * 128u + ((unit ^ ((uint32_t)r & 7u)) << 4) + wsel);
+                  const float lo = __uint_as_float(w << 16), hi = __uint_as_float(w & 0xffff0000u);
+                  if (r < b) { s00 += lo; s01 += hi; }
+                  else if (r < rows_ok) { s10 += lo; s11 += hi; }
+                }
+                float* dst = p.pool + (long long)(m0w >> 5) * 2 * Nn + n0 + 2 * lane;
+                *reinterpret_cast<float2*>(dst) = make_float2(s00, s01);
+                *reinterpret_cast<float2*>(dst + Nn) = make_float2(s10, s11);
+              }
+              __syncwarp();        // every lane has read the tile: the next pair may overwrite it
+              continue;
+            }
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) {
@@ -774,12 +809,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       using T_ = std::true_type; using F_ = std::false_type;
       using I0 = std::integral_constant<int, 0>; using I1 = std::integral_constant<int, 1>; using I2 = std::integral_constant<int, 2>;
       const bool hr = p.res != nullptr, hm = p.mask != nullptr;
-      if (MODE == FPROP) {          // host guarantees: bias, no mask
-        if (hr) { if (p.relu == 0) drain(T_{}, T_{}, F_{}, I0{}); else if (p.relu == 1) drain(T_{}, T_{}, F_{}, I1{}); else drain(T_{}, T_{}, F_{}, I2{}); }
-        else    { if (p.relu == 0) drain(T_{}, F_{}, F_{}, I0{}); else if (p.relu == 1) drain(T_{}, F_{}, F_{}, I1{}); else drain(T_{}, F_{}, F_{}, I2{}); }
+      if (MODE == FPROP) {          // host guarantees: bias, no mask (pooled output: residual + ReLU, the bottleneck's conv3)
+        if (p.pool) drain(T_{}, T_{}, F_{}, I1{}, T_{});
+        else if (hr) { if (p.relu == 0) drain(T_{}, T_{}, F_{}, I0{}, F_{}); else if (p.relu == 1) drain(T_{}, T_{}, F_{}, I1{}, F_{}); else drain(T_{}, T_{}, F_{}, I2{}, F_{}); }
+        else    { if (p.relu == 0) drain(T_{}, F_{}, F_{}, I0{}, F_{}); else if (p.relu == 1) drain(T_{}, F_{}, F_{}, I1{}, F_{}); else drain(T_{}, F_{}, F_{}, I2{}, F_{}); }
       } else {                      // DGRAD: no bias, no activation
-        if (hr) { if (hm) drain(F_{}, T_{}, T_{}, I0{}); else drain(F_{}, T_{}, F_{}, I0{}); }
-        else    { if (hm) drain(F_{}, F_{}, T_{}, I0{}); else drain(F_{}, F_{}, F_{}, I0{}); }
+        if (hr) { if (hm) drain(F_{}, T_{}, T_{}, I0{}, F_{}); else drain(F_{}, T_{}, F_{}, I0{}, F_{}); }
+        else    { if (hm) drain(F_{}, F_{}, T_{}, I0{}, F_{}); else drain(F_{}, F_{}, F_{}, I0{}, F_{}); }
       }
       continue;
     }
@@ -1627,6 +1663,8 @@ struct mtl_conv_args {
   int force_cluster;        // 0 auto, 1 never pair CTAs, 2 pair CTAs (fprop/dgrad with TMA operands)
   int max_ctas;             // 0 = whole GPU; otherwise the persistent grid (and wgrad's split-K) is sized for this many
                             // SMs: work that overlaps a latency-bound chain on another stream leaves it room
+  float* pool_out;          // fprop (+ residual + ReLU): partial row sums per 32-row group instead of y (see mtlssl.h)
+  int pool_hw;
 };
 
 // Everything mtl_conv_tc decides on the host for one problem: kernel parameters, tensor maps, tile width, operand path.
@@ -1677,6 +1715,7 @@ static int plan_conv(const mtl_conv_args* a, mtl_conv_plan* out) {
     p.ldm = a->mask_ld ? a->mask_ld : a->K;
     epi_ok = epi_tma_ok(a->out, a->out_fp32, p.ldo, a->res, a->res_fp32, p.ldr, a->mask, p.ldm);
     plan_tile(p.M, p.N, p.k_iters, epi_ok && a->ws, a->force_bn, a->force_splits, &bn, &p.splits);
+    if (a->pool_out && !a->force_bn && bn < 128) { bn = 128; p.splits = 1; }      // pooled output: the streamlined drain only
     p.cluster = pick_cluster(p.M, p.N, bn, p.splits, gather, a->force_cluster);
     if (im2col) {
       p.im_low_h = -a->pad_h; p.im_low_w = -a->pad_w;
@@ -1769,6 +1808,14 @@ static int plan_conv(const mtl_conv_args* a, mtl_conv_plan* out) {
     p.epi_fast = !no_fast && bn >= 128 && p.splits == 1 && (p.N % 64) == 0 &&
                  (a->mode == FPROP ? (a->bias != nullptr && a->mask == nullptr)
                                    : (a->bias == nullptr && a->relu == 0));
+    if (a->pool_out) {
+      if (!p.epi_fast || a->mode != FPROP || !a->res || a->relu != 1 || a->pool_hw < 32) {
+        mtl_set_error("gemm_tc: pooled output needs the streamlined drain (bf16, N %% 64 == 0, tile width >= 128), a "
+                      "residual, ReLU and windows of >= 32 rows");
+        return MTL_ERR_UNSUPPORTED;
+      }
+      p.pool = a->pool_out; p.pool_hw = a->pool_hw;
+    }
     if (p.epi_fast) { if ((rc = make_map(&t.o, a->out, p.M, p.N, p.ldo, 32, 64, CU_TENSOR_MAP_SWIZZLE_128B))) return rc; }
     else
     if ((rc = make_map(&t.o, a->out, p.M, p.N, p.ldo, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;

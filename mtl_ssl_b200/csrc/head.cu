@@ -36,10 +36,14 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 }
 
 // x [R,HW,C] bf16, w [n,C] bf16 (rows = outputs), bias [n] fp32 -> pooled [R,C] bf16, out [R,ldo] fp32 (columns 0..n-1)
+// PART: instead of x, the partial row sums of the tail's last conv (mtl_conv_args.pool_out): part[(2g + s) * C + c] =
+// sum over the rows of 32-row group g in its first / second ROI; a ROI (HW >= 32 rows) meets two or three groups,
+// summed here in ascending order.
+template <bool PART>
 __global__ void __launch_bounds__(256)
-head_fwd_kernel(const bf16* __restrict__ x, int R, int HW, int C, const bf16* __restrict__ w,
-                const float* __restrict__ bias, int n, bf16* __restrict__ pooled, float* __restrict__ out,
-                long long ldo) {
+head_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ part, int R, int HW, int C,
+                const bf16* __restrict__ w, const float* __restrict__ bias, int n, bf16* __restrict__ pooled,
+                float* __restrict__ out, long long ldo) {
   extern __shared__ float sp[];                     // [HG][C] pooled features (bf16-rounded values)
   const int nvec = C >> 3;
   const long long r0 = (long long)blockIdx.x * HG;
@@ -51,12 +55,23 @@ head_fwd_kernel(const bf16* __restrict__ x, int R, int HW, int C, const bf16* __
 #pragma unroll
       for (int e = 0; e < 8; ++e) acc[e] = 0.0f;
       if (r0 + g < R) {
+        if (PART) {
+          const long long row0 = (r0 + g) * HW;
+          for (long long gi = row0 >> 5; gi <= (row0 + HW - 1) >> 5; ++gi) {
+            const int slot = ((gi << 5) / HW == r0 + g) ? 0 : 1;      // the group starts inside this ROI or in the previous one
+            const float4* src = reinterpret_cast<const float4*>(part + (2 * gi + slot) * C) + 2 * v;
+            const float4 a = __ldg(src), b = __ldg(src + 1);
+            acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
+            acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
+          }
+        } else {
         const uint4* src = reinterpret_cast<const uint4*>(x + (r0 + g) * HW * C) + v;
         for (int p = 0; p < HW; ++p) {
           float f[8];
           unpack8(__ldg(src + (long long)p * nvec), f);
 #pragma unroll
           for (int e = 0; e < 8; ++e) acc[e] += f[e];
+        }
         }
 #pragma unroll
         for (int e = 0; e < 8; ++e) acc[e] *= inv;
@@ -173,10 +188,24 @@ extern "C" int mtl_head_fwd(const void* x, int R, int HW, int C, const void* w, 
   if (R == 0) return MTL_OK;
   const size_t smem = sizeof(float) * HG * (size_t)C;
   MTL_CHECK_ARG(smem <= 48 * 1024, "mtl_head_fwd: C too large (%d)", C);
-  head_fwd_kernel<<<(unsigned)ceil_div(R, HG), 256, smem, stream>>>(
-      reinterpret_cast<const bf16*>(x), R, HW, C, reinterpret_cast<const bf16*>(w), bias, n,
+  head_fwd_kernel<false><<<(unsigned)ceil_div(R, HG), 256, smem, stream>>>(
+      reinterpret_cast<const bf16*>(x), nullptr, R, HW, C, reinterpret_cast<const bf16*>(w), bias, n,
       reinterpret_cast<bf16*>(pooled), out, ldo);
   MTL_CUDA_LAUNCH_CHECK("head_fwd_kernel");
+  return MTL_OK;
+}
+
+extern "C" int mtl_head_fwd_pooled(const float* part, int R, int HW, int C, const void* w, const float* bias, int n,
+                                   void* pooled, float* out, long long ldo, cudaStream_t stream) {
+  MTL_CHECK_ARG(part && w && pooled && out, "mtl_head_fwd_pooled: null tensor");
+  MTL_CHECK_ARG(C % 8 == 0 && C > 0 && n > 0 && HW >= 32 && ldo >= n, "mtl_head_fwd_pooled: bad geometry (C=%d n=%d HW=%d)",
+                C, n, HW);
+  if (R == 0) return MTL_OK;
+  const size_t smem = sizeof(float) * HG * (size_t)C;
+  MTL_CHECK_ARG(smem <= 48 * 1024, "mtl_head_fwd_pooled: C too large (%d)", C);
+  head_fwd_kernel<true><<<(unsigned)ceil_div(R, HG), 256, smem, stream>>>(
+      nullptr, part, R, HW, C, reinterpret_cast<const bf16*>(w), bias, n, reinterpret_cast<bf16*>(pooled), out, ldo);
+  MTL_CUDA_LAUNCH_CHECK("head_fwd_kernel<pooled>");
   return MTL_OK;
 }
 

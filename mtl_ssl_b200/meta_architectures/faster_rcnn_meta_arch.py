@@ -515,7 +515,14 @@ class FasterRCNNMetaArch(model.DetectionModel):
             if _pre is not None:
                 _pre()
             maps, pre_pool = self._compute_second_stage_input_feature_maps(feat, wb, box_ind, _tag)
-            wfeat = fe.extract_box_classifier_features(maps, self.window_box_predictor_scope, ws, _tag, keep=_keep)
+            if (not _keep and getattr(fe, "supports_pooled_tail", False)
+                    and getattr(self._window_box_predictor, "accepts_pooled_tail", lambda s: False)(
+                        self.window_box_predictor_scope)):
+                # forward-only pass (the refiner's expanded windows): the tail's last conv sums the ROI grid itself
+                wfeat = fe.extract_box_classifier_features(maps, self.window_box_predictor_scope, ws, _tag, keep=False,
+                                                           pool=True)
+            else:
+                wfeat = fe.extract_box_classifier_features(maps, self.window_box_predictor_scope, ws, _tag, keep=_keep)
             wp = self._window_box_predictor.predict_class(wfeat, self.window_box_predictor_scope, ws=ws, tag=_tag,
                                                           activation_fn=None)
             self._lanes.mark(lane + "_fwd")

@@ -97,8 +97,10 @@ class FasterRCNNResnetV1FeatureExtractor(FasterRCNNFeatureExtractor):
         t = self._trunks[scope]
         return t.units[t.split_unit()].scope + "/"
 
-    def extract_box_classifier_features(self, proposal_feature_maps, scope, ws, tag="main", keep=True):
-        return self._tails[scope].fwd(proposal_feature_maps, ws, tag, keep)
+    supports_pooled_tail = True     # forward-only tails can hand the box predictor partial row sums (layers.PooledTail)
+
+    def extract_box_classifier_features(self, proposal_feature_maps, scope, ws, tag="main", keep=True, pool=False):
+        return self._tails[scope].fwd(proposal_feature_maps, ws, tag, keep, pool)
 
     def backward_box_classifier_features(self, scope, grad, ws, tag="main", need_dx=True, dx_extra=None,
                                          pre_unit0=None):

@@ -9,7 +9,7 @@ inference mode (fe:139) and is folded into the conv weights / epilogue bias.
 """
 import torch
 
-from .layers import Conv2d, max_pool, max_pool_bwd, max_pool_out_hw
+from .layers import Conv2d, PooledTail, max_pool, max_pool_bwd, max_pool_out_hw
 from .. import ops
 from .. import ops_conv as oc
 
@@ -42,8 +42,9 @@ class Bottleneck(object):
         P, Q, _, _ = self.conv2.geom(H, W)
         return P, Q
 
-    def fwd(self, x, ws, tag, keep=True, parity=0):
-        """keep=False: forward-only pass, intermediates share scratch buffers across units."""
+    def fwd(self, x, ws, tag, keep=True, parity=0, pool=False):
+        """keep=False: forward-only pass, intermediates share scratch buffers across units.  pool (forward-only): the
+        unit's output is only ever averaged over the ROI grid -- conv3 writes partial row sums instead (PooledTail)."""
         N, H, W, C = x.shape
         P, Q = self.out_hw(H, W)
         key = (self.scope if keep else "scratch") + "/" + tag
@@ -57,6 +58,11 @@ class Bottleneck(object):
         r1 = self.conv1.fwd(x, ws.get(key + "/r1", (N, H, W, db)))
         r2 = self.conv2.fwd(r1, ws.get(key + "/r2", (N, P, Q, db)))
         okey = (self.scope + "/" + tag + "/out") if keep else ("scratch/" + tag + "/out%d" % parity)
+        if pool and P * Q >= 32 and self.depth % 64 == 0:      # (what the kernel's pooled output supports)
+            assert not keep
+            part = ws.get("scratch/%s/pool_part" % tag, (oc.pool_partial_rows(N * P * Q), self.depth), torch.float32)
+            self.conv3.fwd(r2, ws.get(okey, (N, P, Q, self.depth)), res=sc, relu=True, pool_out=part, pool_hw=P * Q)
+            return PooledTail(part, (N, P, Q, self.depth))
         out = self.conv3.fwd(r2, ws.get(okey, (N, P, Q, self.depth)), res=sc, relu=True)
         if keep:
             self.saved = getattr(self, "saved", {})
@@ -217,9 +223,9 @@ class Block4(object):
             cin = 2048
         self.out_channels = 2048
 
-    def fwd(self, x, ws, tag, keep=True):
+    def fwd(self, x, ws, tag, keep=True, pool=False):
         for i, u in enumerate(self.units):
-            x = u.fwd(x, ws, tag, keep, i % 2)
+            x = u.fwd(x, ws, tag, keep, i % 2, pool=pool and not keep and i == len(self.units) - 1)
         return x
 
     def bwd(self, g, ws, tag, need_dx=True, dx_extra=None, pre_unit0=None):

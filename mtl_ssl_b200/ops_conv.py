@@ -76,6 +76,7 @@ class ConvArgs(ctypes.Structure):
         ("mask_ld", ctypes.c_longlong), ("bias_scale", ctypes.c_float),
         ("force_stages", ctypes.c_int), ("ws", ctypes.c_void_p), ("ws_bytes", ctypes.c_longlong),
         ("force_cluster", ctypes.c_int), ("max_ctas", ctypes.c_int),
+        ("pool_out", ctypes.c_void_p), ("pool_hw", ctypes.c_int),
     ]
 
 
@@ -238,8 +239,11 @@ def _geom(a, xshape, wshape, stride, pad, dil, P, Q):
 
 def conv_fprop(x, w, stride=1, pad=(0, 0), dil=1, out_hw=None, bias=None, res=None, relu=False,
                out=None, out_dtype=torch.bfloat16, force_bn=0, bias_scale=1.0, force_splits=0, force_stages=0,
-               force_cluster=0):
-    """y = relu?(conv(x, w) + bias + res).  x [N,H,W,C] bf16, w [K,R,S,C] bf16."""
+               force_cluster=0, pool_out=None, pool_hw=0):
+    """y = relu?(conv(x, w) + bias + res).  x [N,H,W,C] bf16, w [K,R,S,C] bf16.
+    pool_out (fp32 [2 * ceil(N*P*Q / 32), K], with res and relu=1): y is not stored; the kernel writes per 32-row group
+    the partial sums of y over the group's first / second window of `pool_hw` rows (pool_partial_rows; the spatial mean
+    that follows a forward-only tail is finished by mtl_head_fwd_pooled)."""
     N, H, W, C = x.shape
     K, R, S, C2 = w.shape
     assert C == C2 and x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
@@ -264,9 +268,18 @@ def conv_fprop(x, w, stride=1, pad=(0, 0), dil=1, out_hw=None, bias=None, res=No
     a.bias_scale = float(bias_scale)
     a.force_bn, a.force_splits, a.force_stages = force_bn, force_splits, force_stages
     a.force_cluster, a.max_ctas = force_cluster, CTA_CAP
+    if pool_out is not None:
+        assert pool_out.dtype == torch.float32 and pool_out.is_contiguous()
+        assert tuple(pool_out.shape) == (pool_partial_rows(N * P * Q), K), pool_out.shape
+        a.pool_out, a.pool_hw = _dp(pool_out), int(pool_hw)
     _attach_ws(a)
     _launch(a, "mtl_conv_tc(fprop)")
     return out
+
+
+def pool_partial_rows(rows):
+    """Rows of the partial-sum buffer of conv_fprop(pool_out=...): two per 32-row group."""
+    return 2 * ((rows + 31) // 32)
 
 
 def conv_dgrad(dy, w, x_shape, stride=1, pad=(0, 0), dil=1, res=None, mask=None, out=None,

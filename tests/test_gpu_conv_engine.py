@@ -276,3 +276,53 @@ def test_grouped_wgrad_launches_match_individual_problems():
     sig, groups = col.groups[0]
     assert len(groups) >= 3 and sum(g.n for g in groups) == len(probs)
     assert max(g.n for g in groups) >= 5
+
+
+def test_fprop_pooled_output_and_pooled_head():
+    """conv3 of a forward-only tail (1x1, residual, ReLU) with the spatial mean fused (mtl_conv_args.pool_out): the
+    partial row sums equal those of the stored output of the same launch without pooling, and mtl_head_fwd_pooled on them
+    equals mtl_head_fwd on the stored maps (core/box_predictor.py:470-500 reduce_mean + fully connected)."""
+    from mtl_ssl_b200 import ops
+    from mtl_ssl_b200 import ops_conv as oc
+    torch.manual_seed(5)
+    for R, HW_side, C, K in ((37, 7, 512, 2048), (5, 6, 256, 1024), (64, 7, 128, 256)):
+        x = torch.randn(R, HW_side, HW_side, C, device="cuda").bfloat16()
+        w = (torch.randn(K, 1, 1, C, device="cuda") * 0.05).bfloat16()
+        res = torch.randn(R, HW_side, HW_side, K, device="cuda").bfloat16()
+        bias = torch.randn(K, device="cuda")
+        y = torch.empty(R, HW_side, HW_side, K, device="cuda", dtype=torch.bfloat16)
+        oc.conv_fprop(x, w, bias=bias, res=res, relu=True, out=y)
+        hw = HW_side * HW_side
+        rows = R * hw
+        part = torch.full((oc.pool_partial_rows(rows), K), float("nan"), device="cuda")
+        scratch = torch.zeros_like(y)
+        oc.conv_fprop(x, w, bias=bias, res=res, relu=True, out=scratch, pool_out=part, pool_hw=hw,
+                      force_bn=0 if K == 2048 else 128)
+        torch.cuda.synchronize()
+        assert not bool(scratch.any())                     # the maps are not written
+        yf = y.float().reshape(rows, K)
+        want = torch.zeros(oc.pool_partial_rows(rows), K, device="cuda")
+        for g in range((rows + 31) // 32):
+            lo, hi = 32 * g, min(32 * g + 32, rows)
+            b = min((lo // hw + 1) * hw, hi)
+            want[2 * g] = yf[lo:b].sum(0)
+            if b < hi:
+                want[2 * g + 1] = yf[b:hi].sum(0)
+        assert torch.isfinite(part).all()
+        assert torch.allclose(part, want, rtol=1e-5, atol=1e-4), (part - want).abs().max()
+        n = 24
+        hwt = (torch.randn(n, K, device="cuda") * 0.02).bfloat16()
+        hb = torch.randn(n, device="cuda")
+        p0 = torch.empty(R, K, device="cuda", dtype=torch.bfloat16); o0 = torch.empty(R, n, device="cuda")
+        p1 = torch.empty_like(p0); o1 = torch.empty_like(o0)
+        ops.call("mtl_head_fwd", y, R, hw, K, hwt, hb, n, p0, o0, n)
+        ops.call("mtl_head_fwd_pooled", part, R, hw, K, hwt, hb, n, p1, o1, n)
+        torch.cuda.synchronize()
+        assert (p0.float() - p1.float()).abs().max() <= 0.01 * p0.float().abs().max()      # one bf16 ulp at most
+        assert torch.allclose(o0, o1, rtol=2e-3, atol=2e-3), (o0 - o1).abs().max()
+    try:                                  # windows shorter than a row group are refused
+        oc.conv_fprop(x, w, bias=bias, res=res, relu=True, out=scratch, pool_out=part, pool_hw=16)
+        refused = False
+    except Exception:
+        refused = True
+    assert refused

@@ -337,7 +337,8 @@ def test_full_size_step_launches_what_the_committed_profile_shows(monkeypatch):
     assert c["mtl_conv_tc"] == 249 and 1 <= c["mtl_conv_tc_group_launch"] <= 12
     assert 249 < profiled["tc_gemm"] <= 249 + 12          # 258 on the device: 249 + 9 grouped launches (the stubbed
     #                                                        group key of the dry run merges some of them)
-    assert c["mtl_head_fwd"] == 4 and c["mtl_head_bwd"] == 3
+    # (the refiner's forward-only window pass hands its head the partial row sums its last conv wrote: no feature maps)
+    assert c["mtl_head_fwd"] == 3 and c["mtl_head_fwd_pooled"] == 1 and c["mtl_head_bwd"] == 3
     assert c["mtl_nms"] == 1 and c["mtl_crop_and_resize_fwd"] == 3 and c["mtl_expand_windows"] == 1
     other = sum(v for k, v in c.items() if not k.startswith("mtl_conv_tc"))
     assert abs(other - profiled["other"]) <= 16          # a few library copies / casts differ
