@@ -117,6 +117,8 @@ def run_case(name, H, W, seed, with_fp32=True):
 
 
 def _record(res):
+    if not torch.cuda.is_available():       # (dry-run lint of this file on a CPU box: nothing measured, nothing to record)
+        return
     out = os.path.join(ROOT, "gpurun_out")
     os.makedirs(out, exist_ok=True)
     path = os.path.join(out, "full_size_parity.json")
