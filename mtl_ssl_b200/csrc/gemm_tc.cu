@@ -607,7 +607,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t slot_ph = 0;
     for (int gj = 0; gj < ngj; ++gj) {
     TC_PROBLEM_SETUP(gj)
-    if (MODE != WGRAD && BN >= 128 && p.epi_fast) {
+    if (MODE != WGRAD && p.epi_fast) {
       // ---------------- streamlined drain (host: TMA epilogue, no split-K, N a multiple of 64) ----------------
       // The generic drain below spends ~490 warp instructions per 32 x 32 chunk (ncu source view, second-stage
       // conv3: 190 of them useful), mostly run-time flag tests, rematerialised addresses and register moves, and with
@@ -615,9 +615,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // 2.2 us of MMAs in a K loop of 8 steps.  Here the flags are compile-time, a warp owns 64-column PAIRS of
       // chunks (two TMEM loads in flight, one 32 x 64 staging tile, one TMA store of full 128-byte rows per pair)
       // and the residual / mask ring keeps its 32-column slots and its order (pair q, half h -> chunk 2q + h).
+      // 64-wide tiles (the trunk at batch 1): one 32-column chunk per warp, same code with H = 1.
       constexpr int EG = EPI_GROUPS;
-      constexpr int PPW = BN / (64 * EG);          // pairs per warp per tile
-      constexpr int CPT = 2 * PPW;                 // ring chunks per warp per tile
+      constexpr int CW = BN >= 128 ? 64 : 32;      // columns a warp handles per step (a pair of chunks, or one)
+      constexpr int H = CW / 32;                   // 32-column halves per step
+      constexpr int PPW = BN / (CW * EG);          // steps per warp per tile
+      constexpr int CPT = H * PPW;                 // ring chunks per warp per tile
       const int R = p.res_slots;
       const int Nn = p.N;
       const int m_lim = p.tiles_m * BM;
@@ -643,9 +646,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               int sp, mt, nt;
               tile_coords(iq_tile, sp, mt, nt);
               iq_m0 = mt * BM + quad * 32;       // a padding tile starts past the last row: nothing to fetch
-              iq_n0 = nt * BN + egrp * 64;
+              iq_n0 = nt * BN + egrp * CW;
             }
-            const int n0 = iq_n0 + (iq_c >> 1) * (64 * EG) + (iq_c & 1) * 32;
+            const int n0 = iq_n0 + (iq_c / H) * (CW * EG) + (iq_c % H) * 32;
             if (n0 < Nn && iq_m0 < m_lim && lane == 0) {
               const uint32_t rb = rbar0 + 8u * (uint32_t)iq_slot;
               const uint32_t dst = ring + (uint32_t)iq_slot * SLOT;
@@ -674,15 +677,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             continue;
           }
-          const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN + egrp * 64;
+          const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN + egrp * CW;
           const int m0w = m_tile * BM + quad * 32;
-          const int ncol0 = n_tile * BN + egrp * 64;
+          const int ncol0 = n_tile * BN + egrp * CW;
           uint32_t va[32], vb[32];
           tmem_ld32(taddr, va);
-          tmem_ld32(taddr + 32, vb);
+          if (H == 2) tmem_ld32(taddr + 32, vb);
 #pragma unroll 1
           for (int i = 0; i < PPW; ++i) {
-            const int n0 = ncol0 + i * (64 * EG);
+            const int n0 = ncol0 + i * (CW * EG);
             tmem_ld_wait();
             if (i == PPW - 1) {
               // both halves of the last pair are in registers: the MMA warp may reuse the accumulator
@@ -690,14 +693,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               mbar_arrive(tempty_bar(acc));
             }
             if (n0 >= Nn) {        // tile columns past the matrix (N is a multiple of 64: whole pairs)
-              for (int h = 0; h < 2; ++h) {
+              for (int h = 0; h < H; ++h) {
                 if (RING && ++cq_slot == R) cq_slot = 0;
                 issue_next();
               }
-              if (i + 1 < PPW) { tmem_ld32(taddr + (i + 1) * (64 * EG), va); tmem_ld32(taddr + (i + 1) * (64 * EG) + 32, vb); }
+              if (i + 1 < PPW) {
+                tmem_ld32(taddr + (i + 1) * (CW * EG), va);
+                if (H == 2) tmem_ld32(taddr + (i + 1) * (CW * EG) + 32, vb);
+              }
               continue;
             }
-            uint32_t o[32];        // the pair's 64 outputs, packed bf16
+            uint32_t o[16 * H];    // the step's 64 (32) outputs, packed bf16
             auto half = [&](uint32_t (&v)[32], auto H_) {
               constexpr int h = decltype(H_)::value;
               float f[32];
@@ -760,15 +766,24 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               }
             };
             half(va, std::integral_constant<int, 0>{});
-            if (i + 1 < PPW) tmem_ld32(taddr + (i + 1) * (64 * EG), va);
-            half(vb, std::integral_constant<int, 1>{});
-            if (i + 1 < PPW) tmem_ld32(taddr + (i + 1) * (64 * EG) + 32, vb);
+            if (i + 1 < PPW) tmem_ld32(taddr + (i + 1) * (CW * EG), va);
+            if (H == 2) {
+              half(vb, std::integral_constant<int, H - 1>{});
+              if (i + 1 < PPW) tmem_ld32(taddr + (i + 1) * (CW * EG) + 32, vb);
+            }
             if (!POOL && lane == 0) bulk_wait_read<0>();     // the previous pair's store has read the staging tile
             __syncwarp();
+            if (H == 2) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-              sts128(srow + (((uint32_t)j ^ sx) << 4), make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]));
-            if (POOL) {
+              for (int j = 0; j < 8; ++j)
+                sts128(srow + (((uint32_t)j ^ sx) << 4), make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]));
+            } else {       // 32 columns: 64-byte rows, 64 B swizzle (the generic drain's staging layout)
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                sts128(ebase + (uint32_t)lane * 64u + (((uint32_t)j ^ swz) << 4),
+                       make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]));
+            }
+            if (POOL && H == 2) {
               // Fused spatial mean (forward-only tails): the 32 x 64 tile is not stored; lane l sums columns 2l, 2l+1
               // down the rows of the group's first / second pooling window (a window has >= 32 rows: at most two per
               // group) and writes the two partial sums.  Fixed summation order: deterministic.
@@ -1805,18 +1820,18 @@ static int plan_conv(const mtl_conv_args* a, mtl_conv_plan* out) {
   if (a->mode != WGRAD && epi_ok) {
     // streamlined drain (see the kernel): whole 64-column pairs, no split-K, the flag combinations of the conv layers
     static const bool no_fast = getenv("MTL_NO_FAST_EPI") != nullptr;
-    p.epi_fast = !no_fast && bn >= 128 && p.splits == 1 && (p.N % 64) == 0 &&
+    p.epi_fast = !no_fast && p.splits == 1 && (p.N % 64) == 0 &&
                  (a->mode == FPROP ? (a->bias != nullptr && a->mask == nullptr)
                                    : (a->bias == nullptr && a->relu == 0));
     if (a->pool_out) {
-      if (!p.epi_fast || a->mode != FPROP || !a->res || a->relu != 1 || a->pool_hw < 32) {
+      if (!p.epi_fast || bn < 128 || a->mode != FPROP || !a->res || a->relu != 1 || a->pool_hw < 32) {
         mtl_set_error("gemm_tc: pooled output needs the streamlined drain (bf16, N %% 64 == 0, tile width >= 128), a "
                       "residual, ReLU and windows of >= 32 rows");
         return MTL_ERR_UNSUPPORTED;
       }
       p.pool = a->pool_out; p.pool_hw = a->pool_hw;
     }
-    if (p.epi_fast) { if ((rc = make_map(&t.o, a->out, p.M, p.N, p.ldo, 32, 64, CU_TENSOR_MAP_SWIZZLE_128B))) return rc; }
+    if (p.epi_fast && bn >= 128) { if ((rc = make_map(&t.o, a->out, p.M, p.N, p.ldo, 32, 64, CU_TENSOR_MAP_SWIZZLE_128B))) return rc; }
     else
     if ((rc = make_map(&t.o, a->out, p.M, p.N, p.ldo, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
     if (a->res && (rc = make_map(&t.r, a->res, p.M, p.N, p.ldr, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
