@@ -281,10 +281,11 @@ __global__ void make_keys_kernel(const float4* __restrict__ boxes, const float* 
 // spread over the whole GPU: 14 k keys -> 0.2 G compares, far cheaper than a multi-pass sort's launches.
 constexpr int RS_THREADS = 256;
 constexpr int RS_TILE = 2048;
-constexpr int RS_SPLIT = 4;       // the comparison range is cut in RS_SPLIT slices (grid z) to fill all SMs
+constexpr int RS_SPLIT = 16;      // the comparison range is cut in RS_SPLIT slices (grid z): 14 k keys -> 880 blocks, six
+                                  // per SM, so the dependent load-compare-add chains of 48 warps hide each other's latency
 __global__ void __launch_bounds__(RS_THREADS)
 rank_count_kernel(const u64* __restrict__ keys, int N, int* __restrict__ rank) {
-  __shared__ u64 tile[RS_TILE];
+  __shared__ __align__(16) u64 tile[RS_TILE];
   const int b = blockIdx.y;
   const u64* k = keys + (long long)b * N;
   const int i = blockIdx.x * RS_THREADS + threadIdx.x;
@@ -298,10 +299,16 @@ rank_count_kernel(const u64* __restrict__ keys, int N, int* __restrict__ rank) {
     for (int t = threadIdx.x; t < n; t += RS_THREADS) tile[t] = k[t0 + t];
     __syncthreads();
     if (mine != 0ull) {
-      int t = 0;
-      for (; t + 4 <= n; t += 4) {
-        r += (tile[t] > mine) + (tile[t + 1] > mine) + (tile[t + 2] > mine) + (tile[t + 3] > mine);
+      int t = 0, r1 = 0;
+      for (; t + 8 <= n; t += 8) {        // two independent accumulators, 16-byte broadcast loads
+        const ulonglong2 a = *reinterpret_cast<const ulonglong2*>(tile + t);
+        const ulonglong2 c = *reinterpret_cast<const ulonglong2*>(tile + t + 2);
+        const ulonglong2 d = *reinterpret_cast<const ulonglong2*>(tile + t + 4);
+        const ulonglong2 e = *reinterpret_cast<const ulonglong2*>(tile + t + 6);
+        r += (a.x > mine) + (a.y > mine) + (c.x > mine) + (c.y > mine);
+        r1 += (d.x > mine) + (d.y > mine) + (e.x > mine) + (e.y > mine);
       }
+      r += r1;
       for (; t < n; ++t) r += (tile[t] > mine);
     }
   }
@@ -325,8 +332,14 @@ __device__ __forceinline__ bool nms_iou_gt(const float4 a, float area_a, const f
   const float iy0 = fmaxf(a.x, b.x), ix0 = fmaxf(a.y, b.y);
   const float iy1 = fminf(a.z, b.z), ix1 = fminf(a.w, b.w);
   const float inter = fmaxf(iy1 - iy0, 0.0f) * fmaxf(ix1 - ix0, 0.0f);
-  const float iou = inter / (area_a + area_b - inter);
-  return iou > thr;
+  const float uni = area_a + area_b - inter;        // >= max(area) > 0 up to rounding
+  // inter / uni > thr, decided without the division unless the quotient lies within 1e-6 (relative) of the threshold:
+  // the IEEE quotient and thr * uni each carry 6e-8 of rounding, so outside that band both tests agree exactly.
+  // (NaNs fail both comparisons and take the division, as before.)
+  const float t = thr * uni;
+  if (inter > t * 1.000001f) return true;
+  if (inter < t * 0.999999f) return false;
+  return inter / uni > thr;
 }
 
 constexpr int NMS_CHUNK = 256;        // candidates per chunk
