@@ -512,14 +512,18 @@ def run_ours(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=None)     # default: 100 (0.7 s timed at c2); CPU reference arm: 20
+    ap.add_argument("--warmup", type=int, default=None)    # default: 5; CPU reference arm: 3
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
     ap.add_argument("--batch-per-gpu", type=int, default=0)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     args = ap.parse_args()
+    if args.steps is None:
+        args.steps = 20 if args.impl == "reference" else 100
+    if args.warmup is None:
+        args.warmup = 3 if args.impl == "reference" else 5
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
