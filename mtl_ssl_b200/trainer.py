@@ -3,15 +3,16 @@
 Replaces the per-clone loss graph + optimizer of /root/reference/object_detection/trainer.py:157-214
 (`_create_losses`), :379-429 (gradient post-processing + apply) and the clone deployment of
 slim/deployment/model_deploy.py:143-307: one process per GPU; every rank runs forward, loss and the
-explicit backward on its shard of the batch, ONE NCCL all-reduce sums the flat gradient arena
-(replacing the CPU `tf.add_n`, model_deploy.py:414-444), then every rank applies the identical
-per-tensor-clip + momentum update.  Loss scaling follows the reference: task losses / num_replicas,
-L2 regularisation once (model_deploy.py:221-225, :296).
+explicit backward on its shard of the batch, NCCL all-reduces sum contiguous buckets of the flat gradient
+arena as the backward pass finishes them (replacing the CPU `tf.add_n`, model_deploy.py:414-444), then
+every rank applies the identical per-tensor-clip + momentum update.  Loss scaling follows the reference:
+task losses / num_replicas, L2 regularisation once (model_deploy.py:221-225, :296).
 
-The step is a fixed list of kernel launches over persistent buffers; after a warm-up it is
-captured into CUDA graphs (forward+backward, optimizer) and replayed, so the ~2000 launches cost
-no Python time.  Inputs arrive through pinned host staging buffers (one H2D per step); the only
-D2H is the 9-float loss vector.
+The step is a fixed list of ~310 kernel launches over persistent buffers; after a warm-up it is captured
+into CUDA graphs, one per stage of `_run_step_deferred` (first stage, second stage + its backward, trunk
+backward, the deferred second-stage weight gradients, the two optimizer passes) and replayed, so the
+launches cost no Python time.  Inputs arrive through pinned host staging buffers (one H2D per step); the
+only D2H is the 9-float loss vector.
 """
 import numpy as np
 import torch
