@@ -290,6 +290,13 @@ int mtl_opt_reg_loss(const mtl_tensor_desc* tensors, int num_tensors, const floa
 int mtl_opt_apply(const mtl_tensor_desc* tensors, const mtl_chunk_desc* chunks, int num_chunks, float* params,
                   float* grads, float* momentum, void* params_bf16, const float* fold_scales, const float* stats,
                   const float* hyper /* [lr, momentum, clip_norm] */, float grad_scale, mtl_stream_t stream);
+/* mtl_opt_apply over the tensors [t0, t1) (`chunks` = first chunk of tensor t0) that also refreshes stats[2t], the squared
+ * norm of the UPDATED weights (fixed summation order through `partials`), so that the next step's regularisation loss needs
+ * no extra pass over them; stats[2t + 1] is left at 0 until the next statistics pass. */
+int mtl_opt_apply_norms(const mtl_tensor_desc* tensors, int t0, int t1, const mtl_chunk_desc* chunks, int num_chunks,
+                        float* params, float* grads, float* momentum, void* params_bf16, const float* fold_scales,
+                        float* stats /* [T,2] */, const float* hyper, float grad_scale, const int* chunk_start /* [T+1] */,
+                        int chunk0 /* index of chunks[0] */, float* partials /* [all chunks,2] */, mtl_stream_t stream);
 int mtl_opt_fold(const mtl_tensor_desc* tensors, const mtl_chunk_desc* chunks, int num_chunks, const float* params,
                  void* params_bf16, const float* fold_scales, mtl_stream_t stream);
 int mtl_cast_f32_bf16(const float* a, long long n, float alpha, void* out, mtl_stream_t stream);

@@ -129,11 +129,22 @@ __global__ void __launch_bounds__(256)
 opt_apply_kernel(const mtl_tensor_desc* __restrict__ td, const mtl_chunk_desc* __restrict__ cd,
                  float* __restrict__ params, float* __restrict__ grads, float* __restrict__ mom,
                  bf16* __restrict__ params_bf16, const float* __restrict__ fold_scales,
-                 const float* __restrict__ stats, const float* __restrict__ hyper, float gscale) {
+                 const float* __restrict__ stats, const float* __restrict__ hyper, float gscale,
+                 float* __restrict__ wsq) {
+  // wsq != null: also leave this chunk's sum of squares of the UPDATED weights in wsq[2 * block] (and 0 in the slot of the
+  // gradient norm): what opt_stats_kernel would compute on the new weights, without a third pass over them
+  __shared__ float red[32];
   const mtl_chunk_desc c = cd[blockIdx.x];
   const mtl_tensor_desc t = td[c.tensor];
-  if (!t.trainable) return;
   const long long base = t.offset + c.start;
+  float sw = 0.0f;
+  if (!t.trainable) {
+    if (!wsq) return;
+    for (int i = threadIdx.x; i < c.len; i += 256) { const float w = params[base + i]; sw += w * w; }
+    const float tw = block_sum256(sw, red);
+    if (threadIdx.x == 0) { wsq[2 * blockIdx.x] = tw; wsq[2 * blockIdx.x + 1] = 0.0f; }
+    return;
+  }
   const float lr = hyper[0], momentum = hyper[1], clip = hyper[2];
   float factor = 1.0f;
   if (clip > 0.0f) {
@@ -161,6 +172,7 @@ opt_apply_kernel(const mtl_tensor_desc* __restrict__ td, const mtl_chunk_desc* _
       *reinterpret_cast<float4*>(mom + o) = make_float4(mv[0], mv[1], mv[2], mv[3]);
       *reinterpret_cast<float4*>(params + o) = make_float4(wv[0], wv[1], wv[2], wv[3]);
       *reinterpret_cast<float4*>(grads + o) = make_float4(0.f, 0.f, 0.f, 0.f);
+      sw += wv[0] * wv[0] + wv[1] * wv[1] + wv[2] * wv[2] + wv[3] * wv[3];
       __nv_bfloat162 lo = __floats2bfloat162_rn(wv[0] * sc, wv[1] * sc);
       __nv_bfloat162 hi = __floats2bfloat162_rn(wv[2] * sc, wv[3] * sc);
       uint2 pk;
@@ -168,8 +180,7 @@ opt_apply_kernel(const mtl_tensor_desc* __restrict__ td, const mtl_chunk_desc* _
       pk.y = *reinterpret_cast<uint32_t*>(&hi);
       *reinterpret_cast<uint2*>(params_bf16 + o) = pk;
     }
-    return;
-  }
+  } else {
   for (int i = threadIdx.x; i < c.len; i += 256) {
     const long long o = base + i;
     const float w = params[o];
@@ -179,9 +190,15 @@ opt_apply_kernel(const mtl_tensor_desc* __restrict__ td, const mtl_chunk_desc* _
     mom[o] = m;
     params[o] = nw;
     grads[o] = 0.0f;                                    // ready for the next step's += wgrad
+    sw += nw * nw;
     float sc = 1.0f;
     if (t.scale_off >= 0) sc = fold_scales[t.scale_off + (c.start + i) / t.row_len];
     params_bf16[o] = __float2bfloat16_rn(nw * sc);
+  }
+  }
+  if (wsq) {
+    const float tw = block_sum256(sw, red);
+    if (threadIdx.x == 0) { wsq[2 * blockIdx.x] = tw; wsq[2 * blockIdx.x + 1] = 0.0f; }
   }
 }
 
@@ -294,8 +311,27 @@ extern "C" int mtl_opt_apply(const mtl_tensor_desc* tensors, const mtl_chunk_des
                 "mtl_opt_apply: null tensor");
   opt_apply_kernel<<<num_chunks, 256, 0, stream>>>(tensors, chunks, params, grads, momentum,
                                                    reinterpret_cast<bf16*>(params_bf16), fold_scales, stats, hyper,
-                                                   grad_scale);
+                                                   grad_scale, nullptr);
   MTL_CUDA_LAUNCH_CHECK("opt_apply_kernel");
+  return MTL_OK;
+}
+
+// mtl_opt_apply over the tensors [t0, t1) that also refreshes their squared weight norms (stats[2t], fixed summation
+// order through `partials`) from the UPDATED weights; stats[2t + 1] (the gradient norm) is left at 0 until the next
+// statistics pass.
+extern "C" int mtl_opt_apply_norms(const mtl_tensor_desc* tensors, int t0, int t1, const mtl_chunk_desc* chunks,
+                                   int num_chunks, float* params, float* grads, float* momentum, void* params_bf16,
+                                   const float* fold_scales, float* stats, const float* hyper, float grad_scale,
+                                   const int* chunk_start, int chunk0, float* partials, cudaStream_t stream) {
+  MTL_CHECK_ARG(tensors && chunks && params && grads && momentum && params_bf16 && stats && hyper && chunk_start &&
+                partials && t0 >= 0 && t1 >= t0, "mtl_opt_apply_norms: bad argument");
+  if (t1 == t0 || num_chunks == 0) return MTL_OK;
+  opt_apply_kernel<<<num_chunks, 256, 0, stream>>>(tensors, chunks, params, grads, momentum,
+                                                   reinterpret_cast<bf16*>(params_bf16), fold_scales, stats, hyper,
+                                                   grad_scale, partials + 2 * (long long)chunk0);
+  MTL_CUDA_LAUNCH_CHECK("opt_apply_kernel");
+  opt_stats_reduce_kernel<<<ceil_div(t1 - t0, 8), 256, 0, stream>>>(chunk_start, t0, t1, 0, partials, stats);
+  MTL_CUDA_LAUNCH_CHECK("opt_stats_reduce_kernel");
   return MTL_OK;
 }
 

@@ -248,11 +248,20 @@ class ParamStore(object):
             ops.call("mtl_opt_stats_range", self.td, t0, t1, cd, n, self.w, self.g, grad_scale, self.stats,
                      self.chunk_start_dev, self.chunk_start[t0], self.partials)
 
-    def apply_range(self, t0, t1, grad_scale=1.0, hyper=None):
+    def apply_range(self, t0, t1, grad_scale=1.0, hyper=None, refresh_norms=False):
+        """refresh_norms: the pass also leaves the squared norms of the UPDATED weights in `stats` (what a following
+        stats_range would compute for the regularisation loss of the next step) -- no third pass over the weights."""
         cd, n = self._chunk_range(t0, t1)
+        if n and refresh_norms and self.partials is not None:
+            ops.call("mtl_opt_apply_norms", self.td, t0, t1, cd, n, self.w, self.g, self.m, self.wb, self.fold_scales,
+                     self.stats, self.hyper if hyper is None else hyper, grad_scale, self.chunk_start_dev,
+                     self.chunk_start[t0], self.partials)
+            return
         if n:
             ops.call("mtl_opt_apply", self.td, cd, n, self.w, self.g, self.m, self.wb, self.fold_scales,
                      self.stats, self.hyper if hyper is None else hyper, grad_scale)
+            if refresh_norms:
+                self.stats_range(t0, t1, grad_scale)
 
     def reg_loss_from_stats(self):
         ops.call("mtl_opt_reg_loss", self.td, self.num_tensors, self.stats, self.reg_loss)

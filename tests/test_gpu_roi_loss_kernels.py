@@ -306,6 +306,39 @@ def test_optimizer_matches_reference_update():
     torch.testing.assert_close(hv.float().cpu(), torch.cat([w_ref[1], w_ref[2]]).to(torch.bfloat16).float())
 
 
+def test_update_pass_leaves_the_new_weight_norms():
+    """apply_range(refresh_norms=True) == apply_range + stats_range: same weights, and the squared norms of the UPDATED
+    weights (frozen tensors: unchanged weights) in the statistics the next step's regularisation loss reads."""
+    from mtl_ssl_b200.runtime import ParamStore
+
+    def make():
+        store = ParamStore()
+        a = store.add("a/weights", (8, 3, 3, 16), l2=1e-2, init=("normal", 1.0))
+        b = store.add("b/weights", (33, 7), l2=1e-3, init=("normal", 1.0))             # scalar path (odd sizes)
+        fz = store.add("frozen/weights", (4, 100), l2=1e-4, trainable=False, init=("normal", 1.0))
+        c = store.add("c/weights", (300, 1, 1, 2048), l2=1e-4, init=("normal", 1.0))    # several chunks
+        store.finalize("cuda", seed=5)
+        store.set_hyper(0.1, 0.9, 10.0)
+        gen = torch.Generator().manual_seed(3)
+        for p in (a, b, fz, c):
+            p.g.copy_(torch.randn(p.shape, generator=gen).cuda())
+        return store, (a, b, fz, c)
+
+    s1, p1 = make()
+    s2, p2 = make()
+    T = s1.num_tensors
+    s1.stats_range(0, T, 0.5); s1.apply_range(0, T, 0.5); s1.stats_range(0, T, 0.5)
+    s2.stats_range(0, T, 0.5); s2.apply_range(0, T, 0.5, refresh_norms=True)
+    torch.cuda.synchronize()
+    for x, y in zip(p1, p2):
+        assert torch.equal(x.w, y.w) and torch.equal(x.m, y.m)
+    n1 = s1.stats.view(-1, 2)[:, 0].cpu(); n2 = s2.stats.view(-1, 2)[:, 0].cpu()
+    torch.testing.assert_close(n2, n1, rtol=1e-6, atol=0)
+    want = torch.stack([(p.w.double() ** 2).sum().float().cpu() for p in p2])
+    torch.testing.assert_close(n2[:len(p2)], want, rtol=1e-5, atol=0)
+    torch.testing.assert_close(s1.reg_loss_from_stats().cpu(), s2.reg_loss_from_stats().cpu(), rtol=1e-6, atol=0)
+
+
 @pytest.mark.parametrize("stride", [1, 2])
 def test_depthwise_conv3x3_fwd_dgrad_wgrad(stride):
     """slim.separable_conv2d depthwise stage (mobilenet_v1.py:230-238) against torch grouped conv."""
