@@ -410,3 +410,40 @@ def test_initializer_parameters_reach_the_variables():
     msg = text_format.Merge("op: FC regularizer { l2_regularizer { weight: 0.1 } }", text_format.Message("Hyperparams"))
     with pytest.raises(ValueError):
         Hyperparams.from_proto(msg)
+
+
+def test_wgrad_collector_flushes_by_output_range(monkeypatch):
+    """ops_conv.WgradCollector.flush(out_range=...): only the deferred GEMMs whose output lies in the given piece of the
+    gradient arena run, the others stay pending, each flush point plans and caches its own groups (the piecewise exchange
+    of the second-stage bucket with several replicas, trainer._run_step_deferred)."""
+    from mtl_ssl_b200 import ops_conv as oc
+    launched = []
+
+    class FakeGroup(object):
+        def __init__(self, args, target):
+            self.outs = [a.out for a in args]
+
+        def launch(self, max_ctas=0):
+            launched.append((tuple(self.outs), max_ctas))
+
+    monkeypatch.setattr(oc, "ConvGroup", FakeGroup)
+    monkeypatch.setattr(oc, "group_key", lambda a: a.C)
+
+    def arg(out, C):
+        a = oc.ConvArgs()
+        a.mode, a.out, a.C, a.N, a.H, a.W, a.K, a.R, a.stride = oc.WGRAD, out, C, 1, 7, 7, 8, 1, 1
+        return a
+
+    col = oc.WgradCollector()
+    for rep in range(2):
+        for out, C in ((1000, 64), (5000, 64), (2000, 128), (9000, 64)):
+            col.add(arg(out, C))
+        del launched[:]
+        col.flush(max_ctas=48, key=("piece", 0), out_range=(0, 4000))
+        assert sorted(o for g, _ in launched for o in g) == [1000, 2000] and len(launched) == 2     # two kernel instances
+        assert all(c == 48 for _, c in launched) and [a.out for a in col.pending] == [5000, 9000]
+        col.flush(max_ctas=48, key=("piece", 1), out_range=(4000, 6000))
+        assert [a.out for a in col.pending] == [9000]
+        col.flush(max_ctas=0, key=("piece", "rest"))
+        assert not col.pending and launched[-1] == ((9000,), 0)
+    assert len(col.groups) == 3                  # planned once per flush point, reused on the second pass
